@@ -1,0 +1,136 @@
+/*
+ * innfer_b200 -- C ABI of the B200-native RRDB/ESRGAN inference path.
+ *
+ * The reference (victorca25/iNNfer) is pure Python and has no FFI; its boundary for this path is
+ * the object protocol between run.py:Model and architectures.get_network.
+ * Every entry point below names the reference interface it replaces (file:line relative to the
+ * reference tree).  The Python shim in innfer_b200/ keeps the reference's classes and calls these
+ * functions through ctypes.
+ *
+ * Conventions: all functions return 0 on success or a negative INNFER_E_* code and never throw;
+ * innfer_last_error() returns a thread-local message for the last failure.  Pointers marked
+ * "device" are CUDA device pointers on the handle's device; "host" pointers are ordinary host
+ * memory.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ * stream ordered and the functions do not synchronise unless stated.  A handle must be used from
+ * one host thread at a time.  There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef INNFER_B200_H_
+#define INNFER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INNFER_OK 0
+#define INNFER_E_INVALID (-1)      /* bad argument / shape */
+#define INNFER_E_UNSUPPORTED (-2)  /* valid for the reference, not built here (fails loudly) */
+#define INNFER_E_CUDA (-3)         /* CUDA runtime / driver error */
+#define INNFER_E_STATE (-4)        /* call order (e.g. forward before finalize, missing weights) */
+#define INNFER_E_NOMEM (-5)
+
+/* element types of tensors crossing the ABI */
+#define INNFER_F16 0
+#define INNFER_F32 1
+#define INNFER_U8 2
+
+typedef struct innfer_rrdb innfer_rrdb; /* opaque network handle */
+
+/* Constructor kwargs of RRDBNet (architectures/RRDBNet_arch.py:17-19) as produced by
+ * get_network_G_config (utils/defaults.py:20-44).  gc is accepted for completeness; like the
+ * reference (RRDBNet_arch.py:26) the blocks are always built with 32 growth channels. */
+typedef struct innfer_rrdb_cfg {
+  int32_t in_nc;
+  int32_t out_nc;
+  int32_t nf;
+  int32_t nb;
+  int32_t gc;
+  int32_t scale; /* upscale: 1, 2, 3, 4, 8 */
+  int32_t plus;  /* ESRGAN+ paths (RRDBNet_arch.py:129,155-160); non-zero -> INNFER_E_UNSUPPORTED */
+  int32_t fp16;  /* 1: fp16 storage + tcgen05 fp16 MMA with fp32 accumulate; 0: fp32 mode */
+} innfer_rrdb_cfg;
+
+typedef struct innfer_tile {
+  int32_t y0, x0; /* low-res origin of the tile */
+} innfer_tile;
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char* innfer_last_error(void);
+const char* innfer_version(void);
+/* number of innfer CUDA kernels launched by this process so far (bench.py "gpu_launches") */
+uint64_t innfer_kernel_launches(void);
+
+/* ---- network handle: replaces architectures.get_network + nn.Module.load_state_dict/.to(device)
+ *      (architectures/__init__.py:5-40, run.py:90-101) ------------------------------------------- */
+int innfer_rrdb_create(const innfer_rrdb_cfg* cfg, int device, innfer_rrdb** out);
+/* one state-dict entry under its REFERENCE key name ("model.0.weight",
+ * "model.1.sub.3.RDB2.conv4.0.bias", "model.1.sub.23.weight", "model.10.bias", ...); host fp32. */
+int innfer_rrdb_load(innfer_rrdb* h, const char* key, const float* host_data, const int64_t* shape,
+                     int ndim);
+/* verifies that every parameter arrived (strict load), repacks OIHW -> kernel layout, uploads. */
+int innfer_rrdb_finalize(innfer_rrdb* h);
+void innfer_rrdb_destroy(innfer_rrdb* h);
+/* upper bound of tiles pushed through the trunk per batch (memory / L2 trade-off), default 32 */
+int innfer_rrdb_set_max_batch(innfer_rrdb* h, int max_tiles);
+
+/* ---- forward: replaces RRDBNet.forward on one batch (RRDBNet_arch.py:50-62) -------------------
+ * x: device NCHW [n][in_nc][h][w], y: device NCHW [n][out_nc][scale*h][scale*w]; dtype INNFER_F16
+ * or INNFER_F32 for both. */
+int innfer_rrdb_forward(innfer_rrdb* h, const void* x, int n, int hgt, int wid, void* y, int dtype,
+                        void* stream);
+
+/* ---- chop_forward: replaces Model.chop_forward = extract_patches_2d -> per-tile forward ->
+ *      recompose_tensor (run.py:167-202, utils/utils.py:318-445) -------------------------------
+ * x: device NCHW [1][in_nc][H][W]; y: device NCHW [1][out_nc][scale*H][scale*W]. */
+int innfer_rrdb_chop_forward(innfer_rrdb* h, const void* x, int H, int W, int patch_size,
+                             float step, void* y, int dtype, void* stream);
+
+/* ---- image in, image out: np2tensor -> chop_forward -> tensor2np fused (run.py:421-431,
+ *      utils/utils.py:164-248).  img: HOST uint8 HWC BGR [H][W][3]; out: HOST uint8 HWC BGR
+ *      [scale*H][scale*W][3].  Copies run on `stream`; the call returns after the result landed
+ *      in `out` (it synchronises the stream). */
+int innfer_rrdb_upscale_u8(innfer_rrdb* h, const uint8_t* img, int H, int W, int patch_size,
+                           float step, uint8_t* out, void* stream);
+/* same with DEVICE uint8 buffers and no synchronisation */
+int innfer_rrdb_upscale_u8_device(innfer_rrdb* h, const uint8_t* img, int H, int W, int patch_size,
+                                  float step, uint8_t* out, void* stream);
+
+/* ---- tiling geometry: replaces the index arithmetic of extract_patches_2d
+ *      (utils/utils.py:349-365).  Writes up to `cap` tiles in row-major order; *n = tile count,
+ *      *tile_size = min(H, W, patch_size). */
+int innfer_tiles_plan(int H, int W, int patch_size, float step, innfer_tile* out, int cap, int* n,
+                      int* tile_size);
+
+/* ---- standalone operators (used by the parity tests, same kernels as the network) ----------- */
+/* image -> tiles: np2tensor + extract_patches_2d.  src device: NCHW fp16/fp32 [1][C][H][W] or
+ * uint8 HWC BGR; dst device planar-chunk tiles [ntiles][ceil(C/16)*2][p][p][8] fp16. */
+int innfer_image_to_tiles(const void* src, int src_dtype, int C, int H, int W, int patch_size,
+                          float step, void* dst_tiles, void* stream);
+/* recompose_tensor (+ tensor2np when dst_dtype is INNFER_U8).  tiles: device planar-chunk
+ * [ntiles][1][P][P][8] fp16 with P = scale*min(H,W,patch_size). */
+int innfer_blend(const void* tiles, int H, int W, int patch_size, float step, int scale, int C,
+                 void* dst, int dst_dtype, void* stream);
+/* one fused conv_block (architectures/block.py:213-254) [+ nearest Upsample in front,
+ * block.py:348-361] [+ LeakyReLU] [+ alpha1*. + res1] on NCHW device tensors; weights host fp32
+ * OIHW.  Builds, runs and frees a temporary layer -- a test/bring-up entry point, not a hot path.
+ * x [n][Cin][h][w], res1 (or NULL) and y [n][Cout][up*h][up*w] all of `dtype`. */
+int innfer_conv3x3(const void* x, int n, int Cin, int hgt, int wid, const float* w_oihw,
+                   const float* bias, int Cout, int up, int lrelu, const void* res1, float alpha1,
+                   void* y, int dtype, int use_fp32_kernel, void* stream);
+
+/* ---- -cf colour correction: replaces color_fix (utils/utils.py:278-315) with srgb2linear /
+ *      linear2srgb (utils/colors.py:29-60), cv2.resize(INTER_CUBIC) and cv2.GaussianBlur((3,3),0).
+ *      lr: device uint8 [h][w][3]; sr: device uint8 [H][W][3]; out: device uint8 [H][W][3].
+ *      scratch is allocated internally and cached per thread. */
+int innfer_color_fix(const uint8_t* lr, int h, int w, const uint8_t* sr, int H, int W, uint8_t* out,
+                     void* stream);
+/* host-buffer convenience wrapper (H2D, kernels, D2H, synchronises) */
+int innfer_color_fix_host(const uint8_t* lr, int h, int w, const uint8_t* sr, int H, int W,
+                          uint8_t* out, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INNFER_B200_H_ */

@@ -1,0 +1,93 @@
+"""ctypes binding of the C-ABI library (include/innfer_b200.h).
+
+There is no CPU fallback behind these calls: if the shared library is missing or a call fails,
+an exception is raised.  Use ``innfer_b200.build.build()`` (or ``__graft_entry__.build()``) to
+compile the library in-tree.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+INNFER_F16, INNFER_F32, INNFER_U8 = 0, 1, 2
+
+
+class NativeError(RuntimeError):
+    """A call into libinnfer_b200.so returned a negative status."""
+
+    def __init__(self, code, message):
+        super().__init__("innfer_b200 native error %d: %s" % (code, message))
+        self.code = code
+
+
+class RRDBCfg(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("in_nc", "out_nc", "nf", "nb", "gc", "scale", "plus", "fp16")]
+
+
+class Tile(ctypes.Structure):
+    _fields_ = [("y0", ctypes.c_int32), ("x0", ctypes.c_int32)]
+
+
+_LIB = None
+
+_vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+_PROTOS = {
+    "innfer_last_error": (ctypes.c_char_p, []),
+    "innfer_version": (ctypes.c_char_p, []),
+    "innfer_kernel_launches": (ctypes.c_uint64, []),
+    "innfer_rrdb_create": (_i, [ctypes.POINTER(RRDBCfg), _i, ctypes.POINTER(_vp)]),
+    "innfer_rrdb_load": (_i, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(ctypes.c_int64), _i]),
+    "innfer_rrdb_finalize": (_i, [_vp]),
+    "innfer_rrdb_destroy": (None, [_vp]),
+    "innfer_rrdb_set_max_batch": (_i, [_vp, _i]),
+    "innfer_rrdb_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "innfer_rrdb_chop_forward": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _i, _vp]),
+    "innfer_rrdb_upscale_u8": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
+    "innfer_rrdb_upscale_u8_device": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
+    "innfer_tiles_plan": (_i, [_i, _i, _i, _f, ctypes.POINTER(Tile), _i, ctypes.POINTER(_i),
+                               ctypes.POINTER(_i)]),
+    "innfer_image_to_tiles": (_i, [_vp, _i, _i, _i, _i, _i, _f, _vp, _vp]),
+    "innfer_blend": (_i, [_vp, _i, _i, _i, _f, _i, _i, _vp, _i, _vp]),
+    "innfer_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _f, _vp, _i, _i, _vp]),
+    "innfer_color_fix": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "innfer_color_fix_host": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i]),
+}
+
+EXPORTED_SYMBOLS = tuple(sorted(_PROTOS))
+
+
+def lib_path():
+    return _build.lib_path()
+
+
+def load():
+    """Load (once) and return the ctypes library; raises if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            "innfer_b200: %s is missing. Build it with `python -m innfer_b200.build` "
+            "(needs nvcc). There is no CPU fallback for the CUDA path." % path)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def last_error():
+    return load().innfer_last_error().decode(errors="replace")
+
+
+def check(rc):
+    if rc != 0:
+        raise NativeError(rc, last_error())
+
+
+def kernel_launches():
+    return int(load().innfer_kernel_launches())

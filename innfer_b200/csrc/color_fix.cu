@@ -1,0 +1,241 @@
+#include "color_fix.cuh"
+
+#include <cmath>
+#include <mutex>
+
+namespace innfer {
+
+namespace {
+
+struct Scratch {
+  float* diff = nullptr;
+  float* blur = nullptr;
+  float* lut = nullptr;
+  size_t cap = 0;
+  int device = -1;
+};
+thread_local Scratch g_scratch;
+
+// cv::interpolateCubic with A = -0.75 (OpenCV imgproc/resize.cpp)
+__device__ __forceinline__ void cubic_coeffs(float x, float (&c)[4]) {
+  const float A = -0.75f;
+  c[0] = ((A * (x + 1.f) - 5.f * A) * (x + 1.f) + 8.f * A) * (x + 1.f) - 4.f * A;
+  c[1] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+  c[2] = ((A + 2.f) * (1.f - x) - (A + 3.f)) * (1.f - x) * (1.f - x) + 1.f;
+  c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+// source index / fraction of destination coordinate d: fx = (d + 0.5) * scale - 0.5
+__device__ __forceinline__ void src_coord(int d, double scale, int& s, float& f) {
+  const float fx = (float)(((double)d + 0.5) * scale - 0.5);
+  const float fl = floorf(fx);
+  s = (int)fl;
+  f = fx - fl;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ int reflect101(int v, int n) {
+  if (n == 1) return 0;
+  if (v < 0) v = -v;
+  if (v >= n) v = 2 * n - 2 - v;
+  return v;
+}
+
+// (1) diff[y][x][c] = lin(lr) - cubic_down(lin(sr))   (or lin(lr) - lin(sr) when not scaling)
+__global__ void cf_down_diff_kernel(const uint8_t* __restrict__ lr, int h, int w, const uint8_t* __restrict__ sr,
+                                    int H, int W, const float* __restrict__ lut_g, double sy_scale, double sx_scale,
+                                    int scaling, float* __restrict__ diff) {
+  __shared__ float lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  float bd[3];
+  if (scaling) {
+    int sx, sy;
+    float fx, fy;
+    src_coord(x, sx_scale, sx, fx);
+    src_coord(y, sy_scale, sy, fy);
+    float cx[4], cy[4];
+    cubic_coeffs(fx, cx);
+    cubic_coeffs(fy, cy);
+    int xs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xs[j] = clampi(sx + j - 1, 0, W - 1);
+    float rows[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = clampi(sy + k - 1, 0, H - 1);
+      const uint8_t* row = sr + (size_t)yy * W * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        rows[k][c] = lut[row[xs[0] * 3 + c]] * cx[0] + lut[row[xs[1] * 3 + c]] * cx[1] +
+                     lut[row[xs[2] * 3 + c]] * cx[2] + lut[row[xs[3] * 3 + c]] * cx[3];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      bd[c] = rows[0][c] * cy[0] + rows[1][c] * cy[1] + rows[2][c] * cy[2] + rows[3][c] * cy[3];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) bd[c] = lut[sr[((size_t)y * W + x) * 3 + c]];
+  }
+  const size_t o = ((size_t)y * w + x) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) diff[o + c] = lut[lr[o + c]] - bd[c];
+}
+
+// (2) separable [0.25 0.5 0.25] with BORDER_REFLECT_101, row pass then column pass
+__global__ void cf_blur_kernel(const float* __restrict__ diff, int h, int w, float* __restrict__ blur) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const int xl = reflect101(x - 1, w), xr = reflect101(x + 1, w);
+  const int yu = reflect101(y - 1, h), yd = reflect101(y + 1, h);
+  const int ys[3] = {yu, y, yd};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float r[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float* row = diff + (size_t)ys[k] * w * 3;
+      r[k] = row[x * 3 + c] * 0.5f + (row[xl * 3 + c] + row[xr * 3 + c]) * 0.25f;
+    }
+    blur[((size_t)y * w + x) * 3 + c] = r[1] * 0.5f + (r[0] + r[2]) * 0.25f;
+  }
+}
+
+__device__ __forceinline__ uint8_t encode_srgb(float v) {
+  // linear2srgb (colors.py:49-60): clip, piecewise gamma, *255, clip, truncating cast
+  v = fminf(fmaxf(v, 0.f), 1.f);
+  const float inv_gamma = (float)(1.0 / 2.4);
+  const float s = v <= 0.0031308f ? v * 12.92f : 1.055f * powf(v, inv_gamma) - 0.055f;
+  const float q = fminf(fmaxf(s * 255.0f, 0.f), 255.f);
+  return (uint8_t)q;
+}
+
+// (3) out = encode(cubic_up(blur) + lin(sr)); each thread produces PX consecutive pixels of a row
+template <int PX>
+__global__ void cf_up_apply_kernel(const float* __restrict__ blur, int h, int w, const uint8_t* __restrict__ sr,
+                                   int H, int W, const float* __restrict__ lut_g, double sy_scale, double sx_scale,
+                                   int scaling, uint8_t* __restrict__ out) {
+  __shared__ float lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
+  __syncthreads();
+  const int X0 = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
+  const int Y = blockIdx.y;
+  if (X0 >= W) return;
+  int sy = Y;
+  float cy[4] = {0.f, 1.f, 0.f, 0.f};
+  if (scaling) {
+    float fy;
+    src_coord(Y, sy_scale, sy, fy);
+    cubic_coeffs(fy, cy);
+  }
+  const float* brow[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) brow[k] = blur + (size_t)clampi(sy + k - 1, 0, h - 1) * w * 3;
+  const size_t base = ((size_t)Y * W + X0) * 3;
+  uint8_t in[PX * 3], res[PX * 3];
+  if (PX == 4) {
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sr + base);
+    uint32_t* i32 = reinterpret_cast<uint32_t*>(in);
+    i32[0] = s32[0];
+    i32[1] = s32[1];
+    i32[2] = s32[2];
+  } else {
+    for (int i = 0; i < 3; ++i) in[i] = sr[base + i];
+  }
+#pragma unroll
+  for (int px = 0; px < PX; ++px) {
+    const int X = X0 + px;
+    float up[3];
+    if (scaling) {
+      int sx;
+      float fx;
+      src_coord(X, sx_scale, sx, fx);
+      float cx[4];
+      cubic_coeffs(fx, cx);
+      int xs[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xs[j] = clampi(sx + j - 1, 0, w - 1) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          r[k] = brow[k][xs[0] + c] * cx[0] + brow[k][xs[1] + c] * cx[1] + brow[k][xs[2] + c] * cx[2] +
+                 brow[k][xs[3] + c] * cx[3];
+        up[c] = r[0] * cy[0] + r[1] * cy[1] + r[2] * cy[2] + r[3] * cy[3];
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) up[c] = blur[((size_t)Y * w + X) * 3 + c];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) res[px * 3 + c] = encode_srgb(up[c] + lut[in[px * 3 + c]]);
+  }
+  if (PX == 4) {
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(out + base);
+    const uint32_t* r32 = reinterpret_cast<const uint32_t*>(res);
+    o32[0] = r32[0];
+    o32[1] = r32[1];
+    o32[2] = r32[2];
+  } else {
+    for (int i = 0; i < 3; ++i) out[base + i] = res[i];
+  }
+}
+
+}  // namespace
+
+int color_fix_run(const uint8_t* lr, int h, int w, const uint8_t* sr, int H, int W, uint8_t* out,
+                  cudaStream_t stream, int* launches) {
+  if (launches) *launches = 0;
+  if (h < 1 || w < 1 || H < 1 || W < 1) return -1;
+  const int scaling = (h < H && w < W) ? 1 : 0;
+  if (!scaling && !(h == H && w == W)) return -1;  // numpy would fail to broadcast imgA - imgB
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  Scratch& s = g_scratch;
+  const size_t need = (size_t)h * w * 3 * sizeof(float);
+  if (s.device != dev || s.cap < need) {
+    if (s.diff) cudaFree(s.diff);
+    if (s.blur) cudaFree(s.blur);
+    s.diff = s.blur = nullptr;
+    s.cap = 0;
+    if (cudaMalloc(&s.diff, need) != cudaSuccess || cudaMalloc(&s.blur, need) != cudaSuccess) return -5;
+    s.cap = need;
+    if (s.device != dev || !s.lut) {
+      if (cudaMalloc(&s.lut, 256 * sizeof(float)) != cudaSuccess) return -5;
+      // srgb2linear on the 256 possible uint8 values, float32 arithmetic like numpy (colors.py:43-46)
+      float lut[256];
+      for (int i = 0; i < 256; ++i) {
+        const float v = (float)i / 255.0f;
+        lut[i] = v <= 0.04045f ? v / 12.92f : powf((v + 0.055f) / 1.055f, 2.4f);
+      }
+      if (cudaMemcpy(s.lut, lut, sizeof lut, cudaMemcpyHostToDevice) != cudaSuccess) return -5;
+    }
+    s.device = dev;
+  }
+  // cv::resize: scale = 1 / (dst / src)
+  const double down_x = 1.0 / ((double)w / (double)W), down_y = 1.0 / ((double)h / (double)H);
+  const double up_x = 1.0 / ((double)W / (double)w), up_y = 1.0 / ((double)H / (double)h);
+  dim3 block(128);
+  dim3 g1((w + 127) / 128, h);
+  cf_down_diff_kernel<<<g1, block, 0, stream>>>(lr, h, w, sr, H, W, s.lut, down_y, down_x, scaling, s.diff);
+  cf_blur_kernel<<<g1, block, 0, stream>>>(s.diff, h, w, s.blur);
+  const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(sr) | reinterpret_cast<uintptr_t>(out)) % 4 == 0);
+  if (vec) {
+    dim3 g3((W / 4 + 127) / 128, H);
+    cf_up_apply_kernel<4><<<g3, block, 0, stream>>>(s.blur, h, w, sr, H, W, s.lut, up_y, up_x, scaling, out);
+  } else {
+    dim3 g3((W + 127) / 128, H);
+    cf_up_apply_kernel<1><<<g3, block, 0, stream>>>(s.blur, h, w, sr, H, W, s.lut, up_y, up_x, scaling, out);
+  }
+  if (launches) *launches = 3;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace innfer

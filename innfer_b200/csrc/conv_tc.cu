@@ -1,0 +1,268 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernel. See conv_tc.cuh for the design notes.
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace innfer {
+
+namespace {
+
+struct TileCoord {
+  int b, y0, x0, phase, jeff;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t) {
+  TileCoord c;
+  c.phase = t % p.nphase;
+  int r = t / p.nphase;
+  int cp = r % p.cps;
+  r /= p.cps;
+  int band = r % p.bands;
+  c.b = r / p.bands;
+  c.y0 = band * kPatchRows;
+  c.x0 = cp * 8 * p.J;
+  int rem = (p.W - c.x0 + 7) >> 3;  // sub-patches that still touch the image
+  c.jeff = rem < p.J ? rem : p.J;
+  return c;
+}
+
+__device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+template <int N>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int Wh = 8 * p.J + 2;
+  const int a_bytes = conv_tc_a_bytes(p.J);
+  int max_taps = 0;
+  for (int i = 0; i < p.nphase; ++i) max_taps = max_taps > p.ph_ntaps[i] ? max_taps : p.ph_ntaps[i];
+  const int w_bytes = conv_tc_w_bytes(N, max_taps);
+  const int stage_bytes = a_bytes + w_bytes;
+  const int S = p.stages;
+
+  uint8_t* bar_base = smem + (size_t)S * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tfull_bar = empty_bar + S;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_in);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tfull_bar[i]), 1);
+      mbar_init(smem_u32(&tempty_bar[i]), 4);
+    }
+    fence_mbar_init();
+  }
+  if (threadIdx.x < N) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.B * p.bands * p.cps * p.nphase;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(p, t);
+        const uint32_t wb = (uint32_t)p.ph_ntaps[c.phase] * 2u * N * 16u;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + p.ph_woff[c.phase];
+        for (int ks = 0; ks < p.kslabs; ++ks) {
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          const uint32_t dstA = smem_base + (uint32_t)s * stage_bytes;
+          mbar_expect_tx(fb, (uint32_t)(2 * kHaloRows * Wh * 16) + wb);
+          tma_load_5d(dstA, &tmap_in, fb, 0, c.x0 - 1, c.y0 - 1, p.in_chunk0 + 2 * ks, c.b);
+          bulk_load(dstA + a_bytes, wsrc + (size_t)ks * wb, wb, fb);
+          if (++s == S) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(N);
+      const uint32_t lboA = (uint32_t)(kHaloRows * Wh * 16);
+      const uint32_t sboA = (uint32_t)(Wh * 16);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const TileCoord c = decode_tile(p, t);
+        const int ntaps = p.ph_ntaps[c.phase];
+        const int buf = it % p.nbuf;
+        const uint32_t use = (uint32_t)(it / p.nbuf);
+        mbar_wait(smem_u32(&tempty_bar[buf]), (use & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(buf * p.J * N);
+        for (int ks = 0; ks < p.kslabs; ++ks) {
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+          const uint64_t adesc0 = make_smem_desc(sa, lboA, sboA);
+          const uint64_t bdesc0 = make_smem_desc(sa + a_bytes, (uint32_t)N * 16u, 128u);
+          for (int j = 0; j < c.jeff; ++j) {
+            const uint32_t acc = acc0 + (uint32_t)(j * N);
+#pragma unroll 1
+            for (int tp = 0; tp < ntaps; ++tp) {
+              const uint32_t aoff = (uint32_t)p.tap_hy[c.phase][tp] * Wh + p.tap_hx[c.phase][tp] + 8u * j;
+              const uint32_t boff = (uint32_t)tp * (2u * N);  // tap stride in 16-byte units
+              umma_f16_ss(acc, adesc0 + aoff, bdesc0 + boff, idesc, (ks | tp) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(smem_u32(&empty_bar[s]));
+          if (++s == S) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+        umma_commit(smem_u32(&tfull_bar[buf]));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int r = m >> 3, cc = m & 7;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const TileCoord c = decode_tile(p, t);
+      const int buf = it % p.nbuf;
+      const uint32_t use = (uint32_t)(it / p.nbuf);
+      mbar_wait(smem_u32(&tfull_bar[buf]), use & 1u);
+      tc_fence_after();
+      const int y = c.y0 + r;
+      const int oy = y * p.up + p.ph_a[c.phase];
+      for (int j = 0; j < c.jeff; ++j) {
+        const int x = c.x0 + 8 * j + cc;
+        const int ox = x * p.up + p.ph_b[c.phase];
+        const bool valid = (y < p.H) && (x < p.W);
+        const uint32_t tacc = tmem_base + lane_base + (uint32_t)(buf * p.J * N + j * N);
+        const size_t opix = (size_t)oy * p.Wout + ox;
+        const size_t oplane = (size_t)p.Hout * p.Wout;
+#pragma unroll
+        for (int g = 0; g < N / 16; ++g) {
+          uint32_t v[16];
+          tmem_ld16(tacc + g * 16, v);
+          // residual loads are issued before the TMEM wait so their latency overlaps it
+          uint4 r1[2], r2[2];
+          const bool do_chunk0 = valid && (2 * g) < p.out_nchunks;
+          const bool do_chunk1 = valid && (2 * g + 1) < p.out_nchunks;
+          if (p.res1 != nullptr) {
+            const size_t base = ((size_t)c.b * p.res1_CT + p.res1_chunk0 + 2 * g) * oplane + opix;
+            if (do_chunk0) r1[0] = *reinterpret_cast<const uint4*>(p.res1 + base * 8);
+            if (do_chunk1) r1[1] = *reinterpret_cast<const uint4*>(p.res1 + (base + oplane) * 8);
+          }
+          if (p.res2 != nullptr) {
+            const size_t base = ((size_t)c.b * p.res2_CT + p.res2_chunk0 + 2 * g) * oplane + opix;
+            if (do_chunk0) r2[0] = *reinterpret_cast<const uint4*>(p.res2 + base * 8);
+            if (do_chunk1) r2[1] = *reinterpret_cast<const uint4*>(p.res2 + (base + oplane) * 8);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const bool doit = h == 0 ? do_chunk0 : do_chunk1;
+            if (!doit) continue;
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float tv = __uint_as_float(v[h * 8 + e]) + s_bias[g * 16 + h * 8 + e];
+              if (p.lrelu) tv = lrelu_f(tv, p.slope);
+              f[e] = tv;
+            }
+            if (p.res1 != nullptr) {
+              const __half2* hp = reinterpret_cast<const __half2*>(&r1[h]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 rv = __half22float2(hp[e]);
+                f[2 * e] = f[2 * e] * p.alpha1 + rv.x;
+                f[2 * e + 1] = f[2 * e + 1] * p.alpha1 + rv.y;
+              }
+            }
+            if (p.res2 != nullptr) {
+              const __half2* hp = reinterpret_cast<const __half2*>(&r2[h]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 rv = __half22float2(hp[e]);
+                f[2 * e] = f[2 * e] * p.alpha2 + rv.x;
+                f[2 * e + 1] = f[2 * e + 1] * p.alpha2 + rv.y;
+              }
+            }
+            uint4 o;
+            __half2 h0 = __floats2half2_rn(f[0], f[1]);
+            __half2 h1 = __floats2half2_rn(f[2], f[3]);
+            __half2 h2 = __floats2half2_rn(f[4], f[5]);
+            __half2 h3 = __floats2half2_rn(f[6], f[7]);
+            o.x = *reinterpret_cast<uint32_t*>(&h0);
+            o.y = *reinterpret_cast<uint32_t*>(&h1);
+            o.z = *reinterpret_cast<uint32_t*>(&h2);
+            o.w = *reinterpret_cast<uint32_t*>(&h3);
+            const size_t obase =
+                ((size_t)c.b * p.out_CT + p.out_chunk0 + 2 * g + h) * oplane + opix;
+            *reinterpret_cast<uint4*>(p.out + obase * 8) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+template <int N>
+int launch_impl(const CUtensorMap* tmap_in, const ConvTcParams& p, int num_sms, cudaStream_t stream) {
+  int max_taps = 0;
+  for (int i = 0; i < p.nphase; ++i) max_taps = max_taps > p.ph_ntaps[i] ? max_taps : p.ph_ntaps[i];
+  const int stage_bytes = conv_tc_a_bytes(p.J) + conv_tc_w_bytes(N, max_taps);
+  const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024;
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_bytes);
+  if (e != cudaSuccess) return (int)e;
+  const int num_tiles = p.B * p.bands * p.cps * p.nphase;
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  conv_tc_kernel<N><<<grid, kConvThreads, smem_bytes, stream>>>(*tmap_in, p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int launch_conv_tc(const CUtensorMap* tmap_in, const ConvTcParams& p, int N, int num_sms,
+                   cudaStream_t stream) {
+  switch (N) {
+    case 16: return launch_impl<16>(tmap_in, p, num_sms, stream);
+    case 32: return launch_impl<32>(tmap_in, p, num_sms, stream);
+    case 64: return launch_impl<64>(tmap_in, p, num_sms, stream);
+    default: return (int)cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace innfer

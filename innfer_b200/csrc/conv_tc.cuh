@@ -1,0 +1,85 @@
+// Implicit-GEMM 3x3 (or phase-folded 2x2) convolution on tcgen05 tensor cores for sm_100a.
+//
+// Replaces, on the GPU path, what the reference runs as nn.Conv2d(k=3,s=1,p=1)+LeakyReLU(0.2)
+// (+ torch.cat, + "*0.2 + x") per call of conv_block / ResidualDenseBlock_5C / RRDB / upconv_block
+// (reference: architectures/block.py:213-254,348-361, architectures/RRDBNet_arch.py:91-98,152-165).
+//
+// Data layout in HBM ("planar chunk", NC/8HW8): activations are [tile][chunk][H][W][8] fp16, one
+// chunk = 8 channels = 16 bytes per pixel.  A dense block's concat buffer is just a tensor with 24
+// chunks; each conv writes its own chunk range, so torch.cat never runs.
+//
+// GEMM mapping: M = 128 output pixels (a 16-row x 8-col sub-patch), N = Cout, K = 16 input
+// channels per MMA, one MMA per (sub-patch, tap, 16-channel slab).  A CTA owns a patch of
+// 16 x (8*J) pixels: the (16+2) x (8J+2) halo tile of one 16-channel slab is brought in ONCE by a
+// 5-D TMA box load (OOB -> zero = the conv's zero padding) and all taps / sub-patches address it
+// through shifted SWIZZLE_NONE K-major matrix descriptors:
+//   addr(pixel row m, kchunk c) = base + ((hy + m/8) * Wh + hx + 8j + m%8) * 16 + c * (Rh*Wh*16)
+// i.e. SBO = Wh*16, LBO = Rh*Wh*16, start shifted by (hy*Wh + hx + 8j) * 16 bytes.
+// Accumulators (J of them, 128 lanes x N fp32 columns) live in TMEM, double buffered when they
+// fit, and the epilogue (bias, LeakyReLU, up to two scaled residual adds, fp16 pack) reads them with
+// tcgen05.ld and stores 16-byte channel chunks straight into the destination chunk slice.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace innfer {
+
+constexpr int kConvThreads = 192;
+constexpr int kPatchRows = 16;            // rows per CTA patch (= rows of one M=128 sub-patch)
+constexpr int kHaloRows = kPatchRows + 2; // Rh
+constexpr int kMaxPhases = 9;
+constexpr int kMaxTaps = 9;
+
+struct ConvTcParams {
+  // source geometry
+  int B, H, W;
+  int in_chunk0;   // first input chunk inside the TMA-mapped buffer
+  int kslabs;      // Cin / 16
+  // CTA tiling
+  int J;           // sub-patches per CTA (patch width = 8*J)
+  int bands, cps;  // ceil(H/16), ceil(W/(8J))
+  int nphase;      // 1 for a plain 3x3, up*up for a nearest-upsample-folded conv
+  int up;          // output = up * source resolution
+  int Hout, Wout;
+  int stages;      // smem pipeline depth
+  int nbuf;        // TMEM accumulator buffers (1 or 2)
+  int tmem_cols;   // power of two >= nbuf*J*N
+  // destination
+  __half* out;
+  int out_CT, out_chunk0, out_nchunks;
+  // weights / bias
+  const __half* w;       // packed [phase][kslab][tap][2][N][8]
+  const float* bias;     // [N]
+  // epilogue
+  int lrelu;
+  float slope;
+  const __half* res1;
+  int res1_CT, res1_chunk0;
+  float alpha1;  // t = t*alpha1 + res1
+  const __half* res2;
+  int res2_CT, res2_chunk0;
+  float alpha2;  // t = t*alpha2 + res2
+  // phase tables
+  uint32_t ph_woff[kMaxPhases];           // byte offset of the phase's weights inside w
+  uint8_t ph_ntaps[kMaxPhases];
+  uint8_t ph_a[kMaxPhases], ph_b[kMaxPhases];      // output sub-pixel offsets
+  uint8_t tap_hy[kMaxPhases][kMaxTaps];   // halo-tile offsets of each tap (0..2)
+  uint8_t tap_hx[kMaxPhases][kMaxTaps];
+};
+
+// Host-side launcher (conv_tc.cu). Returns cudaError_t as int.
+int launch_conv_tc(const CUtensorMap* tmap_in, const ConvTcParams& p, int N, int num_sms,
+                   cudaStream_t stream);
+// Bytes of dynamic smem / stage geometry helpers shared by host and device.
+__host__ __device__ inline int conv_tc_a_bytes(int J) {
+  int b = 2 * kHaloRows * (8 * J + 2) * 16;
+  return (b + 127) & ~127;
+}
+__host__ __device__ inline int conv_tc_w_bytes(int N, int max_taps) { return max_taps * 2 * N * 16; }
+
+}  // namespace innfer

@@ -1,0 +1,641 @@
+// C-ABI of the RRDB path (include/innfer_b200.h): network handle, weight loading under the
+// reference's state-dict key names, forward schedule over planar-chunk buffers, chop_forward.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/innfer_b200.h"
+#include "color_fix.cuh"
+#include "conv_direct.cuh"
+#include "layers.cuh"
+#include "pixel_ops.cuh"
+
+using namespace innfer;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(INNFER_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU_TRY(expr)                                          \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return cuda_fail(_e, #expr);       \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess) return (int)e;
+    bytes = need;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+struct Param {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+PixelDType to_pix(int dtype) { return dtype == INNFER_F16 ? kF16 : (dtype == INNFER_F32 ? kF32 : kU8); }
+
+}  // namespace
+
+struct innfer_rrdb {
+  innfer_rrdb_cfg cfg;
+  int device = 0;
+  int num_sms = 148;
+  int n_up = 0, up_factor = 2;
+  bool finalized = false;
+  int max_batch = 38;
+  std::map<std::string, Param> params;
+  // layers in execution order
+  ConvLayer fea, lr_conv, hr0, hr1;
+  std::vector<ConvLayer> rdb;  // [nb][3][5]
+  std::vector<ConvLayer> ups;
+  TmapCache cache;
+  // workspace
+  DevBuf in_tiles, feat, xbuf[3], hrbuf[2], out_tiles, img_in, img_out;
+  // fp32-mode workspace lives in the same buffers (sized in bytes)
+  ~innfer_rrdb() {
+    conv_layer_free(fea);
+    conv_layer_free(lr_conv);
+    conv_layer_free(hr0);
+    conv_layer_free(hr1);
+    for (auto& l : rdb) conv_layer_free(l);
+    for (auto& l : ups) conv_layer_free(l);
+    in_tiles.release();
+    feat.release();
+    for (auto& b : xbuf) b.release();
+    for (auto& b : hrbuf) b.release();
+    out_tiles.release();
+    img_in.release();
+    img_out.release();
+  }
+  int in_ct() const { return (cfg.in_nc + 15) / 16 * 2; }
+  int nf_ct() const { return cfg.nf / 8; }
+  int cat_ct() const { return (cfg.nf + 4 * 32) / 8; }
+  size_t esz() const { return cfg.fp16 ? 2 : 4; }
+};
+
+namespace {
+
+int set_device(const innfer_rrdb* h) {
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  return 0;
+}
+
+int build_layer(innfer_rrdb* h, ConvLayer& L, const std::string& prefix, int Cout, int Cin, int up) {
+  auto wi = h->params.find(prefix + ".weight");
+  auto bi = h->params.find(prefix + ".bias");
+  if (wi == h->params.end()) return fail(INNFER_E_STATE, "missing key " + prefix + ".weight");
+  if (bi == h->params.end()) return fail(INNFER_E_STATE, "missing key " + prefix + ".bias");
+  const auto& ws = wi->second.shape;
+  if (ws.size() != 4 || ws[0] != Cout || ws[1] != Cin || ws[2] != 3 || ws[3] != 3)
+    return fail(INNFER_E_INVALID, "size mismatch for " + prefix + ".weight");
+  if (bi->second.shape.size() != 1 || bi->second.shape[0] != Cout)
+    return fail(INNFER_E_INVALID, "size mismatch for " + prefix + ".bias");
+  std::string err;
+  int rc = conv_layer_build(L, wi->second.data.data(), bi->second.data.data(), Cout, Cin, up, err);
+  if (rc) return fail(rc == -2 ? INNFER_E_UNSUPPORTED : INNFER_E_CUDA, prefix + ": " + err);
+  if (!h->cfg.fp16) {
+    rc = conv_direct_upload(L);
+    if (rc) return fail(INNFER_E_CUDA, prefix + ": fp32 weight upload failed");
+  }
+  return 0;
+}
+
+// run one conv in the handle's precision mode
+int run_conv(innfer_rrdb* h, const ConvLayer& L, ChunkView in, int B, int H, int W, ChunkView out,
+             int out_nchunks, const Epilogue& ep, cudaStream_t st) {
+  int rc;
+  if (h->cfg.fp16) {
+    rc = conv_layer_run(L, h->cache, in, B, H, W, out, out_nchunks, ep, h->num_sms, st);
+  } else {
+    rc = conv_direct_run(L, in, B, H, W, out, out_nchunks, ep, st);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (rc != 0) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "conv launch failed (rc=%d, Cin=%d Cout=%d up=%d H=%d W=%d B=%d): %s", rc,
+             L.Cin, L.Cout, L.up, H, W, B, rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "launcher error");
+    return fail(INNFER_E_CUDA, msg);
+  }
+  return 0;
+}
+
+ChunkView view(DevBuf& b, int CT, int chunk0) {
+  ChunkView v;
+  v.base = reinterpret_cast<__half*>(b.p);
+  v.CT = CT;
+  v.chunk0 = chunk0;
+  return v;
+}
+
+int ensure_workspace(innfer_rrdb* h, int B, int hgt, int wid) {
+  const size_t px = (size_t)B * hgt * wid;
+  const size_t e8 = 8 * h->esz();
+  const int s = h->cfg.scale;
+  int rc = 0;
+  rc |= h->in_tiles.ensure(px * h->in_ct() * e8);
+  rc |= h->feat.ensure(px * h->nf_ct() * e8);
+  for (auto& b : h->xbuf) rc |= b.ensure(px * h->cat_ct() * e8);
+  const size_t hpx = px * s * s;
+  // HR ping-pong buffers: the last upconv output and HR_conv0 output are both full resolution
+  for (auto& b : h->hrbuf) rc |= b.ensure(hpx * h->nf_ct() * e8);
+  if (rc) return fail(INNFER_E_NOMEM, "workspace allocation failed");
+  return 0;
+}
+
+// Forward B tiles that already sit in h->in_tiles ([B][in_ct][hgt][wid][8]); the result
+// ([B][1 or 2][s*hgt][s*wid][8], out_nc channels in chunk 0..) is written to `dst`.
+int forward_tiles(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, cudaStream_t st) {
+  const int nfc = h->nf_ct(), catc = h->cat_ct();
+  const int gcc = 32 / 8;
+  int rc;
+  Epilogue plain;
+  Epilogue act;
+  act.lrelu = true;
+  // fea_conv -> feat (kept for the ShortcutBlock) and copy into xbuf[0][0:nfc]
+  if ((rc = run_conv(h, h->fea, view(h->in_tiles, h->in_ct(), 0), B, hgt, wid, view(h->feat, nfc, 0), nfc, plain, st))) return rc;
+  {
+    const size_t row = (size_t)nfc * hgt * wid * 8 * h->esz();
+    CU_TRY(cudaMemcpy2DAsync(h->xbuf[0].p, (size_t)catc * hgt * wid * 8 * h->esz(), h->feat.p, row, row, B,
+                             cudaMemcpyDeviceToDevice, st));
+  }
+  int P = 0, Q = 1, R = 2;
+  for (int b = 0; b < h->cfg.nb; ++b) {
+    const int order[3] = {P, Q, R};
+    for (int r = 0; r < 3; ++r) {
+      const int cur = order[r];
+      const ConvLayer* L = &h->rdb[((size_t)b * 3 + r) * 5];
+      for (int k = 0; k < 4; ++k) {
+        if ((rc = run_conv(h, L[k], view(h->xbuf[cur], catc, 0), B, hgt, wid,
+                           view(h->xbuf[cur], catc, nfc + gcc * k), gcc, act, st)))
+          return rc;
+      }
+      Epilogue e5;
+      e5.res1 = view(h->xbuf[cur], catc, 0);
+      e5.alpha1 = 0.2f;
+      int dstbuf;
+      if (r < 2) {
+        dstbuf = order[r + 1];
+      } else {
+        dstbuf = Q;  // RRDB output: (rdb3*0.2 + x_rdb3)*0.2 + x_rrdb  (RRDBNet_arch.py:98,165)
+        e5.res2 = view(h->xbuf[P], catc, 0);
+        e5.alpha2 = 0.2f;
+      }
+      if ((rc = run_conv(h, L[4], view(h->xbuf[cur], catc, 0), B, hgt, wid, view(h->xbuf[dstbuf], catc, 0), nfc, e5, st)))
+        return rc;
+    }
+    const int nP = Q, nQ = R, nR = P;
+    P = nP;
+    Q = nQ;
+    R = nR;
+  }
+  // LR_conv + ShortcutBlock: fea + LR_conv(trunk)  (block.py:189-191)
+  {
+    Epilogue e;
+    e.res1 = view(h->feat, nfc, 0);
+    e.alpha1 = 1.0f;
+    if ((rc = run_conv(h, h->lr_conv, view(h->xbuf[P], catc, 0), B, hgt, wid, view(h->xbuf[Q], catc, 0), nfc, e, st)))
+      return rc;
+  }
+  ChunkView cur = view(h->xbuf[Q], catc, 0);
+  int ch = hgt, cw = wid, pp = 0;
+  for (size_t i = 0; i < h->ups.size(); ++i) {
+    ChunkView o = view(h->hrbuf[pp], nfc, 0);
+    if ((rc = run_conv(h, h->ups[i], cur, B, ch, cw, o, nfc, act, st))) return rc;
+    ch *= h->ups[i].up;
+    cw *= h->ups[i].up;
+    cur = o;
+    pp ^= 1;
+  }
+  ChunkView o = view(h->hrbuf[pp], nfc, 0);
+  if ((rc = run_conv(h, h->hr0, cur, B, ch, cw, o, nfc, act, st))) return rc;
+  const int out_chunks = (h->cfg.out_nc + 7) / 8;
+  if ((rc = run_conv(h, h->hr1, o, B, ch, cw, dst, out_chunks, plain, st))) return rc;
+  return 0;
+}
+
+// Split ntiles into batches <= max_batch minimising the number of CTA waves of the LR convs.
+int pick_batch(const innfer_rrdb* h, int ntiles, int p) {
+  if (ntiles <= 1) return 1;
+  const int J = choose_J(p, 32);
+  const long ctas = (long)((p + 15) / 16) * ((p + 8 * J - 1) / (8 * J));
+  long best_waves = -1;
+  int best = 1;
+  const int hi = h->max_batch < ntiles ? h->max_batch : ntiles;
+  for (int B = hi; B >= (hi + 1) / 2; --B) {
+    long waves = 0;
+    for (int t = 0; t < ntiles; t += B) {
+      const int nb = (ntiles - t) < B ? (ntiles - t) : B;
+      waves += (nb * ctas + h->num_sms - 1) / h->num_sms;
+    }
+    if (best_waves < 0 || waves < best_waves) {
+      best_waves = waves;
+      best = B;
+    }
+  }
+  return best;
+}
+
+int chop_impl(innfer_rrdb* h, const void* src, PixelDType st, int H, int W, int patch, float step, void* dst,
+              PixelDType dt, cudaStream_t stream) {
+  if (!h->finalized) return fail(INNFER_E_STATE, "innfer_rrdb_finalize has not been called");
+  if (!(step >= 0.5f && step <= 1.0f)) return fail(INNFER_E_INVALID, "step must be in [0.5, 1.0]");
+  TilePlan plan;
+  if (make_tile_plan(H, W, patch, step, plan)) return fail(INNFER_E_INVALID, "cannot tile this image size");
+  if (step != 0.5f) return fail(INNFER_E_UNSUPPORTED, "only step=0.5 (run.py:214-215) is implemented");
+  const int ntiles = plan.nty * plan.ntx;
+  const int p = plan.p, s = h->cfg.scale;
+  const int B = pick_batch(h, ntiles, p);
+  int rc;
+  if ((rc = ensure_workspace(h, B, p, p))) return rc;
+  const int oct = 1 * ((h->cfg.out_nc + 7) / 8);
+  const size_t tile_out_elems = (size_t)oct * (s * p) * (s * p) * 8;
+  if (h->out_tiles.ensure((size_t)ntiles * tile_out_elems * h->esz()))
+    return fail(INNFER_E_NOMEM, "tile output allocation failed");
+  for (int t0 = 0; t0 < ntiles; t0 += B) {
+    const int nb = (ntiles - t0) < B ? (ntiles - t0) : B;
+    if (h->cfg.fp16) {
+      rc = launch_image_to_tiles(src, st, h->cfg.in_nc, plan, t0, nb, reinterpret_cast<__half*>(h->in_tiles.p),
+                                 h->in_ct(), stream);
+    } else {
+      rc = launch_image_to_tiles_f32(src, st, h->cfg.in_nc, plan, t0, nb, reinterpret_cast<float*>(h->in_tiles.p),
+                                     h->in_ct(), stream);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (rc) return fail(INNFER_E_CUDA, "image_to_tiles launch failed");
+    ChunkView dv;
+    dv.base = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(h->out_tiles.p) +
+                                        (size_t)t0 * tile_out_elems * h->esz());
+    dv.CT = oct;
+    dv.chunk0 = 0;
+    if ((rc = forward_tiles(h, nb, p, p, dv, stream))) return rc;
+  }
+  if (h->cfg.fp16)
+    rc = launch_blend(reinterpret_cast<const __half*>(h->out_tiles.p), oct, plan, s, h->cfg.out_nc, dst, dt, stream);
+  else
+    rc = launch_blend_f32(reinterpret_cast<const float*>(h->out_tiles.p), oct, plan, s, h->cfg.out_nc, dst, dt, stream);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (rc == -2) return fail(INNFER_E_UNSUPPORTED, "tile size with negative blend core (odd tile size)");
+  if (rc) return fail(INNFER_E_CUDA, "blend launch failed");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char* innfer_last_error(void) { return g_err.c_str(); }
+const char* innfer_version(void) { return "innfer_b200 0.1 (sm_100a)"; }
+uint64_t innfer_kernel_launches(void) { return g_launches.load(); }
+
+int innfer_rrdb_create(const innfer_rrdb_cfg* cfg, int device, innfer_rrdb** out) {
+  if (!cfg || !out) return fail(INNFER_E_INVALID, "null argument");
+  if (cfg->plus) return fail(INNFER_E_UNSUPPORTED, "ESRGAN+ (plus=True) residual paths are not implemented");
+  if (cfg->nf != 64 && cfg->nf != 32) return fail(INNFER_E_UNSUPPORTED, "nf must be 32 or 64");
+  if (cfg->in_nc < 1 || cfg->in_nc > 16 || cfg->out_nc < 1 || cfg->out_nc > 8)
+    return fail(INNFER_E_UNSUPPORTED, "in_nc must be <= 16 and out_nc <= 8");
+  if (cfg->nb < 1) return fail(INNFER_E_INVALID, "nb must be >= 1");
+  int n_up = 0, f = 2;
+  switch (cfg->scale) {
+    case 1: n_up = 0; break;
+    case 2: n_up = 1; break;
+    case 3: n_up = 1; f = 3; break;
+    case 4: n_up = 2; break;
+    case 8: n_up = 3; break;
+    default: return fail(INNFER_E_UNSUPPORTED, "scale must be 1, 2, 3, 4 or 8");
+  }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(INNFER_E_UNSUPPORTED, "this library contains sm_100a code only; device is not compute capability 10.x");
+  innfer_rrdb* h = new innfer_rrdb();
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->n_up = n_up;
+  h->up_factor = f;
+  *out = h;
+  return 0;
+}
+
+int innfer_rrdb_load(innfer_rrdb* h, const char* key, const float* host_data, const int64_t* shape, int ndim) {
+  if (!h || !key || !host_data || !shape || ndim < 1 || ndim > 4) return fail(INNFER_E_INVALID, "bad argument");
+  if (h->finalized) return fail(INNFER_E_STATE, "handle already finalized");
+  Param p;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    p.shape.push_back(shape[i]);
+    n *= (size_t)shape[i];
+  }
+  p.data.assign(host_data, host_data + n);
+  h->params[key] = std::move(p);
+  return 0;
+}
+
+int innfer_rrdb_finalize(innfer_rrdb* h) {
+  if (!h) return fail(INNFER_E_INVALID, "null handle");
+  if (h->finalized) return 0;
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  const auto& c = h->cfg;
+  size_t expected = 0;
+  if ((rc = build_layer(h, h->fea, "model.0", c.nf, c.in_nc, 1))) return rc;
+  expected += 2;
+  h->rdb.resize((size_t)c.nb * 15);
+  for (int b = 0; b < c.nb; ++b)
+    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < 5; ++k) {
+        char key[96];
+        snprintf(key, sizeof key, "model.1.sub.%d.RDB%d.conv%d.0", b, r + 1, k + 1);
+        const int cin = c.nf + 32 * k, cout = k < 4 ? 32 : c.nf;
+        if ((rc = build_layer(h, h->rdb[((size_t)b * 3 + r) * 5 + k], key, cout, cin, 1))) return rc;
+        expected += 2;
+      }
+  {
+    char key[64];
+    snprintf(key, sizeof key, "model.1.sub.%d", c.nb);
+    if ((rc = build_layer(h, h->lr_conv, key, c.nf, c.nf, 1))) return rc;
+    expected += 2;
+  }
+  h->ups.resize(h->n_up);
+  for (int i = 0; i < h->n_up; ++i) {
+    char key[64];
+    snprintf(key, sizeof key, "model.%d", 3 + 3 * i);
+    if ((rc = build_layer(h, h->ups[i], key, c.nf, c.nf, h->up_factor))) return rc;
+    expected += 2;
+  }
+  {
+    char key[64];
+    snprintf(key, sizeof key, "model.%d", 2 + 3 * h->n_up);
+    if ((rc = build_layer(h, h->hr0, key, c.nf, c.nf, 1))) return rc;
+    snprintf(key, sizeof key, "model.%d", 4 + 3 * h->n_up);
+    if ((rc = build_layer(h, h->hr1, key, c.out_nc, c.nf, 1))) return rc;
+    expected += 4;
+  }
+  if (h->params.size() != expected) {
+    // strict load (run.py:93): unexpected keys are an error
+    return fail(INNFER_E_INVALID, "unexpected keys in state dict (" + std::to_string(h->params.size()) +
+                                      " loaded, " + std::to_string(expected) + " expected)");
+  }
+  h->params.clear();
+  h->finalized = true;
+  return 0;
+}
+
+void innfer_rrdb_destroy(innfer_rrdb* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  delete h;
+}
+
+int innfer_rrdb_set_max_batch(innfer_rrdb* h, int max_tiles) {
+  if (!h || max_tiles < 1) return fail(INNFER_E_INVALID, "bad argument");
+  h->max_batch = max_tiles;
+  return 0;
+}
+
+int innfer_rrdb_forward(innfer_rrdb* h, const void* x, int n, int hgt, int wid, void* y, int dtype, void* stream) {
+  if (!h || !x || !y) return fail(INNFER_E_INVALID, "null argument");
+  if (!h->finalized) return fail(INNFER_E_STATE, "innfer_rrdb_finalize has not been called");
+  if (dtype != INNFER_F16 && dtype != INNFER_F32) return fail(INNFER_E_INVALID, "dtype must be F16 or F32");
+  if (n < 1 || hgt < 1 || wid < 1) return fail(INNFER_E_INVALID, "bad shape");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int s = h->cfg.scale;
+  const int oct = (h->cfg.out_nc + 7) / 8;
+  // batch images one at a time through max_batch-sized groups
+  for (int b0 = 0; b0 < n; b0 += h->max_batch) {
+    const int nb = (n - b0) < h->max_batch ? (n - b0) : h->max_batch;
+    if ((rc = ensure_workspace(h, nb, hgt, wid))) return rc;
+    if (h->out_tiles.ensure((size_t)nb * oct * s * hgt * s * wid * 8 * h->esz()))
+      return fail(INNFER_E_NOMEM, "output tile allocation failed");
+    const size_t in_off = (size_t)b0 * h->cfg.in_nc * hgt * wid * (dtype == INNFER_F16 ? 2 : 4);
+    const size_t out_off = (size_t)b0 * h->cfg.out_nc * s * hgt * s * wid * (dtype == INNFER_F16 ? 2 : 4);
+    const void* xs = reinterpret_cast<const uint8_t*>(x) + in_off;
+    void* ys = reinterpret_cast<uint8_t*>(y) + out_off;
+    if (h->cfg.fp16)
+      rc = launch_nchw_to_chunks(xs, to_pix(dtype), nb, h->cfg.in_nc, hgt, wid, reinterpret_cast<__half*>(h->in_tiles.p), h->in_ct(), st);
+    else
+      rc = launch_nchw_to_chunks_f32(xs, to_pix(dtype), nb, h->cfg.in_nc, hgt, wid, reinterpret_cast<float*>(h->in_tiles.p), h->in_ct(), st);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (rc) return fail(INNFER_E_CUDA, "nchw_to_chunks launch failed");
+    ChunkView dv = view(h->out_tiles, oct, 0);
+    if ((rc = forward_tiles(h, nb, hgt, wid, dv, st))) return rc;
+    if (h->cfg.fp16)
+      rc = launch_chunks_to_nchw(reinterpret_cast<const __half*>(h->out_tiles.p), oct, nb, h->cfg.out_nc, s * hgt, s * wid, ys, to_pix(dtype), st);
+    else
+      rc = launch_chunks_to_nchw_f32(reinterpret_cast<const float*>(h->out_tiles.p), oct, nb, h->cfg.out_nc, s * hgt, s * wid, ys, to_pix(dtype), st);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (rc) return fail(INNFER_E_CUDA, "chunks_to_nchw launch failed");
+  }
+  return 0;
+}
+
+int innfer_rrdb_chop_forward(innfer_rrdb* h, const void* x, int H, int W, int patch_size, float step, void* y,
+                             int dtype, void* stream) {
+  if (!h || !x || !y) return fail(INNFER_E_INVALID, "null argument");
+  if (dtype != INNFER_F16 && dtype != INNFER_F32) return fail(INNFER_E_INVALID, "dtype must be F16 or F32");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  return chop_impl(h, x, to_pix(dtype), H, W, patch_size, step, y, to_pix(dtype), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int innfer_rrdb_upscale_u8_device(innfer_rrdb* h, const uint8_t* img, int H, int W, int patch_size, float step,
+                                  uint8_t* out, void* stream) {
+  if (!h || !img || !out) return fail(INNFER_E_INVALID, "null argument");
+  if (h->cfg.in_nc != 3 || h->cfg.out_nc != 3) return fail(INNFER_E_INVALID, "uint8 path needs 3-channel models");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  return chop_impl(h, img, kU8, H, W, patch_size, step, out, kU8, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int innfer_rrdb_upscale_u8(innfer_rrdb* h, const uint8_t* img, int H, int W, int patch_size, float step,
+                           uint8_t* out, void* stream) {
+  if (!h || !img || !out) return fail(INNFER_E_INVALID, "null argument");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int s = h->cfg.scale;
+  const size_t ib = (size_t)H * W * 3, ob = ib * s * s;
+  if (h->img_in.ensure(ib) || h->img_out.ensure(ob)) return fail(INNFER_E_NOMEM, "image buffer allocation failed");
+  CU_TRY(cudaMemcpyAsync(h->img_in.p, img, ib, cudaMemcpyHostToDevice, st));
+  rc = innfer_rrdb_upscale_u8_device(h, reinterpret_cast<const uint8_t*>(h->img_in.p), H, W, patch_size, step,
+                                     reinterpret_cast<uint8_t*>(h->img_out.p), stream);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(out, h->img_out.p, ob, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int innfer_tiles_plan(int H, int W, int patch_size, float step, innfer_tile* out, int cap, int* n, int* tile_size) {
+  TilePlan plan;
+  if (make_tile_plan(H, W, patch_size, step, plan)) return fail(INNFER_E_INVALID, "cannot tile this image size");
+  const int nt = plan.nty * plan.ntx;
+  if (n) *n = nt;
+  if (tile_size) *tile_size = plan.p;
+  if (out) {
+    for (int i = 0; i < nt && i < cap; ++i) {
+      out[i].y0 = plan.ys[i / plan.ntx];
+      out[i].x0 = plan.xs[i % plan.ntx];
+    }
+  }
+  return 0;
+}
+
+int innfer_image_to_tiles(const void* src, int src_dtype, int C, int H, int W, int patch_size, float step,
+                          void* dst_tiles, void* stream) {
+  if (!src || !dst_tiles) return fail(INNFER_E_INVALID, "null argument");
+  TilePlan plan;
+  if (make_tile_plan(H, W, patch_size, step, plan)) return fail(INNFER_E_INVALID, "cannot tile this image size");
+  const int CT = (C + 15) / 16 * 2;
+  int rc = launch_image_to_tiles(src, to_pix(src_dtype), C, plan, 0, plan.nty * plan.ntx,
+                                 reinterpret_cast<__half*>(dst_tiles), CT, reinterpret_cast<cudaStream_t>(stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (rc) return fail(INNFER_E_CUDA, "image_to_tiles launch failed");
+  return 0;
+}
+
+int innfer_blend(const void* tiles, int H, int W, int patch_size, float step, int scale, int C, void* dst,
+                 int dst_dtype, void* stream) {
+  if (!tiles || !dst) return fail(INNFER_E_INVALID, "null argument");
+  if (step != 0.5f) return fail(INNFER_E_UNSUPPORTED, "only step=0.5 is implemented");
+  TilePlan plan;
+  if (make_tile_plan(H, W, patch_size, step, plan)) return fail(INNFER_E_INVALID, "cannot tile this image size");
+  int rc = launch_blend(reinterpret_cast<const __half*>(tiles), 1, plan, scale, C, dst, to_pix(dst_dtype),
+                        reinterpret_cast<cudaStream_t>(stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (rc == -2) return fail(INNFER_E_UNSUPPORTED, "tile size with negative blend core (odd tile size)");
+  if (rc) return fail(INNFER_E_CUDA, "blend launch failed");
+  return 0;
+}
+
+int innfer_conv3x3(const void* x, int n, int Cin, int hgt, int wid, const float* w_oihw, const float* bias,
+                   int Cout, int up, int lrelu, const void* res1, float alpha1, void* y, int dtype,
+                   int use_fp32_kernel, void* stream) {
+  if (!x || !w_oihw || !y) return fail(INNFER_E_INVALID, "null argument");
+  if (dtype != INNFER_F16 && dtype != INNFER_F32) return fail(INNFER_E_INVALID, "dtype must be F16 or F32");
+  if (res1 && up != 1) return fail(INNFER_E_INVALID, "residual needs up == 1");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(INNFER_E_UNSUPPORTED, "device is not compute capability 10.x");
+  ConvLayer L;
+  std::string err;
+  int rc = conv_layer_build(L, w_oihw, bias, Cout, Cin, up, err);
+  if (rc) return fail(rc == -2 ? INNFER_E_UNSUPPORTED : INNFER_E_CUDA, err);
+  const size_t esz = use_fp32_kernel ? 4 : 2;
+  const int ict = L.Cin_pad / 8, oct = (Cout + 7) / 8;
+  const size_t ipx = (size_t)n * hgt * wid, opx = ipx * up * up;
+  DevBuf bi, bo, br;
+  TmapCache cache;
+  auto cleanup = [&]() {
+    bi.release();
+    bo.release();
+    br.release();
+    conv_layer_free(L);
+  };
+  if (bi.ensure(ipx * ict * 8 * esz) || bo.ensure(opx * oct * 8 * esz) || (res1 && br.ensure(opx * oct * 8 * esz))) {
+    cleanup();
+    return fail(INNFER_E_NOMEM, "allocation failed");
+  }
+  Epilogue ep;
+  ep.lrelu = lrelu != 0;
+  if (use_fp32_kernel) {
+    rc = conv_direct_upload(L);
+    rc |= launch_nchw_to_chunks_f32(x, to_pix(dtype), n, Cin, hgt, wid, reinterpret_cast<float*>(bi.p), ict, st);
+    if (res1) {
+      rc |= launch_nchw_to_chunks_f32(res1, to_pix(dtype), n, Cout, hgt, wid, reinterpret_cast<float*>(br.p), oct, st);
+      ep.res1 = view(br, oct, 0);
+      ep.alpha1 = alpha1;
+    }
+    if (!rc) rc = conv_direct_run(L, view(bi, ict, 0), n, hgt, wid, view(bo, oct, 0), oct, ep, st);
+    if (!rc) rc = launch_chunks_to_nchw_f32(reinterpret_cast<const float*>(bo.p), oct, n, Cout, hgt * up, wid * up, y, to_pix(dtype), st);
+  } else {
+    rc = launch_nchw_to_chunks(x, to_pix(dtype), n, Cin, hgt, wid, reinterpret_cast<__half*>(bi.p), ict, st);
+    if (res1) {
+      rc |= launch_nchw_to_chunks(res1, to_pix(dtype), n, Cout, hgt, wid, reinterpret_cast<__half*>(br.p), oct, st);
+      ep.res1 = view(br, oct, 0);
+      ep.alpha1 = alpha1;
+    }
+    if (!rc) rc = conv_layer_run(L, cache, view(bi, ict, 0), n, hgt, wid, view(bo, oct, 0), oct, ep, prop.multiProcessorCount, st);
+    if (!rc) rc = launch_chunks_to_nchw(reinterpret_cast<const __half*>(bo.p), oct, n, Cout, hgt * up, wid * up, y, to_pix(dtype), st);
+  }
+  g_launches.fetch_add(3 + (res1 ? 1 : 0), std::memory_order_relaxed);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cleanup();
+  if (rc) return fail(INNFER_E_CUDA, "conv3x3 launch failed (rc=" + std::to_string(rc) + ")");
+  if (e != cudaSuccess) return cuda_fail(e, "conv3x3 execution");
+  return 0;
+}
+
+int innfer_color_fix(const uint8_t* lr, int h, int w, const uint8_t* sr, int H, int W, uint8_t* out, void* stream) {
+  if (!lr || !sr || !out) return fail(INNFER_E_INVALID, "null argument");
+  int launches = 0;
+  int rc = color_fix_run(lr, h, w, sr, H, W, out, reinterpret_cast<cudaStream_t>(stream), &launches);
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
+  if (rc == -1) return fail(INNFER_E_INVALID, "color_fix: unsupported image shapes");
+  if (rc == -5) return fail(INNFER_E_NOMEM, "color_fix: scratch allocation failed");
+  if (rc) return fail(INNFER_E_CUDA, "color_fix launch failed");
+  return 0;
+}
+
+int innfer_color_fix_host(const uint8_t* lr, int h, int w, const uint8_t* sr, int H, int W, uint8_t* out, int device) {
+  if (!lr || !sr || !out) return fail(INNFER_E_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(device));
+  DevBuf dl, ds, dout;
+  const size_t lb = (size_t)h * w * 3, sb = (size_t)H * W * 3;
+  if (dl.ensure(lb) || ds.ensure(sb) || dout.ensure(sb)) {
+    dl.release(); ds.release(); dout.release();
+    return fail(INNFER_E_NOMEM, "allocation failed");
+  }
+  int rc = 0;
+  cudaError_t e = cudaMemcpy(dl.p, lr, lb, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(ds.p, sr, sb, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = innfer_color_fix(reinterpret_cast<const uint8_t*>(dl.p), h, w, reinterpret_cast<const uint8_t*>(ds.p), H, W,
+                          reinterpret_cast<uint8_t*>(dout.p), nullptr);
+    if (!rc) e = cudaMemcpy(out, dout.p, sb, cudaMemcpyDeviceToHost);
+  }
+  dl.release(); ds.release(); dout.release();
+  if (rc) return rc;
+  if (e != cudaSuccess) return cuda_fail(e, "color_fix_host");
+  return 0;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,210 @@
+#include "layers.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "tmap.cuh"
+
+namespace innfer {
+
+static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+int conv_layer_build(ConvLayer& L, const float* w, const float* bias, int Cout, int Cin, int up,
+                     std::string& err) {
+  if (up < 1 || up > 3) {
+    err = "unsupported upsample factor (1, 2 or 3 expected)";
+    return -2;
+  }
+  L.Cin = Cin;
+  L.Cout = Cout;
+  L.Cin_pad = (Cin + 15) / 16 * 16;
+  L.N = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : 64);
+  if (Cout > 64) {
+    err = "conv with more than 64 output channels is not supported by the tcgen05 kernel";
+    return -2;
+  }
+  L.up = up;
+  L.nphase = up * up;
+  const int kslabs = L.Cin_pad / 16;
+  const int N = L.N;
+
+  // per-axis folding tables: for phase a, kernel index k -> halo offset h (0..2)
+  int hof[3][3];
+  for (int a = 0; a < up; ++a)
+    for (int k = 0; k < 3; ++k) hof[a][k] = floordiv(a + k - 1, up) + 1;
+
+  std::vector<__half> packed;
+  L.max_taps = 0;
+  for (int a = 0; a < up; ++a) {
+    for (int b = 0; b < up; ++b) {
+      const int ph = a * up + b;
+      std::vector<int> hys, hxs;
+      for (int k = 0; k < 3; ++k) {
+        if (std::find(hys.begin(), hys.end(), hof[a][k]) == hys.end()) hys.push_back(hof[a][k]);
+        if (std::find(hxs.begin(), hxs.end(), hof[b][k]) == hxs.end()) hxs.push_back(hof[b][k]);
+      }
+      std::sort(hys.begin(), hys.end());
+      std::sort(hxs.begin(), hxs.end());
+      const int ntaps = (int)(hys.size() * hxs.size());
+      L.ph_ntaps[ph] = (uint8_t)ntaps;
+      L.ph_a[ph] = (uint8_t)a;
+      L.ph_b[ph] = (uint8_t)b;
+      L.ph_woff[ph] = (uint32_t)(packed.size() * sizeof(__half));
+      L.max_taps = std::max(L.max_taps, ntaps);
+      int t = 0;
+      for (int hy : hys)
+        for (int hx : hxs) {
+          L.tap_hy[ph][t] = (uint8_t)hy;
+          L.tap_hx[ph][t] = (uint8_t)hx;
+          ++t;
+        }
+      // folded weights for this phase: wf[tap][co][ci]
+      std::vector<float> wf((size_t)ntaps * Cout * Cin, 0.f);
+      t = 0;
+      for (int hy : hys)
+        for (int hx : hxs) {
+          for (int ky = 0; ky < 3; ++ky) {
+            if (hof[a][ky] != hy) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+              if (hof[b][kx] != hx) continue;
+              for (int co = 0; co < Cout; ++co)
+                for (int ci = 0; ci < Cin; ++ci)
+                  wf[((size_t)t * Cout + co) * Cin + ci] += w[(((size_t)co * Cin + ci) * 3 + ky) * 3 + kx];
+            }
+          }
+          ++t;
+        }
+      const size_t base = packed.size();
+      packed.resize(base + (size_t)kslabs * ntaps * 2 * N * 8);
+      size_t o = base;
+      for (int ks = 0; ks < kslabs; ++ks)
+        for (int tp = 0; tp < ntaps; ++tp)
+          for (int kc = 0; kc < 2; ++kc)
+            for (int n = 0; n < N; ++n)
+              for (int e = 0; e < 8; ++e) {
+                const int ci = ks * 16 + kc * 8 + e;
+                float v = 0.f;
+                if (n < Cout && ci < Cin) v = wf[((size_t)tp * Cout + n) * Cin + ci];
+                packed[o++] = __float2half_rn(v);
+              }
+    }
+  }
+  L.w_bytes = packed.size() * sizeof(__half);
+  std::vector<float> hb(N, 0.f);
+  if (bias)
+    for (int i = 0; i < Cout; ++i) hb[i] = bias[i];
+  L.h_w32.assign(w, w + (size_t)Cout * Cin * 9);
+  L.h_b32.assign(hb.begin(), hb.begin() + Cout);
+
+  cudaError_t e;
+  if ((e = cudaMalloc(&L.d_w, L.w_bytes)) != cudaSuccess ||
+      (e = cudaMalloc(&L.d_bias, N * sizeof(float))) != cudaSuccess ||
+      (e = cudaMemcpy(L.d_w, packed.data(), L.w_bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(L.d_bias, hb.data(), N * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+    err = std::string("cuda error while uploading weights: ") + cudaGetErrorString(e);
+    return -3;
+  }
+  return 0;
+}
+
+void conv_layer_free(ConvLayer& L) {
+  if (L.d_w) cudaFree(L.d_w);
+  if (L.d_bias) cudaFree(L.d_bias);
+  if (L.d_w32) cudaFree(L.d_w32);
+  L.d_w = nullptr;
+  L.d_bias = nullptr;
+  L.d_w32 = nullptr;
+}
+
+const CUtensorMap* TmapCache::get(const void* base, int B, int CT, int H, int W, int J, int& rc) {
+  auto key = std::make_tuple(base, B, CT, H, W, J);
+  auto it = maps_.find(key);
+  rc = 0;
+  if (it != maps_.end()) return &it->second->m;
+  Slot* s = new Slot();
+  rc = encode_act_tmap(&s->m, base, B, CT, H, W, J);
+  if (rc != 0) {
+    delete s;
+    return nullptr;
+  }
+  maps_[key] = s;
+  return &s->m;
+}
+
+int choose_J(int W, int N) {
+  int best = 1;
+  long best_cost = -1;
+  for (int J = 1; J <= 5; ++J) {
+    if (J * N > 512) break;
+    const int cps = (W + 8 * J - 1) / (8 * J);
+    const long cost = (long)cps * (8 * J + 2);
+    if (best_cost < 0 || cost <= best_cost) {
+      best_cost = cost;
+      best = J;
+    }
+  }
+  return best;
+}
+
+int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, int H, int W,
+                   ChunkView out, int out_nchunks, const Epilogue& ep, int num_sms,
+                   cudaStream_t stream) {
+  ConvTcParams p;
+  std::memset(&p, 0, sizeof(p));
+  const int N = L.N;
+  const int J = choose_J(W, N);
+  p.B = B;
+  p.H = H;
+  p.W = W;
+  p.in_chunk0 = in.chunk0;
+  p.kslabs = L.Cin_pad / 16;
+  p.J = J;
+  p.bands = (H + kPatchRows - 1) / kPatchRows;
+  p.cps = (W + 8 * J - 1) / (8 * J);
+  p.nphase = L.nphase;
+  p.up = L.up;
+  p.Hout = H * L.up;
+  p.Wout = W * L.up;
+  p.nbuf = (2 * J * N <= 512) ? 2 : 1;
+  int cols = p.nbuf * J * N, pw = 32;
+  while (pw < cols) pw <<= 1;
+  p.tmem_cols = pw;
+  const int stage_bytes = conv_tc_a_bytes(J) + conv_tc_w_bytes(N, L.max_taps);
+  int S = (232448 - 1024) / stage_bytes;
+  if (S > 8) S = 8;
+  if (S < 2) return -4;
+  p.stages = S;
+  p.out = out.base;
+  p.out_CT = out.CT;
+  p.out_chunk0 = out.chunk0;
+  p.out_nchunks = out_nchunks;
+  p.w = L.d_w;
+  p.bias = L.d_bias;
+  p.lrelu = ep.lrelu ? 1 : 0;
+  p.slope = ep.slope;
+  p.res1 = ep.res1.base;
+  p.res1_CT = ep.res1.CT;
+  p.res1_chunk0 = ep.res1.chunk0;
+  p.alpha1 = ep.alpha1;
+  p.res2 = ep.res2.base;
+  p.res2_CT = ep.res2.CT;
+  p.res2_chunk0 = ep.res2.chunk0;
+  p.alpha2 = ep.alpha2;
+  for (int i = 0; i < L.nphase; ++i) {
+    p.ph_woff[i] = L.ph_woff[i];
+    p.ph_ntaps[i] = L.ph_ntaps[i];
+    p.ph_a[i] = L.ph_a[i];
+    p.ph_b[i] = L.ph_b[i];
+    for (int t = 0; t < kMaxTaps; ++t) {
+      p.tap_hy[i][t] = L.tap_hy[i][t];
+      p.tap_hx[i][t] = L.tap_hx[i][t];
+    }
+  }
+  int rc = 0;
+  const CUtensorMap* tm = cache.get(in.base, B, in.CT, H, W, J, rc);
+  if (!tm) return rc ? rc : -5;
+  return launch_conv_tc(tm, p, N, num_sms, stream);
+}
+
+}  // namespace innfer

@@ -1,0 +1,79 @@
+// Host-side description of one fused convolution "layer" of the RRDB path and the helper that
+// launches it on planar-chunk tensors.  One ConvLayer corresponds to one reference conv_block
+// (architectures/block.py:213-254) optionally preceded by the nearest-neighbour Upsample of
+// upconv_block (block.py:286-361), which is folded into per-output-phase 2x2 weight sets.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "conv_tc.cuh"
+
+namespace innfer {
+
+// A view of `nchunks` channel chunks inside a planar-chunk buffer [B][CT][H][W][8] fp16.
+struct ChunkView {
+  __half* base = nullptr;  // buffer start
+  int CT = 0;              // chunks per tile in the buffer
+  int chunk0 = 0;          // first chunk of the view
+};
+
+struct ConvLayer {
+  int Cin = 0, Cout = 0;   // real channel counts
+  int Cin_pad = 0;         // multiple of 16
+  int N = 0;               // padded Cout: 16, 32 or 64
+  int up = 1;              // nearest-upsample factor folded in front of the conv
+  int nphase = 1;
+  uint32_t ph_woff[kMaxPhases] = {};
+  uint8_t ph_ntaps[kMaxPhases] = {};
+  uint8_t ph_a[kMaxPhases] = {}, ph_b[kMaxPhases] = {};
+  uint8_t tap_hy[kMaxPhases][kMaxTaps] = {};
+  uint8_t tap_hx[kMaxPhases][kMaxTaps] = {};
+  int max_taps = 0;
+  __half* d_w = nullptr;   // device, packed [phase][kslab][tap][2][N][8]
+  float* d_bias = nullptr; // device, [N]
+  size_t w_bytes = 0;
+  // fp32 copies (OIHW + bias) kept on the device for the fp32-mode direct kernel
+  float* d_w32 = nullptr;
+  std::vector<float> h_w32, h_b32;
+};
+
+struct Epilogue {
+  bool lrelu = false;
+  float slope = 0.2f;
+  ChunkView res1, res2;   // base == nullptr -> unused
+  float alpha1 = 1.f, alpha2 = 1.f;
+};
+
+// Build the packed fp16 weights (and phase tables) from OIHW fp32 weights.  `bias` may be null.
+// Returns 0 or a negative error code; `err` receives a message.
+int conv_layer_build(ConvLayer& L, const float* w_oihw, const float* bias, int Cout, int Cin,
+                     int up, std::string& err);
+void conv_layer_free(ConvLayer& L);
+
+// Cache of encoded TMA descriptors keyed by (base, B, CT, H, W, J).
+class TmapCache {
+ public:
+  const CUtensorMap* get(const void* base, int B, int CT, int H, int W, int J, int& rc);
+  void clear() { maps_.clear(); }
+
+ private:
+  struct alignas(64) Slot { CUtensorMap m; };
+  std::map<std::tuple<const void*, int, int, int, int, int>, Slot*> maps_;
+};
+
+// Pick the number of 8-pixel sub-patches per CTA for an image of width W and accumulator width N.
+int choose_J(int W, int N);
+
+// Launch one fused conv.  in: `L.Cin_pad/8` chunks starting at in.chunk0 of a [B][in.CT][H][W][8]
+// buffer; out: `out_nchunks` chunks at out.chunk0 of a [B][out.CT][up*H][up*W][8] buffer.
+int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, int H, int W,
+                   ChunkView out, int out_nchunks, const Epilogue& ep, int num_sms,
+                   cudaStream_t stream);
+
+}  // namespace innfer

@@ -1,0 +1,369 @@
+#include "pixel_ops.cuh"
+
+#include <cmath>
+
+namespace innfer {
+
+int make_tile_plan(int H, int W, int patch, float step, TilePlan& plan) {
+  if (H <= 0 || W <= 0 || patch <= 0) return -1;
+  int p = H < W ? H : W;
+  if (patch < p) p = patch;
+  plan.H = H;
+  plan.W = W;
+  plan.p = p;
+  // int(patch_H * step) with a Python float product (utils.py:351-352)
+  int s = (int)((double)p * (double)step);
+  if (s < 1) return -1;
+  plan.step = s;
+  auto fill = [&](int L, int* o, int& n) -> int {
+    n = 0;
+    const int cnt = (L - p) / s + 1;  // tensor.unfold window count
+    for (int i = 0; i < cnt; ++i) {
+      if (n >= kMaxTilesPerAxis) return -1;
+      o[n++] = i * s;
+    }
+    if ((L - p) % s != 0) {            // extra window anchored at the far edge (utils.py:355-362)
+      if (n >= kMaxTilesPerAxis) return -1;
+      o[n++] = L - p;
+    }
+    return 0;
+  };
+  if (fill(H, plan.ys, plan.nty)) return -2;
+  if (fill(W, plan.xs, plan.ntx)) return -2;
+  return 0;
+}
+
+namespace {
+
+struct TileGeom {
+  int H, W, p, nty, ntx;
+  int ys[kMaxTilesPerAxis];
+  int xs[kMaxTilesPerAxis];
+};
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p, size_t i);
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p, size_t i) {
+  return __half2float(p[i]);
+}
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p, size_t i) {
+  return p[i];
+}
+
+// one thread = one (tile, chunk, y, x): 16-byte store, reads are coalesced along x per channel plane
+template <typename E>
+__device__ __forceinline__ void store_chunk(E* dst, size_t chunk_index, const float (&f)[8]);
+template <>
+__device__ __forceinline__ void store_chunk<__half>(__half* dst, size_t i, const float (&f)[8]) {
+  __align__(16) __half v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = __float2half_rn(f[e]);
+  *reinterpret_cast<uint4*>(dst + i * 8) = *reinterpret_cast<const uint4*>(v);
+}
+template <>
+__device__ __forceinline__ void store_chunk<float>(float* dst, size_t i, const float (&f)[8]) {
+  float4* d = reinterpret_cast<float4*>(dst + i * 8);
+  d[0] = make_float4(f[0], f[1], f[2], f[3]);
+  d[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+template <typename E>
+__device__ __forceinline__ void load_chunk(const E* src, size_t chunk_index, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load_chunk<__half>(const __half* src, size_t i, float (&f)[8]) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(src + i * 8);
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 v = __half22float2(h[e]);
+    f[2 * e] = v.x;
+    f[2 * e + 1] = v.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load_chunk<float>(const float* src, size_t i, float (&f)[8]) {
+  const float4* s = reinterpret_cast<const float4*>(src + i * 8);
+  const float4 a = s[0], b = s[1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+template <typename T, bool U8, typename E>
+__global__ void image_to_tiles_kernel(const void* __restrict__ src_, int C, const __grid_constant__ TileGeom g,
+                                      int t0, int nt, E* __restrict__ dst, int CT) {
+  const int p = g.p;
+  const size_t total = (size_t)nt * CT * p * p;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % p);
+    size_t r = i / p;
+    const int y = (int)(r % p);
+    r /= p;
+    const int ch = (int)(r % CT);
+    const int t = (int)(r / CT) + t0;
+    const int sy = g.ys[t / g.ntx] + y;
+    const int sx = g.xs[t % g.ntx] + x;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = ch * 8 + e;
+      float f = 0.f;
+      if (c < C) {
+        if (U8) {
+          // HWC BGR uint8 -> RGB /255 (np2tensor + bgr_to_rgb, utils.py:177-187, colors.py:5-11)
+          const uint8_t* s8 = reinterpret_cast<const uint8_t*>(src_);
+          f = (float)s8[((size_t)sy * g.W + sx) * C + (C - 1 - c)] / 255.0f;
+        } else {
+          f = load_as_float<T>(reinterpret_cast<const T*>(src_), ((size_t)c * g.H + sy) * g.W + sx);
+        }
+      }
+      v[e] = f;
+    }
+    store_chunk<E>(dst, i, v);
+  }
+}
+
+struct BlendGeom {
+  int Hs, Ws;      // full output size
+  int P;           // HR tile size
+  int eff;         // int(0.5 * P)
+  int overlap;
+  int nty, ntx;
+  int oys[kMaxTilesPerAxis];
+  int oxs[kMaxTilesPerAxis];
+};
+
+// torch.linspace(0.1, 1.0, n) in fp32 (symmetric evaluation), then ones, then linspace(1.0, 0.1, n)
+__device__ __forceinline__ float blend_profile(int i, int P, int n) {
+  const float step = n > 1 ? (1.0f - 0.1f) / (float)(n - 1) : 0.f;
+  if (i < n) {
+    return (i < n / 2) ? 0.1f + step * (float)i : 1.0f - step * (float)(n - 1 - i);
+  }
+  if (i >= P - n) {
+    const int k = i - (P - n);
+    const float dstep = n > 1 ? (0.1f - 1.0f) / (float)(n - 1) : 0.f;
+    return (k < n / 2) ? 1.0f + dstep * (float)k : 0.1f - dstep * (float)(n - 1 - k);
+  }
+  return 1.0f;
+}
+
+__device__ __forceinline__ float quant_u8(float v) {
+  // np.clip(255 * x, 0, 255).round() -- round half to even (utils.py:245)
+  v = fminf(fmaxf(v * 255.0f, 0.f), 255.0f);
+  return rintf(v);
+}
+
+template <int DT, typename E>
+__global__ void blend_kernel(const E* __restrict__ tiles, int CT, const __grid_constant__ BlendGeom g, int C,
+                             void* __restrict__ dst) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y;
+  if (X >= g.Ws) return;
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  float wsum = 0.f;
+  const int ty_hi = min(Y / g.eff, g.nty - 1);
+  const int ty_lo = max(0, (Y - g.P) / g.eff);
+  const int tx_hi = min(X / g.eff, g.ntx - 1);
+  const int tx_lo = max(0, (X - g.P) / g.eff);
+  for (int pass_y = 0; pass_y < 2; ++pass_y) {
+    // regular tiles first (ascending), then the edge-anchored last tile if it was not visited
+    const int ya = pass_y == 0 ? ty_lo : g.nty - 1;
+    const int yb = pass_y == 0 ? ty_hi : (ty_hi < g.nty - 1 ? g.nty - 1 : g.nty - 2);
+    for (int ty = ya; ty <= yb; ++ty) {
+      const int ly = Y - g.oys[ty];
+      if (ly < 0 || ly >= g.P) continue;
+      const float wy = blend_profile(ly, g.P, g.overlap);
+      for (int pass_x = 0; pass_x < 2; ++pass_x) {
+        const int xa = pass_x == 0 ? tx_lo : g.ntx - 1;
+        const int xb = pass_x == 0 ? tx_hi : (tx_hi < g.ntx - 1 ? g.ntx - 1 : g.ntx - 2);
+        for (int tx = xa; tx <= xb; ++tx) {
+          const int lx = X - g.oxs[tx];
+          if (lx < 0 || lx >= g.P) continue;
+          const float w = blend_profile(lx, g.P, g.overlap) * wy;
+          const size_t t = (size_t)ty * g.ntx + tx;
+          float f[8];
+          load_chunk<E>(tiles, (t * CT * g.P + ly) * g.P + lx, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += f[e] * w;
+          wsum += w;
+        }
+      }
+    }
+  }
+  const size_t plane = (size_t)g.Hs * g.Ws;
+  const size_t pix = (size_t)Y * g.Ws + X;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (c >= C) break;
+    const float v = acc[c] / wsum;
+    if (DT == kF16) reinterpret_cast<__half*>(dst)[c * plane + pix] = __float2half_rn(v);
+    if (DT == kF32) reinterpret_cast<float*>(dst)[c * plane + pix] = v;
+    if (DT == kU8) reinterpret_cast<uint8_t*>(dst)[pix * C + (C - 1 - c)] = (uint8_t)quant_u8(v);
+  }
+}
+
+template <typename T, typename E>
+__global__ void nchw_to_chunks_kernel(const T* __restrict__ src, int n, int C, int H, int W,
+                                      E* __restrict__ dst, int CT) {
+  const size_t plane = (size_t)H * W;
+  const size_t total = (size_t)n * CT * plane;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i % plane;
+    const size_t r = i / plane;
+    const int ch = (int)(r % CT);
+    const size_t b = r / CT;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = ch * 8 + e;
+      v[e] = c < C ? load_as_float<T>(src, (b * C + c) * plane + pix) : 0.f;
+    }
+    store_chunk<E>(dst, i, v);
+  }
+}
+
+template <typename T, typename E>
+__global__ void chunks_to_nchw_kernel(const E* __restrict__ src, int CT, int n, int C, int H, int W,
+                                      T* __restrict__ dst) {
+  const size_t plane = (size_t)H * W;
+  const size_t total = (size_t)n * C * plane;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i % plane;
+    const size_t r = i / plane;
+    const int c = (int)(r % C);
+    const size_t b = r / C;
+    const float v = load_as_float<E>(src, ((b * CT + c / 8) * plane + pix) * 8 + (c & 7));
+    if (sizeof(T) == 2) reinterpret_cast<__half*>(dst)[i] = __float2half_rn(v);
+    else reinterpret_cast<float*>(dst)[i] = v;
+  }
+}
+
+int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = 148 * 16;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+template <typename E>
+int image_to_tiles_impl(const void* src, PixelDType st, int C, const TilePlan& plan, int t0, int nt, E* dst,
+                        int CT, cudaStream_t stream) {
+  TileGeom g;
+  g.H = plan.H;
+  g.W = plan.W;
+  g.p = plan.p;
+  g.nty = plan.nty;
+  g.ntx = plan.ntx;
+  for (int i = 0; i < kMaxTilesPerAxis; ++i) {
+    g.ys[i] = plan.ys[i];
+    g.xs[i] = plan.xs[i];
+  }
+  const size_t total = (size_t)nt * CT * plan.p * plan.p;
+  const int block = 256, grid = grid_for(total, block);
+  if (st == kF16)
+    image_to_tiles_kernel<__half, false, E><<<grid, block, 0, stream>>>(src, C, g, t0, nt, dst, CT);
+  else if (st == kF32)
+    image_to_tiles_kernel<float, false, E><<<grid, block, 0, stream>>>(src, C, g, t0, nt, dst, CT);
+  else
+    image_to_tiles_kernel<float, true, E><<<grid, block, 0, stream>>>(src, C, g, t0, nt, dst, CT);
+  return (int)cudaGetLastError();
+}
+
+template <typename E>
+int blend_impl(const E* tiles, int CT, const TilePlan& plan, int scale, int C, void* dst, PixelDType dt,
+               cudaStream_t stream) {
+  if (C > 8) return -1;
+  BlendGeom g;
+  g.Hs = plan.H * scale;
+  g.Ws = plan.W * scale;
+  g.P = plan.p * scale;
+  // recompose_tensor (utils.py:396-399): overlap = scale*int(round((1-step)*(P/scale))), step 0.5;
+  // Python's round() is round-half-to-even, as is nearbyint in the default rounding mode.
+  g.overlap = scale * (int)std::nearbyint(0.5 * ((double)g.P / (double)scale));
+  g.eff = (int)(0.5 * (double)g.P);
+  if (g.P - 2 * g.overlap < 0 || g.eff < 1) return -2;
+  g.nty = plan.nty;
+  g.ntx = plan.ntx;
+  for (int i = 0; i < plan.nty; ++i) {
+    const int o = i * g.eff;
+    g.oys[i] = o < g.Hs - g.P ? o : g.Hs - g.P;
+  }
+  for (int i = 0; i < plan.ntx; ++i) {
+    const int o = i * g.eff;
+    g.oxs[i] = o < g.Ws - g.P ? o : g.Ws - g.P;
+  }
+  dim3 block(256), grid((g.Ws + 255) / 256, g.Hs);
+  if (dt == kF16) blend_kernel<kF16, E><<<grid, block, 0, stream>>>(tiles, CT, g, C, dst);
+  else if (dt == kF32) blend_kernel<kF32, E><<<grid, block, 0, stream>>>(tiles, CT, g, C, dst);
+  else blend_kernel<kU8, E><<<grid, block, 0, stream>>>(tiles, CT, g, C, dst);
+  return (int)cudaGetLastError();
+}
+
+template <typename E>
+int nchw_to_chunks_impl(const void* src, PixelDType st, int n, int C, int H, int W, E* dst, int CT,
+                        cudaStream_t stream) {
+  const size_t total = (size_t)n * CT * H * W;
+  const int block = 256, grid = grid_for(total, block);
+  if (st == kF16)
+    nchw_to_chunks_kernel<__half, E><<<grid, block, 0, stream>>>(reinterpret_cast<const __half*>(src), n, C, H, W, dst, CT);
+  else if (st == kF32)
+    nchw_to_chunks_kernel<float, E><<<grid, block, 0, stream>>>(reinterpret_cast<const float*>(src), n, C, H, W, dst, CT);
+  else
+    return -1;
+  return (int)cudaGetLastError();
+}
+
+template <typename E>
+int chunks_to_nchw_impl(const E* src, int CT, int n, int C, int H, int W, void* dst, PixelDType dt,
+                        cudaStream_t stream) {
+  const size_t total = (size_t)n * C * H * W;
+  const int block = 256, grid = grid_for(total, block);
+  if (dt == kF16)
+    chunks_to_nchw_kernel<__half, E><<<grid, block, 0, stream>>>(src, CT, n, C, H, W, reinterpret_cast<__half*>(dst));
+  else if (dt == kF32)
+    chunks_to_nchw_kernel<float, E><<<grid, block, 0, stream>>>(src, CT, n, C, H, W, reinterpret_cast<float*>(dst));
+  else
+    return -1;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int launch_image_to_tiles(const void* src, PixelDType st, int C, const TilePlan& plan, int t0, int nt,
+                          __half* dst, int CT, cudaStream_t stream) {
+  return image_to_tiles_impl<__half>(src, st, C, plan, t0, nt, dst, CT, stream);
+}
+int launch_image_to_tiles_f32(const void* src, PixelDType st, int C, const TilePlan& plan, int t0, int nt,
+                              float* dst, int CT, cudaStream_t stream) {
+  return image_to_tiles_impl<float>(src, st, C, plan, t0, nt, dst, CT, stream);
+}
+int launch_blend(const __half* tiles, int CT, const TilePlan& plan, int scale, int C, void* dst,
+                 PixelDType dt, cudaStream_t stream) {
+  return blend_impl<__half>(tiles, CT, plan, scale, C, dst, dt, stream);
+}
+int launch_blend_f32(const float* tiles, int CT, const TilePlan& plan, int scale, int C, void* dst,
+                     PixelDType dt, cudaStream_t stream) {
+  return blend_impl<float>(tiles, CT, plan, scale, C, dst, dt, stream);
+}
+int launch_nchw_to_chunks(const void* src, PixelDType st, int n, int C, int H, int W, __half* dst,
+                          int CT, cudaStream_t stream) {
+  return nchw_to_chunks_impl<__half>(src, st, n, C, H, W, dst, CT, stream);
+}
+int launch_nchw_to_chunks_f32(const void* src, PixelDType st, int n, int C, int H, int W, float* dst,
+                              int CT, cudaStream_t stream) {
+  return nchw_to_chunks_impl<float>(src, st, n, C, H, W, dst, CT, stream);
+}
+int launch_chunks_to_nchw(const __half* src, int CT, int n, int C, int H, int W, void* dst,
+                          PixelDType dt, cudaStream_t stream) {
+  return chunks_to_nchw_impl<__half>(src, CT, n, C, H, W, dst, dt, stream);
+}
+int launch_chunks_to_nchw_f32(const float* src, int CT, int n, int C, int H, int W, void* dst,
+                              PixelDType dt, cudaStream_t stream) {
+  return chunks_to_nchw_impl<float>(src, CT, n, C, H, W, dst, dt, stream);
+}
+
+}  // namespace innfer

@@ -1,0 +1,209 @@
+"""Bring-up / diagnostics script for the GPU box (not collected by pytest).
+
+    python tests/gpu_bringup.py --stage conv1|convs|net|time
+
+Each stage prints PASS/FAIL lines with error statistics so that one gpurun call tells which layer of
+the stack (TMA box, UMMA descriptors, epilogue, schedule) is wrong.
+"""
+import argparse
+import ctypes
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from innfer_b200 import _native as N  # noqa: E402
+from oracle import rrdb_oracle as O  # noqa: E402
+
+dev = torch.device("cuda:0")
+
+
+def conv_case(cin, cout, h, w, n=1, up=1, lrelu=False, res=False, fp32=False, seed=0, verbose=True):
+    lib = N.load()
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.rand(n, cin, h, w, generator=g) * 2 - 1)
+    wgt = (torch.rand(cout, cin, 3, 3, generator=g) * 2 - 1) / np.sqrt(cin * 9.0) * 2
+    b = torch.rand(cout, generator=g) - 0.5
+    r = (torch.rand(n, cout, h * up, w * up, generator=g) * 2 - 1) if res else None
+    dt = torch.float32 if fp32 else torch.float16
+    xd = x.to(dev, dt)
+    rd = r.to(dev, dt) if res else None
+    y = torch.empty(n, cout, h * up, w * up, device=dev, dtype=dt)
+    wc = wgt.contiguous().numpy()
+    bc = b.contiguous().numpy()
+    rc = lib.innfer_conv3x3(xd.data_ptr(), n, cin, h, w, wc.ctypes.data, bc.ctypes.data, cout, up,
+                            int(lrelu), rd.data_ptr() if res else None, 0.2, y.data_ptr(),
+                            N.INNFER_F32 if fp32 else N.INNFER_F16, int(fp32), None)
+    if rc != 0:
+        print("FAIL rc=%d %s" % (rc, N.last_error()))
+        return False
+    torch.cuda.synchronize()
+    # reference in fp64 on the (rounded) inputs the kernel saw
+    xr = xd.double()
+    wr = (wgt.to(dev, dt)).double() if not fp32 else wgt.to(dev).double()
+    if up > 1:
+        xr = F.interpolate(xr, scale_factor=float(up), mode="nearest")
+    ref = F.conv2d(xr, wr, b.to(dev).double(), padding=1)
+    if lrelu:
+        ref = F.leaky_relu(ref, 0.2)
+    if res:
+        ref = ref * 0.2 + rd.double()
+    err = (y.double() - ref).abs()
+    tol = 2e-5 if fp32 else 2e-2
+    scale = ref.abs().max().item()
+    ok = bool(err.max().item() <= tol * max(scale, 1.0)) and bool(torch.isfinite(y).all())
+    tag = "PASS" if ok else "FAIL"
+    print("%s conv cin=%d cout=%d %dx%d n=%d up=%d lrelu=%d res=%d fp32=%d: max_err=%.3e mean_err=%.3e ref_max=%.3f"
+          % (tag, cin, cout, h, w, n, up, lrelu, res, fp32, err.max().item(), err.mean().item(), scale))
+    if not ok and verbose:
+        bad = err > tol * max(scale, 1.0)
+        print("   bad fraction %.4f" % bad.float().mean().item())
+        e = err[0]
+        print("   per-out-channel max err:", [round(v, 3) for v in e.amax(dim=(1, 2)).tolist()][:16])
+        ey = e.amax(dim=(0, 2))
+        ex = e.amax(dim=(0, 1))
+        print("   per-row max err:", [round(v, 3) for v in ey.tolist()][:40])
+        print("   per-col max err:", [round(v, 3) for v in ex.tolist()][:48])
+        print("   y[0,0,:4,:8]  ", y[0, 0, :4, :8].float().cpu().numpy().round(3).tolist())
+        print("   ref[0,0,:4,:8]", ref[0, 0, :4, :8].float().cpu().numpy().round(3).tolist())
+    return ok
+
+
+def stage_conv1():
+    ok = conv_case(64, 32, 16, 40)
+    ok &= conv_case(16, 32, 16, 8)
+    return ok
+
+
+def stage_convs():
+    ok = True
+    for cin, cout in ((64, 32), (96, 32), (128, 32), (160, 32), (192, 64)):
+        ok &= conv_case(cin, cout, 40, 48, lrelu=cout == 32, res=cout == 64)
+    ok &= conv_case(3, 64, 33, 47)
+    ok &= conv_case(64, 3, 50, 70)
+    ok &= conv_case(64, 64, 37, 53, n=3, lrelu=True)
+    ok &= conv_case(64, 64, 24, 40, up=2, lrelu=True)
+    ok &= conv_case(64, 64, 19, 21, up=2, lrelu=True)
+    ok &= conv_case(64, 64, 17, 23, up=3, lrelu=True)
+    ok &= conv_case(32, 32, 20, 20, lrelu=True)
+    ok &= conv_case(64, 32, 200, 200, n=2, lrelu=True)
+    # fp32 direct kernel
+    ok &= conv_case(64, 32, 40, 48, lrelu=True, fp32=True)
+    ok &= conv_case(192, 64, 21, 35, res=True, fp32=True)
+    ok &= conv_case(3, 64, 33, 47, fp32=True)
+    ok &= conv_case(64, 3, 30, 30, fp32=True)
+    ok &= conv_case(64, 64, 19, 21, up=2, lrelu=True, fp32=True)
+    ok &= conv_case(64, 64, 17, 23, up=3, lrelu=True, fp32=True)
+    return ok
+
+
+def make_handle(sd, fp16=True, scale=None):
+    lib = N.load()
+    p = O.infer_params(sd)
+    cfg = N.RRDBCfg(p["in_nc"], p["out_nc"], p["nf"], p["nb"], 32, scale or p["scale"], 0, int(fp16))
+    h = ctypes.c_void_p()
+    N.check(lib.innfer_rrdb_create(ctypes.byref(cfg), 0, ctypes.byref(h)))
+    for k, v in sd.items():
+        a = v.detach().cpu().float().contiguous().numpy()
+        shp = (ctypes.c_int64 * a.ndim)(*a.shape)
+        N.check(lib.innfer_rrdb_load(h, k.encode(), a.ctypes.data, shp, a.ndim))
+    N.check(lib.innfer_rrdb_finalize(h))
+    return h
+
+
+def stage_net():
+    lib = N.load()
+    ok = True
+    for scale, nb, hw, fp16 in ((4, 2, (40, 56), True), (1, 2, (48, 40), True), (2, 1, (32, 32), True),
+                                (4, 23, (64, 64), True), (4, 2, (40, 56), False), (3, 1, (24, 24), True)):
+        sd = O.make_state_dict(scale=scale, nb=nb, seed=1)
+        sdd = {k: v.to(dev) for k, v in sd.items()}
+        h = make_handle(sd, fp16=fp16)
+        img = np.random.default_rng(3).integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
+        x = O.np2tensor(img).to(dev)
+        ref = O.rrdbnet_forward(sdd, x, scale)
+        dt = torch.float16 if fp16 else torch.float32
+        xin = x.to(dt).contiguous()
+        y = torch.empty(1, 3, scale * hw[0], scale * hw[1], device=dev, dtype=dt)
+        rc = lib.innfer_rrdb_forward(h, xin.data_ptr(), 1, hw[0], hw[1], y.data_ptr(),
+                                     N.INNFER_F16 if fp16 else N.INNFER_F32, None)
+        if rc:
+            print("FAIL forward rc=%d %s" % (rc, N.last_error()))
+            ok = False
+            continue
+        torch.cuda.synchronize()
+        err = (y.float() - ref).abs()
+        u8a = O.tensor2np(y)
+        u8b = O.tensor2np(ref)
+        du8 = np.abs(u8a.astype(int) - u8b.astype(int))
+        mse = np.mean((u8a.astype(float) - u8b.astype(float)) ** 2)
+        psnr = 99.0 if mse == 0 else 10 * np.log10(255 ** 2 / mse)
+        rel = (err.max() / ref.abs().max()).item()
+        good = du8.max() <= 1 and psnr >= 50 and (fp16 or rel < 1e-4)
+        ok &= bool(good)
+        print("%s net scale=%d nb=%d %s fp16=%d: max_abs=%.3e rel=%.3e u8_maxdiff=%d psnr=%.1f unclipped=%.2f"
+              % ("PASS" if good else "FAIL", scale, nb, hw, fp16, err.max().item(), rel, du8.max(), psnr,
+                 ((u8b > 0) & (u8b < 255)).mean()))
+        # chop path on the same image with a small patch
+        y2 = torch.empty_like(y)
+        rc = lib.innfer_rrdb_chop_forward(h, xin.data_ptr(), hw[0], hw[1], 32 if scale != 3 else 200, 0.5, y2.data_ptr(),
+                                          N.INNFER_F16 if fp16 else N.INNFER_F32, None)
+        if rc:
+            print("FAIL chop rc=%d %s" % (rc, N.last_error()))
+            ok = False
+        else:
+            torch.cuda.synchronize()
+            sdc = {k: v for k, v in sd.items()}
+            refc = O.chop_forward(sdc, x.cpu(), patch_size=32 if scale != 3 else 200)
+            e2 = (y2.float().cpu() - refc).abs()
+            d2 = np.abs(O.tensor2np(y2).astype(int) - O.tensor2np(refc).astype(int))
+            good = d2.max() <= 1
+            ok &= bool(good)
+            print("%s chop scale=%d nb=%d %s fp16=%d: max_abs=%.3e u8_maxdiff=%d"
+                  % ("PASS" if good else "FAIL", scale, nb, hw, fp16, e2.max().item(), d2.max()))
+        lib.innfer_rrdb_destroy(h)
+    return ok
+
+
+def stage_time():
+    lib = N.load()
+    sd = O.make_state_dict(scale=4, nb=23, seed=0)
+    h = make_handle(sd, fp16=True)
+    H, W = 1080, 1920
+    img = np.random.default_rng(0).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    din = torch.from_numpy(img).to(dev)
+    dout = torch.empty(4 * H, 4 * W, 3, dtype=torch.uint8, device=dev)
+    flop = 190 * 200 * 200 * O.flop_per_lr_pixel(4, 23, 64)
+    for mb in (38, 19, 10):
+        lib.innfer_rrdb_set_max_batch(h, mb)
+        for it in range(3):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = lib.innfer_rrdb_upscale_u8_device(h, din.data_ptr(), H, W, 200, 0.5, dout.data_ptr(), None)
+            e1.record()
+            torch.cuda.synchronize()
+            if rc:
+                print("FAIL rc=%d %s" % (rc, N.last_error()))
+                return False
+            ms = e0.elapsed_time(e1)
+            print("time 1080p max_batch=%d iter=%d: %.1f ms  %.1f out-Mpix/s  %.1f TFLOP/s" %
+                  (mb, it, ms, 16 * H * W / ms / 1e3, flop / ms / 1e9))
+    print("launches", N.kernel_launches())
+    print("out mean", dout.float().mean().item())
+    return True
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--stage", required=True)
+    a = ap.parse_args()
+    t0 = time.time()
+    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time}[a.stage]()
+    print("STAGE %s %s (%.1fs)" % (a.stage, "OK" if ok else "FAILED", time.time() - t0))
+    sys.exit(0 if ok else 1)
