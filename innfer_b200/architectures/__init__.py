@@ -1,0 +1,16 @@
+"""get_network -- mirror of the reference's architectures/__init__.py:5-40 for the hot path."""
+
+_OUT_OF_SCOPE = ("sr_resnet", "mrrdb_net", "ppon", "pan_net", "unet_net", "resnet_net", "wbcunet_net")
+
+
+def get_network(opt_net):
+    """Instantiate the network described by ``opt_net`` (``type`` + constructor kwargs)."""
+    kind = opt_net.pop("type").lower()
+    if kind == "rrdb_net":
+        from . import RRDBNet_arch
+        return RRDBNet_arch.RRDBNet(**opt_net)
+    if kind in _OUT_OF_SCOPE:
+        raise NotImplementedError(
+            "Model [%s] exists in the reference but is outside the B200 RRDB hot-path scope "
+            "(SURVEY.md section 8f)" % kind)
+    raise NotImplementedError("Model [{:s}] not recognized".format(kind))

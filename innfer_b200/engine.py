@@ -1,0 +1,149 @@
+"""Python handle over the native RRDB engine (include/innfer_b200.h).
+
+torch is plumbing here: it owns device memory and streams; every FLOP of the CUDA path runs in
+libinnfer_b200.so.  Nothing in this module falls back to torch ops on failure.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _dtype_code(dtype):
+    if dtype == torch.float16:
+        return N.INNFER_F16
+    if dtype == torch.float32:
+        return N.INNFER_F32
+    raise TypeError("innfer_b200: tensors must be float16 or float32, got %s" % dtype)
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class RRDBEngine:
+    """One native network handle (weights repacked for the sm_100a kernels) on one CUDA device."""
+
+    def __init__(self, cfg, device, fp16=True):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("RRDBEngine needs a CUDA device; the -cpu mode runs the torch modules instead")
+        if not torch.cuda.is_available():
+            raise RuntimeError("innfer_b200: CUDA is not available and there is no CPU fallback for the engine")
+        self.lib = N.load()
+        self.device = device
+        self.index = device.index if device.index is not None else torch.cuda.current_device()
+        self.fp16 = bool(fp16)
+        self.cfg = dict(cfg)
+        c = N.RRDBCfg(cfg["in_nc"], cfg["out_nc"], cfg["nf"], cfg["nb"], cfg.get("gc", 32), cfg["scale"],
+                      int(bool(cfg.get("plus", False))), int(self.fp16))
+        self._h = ctypes.c_void_p()
+        N.check(self.lib.innfer_rrdb_create(ctypes.byref(c), self.index, ctypes.byref(self._h)))
+        self._finalized = False
+
+    # -- construction ----------------------------------------------------------------------------
+    @classmethod
+    def from_state_dict(cls, sd, cfg, device, fp16=True):
+        eng = cls(cfg, device, fp16)
+        try:
+            for key, val in sd.items():
+                eng.load(key, val)
+            eng.finalize()
+        except Exception:
+            eng.close()
+            raise
+        return eng
+
+    @classmethod
+    def from_module(cls, module, device, fp16=True):
+        """Build from an architectures.RRDBNet_arch.RRDBNet (uses its reference-named state dict)."""
+        return cls.from_state_dict(module.state_dict(), module.cfg, device, fp16)
+
+    def load(self, key, tensor):
+        a = np.ascontiguousarray(tensor.detach().to("cpu", torch.float32).numpy())
+        shape = (ctypes.c_int64 * a.ndim)(*a.shape)
+        N.check(self.lib.innfer_rrdb_load(self._h, key.encode(), a.ctypes.data_as(ctypes.c_void_p), shape, a.ndim))
+
+    def finalize(self):
+        N.check(self.lib.innfer_rrdb_finalize(self._h))
+        self._finalized = True
+
+    def set_max_batch(self, n):
+        N.check(self.lib.innfer_rrdb_set_max_batch(self._h, int(n)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.innfer_rrdb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- execution -------------------------------------------------------------------------------
+    def _check_input(self, x):
+        if x.dim() != 4 or x.shape[1] != self.cfg["in_nc"]:
+            raise ValueError("expected [N,%d,H,W] input, got %s" % (self.cfg["in_nc"], tuple(x.shape)))
+        if not x.is_cuda or (x.device.index is not None and x.device.index != self.index):
+            raise ValueError("input must live on %s" % self.device)
+        return x.contiguous()
+
+    def forward(self, x):
+        """RRDBNet.forward on a batch: [N,in_nc,h,w] -> [N,out_nc,s*h,s*w], same dtype."""
+        x = self._check_input(x)
+        n, _, h, w = x.shape
+        s = self.cfg["scale"]
+        y = torch.empty((n, self.cfg["out_nc"], s * h, s * w), dtype=x.dtype, device=x.device)
+        N.check(self.lib.innfer_rrdb_forward(self._h, x.data_ptr(), n, h, w, y.data_ptr(), _dtype_code(x.dtype),
+                                             _stream_ptr(x.device)))
+        return y
+
+    def chop_forward(self, x, patch_size=200, step=0.5):
+        """Model.chop_forward (tile, forward, blend) on a [1,in_nc,H,W] image in one native call."""
+        x = self._check_input(x)
+        if x.shape[0] != 1:
+            raise ValueError("chop_forward expects batch size 1 (run.py:178-181 squeezes the batch)")
+        _, _, H, W = x.shape
+        s = self.cfg["scale"]
+        y = torch.empty((1, self.cfg["out_nc"], s * H, s * W), dtype=x.dtype, device=x.device)
+        N.check(self.lib.innfer_rrdb_chop_forward(self._h, x.data_ptr(), H, W, int(patch_size), float(step),
+                                                  y.data_ptr(), _dtype_code(x.dtype), _stream_ptr(x.device)))
+        return y
+
+    def upscale_u8(self, img, patch_size=200, step=0.5, out=None):
+        """np2tensor -> chop_forward -> tensor2np fused.  ``img``: HOST uint8 HWC BGR array (numpy, or
+        a pinned CPU torch tensor); returns a HOST uint8 array [s*H, s*W, 3].  H2D and D2H copies are
+        part of the call."""
+        if isinstance(img, torch.Tensor):
+            src_ptr, (H, W, C) = img.data_ptr(), img.shape
+            if img.dtype != torch.uint8 or img.is_cuda or not img.is_contiguous():
+                raise ValueError("expected a contiguous CPU uint8 tensor")
+        else:
+            img = np.ascontiguousarray(img)
+            if img.dtype != np.uint8 or img.ndim != 3:
+                raise ValueError("expected a uint8 HWC image")
+            src_ptr, (H, W, C) = img.ctypes.data, img.shape
+        if C != 3:
+            raise ValueError("the uint8 path handles 3-channel images")
+        s = self.cfg["scale"]
+        if out is None:
+            out = np.empty((s * H, s * W, 3), dtype=np.uint8)
+        dst_ptr = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
+        with torch.cuda.device(self.index):
+            N.check(self.lib.innfer_rrdb_upscale_u8(self._h, src_ptr, H, W, int(patch_size), float(step), dst_ptr,
+                                                    _stream_ptr(self.device)))
+        return out
+
+    def upscale_u8_device(self, img, patch_size=200, step=0.5, out=None):
+        """Same with DEVICE uint8 tensors (no copies, no synchronisation)."""
+        H, W, _ = img.shape
+        s = self.cfg["scale"]
+        if out is None:
+            out = torch.empty((s * H, s * W, 3), dtype=torch.uint8, device=img.device)
+        N.check(self.lib.innfer_rrdb_upscale_u8_device(self._h, img.data_ptr(), H, W, int(patch_size), float(step),
+                                                       out.data_ptr(), _stream_ptr(img.device)))
+        return out

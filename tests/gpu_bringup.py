@@ -21,6 +21,8 @@ from innfer_b200 import _native as N  # noqa: E402
 from oracle import rrdb_oracle as O  # noqa: E402
 
 dev = torch.device("cuda:0")
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def conv_case(cin, cout, h, w, n=1, up=1, lrelu=False, res=False, fp32=False, seed=0, verbose=True):
@@ -123,7 +125,7 @@ def stage_net():
                                 (4, 23, (64, 64), True), (4, 2, (40, 56), False), (3, 1, (24, 24), True)):
         sd = O.make_state_dict(scale=scale, nb=nb, seed=1)
         sdd = {k: v.to(dev) for k, v in sd.items()}
-        h = make_handle(sd, fp16=fp16)
+        h = make_handle(sd, fp16=fp16, scale=scale)
         img = np.random.default_rng(3).integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
         x = O.np2tensor(img).to(dev)
         ref = O.rrdbnet_forward(sdd, x, scale)
@@ -159,7 +161,9 @@ def stage_net():
         else:
             torch.cuda.synchronize()
             sdc = {k: v for k, v in sd.items()}
-            refc = O.chop_forward(sdc, x.cpu(), patch_size=32 if scale != 3 else 200)
+            refc = O.chop_forward(sdc, x.cpu(), patch_size=32 if scale != 3 else 200,
+                                  forward=lambda t: O.rrdbnet_forward(sdc, t, scale)) if scale != 3 else \
+                O.rrdbnet_forward(sdc, x.cpu(), scale)
             e2 = (y2.float().cpu() - refc).abs()
             d2 = np.abs(O.tensor2np(y2).astype(int) - O.tensor2np(refc).astype(int))
             good = d2.max() <= 1
@@ -168,6 +172,20 @@ def stage_net():
                   % ("PASS" if good else "FAIL", scale, nb, hw, fp16, e2.max().item(), d2.max()))
         lib.innfer_rrdb_destroy(h)
     return ok
+
+
+def stage_prof():
+    """One 800x1000 frame (63 tiles) for ncu: launch list and full captures."""
+    lib = N.load()
+    sd = O.make_state_dict(scale=4, nb=23, seed=0)
+    h = make_handle(sd, fp16=True)
+    H, W = 800, 1000
+    img = np.random.default_rng(0).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    din = torch.from_numpy(img).to(dev)
+    dout = torch.empty(4 * H, 4 * W, 3, dtype=torch.uint8, device=dev)
+    N.check(lib.innfer_rrdb_upscale_u8_device(h, din.data_ptr(), H, W, 200, 0.5, dout.data_ptr(), None))
+    torch.cuda.synchronize()
+    return True
 
 
 def stage_time():
@@ -204,6 +222,6 @@ if __name__ == "__main__":
     ap.add_argument("--stage", required=True)
     a = ap.parse_args()
     t0 = time.time()
-    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time}[a.stage]()
+    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof}[a.stage]()
     print("STAGE %s %s (%.1fs)" % (a.stage, "OK" if ok else "FAILED", time.time() - t0))
     sys.exit(0 if ok else 1)
