@@ -75,6 +75,13 @@ void innfer_rrdb_destroy(innfer_rrdb* h);
 /* upper bound of tiles pushed through the trunk per batch (memory / L2 trade-off), default 32 */
 int innfer_rrdb_set_max_batch(innfer_rrdb* h, int max_tiles);
 
+/* device-side timing of the conv sequence (CUDA events on the launching stream around every
+ * per-batch trunk+tail pass): enable/reset with innfer_rrdb_profile(h, 1); innfer_rrdb_profile_read
+ * synchronises on the recorded events and returns the summed milliseconds and the number of conv
+ * kernels launched inside them.  Used by bench.py for the roofline line; no reference equivalent. */
+int innfer_rrdb_profile(innfer_rrdb* h, int enable);
+int innfer_rrdb_profile_read(innfer_rrdb* h, double* conv_ms, uint64_t* conv_launches);
+
 /* ---- forward: replaces RRDBNet.forward on one batch (RRDBNet_arch.py:50-62) -------------------
  * x: device NCHW [n][in_nc][h][w], y: device NCHW [n][out_nc][scale*h][scale*w]; dtype INNFER_F16
  * or INNFER_F32 for both. */

@@ -41,6 +41,8 @@ _PROTOS = {
     "innfer_rrdb_finalize": (_i, [_vp]),
     "innfer_rrdb_destroy": (None, [_vp]),
     "innfer_rrdb_set_max_batch": (_i, [_vp, _i]),
+    "innfer_rrdb_profile": (_i, [_vp, _i]),
+    "innfer_rrdb_profile_read": (_i, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
     "innfer_rrdb_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "innfer_rrdb_chop_forward": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _i, _vp]),
     "innfer_rrdb_upscale_u8": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),

@@ -100,44 +100,73 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(N);
-      const uint32_t lboA = (uint32_t)(kHaloRows * Wh * 16);
-      const uint32_t sboA = (uint32_t)(Wh * 16);
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const TileCoord c = decode_tile(p, t);
-        const int ntaps = p.ph_ntaps[c.phase];
-        const int buf = it % p.nbuf;
-        const uint32_t use = (uint32_t)(it / p.nbuf);
-        mbar_wait(smem_u32(&tempty_bar[buf]), (use & 1u) ^ 1u);
+    // The whole warp runs the (warp-uniform) control flow so that descriptor arithmetic stays in
+    // the uniform datapath; only the elected lane issues tcgen05.mma / tcgen05.commit.
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_f16(N);
+    const uint32_t a_lbo = (uint32_t)(kHaloRows * Wh);   // in 16-byte units
+    const uint32_t a_sbo = (uint32_t)Wh;
+    const uint32_t a_hi = a_sbo | (1u << 14);            // SBO [32,46) + version=1 [46,48)
+    const uint32_t b_hi = 8u | (1u << 14);               // SBO = 128 B
+    const uint32_t b_lbo = (uint32_t)N;                  // N * 16 B
+    const uint32_t tap_stride = 2u * N;                  // 16-byte units per tap in the weight stage
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const TileCoord c = decode_tile(p, t);
+      const int ntaps = p.ph_ntaps[c.phase];
+      const int buf = it % p.nbuf;
+      const uint32_t use = (uint32_t)(it / p.nbuf);
+      mbar_wait(smem_u32(&tempty_bar[buf]), (use & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + (uint32_t)(buf * p.J * N);
+      for (int ks = 0; ks < p.kslabs; ++ks) {
+        mbar_wait(smem_u32(&full_bar[s]), ph);
         tc_fence_after();
-        const uint32_t acc0 = tmem_base + (uint32_t)(buf * p.J * N);
-        for (int ks = 0; ks < p.kslabs; ++ks) {
-          mbar_wait(smem_u32(&full_bar[s]), ph);
-          tc_fence_after();
-          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-          const uint64_t adesc0 = make_smem_desc(sa, lboA, sboA);
-          const uint64_t bdesc0 = make_smem_desc(sa + a_bytes, (uint32_t)N * 16u, 128u);
+        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+        const uint32_t a_lo = ((sa & 0x3FFFFu) >> 4) | (a_lbo << 16);
+        const uint32_t b_lo = (((sa + a_bytes) & 0x3FFFFu) >> 4) | (b_lbo << 16);
+        const uint32_t first = ks != 0 ? 1u : 0u;
+        if (ntaps == 9) {
+          // plain 3x3: taps are (hy, hx) in row-major order, fully unrolled
           for (int j = 0; j < c.jeff; ++j) {
             const uint32_t acc = acc0 + (uint32_t)(j * N);
-#pragma unroll 1
-            for (int tp = 0; tp < ntaps; ++tp) {
-              const uint32_t aoff = (uint32_t)p.tap_hy[c.phase][tp] * Wh + p.tap_hx[c.phase][tp] + 8u * j;
-              const uint32_t boff = (uint32_t)tp * (2u * N);  // tap stride in 16-byte units
-              umma_f16_ss(acc, adesc0 + aoff, bdesc0 + boff, idesc, (ks | tp) != 0 ? 1u : 0u);
+            const uint32_t aj = a_lo + 8u * j;
+            if (leader) {
+#pragma unroll
+              for (int hy = 0; hy < 3; ++hy) {
+#pragma unroll
+                for (int hx = 0; hx < 3; ++hx) {
+                  const int tp = hy * 3 + hx;
+                  umma_f16_ss(acc, make_desc64(aj + hy * a_sbo + hx, a_hi),
+                              make_desc64(b_lo + tp * tap_stride, b_hi), idesc, tp == 0 ? first : 1u);
+                }
+              }
             }
           }
-          umma_commit(smem_u32(&empty_bar[s]));
-          if (++s == S) {
-            s = 0;
-            ph ^= 1u;
+        } else {
+          for (int j = 0; j < c.jeff; ++j) {
+            const uint32_t acc = acc0 + (uint32_t)(j * N);
+            const uint32_t aj = a_lo + 8u * j;
+#pragma unroll 1
+            for (int tp = 0; tp < ntaps; ++tp) {
+              const uint32_t aoff = (uint32_t)p.tap_hy[c.phase][tp] * a_sbo + p.tap_hx[c.phase][tp];
+              if (leader)
+                umma_f16_ss(acc, make_desc64(aj + aoff, a_hi), make_desc64(b_lo + tp * tap_stride, b_hi), idesc,
+                            tp == 0 ? first : 1u);
+            }
           }
         }
-        umma_commit(smem_u32(&tfull_bar[buf]));
+        if (leader) umma_commit(smem_u32(&empty_bar[s]));
+        __syncwarp();
+        if (++s == S) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
+      if (leader) umma_commit(smem_u32(&tfull_bar[buf]));
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue warps

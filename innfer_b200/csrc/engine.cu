@@ -79,8 +79,16 @@ struct innfer_rrdb {
   TmapCache cache;
   // workspace
   DevBuf in_tiles, feat, xbuf[3], hrbuf[2], out_tiles, img_in, img_out;
+  // optional device-side timing of the conv sequence (bench.py roofline)
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  uint64_t prof_conv_launches = 0;
   // fp32-mode workspace lives in the same buffers (sized in bytes)
   ~innfer_rrdb() {
+    for (auto& e : prof_events) {
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
+    }
     conv_layer_free(fea);
     conv_layer_free(lr_conv);
     conv_layer_free(hr0);
@@ -173,7 +181,23 @@ int ensure_workspace(innfer_rrdb* h, int B, int hgt, int wid) {
 
 // Forward B tiles that already sit in h->in_tiles ([B][in_ct][hgt][wid][8]); the result
 // ([B][1 or 2][s*hgt][s*wid][8], out_nc channels in chunk 0..) is written to `dst`.
+int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, cudaStream_t st);
+
 int forward_tiles(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, cudaStream_t st) {
+  if (!h->profiling) return forward_tiles_impl(h, B, hgt, wid, dst, st);
+  cudaEvent_t a, b;
+  CU_TRY(cudaEventCreate(&a));
+  CU_TRY(cudaEventCreate(&b));
+  CU_TRY(cudaEventRecord(a, st));
+  const uint64_t l0 = g_launches.load();
+  int rc = forward_tiles_impl(h, B, hgt, wid, dst, st);
+  CU_TRY(cudaEventRecord(b, st));
+  h->prof_events.emplace_back(a, b);
+  h->prof_conv_launches += g_launches.load() - l0;
+  return rc;
+}
+
+int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, cudaStream_t st) {
   const int nfc = h->nf_ct(), catc = h->cat_ct();
   const int gcc = 32 / 8;
   int rc;
@@ -423,6 +447,32 @@ void innfer_rrdb_destroy(innfer_rrdb* h) {
 int innfer_rrdb_set_max_batch(innfer_rrdb* h, int max_tiles) {
   if (!h || max_tiles < 1) return fail(INNFER_E_INVALID, "bad argument");
   h->max_batch = max_tiles;
+  return 0;
+}
+
+int innfer_rrdb_profile(innfer_rrdb* h, int enable) {
+  if (!h) return fail(INNFER_E_INVALID, "null handle");
+  for (auto& e : h->prof_events) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  h->prof_events.clear();
+  h->prof_conv_launches = 0;
+  h->profiling = enable != 0;
+  return 0;
+}
+
+int innfer_rrdb_profile_read(innfer_rrdb* h, double* conv_ms, uint64_t* conv_launches) {
+  if (!h || !conv_ms || !conv_launches) return fail(INNFER_E_INVALID, "null argument");
+  double total = 0.0;
+  for (auto& e : h->prof_events) {
+    CU_TRY(cudaEventSynchronize(e.second));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, e.first, e.second));
+    total += ms;
+  }
+  *conv_ms = total;
+  *conv_launches = h->prof_conv_launches;
   return 0;
 }
 

@@ -138,6 +138,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t start, uint32_t lbo_
   d |= static_cast<uint64_t>(1) << 46;
   return d;
 }
+__device__ __forceinline__ uint64_t make_desc64(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+// One lane of the (converged) warp is elected; the same lane every time it is called.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // Instruction descriptor for kind::f16: fp16 A/B (K-major both), fp32 D, M=128, N=n.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);

@@ -73,6 +73,16 @@ class RRDBEngine:
     def set_max_batch(self, n):
         N.check(self.lib.innfer_rrdb_set_max_batch(self._h, int(n)))
 
+    def profile_reset(self, enable=True):
+        """Start (or stop) device-side timing of the conv sequence; see innfer_rrdb_profile."""
+        N.check(self.lib.innfer_rrdb_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """(milliseconds spent in the conv sequences, conv kernels launched) since profile_reset."""
+        ms, n = ctypes.c_double(), ctypes.c_uint64()
+        N.check(self.lib.innfer_rrdb_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, int(n.value)
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self.lib.innfer_rrdb_destroy(self._h)

@@ -1,0 +1,298 @@
+"""GPU parity tests (run with -m gpu on the B200 box): every check calls the CUDA path through the
+C-ABI (directly with ctypes or via the Python mirror that wraps it) and compares with the CPU
+oracle and with fixtures produced by the unmodified reference (tests/golden).
+
+Tolerances (BASELINE.json north_star): fp16 mode <= 1/255 max-abs on the uint8 image and >= 50 dB
+PSNR against the reference's fp32 forward; fp32 mode <= 1e-4 relative on the float tensor;
+-cf output <= 1 LSB.  Byte/index work (tiling, uint8 conversion of identical floats) is exact.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden, psnr_u8, synth_image
+from oracle import rrdb_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def _engine(sd, dev, fp16=True, scale=None):
+    from innfer_b200.engine import RRDBEngine
+    p = O.infer_params(sd)
+    cfg = dict(in_nc=p["in_nc"], out_nc=p["out_nc"], nf=p["nf"], nb=p["nb"], gc=32, scale=scale or p["scale"], plus=False)
+    return RRDBEngine.from_state_dict(sd, cfg, dev, fp16=fp16)
+
+
+def _conv(native, dev, cin, cout, h, w, n=1, up=1, lrelu=False, res=False, fp32=False, seed=0):
+    lib = native.load()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, cin, h, w, generator=g) * 2 - 1
+    wgt = (torch.rand(cout, cin, 3, 3, generator=g) * 2 - 1) * (2.0 / np.sqrt(cin * 9.0))
+    b = torch.rand(cout, generator=g) - 0.5
+    r = (torch.rand(n, cout, h * up, w * up, generator=g) * 2 - 1) if res else None
+    dt = torch.float32 if fp32 else torch.float16
+    xd = x.to(dev, dt)
+    rd = r.to(dev, dt) if res else None
+    y = torch.empty(n, cout, h * up, w * up, device=dev, dtype=dt)
+    wc, bc = wgt.contiguous().numpy(), b.contiguous().numpy()
+    native.check(lib.innfer_conv3x3(xd.data_ptr(), n, cin, h, w, wc.ctypes.data, bc.ctypes.data, cout, up, int(lrelu),
+                                    rd.data_ptr() if res else None, 0.2, y.data_ptr(),
+                                    native.INNFER_F32 if fp32 else native.INNFER_F16, int(fp32), None))
+    torch.cuda.synchronize()
+    xr = xd.double().cpu()
+    wr = wgt.double() if fp32 else wgt.half().double()
+    if up > 1:
+        xr = F.interpolate(xr, scale_factor=float(up), mode="nearest")
+    ref = F.conv2d(xr, wr, b.double(), padding=1)
+    if lrelu:
+        ref = F.leaky_relu(ref, 0.2)
+    if res:
+        ref = ref * 0.2 + rd.double().cpu()
+    return y.double().cpu(), ref
+
+
+@pytest.mark.parametrize("cin,cout,h,w,kw", [
+    (64, 32, 16, 40, {}), (64, 32, 40, 48, dict(lrelu=True)), (96, 32, 40, 48, dict(lrelu=True)),
+    (128, 32, 33, 47, dict(lrelu=True)), (160, 32, 40, 48, dict(lrelu=True)), (192, 64, 40, 48, dict(res=True)),
+    (3, 64, 33, 47, {}), (64, 3, 50, 70, {}), (64, 64, 37, 53, dict(n=3, lrelu=True)),
+    (64, 64, 24, 40, dict(up=2, lrelu=True)), (64, 64, 19, 21, dict(up=2, lrelu=True)),
+    (64, 64, 17, 23, dict(up=3, lrelu=True)), (32, 32, 20, 20, dict(lrelu=True)), (64, 32, 1, 1, {}),
+    (64, 32, 7, 200, dict(lrelu=True)), (64, 32, 200, 200, dict(n=2, lrelu=True)),
+])
+def test_conv_block_tcgen05(native, dev, cin, cout, h, w, kw):
+    """conv_block / upconv_block on the tensor-core kernel vs F.conv2d in fp64 on the same
+    fp16-rounded operands: only fp32 accumulation order and the fp16 output rounding differ."""
+    y, ref = _conv(native, dev, cin, cout, h, w, **kw)
+    tol = 2e-3 * max(1.0, ref.abs().max().item())
+    assert torch.isfinite(y).all()
+    assert (y - ref).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("cin,cout,h,w,kw", [
+    (64, 32, 40, 48, dict(lrelu=True)), (192, 64, 21, 35, dict(res=True)), (3, 64, 33, 47, {}),
+    (64, 3, 30, 30, {}), (64, 64, 19, 21, dict(up=2, lrelu=True)), (64, 64, 17, 23, dict(up=3, lrelu=True)),
+])
+def test_conv_block_fp32_kernel(native, dev, cin, cout, h, w, kw):
+    y, ref = _conv(native, dev, cin, cout, h, w, fp32=True, **kw)
+    assert ((y - ref).abs().max() / ref.abs().max()).item() <= 1e-5
+
+
+def test_full_model_config1_vs_reference_fixture(dev):
+    """BASELINE configs[0]: 4x RRDBNet (23 blocks) on the 64x64 image, reference fp32 CPU output."""
+    g = golden("rrdb4x_nb23_64x64.npz")
+    sd = O.make_state_dict(scale=4, nb=23, seed=0)
+    img = synth_image(0, 64, 64)
+    eng = _engine(sd, dev, fp16=True)
+    x = O.np2tensor(img).to(dev, torch.float16)
+    y = eng.chop_forward(x, 200, 0.5)
+    u8 = O.tensor2np(y)
+    assert np.abs(u8.astype(int) - g["u8"].astype(int)).max() <= 1
+    assert psnr_u8(u8, g["u8"]) >= 50.0
+    assert ((g["u8"] > 0) & (g["u8"] < 255)).mean() > 0.2  # not vacuous
+    u8b = eng.upscale_u8(img, 200, 0.5)
+    assert np.abs(u8b.astype(int) - g["u8"].astype(int)).max() <= 1
+    assert psnr_u8(u8b, g["u8"]) >= 50.0
+    # fp32 mode: <= 1e-4 relative on the float tensor
+    eng32 = _engine(sd, dev, fp16=False)
+    y32 = eng32.chop_forward(O.np2tensor(img).to(dev), 200, 0.5).cpu().numpy()
+    assert np.abs(y32 - g["y"]).max() / np.abs(g["y"]).max() <= 1e-4
+    eng.close()
+    eng32.close()
+
+
+@pytest.mark.parametrize("name", ["chop_s4_nb2_40x56_p32.npz", "chop_s1_nb2_80x64_p32.npz",
+                                  "chop_s2_nb1_50x70_p32.npz", "chop_s3_nb1_36x30_p200.npz"])
+@pytest.mark.parametrize("fp16", [True, False])
+def test_chop_forward_vs_reference_fixture(dev, name, fp16):
+    g = golden(name)
+    sd = O.make_state_dict(scale=int(g["scale"]), nb=int(g["nb"]), seed=int(g["seed"]))
+    # like run.Model the scale comes from the key names: a "3x" checkpoint has the key set of a
+    # 2x one, and the reference (hence the fixture) runs it as 2x (run.py:121-139)
+    scale = O.infer_params(sd)["scale"]
+    img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))
+    eng = _engine(sd, dev, fp16=fp16, scale=scale)
+    x = O.np2tensor(img).to(dev, torch.float16 if fp16 else torch.float32)
+    y = eng.chop_forward(x, int(g["patch"]), 0.5)
+    u8 = O.tensor2np(y)
+    assert np.abs(u8.astype(int) - g["u8"].astype(int)).max() <= 1
+    assert psnr_u8(u8, g["u8"]) >= 50.0
+    if not fp16:
+        assert np.abs(y.cpu().numpy() - g["y"]).max() / np.abs(g["y"]).max() <= 1e-4
+    # un-chopped forward on the same image against the oracle
+    ref = O.rrdbnet_forward(sd, O.np2tensor(img), scale)
+    y2 = eng.forward(x).float().cpu()
+    assert np.abs(O.tensor2np(y2).astype(int) - O.tensor2np(ref).astype(int)).max() <= 1
+    eng.close()
+
+
+@pytest.mark.parametrize("scale,hw", [(3, (24, 30)), (8, (16, 24))])
+def test_scale_3_and_8_vs_oracle(dev, scale, hw):
+    sd = O.make_state_dict(scale=scale, nb=1, seed=4)
+    eng = _engine(sd, dev, scale=scale)
+    img = synth_image(scale, *hw)
+    x = O.np2tensor(img)
+    ref = O.tensor2np(O.rrdbnet_forward(sd, x, scale))
+    got = O.tensor2np(eng.forward(x.to(dev).half()))
+    assert got.shape == (scale * hw[0], scale * hw[1], 3)
+    assert np.abs(got.astype(int) - ref.astype(int)).max() <= 1 and psnr_u8(got, ref) >= 50.0
+    eng.close()
+
+
+def test_python_api_model_chain_and_color_fix(dev, tmp_path, monkeypatch):
+    """run.Model on cuda (fp16) + chaining + -cf, and the CLI, vs the reference fixture (config 3 shrunk)."""
+    import cv2
+    from innfer_b200 import run as R
+    from innfer_b200.utils import utils as U
+    g = golden("chain_1x4x_cf_40x56.npz")
+    (tmp_path / "models").mkdir()
+    (tmp_path / "input").mkdir()
+    (tmp_path / "output").mkdir()
+    torch.save(O.make_state_dict(scale=1, nb=1, seed=5), tmp_path / "models" / "1x_rand_jpeg.pth")
+    torch.save(O.make_state_dict(scale=4, nb=1, seed=6), tmp_path / "models" / "4x_rand_fatal.pth")
+    img = synth_image(7, 40, 56)
+    cv2.imwrite(str(tmp_path / "input" / "a.png"), img)
+    monkeypatch.chdir(tmp_path)
+    chain, scales = R.parse_models("jpeg+fatal")
+    models = [R.Model(p, "infer", s, device=dev) for p, s in zip(chain, scales)]
+    for m in models:
+        m.model.half()
+    t = U.np2tensor(img).to(dev).half()
+    for m in models:
+        t = m(t)
+    assert t.dtype == torch.float16 and tuple(t.shape) == (1, 3, 160, 224)
+    u8 = U.tensor2np(t)
+    assert np.abs(u8.astype(int) - g["u8"].astype(int)).max() <= 1
+    assert psnr_u8(u8, g["u8"]) >= 50.0
+    cf = U.color_fix(img, g["u8"], device=dev)
+    d = np.abs(cf.astype(int) - g["cf"].astype(int))
+    assert d.max() <= 1
+    R.main(["-m", "jpeg+fatal", "-cf", "-i", "input", "-o", "output"])
+    out = cv2.imread(str(tmp_path / "output" / "a.png"), cv2.IMREAD_UNCHANGED)
+    # cf of a +-1 different SR image: the low-pass difference keeps this within a couple of LSBs
+    assert np.abs(out.astype(int) - g["cf"].astype(int)).max() <= 2
+    assert psnr_u8(out, g["cf"]) >= 48.0
+    # -no_fp16 on the GPU runs the fp32 kernels
+    R.main(["-m", "jpeg+fatal", "-no_fp16", "-i", "input", "-o", "output"])
+    out32 = cv2.imread(str(tmp_path / "output" / "a.png"), cv2.IMREAD_UNCHANGED)
+    assert np.abs(out32.astype(int) - g["u8"].astype(int)).max() <= 1
+    # chop=False goes through RRDBNet.forward
+    m = R.Model(chain[1], "infer", None, device=dev, chop=False)
+    y = m(U.np2tensor(img).to(dev))
+    ref = O.rrdbnet_forward(O.make_state_dict(scale=4, nb=1, seed=6), U.np2tensor(img), 4)
+    assert ((y.cpu() - ref).abs().max() / ref.abs().max()).item() <= 1e-4
+
+
+def test_color_fix_kernels_vs_reference_fixture(native, dev):
+    g = golden("color.npz")
+    from innfer_b200.utils import utils as U
+    for name in "abcd":
+        got = U.color_fix(g["lr_" + name], g["sr_" + name], device=dev)
+        d = np.abs(got.astype(int) - g["out_" + name].astype(int))
+        assert d.max() <= 1, name
+        assert (d > 0).mean() < 0.02, name
+    with pytest.raises(native.NativeError):
+        U.color_fix(g["sr_a"], g["lr_a"], device=dev)  # LR larger than SR: numpy would not broadcast
+
+
+def test_pixel_kernels_tiles_and_blend(native, dev):
+    lib = native.load()
+    H, W, p = 50, 70, 32
+    img = synth_image(5, H, W)
+    x = O.np2tensor(img)
+    patches, ys, xs = O.extract_patches(x, p, 0.5)
+    n = patches.shape[0]
+    # image -> tiles, uint8 and fp32 sources: exact (same fp16 rounding of the same floats)
+    for src, code in ((torch.from_numpy(img).to(dev), native.INNFER_U8), (x.to(dev), native.INNFER_F32),
+                      (x.to(dev).half(), native.INNFER_F16)):
+        tiles = torch.full((n, 2, p, p, 8), -7.0, dtype=torch.float16, device=dev)
+        native.check(lib.innfer_image_to_tiles(src.data_ptr(), code, 3, H, W, p, 0.5, tiles.data_ptr(), None))
+        torch.cuda.synchronize()
+        got = tiles.cpu()
+        want = patches.half()
+        assert torch.equal(got[:, 0, :, :, :3].permute(0, 3, 1, 2), want)
+        assert (got[:, 0, :, :, 3:] == 0).all() and (got[:, 1] == 0).all()
+    # blend: recompose_tensor fixture (fp32 reference) on fp16-rounded tiles
+    rec = golden("recompose.npz")
+    for key in rec.files:
+        h, w, pp, s = (int(v) for v in key.split("_")[1:])
+        pp = min(h, w, pp)
+        nt = len(O.tile_origins(h, pp)) * len(O.tile_origins(w, pp))
+        t = torch.rand(nt, 3, s * pp, s * pp, generator=torch.Generator().manual_seed(11))
+        chunks = torch.zeros(nt, 1, s * pp, s * pp, 8, dtype=torch.float16)
+        chunks[:, 0, :, :, :3] = t.permute(0, 2, 3, 1).half()
+        out = torch.empty(1, 3, s * h, s * w, dtype=torch.float32, device=dev)
+        native.check(lib.innfer_blend(chunks.to(dev).data_ptr(), h, w, pp, 0.5, s, 3, out.data_ptr(), native.INNFER_F32, None))
+        torch.cuda.synchronize()
+        assert np.abs(out.cpu().numpy() - rec[key]).max() <= 6e-4   # fp16 rounding of the tiles
+        # against the oracle on the SAME rounded tiles: only fp32 summation order differs
+        want = O.recompose(t.half().float(), h, w, 0.5, s)
+        assert (out.cpu() - want).abs().max().item() <= 2e-6
+        u8 = torch.empty(s * h, s * w, 3, dtype=torch.uint8, device=dev)
+        native.check(lib.innfer_blend(chunks.to(dev).data_ptr(), h, w, pp, 0.5, s, 3, u8.data_ptr(), native.INNFER_U8, None))
+        torch.cuda.synchronize()
+        assert np.abs(u8.cpu().numpy().astype(int) - O.tensor2np(want).astype(int)).max() <= 1
+
+
+def test_determinism_and_batch_invariance(dev):
+    sd = O.make_state_dict(scale=4, nb=2, seed=1)
+    eng = _engine(sd, dev)
+    img = synth_image(9, 130, 170)
+    a = eng.upscale_u8(img, 32, 0.5).copy()
+    b = eng.upscale_u8(img, 32, 0.5).copy()
+    assert np.array_equal(a, b)
+    eng.set_max_batch(5)
+    c = eng.upscale_u8(img, 32, 0.5).copy()
+    assert np.array_equal(a, c)          # tile batching must not change a single byte
+    eng.close()
+
+
+def test_edge_shapes(dev):
+    sd = O.make_state_dict(scale=2, nb=1, seed=2)
+    eng = _engine(sd, dev)
+    for h, w in ((8, 8), (9, 31), (64, 8), (201, 17)):
+        img = synth_image(h * 100 + w, h, w)
+        x = O.np2tensor(img)
+        ref = O.tensor2np(O.rrdbnet_forward(sd, x, 2))
+        got = O.tensor2np(eng.forward(x.to(dev).half()))
+        assert np.abs(got.astype(int) - ref.astype(int)).max() <= 1, (h, w)
+    with pytest.raises(ValueError):
+        eng.forward(torch.zeros(1, 4, 8, 8, device=dev, dtype=torch.float16))
+    eng.close()
+
+
+def test_full_size_properties_1080p(dev):
+    """BASELINE configs[1] at full size: properties that do not need a CPU reference of 272 TFLOP."""
+    sd = O.make_state_dict(scale=4, nb=23, seed=0)
+    eng = _engine(sd, dev)
+    img = synth_image(0, 1080, 1920)
+    out = eng.upscale_u8(img, 200, 0.5).copy()
+    assert out.shape == (4320, 7680, 3)
+    assert 0.2 < ((out > 0) & (out < 255)).mean()
+    # (1) bit-reproducible across runs and across tile batch sizes
+    eng.set_max_batch(19)
+    assert np.array_equal(out, eng.upscale_u8(img, 200, 0.5))
+    # (2) the top-left 400x400 output block is covered by tile (0,0) only, so it must equal the
+    #     stand-alone forward of that tile (and that one is checked against the CPU oracle)
+    x = O.np2tensor(img[:200, :200])
+    tile = O.tensor2np(eng.forward(x.to(dev).half()))
+    assert np.abs(tile[:400, :400].astype(int) - out[:400, :400].astype(int)).max() <= 1
+    ref = O.tensor2np(O.rrdbnet_forward(sd, x[:, :, :64, :64], 4))
+    small = O.tensor2np(eng.forward(x[:, :, :64, :64].to(dev).half()))
+    assert np.abs(small.astype(int) - ref.astype(int)).max() <= 1
+    # (3) same frame shifted by one tile stride: interior tiles see the same pixels -> same output
+    shifted = np.roll(img, -100, axis=1)
+    out2 = eng.upscale_u8(shifted, 200, 0.5)
+    assert np.array_equal(out[:, 800:6800], out2[:, 400:6400])
+    eng.close()

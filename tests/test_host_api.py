@@ -1,0 +1,194 @@
+"""CPU tests of the host-side mirror (innfer_b200.run / architectures / utils) against fixtures
+generated from the unmodified reference, and of the C-ABI surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden, synth_image
+from innfer_b200 import _native
+from innfer_b200 import run as R
+from innfer_b200.architectures import get_network
+from innfer_b200.utils import utils as U
+from innfer_b200.utils.defaults import get_network_G_config
+from oracle import rrdb_oracle as O
+
+
+def _save(sd, path):
+    torch.save(sd, path)
+    return str(path)
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "innfer_b200.h")).read()
+    declared = set(re.findall(r"\b(innfer_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = _native.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_native.EXPORTED_SYMBOLS)
+
+
+def test_tiles_plan_matches_reference_geometry():
+    lib = _native.load()
+    g = golden("tile_geometry.npz")
+    for key in g.files:
+        h, w, p = (int(v) for v in key.split("_"))
+        tiles = (_native.Tile * 4096)()
+        n, ts = ctypes.c_int(), ctypes.c_int()
+        _native.check(lib.innfer_tiles_plan(h, w, p, 0.5, tiles, 4096, ctypes.byref(n), ctypes.byref(ts)))
+        got = np.array([(tiles[i].y0, tiles[i].x0) for i in range(n.value)])
+        np.testing.assert_array_equal(got, g[key])
+        assert ts.value == min(h, w, p)
+
+
+def test_abi_rejects_bad_arguments_without_gpu():
+    lib = _native.load()
+    n = ctypes.c_int()
+    assert lib.innfer_tiles_plan(0, 10, 200, 0.5, None, 0, ctypes.byref(n), None) == -1
+    assert b"tile" in lib.innfer_last_error()
+    cfg = _native.RRDBCfg(3, 3, 64, 23, 32, 4, 1, 1)  # plus=1 is not implemented: must fail loudly
+    h = ctypes.c_void_p()
+    assert lib.innfer_rrdb_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -2
+    assert b"plus" in lib.innfer_last_error()
+
+
+def test_state_dict_keys_and_cpu_forward_match_reference(tmp_path):
+    g = golden("rrdb4x_nb23_64x64.npz")
+    sd = O.make_state_dict(scale=4, nb=23, seed=0)
+    path = _save(sd, tmp_path / "4x_rand_rrdb.pth")
+    m = R.Model(path, "infer", None, device=torch.device("cpu"), chop=True)
+    assert (m.arch, m.scale, m.in_nc, m.out_nc) == (str(g["arch"]), int(g["scale"]), int(g["in_nc"]), int(g["out_nc"]))
+    assert list(m.model.state_dict().keys()) == list(sd.keys())
+    img = synth_image(0, 64, 64)
+    y = m(U.np2tensor(img))
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)
+    assert np.abs(U.tensor2np(y).astype(int) - g["u8"].astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("name", ["chop_s4_nb2_40x56_p32.npz", "chop_s1_nb2_80x64_p32.npz", "chop_s2_nb1_50x70_p32.npz"])
+def test_cpu_mode_chop_forward(tmp_path, name):
+    g = golden(name)
+    scale = int(g["scale"])
+    sd = O.make_state_dict(scale=scale, nb=int(g["nb"]), seed=int(g["seed"]))
+    m = R.Model(_save(sd, tmp_path / ("%dx_t.pth" % scale)), "infer", None, device=torch.device("cpu"))
+    assert m.scale == scale
+    img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))
+    y = m.chop_forward(U.np2tensor(img), patch_size=int(g["patch"]), step=0.5)
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)
+
+
+def test_infer_params_and_key_mapping(tmp_path):
+    g = golden("load_logic.npz")
+    for scale, nb in ((1, 2), (2, 3), (4, 23), (8, 1)):
+        sd = O.make_state_dict(scale=scale, nb=nb, seed=0)
+        m = R.Model.__new__(R.Model)
+        m.arch, m.scale, m.in_nc, m.out_nc = "esrgan", None, 3, 3
+        cfg = m.infer_params(sd)
+        got = [m.scale, cfg["nb"], cfg["nf"], cfg["in_nc"], cfg["out_nc"], int(cfg["plus"]), cfg["upscale"]]
+        assert got == list(g["infer_s%d_nb%d" % (scale, nb)])
+    sd = O.make_state_dict(scale=4, nb=23, seed=0)
+    mod = U.normal2mod(dict(sd))
+    assert list(mod.keys()) == list(g["mod_keys"])
+    back = U.mod2normal(mod)
+    assert list(back.keys()) == list(g["mod2normal_keys"])
+    for k in sd:
+        assert torch.equal(back[k], sd[k])
+    # a 'new-arch' checkpoint is auto-detected, converted and loads strictly
+    m = R.Model(_save(mod, tmp_path / "4x_newarch.pth"), "infer", None, device=torch.device("cpu"))
+    assert m.arch == "esrgan" and m.scale == 4
+    # SWA wrapper
+    swa = {"n_averaged": torch.tensor(3)}
+    swa.update({"module.module." + k: v for k, v in O.make_state_dict(scale=1, nb=1).items()})
+    assert list(U.swa2normal(swa).keys()) == list(O.make_state_dict(scale=1, nb=1).keys())
+    m = R.Model(_save(swa, tmp_path / "1x_swa.pth"), "infer", None, device=torch.device("cpu"))
+    assert m.scale == 1
+    names, vals = g["scale_names"], g["scale_vals"]
+    for n, v in zip(names, vals):
+        got = R.get_scale_name(str(n))
+        assert (-1 if got is None else got) == int(v)
+
+
+def test_model_path_resolution(tmp_path, monkeypatch):
+    (tmp_path / "models").mkdir()
+    for name in ("4x_rand_rrdb.pth", "1x_rand_jpeg.pth", "4x_other_rrdb.pth"):
+        torch.save({}, tmp_path / "models" / name)
+    monkeypatch.chdir(tmp_path)
+    chain, scales = R.parse_models("jpeg+rand_rrdb")
+    assert [os.path.basename(c) for c in chain] == ["1x_rand_jpeg.pth", "4x_rand_rrdb.pth"]
+    assert scales == [1, 4]
+    chain, _ = R.parse_models("JPEG>other")
+    assert os.path.basename(chain[1]) == "4x_other_rrdb.pth"
+    with pytest.raises(ValueError):
+        R.parse_models("rrdb")           # ambiguous filter
+    with pytest.raises(IndexError):
+        R.parse_models("nosuchmodel")    # the reference falls through to m_list[0]
+    with pytest.raises(ValueError):
+        R.parse_models("jpeg+rand_rrdb", scales_list=[4])
+    assert R.check_model_path("4x_rand_rrdb.pth", None) == os.path.join("models", "4x_rand_rrdb.pth")
+
+
+def test_unknown_architectures_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        get_network({"type": "sr_resnet"})
+    with pytest.raises(NotImplementedError):
+        get_network_G_config({"type": "pan"}, 4)
+    with pytest.raises(Exception, match="Could not infer"):
+        m = R.Model.__new__(R.Model)
+        m.__dict__.update(model_path="x", arch="infer", scale=None, in_nc=3, out_nc=3, device="cpu", eval=True,
+                          strict=True, chop=True)
+        torch.save({"weird.weight": torch.zeros(1)}, "/tmp/_innfer_weird.pth")
+        m.model_path = "/tmp/_innfer_weird.pth"
+        m.load_model()
+    cfg = get_network_G_config("esrgan-lite", 2)
+    assert (cfg["nf"], cfg["nb"], cfg["upscale"], cfg["type"]) == (32, 12, 2, "rrdb_net")
+
+
+def test_np2tensor_tensor2np_colorfix_host():
+    g = golden("color.npz")
+    np.testing.assert_array_equal(U.np2tensor(g["np2tensor_img"]).numpy(), g["np2tensor_out"])
+    np.testing.assert_array_equal(U.tensor2np(torch.from_numpy(g["tensor2np_in"])), g["tensor2np_out"])
+    for name in "abcd":
+        np.testing.assert_array_equal(U.color_fix(g["lr_" + name], g["sr_" + name]), g["out_" + name])
+    rec = golden("recompose.npz")
+    for key in rec.files:
+        h, w, p, s = (int(v) for v in key.split("_")[1:])
+        pp = min(h, w, p)
+        n = len(O.tile_origins(h, pp)) * len(O.tile_origins(w, pp))
+        tiles = torch.rand(n, 3, s * pp, s * pp, generator=torch.Generator().manual_seed(11))
+        np.testing.assert_allclose(U.recompose_tensor(tiles, h, w, step=0.5, scale=s).numpy(), rec[key], atol=1e-6)
+
+
+def test_cli_cpu_end_to_end(tmp_path, monkeypatch):
+    """python run.py -m jpeg+fatal -cf -cpu on a tiny image (config 3, shrunk)."""
+    import cv2
+    g = golden("chain_1x4x_cf_40x56.npz")
+    (tmp_path / "models").mkdir()
+    (tmp_path / "input").mkdir()
+    (tmp_path / "output").mkdir()
+    torch.save(O.make_state_dict(scale=1, nb=1, seed=5), tmp_path / "models" / "1x_rand_jpeg.pth")
+    torch.save(O.make_state_dict(scale=4, nb=1, seed=6), tmp_path / "models" / "4x_rand_fatal.pth")
+    cv2.imwrite(str(tmp_path / "input" / "a.png"), synth_image(7, 40, 56))
+    monkeypatch.chdir(tmp_path)
+    R.main(["-m", "jpeg+fatal", "-cf", "-cpu", "-i", "input", "-o", "output"])
+    out = cv2.imread(str(tmp_path / "output" / "a.png"), cv2.IMREAD_UNCHANGED)
+    d = np.abs(out.astype(int) - g["cf"].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.01
+    with pytest.raises(NotImplementedError):
+        R.main(["-m", "jpeg", "-a", "unet_256", "-cpu"])
+
+
+def test_cuda_request_never_falls_back(tmp_path, monkeypatch):
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without CUDA")
+    (tmp_path / "models").mkdir()
+    torch.save(O.make_state_dict(scale=1, nb=1), tmp_path / "models" / "1x_a.pth")
+    monkeypatch.chdir(tmp_path)
+    with pytest.raises(RuntimeError, match="CUDA is not available"):
+        R.main(["-m", "1x_a"])
+    from innfer_b200.engine import RRDBEngine
+    with pytest.raises(RuntimeError):
+        RRDBEngine(dict(in_nc=3, out_nc=3, nf=64, nb=1, scale=1), "cuda:0")
