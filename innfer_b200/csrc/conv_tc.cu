@@ -10,20 +10,45 @@ struct TileCoord {
   int b, y0, x0, phase, jeff;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t) {
-  TileCoord c;
-  c.phase = t % p.nphase;
-  int r = t / p.nphase;
-  int cp = r % p.cps;
-  r /= p.cps;
-  int band = r % p.bands;
-  c.b = r / p.bands;
-  c.y0 = band * kPatchRows;
-  c.x0 = cp * 8 * p.J;
-  int rem = (p.W - c.x0 + 7) >> 3;  // sub-patches that still touch the image
-  c.jeff = rem < p.J ? rem : p.J;
-  return c;
-}
+// Walks the tile list t0, t0+stride, ... as a mixed-radix counter (phase, col-patch, band, image)
+// so that the per-tile decode on the MMA warp's critical path needs no integer division.
+struct TileIter {
+  int phase, cp, band, b;
+  int dphase, dcp, dband, db;
+  int nphase, cps, bands, B, J, W;
+  __device__ __forceinline__ void init(const ConvTcParams& p, int t0, int stride) {
+    nphase = p.nphase; cps = p.cps; bands = p.bands; B = p.B; J = p.J; W = p.W;
+    phase = t0 % nphase; int r = t0 / nphase;
+    cp = r % cps; r /= cps;
+    band = r % bands; b = r / bands;
+    dphase = stride % nphase; r = stride / nphase;
+    dcp = r % cps; r /= cps;
+    dband = r % bands; db = r / bands;
+  }
+  __device__ __forceinline__ bool valid() const { return b < B; }
+  __device__ __forceinline__ void advance() {
+    phase += dphase;
+    int c = phase >= nphase ? 1 : 0;
+    phase -= c ? nphase : 0;
+    cp += dcp + c;
+    c = cp >= cps ? 1 : 0;
+    cp -= c ? cps : 0;
+    band += dband + c;
+    c = band >= bands ? 1 : 0;
+    band -= c ? bands : 0;
+    b += db + c;
+  }
+  __device__ __forceinline__ TileCoord coord() const {
+    TileCoord c;
+    c.b = b;
+    c.phase = phase;
+    c.y0 = band * kPatchRows;
+    c.x0 = cp * 8 * J;
+    const int rem = (W - c.x0 + 7) >> 3;  // sub-patches that still touch the image
+    c.jeff = rem < J ? rem : J;
+    return c;
+  }
+};
 
 __device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.f ? v : v * slope; }
 
@@ -46,8 +71,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tfull_bar = empty_bar + S;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* set_bar = tfull_bar + 2;       // "accumulator set is drained" (4 epilogue warps arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(set_bar + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
 
   if (threadIdx.x == 0) {
@@ -56,10 +81,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&tempty_bar[i]), 4);
-    }
+    for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&tfull_bar[i]), 1);
+    for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&set_bar[i]), 4);
     fence_mbar_init();
   }
   if (threadIdx.x < N) s_bias[threadIdx.x] = p.bias[threadIdx.x];
@@ -72,7 +95,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.B * p.bands * p.cps * p.nphase;
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp == 0) {
@@ -80,17 +102,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const TileCoord c = decode_tile(p, t);
+      TileIter ti;
+      ti.init(p, blockIdx.x, gridDim.x);
+      for (; ti.valid(); ti.advance()) {
+        const TileCoord c = ti.coord();
         const uint32_t wb = (uint32_t)p.ph_ntaps[c.phase] * 2u * N * 16u;
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + p.ph_woff[c.phase];
         for (int ks = 0; ks < p.kslabs; ++ks) {
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
           const uint32_t fb = smem_u32(&full_bar[s]);
           const uint32_t dstA = smem_base + (uint32_t)s * stage_bytes;
-          mbar_expect_tx(fb, (uint32_t)(2 * kHaloRows * Wh * 16) + wb);
-          tma_load_5d(dstA, &tmap_in, fb, 0, c.x0 - 1, c.y0 - 1, p.in_chunk0 + 2 * ks, c.b);
-          bulk_load(dstA + a_bytes, wsrc + (size_t)ks * wb, wb, fb);
+          if (p.debug & 1) {
+            mbar_arrive(fb);
+          } else if (p.debug & 2) {
+            mbar_expect_tx(fb, wb);
+            bulk_load(dstA + a_bytes, wsrc + (size_t)ks * wb, wb, fb);
+          } else {
+            mbar_expect_tx(fb, (uint32_t)(2 * kHaloRows * Wh * 16) + wb);
+            tma_load_5d(dstA, &tmap_in, fb, 0, c.x0 - 1, c.y0 - 1, p.in_chunk0 + 2 * ks, c.b);
+            bulk_load(dstA + a_bytes, wsrc + (size_t)ks * wb, wb, fb);
+          }
           if (++s == S) {
             s = 0;
             ph ^= 1u;
@@ -100,8 +131,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    // The whole warp runs the (warp-uniform) control flow so that descriptor arithmetic stays in
-    // the uniform datapath; only the elected lane issues tcgen05.mma / tcgen05.commit.
+    // tcgen05.mma is issued by one thread and the tensor pipe buffers only a few instructions:
+    // with M=128 x N=32..64 x K=16 MMAs (16-32 tensor cycles each) every instruction on this
+    // warp's path shows up as a pipe bubble, so the loop is kept as lean as possible (division-free
+    // tile iteration, one accumulator-set barrier per tile, taps fully unrolled).  Measured on
+    // B200: a second issuing warp does NOT help -- MMAs from two threads interleave worse than the
+    // same MMAs from one thread.  The whole warp runs the (warp-uniform) control flow so that
+    // descriptor arithmetic stays in the uniform datapath; only the elected lane issues.
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_f16(N);
     const uint32_t a_lbo = (uint32_t)(kHaloRows * Wh);   // in 16-byte units
@@ -110,17 +146,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     const uint32_t b_hi = 8u | (1u << 14);               // SBO = 128 B
     const uint32_t b_lbo = (uint32_t)N;                  // N * 16 B
     const uint32_t tap_stride = 2u * N;                  // 16-byte units per tap in the weight stage
+    const int J = p.J;
+    const bool plain3x3 = (p.nphase == 1) && (p.ph_ntaps[0] == 9);
     int s = 0;
     uint32_t ph = 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const TileCoord c = decode_tile(p, t);
-      const int ntaps = p.ph_ntaps[c.phase];
-      const int buf = it % p.nbuf;
-      const uint32_t use = (uint32_t)(it / p.nbuf);
-      mbar_wait(smem_u32(&tempty_bar[buf]), (use & 1u) ^ 1u);
+    uint32_t it = 0;
+    TileIter ti;
+    ti.init(p, blockIdx.x, gridDim.x);
+    for (; ti.valid(); ti.advance(), ++it) {
+      const TileCoord c = ti.coord();
+      const int ntaps = plain3x3 ? 9 : (int)p.ph_ntaps[c.phase];
+      const uint32_t set = it & 1u;
+      // the epilogue must have drained the tile that used this accumulator set two tiles ago
+      mbar_wait(smem_u32(&set_bar[set]), ((it >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t acc0 = tmem_base + (uint32_t)(buf * p.J * N);
+      const uint32_t acc0 = tmem_base + set * (uint32_t)(J * N);
       for (int ks = 0; ks < p.kslabs; ++ks) {
         mbar_wait(smem_u32(&full_bar[s]), ph);
         tc_fence_after();
@@ -165,7 +205,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           ph ^= 1u;
         }
       }
-      if (leader) umma_commit(smem_u32(&tfull_bar[buf]));
+      if (leader) umma_commit(smem_u32(&tfull_bar[set]));
       __syncwarp();
     }
   } else {
@@ -174,88 +214,94 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     const int m = q * 32 + lane;
     const int r = m >> 3, cc = m & 7;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const size_t oplane = (size_t)p.Hout * p.Wout;
+    constexpr int NCH = N / 8;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const TileCoord c = decode_tile(p, t);
-      const int buf = it % p.nbuf;
-      const uint32_t use = (uint32_t)(it / p.nbuf);
-      mbar_wait(smem_u32(&tfull_bar[buf]), use & 1u);
+    TileIter ti;
+    ti.init(p, blockIdx.x, gridDim.x);
+    for (; ti.valid(); ti.advance(), ++it) {
+      const TileCoord c = ti.coord();
+      mbar_wait(smem_u32(&tfull_bar[it & 1]), (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       const int y = c.y0 + r;
       const int oy = y * p.up + p.ph_a[c.phase];
+      const uint32_t sb = smem_u32(&set_bar[it & 1]);
       for (int j = 0; j < c.jeff; ++j) {
+        const uint32_t tacc = tmem_base + lane_base + (uint32_t)(((it & 1) * p.J + j) * N);
         const int x = c.x0 + 8 * j + cc;
         const int ox = x * p.up + p.ph_b[c.phase];
         const bool valid = (y < p.H) && (x < p.W);
-        const uint32_t tacc = tmem_base + lane_base + (uint32_t)(buf * p.J * N + j * N);
         const size_t opix = (size_t)oy * p.Wout + ox;
-        const size_t oplane = (size_t)p.Hout * p.Wout;
+        // 1. residual loads first: their latency overlaps the TMEM read and nothing below the
+        //    slot release depends on the tensor pipe any more
+        uint4 r1[NCH], r2[NCH];
+        if (p.res1 != nullptr) {
+          const __half* rp = p.res1 + (((size_t)c.b * p.res1_CT + p.res1_chunk0) * oplane + opix) * 8;
 #pragma unroll
-        for (int g = 0; g < N / 16; ++g) {
-          uint32_t v[16];
-          tmem_ld16(tacc + g * 16, v);
-          // residual loads are issued before the TMEM wait so their latency overlaps it
-          uint4 r1[2], r2[2];
-          const bool do_chunk0 = valid && (2 * g) < p.out_nchunks;
-          const bool do_chunk1 = valid && (2 * g + 1) < p.out_nchunks;
-          if (p.res1 != nullptr) {
-            const size_t base = ((size_t)c.b * p.res1_CT + p.res1_chunk0 + 2 * g) * oplane + opix;
-            if (do_chunk0) r1[0] = *reinterpret_cast<const uint4*>(p.res1 + base * 8);
-            if (do_chunk1) r1[1] = *reinterpret_cast<const uint4*>(p.res1 + (base + oplane) * 8);
-          }
-          if (p.res2 != nullptr) {
-            const size_t base = ((size_t)c.b * p.res2_CT + p.res2_chunk0 + 2 * g) * oplane + opix;
-            if (do_chunk0) r2[0] = *reinterpret_cast<const uint4*>(p.res2 + base * 8);
-            if (do_chunk1) r2[1] = *reinterpret_cast<const uint4*>(p.res2 + (base + oplane) * 8);
-          }
-          tmem_ld_wait();
+          for (int ch = 0; ch < NCH; ++ch)
+            if (valid && ch < p.out_nchunks) r1[ch] = *reinterpret_cast<const uint4*>(rp + (size_t)ch * oplane * 8);
+        }
+        if (p.res2 != nullptr) {
+          const __half* rp = p.res2 + (((size_t)c.b * p.res2_CT + p.res2_chunk0) * oplane + opix) * 8;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const bool doit = h == 0 ? do_chunk0 : do_chunk1;
-            if (!doit) continue;
-            float f[8];
+          for (int ch = 0; ch < NCH; ++ch)
+            if (valid && ch < p.out_nchunks) r2[ch] = *reinterpret_cast<const uint4*>(rp + (size_t)ch * oplane * 8);
+        }
+        // 2. drain the accumulator into registers (the set goes back to the MMA warp after the last one)
+        uint32_t v[N];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float tv = __uint_as_float(v[h * 8 + e]) + s_bias[g * 16 + h * 8 + e];
-              if (p.lrelu) tv = lrelu_f(tv, p.slope);
-              f[e] = tv;
-            }
-            if (p.res1 != nullptr) {
-              const __half2* hp = reinterpret_cast<const __half2*>(&r1[h]);
+        for (int g = 0; g < N / 16; ++g) tmem_ld16(tacc + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[g * 16]));
+        tmem_ld_wait();
+        if (j == c.jeff - 1) {  // last accumulator of the tile is in registers: release the set
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sb);
+        }
+        // 3. bias, activation, residuals, fp16 pack, 16-byte stores into the destination chunk slice
+        if (valid) {
+          __half* op = p.out + (((size_t)c.b * p.out_CT + p.out_chunk0) * oplane + opix) * 8;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 rv = __half22float2(hp[e]);
-                f[2 * e] = f[2 * e] * p.alpha1 + rv.x;
-                f[2 * e + 1] = f[2 * e + 1] * p.alpha1 + rv.y;
+          for (int ch = 0; ch < NCH; ++ch) {
+            if (ch < p.out_nchunks) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float tv = __uint_as_float(v[ch * 8 + e]) + s_bias[ch * 8 + e];
+                if (p.lrelu) tv = lrelu_f(tv, p.slope);
+                f[e] = tv;
               }
-            }
-            if (p.res2 != nullptr) {
-              const __half2* hp = reinterpret_cast<const __half2*>(&r2[h]);
+              if (p.res1 != nullptr) {
+                const __half2* hp = reinterpret_cast<const __half2*>(&r1[ch]);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 rv = __half22float2(hp[e]);
-                f[2 * e] = f[2 * e] * p.alpha2 + rv.x;
-                f[2 * e + 1] = f[2 * e + 1] * p.alpha2 + rv.y;
+                for (int e = 0; e < 4; ++e) {
+                  const float2 rv = __half22float2(hp[e]);
+                  f[2 * e] = f[2 * e] * p.alpha1 + rv.x;
+                  f[2 * e + 1] = f[2 * e + 1] * p.alpha1 + rv.y;
+                }
               }
+              if (p.res2 != nullptr) {
+                const __half2* hp = reinterpret_cast<const __half2*>(&r2[ch]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 rv = __half22float2(hp[e]);
+                  f[2 * e] = f[2 * e] * p.alpha2 + rv.x;
+                  f[2 * e + 1] = f[2 * e + 1] * p.alpha2 + rv.y;
+                }
+              }
+              uint4 o;
+              const __half2 h0 = __floats2half2_rn(f[0], f[1]);
+              const __half2 h1 = __floats2half2_rn(f[2], f[3]);
+              const __half2 h2 = __floats2half2_rn(f[4], f[5]);
+              const __half2 h3 = __floats2half2_rn(f[6], f[7]);
+              o.x = *reinterpret_cast<const uint32_t*>(&h0);
+              o.y = *reinterpret_cast<const uint32_t*>(&h1);
+              o.z = *reinterpret_cast<const uint32_t*>(&h2);
+              o.w = *reinterpret_cast<const uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(op + (size_t)ch * oplane * 8) = o;
             }
-            uint4 o;
-            __half2 h0 = __floats2half2_rn(f[0], f[1]);
-            __half2 h1 = __floats2half2_rn(f[2], f[3]);
-            __half2 h2 = __floats2half2_rn(f[4], f[5]);
-            __half2 h3 = __floats2half2_rn(f[6], f[7]);
-            o.x = *reinterpret_cast<uint32_t*>(&h0);
-            o.y = *reinterpret_cast<uint32_t*>(&h1);
-            o.z = *reinterpret_cast<uint32_t*>(&h2);
-            o.w = *reinterpret_cast<uint32_t*>(&h3);
-            const size_t obase =
-                ((size_t)c.b * p.out_CT + p.out_chunk0 + 2 * g + h) * oplane + opix;
-            *reinterpret_cast<uint4*>(p.out + obase * 8) = o;
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
     }
   }
 

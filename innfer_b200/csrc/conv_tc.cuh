@@ -15,8 +15,9 @@
 // through shifted SWIZZLE_NONE K-major matrix descriptors:
 //   addr(pixel row m, kchunk c) = base + ((hy + m/8) * Wh + hx + 8j + m%8) * 16 + c * (Rh*Wh*16)
 // i.e. SBO = Wh*16, LBO = Rh*Wh*16, start shifted by (hy*Wh + hx + 8j) * 16 bytes.
-// Accumulators (J of them, 128 lanes x N fp32 columns) live in TMEM, double buffered when they
-// fit, and the epilogue (bias, LeakyReLU, up to two scaled residual adds, fp16 pack) reads them with
+// Accumulators (J per tile, 128 lanes x N fp32 columns each) live in two TMEM sets used by
+// alternate tiles, so the MMA warp works on the next tile while the epilogue drains the previous
+// one.  The epilogue (bias, LeakyReLU, up to two scaled residual adds, fp16 pack) reads them with
 // tcgen05.ld and stores 16-byte channel chunks straight into the destination chunk slice.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
@@ -47,8 +48,9 @@ struct ConvTcParams {
   int up;          // output = up * source resolution
   int Hout, Wout;
   int stages;      // smem pipeline depth
-  int nbuf;        // TMEM accumulator buffers (1 or 2)
-  int tmem_cols;   // power of two >= nbuf*J*N
+  int nslots;      // TMEM accumulator slots of N columns: 2*J (two sets of J, alternate tiles)
+  int tmem_cols;   // power of two >= nslots*N
+  int debug;       // bit0: skip TMA loads (timing experiments only, garbage results)
   // destination
   __half* out;
   int out_CT, out_chunk0, out_nchunks;

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "tmap.cuh"
@@ -133,12 +134,16 @@ const CUtensorMap* TmapCache::get(const void* base, int B, int CT, int H, int W,
 }
 
 int choose_J(int W, int N) {
+  // Alternate tiles use alternate sets of J accumulators (double buffering against the epilogue),
+  // so 2*J*N fp32 columns must fit the 512 TMEM columns.  Among the feasible J pick the one that
+  // loads the fewest halo columns, charging a few columns per tile for fixed per-tile costs.
+  int jmax = 256 / N;
+  if (jmax > 5) jmax = 5;
   int best = 1;
   long best_cost = -1;
-  for (int J = 1; J <= 5; ++J) {
-    if (J * N > 512) break;
+  for (int J = 1; J <= jmax; ++J) {
     const int cps = (W + 8 * J - 1) / (8 * J);
-    const long cost = (long)cps * (8 * J + 2);
+    const long cost = (long)cps * (8 * J + 2 + 6);
     if (best_cost < 0 || cost <= best_cost) {
       best_cost = cost;
       best = J;
@@ -166,8 +171,8 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
   p.up = L.up;
   p.Hout = H * L.up;
   p.Wout = W * L.up;
-  p.nbuf = (2 * J * N <= 512) ? 2 : 1;
-  int cols = p.nbuf * J * N, pw = 32;
+  p.nslots = 2 * J;
+  int cols = p.nslots * N, pw = 32;
   while (pw < cols) pw <<= 1;
   p.tmem_cols = pw;
   const int stage_bytes = conv_tc_a_bytes(J) + conv_tc_w_bytes(N, L.max_taps);
@@ -201,6 +206,8 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
       p.tap_hx[i][t] = L.tap_hx[i][t];
     }
   }
+  static const int dbg = getenv("INNFER_DEBUG") ? atoi(getenv("INNFER_DEBUG")) : 0;
+  p.debug = dbg;
   int rc = 0;
   const CUtensorMap* tm = cache.get(in.base, B, in.CT, H, W, J, rc);
   if (!tm) return rc ? rc : -5;

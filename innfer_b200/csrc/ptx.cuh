@@ -42,8 +42,12 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// Spin until the phase with the given parity has completed.  A bounded spin count turns a protocol
+// bug into a trap (reported as a CUDA error by the host) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
   }
 }
 

@@ -197,7 +197,7 @@ def stage_time():
     din = torch.from_numpy(img).to(dev)
     dout = torch.empty(4 * H, 4 * W, 3, dtype=torch.uint8, device=dev)
     flop = 190 * 200 * 200 * O.flop_per_lr_pixel(4, 23, 64)
-    for mb in (38, 19, 10):
+    for mb in [int(v) for v in os.environ.get('INNFER_MB', '38,19,10').split(',')]:
         lib.innfer_rrdb_set_max_batch(h, mb)
         for it in range(3):
             torch.cuda.synchronize()
