@@ -104,6 +104,34 @@ int innfer_rrdb_upscale_u8(innfer_rrdb* h, const uint8_t* img, int H, int W, int
 int innfer_rrdb_upscale_u8_device(innfer_rrdb* h, const uint8_t* img, int H, int W, int patch_size,
                                   float step, uint8_t* out, void* stream);
 
+/* ---- tile-sharded execution across GPUs (the reference is single-GPU and runs the
+ *      tile loop of run.py:187-197 serially).  One process per GPU; the frame's owner exposes its
+ *      tile buffer and its low-res frame through CUDA IPC, every rank computes a contiguous range
+ *      of the row-major tile list and its last conv stores the finished tiles straight into the
+ *      owner's buffer (peer stores over NVLink, no NCCL, no staging copy); the owner then blends.
+ *      Results are bit-identical for any number of ranks. ------------------------------------- */
+/* owner: (re)allocate the handle's tile buffer for an HxW frame; returns its device pointer */
+int innfer_rrdb_tile_buffer(innfer_rrdb* h, int H, int W, int patch_size, float step, void** ptr,
+                            uint64_t* bytes, uint64_t* bytes_per_tile);
+/* any rank: tiles [t_begin, t_end) of the frame `img` (device or peer pointer; INNFER_U8 HWC BGR or
+ * NCHW F16/F32) -> tiles_base + t * bytes_per_tile (device or peer pointer) */
+int innfer_rrdb_forward_tile_range(innfer_rrdb* h, const void* img, int img_dtype, int H, int W,
+                                   int patch_size, float step, int t_begin, int t_end,
+                                   void* tiles_base, void* stream);
+/* owner: recompose_tensor (+ tensor2np for INNFER_U8) over a complete tile buffer */
+int innfer_rrdb_blend_tiles(innfer_rrdb* h, const void* tiles_base, int H, int W, int patch_size,
+                            float step, void* dst, int dst_dtype, void* stream);
+/* CUDA IPC plumbing for the two calls above (handles are 64 opaque bytes) */
+int innfer_ipc_export(const void* device_ptr, uint8_t handle[64]);
+int innfer_ipc_open(const uint8_t handle[64], void** device_ptr);
+int innfer_ipc_close(void* device_ptr);
+/* plain cudaMalloc / cudaFree on `device` (IPC needs allocations that are not sub-allocated by a
+ * caching allocator) */
+int innfer_device_alloc(int device, uint64_t bytes, void** ptr);
+int innfer_device_free(void* ptr);
+/* host -> device copy into such an allocation (synchronises `stream`) */
+int innfer_device_upload(void* device_dst, const void* host_src, uint64_t bytes, void* stream);
+
 /* ---- tiling geometry: replaces the index arithmetic of extract_patches_2d
  *      (utils/utils.py:349-365).  Writes up to `cap` tiles in row-major order; *n = tile count,
  *      *tile_size = min(H, W, patch_size). */

@@ -47,6 +47,16 @@ _PROTOS = {
     "innfer_rrdb_chop_forward": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _i, _vp]),
     "innfer_rrdb_upscale_u8": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "innfer_rrdb_upscale_u8_device": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
+    "innfer_rrdb_tile_buffer": (_i, [_vp, _i, _i, _i, _f, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_uint64),
+                                     ctypes.POINTER(ctypes.c_uint64)]),
+    "innfer_rrdb_forward_tile_range": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp, _vp]),
+    "innfer_rrdb_blend_tiles": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _i, _vp]),
+    "innfer_ipc_export": (_i, [_vp, _vp]),
+    "innfer_ipc_open": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "innfer_ipc_close": (_i, [_vp]),
+    "innfer_device_alloc": (_i, [_i, ctypes.c_uint64, ctypes.POINTER(_vp)]),
+    "innfer_device_free": (_i, [_vp]),
+    "innfer_device_upload": (_i, [_vp, _vp, ctypes.c_uint64, _vp]),
     "innfer_tiles_plan": (_i, [_i, _i, _i, _f, ctypes.POINTER(Tile), _i, ctypes.POINTER(_i),
                                ctypes.POINTER(_i)]),
     "innfer_image_to_tiles": (_i, [_vp, _i, _i, _i, _i, _i, _f, _vp, _vp]),

@@ -288,24 +288,21 @@ int pick_batch(const innfer_rrdb* h, int ntiles, int p) {
   return best;
 }
 
-int chop_impl(innfer_rrdb* h, const void* src, PixelDType st, int H, int W, int patch, float step, void* dst,
-              PixelDType dt, cudaStream_t stream) {
-  if (!h->finalized) return fail(INNFER_E_STATE, "innfer_rrdb_finalize has not been called");
-  if (!(step >= 0.5f && step <= 1.0f)) return fail(INNFER_E_INVALID, "step must be in [0.5, 1.0]");
-  TilePlan plan;
-  if (make_tile_plan(H, W, patch, step, plan)) return fail(INNFER_E_INVALID, "cannot tile this image size");
-  if (step != 0.5f) return fail(INNFER_E_UNSUPPORTED, "only step=0.5 (run.py:214-215) is implemented");
-  const int ntiles = plan.nty * plan.ntx;
+// Compute tiles [t_begin, t_end) of the plan from `src` and store them at
+// tiles_base + t * tile_bytes.  tiles_base may be peer memory of another GPU (P2P stores over
+// NVLink): the HR_conv1 epilogue writes there directly, no staging copy.
+int compute_tiles(innfer_rrdb* h, const void* src, PixelDType st, const TilePlan& plan, int t_begin, int t_end,
+                  void* tiles_base, cudaStream_t stream) {
   const int p = plan.p, s = h->cfg.scale;
-  const int B = pick_batch(h, ntiles, p);
+  const int n = t_end - t_begin;
+  if (n <= 0) return 0;
+  const int B = pick_batch(h, n, p);
   int rc;
   if ((rc = ensure_workspace(h, B, p, p))) return rc;
-  const int oct = 1 * ((h->cfg.out_nc + 7) / 8);
+  const int oct = (h->cfg.out_nc + 7) / 8;
   const size_t tile_out_elems = (size_t)oct * (s * p) * (s * p) * 8;
-  if (h->out_tiles.ensure((size_t)ntiles * tile_out_elems * h->esz()))
-    return fail(INNFER_E_NOMEM, "tile output allocation failed");
-  for (int t0 = 0; t0 < ntiles; t0 += B) {
-    const int nb = (ntiles - t0) < B ? (ntiles - t0) : B;
+  for (int t0 = t_begin; t0 < t_end; t0 += B) {
+    const int nb = (t_end - t0) < B ? (t_end - t0) : B;
     if (h->cfg.fp16) {
       rc = launch_image_to_tiles(src, st, h->cfg.in_nc, plan, t0, nb, reinterpret_cast<__half*>(h->in_tiles.p),
                                  h->in_ct(), stream);
@@ -316,20 +313,52 @@ int chop_impl(innfer_rrdb* h, const void* src, PixelDType st, int H, int W, int 
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (rc) return fail(INNFER_E_CUDA, "image_to_tiles launch failed");
     ChunkView dv;
-    dv.base = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(h->out_tiles.p) +
-                                        (size_t)t0 * tile_out_elems * h->esz());
+    dv.base = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(tiles_base) + (size_t)t0 * tile_out_elems * h->esz());
     dv.CT = oct;
     dv.chunk0 = 0;
     if ((rc = forward_tiles(h, nb, p, p, dv, stream))) return rc;
   }
+  return 0;
+}
+
+int blend_tiles(innfer_rrdb* h, const void* tiles_base, const TilePlan& plan, void* dst, PixelDType dt,
+                cudaStream_t stream) {
+  const int oct = (h->cfg.out_nc + 7) / 8;
+  int rc;
   if (h->cfg.fp16)
-    rc = launch_blend(reinterpret_cast<const __half*>(h->out_tiles.p), oct, plan, s, h->cfg.out_nc, dst, dt, stream);
+    rc = launch_blend(reinterpret_cast<const __half*>(tiles_base), oct, plan, h->cfg.scale, h->cfg.out_nc, dst, dt, stream);
   else
-    rc = launch_blend_f32(reinterpret_cast<const float*>(h->out_tiles.p), oct, plan, s, h->cfg.out_nc, dst, dt, stream);
+    rc = launch_blend_f32(reinterpret_cast<const float*>(tiles_base), oct, plan, h->cfg.scale, h->cfg.out_nc, dst, dt, stream);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (rc == -2) return fail(INNFER_E_UNSUPPORTED, "tile size with negative blend core (odd tile size)");
   if (rc) return fail(INNFER_E_CUDA, "blend launch failed");
   return 0;
+}
+
+int make_plan_checked(innfer_rrdb* h, int H, int W, int patch, float step, TilePlan& plan) {
+  if (!h->finalized) return fail(INNFER_E_STATE, "innfer_rrdb_finalize has not been called");
+  if (!(step >= 0.5f && step <= 1.0f)) return fail(INNFER_E_INVALID, "step must be in [0.5, 1.0]");
+  if (make_tile_plan(H, W, patch, step, plan)) return fail(INNFER_E_INVALID, "cannot tile this image size");
+  if (step != 0.5f) return fail(INNFER_E_UNSUPPORTED, "only step=0.5 (run.py:214-215) is implemented");
+  return 0;
+}
+
+size_t tile_bytes(const innfer_rrdb* h, const TilePlan& plan) {
+  const int oct = (h->cfg.out_nc + 7) / 8;
+  const size_t P = (size_t)h->cfg.scale * plan.p;
+  return (size_t)oct * P * P * 8 * h->esz();
+}
+
+int chop_impl(innfer_rrdb* h, const void* src, PixelDType st, int H, int W, int patch, float step, void* dst,
+              PixelDType dt, cudaStream_t stream) {
+  TilePlan plan;
+  int rc;
+  if ((rc = make_plan_checked(h, H, W, patch, step, plan))) return rc;
+  const int ntiles = plan.nty * plan.ntx;
+  if (h->out_tiles.ensure((size_t)ntiles * tile_bytes(h, plan)))
+    return fail(INNFER_E_NOMEM, "tile output allocation failed");
+  if ((rc = compute_tiles(h, src, st, plan, 0, ntiles, h->out_tiles.p, stream))) return rc;
+  return blend_tiles(h, h->out_tiles.p, plan, dst, dt, stream);
 }
 
 }  // namespace
@@ -547,6 +576,86 @@ int innfer_rrdb_upscale_u8(innfer_rrdb* h, const uint8_t* img, int H, int W, int
   if (rc) return rc;
   CU_TRY(cudaMemcpyAsync(out, h->img_out.p, ob, cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int innfer_rrdb_tile_buffer(innfer_rrdb* h, int H, int W, int patch_size, float step, void** ptr, uint64_t* bytes,
+                            uint64_t* bytes_per_tile) {
+  if (!h || !ptr || !bytes) return fail(INNFER_E_INVALID, "null argument");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  TilePlan plan;
+  if ((rc = make_plan_checked(h, H, W, patch_size, step, plan))) return rc;
+  const size_t tb = tile_bytes(h, plan), total = (size_t)plan.nty * plan.ntx * tb;
+  if (h->out_tiles.ensure(total)) return fail(INNFER_E_NOMEM, "tile output allocation failed");
+  *ptr = h->out_tiles.p;
+  *bytes = h->out_tiles.bytes;
+  if (bytes_per_tile) *bytes_per_tile = tb;
+  return 0;
+}
+
+int innfer_rrdb_forward_tile_range(innfer_rrdb* h, const void* img, int img_dtype, int H, int W, int patch_size,
+                                   float step, int t_begin, int t_end, void* tiles_base, void* stream) {
+  if (!h || !img || !tiles_base) return fail(INNFER_E_INVALID, "null argument");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  TilePlan plan;
+  if ((rc = make_plan_checked(h, H, W, patch_size, step, plan))) return rc;
+  if (t_begin < 0 || t_end > plan.nty * plan.ntx || t_begin > t_end) return fail(INNFER_E_INVALID, "bad tile range");
+  if (img_dtype == INNFER_U8 && h->cfg.in_nc != 3) return fail(INNFER_E_INVALID, "uint8 input needs a 3-channel model");
+  return compute_tiles(h, img, to_pix(img_dtype), plan, t_begin, t_end, tiles_base, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int innfer_rrdb_blend_tiles(innfer_rrdb* h, const void* tiles_base, int H, int W, int patch_size, float step, void* dst,
+                            int dst_dtype, void* stream) {
+  if (!h || !tiles_base || !dst) return fail(INNFER_E_INVALID, "null argument");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  TilePlan plan;
+  if ((rc = make_plan_checked(h, H, W, patch_size, step, plan))) return rc;
+  return blend_tiles(h, tiles_base, plan, dst, to_pix(dst_dtype), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int innfer_ipc_export(const void* device_ptr, uint8_t handle[64]) {
+  if (!device_ptr || !handle) return fail(INNFER_E_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+  cudaIpcMemHandle_t hd;
+  CU_TRY(cudaIpcGetMemHandle(&hd, const_cast<void*>(device_ptr)));
+  std::memcpy(handle, &hd, 64);
+  return 0;
+}
+
+int innfer_ipc_open(const uint8_t handle[64], void** device_ptr) {
+  if (!handle || !device_ptr) return fail(INNFER_E_INVALID, "null argument");
+  cudaIpcMemHandle_t hd;
+  std::memcpy(&hd, handle, 64);
+  CU_TRY(cudaIpcOpenMemHandle(device_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int innfer_ipc_close(void* device_ptr) {
+  if (!device_ptr) return 0;
+  CU_TRY(cudaIpcCloseMemHandle(device_ptr));
+  return 0;
+}
+
+int innfer_device_alloc(int device, uint64_t bytes, void** ptr) {
+  if (!ptr) return fail(INNFER_E_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaMalloc(ptr, bytes));
+  return 0;
+}
+
+int innfer_device_upload(void* device_dst, const void* host_src, uint64_t bytes, void* stream) {
+  if (!device_dst || !host_src) return fail(INNFER_E_INVALID, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CU_TRY(cudaMemcpyAsync(device_dst, host_src, bytes, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int innfer_device_free(void* ptr) {
+  if (ptr) CU_TRY(cudaFree(ptr));
   return 0;
 }
 

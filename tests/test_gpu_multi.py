@@ -1,0 +1,74 @@
+"""Tile-sharded execution on 2 GPUs (skipped on a single-GPU box): the stitched result must be
+bit-identical to the single-GPU result."""
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+H, W, PATCH = 300, 520, 200
+
+
+def _worker(rank, world, port, q):
+    try:
+        _worker_impl(rank, world, port, q)
+    except Exception:  # report instead of leaving the parent waiting for its timeout
+        import traceback
+        q.put((rank, traceback.format_exc()))
+
+
+def _worker_impl(rank, world, port, q):
+    import torch.distributed as dist
+
+    from innfer_b200 import multi_gpu as MG
+    from innfer_b200.engine import RRDBEngine
+    from oracle import rrdb_oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sd = O.make_state_dict(scale=4, nb=2, seed=1)
+    eng = RRDBEngine.from_state_dict(sd, dict(in_nc=3, out_nc=3, nf=64, nb=2, gc=32, scale=4, plus=False),
+                                     torch.device("cuda", rank), fp16=True)
+    be = MG.NativeTileBackend(eng, H, W, PATCH, 0.5)
+    up = MG.TileShardedUpscaler(be, dist)
+    outs = {}
+    for f in range(3):
+        img = np.random.default_rng(50 + f).integers(0, 256, (H, W, 3), dtype=np.uint8)
+        res = up.upscale(f, img if MG.frame_owner(f, world) == rank else None)
+        if res is not None:
+            outs[f] = res
+    up.close()
+    # single-GPU result of the frames this rank owned, on the same engine
+    for f in list(outs):
+        img = np.random.default_rng(50 + f).integers(0, 256, (H, W, 3), dtype=np.uint8)
+        outs[f] = (outs[f], eng.upscale_u8(img, PATCH, 0.5))
+    q.put((rank, outs))
+    dist.destroy_process_group()
+
+
+def test_tile_sharded_two_gpus_bit_identical():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    seen = set()
+    for _ in procs:
+        rank, outs = q.get(timeout=120)
+        assert not isinstance(outs, str), outs
+        for f, (sharded, single) in outs.items():
+            assert np.array_equal(sharded, single), f
+            assert 0.1 < ((single > 0) & (single < 255)).mean()
+            seen.add(f)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert seen == {0, 1, 2}
