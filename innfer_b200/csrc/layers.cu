@@ -91,6 +91,21 @@ int conv_layer_build(ConvLayer& L, const float* w, const float* bias, int Cout, 
               }
     }
   }
+  // dx-as-N packing for the Cout == 32 convs: [kslab][dy][kchunk][dx*32 + co][8]
+  std::vector<__half> packed_dx;
+  if (up == 1 && Cout == 32) {
+    packed_dx.resize((size_t)kslabs * 3 * 2 * 96 * 8);
+    size_t o = 0;
+    for (int ks = 0; ks < kslabs; ++ks)
+      for (int dy = 0; dy < 3; ++dy)
+        for (int kc = 0; kc < 2; ++kc)
+          for (int n = 0; n < 96; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int ci = ks * 16 + kc * 8 + e, dx = n / 32, co = n % 32;
+              const float v = ci < Cin ? w[(((size_t)co * Cin + ci) * 3 + dy) * 3 + dx] : 0.f;
+              packed_dx[o++] = __float2half_rn(v);
+            }
+  }
   L.w_bytes = packed.size() * sizeof(__half);
   std::vector<float> hb(N, 0.f);
   if (bias)
@@ -102,7 +117,11 @@ int conv_layer_build(ConvLayer& L, const float* w, const float* bias, int Cout, 
   if ((e = cudaMalloc(&L.d_w, L.w_bytes)) != cudaSuccess ||
       (e = cudaMalloc(&L.d_bias, N * sizeof(float))) != cudaSuccess ||
       (e = cudaMemcpy(L.d_w, packed.data(), L.w_bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
-      (e = cudaMemcpy(L.d_bias, hb.data(), N * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+      (e = cudaMemcpy(L.d_bias, hb.data(), N * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (!packed_dx.empty() &&
+       ((e = cudaMalloc(&L.d_wdx, packed_dx.size() * sizeof(__half))) != cudaSuccess ||
+        (e = cudaMemcpy(L.d_wdx, packed_dx.data(), packed_dx.size() * sizeof(__half), cudaMemcpyHostToDevice)) !=
+            cudaSuccess))) {
     err = std::string("cuda error while uploading weights: ") + cudaGetErrorString(e);
     return -3;
   }
@@ -113,18 +132,21 @@ void conv_layer_free(ConvLayer& L) {
   if (L.d_w) cudaFree(L.d_w);
   if (L.d_bias) cudaFree(L.d_bias);
   if (L.d_w32) cudaFree(L.d_w32);
+  if (L.d_wdx) cudaFree(L.d_wdx);
+  L.d_wdx = nullptr;
   L.d_w = nullptr;
   L.d_bias = nullptr;
   L.d_w32 = nullptr;
 }
 
-const CUtensorMap* TmapCache::get(const void* base, int B, int CT, int H, int W, int J, int& rc) {
-  auto key = std::make_tuple(base, B, CT, H, W, J);
+const CUtensorMap* TmapCache::get(const void* base, int B, int CT, int H, int W, int box_w, int& rc) {
+  auto key = std::make_tuple(base, B, CT, H, W, box_w);
   auto it = maps_.find(key);
   rc = 0;
   if (it != maps_.end()) return &it->second->m;
   Slot* s = new Slot();
-  rc = encode_act_tmap(&s->m, base, B, CT, H, W, J);
+  rc = box_w > 0 ? encode_act_tmap(&s->m, base, B, CT, H, W, box_w)
+                 : encode_act_tmap_merged(&s->m, base, B, CT, H, W, -box_w);
   if (rc != 0) {
     delete s;
     return nullptr;
@@ -158,6 +180,40 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
   ConvTcParams p;
   std::memset(&p, 0, sizeof(p));
   const int N = L.N;
+  static const int dx_mode = getenv("INNFER_DX") ? atoi(getenv("INNFER_DX")) : 1;
+  static const int dx_j = getenv("INNFER_DX_J") ? atoi(getenv("INNFER_DX_J")) : 4;
+  if (dx_mode && L.d_wdx != nullptr && ep.res1.base == nullptr && ep.res2.base == nullptr && out_nchunks == 4) {
+    // dx-taps-as-N kernel: tiles of 16 x (8J-2) outputs
+    const int J = dx_j < 2 ? 2 : (dx_j > 5 ? 5 : dx_j);
+    const int OW = 8 * J - 2;
+    p.B = B;
+    p.H = H;
+    p.W = W;
+    p.in_chunk0 = in.chunk0;
+    p.kslabs = L.Cin_pad / 16;
+    p.J = J;
+    p.bands = (H + kPatchRows - 1) / kPatchRows;
+    p.cps = (W + OW - 1) / OW;
+    p.nphase = 1;
+    p.up = 1;
+    p.Hout = H;
+    p.Wout = W;
+    int S = (232448 - 1024) / conv_dx_stage_bytes(J);
+    p.stages = S > 8 ? 8 : S;
+    p.out = out.base;
+    p.out_CT = out.CT;
+    p.out_chunk0 = out.chunk0;
+    p.out_nchunks = out_nchunks;
+    p.w = L.d_wdx;
+    p.bias = L.d_bias;
+    p.lrelu = ep.lrelu ? 1 : 0;
+    p.slope = ep.slope;
+    int rc = 0;
+    const CUtensorMap* tm = cache.get(in.base, B, in.CT, H, W, J <= 4 ? -8 * J : 8 * J, rc);
+    p.debug = J <= 4 ? 4 : 0;  // bit 2: merged 4-D tensor map
+    if (!tm) return rc ? rc : -5;
+    return launch_conv_dx(tm, p, num_sms, stream);
+  }
   const int J = choose_J(W, N);
   p.B = B;
   p.H = H;
@@ -209,7 +265,7 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
   static const int dbg = getenv("INNFER_DEBUG") ? atoi(getenv("INNFER_DEBUG")) : 0;
   p.debug = dbg;
   int rc = 0;
-  const CUtensorMap* tm = cache.get(in.base, B, in.CT, H, W, J, rc);
+  const CUtensorMap* tm = cache.get(in.base, B, in.CT, H, W, 8 * J + 2, rc);
   if (!tm) return rc ? rc : -5;
   return launch_conv_tc(tm, p, N, num_sms, stream);
 }

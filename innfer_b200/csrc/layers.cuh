@@ -36,6 +36,7 @@ struct ConvLayer {
   uint8_t tap_hx[kMaxPhases][kMaxTaps] = {};
   int max_taps = 0;
   __half* d_w = nullptr;   // device, packed [phase][kslab][tap][2][N][8]
+  __half* d_wdx = nullptr; // device, dx-as-N packing [kslab][dy][2][dx*32+co][8] (Cout == 32, up == 1 only)
   float* d_bias = nullptr; // device, [N]
   size_t w_bytes = 0;
   // fp32 copies (OIHW + bias) kept on the device for the fp32-mode direct kernel
@@ -56,10 +57,11 @@ int conv_layer_build(ConvLayer& L, const float* w_oihw, const float* bias, int C
                      int up, std::string& err);
 void conv_layer_free(ConvLayer& L);
 
-// Cache of encoded TMA descriptors keyed by (base, B, CT, H, W, J).
+// Cache of encoded TMA descriptors keyed by (base, B, CT, H, W, box width in pixels).
 class TmapCache {
  public:
-  const CUtensorMap* get(const void* base, int B, int CT, int H, int W, int J, int& rc);
+  // box_w > 0: 5-D map with a box of box_w pixels; box_w < 0: merged 4-D map with -box_w pixels per row
+  const CUtensorMap* get(const void* base, int B, int CT, int H, int W, int box_w, int& rc);
   void clear() { maps_.clear(); }
 
  private:

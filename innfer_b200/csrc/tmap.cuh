@@ -1,5 +1,5 @@
 // Host helper: encode the 5-D TMA descriptor of a planar-chunk activation tensor
-// [B][CT][H][W][8] fp16 with a (8, 8J+2, 18, 2, 1) box. cuTensorMapEncodeTiled is resolved through
+// [B][CT][H][W][8] fp16 with a (8, box_w, 18, 2, 1) box. cuTensorMapEncodeTiled is resolved through
 // cudaGetDriverEntryPoint so the library never links libcuda at build time.
 #pragma once
 #include <cuda.h>
@@ -7,5 +7,10 @@
 
 namespace innfer {
 // Returns 0 on success, a CUresult/cudaError-style non-zero code otherwise.
-int encode_act_tmap(CUtensorMap* out, const void* base, int B, int CT, int H, int W, int J);
+int encode_act_tmap(CUtensorMap* out, const void* base, int B, int CT, int H, int W, int box_w);
+// Same tensor seen as 4-D [B][CT][H][W*8]: the 8 channels of a chunk and the W pixels are merged
+// into one contiguous inner dimension so that a box row is box_w*16 bytes (TMA moves whole rows;
+// with the 5-D form every 16-byte pixel chunk is its own request and the TMA unit becomes the
+// bottleneck).  box_w * 8 must be <= 256 elements.  Box = (box_w*8, 18, 2, 1), OOB -> zero.
+int encode_act_tmap_merged(CUtensorMap* out, const void* base, int B, int CT, int H, int W, int box_w);
 }  // namespace innfer
