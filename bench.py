@@ -80,8 +80,13 @@ def cpu_reference_rate(n_tiles, threads=None):
     """Times the oracle (CPU restatement of the reference forward, fp32, torch CPU) on the first
     n_tiles 200x200 tiles of frame 0; returns (output Mpix/s extrapolated to a frame, seconds, threads)."""
     from oracle import rrdb_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    if threads is None:
+        # torchrun exports OMP_NUM_THREADS=1; the CPU legs use every core this process may run on
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(max(1, threads))
     sd = O.make_state_dict(scale=SCALE, nb=NB, nf=NF, seed=0)
     x = O.np2tensor(synth_frame(0))
     patches, _, _ = O.extract_patches(x, PATCH, STEP)
@@ -151,10 +156,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from innfer_b200 import _native as N
+    from innfer_b200 import synth
     from innfer_b200.engine import RRDBEngine
-    from oracle import rrdb_oracle as O  # weights recipe + FLOP accounting + CPU baseline only
 
-    sd = O.make_state_dict(scale=SCALE, nb=NB, nf=NF, seed=0)
+    sd = synth.make_state_dict(scale=SCALE, nb=NB, nf=NF, seed=0)
     cfg = dict(in_nc=3, out_nc=3, nf=NF, nb=NB, gc=32, scale=SCALE, plus=False)
     eng = RRDBEngine.from_state_dict(sd, cfg, dev, fp16=True)
     if args.max_batch:
@@ -223,7 +228,7 @@ def main():
         return
 
     peaks, peak_src = measured_peaks()
-    flop_step = 190 * PATCH * PATCH * O.flop_per_lr_pixel(SCALE, NB, NF)
+    flop_step = 190 * PATCH * PATCH * synth.flop_per_lr_pixel(SCALE, NB, NF)
     roof = None
     if conv_launches:
         achieved = flop_step * args.steps / (conv_ms * 1e-3) / 1e12
@@ -234,7 +239,7 @@ def main():
             with open(tpath) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch_avg")
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "conv_tc_kernel<N> (all %d conv launches of a step)" % (conv_launches // args.steps),
+                "traffic": traffic, "kernel": "conv_dx_kernel + conv_tc_kernel<N> (all %d conv launches of a step)" % (conv_launches // args.steps),
                 "flop_per_launch_avg": flop_step * args.steps / conv_launches,
                 "avg_launch_ms": conv_ms / conv_launches, "peak_source": peak_src}
     cpu = None

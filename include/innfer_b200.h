@@ -72,7 +72,8 @@ int innfer_rrdb_load(innfer_rrdb* h, const char* key, const float* host_data, co
 /* verifies that every parameter arrived (strict load), repacks OIHW -> kernel layout, uploads. */
 int innfer_rrdb_finalize(innfer_rrdb* h);
 void innfer_rrdb_destroy(innfer_rrdb* h);
-/* upper bound of tiles pushed through the trunk per batch (memory / L2 trade-off), default 32 */
+/* upper bound of tiles pushed through the trunk per batch (workspace memory vs. launch count);
+ * default 95 (two batches per 1080p frame, ~20 GB of workspace at 4x) */
 int innfer_rrdb_set_max_batch(innfer_rrdb* h, int max_tiles);
 
 /* device-side timing of the conv sequence (CUDA events on the launching stream around every

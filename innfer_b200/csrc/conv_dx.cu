@@ -64,16 +64,23 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
 
   const int Wh = 8 * p.J;                                  // smem tile width in pixels (no x halo)
   const int a_bytes = 2 * kHaloRows * Wh * 16;             // multiple of 128
-  const int w_bytes = 3 * 2 * kDxN * 16;                   // 9216
-  const int stage_bytes = a_bytes + w_bytes;
+  const int w_bytes = 3 * 2 * kDxN * 16;                   // 9216 per 16-channel slab
+  // debug bit 3: all weight slabs of this conv (kslabs x 9216 B <= 92 KB) stay resident in shared
+  // memory for the whole persistent kernel instead of travelling with every stage;
+  // bit 4: the resident block sits in front of the stage ring instead of behind it.
+  const bool resident = (p.debug & 8) != 0;
+  const int stage_bytes = resident ? a_bytes : a_bytes + w_bytes;
   const int S = p.stages;
+  const uint32_t w_total = resident ? (uint32_t)p.kslabs * w_bytes : 0u;
+  const uint32_t ring_off = (resident && (p.debug & 16)) ? w_total : 0u;
 
-  uint8_t* bar_base = smem + (size_t)S * stage_bytes;
+  uint8_t* bar_base = smem + (size_t)S * stage_bytes + w_total;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tfull_bar = empty_bar + S;                     // one per slot: accumulator complete
   uint64_t* slot_bar = tfull_bar + kDxSlots;               // one per slot: accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_bar + kDxSlots);
+  uint64_t* wfull_bar = slot_bar + kDxSlots;               // resident weights have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
 
   if (threadIdx.x == 0) {
@@ -82,6 +89,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
+    mbar_init(smem_u32(wfull_bar), 1);
     for (int i = 0; i < kDxSlots; ++i) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
       mbar_init(smem_u32(&slot_bar[i]), 8);
@@ -97,11 +105,19 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t smem_base = smem_u32(smem) + ring_off;
+  const uint32_t w_base = ring_off ? smem_u32(smem) : smem_base + (uint32_t)S * stage_bytes;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      if (resident) {
+        const uint32_t wb = smem_u32(wfull_bar);
+        mbar_expect_tx(wb, w_total);
+        for (int ks = 0; ks < p.kslabs; ++ks)
+          bulk_load(w_base + (uint32_t)ks * w_bytes, reinterpret_cast<const uint8_t*>(p.w) + (size_t)ks * w_bytes,
+                    w_bytes, wb);
+      }
       int s = 0;
       uint32_t ph = 0;
       DxIter ti;
@@ -112,12 +128,13 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
           const uint32_t fb = smem_u32(&full_bar[s]);
           const uint32_t dstA = smem_base + (uint32_t)s * stage_bytes;
-          mbar_expect_tx(fb, (uint32_t)(a_bytes + w_bytes));
+          mbar_expect_tx(fb, (uint32_t)(resident ? a_bytes : a_bytes + w_bytes));
           if (p.debug & 4)
             tma_load_4d(dstA, &tmap_in, fb, (x0 - 1) * 8, y0 - 1, p.in_chunk0 + 2 * ks, ti.b);
           else
             tma_load_5d(dstA, &tmap_in, fb, 0, x0 - 1, y0 - 1, p.in_chunk0 + 2 * ks, ti.b);
-          bulk_load(dstA + a_bytes, reinterpret_cast<const uint8_t*>(p.w) + (size_t)ks * w_bytes, w_bytes, fb);
+          if (!resident)
+            bulk_load(dstA + a_bytes, reinterpret_cast<const uint8_t*>(p.w) + (size_t)ks * w_bytes, w_bytes, fb);
           if (++s == S) {
             s = 0;
             ph ^= 1u;
@@ -141,6 +158,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     uint32_t use0 = 0;      // how many times slot0's ring position has wrapped
     DxIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
+    if (resident) mbar_wait(smem_u32(wfull_bar), 0u);
     for (; ti.valid(); ti.advance()) {
       const int jeff = ti.jeff();
       for (int ks = 0; ks < p.kslabs; ++ks) {
@@ -148,7 +166,8 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         tc_fence_after();
         const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
         const uint32_t a_lo = ((sa & 0x3FFFFu) >> 4) | (a_lbo << 16);
-        const uint32_t b_lo = (((sa + a_bytes) & 0x3FFFFu) >> 4) | (b_lbo << 16);
+        const uint32_t wsrc = resident ? w_base + (uint32_t)ks * w_bytes : sa + a_bytes;
+        const uint32_t b_lo = ((wsrc & 0x3FFFFu) >> 4) | (b_lbo << 16);
         const uint32_t first = ks != 0 ? 1u : 0u;
         const bool last = ks == p.kslabs - 1;
         for (int j = 0; j < jeff; ++j) {
@@ -158,7 +177,7 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
             slot -= kDxSlots;
             ++use;
           }
-          if (ks == 0) {
+          if (ks == 0 && !(p.debug & 32)) {
             mbar_wait(smem_u32(&slot_bar[slot]), (use & 1u) ^ 1u);  // previous user of the slot drained
             tc_fence_after();
           }
@@ -276,10 +295,14 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
 
 }  // namespace
 
-int conv_dx_stage_bytes(int J) { return 2 * kHaloRows * 8 * J * 16 + 3 * 2 * kDxN * 16; }
+int conv_dx_stage_bytes(int J) { return 2 * kHaloRows * 8 * J * 16; }
+int conv_dx_weight_bytes(int kslabs) { return kslabs * 3 * 2 * kDxN * 16; }
 
 int launch_conv_dx(const CUtensorMap* tmap_in, const ConvTcParams& p, int num_sms, cudaStream_t stream) {
-  const size_t smem_bytes = (size_t)p.stages * conv_dx_stage_bytes(p.J) + 1024;
+  const bool resident = (p.debug & 8) != 0;
+  const size_t smem_bytes = resident
+                                ? (size_t)p.stages * conv_dx_stage_bytes(p.J) + conv_dx_weight_bytes(p.kslabs) + 1024
+                                : (size_t)p.stages * (conv_dx_stage_bytes(p.J) + conv_dx_weight_bytes(1)) + 1024;
   cudaError_t e = cudaFuncSetAttribute(conv_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int)e;
   const int num_tiles = p.B * p.bands * p.cps;

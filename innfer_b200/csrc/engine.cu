@@ -70,7 +70,7 @@ struct innfer_rrdb {
   int num_sms = 148;
   int n_up = 0, up_factor = 2;
   bool finalized = false;
-  int max_batch = 38;
+  int max_batch = 95;
   std::map<std::string, Param> params;
   // layers in execution order
   ConvLayer fea, lr_conv, hr0, hr1;

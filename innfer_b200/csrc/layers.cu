@@ -198,7 +198,10 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
     p.up = 1;
     p.Hout = H;
     p.Wout = W;
-    int S = (232448 - 1024) / conv_dx_stage_bytes(J);
+    static const int dx_res = getenv("INNFER_DX_RES") ? atoi(getenv("INNFER_DX_RES")) : 1;
+    int S = dx_res ? (232448 - 1024 - conv_dx_weight_bytes(p.kslabs)) / conv_dx_stage_bytes(J)
+                   : (232448 - 1024) / (conv_dx_stage_bytes(J) + conv_dx_weight_bytes(1));
+    if (S < 2) return -4;
     p.stages = S > 8 ? 8 : S;
     p.out = out.base;
     p.out_CT = out.CT;
@@ -210,7 +213,8 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
     p.slope = ep.slope;
     int rc = 0;
     const CUtensorMap* tm = cache.get(in.base, B, in.CT, H, W, J <= 4 ? -8 * J : 8 * J, rc);
-    p.debug = J <= 4 ? 4 : 0;  // bit 2: merged 4-D tensor map
+    static const int dx_dbg = getenv("INNFER_DX_DBG") ? atoi(getenv("INNFER_DX_DBG")) : 0;
+    p.debug = (J <= 4 ? 4 : 0) | (dx_res == 1 ? 8 : 0) | (dx_res == 2 ? 24 : 0) | dx_dbg;  // bit 2: merged 4-D tensor map
     if (!tm) return rc ? rc : -5;
     return launch_conv_dx(tm, p, num_sms, stream);
   }

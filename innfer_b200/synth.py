@@ -1,0 +1,37 @@
+"""Synthetic weights and work accounting for benchmarks and demos (SURVEY.md 8d recipe).
+
+``make_state_dict`` builds the network through the package's own factory with PyTorch's default
+initialisation under a fixed seed and sets the last conv's bias to 0.5, which keeps ~60 % of the
+output pixels un-clipped so uint8 comparisons are meaningful.  (tests/ check that this reproduces
+the reference's initialisation bit for bit.)
+"""
+import torch
+
+from .architectures import get_network
+from .utils.defaults import get_network_G_config
+
+
+def make_state_dict(scale=4, nb=23, nf=64, in_nc=3, out_nc=3, seed=0, last_bias=0.5):
+    torch.manual_seed(seed)
+    net = get_network(get_network_G_config({"type": "esrgan", "nb": nb, "nf": nf, "in_nc": in_nc, "out_nc": out_nc}, scale))
+    sd = net.state_dict()
+    if last_bias is not None:
+        last = max((int(k.split(".")[1]) for k in sd if k.count(".") == 2), default=None)
+        sd["model.%d.bias" % last].fill_(last_bias)
+    return sd
+
+
+def flop_per_lr_pixel(scale=4, nb=23, nf=64, in_nc=3, out_nc=3):
+    """Algorithmic conv FLOPs per low-res pixel pushed through RRDBNet (real channels only):
+    35 853 696 for the 4x / 23-block / nf=64 net."""
+    mac = 9 * in_nc * nf
+    rdb = 9 * (sum((nf + 32 * k) * 32 for k in range(4)) + (nf + 128) * nf)
+    mac += nb * 3 * rdb + 9 * nf * nf
+    n_up = {1: 0, 2: 1, 3: 1, 4: 2, 8: 3}[scale]
+    f = 3 if scale == 3 else 2
+    res = 1
+    for _ in range(n_up):
+        res *= f * f
+        mac += res * 9 * nf * nf
+    mac += res * 9 * nf * nf + res * 9 * nf * out_nc
+    return 2 * mac

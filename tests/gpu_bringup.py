@@ -188,6 +188,30 @@ def stage_prof():
     return True
 
 
+def stage_pix():
+    """HBM-bound kernels at benchmark sizes: image->tiles, blend (+uint8), colour fix (for ncu)."""
+    lib = N.load()
+    H, W, s = 1080, 1920, 4
+    img = torch.from_numpy(np.random.default_rng(0).integers(0, 256, (H, W, 3), dtype=np.uint8)).to(dev)
+    nt = 190
+    tiles_in = torch.empty(nt, 2, 200, 200, 8, dtype=torch.float16, device=dev)
+    tiles_out = torch.rand(nt, 1, 800, 800, 8, device=dev).half()
+    out = torch.empty(s * H, s * W, 3, dtype=torch.uint8, device=dev)
+    outf = torch.empty(1, 3, s * H, s * W, dtype=torch.float16, device=dev)
+    for _ in range(3):
+        N.check(lib.innfer_image_to_tiles(img.data_ptr(), N.INNFER_U8, 3, H, W, 200, 0.5, tiles_in.data_ptr(), None))
+        N.check(lib.innfer_blend(tiles_out.data_ptr(), H, W, 200, 0.5, s, 3, out.data_ptr(), N.INNFER_U8, None))
+        N.check(lib.innfer_blend(tiles_out.data_ptr(), H, W, 200, 0.5, s, 3, outf.data_ptr(), N.INNFER_F16, None))
+    h, w = 720, 1280
+    lr = torch.from_numpy(np.random.default_rng(1).integers(0, 256, (h, w, 3), dtype=np.uint8)).to(dev)
+    sr = torch.from_numpy(np.random.default_rng(2).integers(0, 256, (4 * h, 4 * w, 3), dtype=np.uint8)).to(dev)
+    cf = torch.empty_like(sr)
+    for _ in range(3):
+        N.check(lib.innfer_color_fix(lr.data_ptr(), h, w, sr.data_ptr(), 4 * h, 4 * w, cf.data_ptr(), None))
+    torch.cuda.synchronize()
+    return True
+
+
 def stage_time():
     lib = N.load()
     sd = O.make_state_dict(scale=4, nb=23, seed=0)
@@ -222,6 +246,6 @@ if __name__ == "__main__":
     ap.add_argument("--stage", required=True)
     a = ap.parse_args()
     t0 = time.time()
-    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof}[a.stage]()
+    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "pix": stage_pix}[a.stage]()
     print("STAGE %s %s (%.1fs)" % (a.stage, "OK" if ok else "FAILED", time.time() - t0))
     sys.exit(0 if ok else 1)

@@ -131,6 +131,15 @@ def test_model_path_resolution(tmp_path, monkeypatch):
     assert R.check_model_path("4x_rand_rrdb.pth", None) == os.path.join("models", "4x_rand_rrdb.pth")
 
 
+def test_synth_recipe_matches_reference_init():
+    from innfer_b200 import synth
+    for scale, nb in ((4, 2), (1, 1), (8, 1)):
+        a, b = synth.make_state_dict(scale=scale, nb=nb, seed=3), O.make_state_dict(scale=scale, nb=nb, seed=3)
+        assert list(a.keys()) == list(b.keys())
+        assert all(torch.equal(a[k], b[k]) for k in a)
+    assert synth.flop_per_lr_pixel(4, 23, 64) == 35853696 == O.flop_per_lr_pixel(4, 23, 64)
+
+
 def test_unknown_architectures_fail_loudly():
     with pytest.raises(NotImplementedError):
         get_network({"type": "sr_resnet"})
