@@ -297,7 +297,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
               o.y = *reinterpret_cast<const uint32_t*>(&h1);
               o.z = *reinterpret_cast<const uint32_t*>(&h2);
               o.w = *reinterpret_cast<const uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(op + (size_t)ch * oplane * 8) = o;
+              if (p.out_compact4) {
+                *reinterpret_cast<uint2*>(p.out + ((size_t)c.b * oplane + opix) * 4) = make_uint2(o.x, o.y);
+              } else {
+                *reinterpret_cast<uint4*>(op + (size_t)ch * oplane * 8) = o;
+              }
             }
           }
         }

@@ -54,6 +54,7 @@ struct ConvTcParams {
   // destination
   __half* out;
   int out_CT, out_chunk0, out_nchunks;
+  int out_compact4;  // final conv only: store channels 0..3 as [tile][Hout][Wout][4] fp16 (8 B / pixel)
   // weights / bias
   const __half* w;       // packed [phase][kslab][tap][2][N][8]
   const float* bias;     // [N]

@@ -181,23 +181,23 @@ int ensure_workspace(innfer_rrdb* h, int B, int hgt, int wid) {
 
 // Forward B tiles that already sit in h->in_tiles ([B][in_ct][hgt][wid][8]); the result
 // ([B][1 or 2][s*hgt][s*wid][8], out_nc channels in chunk 0..) is written to `dst`.
-int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, cudaStream_t st);
+int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool compact, cudaStream_t st);
 
-int forward_tiles(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, cudaStream_t st) {
-  if (!h->profiling) return forward_tiles_impl(h, B, hgt, wid, dst, st);
+int forward_tiles(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool compact, cudaStream_t st) {
+  if (!h->profiling) return forward_tiles_impl(h, B, hgt, wid, dst, compact, st);
   cudaEvent_t a, b;
   CU_TRY(cudaEventCreate(&a));
   CU_TRY(cudaEventCreate(&b));
   CU_TRY(cudaEventRecord(a, st));
   const uint64_t l0 = g_launches.load();
-  int rc = forward_tiles_impl(h, B, hgt, wid, dst, st);
+  int rc = forward_tiles_impl(h, B, hgt, wid, dst, compact, st);
   CU_TRY(cudaEventRecord(b, st));
   h->prof_events.emplace_back(a, b);
   h->prof_conv_launches += g_launches.load() - l0;
   return rc;
 }
 
-int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, cudaStream_t st) {
+int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool compact, cudaStream_t st) {
   const int nfc = h->nf_ct(), catc = h->cat_ct();
   const int gcc = 32 / 8;
   int rc;
@@ -262,7 +262,9 @@ int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, c
   ChunkView o = view(h->hrbuf[pp], nfc, 0);
   if ((rc = run_conv(h, h->hr0, cur, B, ch, cw, o, nfc, act, st))) return rc;
   const int out_chunks = (h->cfg.out_nc + 7) / 8;
-  if ((rc = run_conv(h, h->hr1, o, B, ch, cw, dst, out_chunks, plain, st))) return rc;
+  Epilogue last;
+  last.compact4 = compact;
+  if ((rc = run_conv(h, h->hr1, o, B, ch, cw, dst, out_chunks, last, st))) return rc;
   return 0;
 }
 
@@ -288,6 +290,9 @@ int pick_batch(const innfer_rrdb* h, int ntiles, int p) {
   return best;
 }
 
+// Tile outputs of the chop path use the compact [tile][P][P][4] fp16 layout when it applies.
+bool compact_tiles(const innfer_rrdb* h) { return h->cfg.fp16 && h->cfg.out_nc <= 4; }
+
 // Compute tiles [t_begin, t_end) of the plan from `src` and store them at
 // tiles_base + t * tile_bytes.  tiles_base may be peer memory of another GPU (P2P stores over
 // NVLink): the HR_conv1 epilogue writes there directly, no staging copy.
@@ -300,7 +305,8 @@ int compute_tiles(innfer_rrdb* h, const void* src, PixelDType st, const TilePlan
   int rc;
   if ((rc = ensure_workspace(h, B, p, p))) return rc;
   const int oct = (h->cfg.out_nc + 7) / 8;
-  const size_t tile_out_elems = (size_t)oct * (s * p) * (s * p) * 8;
+  const bool compact = compact_tiles(h);
+  const size_t tile_out_elems = compact ? (size_t)(s * p) * (s * p) * 4 : (size_t)oct * (s * p) * (s * p) * 8;
   for (int t0 = t_begin; t0 < t_end; t0 += B) {
     const int nb = (t_end - t0) < B ? (t_end - t0) : B;
     if (h->cfg.fp16) {
@@ -316,7 +322,7 @@ int compute_tiles(innfer_rrdb* h, const void* src, PixelDType st, const TilePlan
     dv.base = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(tiles_base) + (size_t)t0 * tile_out_elems * h->esz());
     dv.CT = oct;
     dv.chunk0 = 0;
-    if ((rc = forward_tiles(h, nb, p, p, dv, stream))) return rc;
+    if ((rc = forward_tiles(h, nb, p, p, dv, compact, stream))) return rc;
   }
   return 0;
 }
@@ -326,7 +332,8 @@ int blend_tiles(innfer_rrdb* h, const void* tiles_base, const TilePlan& plan, vo
   const int oct = (h->cfg.out_nc + 7) / 8;
   int rc;
   if (h->cfg.fp16)
-    rc = launch_blend(reinterpret_cast<const __half*>(tiles_base), oct, plan, h->cfg.scale, h->cfg.out_nc, dst, dt, stream);
+    rc = launch_blend(reinterpret_cast<const __half*>(tiles_base), compact_tiles(h) ? 0 : oct, plan, h->cfg.scale,
+                      h->cfg.out_nc, dst, dt, stream);
   else
     rc = launch_blend_f32(reinterpret_cast<const float*>(tiles_base), oct, plan, h->cfg.scale, h->cfg.out_nc, dst, dt, stream);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -346,6 +353,7 @@ int make_plan_checked(innfer_rrdb* h, int H, int W, int patch, float step, TileP
 size_t tile_bytes(const innfer_rrdb* h, const TilePlan& plan) {
   const int oct = (h->cfg.out_nc + 7) / 8;
   const size_t P = (size_t)h->cfg.scale * plan.p;
+  if (compact_tiles(h)) return P * P * 4 * sizeof(__half);
   return (size_t)oct * P * P * 8 * h->esz();
 }
 
@@ -532,7 +540,7 @@ int innfer_rrdb_forward(innfer_rrdb* h, const void* x, int n, int hgt, int wid, 
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (rc) return fail(INNFER_E_CUDA, "nchw_to_chunks launch failed");
     ChunkView dv = view(h->out_tiles, oct, 0);
-    if ((rc = forward_tiles(h, nb, hgt, wid, dv, st))) return rc;
+    if ((rc = forward_tiles(h, nb, hgt, wid, dv, false, st))) return rc;
     if (h->cfg.fp16)
       rc = launch_chunks_to_nchw(reinterpret_cast<const __half*>(h->out_tiles.p), oct, nb, h->cfg.out_nc, s * hgt, s * wid, ys, to_pix(dtype), st);
     else

@@ -244,6 +244,7 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
   p.out_CT = out.CT;
   p.out_chunk0 = out.chunk0;
   p.out_nchunks = out_nchunks;
+  p.out_compact4 = ep.compact4 ? 1 : 0;
   p.w = L.d_w;
   p.bias = L.d_bias;
   p.lrelu = ep.lrelu ? 1 : 0;

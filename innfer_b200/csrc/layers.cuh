@@ -49,6 +49,7 @@ struct Epilogue {
   float slope = 0.2f;
   ChunkView res1, res2;   // base == nullptr -> unused
   float alpha1 = 1.f, alpha2 = 1.f;
+  bool compact4 = false;  // store out channels 0..3 as [tile][H][W][4] (8 bytes per pixel), see ConvTcParams
 };
 
 // Build the packed fp16 weights (and phase tables) from OIHW fp32 weights.  `bias` may be null.

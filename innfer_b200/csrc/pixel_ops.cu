@@ -154,7 +154,44 @@ __device__ __forceinline__ float quant_u8(float v) {
   return rintf(v);
 }
 
-template <int DT, typename E>
+// Compact tile pixel: 4 fp16 channels in 8 bytes.
+__device__ __forceinline__ void load_compact4(const __half* src, size_t pixel_index, float (&f)[8]) {
+  const uint2 raw = *reinterpret_cast<const uint2*>(src + pixel_index * 4);
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+  const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  f[4] = f[5] = f[6] = f[7] = 0.f;
+}
+
+// Visits the tiles covering output position (Y, X) in the reference's row-major accumulation order
+// (utils.py:436-443): regular tiles ascending, then the edge-anchored last tile of each axis.
+template <typename F>
+__device__ __forceinline__ void for_each_covering_tile(const BlendGeom& g, int Y, int X, F&& fn) {
+  const int ty_hi = min(Y / g.eff, g.nty - 1);
+  const int ty_lo = max(0, (Y - g.P) / g.eff);
+  const int tx_hi = min(X / g.eff, g.ntx - 1);
+  const int tx_lo = max(0, (X - g.P) / g.eff);
+  for (int pass_y = 0; pass_y < 2; ++pass_y) {
+    const int ya = pass_y == 0 ? ty_lo : g.nty - 1;
+    const int yb = pass_y == 0 ? ty_hi : (ty_hi < g.nty - 1 ? g.nty - 1 : g.nty - 2);
+    for (int ty = ya; ty <= yb; ++ty) {
+      const int ly = Y - g.oys[ty];
+      if (ly < 0 || ly >= g.P) continue;
+      for (int pass_x = 0; pass_x < 2; ++pass_x) {
+        const int xa = pass_x == 0 ? tx_lo : g.ntx - 1;
+        const int xb = pass_x == 0 ? tx_hi : (tx_hi < g.ntx - 1 ? g.ntx - 1 : g.ntx - 2);
+        for (int tx = xa; tx <= xb; ++tx) {
+          const int lx = X - g.oxs[tx];
+          if (lx < 0 || lx >= g.P) continue;
+          fn(ty, tx, ly, lx);
+        }
+      }
+    }
+  }
+}
+
+// Scalar gather-blend: one thread per output pixel (any geometry).
+template <int DT, typename E, bool COMPACT>
 __global__ void blend_kernel(const E* __restrict__ tiles, int CT, const __grid_constant__ BlendGeom g, int C,
                              void* __restrict__ dst) {
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,35 +201,16 @@ __global__ void blend_kernel(const E* __restrict__ tiles, int CT, const __grid_c
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[c] = 0.f;
   float wsum = 0.f;
-  const int ty_hi = min(Y / g.eff, g.nty - 1);
-  const int ty_lo = max(0, (Y - g.P) / g.eff);
-  const int tx_hi = min(X / g.eff, g.ntx - 1);
-  const int tx_lo = max(0, (X - g.P) / g.eff);
-  for (int pass_y = 0; pass_y < 2; ++pass_y) {
-    // regular tiles first (ascending), then the edge-anchored last tile if it was not visited
-    const int ya = pass_y == 0 ? ty_lo : g.nty - 1;
-    const int yb = pass_y == 0 ? ty_hi : (ty_hi < g.nty - 1 ? g.nty - 1 : g.nty - 2);
-    for (int ty = ya; ty <= yb; ++ty) {
-      const int ly = Y - g.oys[ty];
-      if (ly < 0 || ly >= g.P) continue;
-      const float wy = blend_profile(ly, g.P, g.overlap);
-      for (int pass_x = 0; pass_x < 2; ++pass_x) {
-        const int xa = pass_x == 0 ? tx_lo : g.ntx - 1;
-        const int xb = pass_x == 0 ? tx_hi : (tx_hi < g.ntx - 1 ? g.ntx - 1 : g.ntx - 2);
-        for (int tx = xa; tx <= xb; ++tx) {
-          const int lx = X - g.oxs[tx];
-          if (lx < 0 || lx >= g.P) continue;
-          const float w = blend_profile(lx, g.P, g.overlap) * wy;
-          const size_t t = (size_t)ty * g.ntx + tx;
-          float f[8];
-          load_chunk<E>(tiles, (t * CT * g.P + ly) * g.P + lx, f);
+  for_each_covering_tile(g, Y, X, [&](int ty, int tx, int ly, int lx) {
+    const float w = blend_profile(lx, g.P, g.overlap) * blend_profile(ly, g.P, g.overlap);
+    const size_t t = (size_t)ty * g.ntx + tx;
+    float f[8];
+    if (COMPACT) load_compact4(reinterpret_cast<const __half*>(tiles), (t * g.P + ly) * g.P + lx, f);
+    else load_chunk<E>(tiles, (t * CT * g.P + ly) * g.P + lx, f);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] += f[e] * w;
-          wsum += w;
-        }
-      }
-    }
-  }
+    for (int e = 0; e < 8; ++e) acc[e] += f[e] * w;
+    wsum += w;
+  });
   const size_t plane = (size_t)g.Hs * g.Ws;
   const size_t pix = (size_t)Y * g.Ws + X;
 #pragma unroll
@@ -202,6 +220,84 @@ __global__ void blend_kernel(const E* __restrict__ tiles, int CT, const __grid_c
     if (DT == kF16) reinterpret_cast<__half*>(dst)[c * plane + pix] = __float2half_rn(v);
     if (DT == kF32) reinterpret_cast<float*>(dst)[c * plane + pix] = v;
     if (DT == kU8) reinterpret_cast<uint8_t*>(dst)[pix * C + (C - 1 - c)] = (uint8_t)quant_u8(v);
+  }
+}
+
+// Vector gather-blend for 3-channel images whose tile origins, tile size and width are multiples of
+// 4 (every reference geometry with an even tile size and scale 4; checked on the host): one thread
+// produces 4 consecutive pixels, which share their covering tiles, and stores 12 bytes (uint8 HWC)
+// or 8 bytes per channel plane (fp16 NCHW) at once.  Same accumulation order as the scalar kernel.
+template <int DT, typename E, bool COMPACT>
+__global__ void blend_vec4_kernel(const E* __restrict__ tiles, int CT, const __grid_constant__ BlendGeom g,
+                                  void* __restrict__ dst) {
+  const int X0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int Y = blockIdx.y;
+  if (X0 >= g.Ws) return;
+  float acc[4][3];
+  float wsum[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    wsum[k] = 0.f;
+    acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
+  }
+  for_each_covering_tile(g, Y, X0, [&](int ty, int tx, int ly, int lx) {
+    const float wy = blend_profile(ly, g.P, g.overlap);
+    const size_t t = (size_t)ty * g.ntx + tx;
+    if (COMPACT) {
+      // 4 pixels x 4 halves = 32 contiguous, 32-byte aligned bytes (lx and P are multiples of 4)
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(tiles) +
+                                                        ((t * g.P + ly) * g.P + lx) * 4);
+      const uint4 a = src[0], b = src[1];
+      const uint32_t raw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float w = blend_profile(lx + k, g.P, g.overlap) * wy;
+        const float2 rg = __half22float2(*reinterpret_cast<const __half2*>(&raw[2 * k]));
+        const float2 bx = __half22float2(*reinterpret_cast<const __half2*>(&raw[2 * k + 1]));
+        acc[k][0] += rg.x * w;
+        acc[k][1] += rg.y * w;
+        acc[k][2] += bx.x * w;
+        wsum[k] += w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float w = blend_profile(lx + k, g.P, g.overlap) * wy;
+        float f[8];
+        load_chunk<E>(tiles, (t * CT * g.P + ly) * g.P + lx + k, f);
+        acc[k][0] += f[0] * w;
+        acc[k][1] += f[1] * w;
+        acc[k][2] += f[2] * w;
+        wsum[k] += w;
+      }
+    }
+  });
+  const size_t plane = (size_t)g.Hs * g.Ws;
+  const size_t pix = (size_t)Y * g.Ws + X0;
+  if (DT == kU8) {
+    __align__(4) uint8_t o[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[k * 3 + (2 - c)] = (uint8_t)quant_u8(acc[k][c] / wsum[k]);
+    uint32_t* out = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(dst) + pix * 3);
+    const uint32_t* o32 = reinterpret_cast<const uint32_t*>(o);
+    out[0] = o32[0];
+    out[1] = o32[1];
+    out[2] = o32[2];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (DT == kF16) {
+        __align__(8) __half hv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hv[k] = __float2half_rn(acc[k][c] / wsum[k]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(dst) + c * plane + pix) = *reinterpret_cast<const uint2*>(hv);
+      } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + c * plane + pix) =
+            make_float4(acc[0][c] / wsum[0], acc[1][c] / wsum[1], acc[2][c] / wsum[2], acc[3][c] / wsum[3]);
+      }
+    }
   }
 }
 
@@ -296,10 +392,25 @@ int blend_impl(const E* tiles, int CT, const TilePlan& plan, int scale, int C, v
     const int o = i * g.eff;
     g.oxs[i] = o < g.Ws - g.P ? o : g.Ws - g.P;
   }
-  dim3 block(256), grid((g.Ws + 255) / 256, g.Hs);
-  if (dt == kF16) blend_kernel<kF16, E><<<grid, block, 0, stream>>>(tiles, CT, g, C, dst);
-  else if (dt == kF32) blend_kernel<kF32, E><<<grid, block, 0, stream>>>(tiles, CT, g, C, dst);
-  else blend_kernel<kU8, E><<<grid, block, 0, stream>>>(tiles, CT, g, C, dst);
+  if (CT == 0 && (C > 4 || sizeof(E) != 2)) return -1;
+  bool vec = (C == 3) && (g.P % 4 == 0) && (g.Ws % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
+  for (int i = 0; i < g.ntx && vec; ++i) vec = (g.oxs[i] % 4 == 0);
+  dim3 block(128), grid(vec ? (g.Ws / 4 + 127) / 128 : (g.Ws + 127) / 128, g.Hs);
+#define INNFER_BLEND_LAUNCH(DT, COMPACT)                                                        \
+  do {                                                                                          \
+    if (vec) blend_vec4_kernel<DT, E, COMPACT><<<grid, block, 0, stream>>>(tiles, CT, g, dst);  \
+    else blend_kernel<DT, E, COMPACT><<<grid, block, 0, stream>>>(tiles, CT, g, C, dst);        \
+  } while (0)
+  if (CT == 0) {
+    if (dt == kF16) INNFER_BLEND_LAUNCH(kF16, true);
+    else if (dt == kF32) INNFER_BLEND_LAUNCH(kF32, true);
+    else INNFER_BLEND_LAUNCH(kU8, true);
+  } else {
+    if (dt == kF16) INNFER_BLEND_LAUNCH(kF16, false);
+    else if (dt == kF32) INNFER_BLEND_LAUNCH(kF32, false);
+    else INNFER_BLEND_LAUNCH(kU8, false);
+  }
+#undef INNFER_BLEND_LAUNCH
   return (int)cudaGetLastError();
 }
 

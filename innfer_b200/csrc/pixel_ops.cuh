@@ -33,6 +33,7 @@ int launch_image_to_tiles(const void* src, PixelDType st, int C, const TilePlan&
 
 // tiles: [ntiles][CT][P][P][8] fp16 (P = scale*p), channel c of chunk 0 is output channel c.
 // dst: NCHW [1][C][scale*H][scale*W] fp16/fp32, or uint8 HWC BGR with clip(255x).round().
+// CT == 0 selects the compact tile layout [ntiles][P][P][4] fp16 (C <= 4) written by the last conv.
 int launch_blend(const __half* tiles, int CT, const TilePlan& plan, int scale, int C, void* dst,
                  PixelDType dt, cudaStream_t stream);
 

@@ -198,6 +198,10 @@ def stage_pix():
     tiles_out = torch.rand(nt, 1, 800, 800, 8, device=dev).half()
     out = torch.empty(s * H, s * W, 3, dtype=torch.uint8, device=dev)
     outf = torch.empty(1, 3, s * H, s * W, dtype=torch.float16, device=dev)
+    # the engine's own path (compact 8-byte tile pixels): one whole frame of a 1-block net
+    sd = O.make_state_dict(scale=4, nb=1, seed=0)
+    h = make_handle(sd, fp16=True)
+    N.check(lib.innfer_rrdb_upscale_u8_device(h, img.data_ptr(), H, W, 200, 0.5, out.data_ptr(), None))
     for _ in range(3):
         N.check(lib.innfer_image_to_tiles(img.data_ptr(), N.INNFER_U8, 3, H, W, 200, 0.5, tiles_in.data_ptr(), None))
         N.check(lib.innfer_blend(tiles_out.data_ptr(), H, W, 200, 0.5, s, 3, out.data_ptr(), N.INNFER_U8, None))
