@@ -24,6 +24,7 @@ namespace {
 
 constexpr int kDxN = 96;      // 3 dx x 32 output channels
 constexpr int kDxSlots = 5;   // 5 x 96 = 480 TMEM columns
+constexpr int kDxChunks = 4;  // 8-channel chunks per pipeline stage (32 channels)
 constexpr int kDxThreads = 320;  // producer, issuer, 8 epilogue warps (2 per TMEM lane quarter)
 
 struct DxIter {
@@ -63,8 +64,11 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   const int lane = threadIdx.x & 31;
 
   const int Wh = 8 * p.J;                                  // smem tile width in pixels (no x halo)
-  const int a_bytes = 2 * kHaloRows * Wh * 16;             // multiple of 128
-  const int w_bytes = 3 * 2 * kDxN * 16;                   // 9216 per 16-channel slab
+  // One pipeline stage = 32 input channels (4 chunks, two K=16 MMA slabs): with N=96 MMAs a
+  // 16-channel stage is only ~900 tensor-pipe cycles and the issuing warp's per-stage barrier
+  // round trip (~360 cycles, measured) would be a 28 % bubble.
+  const int a_bytes = kDxChunks * kHaloRows * Wh * 16;     // multiple of 128
+  const int w_bytes = (kDxChunks / 2) * 3 * 2 * kDxN * 16; // 18432 per 32-channel stage
   // debug bit 3: all weight slabs of this conv (kslabs x 9216 B <= 92 KB) stay resident in shared
   // memory for the whole persistent kernel instead of travelling with every stage;
   // bit 4: the resident block sits in front of the stage ring instead of behind it.
@@ -130,9 +134,9 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           const uint32_t dstA = smem_base + (uint32_t)s * stage_bytes;
           mbar_expect_tx(fb, (uint32_t)(resident ? a_bytes : a_bytes + w_bytes));
           if (p.debug & 4)
-            tma_load_4d(dstA, &tmap_in, fb, (x0 - 1) * 8, y0 - 1, p.in_chunk0 + 2 * ks, ti.b);
+            tma_load_4d(dstA, &tmap_in, fb, (x0 - 1) * 8, y0 - 1, p.in_chunk0 + kDxChunks * ks, ti.b);
           else
-            tma_load_5d(dstA, &tmap_in, fb, 0, x0 - 1, y0 - 1, p.in_chunk0 + 2 * ks, ti.b);
+            tma_load_5d(dstA, &tmap_in, fb, 0, x0 - 1, y0 - 1, p.in_chunk0 + kDxChunks * ks, ti.b);
           if (!resident)
             bulk_load(dstA + a_bytes, reinterpret_cast<const uint8_t*>(p.w) + (size_t)ks * w_bytes, w_bytes, fb);
           if (++s == S) {
@@ -151,7 +155,8 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     const uint32_t a_hi = a_sbo | (1u << 14);
     const uint32_t b_hi = 8u | (1u << 14);               // SBO = 128 B
     const uint32_t b_lbo = (uint32_t)kDxN;               // 96 rows * 16 B
-    const uint32_t dy_stride = 2u * kDxN;                // 16-byte units per dy block of the weight stage
+    const uint32_t dy_stride = 2u * kDxN;                // 16-byte units per dy block of a weight slab
+    const uint32_t slab_stride = 3u * dy_stride;         // 16-byte units per 16-channel weight slab
     int s = 0;
     uint32_t ph = 0;
     int slot0 = 0;          // slot of sub-patch 0 of the current tile (accumulators rotate over 5 slots)
@@ -185,9 +190,13 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           const uint32_t aj = a_lo + 8u * j;
           if (leader) {
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-              umma_f16_ss(acc, make_desc64(aj + dy * a_sbo, a_hi), make_desc64(b_lo + dy * dy_stride, b_hi), idesc,
-                          dy == 0 ? first : 1u);
+            for (int kk = 0; kk < kDxChunks / 2; ++kk) {
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy)
+                umma_f16_ss(acc, make_desc64(aj + kk * 2u * a_lbo + dy * a_sbo, a_hi),
+                            make_desc64(b_lo + kk * slab_stride + dy * dy_stride, b_hi), idesc,
+                            (kk | dy) == 0 ? first : 1u);
+            }
             if (last) umma_commit(smem_u32(&tfull_bar[slot]));  // this accumulator is complete
           }
         }
@@ -295,8 +304,8 @@ conv_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
 
 }  // namespace
 
-int conv_dx_stage_bytes(int J) { return 2 * kHaloRows * 8 * J * 16; }
-int conv_dx_weight_bytes(int kslabs) { return kslabs * 3 * 2 * kDxN * 16; }
+int conv_dx_stage_bytes(int J) { return kDxChunks * kHaloRows * 8 * J * 16; }
+int conv_dx_weight_bytes(int kstages) { return kstages * (kDxChunks / 2) * 3 * 2 * kDxN * 16; }
 
 int launch_conv_dx(const CUtensorMap* tmap_in, const ConvTcParams& p, int num_sms, cudaStream_t stream) {
   const bool resident = (p.debug & 8) != 0;

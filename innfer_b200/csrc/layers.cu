@@ -146,7 +146,7 @@ const CUtensorMap* TmapCache::get(const void* base, int B, int CT, int H, int W,
   if (it != maps_.end()) return &it->second->m;
   Slot* s = new Slot();
   rc = box_w > 0 ? encode_act_tmap(&s->m, base, B, CT, H, W, box_w)
-                 : encode_act_tmap_merged(&s->m, base, B, CT, H, W, -box_w);
+                 : encode_act_tmap_merged(&s->m, base, B, CT, H, W, -box_w, 4);
   if (rc != 0) {
     delete s;
     return nullptr;
@@ -182,15 +182,16 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
   const int N = L.N;
   static const int dx_mode = getenv("INNFER_DX") ? atoi(getenv("INNFER_DX")) : 1;
   static const int dx_j = getenv("INNFER_DX_J") ? atoi(getenv("INNFER_DX_J")) : 4;
-  if (dx_mode && L.d_wdx != nullptr && ep.res1.base == nullptr && ep.res2.base == nullptr && out_nchunks == 4) {
+  if (dx_mode && L.d_wdx != nullptr && ep.res1.base == nullptr && ep.res2.base == nullptr && out_nchunks == 4 &&
+      L.Cin_pad % 32 == 0) {
     // dx-taps-as-N kernel: tiles of 16 x (8J-2) outputs
-    const int J = dx_j < 2 ? 2 : (dx_j > 5 ? 5 : dx_j);
+    const int J = dx_j < 2 ? 2 : (dx_j > 4 ? 4 : dx_j);  // merged TMA map: 8J*8 <= 256 elements
     const int OW = 8 * J - 2;
     p.B = B;
     p.H = H;
     p.W = W;
     p.in_chunk0 = in.chunk0;
-    p.kslabs = L.Cin_pad / 16;
+    p.kslabs = L.Cin_pad / 32;  // pipeline stages of 32 channels
     p.J = J;
     p.bands = (H + kPatchRows - 1) / kPatchRows;
     p.cps = (W + OW - 1) / OW;
@@ -212,7 +213,7 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
     p.lrelu = ep.lrelu ? 1 : 0;
     p.slope = ep.slope;
     int rc = 0;
-    const CUtensorMap* tm = cache.get(in.base, B, in.CT, H, W, J <= 4 ? -8 * J : 8 * J, rc);
+    const CUtensorMap* tm = cache.get(in.base, B, in.CT, H, W, -8 * J, rc);
     static const int dx_dbg = getenv("INNFER_DX_DBG") ? atoi(getenv("INNFER_DX_DBG")) : 0;
     p.debug = (J <= 4 ? 4 : 0) | (dx_res == 1 ? 8 : 0) | (dx_res == 2 ? 24 : 0) | dx_dbg;  // bit 2: merged 4-D tensor map
     if (!tm) return rc ? rc : -5;

@@ -11,6 +11,7 @@ int encode_act_tmap(CUtensorMap* out, const void* base, int B, int CT, int H, in
 // Same tensor seen as 4-D [B][CT][H][W*8]: the 8 channels of a chunk and the W pixels are merged
 // into one contiguous inner dimension so that a box row is box_w*16 bytes (TMA moves whole rows;
 // with the 5-D form every 16-byte pixel chunk is its own request and the TMA unit becomes the
-// bottleneck).  box_w * 8 must be <= 256 elements.  Box = (box_w*8, 18, 2, 1), OOB -> zero.
-int encode_act_tmap_merged(CUtensorMap* out, const void* base, int B, int CT, int H, int W, int box_w);
+// bottleneck).  box_w * 8 must be <= 256 elements.  Box = (box_w*8, 18, box_chunks, 1), OOB -> zero.
+int encode_act_tmap_merged(CUtensorMap* out, const void* base, int B, int CT, int H, int W, int box_w,
+                           int box_chunks);
 }  // namespace innfer

@@ -180,6 +180,8 @@ def stage_prof():
     sd = O.make_state_dict(scale=4, nb=23, seed=0)
     h = make_handle(sd, fp16=True)
     H, W = 800, 1000
+    if os.environ.get("INNFER_MB_PROF"):
+        lib.innfer_rrdb_set_max_batch(h, int(os.environ["INNFER_MB_PROF"]))
     img = np.random.default_rng(0).integers(0, 256, (H, W, 3), dtype=np.uint8)
     din = torch.from_numpy(img).to(dev)
     dout = torch.empty(4 * H, 4 * W, 3, dtype=torch.uint8, device=dev)
