@@ -150,6 +150,25 @@ def test_scale_3_and_8_vs_oracle(dev, scale, hw):
     eng.close()
 
 
+@pytest.mark.parametrize("nf,in_nc,out_nc,scale", [(32, 3, 3, 4), (32, 3, 3, 2), (64, 1, 1, 2), (64, 4, 4, 1)])
+def test_variants_nf32_and_channel_counts(dev, nf, in_nc, out_nc, scale):
+    """esrgan-lite width (nf=32) and non-RGB channel counts that infer_params can select."""
+    sd = O.make_state_dict(scale=scale, nb=2, nf=nf, in_nc=in_nc, out_nc=out_nc, seed=8)
+    eng = _engine(sd, dev, scale=scale)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(1, in_nc, 72, 56, generator=g)
+    ref = O.rrdbnet_forward(sd, x, scale)
+    y = eng.forward(x.to(dev).half()).float().cpu()
+    q = lambda t: np.clip(255 * t.numpy(), 0, 255).round()
+    assert np.abs(q(y) - q(ref)).max() <= 1
+    assert ((y - ref).abs().max() / ref.abs().max()).item() < 5e-3
+    # chop path (tiles + blend) against the oracle as well
+    y2 = eng.chop_forward(x.to(dev).half(), 32, 0.5).float().cpu()
+    ref2 = O.chop_forward(sd, x, patch_size=32, forward=lambda t: O.rrdbnet_forward(sd, t, scale))
+    assert np.abs(q(y2) - q(ref2)).max() <= 1
+    eng.close()
+
+
 def test_python_api_model_chain_and_color_fix(dev, tmp_path, monkeypatch):
     """run.Model on cuda (fp16) + chaining + -cf, and the CLI, vs the reference fixture (config 3 shrunk)."""
     import cv2
