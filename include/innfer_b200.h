@@ -48,7 +48,7 @@ typedef struct innfer_rrdb_cfg {
   int32_t nb;
   int32_t gc;
   int32_t scale; /* upscale: 1, 2, 3, 4, 8 */
-  int32_t plus;  /* ESRGAN+ paths (RRDBNet_arch.py:129,155-160); non-zero -> INNFER_E_UNSUPPORTED */
+  int32_t plus;  /* ESRGAN+ residual paths: conv1x1 + extra adds (RRDBNet_arch.py:129,155-160) */
   int32_t fp16;  /* 1: fp16 storage + tcgen05 fp16 MMA with fp32 accumulate; 0: fp32 mode */
 } innfer_rrdb_cfg;
 

@@ -75,6 +75,7 @@ struct innfer_rrdb {
   // layers in execution order
   ConvLayer fea, lr_conv, hr0, hr1;
   std::vector<ConvLayer> rdb;  // [nb][3][5]
+  std::vector<ConvLayer> c1x1; // [nb][3] ESRGAN+ conv1x1 (cfg.plus)
   std::vector<ConvLayer> ups;
   TmapCache cache;
   // workspace
@@ -94,6 +95,7 @@ struct innfer_rrdb {
     conv_layer_free(hr0);
     conv_layer_free(hr1);
     for (auto& l : rdb) conv_layer_free(l);
+    for (auto& l : c1x1) conv_layer_free(l);
     for (auto& l : ups) conv_layer_free(l);
     in_tiles.release();
     feat.release();
@@ -105,7 +107,8 @@ struct innfer_rrdb {
   }
   int in_ct() const { return (cfg.in_nc + 15) / 16 * 2; }
   int nf_ct() const { return cfg.nf / 8; }
-  int cat_ct() const { return (cfg.nf + 4 * 32) / 8; }
+  // concat buffer: x, x1..x4 (+ 4 chunks for conv1x1(x) in ESRGAN+ mode)
+  int cat_ct() const { return (cfg.nf + 4 * 32) / 8 + (cfg.plus ? 4 : 0); }
   size_t esz() const { return cfg.fp16 ? 2 : 4; }
 };
 
@@ -117,18 +120,20 @@ int set_device(const innfer_rrdb* h) {
   return 0;
 }
 
-int build_layer(innfer_rrdb* h, ConvLayer& L, const std::string& prefix, int Cout, int Cin, int up) {
+int build_layer(innfer_rrdb* h, ConvLayer& L, const std::string& prefix, int Cout, int Cin, int up, int ksize = 3,
+                bool has_bias = true) {
   auto wi = h->params.find(prefix + ".weight");
   auto bi = h->params.find(prefix + ".bias");
   if (wi == h->params.end()) return fail(INNFER_E_STATE, "missing key " + prefix + ".weight");
-  if (bi == h->params.end()) return fail(INNFER_E_STATE, "missing key " + prefix + ".bias");
+  if (has_bias && bi == h->params.end()) return fail(INNFER_E_STATE, "missing key " + prefix + ".bias");
   const auto& ws = wi->second.shape;
-  if (ws.size() != 4 || ws[0] != Cout || ws[1] != Cin || ws[2] != 3 || ws[3] != 3)
+  if (ws.size() != 4 || ws[0] != Cout || ws[1] != Cin || ws[2] != ksize || ws[3] != ksize)
     return fail(INNFER_E_INVALID, "size mismatch for " + prefix + ".weight");
-  if (bi->second.shape.size() != 1 || bi->second.shape[0] != Cout)
+  if (has_bias && (bi->second.shape.size() != 1 || bi->second.shape[0] != Cout))
     return fail(INNFER_E_INVALID, "size mismatch for " + prefix + ".bias");
   std::string err;
-  int rc = conv_layer_build(L, wi->second.data.data(), bi->second.data.data(), Cout, Cin, up, err);
+  int rc = conv_layer_build(L, wi->second.data.data(), has_bias ? bi->second.data.data() : nullptr, Cout, Cin, up, err,
+                            ksize);
   if (rc) return fail(rc == -2 ? INNFER_E_UNSUPPORTED : INNFER_E_CUDA, prefix + ": " + err);
   if (!h->cfg.fp16) {
     rc = conv_direct_upload(L);
@@ -217,9 +222,23 @@ int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, b
     for (int r = 0; r < 3; ++r) {
       const int cur = order[r];
       const ConvLayer* L = &h->rdb[((size_t)b * 3 + r) * 5];
+      if (h->cfg.plus) {
+        // ESRGAN+ (RRDBNet_arch.py:155-160): t = conv1x1(x) parked behind x4
+        if ((rc = run_conv(h, h->c1x1[(size_t)b * 3 + r], view(h->xbuf[cur], catc, 0), B, hgt, wid,
+                           view(h->xbuf[cur], catc, nfc + gcc * 4), gcc, plain, st)))
+          return rc;
+      }
       for (int k = 0; k < 4; ++k) {
+        Epilogue e = act;
+        if (h->cfg.plus && k == 1) {         // x2 = lrelu(conv2(..)) + conv1x1(x)
+          e.res1 = view(h->xbuf[cur], catc, nfc + gcc * 4);
+          e.alpha1 = 1.0f;
+        } else if (h->cfg.plus && k == 3) {  // x4 = lrelu(conv4(..)) + x2
+          e.res1 = view(h->xbuf[cur], catc, nfc + gcc * 1);
+          e.alpha1 = 1.0f;
+        }
         if ((rc = run_conv(h, L[k], view(h->xbuf[cur], catc, 0), B, hgt, wid,
-                           view(h->xbuf[cur], catc, nfc + gcc * k), gcc, act, st)))
+                           view(h->xbuf[cur], catc, nfc + gcc * k), gcc, e, st)))
           return rc;
       }
       Epilogue e5;
@@ -380,7 +399,6 @@ uint64_t innfer_kernel_launches(void) { return g_launches.load(); }
 
 int innfer_rrdb_create(const innfer_rrdb_cfg* cfg, int device, innfer_rrdb** out) {
   if (!cfg || !out) return fail(INNFER_E_INVALID, "null argument");
-  if (cfg->plus) return fail(INNFER_E_UNSUPPORTED, "ESRGAN+ (plus=True) residual paths are not implemented");
   if (cfg->nf != 64 && cfg->nf != 32) return fail(INNFER_E_UNSUPPORTED, "nf must be 32 or 64");
   if (cfg->in_nc < 1 || cfg->in_nc > 16 || cfg->out_nc < 1 || cfg->out_nc > 8)
     return fail(INNFER_E_UNSUPPORTED, "in_nc must be <= 16 and out_nc <= 8");
@@ -435,8 +453,15 @@ int innfer_rrdb_finalize(innfer_rrdb* h) {
   if ((rc = build_layer(h, h->fea, "model.0", c.nf, c.in_nc, 1))) return rc;
   expected += 2;
   h->rdb.resize((size_t)c.nb * 15);
+  if (c.plus) h->c1x1.resize((size_t)c.nb * 3);
   for (int b = 0; b < c.nb; ++b)
-    for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 3; ++r) {
+      if (c.plus) {
+        char key[96];
+        snprintf(key, sizeof key, "model.1.sub.%d.RDB%d.conv1x1", b, r + 1);
+        if ((rc = build_layer(h, h->c1x1[(size_t)b * 3 + r], key, 32, c.nf, 1, 1, false))) return rc;
+        expected += 1;
+      }
       for (int k = 0; k < 5; ++k) {
         char key[96];
         snprintf(key, sizeof key, "model.1.sub.%d.RDB%d.conv%d.0", b, r + 1, k + 1);
@@ -444,6 +469,7 @@ int innfer_rrdb_finalize(innfer_rrdb* h) {
         if ((rc = build_layer(h, h->rdb[((size_t)b * 3 + r) * 5 + k], key, cout, cin, 1))) return rc;
         expected += 2;
       }
+    }
   {
     char key[64];
     snprintf(key, sizeof key, "model.1.sub.%d", c.nb);

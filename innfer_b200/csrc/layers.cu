@@ -11,8 +11,24 @@ namespace innfer {
 
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-int conv_layer_build(ConvLayer& L, const float* w, const float* bias, int Cout, int Cin, int up,
-                     std::string& err) {
+int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cout, int Cin, int up,
+                     std::string& err, int ksize) {
+  // a 1x1 kernel is embedded as the centre tap of a 3x3 one; the tap tables below then keep only
+  // taps with a non-zero weight plane, i.e. exactly that centre tap
+  std::vector<float> w3;
+  const float* w = w_in;
+  if (ksize == 1) {
+    if (up != 1) {
+      err = "1x1 conv with upsample is not supported";
+      return -2;
+    }
+    w3.assign((size_t)Cout * Cin * 9, 0.f);
+    for (size_t i = 0; i < (size_t)Cout * Cin; ++i) w3[i * 9 + 4] = w_in[i];
+    w = w3.data();
+  } else if (ksize != 3) {
+    err = "kernel size must be 1 or 3";
+    return -2;
+  }
   if (up < 1 || up > 3) {
     err = "unsupported upsample factor (1, 2 or 3 expected)";
     return -2;
@@ -47,6 +63,10 @@ int conv_layer_build(ConvLayer& L, const float* w, const float* bias, int Cout, 
       }
       std::sort(hys.begin(), hys.end());
       std::sort(hxs.begin(), hxs.end());
+      if (ksize == 1) {
+        hys.assign(1, 1);
+        hxs.assign(1, 1);
+      }
       const int ntaps = (int)(hys.size() * hxs.size());
       L.ph_ntaps[ph] = (uint8_t)ntaps;
       L.ph_a[ph] = (uint8_t)a;
@@ -93,7 +113,7 @@ int conv_layer_build(ConvLayer& L, const float* w, const float* bias, int Cout, 
   }
   // dx-as-N packing for the Cout == 32 convs: [kslab][dy][kchunk][dx*32 + co][8]
   std::vector<__half> packed_dx;
-  if (up == 1 && Cout == 32) {
+  if (up == 1 && Cout == 32 && ksize == 3) {
     packed_dx.resize((size_t)kslabs * 3 * 2 * 96 * 8);
     size_t o = 0;
     for (int ks = 0; ks < kslabs; ++ks)

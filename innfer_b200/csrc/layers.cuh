@@ -54,8 +54,9 @@ struct Epilogue {
 
 // Build the packed fp16 weights (and phase tables) from OIHW fp32 weights.  `bias` may be null.
 // Returns 0 or a negative error code; `err` receives a message.
+// ksize 3 (default) or 1: a 1x1 conv (ESRGAN+ conv1x1, block.py:390-391) runs as a single centre tap.
 int conv_layer_build(ConvLayer& L, const float* w_oihw, const float* bias, int Cout, int Cin,
-                     int up, std::string& err);
+                     int up, std::string& err, int ksize = 3);
 void conv_layer_free(ConvLayer& L);
 
 // Cache of encoded TMA descriptors keyed by (base, B, CT, H, W, box width in pixels).

@@ -36,7 +36,7 @@ def upconv_indices(scale):
     return ups, 2 + 3 * n_up, 4 + 3 * n_up
 
 
-def make_state_dict(scale=4, nb=23, nf=64, in_nc=3, out_nc=3, seed=0, last_bias=0.5):
+def make_state_dict(scale=4, nb=23, nf=64, in_nc=3, out_nc=3, seed=0, last_bias=0.5, plus=False):
     """Synthetic weights recipe of SURVEY.md 8(d): torch default init in the construction order of
     RRDBNet.__init__ (RRDBNet_arch.py:25-48), then the last conv's bias set to 0.5 so the uint8
     comparison is not vacuous."""
@@ -51,6 +51,9 @@ def make_state_dict(scale=4, nb=23, nf=64, in_nc=3, out_nc=3, seed=0, last_bias=
     put("model.0", nf, in_nc)
     for b in range(nb):
         for r in (1, 2, 3):
+            if plus:  # ESRGAN+: conv1x1 is constructed before conv1..5 (RRDBNet_arch.py:127-133), no bias
+                sd["model.1.sub.%d.RDB%d.conv1x1.weight" % (b, r)] = \
+                    torch.nn.Conv2d(nf, 32, 1, bias=False).weight.detach().clone()
             for k in range(5):
                 put("model.1.sub.%d.RDB%d.conv%d.0" % (b, r, k + 1), 32 if k < 4 else nf, nf + 32 * k)
     put("model.1.sub.%d" % nb, nf, nf)
@@ -95,11 +98,17 @@ def _conv(sd, name, x, act=False):
 
 
 def rdb_forward(sd, prefix, x):
-    """ResidualDenseBlock_5C.forward (RRDBNet_arch.py:152-165), plus=False."""
+    """ResidualDenseBlock_5C.forward (RRDBNet_arch.py:152-165); the ESRGAN+ additions (155-160) are
+    taken when the block has a conv1x1 weight."""
+    plus = (prefix + ".conv1x1.weight") in sd
     x1 = _conv(sd, prefix + ".conv1.0", x, True)
     x2 = _conv(sd, prefix + ".conv2.0", torch.cat((x, x1), 1), True)
+    if plus:
+        x2 = x2 + F.conv2d(x, sd[prefix + ".conv1x1.weight"])
     x3 = _conv(sd, prefix + ".conv3.0", torch.cat((x, x1, x2), 1), True)
     x4 = _conv(sd, prefix + ".conv4.0", torch.cat((x, x1, x2, x3), 1), True)
+    if plus:
+        x4 = x4 + x2
     x5 = _conv(sd, prefix + ".conv5.0", torch.cat((x, x1, x2, x3, x4), 1), False)
     return x5 * 0.2 + x
 

@@ -169,6 +169,23 @@ def test_variants_nf32_and_channel_counts(dev, nf, in_nc, out_nc, scale):
     eng.close()
 
 
+@pytest.mark.parametrize("fp16", [True, False])
+def test_esrgan_plus_vs_reference_fixture(dev, fp16):
+    """ESRGAN+ (conv1x1 + extra residuals) against the reference fixture."""
+    g = golden("plus_s4_nb2_40x48_p32.npz")
+    sd = O.make_state_dict(scale=4, nb=2, seed=int(g["seed"]), plus=True)
+    from innfer_b200.engine import RRDBEngine
+    eng = RRDBEngine.from_state_dict(sd, dict(in_nc=3, out_nc=3, nf=64, nb=2, gc=32, scale=4, plus=True), dev, fp16=fp16)
+    img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))
+    x = O.np2tensor(img).to(dev, torch.float16 if fp16 else torch.float32)
+    y = eng.chop_forward(x, int(g["patch"]), 0.5)
+    u8 = O.tensor2np(y)
+    assert np.abs(u8.astype(int) - g["u8"].astype(int)).max() <= 1 and psnr_u8(u8, g["u8"]) >= 50.0
+    if not fp16:
+        assert np.abs(y.cpu().numpy() - g["y"]).max() / np.abs(g["y"]).max() <= 1e-4
+    eng.close()
+
+
 def test_python_api_model_chain_and_color_fix(dev, tmp_path, monkeypatch):
     """run.Model on cuda (fp16) + chaining + -cf, and the CLI, vs the reference fixture (config 3 shrunk)."""
     import cv2

@@ -50,10 +50,10 @@ def test_abi_rejects_bad_arguments_without_gpu():
     n = ctypes.c_int()
     assert lib.innfer_tiles_plan(0, 10, 200, 0.5, None, 0, ctypes.byref(n), None) == -1
     assert b"tile" in lib.innfer_last_error()
-    cfg = _native.RRDBCfg(3, 3, 64, 23, 32, 4, 1, 1)  # plus=1 is not implemented: must fail loudly
+    cfg = _native.RRDBCfg(3, 3, 48, 23, 32, 4, 0, 1)  # nf=48 is not implemented: must fail loudly
     h = ctypes.c_void_p()
     assert lib.innfer_rrdb_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -2
-    assert b"plus" in lib.innfer_last_error()
+    assert b"nf" in lib.innfer_last_error()
 
 
 def test_state_dict_keys_and_cpu_forward_match_reference(tmp_path):
@@ -76,6 +76,16 @@ def test_cpu_mode_chop_forward(tmp_path, name):
     sd = O.make_state_dict(scale=scale, nb=int(g["nb"]), seed=int(g["seed"]))
     m = R.Model(_save(sd, tmp_path / ("%dx_t.pth" % scale)), "infer", None, device=torch.device("cpu"))
     assert m.scale == scale
+    img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))
+    y = m.chop_forward(U.np2tensor(img), patch_size=int(g["patch"]), step=0.5)
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)
+
+
+def test_esrgan_plus_is_detected_and_runs_on_cpu(tmp_path):
+    g = golden("plus_s4_nb2_40x48_p32.npz")
+    sd = O.make_state_dict(scale=4, nb=2, seed=int(g["seed"]), plus=True)
+    m = R.Model(_save(sd, tmp_path / "4x_plus.pth"), "infer", None, device=torch.device("cpu"))
+    assert m.model.cfg["plus"] is True and list(m.model.state_dict().keys()) == list(g["keys"])
     img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))
     y = m.chop_forward(U.np2tensor(img), patch_size=int(g["patch"]), step=0.5)
     np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)

@@ -43,6 +43,17 @@ def test_chop_forward_multi_tile(name):
     assert np.abs(O.tensor2np(y).astype(int) - g["u8"].astype(int)).max() <= 1
 
 
+def test_esrgan_plus_fixture():
+    g = golden("plus_s4_nb2_40x48_p32.npz")
+    sd = O.make_state_dict(scale=4, nb=2, seed=int(g["seed"]), plus=True)
+    assert list(sd.keys()) == list(g["keys"])
+    np.testing.assert_array_equal(np.array([float(v.double().sum()) for v in sd.values()]), g["wsum"])
+    assert O.infer_params(sd)["plus"] is True
+    img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))
+    y = O.chop_forward(sd, O.np2tensor(img), patch_size=int(g["patch"]))
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)
+
+
 def test_tile_geometry():
     g = golden("tile_geometry.npz")
     for key in g.files:

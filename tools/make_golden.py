@@ -29,9 +29,9 @@ OUT = os.path.join(ROOT, "tests", "golden")
 os.makedirs(OUT, exist_ok=True)
 
 
-def ref_net(scale, nb, nf=64, seed=0, last_bias=0.5):
+def ref_net(scale, nb, nf=64, seed=0, last_bias=0.5, plus=False):
     torch.manual_seed(seed)
-    cfg = get_network_G_config({"type": "esrgan", "nb": nb, "nf": nf}, scale)
+    cfg = get_network_G_config({"type": "esrgan", "nb": nb, "nf": nf, "plus": plus}, scale)
     net = get_network(cfg).eval()
     _, _, hr1 = O.upconv_indices(scale)
     with torch.no_grad():
@@ -102,6 +102,18 @@ def main():
         cf = ref_utils.color_fix(img, u8)
         np.savez_compressed(os.path.join(OUT, "chain_1x4x_cf_40x56.npz"), img_seed=7, h=40, w=56,
                             y=y.numpy().astype(np.float32), u8=u8, cf=cf)
+
+        # ---- G4b: ESRGAN+ (plus=True) is auto-detected from the conv1x1 keys
+        net = ref_net(4, 2, seed=9, plus=True)
+        path = os.path.join(td, "4x_plus.pth")
+        save_model(net, path)
+        model = ref_run.Model(path, "infer", None, device=torch.device("cpu"), chop=True)
+        img = image(12, 40, 48)
+        y = model.chop_forward(ref_utils.np2tensor(img), patch_size=32, step=0.5)
+        np.savez_compressed(os.path.join(OUT, "plus_s4_nb2_40x48_p32.npz"), img_seed=12, h=40, w=48, patch=32, seed=9,
+                            keys=np.array(list(net.state_dict().keys())),
+                            wsum=np.array([float(v.double().sum()) for v in net.state_dict().values()]),
+                            y=y.numpy().astype(np.float32), u8=ref_utils.tensor2np(y.detach()))
 
     # ---- G5: tile geometry of extract_patches_2d for a list of sizes
     geo = {}
