@@ -52,6 +52,19 @@ typedef struct innfer_rrdb_cfg {
   int32_t fp16;  /* 1: fp16 storage + tcgen05 fp16 MMA with fp32 accumulate; 0: fp32 mode */
 } innfer_rrdb_cfg;
 
+/* Constructor kwargs of SRResNet (architectures/SRResNet_arch.py:16-17) as produced by
+ * get_network_G_config (utils/defaults.py:53-67): no norm, ReLU, mode CNA.  SURVEY.md 8(f) rank 1. */
+typedef struct innfer_srresnet_cfg {
+  int32_t in_nc;
+  int32_t out_nc;
+  int32_t nf;            /* 32 or 64 */
+  int32_t nb;            /* ResNetBlocks */
+  int32_t scale;         /* 1, 2, 3, 4, 8 */
+  int32_t upsample_mode; /* 0: pixelshuffle (reference default, block.py:333-346), 1: upconv */
+  float res_scale;       /* ResNetBlock residual scaling */
+  int32_t fp16;
+} innfer_srresnet_cfg;
+
 typedef struct innfer_tile {
   int32_t y0, x0; /* low-res origin of the tile */
 } innfer_tile;
@@ -65,6 +78,10 @@ uint64_t innfer_kernel_launches(void);
 /* ---- network handle: replaces architectures.get_network + nn.Module.load_state_dict/.to(device)
  *      (architectures/__init__.py:5-40, run.py:90-101) ------------------------------------------- */
 int innfer_rrdb_create(const innfer_rrdb_cfg* cfg, int device, innfer_rrdb** out);
+/* SRResNet handle; every other innfer_rrdb_* call (load / finalize / forward / chop_forward / upscale_u8 /
+ * tile-range / destroy) works on it unchanged.  Keys: "model.0", "model.1.sub.<i>.res.0|2", "model.1.sub.<nb>",
+ * "model.2|5" (pixel-shuffle convs, 4*nf filters), "model.8", "model.10" (4x). */
+int innfer_srresnet_create(const innfer_srresnet_cfg* cfg, int device, innfer_rrdb** out);
 /* one state-dict entry under its REFERENCE key name ("model.0.weight",
  * "model.1.sub.3.RDB2.conv4.0.bias", "model.1.sub.23.weight", "model.10.bias", ...); host fp32. */
 int innfer_rrdb_load(innfer_rrdb* h, const char* key, const float* host_data, const int64_t* shape,

@@ -1,6 +1,6 @@
 """get_network -- mirror of the reference's architectures/__init__.py:5-40 for the hot path."""
 
-_OUT_OF_SCOPE = ("sr_resnet", "mrrdb_net", "ppon", "pan_net", "unet_net", "resnet_net", "wbcunet_net")
+_OUT_OF_SCOPE = ("mrrdb_net", "ppon", "pan_net", "unet_net", "resnet_net", "wbcunet_net")
 
 
 def get_network(opt_net):
@@ -9,6 +9,9 @@ def get_network(opt_net):
     if kind == "rrdb_net":
         from . import RRDBNet_arch
         return RRDBNet_arch.RRDBNet(**opt_net)
+    if kind == "sr_resnet":
+        from . import SRResNet_arch
+        return SRResNet_arch.SRResNet(**opt_net)
     if kind in _OUT_OF_SCOPE:
         raise NotImplementedError(
             "Model [%s] exists in the reference but is outside the B200 RRDB hot-path scope "

@@ -87,6 +87,17 @@ def upconv_block(in_nc, out_nc, upscale_factor=2, kernel_size=3, stride=1, bias=
     return sequential(up, conv)
 
 
+def pixelshuffle_block(in_nc, out_nc, upscale_factor=2, kernel_size=3, stride=1, bias=True, pad_type="zero",
+                       norm_type=None, act_type="relu", convtype="Conv2D"):
+    """conv (in_nc -> out_nc * r^2) + PixelShuffle(r) [+ activation] (reference block.py:333-346)."""
+    if norm_type:
+        raise NotImplementedError("pixelshuffle_block: norm layers are not supported")
+    conv = conv_block(in_nc, out_nc * (upscale_factor ** 2), kernel_size, stride, bias=bias, pad_type=pad_type,
+                      norm_type=None, act_type=None, convtype=convtype)
+    a = act(act_type) if act_type else None
+    return sequential(conv, nn.PixelShuffle(upscale_factor), None, a)
+
+
 class GaussianNoise(nn.Module):
     """Identity in eval mode (the only mode inference uses)."""
 

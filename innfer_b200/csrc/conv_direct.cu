@@ -13,6 +13,7 @@ struct DirectParams {
   int in_CT, in_chunk0, cin_chunks;
   int B, H, W, up;      // source dims
   int Ho, Wo;
+  int ps, ps_a, ps_b;   // pixel-shuffle factor (1 = none) and this launch's output sub-pixel
   const float* w;       // [ci_pad][9][N]
   const float* bias;    // [N]
   float* out;
@@ -77,8 +78,8 @@ conv_direct_kernel(const __grid_constant__ DirectParams p) {
     }
   }
   if (ox >= p.Wo || oy >= p.Ho) return;
-  const size_t oplane = (size_t)p.Ho * p.Wo;
-  const size_t opix = (size_t)oy * p.Wo + ox;
+  const size_t oplane = (size_t)p.Ho * p.Wo * p.ps * p.ps;
+  const size_t opix = (size_t)(oy * p.ps + p.ps_a) * (p.Wo * p.ps) + (ox * p.ps + p.ps_b);
 #pragma unroll
   for (int ch = 0; ch < N / 8; ++ch) {
     if (ch >= p.out_nchunks) break;
@@ -115,11 +116,15 @@ conv_direct_kernel(const __grid_constant__ DirectParams p) {
 int conv_direct_upload(ConvLayer& L) {
   if (L.d_w32) return 0;
   const int N = L.N;
-  std::vector<float> t((size_t)L.Cin_pad * 9 * N, 0.f);
-  for (int co = 0; co < L.Cout; ++co)
-    for (int ci = 0; ci < L.Cin; ++ci)
-      for (int k = 0; k < 9; ++k)
-        t[((size_t)ci * 9 + k) * N + co] = L.h_w32[((size_t)co * L.Cin + ci) * 9 + k];
+  const int nsets = L.pixel_shuffle ? L.nphase : 1;   // one filter set per output sub-pixel
+  std::vector<float> t((size_t)nsets * L.Cin_pad * 9 * N, 0.f);
+  for (int ph = 0; ph < nsets; ++ph)
+    for (int co = 0; co < L.Cout; ++co) {
+      const int row = L.pixel_shuffle ? co * L.nphase + ph : co;
+      for (int ci = 0; ci < L.Cin; ++ci)
+        for (int k = 0; k < 9; ++k)
+          t[(((size_t)ph * L.Cin_pad + ci) * 9 + k) * N + co] = L.h_w32[((size_t)row * L.Cin + ci) * 9 + k];
+    }
   cudaError_t e = cudaMalloc(&L.d_w32, t.size() * sizeof(float));
   if (e != cudaSuccess) return (int)e;
   e = cudaMemcpy(L.d_w32, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -137,9 +142,11 @@ int conv_direct_run(const ConvLayer& L, ChunkView in, int B, int H, int W, Chunk
   p.B = B;
   p.H = H;
   p.W = W;
-  p.up = L.up;
-  p.Ho = H * L.up;
-  p.Wo = W * L.up;
+  p.up = L.pixel_shuffle ? 1 : L.up;
+  p.Ho = H * p.up;
+  p.Wo = W * p.up;
+  p.ps = L.pixel_shuffle ? L.up : 1;
+  p.ps_a = p.ps_b = 0;
   p.w = L.d_w32;
   p.bias = L.d_bias;
   p.out = reinterpret_cast<float*>(out.base);
@@ -157,11 +164,18 @@ int conv_direct_run(const ConvLayer& L, ChunkView in, int B, int H, int W, Chunk
   p.res2_chunk0 = ep.res2.chunk0;
   p.alpha2 = ep.alpha2;
   dim3 grid((p.Wo + kTX - 1) / kTX, (p.Ho + kTY - 1) / kTY, B), block(kTY * kTX);
-  switch (L.N) {
-    case 16: conv_direct_kernel<16><<<grid, block, 0, stream>>>(p); break;
-    case 32: conv_direct_kernel<32><<<grid, block, 0, stream>>>(p); break;
-    case 64: conv_direct_kernel<64><<<grid, block, 0, stream>>>(p); break;
-    default: return -7;
+  const int nsets = L.pixel_shuffle ? L.nphase : 1;
+  for (int ph = 0; ph < nsets; ++ph) {
+    p.ps_a = ph / p.ps;
+    p.ps_b = ph % p.ps;
+    p.w = L.d_w32 + (size_t)ph * L.Cin_pad * 9 * L.N;
+    p.bias = L.d_bias + (size_t)ph * L.N;
+    switch (L.N) {
+      case 16: conv_direct_kernel<16><<<grid, block, 0, stream>>>(p); break;
+      case 32: conv_direct_kernel<32><<<grid, block, 0, stream>>>(p); break;
+      case 64: conv_direct_kernel<64><<<grid, block, 0, stream>>>(p); break;
+      default: return -7;
+    }
   }
   return (int)cudaGetLastError();
 }

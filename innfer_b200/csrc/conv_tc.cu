@@ -85,7 +85,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&set_bar[i]), 4);
     fence_mbar_init();
   }
-  if (threadIdx.x < N) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  for (int i = threadIdx.x; i < p.nphase * N; i += blockDim.x) s_bias[i] = p.bias[i];  // bias is [phase][N]
   if (warp == 1) {
     tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
     tmem_relinquish();
@@ -266,7 +266,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                float tv = __uint_as_float(v[ch * 8 + e]) + s_bias[ch * 8 + e];
+                float tv = __uint_as_float(v[ch * 8 + e]) + s_bias[c.phase * N + ch * 8 + e];
                 if (p.lrelu) tv = lrelu_f(tv, p.slope);
                 f[e] = tv;
               }
@@ -322,7 +322,7 @@ int launch_impl(const CUtensorMap* tmap_in, const ConvTcParams& p, int num_sms, 
   int max_taps = 0;
   for (int i = 0; i < p.nphase; ++i) max_taps = max_taps > p.ph_ntaps[i] ? max_taps : p.ph_ntaps[i];
   const int stage_bytes = conv_tc_a_bytes(p.J) + conv_tc_w_bytes(N, max_taps);
-  const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024;
+  const size_t smem_bytes = (size_t)p.stages * stage_bytes + kConvTailBytes;
   cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes);
   if (e != cudaSuccess) return (int)e;

@@ -35,6 +35,7 @@ constexpr int kPatchRows = 16;            // rows per CTA patch (= rows of one M
 constexpr int kHaloRows = kPatchRows + 2; // Rh
 constexpr int kMaxPhases = 9;
 constexpr int kMaxTaps = 9;
+constexpr int kConvTailBytes = 4096;       // barriers + TMEM slot + per-phase bias behind the stage ring
 
 struct ConvTcParams {
   // source geometry
@@ -57,7 +58,7 @@ struct ConvTcParams {
   int out_compact4;  // final conv only: store channels 0..3 as [tile][Hout][Wout][4] fp16 (8 B / pixel)
   // weights / bias
   const __half* w;       // packed [phase][kslab][tap][2][N][8]
-  const float* bias;     // [N]
+  const float* bias;     // [nphase][N]
   // epilogue
   int lrelu;
   float slope;

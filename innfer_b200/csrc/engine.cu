@@ -66,6 +66,9 @@ PixelDType to_pix(int dtype) { return dtype == INNFER_F16 ? kF16 : (dtype == INN
 
 struct innfer_rrdb {
   innfer_rrdb_cfg cfg;
+  int arch = 0;            // 0: RRDBNet (ESRGAN), 1: SRResNet (SRGAN generator)
+  float res_scale = 1.f;   // SRResNet residual scaling
+  bool ps_mode = true;     // SRResNet upsampler: pixelshuffle (default) or upconv
   int device = 0;
   int num_sms = 148;
   int n_up = 0, up_factor = 2;
@@ -108,7 +111,7 @@ struct innfer_rrdb {
   int in_ct() const { return (cfg.in_nc + 15) / 16 * 2; }
   int nf_ct() const { return cfg.nf / 8; }
   // concat buffer: x, x1..x4 (+ 4 chunks for conv1x1(x) in ESRGAN+ mode)
-  int cat_ct() const { return (cfg.nf + 4 * 32) / 8 + (cfg.plus ? 4 : 0); }
+  int cat_ct() const { return arch == 1 ? cfg.nf / 8 : (cfg.nf + 4 * 32) / 8 + (cfg.plus ? 4 : 0); }
   size_t esz() const { return cfg.fp16 ? 2 : 4; }
 };
 
@@ -134,6 +137,26 @@ int build_layer(innfer_rrdb* h, ConvLayer& L, const std::string& prefix, int Cou
   std::string err;
   int rc = conv_layer_build(L, wi->second.data.data(), has_bias ? bi->second.data.data() : nullptr, Cout, Cin, up, err,
                             ksize);
+  if (rc) return fail(rc == -2 ? INNFER_E_UNSUPPORTED : INNFER_E_CUDA, prefix + ": " + err);
+  if (!h->cfg.fp16) {
+    rc = conv_direct_upload(L);
+    if (rc) return fail(INNFER_E_CUDA, prefix + ": fp32 weight upload failed");
+  }
+  return 0;
+}
+
+int build_ps_layer(innfer_rrdb* h, ConvLayer& L, const std::string& prefix, int Cout, int Cin, int r) {
+  auto wi = h->params.find(prefix + ".weight");
+  auto bi = h->params.find(prefix + ".bias");
+  if (wi == h->params.end()) return fail(INNFER_E_STATE, "missing key " + prefix + ".weight");
+  if (bi == h->params.end()) return fail(INNFER_E_STATE, "missing key " + prefix + ".bias");
+  const auto& ws = wi->second.shape;
+  if (ws.size() != 4 || ws[0] != Cout * r * r || ws[1] != Cin || ws[2] != 3 || ws[3] != 3)
+    return fail(INNFER_E_INVALID, "size mismatch for " + prefix + ".weight");
+  if (bi->second.shape.size() != 1 || bi->second.shape[0] != Cout * r * r)
+    return fail(INNFER_E_INVALID, "size mismatch for " + prefix + ".bias");
+  std::string err;
+  int rc = conv_layer_build_ps(L, wi->second.data.data(), bi->second.data.data(), Cout, Cin, r, err);
   if (rc) return fail(rc == -2 ? INNFER_E_UNSUPPORTED : INNFER_E_CUDA, prefix + ": " + err);
   if (!h->cfg.fp16) {
     rc = conv_direct_upload(L);
@@ -202,7 +225,55 @@ int forward_tiles(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool c
   return rc;
 }
 
+// SRResNet.forward (SRResNet_arch.py:15-62): fea_conv, ShortcutBlock(ResNetBlock x nb, LR_conv),
+// pixel-shuffle (or upconv) blocks + ReLU, HR_conv0 + ReLU, HR_conv1.  ResNetBlock (CNA, no norm):
+// x + res_scale * conv1(relu(conv0(x))) -- the scaled add is conv1's residual epilogue.
+int forward_tiles_srresnet(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool compact, cudaStream_t st) {
+  const int nfc = h->nf_ct();
+  int rc;
+  Epilogue plain, relu;
+  relu.lrelu = true;
+  relu.slope = 0.f;
+  if ((rc = run_conv(h, h->fea, view(h->in_tiles, h->in_ct(), 0), B, hgt, wid, view(h->feat, nfc, 0), nfc, plain, st))) return rc;
+  int X = 0, T = 1, Y = 2;
+  ChunkView cur = view(h->feat, nfc, 0);
+  for (int b = 0; b < h->cfg.nb; ++b) {
+    const ConvLayer* L = &h->rdb[(size_t)b * 2];
+    if ((rc = run_conv(h, L[0], cur, B, hgt, wid, view(h->xbuf[T], nfc, 0), nfc, relu, st))) return rc;
+    Epilogue e;
+    e.res1 = cur;
+    e.alpha1 = h->res_scale;
+    if ((rc = run_conv(h, L[1], view(h->xbuf[T], nfc, 0), B, hgt, wid, view(h->xbuf[Y], nfc, 0), nfc, e, st))) return rc;
+    cur = view(h->xbuf[Y], nfc, 0);
+    const int t = X;
+    X = Y;
+    Y = t;
+  }
+  {
+    Epilogue e;
+    e.res1 = view(h->feat, nfc, 0);
+    e.alpha1 = 1.0f;
+    if ((rc = run_conv(h, h->lr_conv, cur, B, hgt, wid, view(h->xbuf[T], nfc, 0), nfc, e, st))) return rc;
+    cur = view(h->xbuf[T], nfc, 0);
+  }
+  int ch = hgt, cw = wid, pp = 0;
+  for (size_t i = 0; i < h->ups.size(); ++i) {
+    ChunkView o = view(h->hrbuf[pp], nfc, 0);
+    if ((rc = run_conv(h, h->ups[i], cur, B, ch, cw, o, nfc, relu, st))) return rc;
+    ch *= h->ups[i].up;
+    cw *= h->ups[i].up;
+    cur = o;
+    pp ^= 1;
+  }
+  ChunkView o = view(h->hrbuf[pp], nfc, 0);
+  if ((rc = run_conv(h, h->hr0, cur, B, ch, cw, o, nfc, relu, st))) return rc;
+  Epilogue last;
+  last.compact4 = compact;
+  return run_conv(h, h->hr1, o, B, ch, cw, dst, (h->cfg.out_nc + 7) / 8, last, st);
+}
+
 int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool compact, cudaStream_t st) {
+  if (h->arch == 1) return forward_tiles_srresnet(h, B, hgt, wid, dst, compact, st);
   const int nfc = h->nf_ct(), catc = h->cat_ct();
   const int gcc = 32 / 8;
   int rc;
@@ -429,6 +500,19 @@ int innfer_rrdb_create(const innfer_rrdb_cfg* cfg, int device, innfer_rrdb** out
   return 0;
 }
 
+int innfer_srresnet_create(const innfer_srresnet_cfg* cfg, int device, innfer_rrdb** out) {
+  if (!cfg || !out) return fail(INNFER_E_INVALID, "null argument");
+  if (cfg->upsample_mode != 0 && cfg->upsample_mode != 1) return fail(INNFER_E_INVALID, "upsample_mode must be 0 or 1");
+  innfer_rrdb_cfg base = {cfg->in_nc, cfg->out_nc, cfg->nf, cfg->nb, 32, cfg->scale, 0, cfg->fp16};
+  int rc = innfer_rrdb_create(&base, device, out);
+  if (rc) return rc;
+  (*out)->arch = 1;
+  (*out)->res_scale = cfg->res_scale;
+  (*out)->up_factor = cfg->scale == 3 ? 3 : 2;
+  (*out)->ps_mode = cfg->upsample_mode == 0;
+  return 0;
+}
+
 int innfer_rrdb_load(innfer_rrdb* h, const char* key, const float* host_data, const int64_t* shape, int ndim) {
   if (!h || !key || !host_data || !shape || ndim < 1 || ndim > 4) return fail(INNFER_E_INVALID, "bad argument");
   if (h->finalized) return fail(INNFER_E_STATE, "handle already finalized");
@@ -452,6 +536,42 @@ int innfer_rrdb_finalize(innfer_rrdb* h) {
   size_t expected = 0;
   if ((rc = build_layer(h, h->fea, "model.0", c.nf, c.in_nc, 1))) return rc;
   expected += 2;
+  if (h->arch == 1) {
+    // SRResNet keys (block.py:197-210 flattening): model.1.sub.<i>.res.{0,2}, model.1.sub.<nb>,
+    // then per upsampler block conv at 2+3i (pixelshuffle: conv, PixelShuffle, ReLU) or 3+3i (upconv:
+    // Upsample, conv, ReLU), HR_conv0 at 2+3*n_up, HR_conv1 at 4+3*n_up
+    h->rdb.resize((size_t)c.nb * 2);
+    for (int b = 0; b < c.nb; ++b)
+      for (int k = 0; k < 2; ++k) {
+        char key[96];
+        snprintf(key, sizeof key, "model.1.sub.%d.res.%d", b, 2 * k);
+        if ((rc = build_layer(h, h->rdb[(size_t)b * 2 + k], key, c.nf, c.nf, 1))) return rc;
+        expected += 2;
+      }
+    char key[64];
+    snprintf(key, sizeof key, "model.1.sub.%d", c.nb);
+    if ((rc = build_layer(h, h->lr_conv, key, c.nf, c.nf, 1))) return rc;
+    expected += 2;
+    h->ups.resize(h->n_up);
+    for (int i = 0; i < h->n_up; ++i) {
+      snprintf(key, sizeof key, "model.%d", (h->ps_mode ? 2 : 3) + 3 * i);
+      rc = h->ps_mode ? build_ps_layer(h, h->ups[i], key, c.nf, c.nf, h->up_factor)
+                      : build_layer(h, h->ups[i], key, c.nf, c.nf, h->up_factor);
+      if (rc) return rc;
+      expected += 2;
+    }
+    snprintf(key, sizeof key, "model.%d", 2 + 3 * h->n_up);
+    if ((rc = build_layer(h, h->hr0, key, c.nf, c.nf, 1))) return rc;
+    snprintf(key, sizeof key, "model.%d", 4 + 3 * h->n_up);
+    if ((rc = build_layer(h, h->hr1, key, c.out_nc, c.nf, 1))) return rc;
+    expected += 4;
+    if (h->params.size() != expected)
+      return fail(INNFER_E_INVALID, "unexpected keys in state dict (" + std::to_string(h->params.size()) +
+                                        " loaded, " + std::to_string(expected) + " expected)");
+    h->params.clear();
+    h->finalized = true;
+    return 0;
+  }
   h->rdb.resize((size_t)c.nb * 15);
   if (c.plus) h->c1x1.resize((size_t)c.nb * 3);
   for (int b = 0; b < c.nb; ++b)

@@ -127,21 +127,79 @@ int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cou
             }
   }
   L.w_bytes = packed.size() * sizeof(__half);
-  std::vector<float> hb(N, 0.f);
+  std::vector<float> hb((size_t)L.nphase * N, 0.f);
   if (bias)
-    for (int i = 0; i < Cout; ++i) hb[i] = bias[i];
+    for (int ph = 0; ph < L.nphase; ++ph)
+      for (int i = 0; i < Cout; ++i) hb[(size_t)ph * N + i] = bias[i];
   L.h_w32.assign(w, w + (size_t)Cout * Cin * 9);
   L.h_b32.assign(hb.begin(), hb.begin() + Cout);
+  L.pixel_shuffle = false;
 
   cudaError_t e;
   if ((e = cudaMalloc(&L.d_w, L.w_bytes)) != cudaSuccess ||
-      (e = cudaMalloc(&L.d_bias, N * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&L.d_bias, hb.size() * sizeof(float))) != cudaSuccess ||
       (e = cudaMemcpy(L.d_w, packed.data(), L.w_bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
-      (e = cudaMemcpy(L.d_bias, hb.data(), N * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(L.d_bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess ||
       (!packed_dx.empty() &&
        ((e = cudaMalloc(&L.d_wdx, packed_dx.size() * sizeof(__half))) != cudaSuccess ||
         (e = cudaMemcpy(L.d_wdx, packed_dx.data(), packed_dx.size() * sizeof(__half), cudaMemcpyHostToDevice)) !=
             cudaSuccess))) {
+    err = std::string("cuda error while uploading weights: ") + cudaGetErrorString(e);
+    return -3;
+  }
+  return 0;
+}
+
+int conv_layer_build_ps(ConvLayer& L, const float* w, const float* bias, int Cout, int Cin, int r,
+                        std::string& err) {
+  if (r < 2 || r > 3 || Cout > 64) {
+    err = "pixel-shuffle conv: factor must be 2 or 3 and at most 64 channels per sub-pixel";
+    return -2;
+  }
+  L.Cin = Cin;
+  L.Cout = Cout;
+  L.Cin_pad = (Cin + 15) / 16 * 16;
+  L.N = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : 64);
+  L.up = r;
+  L.nphase = r * r;
+  L.pixel_shuffle = true;
+  L.max_taps = 9;
+  const int N = L.N, kslabs = L.Cin_pad / 16;
+  std::vector<__half> packed;
+  std::vector<float> hb((size_t)L.nphase * N, 0.f);
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < r; ++j) {
+      const int ph = i * r + j;
+      L.ph_ntaps[ph] = 9;
+      L.ph_a[ph] = (uint8_t)i;
+      L.ph_b[ph] = (uint8_t)j;
+      L.ph_woff[ph] = (uint32_t)(packed.size() * sizeof(__half));
+      for (int t = 0; t < 9; ++t) {
+        L.tap_hy[ph][t] = (uint8_t)(t / 3);
+        L.tap_hx[ph][t] = (uint8_t)(t % 3);
+      }
+      for (int ks = 0; ks < kslabs; ++ks)
+        for (int tp = 0; tp < 9; ++tp)
+          for (int kc = 0; kc < 2; ++kc)
+            for (int n = 0; n < N; ++n)
+              for (int e = 0; e < 8; ++e) {
+                const int ci = ks * 16 + kc * 8 + e;
+                float v = 0.f;
+                if (n < Cout && ci < Cin) v = w[(((size_t)(n * r * r + ph) * Cin + ci) * 9) + tp];
+                packed.push_back(__float2half_rn(v));
+              }
+      if (bias)
+        for (int n = 0; n < Cout; ++n) hb[(size_t)ph * N + n] = bias[n * r * r + ph];
+    }
+  L.w_bytes = packed.size() * sizeof(__half);
+  L.h_w32.assign(w, w + (size_t)Cout * r * r * Cin * 9);
+  L.h_b32.assign(r * r * Cout, 0.f);
+  if (bias) L.h_b32.assign(bias, bias + (size_t)r * r * Cout);
+  cudaError_t e;
+  if ((e = cudaMalloc(&L.d_w, L.w_bytes)) != cudaSuccess ||
+      (e = cudaMalloc(&L.d_bias, hb.size() * sizeof(float))) != cudaSuccess ||
+      (e = cudaMemcpy(L.d_w, packed.data(), L.w_bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(L.d_bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
     err = std::string("cuda error while uploading weights: ") + cudaGetErrorString(e);
     return -3;
   }
@@ -257,7 +315,7 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
   while (pw < cols) pw <<= 1;
   p.tmem_cols = pw;
   const int stage_bytes = conv_tc_a_bytes(J) + conv_tc_w_bytes(N, L.max_taps);
-  int S = (232448 - 1024) / stage_bytes;
+  int S = (232448 - kConvTailBytes) / stage_bytes;
   if (S > 8) S = 8;
   if (S < 2) return -4;
   p.stages = S;

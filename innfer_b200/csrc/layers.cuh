@@ -27,7 +27,8 @@ struct ConvLayer {
   int Cin = 0, Cout = 0;   // real channel counts
   int Cin_pad = 0;         // multiple of 16
   int N = 0;               // padded Cout: 16, 32 or 64
-  int up = 1;              // nearest-upsample factor folded in front of the conv
+  int up = 1;              // nearest-upsample factor folded in front of the conv (or PixelShuffle factor)
+  bool pixel_shuffle = false;  // conv -> PixelShuffle(up) (block.py:333-346): phase = output sub-pixel
   int nphase = 1;
   uint32_t ph_woff[kMaxPhases] = {};
   uint8_t ph_ntaps[kMaxPhases] = {};
@@ -37,7 +38,7 @@ struct ConvLayer {
   int max_taps = 0;
   __half* d_w = nullptr;   // device, packed [phase][kslab][tap][2][N][8]
   __half* d_wdx = nullptr; // device, dx-as-N packing [kslab][dy][2][dx*32+co][8] (Cout == 32, up == 1 only)
-  float* d_bias = nullptr; // device, [N]
+  float* d_bias = nullptr; // device, [nphase][N]
   size_t w_bytes = 0;
   // fp32 copies (OIHW + bias) kept on the device for the fp32-mode direct kernel
   float* d_w32 = nullptr;
@@ -57,6 +58,10 @@ struct Epilogue {
 // ksize 3 (default) or 1: a 1x1 conv (ESRGAN+ conv1x1, block.py:390-391) runs as a single centre tap.
 int conv_layer_build(ConvLayer& L, const float* w_oihw, const float* bias, int Cout, int Cin,
                      int up, std::string& err, int ksize = 3);
+// conv (Cin -> Cout*r*r) followed by PixelShuffle(r): one 9-tap phase per output sub-pixel (i, j), whose
+// Cout filters are rows c*r*r + i*r + j of the weight tensor; the shuffle becomes output addressing.
+int conv_layer_build_ps(ConvLayer& L, const float* w_oihw, const float* bias, int Cout, int Cin, int r,
+                        std::string& err);
 void conv_layer_free(ConvLayer& L);
 
 // Cache of encoded TMA descriptors keyed by (base, B, CT, H, W, box width in pixels).

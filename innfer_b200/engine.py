@@ -37,11 +37,15 @@ class RRDBEngine:
         self.index = device.index if device.index is not None else torch.cuda.current_device()
         self.fp16 = bool(fp16)
         self.cfg = dict(cfg)
+        self._h = ctypes.c_void_p()
+        self._create()
+        self._finalized = False
+
+    def _create(self):
+        cfg = self.cfg
         c = N.RRDBCfg(cfg["in_nc"], cfg["out_nc"], cfg["nf"], cfg["nb"], cfg.get("gc", 32), cfg["scale"],
                       int(bool(cfg.get("plus", False))), int(self.fp16))
-        self._h = ctypes.c_void_p()
         N.check(self.lib.innfer_rrdb_create(ctypes.byref(c), self.index, ctypes.byref(self._h)))
-        self._finalized = False
 
     # -- construction ----------------------------------------------------------------------------
     @classmethod
@@ -157,3 +161,14 @@ class RRDBEngine:
         N.check(self.lib.innfer_rrdb_upscale_u8_device(self._h, img.data_ptr(), H, W, int(patch_size), float(step),
                                                        out.data_ptr(), _stream_ptr(img.device)))
         return out
+
+
+class SRResNetEngine(RRDBEngine):
+    """Native handle for architectures.SRResNet_arch.SRResNet (same execution API as RRDBEngine)."""
+
+    def _create(self):
+        cfg = self.cfg
+        mode = {"pixelshuffle": 0, "upconv": 1}[cfg.get("upsample_mode", "pixelshuffle")]
+        c = N.SRResNetCfg(cfg["in_nc"], cfg["out_nc"], cfg["nf"], cfg["nb"], cfg["scale"], mode,
+                          float(cfg.get("res_scale", 1.0)), int(self.fp16))
+        N.check(self.lib.innfer_srresnet_create(ctypes.byref(c), self.index, ctypes.byref(self._h)))

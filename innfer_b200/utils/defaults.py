@@ -2,7 +2,8 @@
 family (other families are outside the hot-path scope and raise NotImplementedError)."""
 
 _RRDB_ALIASES = ("rrdb_net", "esrgan", "esrgan-lite")
-_OTHER_KINDS = ("evsrgan", "mrrdb_net", "mesrgan", "sr_resnet", "srresnet", "srgan", "ppon", "pan", "pan_net",
+_SRRESNET_ALIASES = ("sr_resnet", "srresnet", "srgan")
+_OTHER_KINDS = ("evsrgan", "mrrdb_net", "mesrgan", "ppon", "pan", "pan_net",
                 "unet_net", "unet", "resnet_net", "resnet", "wbcunet", "wbcunet_net")
 
 
@@ -39,6 +40,22 @@ def get_network_G_config(network_G, scale):
             "upsample_mode": opts.pop("upsample_mode", "upconv"),
         }
         return full
+    if kind in _SRRESNET_ALIASES:
+        return {
+            "type": "sr_resnet",
+            "in_nc": opts.pop("in_nc", 3),
+            "out_nc": opts.pop("out_nc", 3),
+            "nf": opts.pop("nf", 64),
+            "nb": opts.pop("nb", 16),
+            "upscale": opts.pop("scale", scale),
+            "norm_type": opts.pop("norm_type", None),
+            "act_type": opts.pop("net_act", None) or opts.pop("act_type", "relu"),
+            "mode": opts.pop("mode", "CNA"),
+            "upsample_mode": opts.pop("upsample_mode", "pixelshuffle"),
+            "convtype": opts.pop("convtype", "Conv2D"),
+            "finalact": opts.pop("finalact", None),
+            "res_scale": opts.pop("res_scale", 1),
+        }
     if kind in _OTHER_KINDS or kind.startswith(("unet_", "p2p_", "resnet_", "cg_")):
         raise NotImplementedError(
             "generator [%s] exists in the reference but is outside the B200 RRDB hot-path scope" % kind)

@@ -144,6 +144,58 @@ def rrdbnet_forward(sd, x, scale=None):
         return _conv(sd, "model.%d" % hr1, t, False)
 
 
+# ----------------------------------------------------------------------------- SRResNet (8f rank 1)
+
+
+def make_srresnet_state_dict(scale=4, nb=16, nf=64, in_nc=3, out_nc=3, seed=0, last_bias=0.5):
+    """Default-initialised SRResNet weights in the construction order of SRResNet.__init__
+    (SRResNet_arch.py:24-45) with the pixelshuffle upsampler of utils/defaults.py:64."""
+    torch.manual_seed(seed)
+    sd = OrderedDict()
+
+    def put(name, cout, cin):
+        w, b = _conv_init(cout, cin)
+        sd[name + ".weight"] = w
+        sd[name + ".bias"] = b
+
+    put("model.0", nf, in_nc)
+    for b in range(nb):
+        put("model.1.sub.%d.res.0" % b, nf, nf)
+        put("model.1.sub.%d.res.2" % b, nf, nf)
+    put("model.1.sub.%d" % nb, nf, nf)
+    n_up = {1: 0, 2: 1, 3: 1, 4: 2, 8: 3}[scale]
+    r = 3 if scale == 3 else 2
+    for i in range(n_up):
+        put("model.%d" % (2 + 3 * i), nf * r * r, nf)
+    put("model.%d" % (2 + 3 * n_up), nf, nf)
+    put("model.%d" % (4 + 3 * n_up), out_nc, nf)
+    if last_bias is not None:
+        sd["model.%d.bias" % (4 + 3 * n_up)].fill_(last_bias)
+    return sd
+
+
+def srresnet_forward(sd, x, scale, res_scale=1.0):
+    """SRResNet.forward (SRResNet_arch.py:47-62) for norm None / ReLU / CNA / pixelshuffle:
+    ResNetBlock = x + res_scale * conv1(relu(conv0(x))) (77-91); pixelshuffle_block = conv,
+    PixelShuffle, ReLU (block.py:333-346)."""
+    def conv(name, t, relu=False):
+        y = F.conv2d(t, sd[name + ".weight"], sd[name + ".bias"], padding=1)
+        return F.relu(y) if relu else y
+    nb = max(int(k.split(".")[3]) for k in sd if k.startswith("model.1.sub.") and k.count(".") == 4)
+    n_up = {1: 0, 2: 1, 3: 1, 4: 2, 8: 3}[scale]
+    r = 3 if scale == 3 else 2
+    with torch.no_grad():
+        fea = conv("model.0", x)
+        t = fea
+        for b in range(nb):
+            t = t + res_scale * conv("model.1.sub.%d.res.2" % b, conv("model.1.sub.%d.res.0" % b, t, True))
+        t = fea + conv("model.1.sub.%d" % nb, t)
+        for i in range(n_up):
+            t = F.relu(F.pixel_shuffle(conv("model.%d" % (2 + 3 * i), t), r))
+        t = conv("model.%d" % (2 + 3 * n_up), t, True)
+        return conv("model.%d" % (4 + 3 * n_up), t)
+
+
 # ----------------------------------------------------------------------------- tiling / blending
 
 

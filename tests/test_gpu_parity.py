@@ -186,6 +186,37 @@ def test_esrgan_plus_vs_reference_fixture(dev, fp16):
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["srresnet_s4_nb3_40x48_p32.npz", "srresnet_s2_nb2_36x44_p32.npz"])
+@pytest.mark.parametrize("fp16", [True, False])
+def test_srresnet_vs_reference_fixture(dev, tmp_path, name, fp16):
+    """SRResNet: ReLU epilogue, res_scale residual, PixelShuffle folded into the
+    conv's output addressing -- through run.Model on cuda against the reference fixture."""
+    from innfer_b200 import run as R
+    from innfer_b200.utils import utils as U
+    g = golden(name)
+    scale = int(g["scale"])
+    sd = O.make_srresnet_state_dict(scale=scale, nb=int(g["nb"]), seed=int(g["seed"]))
+    path = str(tmp_path / ("%dx_srres.pth" % scale))
+    torch.save(sd, path)
+    m = R.Model(path, "infer", None, device=dev)
+    assert (m.arch, m.scale) == ("srgan", scale)
+    if fp16:
+        m.model.half()
+    img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))
+    x = U.np2tensor(img).to(dev)
+    x = x.half() if fp16 else x
+    y = m.chop_forward(x, patch_size=int(g["patch"]), step=0.5)
+    u8 = U.tensor2np(y)
+    assert np.abs(u8.astype(int) - g["u8"].astype(int)).max() <= 1 and psnr_u8(u8, g["u8"]) >= 50.0
+    if not fp16:
+        assert np.abs(y.cpu().numpy() - g["y"]).max() / np.abs(g["y"]).max() <= 1e-4
+    # un-chopped forward against the oracle
+    m.chop = False
+    y2 = m(x).float().cpu()
+    ref = O.srresnet_forward(sd, U.np2tensor(img), scale)
+    assert np.abs(U.tensor2np(y2).astype(int) - O.tensor2np(ref).astype(int)).max() <= 1
+
+
 def test_python_api_model_chain_and_color_fix(dev, tmp_path, monkeypatch):
     """run.Model on cuda (fp16) + chaining + -cf, and the CLI, vs the reference fixture (config 3 shrunk)."""
     import cv2

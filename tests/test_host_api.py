@@ -91,6 +91,16 @@ def test_esrgan_plus_is_detected_and_runs_on_cpu(tmp_path):
     np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)
 
 
+def test_srresnet_is_detected_and_runs_on_cpu(tmp_path):
+    g = golden("srresnet_s4_nb3_40x48_p32.npz")
+    sd = O.make_srresnet_state_dict(scale=4, nb=3, seed=int(g["seed"]))
+    m = R.Model(_save(sd, tmp_path / "4x_srres.pth"), "infer", None, device=torch.device("cpu"))
+    assert (m.arch, m.scale) == ("srgan", 4) and list(m.model.state_dict().keys()) == list(g["keys"])
+    img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))
+    y = m.chop_forward(U.np2tensor(img), patch_size=int(g["patch"]), step=0.5)
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)
+
+
 def test_infer_params_and_key_mapping(tmp_path):
     g = golden("load_logic.npz")
     for scale, nb in ((1, 2), (2, 3), (4, 23), (8, 1)):
@@ -152,7 +162,7 @@ def test_synth_recipe_matches_reference_init():
 
 def test_unknown_architectures_fail_loudly():
     with pytest.raises(NotImplementedError):
-        get_network({"type": "sr_resnet"})
+        get_network({"type": "ppon"})
     with pytest.raises(NotImplementedError):
         get_network_G_config({"type": "pan"}, 4)
     with pytest.raises(Exception, match="Could not infer"):

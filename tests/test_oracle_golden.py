@@ -54,6 +54,20 @@ def test_esrgan_plus_fixture():
     np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)
 
 
+@pytest.mark.parametrize("name", ["srresnet_s4_nb3_40x48_p32.npz", "srresnet_s2_nb2_36x44_p32.npz"])
+def test_srresnet_fixture(name):
+    g = golden(name)
+    scale = int(g["scale"])
+    sd = O.make_srresnet_state_dict(scale=scale, nb=int(g["nb"]), seed=int(g["seed"]))
+    assert list(sd.keys()) == list(g["keys"])
+    np.testing.assert_array_equal(np.array([float(v.double().sum()) for v in sd.values()]), g["wsum"])
+    assert str(g["arch"]) == "srgan" and int(g["mscale"]) == scale
+    img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))
+    y = O.chop_forward(sd, O.np2tensor(img), patch_size=int(g["patch"]),
+                       forward=lambda t: O.srresnet_forward(sd, t, scale))
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)
+
+
 def test_tile_geometry():
     g = golden("tile_geometry.npz")
     for key in g.files:

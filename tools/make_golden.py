@@ -115,6 +115,23 @@ def main():
                             wsum=np.array([float(v.double().sum()) for v in net.state_dict().values()]),
                             y=y.numpy().astype(np.float32), u8=ref_utils.tensor2np(y.detach()))
 
+        # ---- G4c: SRResNet: auto-detected as 'srgan', pixelshuffle upsampler
+        for scale, nb, (h, w) in ((4, 3, (40, 48)), (2, 2, (36, 44))):
+            torch.manual_seed(13)
+            net = get_network(get_network_G_config({"type": "sr_resnet", "nb": nb}, scale)).eval()
+            with torch.no_grad():
+                list(net.state_dict().values())[-1].fill_(0.5)
+            path = os.path.join(td, "%dx_srres.pth" % scale)
+            save_model(net, path)
+            model = ref_run.Model(path, "infer", None, device=torch.device("cpu"), chop=True)
+            img = image(14, h, w)
+            y = model.chop_forward(ref_utils.np2tensor(img), patch_size=32, step=0.5)
+            np.savez_compressed(os.path.join(OUT, "srresnet_s%d_nb%d_%dx%d_p32.npz" % (scale, nb, h, w)), img_seed=14,
+                                h=h, w=w, patch=32, seed=13, scale=scale, nb=nb, arch=model.arch, mscale=model.scale,
+                                keys=np.array(list(net.state_dict().keys())),
+                                wsum=np.array([float(v.double().sum()) for v in net.state_dict().values()]),
+                                y=y.numpy().astype(np.float32), u8=ref_utils.tensor2np(y.detach()))
+
     # ---- G5: tile geometry of extract_patches_2d for a list of sizes
     geo = {}
     for (h, w, p) in ((1080, 1920, 200), (720, 1280, 200), (512, 512, 200), (64, 64, 200), (256, 320, 200),
