@@ -125,6 +125,44 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_tile_sharded(args, eng, dist, rank, world, local, warm):
+    """Strong scaling on single frames: every rank computes ceil(190/N) tiles of each frame and its
+    last conv stores them into the owner's tile buffer over NVLink (innfer_b200/multi_gpu.py)."""
+    from innfer_b200 import multi_gpu as MG
+    be = MG.NativeTileBackend(eng, H, W, PATCH, STEP)
+    up = MG.TileShardedUpscaler(be, dist)
+    frames = [synth_frame(i) for i in range(2)]
+    out_pix = SCALE * H * SCALE * W
+    f = 0
+    for _ in range(warm):
+        up.upscale(f, frames[f % 2] if MG.frame_owner(f, world) == rank else None)
+        f += 1
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        up.upscale(f, frames[f % 2] if MG.frame_owner(f, world) == rank else None)
+        f += 1
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    up.close()
+    if rank == 0:
+        line = {"metric": "output Mpix/s", "value": out_pix / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,
+                "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "sharding": "tiles of one frame across ranks, CUDA-IPC peer stores, "
+                                                             "owner-side blend, 2 host barriers per frame",
+                           "timing": "host wall clock around whole frames incl. H2D of the frame and D2H of the result"},
+                "e2e": {"value": out_pix / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": ms,
+                        "h2d_bytes_per_step": H * W * 3, "d2h_bytes_per_step": out_pix * 3}}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -134,6 +172,9 @@ def main():
     ap.add_argument("--ref-tiles", type=int, default=2, help="tiles per step for the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-batch", type=int, default=0)
+    ap.add_argument("--shard", default="images", choices=["images", "tiles"],
+                    help="N>1: 'images' = one frame per rank per step (weak scaling, default); 'tiles' = all ranks "
+                         "split the tiles of ONE frame and stitch through CUDA-IPC peer stores (strong scaling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -164,6 +205,10 @@ def main():
     eng = RRDBEngine.from_state_dict(sd, cfg, dev, fp16=True)
     if args.max_batch:
         eng.set_max_batch(args.max_batch)
+
+    if args.shard == "tiles" and world > 1:
+        run_tile_sharded(args, eng, dist, rank, world, local, warm)
+        return
 
     frames = [synth_frame(1000 * rank + i) for i in range(2)]
     d_in = [torch.from_numpy(f).to(dev) for f in frames]

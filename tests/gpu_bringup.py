@@ -218,6 +218,37 @@ def stage_pix():
     return True
 
 
+def stage_cfg3():
+    """BASELINE configs[2] at full size: chained 1x RRDB (JPEG-denoise stand-in) + 4x RRDB with -cf on 1280x720."""
+    import time as _t
+    from innfer_b200.engine import RRDBEngine
+    from innfer_b200.utils import utils as U
+    H, W = 720, 1280
+    sd1 = O.make_state_dict(scale=1, nb=23, seed=5)
+    sd4 = O.make_state_dict(scale=4, nb=23, seed=6)
+    e1 = RRDBEngine.from_state_dict(sd1, dict(in_nc=3, out_nc=3, nf=64, nb=23, gc=32, scale=1, plus=False), dev)
+    e4 = RRDBEngine.from_state_dict(sd4, dict(in_nc=3, out_nc=3, nf=64, nb=23, gc=32, scale=4, plus=False), dev)
+    img = np.random.default_rng(0).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    lib = N.load()
+    d_lr = torch.from_numpy(img).to(dev)
+    d_cf = torch.empty(4 * H, 4 * W, 3, dtype=torch.uint8, device=dev)
+    for it in range(3):
+        torch.cuda.synchronize()
+        t0 = _t.perf_counter()
+        x = O.np2tensor(img).to(dev).half()
+        y = e4.chop_forward(e1.chop_forward(x, 200, 0.5), 200, 0.5)
+        # tensor2np on the device: clip(255x).round() -> uint8 HWC BGR
+        sr = (y[0].float().flip(0).permute(1, 2, 0) * 255).clamp_(0, 255).round_().to(torch.uint8).contiguous()
+        N.check(lib.innfer_color_fix(d_lr.data_ptr(), H, W, sr.data_ptr(), 4 * H, 4 * W, d_cf.data_ptr(), None))
+        out = d_cf.cpu()
+        torch.cuda.synchronize()
+        ms = (_t.perf_counter() - t0) * 1e3
+        print("cfg3 720p 1x+4x+cf iter=%d: %.1f ms  %.1f out-Mpix/s (84+84 tiles, %.1f TFLOP)" %
+              (it, ms, 16 * H * W / ms / 1e3, 84 * 40000 * (O.flop_per_lr_pixel(1) + O.flop_per_lr_pixel(4)) / 1e12))
+    print("unclipped fraction", float(((out > 0) & (out < 255)).float().mean()))
+    return True
+
+
 def stage_time():
     lib = N.load()
     sd = O.make_state_dict(scale=4, nb=23, seed=0)
@@ -252,6 +283,6 @@ if __name__ == "__main__":
     ap.add_argument("--stage", required=True)
     a = ap.parse_args()
     t0 = time.time()
-    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "pix": stage_pix}[a.stage]()
+    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
     print("STAGE %s %s (%.1fs)" % (a.stage, "OK" if ok else "FAILED", time.time() - t0))
     sys.exit(0 if ok else 1)
