@@ -203,7 +203,14 @@ int ensure_workspace(innfer_rrdb* h, int B, int hgt, int wid) {
   const size_t hpx = px * s * s;
   // HR ping-pong buffers: the last upconv output and HR_conv0 output are both full resolution
   for (auto& b : h->hrbuf) rc |= b.ensure(hpx * h->nf_ct() * e8);
-  if (rc) return fail(INNFER_E_NOMEM, "workspace allocation failed");
+  if (rc) {
+    // drop partial allocations so that a retry with a smaller batch starts clean
+    h->in_tiles.release();
+    h->feat.release();
+    for (auto& b : h->xbuf) b.release();
+    for (auto& b : h->hrbuf) b.release();
+    return fail(INNFER_E_NOMEM, "workspace allocation failed");
+  }
   return 0;
 }
 
@@ -391,9 +398,16 @@ int compute_tiles(innfer_rrdb* h, const void* src, PixelDType st, const TilePlan
   const int p = plan.p, s = h->cfg.scale;
   const int n = t_end - t_begin;
   if (n <= 0) return 0;
-  const int B = pick_batch(h, n, p);
+  int B = pick_batch(h, n, p);
   int rc;
-  if ((rc = ensure_workspace(h, B, p, p))) return rc;
+  // Workspace grows with the batch (about 215 MB per 200x200 tile at 4x): when the device cannot
+  // hold it (small GPU, several handles alive) shrink the batch instead of failing.
+  while ((rc = ensure_workspace(h, B, p, p)) == INNFER_E_NOMEM && B > 1) {
+    cudaGetLastError();  // clear the allocation error
+    h->max_batch = B / 2;
+    B = pick_batch(h, n, p);
+  }
+  if (rc) return rc;
   const int oct = (h->cfg.out_nc + 7) / 8;
   const bool compact = compact_tiles(h);
   const size_t tile_out_elems = compact ? (size_t)(s * p) * (s * p) * 4 : (size_t)oct * (s * p) * (s * p) * 8;
