@@ -1,0 +1,38 @@
+// Row-streaming dy-taps-as-N convolution on the wide activation layout (conv_rows.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace innfer {
+
+struct ConvRowsParams {
+  // wide source image [chunk][H][Wtot][8]; Wtot is a multiple of 16
+  int H, Wtot;
+  int nimg, pitch, Wimg;   // image b occupies columns [b*pitch, b*pitch + Wimg)
+  uint32_t magic;          // floor(2^32 / pitch) + 1: column / pitch == umulhi(column, magic)
+  int in_chunk0;           // first input chunk inside the TMA-mapped buffer
+  int nch;                 // input chunks (Cin_pad / 8), even
+  int kc;                  // chunks per pipeline stage (= box depth of the tensor map), even, divides nch
+  int nsub;                // nch / kc stages per row
+  int nstrips;             // ceil((Wtot + 15) / 128); strip m covers columns [128m - 15, 128m + 113)
+  int stages;              // shared-memory ring depth
+  // destination, wide layout with the same geometry
+  __half* out;
+  long long out_cs;        // elements between chunks
+  int out_ys;              // elements between rows (Wtot * 8)
+  int out_chunk0;
+  // weights [slab][dx][2][dy*COUT + co][8] fp16, bias [COUT]
+  const __half* w;
+  const float* bias;
+  int lrelu;
+  float slope;
+  int debug;
+};
+
+int launch_conv_rows(const CUtensorMap* tmap_in, const ConvRowsParams& p, int cout, int num_sms, cudaStream_t stream);
+int conv_rows_stage_bytes(int kc);
+int conv_rows_weight_bytes(int nch, int cout);
+
+}  // namespace innfer

@@ -168,7 +168,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         const uint32_t a_lo = ((sa & 0x3FFFFu) >> 4) | (a_lbo << 16);
         const uint32_t b_lo = (((sa + a_bytes) & 0x3FFFFu) >> 4) | (b_lbo << 16);
         const uint32_t first = ks != 0 ? 1u : 0u;
-        if (ntaps == 9) {
+        if (N == 64 && ntaps == 9 && (p.debug & 64)) {
+          // weight-stationary order: tap outer, sub-patch inner; the tap's B tile is read from shared
+          // memory once (collector fill) and reused for the other sub-patches
+          if (leader) {
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp) {
+              const int hy = tp / 3, hx = tp % 3;
+              const uint64_t bd = make_desc64(b_lo + tp * tap_stride, b_hi);
+              const uint32_t at = a_lo + hy * a_sbo + hx;
+              const uint32_t accf = tp == 0 ? first : 1u;
+              if (tp & 1) {
+                umma_f16_ws<1, true>(acc0, make_desc64(at, a_hi), bd, idesc, accf);
+                for (int j = 1; j < c.jeff; ++j)
+                  umma_f16_ws<1, false>(acc0 + (uint32_t)(j * N), make_desc64(at + 8u * j, a_hi), bd, idesc, accf);
+              } else {
+                umma_f16_ws<0, true>(acc0, make_desc64(at, a_hi), bd, idesc, accf);
+                for (int j = 1; j < c.jeff; ++j)
+                  umma_f16_ws<0, false>(acc0 + (uint32_t)(j * N), make_desc64(at + 8u * j, a_hi), bd, idesc, accf);
+              }
+            }
+          }
+        } else if (ntaps == 9) {
           // plain 3x3: taps are (hy, hx) in row-major order, fully unrolled
           for (int j = 0; j < c.jeff; ++j) {
             const uint32_t acc = acc0 + (uint32_t)(j * N);
@@ -214,7 +235,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     const int m = q * 32 + lane;
     const int r = m >> 3, cc = m & 7;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const size_t oplane = (size_t)p.Hout * p.Wout;
     constexpr int NCH = N / 8;
     int it = 0;
     TileIter ti;
@@ -229,23 +249,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       for (int j = 0; j < c.jeff; ++j) {
         const uint32_t tacc = tmem_base + lane_base + (uint32_t)(((it & 1) * p.J + j) * N);
         const int x = c.x0 + 8 * j + cc;
-        const int ox = x * p.up + p.ph_b[c.phase];
-        const bool valid = (y < p.H) && (x < p.W);
-        const size_t opix = (size_t)oy * p.Wout + ox;
+        const bool inside = (y < p.H) && (x < p.W);
+        // wide source: column -> (image, column inside the image); separator columns are not real pixels
+        int img = c.b, xi = x;
+        bool valid = inside;
+        if (p.sep_pitch) {
+          img = (int)__umulhi((uint32_t)x, p.sep_magic);
+          xi = x - img * p.sep_pitch;
+          valid = inside && (img < p.sep_nimg) && (xi < p.sep_w);
+        }
+        const int ox = xi * p.up + p.ph_b[c.phase];
         // 1. residual loads first: their latency overlaps the TMEM read and nothing below the
         //    slot release depends on the tensor pipe any more
         uint4 r1[NCH], r2[NCH];
         if (p.res1 != nullptr) {
-          const __half* rp = p.res1 + (((size_t)c.b * p.res1_CT + p.res1_chunk0) * oplane + opix) * 8;
+          const __half* rp = p.res1 + (size_t)img * p.res1_bs + (size_t)p.res1_chunk0 * p.res1_cs + (size_t)oy * p.res1_ys + (size_t)ox * 8;
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch)
-            if (valid && ch < p.out_nchunks) r1[ch] = *reinterpret_cast<const uint4*>(rp + (size_t)ch * oplane * 8);
+            if (valid && ch < p.out_nchunks) r1[ch] = *reinterpret_cast<const uint4*>(rp + (size_t)ch * p.res1_cs);
         }
         if (p.res2 != nullptr) {
-          const __half* rp = p.res2 + (((size_t)c.b * p.res2_CT + p.res2_chunk0) * oplane + opix) * 8;
+          const __half* rp = p.res2 + (size_t)img * p.res2_bs + (size_t)p.res2_chunk0 * p.res2_cs + (size_t)oy * p.res2_ys + (size_t)ox * 8;
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch)
-            if (valid && ch < p.out_nchunks) r2[ch] = *reinterpret_cast<const uint4*>(rp + (size_t)ch * oplane * 8);
+            if (valid && ch < p.out_nchunks) r2[ch] = *reinterpret_cast<const uint4*>(rp + (size_t)ch * p.res2_cs);
         }
         // 2. drain the accumulator into registers (the set goes back to the MMA warp after the last one)
         uint32_t v[N];
@@ -258,8 +285,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           if (lane == 0) mbar_arrive(sb);
         }
         // 3. bias, activation, residuals, fp16 pack, 16-byte stores into the destination chunk slice
+        __half* op = p.out + (size_t)img * p.out_bs + (size_t)p.out_chunk0 * p.out_cs + (size_t)oy * p.out_ys + (size_t)ox * p.out_px;
         if (valid) {
-          __half* op = p.out + (((size_t)c.b * p.out_CT + p.out_chunk0) * oplane + opix) * 8;
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch) {
             if (ch < p.out_nchunks) {
@@ -298,12 +325,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
               o.z = *reinterpret_cast<const uint32_t*>(&h2);
               o.w = *reinterpret_cast<const uint32_t*>(&h3);
               if (p.out_compact4) {
-                *reinterpret_cast<uint2*>(p.out + ((size_t)c.b * oplane + opix) * 4) = make_uint2(o.x, o.y);
+                *reinterpret_cast<uint2*>(op) = make_uint2(o.x, o.y);
               } else {
-                *reinterpret_cast<uint4*>(op + (size_t)ch * oplane * 8) = o;
+                *reinterpret_cast<uint4*>(op + (size_t)ch * p.out_cs) = o;
               }
             }
           }
+        } else if (inside && p.out_zero_sep) {
+          // separator column of a wide destination: keep the zero padding between images intact
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch)
+            if (ch < p.out_nchunks) *reinterpret_cast<uint4*>(op + (size_t)ch * p.out_cs) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
     }

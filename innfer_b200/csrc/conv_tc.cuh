@@ -56,6 +56,19 @@ struct ConvTcParams {
   __half* out;
   int out_CT, out_chunk0, out_nchunks;
   int out_compact4;  // final conv only: store channels 0..3 as [tile][Hout][Wout][4] fp16 (8 B / pixel)
+  // element strides of the destination / residual tensors: address = base + image * bs + chunk * cs +
+  // row * ys + column * px.  Tiled [B][CT][H][W][8]: bs = CT*H*W*8, cs = H*W*8, ys = W*8, px = 8.
+  // Wide [CT][H][Wtot][8] (images side by side, `pitch` columns apart): bs = pitch*8, cs = H*Wtot*8,
+  // ys = Wtot*8.  Compact [B][H][W][4]: bs = H*W*4, ys = W*4, px = 4.
+  long long out_bs, out_cs;
+  int out_ys, out_px;
+  long long res1_bs, res1_cs, res2_bs, res2_cs;
+  int res1_ys, res2_ys;
+  // wide SOURCE: B == 1, W == Wtot and a column decomposes as image * sep_pitch + x; columns with
+  // x >= sep_w or image >= sep_nimg are separators: never computed, stored as zeros when the
+  // destination is wide too (out_zero_sep), skipped otherwise.  sep_pitch == 0: tiled source.
+  int sep_pitch, sep_w, sep_nimg, out_zero_sep;
+  uint32_t sep_magic;    // floor(2^32 / sep_pitch) + 1
   // weights / bias
   const __half* w;       // packed [phase][kslab][tap][2][N][8]
   const float* bias;     // [nphase][N]

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -184,6 +185,20 @@ int run_conv(innfer_rrdb* h, const ConvLayer& L, ChunkView in, int B, int H, int
   return 0;
 }
 
+// Wide layout geometry (layers.cuh: ChunkView): images `wid + 1` columns apart, rows padded to 16 columns.
+int wide_pitch(int wid) { return wid + 1; }
+int wide_cols(int B, int wid) { return (B * wide_pitch(wid) + 15) / 16 * 16; }
+
+ChunkView wview(DevBuf& b, int CT, int chunk0, int B, int wid, int up) {
+  ChunkView v;
+  v.base = reinterpret_cast<__half*>(b.p);
+  v.CT = CT;
+  v.chunk0 = chunk0;
+  v.pitch = wide_pitch(wid) * up;
+  v.Wtot = wide_cols(B, wid) * up;
+  return v;
+}
+
 ChunkView view(DevBuf& b, int CT, int chunk0) {
   ChunkView v;
   v.base = reinterpret_cast<__half*>(b.p);
@@ -193,7 +208,8 @@ ChunkView view(DevBuf& b, int CT, int chunk0) {
 }
 
 int ensure_workspace(innfer_rrdb* h, int B, int hgt, int wid) {
-  const size_t px = (size_t)B * hgt * wid;
+  // sized for the wide layout of the fp16 path (one separator column per image, row padded to 16)
+  const size_t px = (size_t)hgt * wide_cols(B, wid);
   const size_t e8 = 8 * h->esz();
   const int s = h->cfg.scale;
   int rc = 0;
@@ -287,9 +303,23 @@ int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, b
   Epilogue plain;
   Epilogue act;
   act.lrelu = true;
+  // fp16 mode runs on the wide layout: the batch is one image with the tiles side by side, which lets
+  // the row-streaming kernel use full 128-pixel MMA tiles whatever the tile width is
+  static const int wide_env = getenv("INNFER_WIDE") ? atoi(getenv("INNFER_WIDE")) : 1;
+  const bool wide = h->cfg.fp16 && wide_env;
+  int lvl = 1;  // resolution of the buffer a view is made for (1 = LR, scale = HR)
+  auto view = [&](DevBuf& b, int CT, int chunk0) {
+    return wide ? wview(b, CT, chunk0, B, wid, lvl) : ::view(b, CT, chunk0);
+  };
   // fea_conv -> feat (kept for the ShortcutBlock) and copy into xbuf[0][0:nfc]
-  if ((rc = run_conv(h, h->fea, view(h->in_tiles, h->in_ct(), 0), B, hgt, wid, view(h->feat, nfc, 0), nfc, plain, st))) return rc;
-  {
+  if (wide) {
+    // fea_conv reads tiled input and skips the separator columns of its wide destination
+    const size_t plane = (size_t)nfc * hgt * wide_cols(B, wid) * 8 * h->esz();
+    CU_TRY(cudaMemsetAsync(h->feat.p, 0, plane, st));
+    if ((rc = run_conv(h, h->fea, ::view(h->in_tiles, h->in_ct(), 0), B, hgt, wid, view(h->feat, nfc, 0), nfc, plain, st))) return rc;
+    CU_TRY(cudaMemcpyAsync(h->xbuf[0].p, h->feat.p, plane, cudaMemcpyDeviceToDevice, st));
+  } else {
+    if ((rc = run_conv(h, h->fea, ::view(h->in_tiles, h->in_ct(), 0), B, hgt, wid, ::view(h->feat, nfc, 0), nfc, plain, st))) return rc;
     const size_t row = (size_t)nfc * hgt * wid * 8 * h->esz();
     CU_TRY(cudaMemcpy2DAsync(h->xbuf[0].p, (size_t)catc * hgt * wid * 8 * h->esz(), h->feat.p, row, row, B,
                              cudaMemcpyDeviceToDevice, st));
@@ -349,6 +379,7 @@ int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, b
   ChunkView cur = view(h->xbuf[Q], catc, 0);
   int ch = hgt, cw = wid, pp = 0;
   for (size_t i = 0; i < h->ups.size(); ++i) {
+    lvl *= h->ups[i].up;
     ChunkView o = view(h->hrbuf[pp], nfc, 0);
     if ((rc = run_conv(h, h->ups[i], cur, B, ch, cw, o, nfc, act, st))) return rc;
     ch *= h->ups[i].up;

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "conv_rows.cuh"
 #include "tmap.cuh"
 
 namespace innfer {
@@ -126,6 +127,22 @@ int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cou
               packed_dx[o++] = __float2half_rn(v);
             }
   }
+  // row-streaming packing (conv_rows.cu): [kslab][dx][kchunk][dy*Cout + co][8]
+  std::vector<__half> packed_rows;
+  if (up == 1 && ksize == 3 && (Cout == 32 || Cout == 64)) {
+    const int NR = 3 * Cout;
+    packed_rows.resize((size_t)kslabs * 3 * 2 * NR * 8);
+    size_t o = 0;
+    for (int ks = 0; ks < kslabs; ++ks)
+      for (int dx = 0; dx < 3; ++dx)
+        for (int kc = 0; kc < 2; ++kc)
+          for (int n = 0; n < NR; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int ci = ks * 16 + kc * 8 + e, dy = n / Cout, co = n % Cout;
+              const float v = ci < Cin ? w[(((size_t)co * Cin + ci) * 3 + dy) * 3 + dx] : 0.f;
+              packed_rows[o++] = __float2half_rn(v);
+            }
+  }
   L.w_bytes = packed.size() * sizeof(__half);
   std::vector<float> hb((size_t)L.nphase * N, 0.f);
   if (bias)
@@ -140,6 +157,10 @@ int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cou
       (e = cudaMalloc(&L.d_bias, hb.size() * sizeof(float))) != cudaSuccess ||
       (e = cudaMemcpy(L.d_w, packed.data(), L.w_bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemcpy(L.d_bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (!packed_rows.empty() &&
+       ((e = cudaMalloc(&L.d_wrows, packed_rows.size() * sizeof(__half))) != cudaSuccess ||
+        (e = cudaMemcpy(L.d_wrows, packed_rows.data(), packed_rows.size() * sizeof(__half), cudaMemcpyHostToDevice)) !=
+            cudaSuccess)) ||
       (!packed_dx.empty() &&
        ((e = cudaMalloc(&L.d_wdx, packed_dx.size() * sizeof(__half))) != cudaSuccess ||
         (e = cudaMemcpy(L.d_wdx, packed_dx.data(), packed_dx.size() * sizeof(__half), cudaMemcpyHostToDevice)) !=
@@ -211,7 +232,9 @@ void conv_layer_free(ConvLayer& L) {
   if (L.d_bias) cudaFree(L.d_bias);
   if (L.d_w32) cudaFree(L.d_w32);
   if (L.d_wdx) cudaFree(L.d_wdx);
+  if (L.d_wrows) cudaFree(L.d_wrows);
   L.d_wdx = nullptr;
+  L.d_wrows = nullptr;
   L.d_w = nullptr;
   L.d_bias = nullptr;
   L.d_w32 = nullptr;
@@ -231,6 +254,68 @@ const CUtensorMap* TmapCache::get(const void* base, int B, int CT, int H, int W,
   }
   maps_[key] = s;
   return &s->m;
+}
+
+const CUtensorMap* TmapCache::get_rows(const void* base, int CT, int H, int Wtot, int kc, int& rc) {
+  auto key = std::make_tuple(base, -1, CT, H, Wtot, -1000 - kc);
+  auto it = maps_.find(key);
+  rc = 0;
+  if (it != maps_.end()) return &it->second->m;
+  Slot* s = new Slot();
+  rc = encode_wide_rows_tmap(&s->m, base, CT, H, Wtot, kc);
+  if (rc != 0) {
+    delete s;
+    return nullptr;
+  }
+  maps_[key] = s;
+  return &s->m;
+}
+
+// Row-streaming kernel on wide tensors; returns -100 when the conv is not eligible.
+static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, int H, int W, ChunkView out,
+                         int out_nchunks, const Epilogue& ep, int num_sms, cudaStream_t stream) {
+  static const int rows_mode = getenv("INNFER_ROWS") ? atoi(getenv("INNFER_ROWS")) : 1;
+  if (!rows_mode || !in.wide() || !out.wide() || L.d_wrows == nullptr || L.up != 1 || ep.res1.base || ep.res2.base ||
+      ep.compact4 || out_nchunks * 8 != L.Cout || in.pitch != out.pitch || in.Wtot != out.Wtot)
+    return -100;
+  if (L.Cout == 64 && !(rows_mode & 2)) return -100;
+  const int nch = L.Cin_pad / 8;
+  int nsub = (nch + 15) / 16;
+  while (nsub <= nch && (nch % nsub != 0 || ((nch / nsub) & 1))) ++nsub;
+  if (nsub > nch) return -100;
+  const int kc = nch / nsub;
+  const int wbytes = conv_rows_weight_bytes(nch, L.Cout);
+  int S = (232448 - 1024 - wbytes) / conv_rows_stage_bytes(kc);
+  if (S < 3) return -100;
+  if (S > 8) S = 8;
+  ConvRowsParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.H = H;
+  p.Wtot = in.Wtot;
+  p.nimg = B;
+  p.pitch = in.pitch;
+  p.Wimg = W;
+  p.magic = (uint32_t)((1ull << 32) / (unsigned)in.pitch) + 1u;
+  p.in_chunk0 = in.chunk0;
+  p.nch = nch;
+  p.kc = kc;
+  p.nsub = nsub;
+  p.nstrips = (in.Wtot + 15 + 127) / 128;
+  p.stages = S;
+  p.out = out.base;
+  p.out_cs = (long long)H * out.Wtot * 8;
+  p.out_ys = out.Wtot * 8;
+  p.out_chunk0 = out.chunk0;
+  p.w = L.d_wrows;
+  p.bias = L.d_bias;
+  p.lrelu = ep.lrelu ? 1 : 0;
+  p.slope = ep.slope;
+  static const int dbg = getenv("INNFER_ROWS_DBG") ? atoi(getenv("INNFER_ROWS_DBG")) : 0;
+  p.debug = dbg;
+  int rc = 0;
+  const CUtensorMap* tm = cache.get_rows(in.base, in.CT, H, in.Wtot, kc, rc);
+  if (!tm) return rc ? rc : -5;
+  return launch_conv_rows(tm, p, L.Cout, num_sms, stream);
 }
 
 int choose_J(int W, int N) {
@@ -260,7 +345,11 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
   const int N = L.N;
   static const int dx_mode = getenv("INNFER_DX") ? atoi(getenv("INNFER_DX")) : 1;
   static const int dx_j = getenv("INNFER_DX_J") ? atoi(getenv("INNFER_DX_J")) : 4;
-  if (dx_mode && L.d_wdx != nullptr && ep.res1.base == nullptr && ep.res2.base == nullptr && out_nchunks == 4 &&
+  {
+    const int rr = conv_rows_run(L, cache, in, B, H, W, out, out_nchunks, ep, num_sms, stream);
+    if (rr != -100) return rr;
+  }
+  if (dx_mode && !in.wide() && !out.wide() && L.d_wdx != nullptr && ep.res1.base == nullptr && ep.res2.base == nullptr && out_nchunks == 4 &&
       L.Cin_pad % 32 == 0) {
     // dx-taps-as-N kernel: tiles of 16 x (8J-2) outputs
     const int J = dx_j < 2 ? 2 : (dx_j > 4 ? 4 : dx_j);  // merged TMA map: 8J*8 <= 256 elements
@@ -297,15 +386,50 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
     if (!tm) return rc ? rc : -5;
     return launch_conv_dx(tm, p, num_sms, stream);
   }
-  const int J = choose_J(W, N);
-  p.B = B;
+  // source geometry as the kernel tiles it: B images of width W, or one wide image
+  const int srcB = in.wide() ? 1 : B;
+  const int srcW = in.wide() ? in.Wtot : W;
+  const int J = choose_J(srcW, N);
+  p.B = srcB;
   p.H = H;
-  p.W = W;
+  p.W = srcW;
   p.in_chunk0 = in.chunk0;
   p.kslabs = L.Cin_pad / 16;
   p.J = J;
   p.bands = (H + kPatchRows - 1) / kPatchRows;
-  p.cps = (W + 8 * J - 1) / (8 * J);
+  p.cps = (srcW + 8 * J - 1) / (8 * J);
+  if (in.wide()) {
+    p.sep_pitch = in.pitch;
+    p.sep_w = W;
+    p.sep_nimg = B;
+    p.sep_magic = (uint32_t)((1ull << 32) / (unsigned)in.pitch) + 1u;
+    p.out_zero_sep = out.wide() ? 1 : 0;
+    if (out.wide() && (out.pitch != in.pitch * L.up || out.Wtot != in.Wtot * L.up)) return -6;
+  }
+  {
+    const long long Ho = (long long)H * L.up, Wo = (long long)W * L.up;
+    auto strides = [&](const ChunkView& v, long long& bs, long long& cs, int& ys) {
+      if (v.wide()) {
+        bs = (long long)v.pitch * 8;
+        cs = Ho * v.Wtot * 8;
+        ys = v.Wtot * 8;
+      } else {
+        bs = (long long)v.CT * Ho * Wo * 8;
+        cs = Ho * Wo * 8;
+        ys = (int)(Wo * 8);
+      }
+    };
+    strides(out, p.out_bs, p.out_cs, p.out_ys);
+    p.out_px = 8;
+    if (ep.compact4) {
+      p.out_bs = Ho * Wo * 4;
+      p.out_cs = 0;
+      p.out_ys = (int)(Wo * 4);
+      p.out_px = 4;
+    }
+    if (ep.res1.base) strides(ep.res1, p.res1_bs, p.res1_cs, p.res1_ys);
+    if (ep.res2.base) strides(ep.res2, p.res2_bs, p.res2_cs, p.res2_ys);
+  }
   p.nphase = L.nphase;
   p.up = L.up;
   p.Hout = H * L.up;
@@ -346,10 +470,11 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
       p.tap_hx[i][t] = L.tap_hx[i][t];
     }
   }
-  static const int dbg = getenv("INNFER_DEBUG") ? atoi(getenv("INNFER_DEBUG")) : 0;
+  // bit 6 (default on): weight-stationary MMA order for the 9-tap N=64 convs
+  static const int dbg = getenv("INNFER_DEBUG") ? atoi(getenv("INNFER_DEBUG")) : 64;
   p.debug = dbg;
   int rc = 0;
-  const CUtensorMap* tm = cache.get(in.base, B, in.CT, H, W, 8 * J + 2, rc);
+  const CUtensorMap* tm = cache.get(in.base, srcB, in.CT, H, srcW, 8 * J + 2, rc);
   if (!tm) return rc ? rc : -5;
   return launch_conv_tc(tm, p, N, num_sms, stream);
 }

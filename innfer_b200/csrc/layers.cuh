@@ -21,6 +21,12 @@ struct ChunkView {
   __half* base = nullptr;  // buffer start
   int CT = 0;              // chunks per tile in the buffer
   int chunk0 = 0;          // first chunk of the view
+  // wide layout (fp16 engine path): the buffer is ONE image [CT][H][Wtot][8] in which tile image b
+  // occupies columns [b*pitch, b*pitch + W) and all other columns (separators, padding of Wtot to a
+  // multiple of 16) hold zeros.  pitch == 0: tiled layout [B][CT][H][W][8].
+  int pitch = 0;
+  int Wtot = 0;
+  bool wide() const { return pitch != 0; }
 };
 
 struct ConvLayer {
@@ -38,6 +44,7 @@ struct ConvLayer {
   int max_taps = 0;
   __half* d_w = nullptr;   // device, packed [phase][kslab][tap][2][N][8]
   __half* d_wdx = nullptr; // device, dx-as-N packing [kslab][dy][2][dx*32+co][8] (Cout == 32, up == 1 only)
+  __half* d_wrows = nullptr; // device, row-streaming packing [kslab][dx][2][dy*Cout+co][8] (Cout 32/64, plain 3x3)
   float* d_bias = nullptr; // device, [nphase][N]
   size_t w_bytes = 0;
   // fp32 copies (OIHW + bias) kept on the device for the fp32-mode direct kernel
@@ -69,6 +76,8 @@ class TmapCache {
  public:
   // box_w > 0: 5-D map with a box of box_w pixels; box_w < 0: merged 4-D map with -box_w pixels per row
   const CUtensorMap* get(const void* base, int B, int CT, int H, int W, int box_w, int& rc);
+  // wide-layout row-segment map of the row-streaming kernel (box of `kc` chunks)
+  const CUtensorMap* get_rows(const void* base, int CT, int H, int Wtot, int kc, int& rc);
   void clear() { maps_.clear(); }
 
  private:

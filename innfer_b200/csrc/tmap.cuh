@@ -14,4 +14,8 @@ int encode_act_tmap(CUtensorMap* out, const void* base, int B, int CT, int H, in
 // bottleneck).  box_w * 8 must be <= 256 elements.  Box = (box_w*8, 18, box_chunks, 1), OOB -> zero.
 int encode_act_tmap_merged(CUtensorMap* out, const void* base, int B, int CT, int H, int W, int box_w,
                            int box_chunks);
+// Wide layout [CT][H][Wtot][8] (Wtot a multiple of 16) seen as [CT][H][Wtot/16][128]: the box is one
+// row segment of 9 groups of 16 pixels (144 pixels, 256-byte inner rows) of `box_chunks` chunks;
+// groups outside [0, Wtot/16) are zero-filled.  Used by the row-streaming kernel (conv_rows.cu).
+int encode_wide_rows_tmap(CUtensorMap* out, const void* base, int CT, int H, int Wtot, int box_chunks);
 }  // namespace innfer
