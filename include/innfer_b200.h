@@ -147,6 +147,13 @@ int innfer_ipc_close(void* device_ptr);
  * caching allocator) */
 int innfer_device_alloc(int device, uint64_t bytes, void** ptr);
 int innfer_device_free(void* ptr);
+
+/* Debugging aid (not part of the reference-facing surface): device buffer of 3072 int64 that receives
+ * clock64 samples of CTA 0 of the row-streaming conv kernel selected by INNFER_TRACE_NCH; NULL disables. */
+int innfer_debug_set_trace(void* device_buf);
+/* Measurement aid: `iters` back-to-back launches (after `warm` untimed ones) of one 3x3 conv on a wide batch
+ * of B random H x W images; *ms_out = device time of the timed launches. */
+int innfer_debug_conv_loop(int Cin, int Cout, int B, int H, int W, int with_res, int warm, int iters, float* ms_out);
 /* host -> device copy into such an allocation (synchronises `stream`) */
 int innfer_device_upload(void* device_dst, const void* host_src, uint64_t bytes, void* stream);
 

@@ -63,6 +63,8 @@ _PROTOS = {
     "innfer_ipc_close": (_i, [_vp]),
     "innfer_device_alloc": (_i, [_i, ctypes.c_uint64, ctypes.POINTER(_vp)]),
     "innfer_device_free": (_i, [_vp]),
+    "innfer_debug_set_trace": (_i, [_vp]),
+    "innfer_debug_conv_loop": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_float)]),
     "innfer_device_upload": (_i, [_vp, _vp, ctypes.c_uint64, _vp]),
     "innfer_tiles_plan": (_i, [_i, _i, _i, _f, ctypes.POINTER(Tile), _i, ctypes.POINTER(_i),
                                ctypes.POINTER(_i)]),

@@ -19,6 +19,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
 
+if os.environ.get("INNFER_TRACE_BUILD"):  # debugging build: clock64 tracing inside conv_rows (tests/gpu_bringup.py --stage trace)
+    NVCC_FLAGS.append("-DINNFER_ROWS_TRACE")
+
+
 def _nvcc():
     exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(exe):

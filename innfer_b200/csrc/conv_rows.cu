@@ -24,11 +24,19 @@
 #include "conv_rows.cuh"
 #include "ptx.cuh"
 
+// clock64 tracing of CTA 0 (tests/gpu_bringup.py --stage trace) is compiled in only with
+// -DINNFER_ROWS_TRACE: the samples themselves cost ~50 cycles each on the issuing thread.
+#ifdef INNFER_ROWS_TRACE
+#define ROWS_TRACE(...) __VA_ARGS__
+#else
+#define ROWS_TRACE(...)
+#endif
+
 namespace innfer {
 
 namespace {
 
-constexpr int kRowsThreads = 320;  // producer, issuer, 8 epilogue warps (2 per TMEM lane quarter)
+constexpr int kRowsThreads = 352;  // producer, issuer, 8 epilogue warps (2 per TMEM lane quarter), scout
 constexpr int kRowPx = 144;        // pixels per staged row segment: 9 groups of 16 (strip of 128 + halo)
 
 struct Piece {
@@ -58,7 +66,7 @@ struct PieceIter {
   }
 };
 
-template <int COUT>
+template <int COUT, int KSLABS>
 __global__ void __launch_bounds__(kRowsThreads, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvRowsParams p) {
   constexpr int N = 3 * COUT;                 // dy-major: column dy*COUT + co
@@ -67,6 +75,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  ROWS_TRACE(if (p.trace && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[3072 + blockIdx.x * 8 + 0] = (long long)gt;
+    p.trace[3072 + blockIdx.x * 8 + 1] = clock64();
+  });
 
   const int S = p.stages;
   const uint32_t stage_bytes = (uint32_t)p.kc * kRowPx * 16;
@@ -78,6 +92,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   uint64_t* slot_bar = tfull_bar + NSLOT;         // accumulator slot is drained
   uint64_t* wfull_bar = slot_bar + NSLOT;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
+  volatile uint32_t* ready_cnt = tmem_slot + 1;    // stages whose barriers the scout warp has seen complete
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
 
   if (threadIdx.x == 0) {
@@ -91,6 +106,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       mbar_init(smem_u32(&slot_bar[i]), 8);
     }
     mbar_init(smem_u32(wfull_bar), 1);
+    *ready_cnt = 0u;
     fence_mbar_init();
   }
   if (threadIdx.x < COUT) s_bias[threadIdx.x] = p.bias[threadIdx.x];
@@ -117,6 +133,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       }
       int s = 0;
       uint32_t ph = 0;
+      ROWS_TRACE(int tcount = 0);
       PieceIter it;
       it.init(p);
       Piece pc;
@@ -128,6 +145,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             const uint32_t fb = smem_u32(&full_bar[s]);
             mbar_expect_tx(fb, stage_bytes);
             tma_load_4d(ring_base + (uint32_t)s * stage_bytes, &tmap_in, fb, 0, gx, r, p.in_chunk0 + sub * p.kc);
+            ROWS_TRACE(if (p.trace && blockIdx.x == 0 && tcount < 256) p.trace[1024 + tcount++] = clock64());
             if (++s == S) {
               s = 0;
               ph ^= 1u;
@@ -138,60 +156,135 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
+    // Everything on this warp's path is a potential tensor-pipe bubble (the pipe buffers very few
+    // MMAs and these are 48..96-cycle MMAs), so the loop is specialised on the number of K slabs per
+    // stage, keeps all of its state as running values (no multiplies, no 64-bit counters) and never
+    // touches an mbarrier: an mbarrier wait on this thread costs 170-260 cycles even when the phase
+    // completed long ago (measured with clock64: the SYNCS instruction queues behind the MMAs already
+    // handed to the pipe).  The scout warp does the waiting and publishes the number of ready stages
+    // in shared memory; this thread re-reads that word only when it runs out of known-ready stages,
+    // in the middle of a stage, while the first half of the stage's MMAs is still queued.
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_f16(N);
     constexpr uint32_t a_lbo = kRowPx;                   // 16-byte units between the two K chunks
-    const uint32_t a_hi = 8u | (1u << 14);               // SBO = 128 B (8 consecutive pixels)
-    const uint32_t b_hi = 8u | (1u << 14);
-    const uint32_t b_lo0 = ((w_base & 0x3FFFFu) >> 4) | ((uint32_t)N << 16);
+    constexpr uint32_t a_hi = 8u | (1u << 14);           // SBO = 128 B (8 consecutive pixels)
+    constexpr uint32_t b_hi = 8u | (1u << 14);
     constexpr uint32_t b_blk = 2u * N;                   // 16-byte units per (slab, dx) weight block
-    const int kslabs = p.kc >> 1;                        // K=16 slabs per sub-stage
-    int s = 0;
-    uint32_t ph = 0;
-    int slot = 0;
-    uint32_t use = 0;
+    constexpr uint32_t b_sub_step = (uint32_t)KSLABS * 3u * b_blk;
+    constexpr int KH = KSLABS > 1 ? KSLABS / 2 : 1;
+    const uint32_t b_lo0 = ((w_base & 0x3FFFFu) >> 4) | ((uint32_t)N << 16);
+    const uint32_t a_step = stage_bytes >> 4;
+    const uint32_t a_first = ((ring_base & 0x3FFFFu) >> 4) | (a_lbo << 16);
+    const uint32_t a_last = a_first + (uint32_t)(S - 1) * a_step;
+    const uint32_t ebar0 = smem_u32(&empty_bar[0]);
+    const uint32_t tbar0 = smem_u32(&tfull_bar[0]);
+    const uint32_t acc_last = tmem_base + (uint32_t)((NSLOT - 1) * N);
+    const uint32_t ready_addr = smem_u32((const void*)ready_cnt);
+    uint32_t nstage = 0;
+    {
+      PieceIter it;
+      it.init(p);
+      Piece pc;
+      while (it.next(pc)) nstage += (uint32_t)(pc.r1 - pc.r0 + 1);
+      nstage *= (uint32_t)p.nsub;
+    }
+    const int nsub = p.nsub;
+    uint32_t ready = 0;
+    uint32_t a_lo = a_first, ebar = ebar0, tbar = tbar0, acc = tmem_base, b_lo = b_lo0;
+    int sub = 0;
     mbar_wait(smem_u32(wfull_bar), 0u);
-    PieceIter it;
-    it.init(p);
-    Piece pc;
-    while (it.next(pc)) {
-      for (int r = pc.r0; r <= pc.r1; ++r) {
-        mbar_wait(smem_u32(&slot_bar[slot]), (use & 1u) ^ 1u);   // drained NSLOT rows ago
+    ROWS_TRACE(if (p.trace && lane == 0) p.trace[3072 + blockIdx.x * 8 + 2] = clock64());
+    for (uint32_t i = 0; i < nstage; ++i) {
+      if (ready <= i) {   // only at the very start, or when the producer is behind
+        uint32_t spins = 0;
+        do {
+          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(ready) : "r"(ready_addr) : "memory");
+          if (++spins > (1u << 26)) __trap();
+        } while (ready <= i);
         tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)(slot * N);
+      }
+      if (leader) {
+        // TMEM lane l is output column 128m - 15 + l; its tap dx reads pixel l + dx of the staged
+        // segment, which starts at column 128m - 16
+#pragma unroll
+        for (int kk = 0; kk < KH; ++kk) {
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+            umma_f16_ss(acc, make_desc64(a_lo + (uint32_t)(kk * 2 * a_lbo + dx), a_hi),
+                        make_desc64(b_lo + (uint32_t)((kk * 3 + dx) * b_blk), b_hi), idesc,
+                        (kk | dx) == 0 ? (sub != 0 ? 1u : 0u) : 1u);
+        }
+      }
+      if (ready <= i + 1 && i + 1 < nstage) {   // look ahead while the pipe is busy with the first half
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(ready) : "r"(ready_addr) : "memory");
+        tc_fence_after();
+      }
+      const bool row_end = sub == nsub - 1;
+      if (leader) {
+#pragma unroll
+        for (int kk = KH; kk < KSLABS; ++kk) {
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+            umma_f16_ss(acc, make_desc64(a_lo + (uint32_t)(kk * 2 * a_lbo + dx), a_hi),
+                        make_desc64(b_lo + (uint32_t)((kk * 3 + dx) * b_blk), b_hi), idesc, 1u);
+        }
+        umma_commit(ebar);
+        if (row_end) umma_commit(tbar);
+      }
+      __syncwarp();
+      if (a_lo == a_last) {
+        a_lo = a_first;
+        ebar = ebar0;
+      } else {
+        a_lo += a_step;
+        ebar += 8u;
+      }
+      if (row_end) {
+        sub = 0;
+        b_lo = b_lo0;
+        if (acc == acc_last) {
+          acc = tmem_base;
+          tbar = tbar0;
+        } else {
+          acc += (uint32_t)N;
+          tbar += 8u;
+        }
+      } else {
+        ++sub;
+        b_lo += b_sub_step;
+      }
+    }
+    ROWS_TRACE(if (p.trace && lane == 0) p.trace[3072 + blockIdx.x * 8 + 3] = clock64());
+    ROWS_TRACE(if (p.trace && lane == 0) p.trace[3072 + blockIdx.x * 8 + 5] = nstage);
+  } else if (warp == 10) {
+    // ------------------------------------------------------------ scout: waits for the issuer
+    if (lane == 0) {
+      long long nrows = 0;
+      {
+        PieceIter it;
+        it.init(p);
+        Piece pc;
+        while (it.next(pc)) nrows += pc.r1 - pc.r0 + 1;
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      int slot = 0;
+      uint32_t use = 0;
+      uint32_t done = 0;
+      for (long long r = 0; r < nrows; ++r) {
+        mbar_wait(smem_u32(&slot_bar[slot]), (use & 1u) ^ 1u);
+        if (++slot == NSLOT) {
+          slot = 0;
+          ++use;
+        }
         for (int sub = 0; sub < p.nsub; ++sub) {
           mbar_wait(smem_u32(&full_bar[s]), ph);
-          tc_fence_after();
-          const uint32_t sa = ring_base + (uint32_t)s * stage_bytes;
-          const uint32_t a_lo = ((sa & 0x3FFFFu) >> 4) | (a_lbo << 16);
-          const uint32_t b_lo = b_lo0 + (uint32_t)(sub * kslabs) * 3u * b_blk;
-          if (leader) {
-            // TMEM lane l is output column 128m - 15 + l; its tap dx reads pixel l + dx of the staged
-            // segment, which starts at column 128m - 16
-            umma_f16_ss(acc, make_desc64(a_lo, a_hi), make_desc64(b_lo, b_hi), idesc, sub != 0 ? 1u : 0u);
-            umma_f16_ss(acc, make_desc64(a_lo + 1u, a_hi), make_desc64(b_lo + b_blk, b_hi), idesc, 1u);
-            umma_f16_ss(acc, make_desc64(a_lo + 2u, a_hi), make_desc64(b_lo + 2u * b_blk, b_hi), idesc, 1u);
-#pragma unroll 2
-            for (int kk = 1; kk < kslabs; ++kk) {
-              const uint32_t ak = a_lo + (uint32_t)kk * 2u * a_lbo;
-              const uint32_t bk = b_lo + (uint32_t)kk * 3u * b_blk;
-              umma_f16_ss(acc, make_desc64(ak, a_hi), make_desc64(bk, b_hi), idesc, 1u);
-              umma_f16_ss(acc, make_desc64(ak + 1u, a_hi), make_desc64(bk + b_blk, b_hi), idesc, 1u);
-              umma_f16_ss(acc, make_desc64(ak + 2u, a_hi), make_desc64(bk + 2u * b_blk, b_hi), idesc, 1u);
-            }
-            umma_commit(smem_u32(&empty_bar[s]));
-          }
-          __syncwarp();
           if (++s == S) {
             s = 0;
             ph ^= 1u;
           }
-        }
-        if (leader) umma_commit(smem_u32(&tfull_bar[slot]));
-        __syncwarp();
-        if (++slot == NSLOT) {
-          slot = 0;
-          ++use;
+          ++done;
+          asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32((const void*)ready_cnt)), "r"(done) : "memory");
         }
       }
     }
@@ -204,6 +297,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     const bool nostore = (p.debug & 128) != 0;
     int slot = 0;
     uint32_t use = 0;
+    ROWS_TRACE(int ecount = 0);
     PieceIter it;
     it.init(p);
     Piece pc;
@@ -246,13 +340,20 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       for (int r = pc.r0; r <= pc.r1; ++r) {
         mbar_wait(smem_u32(&tfull_bar[slot]), use & 1u);
         tc_fence_after();
+        ROWS_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && ecount < 256) p.trace[2048 + ecount++] = clock64());
         const uint32_t tacc = tmem_base + lane_base + (uint32_t)(slot * N + half * CH);
         uint32_t v0[CH], v1[CH], v2[CH];
 #pragma unroll
+        for (int c = 0; c < CH; ++c) v0[c] = v1[c] = v2[c] = 0u;
+#pragma unroll
         for (int g = 0; g < CH / 16; ++g) {
-          tmem_ld16(tacc + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v0[g * 16]));
-          tmem_ld16(tacc + COUT + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v1[g * 16]));
-          tmem_ld16(tacc + 2 * COUT + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v2[g * 16]));
+          if (!(p.debug & 2)) {   // timing experiments: bit 1 skips all TMEM reads, bit 2 reads one block of three
+            tmem_ld16(tacc + COUT + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v1[g * 16]));
+            if (!(p.debug & 4)) {
+              tmem_ld16(tacc + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v0[g * 16]));
+              tmem_ld16(tacc + 2 * COUT + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v2[g * 16]));
+            }
+          }
         }
         tmem_ld_wait();
         tc_fence_before();
@@ -284,17 +385,34 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
   }
+  ROWS_TRACE(if (p.trace && threadIdx.x == 0) p.trace[3072 + blockIdx.x * 8 + 4] = clock64());
 }
 
-template <int COUT>
+template <int COUT, int KSLABS>
 int launch_rows_impl(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num_sms, cudaStream_t stream) {
   const size_t smem_bytes = conv_rows_weight_bytes(p.nch, COUT) + (size_t)p.stages * conv_rows_stage_bytes(p.kc) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(conv_rows_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  cudaError_t e = cudaFuncSetAttribute(conv_rows_kernel<COUT, KSLABS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_bytes);
   if (e != cudaSuccess) return (int)e;
   const long long T = (long long)p.nstrips * p.H;
   const int grid = T < num_sms ? (int)T : num_sms;
-  conv_rows_kernel<COUT><<<grid, kRowsThreads, smem_bytes, stream>>>(*tmap_in, p);
+  conv_rows_kernel<COUT, KSLABS><<<grid, kRowsThreads, smem_bytes, stream>>>(*tmap_in, p);
   return (int)cudaGetLastError();
+}
+
+template <int COUT>
+int launch_rows_k(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num_sms, cudaStream_t stream) {
+  switch (p.kc / 2) {
+    case 1: return launch_rows_impl<COUT, 1>(tmap_in, p, num_sms, stream);
+    case 2: return launch_rows_impl<COUT, 2>(tmap_in, p, num_sms, stream);
+    case 3: return launch_rows_impl<COUT, 3>(tmap_in, p, num_sms, stream);
+    case 4: return launch_rows_impl<COUT, 4>(tmap_in, p, num_sms, stream);
+    case 5: return launch_rows_impl<COUT, 5>(tmap_in, p, num_sms, stream);
+    case 6: return launch_rows_impl<COUT, 6>(tmap_in, p, num_sms, stream);
+    case 7: return launch_rows_impl<COUT, 7>(tmap_in, p, num_sms, stream);
+    case 8: return launch_rows_impl<COUT, 8>(tmap_in, p, num_sms, stream);
+    default: return (int)cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace
@@ -303,8 +421,8 @@ int conv_rows_stage_bytes(int kc) { return kc * kRowPx * 16; }
 int conv_rows_weight_bytes(int nch, int cout) { return (nch / 2) * 3 * 2 * (3 * cout) * 16; }
 
 int launch_conv_rows(const CUtensorMap* tmap_in, const ConvRowsParams& p, int cout, int num_sms, cudaStream_t stream) {
-  if (cout == 32) return launch_rows_impl<32>(tmap_in, p, num_sms, stream);
-  if (cout == 64) return launch_rows_impl<64>(tmap_in, p, num_sms, stream);
+  if (cout == 32) return launch_rows_k<32>(tmap_in, p, num_sms, stream);
+  if (cout == 64) return launch_rows_k<64>(tmap_in, p, num_sms, stream);
   return (int)cudaErrorInvalidValue;
 }
 

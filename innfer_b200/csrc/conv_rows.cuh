@@ -29,6 +29,7 @@ struct ConvRowsParams {
   int lrelu;
   float slope;
   int debug;
+  long long* trace;      // debugging: clock64 samples of CTA 0 (see tests/gpu_bringup.py --stage trace), or null
 };
 
 int launch_conv_rows(const CUtensorMap* tmap_in, const ConvRowsParams& p, int cout, int num_sms, cudaStream_t stream);

@@ -961,6 +961,73 @@ int innfer_conv3x3(const void* x, int n, int Cin, int hgt, int wid, const float*
   return 0;
 }
 
+// Debugging / measurement aid: `iters` back-to-back launches of ONE 3x3 conv (Cin -> Cout, + LeakyReLU,
+// optional residual) on a wide batch of B images of H x W random pixels, timed with CUDA events after
+// `warm` untimed launches.  Long runs show the kernel's power-limited steady state.
+int innfer_debug_conv_loop(int Cin, int Cout, int B, int H, int W, int with_res, int warm, int iters, float* ms_out) {
+  if (!ms_out) return fail(INNFER_E_INVALID, "null argument");
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, dev));
+  std::vector<float> w((size_t)Cout * Cin * 9), b(Cout);
+  uint32_t rng = 12345u;
+  auto rnd = [&]() { rng = rng * 1664525u + 1013904223u; return ((rng >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+  for (auto& v : w) v = rnd() * 0.1f;
+  for (auto& v : b) v = rnd();
+  ConvLayer L;
+  std::string err;
+  if (conv_layer_build(L, w.data(), b.data(), Cout, Cin, 1, err)) return fail(INNFER_E_CUDA, err);
+  const int ict = L.Cin_pad / 8, oct = (Cout + 7) / 8;
+  const int Wtot = wide_cols(B, W);
+  DevBuf bi, bo, br;
+  TmapCache cache;
+  const size_t ib = (size_t)ict * H * Wtot * 16, ob = (size_t)oct * H * Wtot * 16;
+  if (bi.ensure(ib) || bo.ensure(ob) || br.ensure(ob)) return fail(INNFER_E_NOMEM, "allocation failed");
+  {
+    std::vector<__half> hbuf(ib / 2);
+    for (auto& v : hbuf) v = __float2half_rn(rnd());
+    // separators must be zero
+    for (int c = 0; c < ict; ++c)
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < Wtot; ++x)
+          if (x % wide_pitch(W) >= W || x / wide_pitch(W) >= B)
+            for (int e = 0; e < 8; ++e) hbuf[(((size_t)c * H + y) * Wtot + x) * 8 + e] = __float2half_rn(0.f);
+    CU_TRY(cudaMemcpy(bi.p, hbuf.data(), ib, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(br.p, hbuf.data(), ob < ib ? ob : ib, cudaMemcpyHostToDevice));
+  }
+  Epilogue ep;
+  ep.lrelu = !with_res;
+  ChunkView vi = wview(bi, ict, 0, B, W, 1), vo = wview(bo, oct, 0, B, W, 1);
+  if (with_res) {
+    ep.res1 = wview(br, oct, 0, B, W, 1);
+    ep.alpha1 = 0.2f;
+  }
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  int rc = 0;
+  for (int i = 0; i < warm + iters && !rc; ++i) {
+    if (i == warm) CU_TRY(cudaEventRecord(e0, nullptr));
+    rc = conv_layer_run(L, cache, vi, B, H, W, vo, oct, ep, prop.multiProcessorCount, nullptr);
+  }
+  CU_TRY(cudaEventRecord(e1, nullptr));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (!rc && e == cudaSuccess) cudaEventElapsedTime(ms_out, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  bi.release(); bo.release(); br.release();
+  conv_layer_free(L);
+  if (rc) return fail(INNFER_E_CUDA, "conv launch failed rc=" + std::to_string(rc));
+  if (e != cudaSuccess) return cuda_fail(e, "conv loop");
+  return 0;
+}
+
+int innfer_debug_set_trace(void* device_buf) {
+  innfer::g_rows_trace = reinterpret_cast<long long*>(device_buf);
+  return 0;
+}
+
 int innfer_color_fix(const uint8_t* lr, int h, int w, const uint8_t* sr, int H, int W, uint8_t* out, void* stream) {
   if (!lr || !sr || !out) return fail(INNFER_E_INVALID, "null argument");
   int launches = 0;

@@ -10,6 +10,8 @@
 
 namespace innfer {
 
+long long* g_rows_trace = nullptr;  // device buffer of 3072 int64 (innfer_debug_set_trace), debugging only
+
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cout, int Cin, int up,
@@ -312,6 +314,8 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   p.slope = ep.slope;
   static const int dbg = getenv("INNFER_ROWS_DBG") ? atoi(getenv("INNFER_ROWS_DBG")) : 0;
   p.debug = dbg;
+  static const int trace_nch = getenv("INNFER_TRACE_NCH") ? atoi(getenv("INNFER_TRACE_NCH")) : 0;
+  p.trace = (trace_nch == nch) ? g_rows_trace : nullptr;
   int rc = 0;
   const CUtensorMap* tm = cache.get_rows(in.base, in.CT, H, in.Wtot, kc, rc);
   if (!tm) return rc ? rc : -5;

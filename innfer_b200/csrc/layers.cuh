@@ -85,6 +85,8 @@ class TmapCache {
   std::map<std::tuple<const void*, int, int, int, int, int>, Slot*> maps_;
 };
 
+extern long long* g_rows_trace;
+
 // Pick the number of 8-pixel sub-patches per CTA for an image of width W and accumulator width N.
 int choose_J(int W, int N);
 

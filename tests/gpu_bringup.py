@@ -190,6 +190,86 @@ def stage_prof():
     return True
 
 
+def stage_trace():
+    """clock64 trace of CTA 0 of the rows kernel with INNFER_TRACE_NCH input chunks (default conv1 = 8)."""
+    os.environ.setdefault("INNFER_TRACE_NCH", "8")
+    lib = N.load()
+    buf = torch.zeros(3072 + 148 * 8, dtype=torch.int64, device=dev)
+    lib.innfer_debug_set_trace(ctypes.c_void_p(buf.data_ptr()))
+    stage_prof()
+    lib.innfer_debug_set_trace(None)
+    t = buf.cpu().numpy()
+    c = t[3072:].reshape(148, 8)
+    if c[:, 1].any():
+        g0 = c[:, 0].min()
+        print("per-CTA (cycles): prologue = kernel start -> issue loop, loop, tail = loop end -> exit; start skew from globaltimer (ns)")
+        print("  prologue median %.0f max %.0f | loop median %.0f min %.0f max %.0f | tail median %.0f max %.0f | skew max %d ns | stages min %d max %d"
+              % (np.median(c[:, 2] - c[:, 1]), (c[:, 2] - c[:, 1]).max(), np.median(c[:, 3] - c[:, 2]), (c[:, 3] - c[:, 2]).min(),
+                 (c[:, 3] - c[:, 2]).max(), np.median(c[:, 4] - c[:, 3]), (c[:, 4] - c[:, 3]).max(), (c[:, 0] - g0).max(),
+                 c[:, 5].min(), c[:, 5].max()))
+        per = (c[:, 3] - c[:, 2]) / np.maximum(c[:, 5], 1)
+        print("  cycles per stage by CTA: min %.0f median %.0f max %.0f; total kernel cycles (max over CTAs) %.0f"
+              % (per.min(), np.median(per), per.max(), (c[:, 4] - c[:, 1]).max()))
+    m = t[:1024].reshape(256, 4)
+    prod = t[1024:1280]
+    epi = t[2048:2304]
+    t0 = m[0, 0]
+    print("stage: start  +firsthalf  +wait  +rest | dt_start | TMA issue | epi tfull   (cycles, relative)")
+    for i in list(range(0, 24)) + list(range(100, 124)):
+        if m[i, 0] == 0:
+            break
+        print("%3d: %8d %5d %5d %5d | %5d | %8d | %8d" % (i, m[i, 0] - t0, m[i, 1] - m[i, 0], m[i, 2] - m[i, 1], m[i, 3] - m[i, 2],
+                                                  m[i, 0] - m[i - 1, 0] if i else 0, prod[i] - t0, epi[i] - t0))
+    n = int((m[:, 0] != 0).sum())
+    w = t[2560:3072].reshape(256, 2)
+    print("ready counter seen at stages 100..123:", [int(v) for v in w[100:124, 0]])
+    print("wait block split (median): full-wait %.0f, slot-wait %.0f, fence %.0f" % (
+        np.median(w[1:n - 1, 0] - m[1:n - 1, 1]), np.median(w[1:n - 1, 1] - w[1:n - 1, 0]), np.median(m[1:n - 1, 2] - w[1:n - 1, 1])))
+    d = np.diff(m[:n, 0])
+    print("stages traced %d; cycles per stage: median %.0f mean %.0f; first-half issue median %.0f, wait median %.0f, rest median %.0f"
+          % (n, np.median(d), d.mean(), np.median(m[:n, 1] - m[:n, 0]), np.median(m[:n, 2] - m[:n, 1]), np.median(m[:n, 3] - m[:n, 2])))
+    return True
+
+
+def stage_steady():
+    """Power-limited steady state of single conv kernels: ~3 s of back-to-back launches each, NVML sampled."""
+    import threading
+    import pynvml
+    pynvml.nvmlInit()
+    hnd = pynvml.nvmlDeviceGetHandleByIndex(0)
+    lib = N.load()
+    B = int(os.environ.get("INNFER_STEADY_B", "95"))
+    cases = ((64, 32, 0), (96, 32, 0), (128, 32, 0), (160, 32, 0), (192, 64, 1), (64, 64, 0))
+    for cin, cout, res in cases:
+        flop = 2.0 * 9 * cin * cout * B * 200 * 200
+        ms = ctypes.c_float(0)
+        N.check(lib.innfer_debug_conv_loop(cin, cout, B, 200, 200, res, 20, 50, ctypes.byref(ms)))
+        iters = max(50, int(3000 / (ms.value / 50)))
+        samples, stop = [], threading.Event()
+
+        def sampler():
+            while not stop.is_set():
+                samples.append((pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM),
+                                pynvml.nvmlDeviceGetPowerUsage(hnd) / 1e3,
+                                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hnd)))
+                time.sleep(0.05)
+        th = threading.Thread(target=sampler)
+        th.start()
+        N.check(lib.innfer_debug_conv_loop(cin, cout, B, 200, 200, res, 20, iters, ctypes.byref(ms)))
+        stop.set()
+        th.join()
+        tail = samples[len(samples) // 2:]   # second half of the run: thermally / power settled
+        clk = sorted(v[0] for v in tail)[len(tail) // 2]
+        pw = sorted(v[1] for v in tail)[len(tail) // 2]
+        reasons = 0
+        for v in tail:
+            reasons |= v[2]
+        us = ms.value / iters * 1e3
+        print("steady conv %3d->%2d res=%d B=%d: %.1f us/launch  %.0f TFLOP/s  sm %d MHz  %.0f W  reasons 0x%x  tensor util at that clock %.0f%%"
+              % (cin, cout, res, B, us, flop / us / 1e6, clk, pw, reasons, 100 * flop / us / 1e6 / (148 * 8192 * clk / 1e6)))
+    return True
+
+
 def stage_pix():
     """HBM-bound kernels at benchmark sizes: image->tiles, blend (+uint8), colour fix (for ncu)."""
     lib = N.load()
@@ -283,6 +363,6 @@ if __name__ == "__main__":
     ap.add_argument("--stage", required=True)
     a = ap.parse_args()
     t0 = time.time()
-    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
+    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
     print("STAGE %s %s (%.1fs)" % (a.stage, "OK" if ok else "FAILED", time.time() - t0))
     sys.exit(0 if ok else 1)
