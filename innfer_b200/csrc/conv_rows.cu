@@ -2,7 +2,9 @@
 // into the N dimension of the MMA and recombined by the epilogue thread that owns the pixel column.
 //
 // Replaces (fp16 engine path) conv1..conv4 of ResidualDenseBlock_5C (RRDBNet_arch.py:152-165:
-// Conv2d(k=3,p=1) + LeakyReLU(0.2), Cout = 32) and, with COUT = 64, the 64->64 convs of the tail.
+// Conv2d(k=3,p=1) + LeakyReLU(0.2), Cout = 32), incl. the ESRGAN+ residual adds and, for nf = 32 nets,
+// conv5 with its "*0.2 + x" epilogues.  (COUT = 64, N = 192 works but was measured slower than the
+// 9-tap weight-stationary kernel, see layers.cu.)
 //
 // Wide layout: the B tile images of a batch stand side by side in one image [chunk][H][Wtot][8],
 // image b in columns [b*pitch, b*pitch + Wimg), the `pitch - Wimg` separator columns hold zeros (they
@@ -36,7 +38,10 @@ namespace innfer {
 
 namespace {
 
-constexpr int kRowsThreads = 352;  // producer, issuer, 8 epilogue warps (2 per TMEM lane quarter), scout
+// warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue (two per TMEM lane quarter, each half of the
+// output channels), 10 = scout.  352 threads leave the epilogue threads 184 registers (COUT = 64 keeps
+// 3 x 32 running sums per thread).
+__host__ __device__ constexpr int rows_threads(int) { return 352; }
 constexpr int kRowPx = 144;        // pixels per staged row segment: 9 groups of 16 (strip of 128 + halo)
 
 struct Piece {
@@ -67,11 +72,12 @@ struct PieceIter {
 };
 
 template <int COUT, int KSLABS>
-__global__ void __launch_bounds__(kRowsThreads, 1)
+__global__ void __launch_bounds__(rows_threads(COUT), 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvRowsParams p) {
   constexpr int N = 3 * COUT;                 // dy-major: column dy*COUT + co
   constexpr int NSLOT = 512 / N;              // 5 (COUT=32) or 2 (COUT=64)
-  constexpr int CH = COUT / 2;                // channels per epilogue thread
+  constexpr int CH = COUT / 2;                // channels per epilogue thread (two warps per lane quarter)
+  constexpr int SCOUT_WARP = 10;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -256,7 +262,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     }
     ROWS_TRACE(if (p.trace && lane == 0) p.trace[3072 + blockIdx.x * 8 + 3] = clock64());
     ROWS_TRACE(if (p.trace && lane == 0) p.trace[3072 + blockIdx.x * 8 + 5] = nstage);
-  } else if (warp == 10) {
+  } else if (warp == SCOUT_WARP) {
     // ------------------------------------------------------------ scout: waits for the issuer
     if (lane == 0) {
       long long nrows = 0;
@@ -291,9 +297,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   } else {
     // ------------------------------------------------------------ epilogue warps
     const int q4 = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int grp = (warp - 2) >> 2;                     // which half of the output channels
     const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
-    const float* bias = s_bias + half * CH;
+    const float* bias = s_bias + grp * CH;
     const bool nostore = (p.debug & 128) != 0;
     int slot = 0;
     uint32_t use = 0;
@@ -307,23 +313,60 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       const uint32_t b = __umulhi((uint32_t)(xw < 0 ? 0 : xw), p.magic);
       const int xi = xw - (int)b * p.pitch;
       const bool real = in_range && (int)b < p.nimg && xi < p.Wimg;   // else separator column: zeros
-      __half* const obase = p.out + (size_t)(p.out_chunk0 + half * (CH / 8)) * p.out_cs + (size_t)(xw < 0 ? 0 : xw) * 8;
+      const size_t col = (size_t)(xw < 0 ? 0 : xw) * 8;
+      __half* const obase = p.out + (size_t)(p.out_chunk0 + grp * (CH / 8)) * p.out_cs + col;
+      const bool noside = (p.debug & 256) != 0;   // timing experiments only
+      const __half* const r1base = (p.res1 && !noside) ? p.res1 + (size_t)(p.res1_chunk0 + grp * (CH / 8)) * p.out_cs + col : nullptr;
+      const __half* const r2base = (p.res2 && !noside) ? p.res2 + (size_t)(p.res2_chunk0 + grp * (CH / 8)) * p.out_cs + col : nullptr;
       float accA[CH], accB[CH];
 #pragma unroll
       for (int c = 0; c < CH; ++c) accA[c] = accB[c] = 0.f;
+      // residual inputs of one output row: prefetched into L2 before the
+      // accumulator wait, loaded chunk by chunk in store_row (keeps the live register set small)
+      auto load_side = [&](int y) {
+        if (!real || y < pc.ya) return;
+        const size_t ro = (size_t)y * p.out_ys;
+#pragma unroll
+        for (int ch = 0; ch < CH / 8; ++ch) {
+          if (r1base) asm volatile("prefetch.global.L2 [%0];" ::"l"(r1base + ro + (size_t)ch * p.out_cs));
+          if (r2base) asm volatile("prefetch.global.L2 [%0];" ::"l"(r2base + ro + (size_t)ch * p.out_cs));
+        }
+      };
       auto store_row = [&](int y, const float (&o)[CH]) {
         if (!in_range || nostore) return;
-        __half* op = obase + (size_t)y * p.out_ys;
+        const size_t ro = (size_t)y * p.out_ys;
+        __half* op = obase + ro;
 #pragma unroll
         for (int ch = 0; ch < CH / 8; ++ch) {
           uint4 pk = make_uint4(0u, 0u, 0u, 0u);
           if (real) {
+            uint4 s1, s2;
+            if (r1base) s1 = *reinterpret_cast<const uint4*>(r1base + ro + (size_t)ch * p.out_cs);
+            if (r2base) s2 = *reinterpret_cast<const uint4*>(r2base + ro + (size_t)ch * p.out_cs);
             float f[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float t = o[ch * 8 + e] + bias[ch * 8 + e];
-              if (p.lrelu) t = t > 0.f ? t : t * p.slope;
-              f[e] = t;
+            for (int e = 0; e < 8; ++e) f[e] = o[ch * 8 + e] + bias[ch * 8 + e];
+            if (p.lrelu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * p.slope;
+            }
+            if (r1base) {
+              const __half2* hp = reinterpret_cast<const __half2*>(&s1);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 v = __half22float2(hp[e]);
+                f[2 * e] = f[2 * e] * p.alpha1 + v.x;
+                f[2 * e + 1] = f[2 * e + 1] * p.alpha1 + v.y;
+              }
+            }
+            if (r2base) {
+              const __half2* hp = reinterpret_cast<const __half2*>(&s2);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 v = __half22float2(hp[e]);
+                f[2 * e] = f[2 * e] * p.alpha2 + v.x;
+                f[2 * e + 1] = f[2 * e + 1] * p.alpha2 + v.y;
+              }
             }
             const __half2 h0 = __floats2half2_rn(f[0], f[1]);
             const __half2 h1 = __floats2half2_rn(f[2], f[3]);
@@ -338,24 +381,33 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         }
       };
       for (int r = pc.r0; r <= pc.r1; ++r) {
+        load_side(r - 1);
         mbar_wait(smem_u32(&tfull_bar[slot]), use & 1u);
         tc_fence_after();
         ROWS_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && ecount < 256) p.trace[2048 + ecount++] = clock64());
-        const uint32_t tacc = tmem_base + lane_base + (uint32_t)(slot * N + half * CH);
-        uint32_t v0[CH], v1[CH], v2[CH];
+        const uint32_t tacc = tmem_base + lane_base + (uint32_t)(slot * N + grp * CH);
+        // dependent TMEM reads through ONE 16-register buffer (TMEM read latency is ~12 cycles):
+        // o = accA + Q[2]; accA = accB + Q[1]; accB = Q[0], 16 channels at a time
+        uint32_t v[16];
+        float o[CH];
+        const bool nold = (p.debug & 2) != 0;       // timing experiments only
 #pragma unroll
-        for (int c = 0; c < CH; ++c) v0[c] = v1[c] = v2[c] = 0u;
+        for (int c = 0; c < 16; ++c) v[c] = 0u;
 #pragma unroll
         for (int g = 0; g < CH / 16; ++g) {
-          if (!(p.debug & 2)) {   // timing experiments: bit 1 skips all TMEM reads, bit 2 reads one block of three
-            tmem_ld16(tacc + COUT + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v1[g * 16]));
-            if (!(p.debug & 4)) {
-              tmem_ld16(tacc + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v0[g * 16]));
-              tmem_ld16(tacc + 2 * COUT + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v2[g * 16]));
-            }
-          }
+          if (!nold) tmem_ld16(tacc + 2 * COUT + g * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) o[g * 16 + c] = accA[g * 16 + c] + __uint_as_float(v[c]);
+          if (!nold) tmem_ld16(tacc + COUT + g * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) accA[g * 16 + c] = accB[g * 16 + c] + __uint_as_float(v[c]);
+          if (!nold) tmem_ld16(tacc + g * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) accB[g * 16 + c] = __uint_as_float(v[c]);
         }
-        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&slot_bar[slot]));
@@ -363,19 +415,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           slot = 0;
           ++use;
         }
-        if (r - 1 >= pc.ya) {
-          float o[CH];
-#pragma unroll
-          for (int c = 0; c < CH; ++c) o[c] = accA[c] + __uint_as_float(v2[c]);
-          store_row(r - 1, o);
-        }
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          accA[c] = accB[c] + __uint_as_float(v1[c]);
-          accB[c] = __uint_as_float(v0[c]);
-        }
+        if (r - 1 >= pc.ya) store_row(r - 1, o);
       }
-      if (pc.yb == p.H) store_row(p.H - 1, accA);   // bottom row: the row below is zero padding
+      if (pc.yb == p.H) {   // bottom row: the row below is zero padding
+        load_side(p.H - 1);
+        store_row(p.H - 1, accA);
+      }
     }
   }
 
@@ -396,7 +441,7 @@ int launch_rows_impl(const CUtensorMap* tmap_in, const ConvRowsParams& p, int nu
   if (e != cudaSuccess) return (int)e;
   const long long T = (long long)p.nstrips * p.H;
   const int grid = T < num_sms ? (int)T : num_sms;
-  conv_rows_kernel<COUT, KSLABS><<<grid, kRowsThreads, smem_bytes, stream>>>(*tmap_in, p);
+  conv_rows_kernel<COUT, KSLABS><<<grid, rows_threads(COUT), smem_bytes, stream>>>(*tmap_in, p);
   return (int)cudaGetLastError();
 }
 
@@ -422,7 +467,6 @@ int conv_rows_weight_bytes(int nch, int cout) { return (nch / 2) * 3 * 2 * (3 * 
 
 int launch_conv_rows(const CUtensorMap* tmap_in, const ConvRowsParams& p, int cout, int num_sms, cudaStream_t stream) {
   if (cout == 32) return launch_rows_k<32>(tmap_in, p, num_sms, stream);
-  if (cout == 64) return launch_rows_k<64>(tmap_in, p, num_sms, stream);
   return (int)cudaErrorInvalidValue;
 }
 

@@ -23,6 +23,12 @@ struct ConvRowsParams {
   long long out_cs;        // elements between chunks
   int out_ys;              // elements between rows (Wtot * 8)
   int out_chunk0;
+  // optional residuals, wide tensors of the destination's geometry (same row / chunk strides):
+  //   t = lrelu(acc + bias);  t = t*alpha1 + res1;  t = t*alpha2 + res2
+  const __half* res1;
+  const __half* res2;
+  int res1_chunk0, res2_chunk0;
+  float alpha1, alpha2;
   // weights [slab][dx][2][dy*COUT + co][8] fp16, bias [COUT]
   const __half* w;
   const float* bias;

@@ -277,10 +277,14 @@ const CUtensorMap* TmapCache::get_rows(const void* base, int CT, int H, int Wtot
 static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, int H, int W, ChunkView out,
                          int out_nchunks, const Epilogue& ep, int num_sms, cudaStream_t stream) {
   static const int rows_mode = getenv("INNFER_ROWS") ? atoi(getenv("INNFER_ROWS")) : 1;
-  if (!rows_mode || !in.wide() || !out.wide() || L.d_wrows == nullptr || L.up != 1 || ep.res1.base || ep.res2.base ||
-      ep.compact4 || out_nchunks * 8 != L.Cout || in.pitch != out.pitch || in.Wtot != out.Wtot)
+  if (!rows_mode || !in.wide() || !out.wide() || L.d_wrows == nullptr || L.up != 1 || ep.compact4 ||
+      out_nchunks * 8 != L.Cout || in.pitch != out.pitch || in.Wtot != out.Wtot)
     return -100;
-  if (L.Cout == 64 && !(rows_mode & 2)) return -100;
+  for (const ChunkView* v : {&ep.res1, &ep.res2})
+    if (v->base && (!v->wide() || v->pitch != out.pitch || v->Wtot != out.Wtot)) return -100;
+  // Cout = 64 (N = 192) was measured slower than the 9-tap weight-stationary kernel: N > 128 MMAs run at
+  // ~130 cycles instead of 96 and the 3 x 32 running sums per epilogue thread spill
+  if (L.Cout != 32) return -100;
   const int nch = L.Cin_pad / 8;
   int nsub = (nch + 15) / 16;
   while (nsub <= nch && (nch % nsub != 0 || ((nch / nsub) & 1))) ++nsub;
@@ -312,6 +316,12 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   p.bias = L.d_bias;
   p.lrelu = ep.lrelu ? 1 : 0;
   p.slope = ep.slope;
+  p.res1 = ep.res1.base;
+  p.res1_chunk0 = ep.res1.chunk0;
+  p.alpha1 = ep.alpha1;
+  p.res2 = ep.res2.base;
+  p.res2_chunk0 = ep.res2.chunk0;
+  p.alpha2 = ep.alpha2;
   static const int dbg = getenv("INNFER_ROWS_DBG") ? atoi(getenv("INNFER_ROWS_DBG")) : 0;
   p.debug = dbg;
   static const int trace_nch = getenv("INNFER_TRACE_NCH") ? atoi(getenv("INNFER_TRACE_NCH")) : 0;
