@@ -279,14 +279,22 @@ def main():
         achieved = flop_step * args.steps / (conv_ms * 1e-3) / 1e12
         peak = float(peaks["bf16_tflops_sustained"])
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch_avg")
+        # the same conv sequence seen from the HBM side: conv1..conv4 of every dense block (row-streaming
+        # kernel, 190-240 FLOP per byte) run at the DRAM roofline when timed alone (profiles/)
+        bytes_step = 190 * PATCH * PATCH * synth.bytes_per_lr_pixel(SCALE, NB, NF)
+        hbm_peak = float(peaks["hbm_gbs"])
+        hbm_achieved = bytes_step * args.steps / (conv_ms * 1e-3) / 1e9
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "conv_dx_kernel + conv_tc_kernel<N> (all %d conv launches of a step)" % (conv_launches // args.steps),
+                "traffic": traffic,
+                "kernel": "conv_rows_kernel<32,K> + conv_tc_kernel<N> (all %d conv launches of a step)" % (conv_launches // args.steps),
                 "flop_per_launch_avg": flop_step * args.steps / conv_launches,
-                "avg_launch_ms": conv_ms / conv_launches, "peak_source": peak_src}
+                "avg_launch_ms": conv_ms / conv_launches, "peak_source": peak_src,
+                "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                        "algorithmic_bytes_per_step": bytes_step}}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         r, dt, threads = cpu_reference_rate(args.ref_tiles)

@@ -71,7 +71,7 @@ struct PieceIter {
   }
 };
 
-template <int COUT, int KSLABS>
+template <int COUT, int KSLABS, bool RES>
 __global__ void __launch_bounds__(rows_threads(COUT), 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvRowsParams p) {
   constexpr int N = 3 * COUT;                 // dy-major: column dy*COUT + co
@@ -316,15 +316,15 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       const size_t col = (size_t)(xw < 0 ? 0 : xw) * 8;
       __half* const obase = p.out + (size_t)(p.out_chunk0 + grp * (CH / 8)) * p.out_cs + col;
       const bool noside = (p.debug & 256) != 0;   // timing experiments only
-      const __half* const r1base = (p.res1 && !noside) ? p.res1 + (size_t)(p.res1_chunk0 + grp * (CH / 8)) * p.out_cs + col : nullptr;
-      const __half* const r2base = (p.res2 && !noside) ? p.res2 + (size_t)(p.res2_chunk0 + grp * (CH / 8)) * p.out_cs + col : nullptr;
+      const __half* const r1base = (RES && p.res1 && !noside) ? p.res1 + (size_t)(p.res1_chunk0 + grp * (CH / 8)) * p.out_cs + col : nullptr;
+      const __half* const r2base = (RES && p.res2 && !noside) ? p.res2 + (size_t)(p.res2_chunk0 + grp * (CH / 8)) * p.out_cs + col : nullptr;
       float accA[CH], accB[CH];
 #pragma unroll
       for (int c = 0; c < CH; ++c) accA[c] = accB[c] = 0.f;
       // residual inputs of one output row: prefetched into L2 before the
       // accumulator wait, loaded chunk by chunk in store_row (keeps the live register set small)
       auto load_side = [&](int y) {
-        if (!real || y < pc.ya) return;
+        if (!RES || !real || y < pc.ya) return;
         const size_t ro = (size_t)y * p.out_ys;
 #pragma unroll
         for (int ch = 0; ch < CH / 8; ++ch) {
@@ -386,28 +386,16 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         tc_fence_after();
         ROWS_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && ecount < 256) p.trace[2048 + ecount++] = clock64());
         const uint32_t tacc = tmem_base + lane_base + (uint32_t)(slot * N + grp * CH);
-        // dependent TMEM reads through ONE 16-register buffer (TMEM read latency is ~12 cycles):
-        // o = accA + Q[2]; accA = accB + Q[1]; accB = Q[0], 16 channels at a time
-        uint32_t v[16];
-        float o[CH];
-        const bool nold = (p.debug & 2) != 0;       // timing experiments only
-#pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = 0u;
+        // all three blocks of this thread's channels are read at once: the slot goes back to the MMA warp
+        // as early as possible, the running sums are updated afterwards
+        uint32_t v0[CH], v1[CH], v2[CH];
 #pragma unroll
         for (int g = 0; g < CH / 16; ++g) {
-          if (!nold) tmem_ld16(tacc + 2 * COUT + g * 16, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 16; ++c) o[g * 16 + c] = accA[g * 16 + c] + __uint_as_float(v[c]);
-          if (!nold) tmem_ld16(tacc + COUT + g * 16, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 16; ++c) accA[g * 16 + c] = accB[g * 16 + c] + __uint_as_float(v[c]);
-          if (!nold) tmem_ld16(tacc + g * 16, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 16; ++c) accB[g * 16 + c] = __uint_as_float(v[c]);
+          tmem_ld16(tacc + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v0[g * 16]));
+          tmem_ld16(tacc + COUT + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v1[g * 16]));
+          tmem_ld16(tacc + 2 * COUT + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v2[g * 16]));
         }
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&slot_bar[slot]));
@@ -415,7 +403,17 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           slot = 0;
           ++use;
         }
-        if (r - 1 >= pc.ya) store_row(r - 1, o);
+        if (r - 1 >= pc.ya) {
+          float o[CH];
+#pragma unroll
+          for (int c = 0; c < CH; ++c) o[c] = accA[c] + __uint_as_float(v2[c]);
+          store_row(r - 1, o);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          accA[c] = accB[c] + __uint_as_float(v1[c]);
+          accB[c] = __uint_as_float(v0[c]);
+        }
       }
       if (pc.yb == p.H) {   // bottom row: the row below is zero padding
         load_side(p.H - 1);
@@ -433,16 +431,23 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   ROWS_TRACE(if (p.trace && threadIdx.x == 0) p.trace[3072 + blockIdx.x * 8 + 4] = clock64());
 }
 
-template <int COUT, int KSLABS>
-int launch_rows_impl(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num_sms, cudaStream_t stream) {
+template <int COUT, int KSLABS, bool RES>
+int launch_rows_res(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num_sms, cudaStream_t stream) {
   const size_t smem_bytes = conv_rows_weight_bytes(p.nch, COUT) + (size_t)p.stages * conv_rows_stage_bytes(p.kc) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(conv_rows_kernel<COUT, KSLABS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(conv_rows_kernel<COUT, KSLABS, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes);
   if (e != cudaSuccess) return (int)e;
   const long long T = (long long)p.nstrips * p.H;
   const int grid = T < num_sms ? (int)T : num_sms;
-  conv_rows_kernel<COUT, KSLABS><<<grid, rows_threads(COUT), smem_bytes, stream>>>(*tmap_in, p);
+  conv_rows_kernel<COUT, KSLABS, RES><<<grid, rows_threads(COUT), smem_bytes, stream>>>(*tmap_in, p);
   return (int)cudaGetLastError();
+}
+
+template <int COUT, int KSLABS>
+int launch_rows_impl(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num_sms, cudaStream_t stream) {
+  // the residual-free variant (conv1..conv4 of the plain net) keeps its epilogue free of the side-input code
+  return (p.res1 || p.res2 || (p.debug & 512)) ? launch_rows_res<COUT, KSLABS, true>(tmap_in, p, num_sms, stream)
+                            : launch_rows_res<COUT, KSLABS, false>(tmap_in, p, num_sms, stream);
 }
 
 template <int COUT>

@@ -92,10 +92,6 @@ struct ConvTcParams {
 // Host-side launcher (conv_tc.cu). Returns cudaError_t as int.
 int launch_conv_tc(const CUtensorMap* tmap_in, const ConvTcParams& p, int N, int num_sms,
                    cudaStream_t stream);
-// dx-taps-as-N variant for Cout == 32 plain 3x3 convs (conv_dx.cu); p.w must be the dx packing.
-int launch_conv_dx(const CUtensorMap* tmap_in, const ConvTcParams& p, int num_sms, cudaStream_t stream);
-int conv_dx_stage_bytes(int J);
-int conv_dx_weight_bytes(int kslabs);
 // Bytes of dynamic smem / stage geometry helpers shared by host and device.
 __host__ __device__ inline int conv_tc_a_bytes(int J) {
   int b = 2 * kHaloRows * (8 * J + 2) * 16;

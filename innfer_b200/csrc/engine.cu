@@ -199,6 +199,12 @@ ChunkView wview(DevBuf& b, int CT, int chunk0, int B, int wid, int up) {
   return v;
 }
 
+// INNFER_WIDE=0 keeps the fp16 path on the tiled layout (9-tap kernel only), for A/B measurements
+bool wide_enabled() {
+  static const int v = getenv("INNFER_WIDE") ? atoi(getenv("INNFER_WIDE")) : 1;
+  return v != 0;
+}
+
 ChunkView view(DevBuf& b, int CT, int chunk0) {
   ChunkView v;
   v.base = reinterpret_cast<__half*>(b.p);
@@ -257,7 +263,13 @@ int forward_tiles_srresnet(innfer_rrdb* h, int B, int hgt, int wid, ChunkView ds
   Epilogue plain, relu;
   relu.lrelu = true;
   relu.slope = 0.f;
-  if ((rc = run_conv(h, h->fea, view(h->in_tiles, h->in_ct(), 0), B, hgt, wid, view(h->feat, nfc, 0), nfc, plain, st))) return rc;
+  const bool wide = h->cfg.fp16 && wide_enabled();
+  int lvl = 1;
+  auto view = [&](DevBuf& b, int CT, int chunk0) {
+    return wide ? wview(b, CT, chunk0, B, wid, lvl) : ::view(b, CT, chunk0);
+  };
+  if (wide) CU_TRY(cudaMemsetAsync(h->feat.p, 0, (size_t)nfc * hgt * wide_cols(B, wid) * 8 * h->esz(), st));
+  if ((rc = run_conv(h, h->fea, ::view(h->in_tiles, h->in_ct(), 0), B, hgt, wid, view(h->feat, nfc, 0), nfc, plain, st))) return rc;
   int X = 0, T = 1, Y = 2;
   ChunkView cur = view(h->feat, nfc, 0);
   for (int b = 0; b < h->cfg.nb; ++b) {
@@ -281,6 +293,7 @@ int forward_tiles_srresnet(innfer_rrdb* h, int B, int hgt, int wid, ChunkView ds
   }
   int ch = hgt, cw = wid, pp = 0;
   for (size_t i = 0; i < h->ups.size(); ++i) {
+    lvl *= h->ups[i].up;
     ChunkView o = view(h->hrbuf[pp], nfc, 0);
     if ((rc = run_conv(h, h->ups[i], cur, B, ch, cw, o, nfc, relu, st))) return rc;
     ch *= h->ups[i].up;
@@ -305,8 +318,7 @@ int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, b
   act.lrelu = true;
   // fp16 mode runs on the wide layout: the batch is one image with the tiles side by side, which lets
   // the row-streaming kernel use full 128-pixel MMA tiles whatever the tile width is
-  static const int wide_env = getenv("INNFER_WIDE") ? atoi(getenv("INNFER_WIDE")) : 1;
-  const bool wide = h->cfg.fp16 && wide_env;
+  const bool wide = h->cfg.fp16 && wide_enabled();
   int lvl = 1;  // resolution of the buffer a view is made for (1 = LR, scale = HR)
   auto view = [&](DevBuf& b, int CT, int chunk0) {
     return wide ? wview(b, CT, chunk0, B, wid, lvl) : ::view(b, CT, chunk0);
@@ -396,26 +408,13 @@ int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, b
   return 0;
 }
 
-// Split ntiles into batches <= max_batch minimising the number of CTA waves of the LR convs.
+// Split ntiles into the fewest batches <= max_batch, evenly sized (the persistent kernels split a batch
+// into equal per-SM ranges, so only the number of launches matters).
 int pick_batch(const innfer_rrdb* h, int ntiles, int p) {
+  (void)p;
   if (ntiles <= 1) return 1;
-  const int J = choose_J(p, 32);
-  const long ctas = (long)((p + 15) / 16) * ((p + 8 * J - 1) / (8 * J));
-  long best_waves = -1;
-  int best = 1;
-  const int hi = h->max_batch < ntiles ? h->max_batch : ntiles;
-  for (int B = hi; B >= (hi + 1) / 2; --B) {
-    long waves = 0;
-    for (int t = 0; t < ntiles; t += B) {
-      const int nb = (ntiles - t) < B ? (ntiles - t) : B;
-      waves += (nb * ctas + h->num_sms - 1) / h->num_sms;
-    }
-    if (best_waves < 0 || waves < best_waves) {
-      best_waves = waves;
-      best = B;
-    }
-  }
-  return best;
+  const int nbatch = (ntiles + h->max_batch - 1) / h->max_batch;
+  return (ntiles + nbatch - 1) / nbatch;
 }
 
 // Tile outputs of the chop path use the compact [tile][P][P][4] fp16 layout when it applies.

@@ -114,21 +114,6 @@ int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cou
               }
     }
   }
-  // dx-as-N packing for the Cout == 32 convs: [kslab][dy][kchunk][dx*32 + co][8]
-  std::vector<__half> packed_dx;
-  if (up == 1 && Cout == 32 && ksize == 3) {
-    packed_dx.resize((size_t)kslabs * 3 * 2 * 96 * 8);
-    size_t o = 0;
-    for (int ks = 0; ks < kslabs; ++ks)
-      for (int dy = 0; dy < 3; ++dy)
-        for (int kc = 0; kc < 2; ++kc)
-          for (int n = 0; n < 96; ++n)
-            for (int e = 0; e < 8; ++e) {
-              const int ci = ks * 16 + kc * 8 + e, dx = n / 32, co = n % 32;
-              const float v = ci < Cin ? w[(((size_t)co * Cin + ci) * 3 + dy) * 3 + dx] : 0.f;
-              packed_dx[o++] = __float2half_rn(v);
-            }
-  }
   // row-streaming packing (conv_rows.cu): [kslab][dx][kchunk][dy*Cout + co][8]
   std::vector<__half> packed_rows;
   if (up == 1 && ksize == 3 && (Cout == 32 || Cout == 64)) {
@@ -162,10 +147,6 @@ int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cou
       (!packed_rows.empty() &&
        ((e = cudaMalloc(&L.d_wrows, packed_rows.size() * sizeof(__half))) != cudaSuccess ||
         (e = cudaMemcpy(L.d_wrows, packed_rows.data(), packed_rows.size() * sizeof(__half), cudaMemcpyHostToDevice)) !=
-            cudaSuccess)) ||
-      (!packed_dx.empty() &&
-       ((e = cudaMalloc(&L.d_wdx, packed_dx.size() * sizeof(__half))) != cudaSuccess ||
-        (e = cudaMemcpy(L.d_wdx, packed_dx.data(), packed_dx.size() * sizeof(__half), cudaMemcpyHostToDevice)) !=
             cudaSuccess))) {
     err = std::string("cuda error while uploading weights: ") + cudaGetErrorString(e);
     return -3;
@@ -233,9 +214,7 @@ void conv_layer_free(ConvLayer& L) {
   if (L.d_w) cudaFree(L.d_w);
   if (L.d_bias) cudaFree(L.d_bias);
   if (L.d_w32) cudaFree(L.d_w32);
-  if (L.d_wdx) cudaFree(L.d_wdx);
   if (L.d_wrows) cudaFree(L.d_wrows);
-  L.d_wdx = nullptr;
   L.d_wrows = nullptr;
   L.d_w = nullptr;
   L.d_bias = nullptr;
@@ -248,8 +227,7 @@ const CUtensorMap* TmapCache::get(const void* base, int B, int CT, int H, int W,
   rc = 0;
   if (it != maps_.end()) return &it->second->m;
   Slot* s = new Slot();
-  rc = box_w > 0 ? encode_act_tmap(&s->m, base, B, CT, H, W, box_w)
-                 : encode_act_tmap_merged(&s->m, base, B, CT, H, W, -box_w, 4);
+  rc = encode_act_tmap(&s->m, base, B, CT, H, W, box_w);
   if (rc != 0) {
     delete s;
     return nullptr;
@@ -357,48 +335,9 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
   ConvTcParams p;
   std::memset(&p, 0, sizeof(p));
   const int N = L.N;
-  static const int dx_mode = getenv("INNFER_DX") ? atoi(getenv("INNFER_DX")) : 1;
-  static const int dx_j = getenv("INNFER_DX_J") ? atoi(getenv("INNFER_DX_J")) : 4;
   {
     const int rr = conv_rows_run(L, cache, in, B, H, W, out, out_nchunks, ep, num_sms, stream);
     if (rr != -100) return rr;
-  }
-  if (dx_mode && !in.wide() && !out.wide() && L.d_wdx != nullptr && ep.res1.base == nullptr && ep.res2.base == nullptr && out_nchunks == 4 &&
-      L.Cin_pad % 32 == 0) {
-    // dx-taps-as-N kernel: tiles of 16 x (8J-2) outputs
-    const int J = dx_j < 2 ? 2 : (dx_j > 4 ? 4 : dx_j);  // merged TMA map: 8J*8 <= 256 elements
-    const int OW = 8 * J - 2;
-    p.B = B;
-    p.H = H;
-    p.W = W;
-    p.in_chunk0 = in.chunk0;
-    p.kslabs = L.Cin_pad / 32;  // pipeline stages of 32 channels
-    p.J = J;
-    p.bands = (H + kPatchRows - 1) / kPatchRows;
-    p.cps = (W + OW - 1) / OW;
-    p.nphase = 1;
-    p.up = 1;
-    p.Hout = H;
-    p.Wout = W;
-    static const int dx_res = getenv("INNFER_DX_RES") ? atoi(getenv("INNFER_DX_RES")) : 1;
-    int S = dx_res ? (232448 - 1024 - conv_dx_weight_bytes(p.kslabs)) / conv_dx_stage_bytes(J)
-                   : (232448 - 1024) / (conv_dx_stage_bytes(J) + conv_dx_weight_bytes(1));
-    if (S < 2) return -4;
-    p.stages = S > 8 ? 8 : S;
-    p.out = out.base;
-    p.out_CT = out.CT;
-    p.out_chunk0 = out.chunk0;
-    p.out_nchunks = out_nchunks;
-    p.w = L.d_wdx;
-    p.bias = L.d_bias;
-    p.lrelu = ep.lrelu ? 1 : 0;
-    p.slope = ep.slope;
-    int rc = 0;
-    const CUtensorMap* tm = cache.get(in.base, B, in.CT, H, W, -8 * J, rc);
-    static const int dx_dbg = getenv("INNFER_DX_DBG") ? atoi(getenv("INNFER_DX_DBG")) : 0;
-    p.debug = (J <= 4 ? 4 : 0) | (dx_res == 1 ? 8 : 0) | (dx_res == 2 ? 24 : 0) | dx_dbg;  // bit 2: merged 4-D tensor map
-    if (!tm) return rc ? rc : -5;
-    return launch_conv_dx(tm, p, num_sms, stream);
   }
   // source geometry as the kernel tiles it: B images of width W, or one wide image
   const int srcB = in.wide() ? 1 : B;

@@ -43,7 +43,6 @@ struct ConvLayer {
   uint8_t tap_hx[kMaxPhases][kMaxTaps] = {};
   int max_taps = 0;
   __half* d_w = nullptr;   // device, packed [phase][kslab][tap][2][N][8]
-  __half* d_wdx = nullptr; // device, dx-as-N packing [kslab][dy][2][dx*32+co][8] (Cout == 32, up == 1 only)
   __half* d_wrows = nullptr; // device, row-streaming packing [kslab][dx][2][dy*Cout+co][8] (Cout 32/64, plain 3x3)
   float* d_bias = nullptr; // device, [nphase][N]
   size_t w_bytes = 0;
@@ -74,7 +73,7 @@ void conv_layer_free(ConvLayer& L);
 // Cache of encoded TMA descriptors keyed by (base, B, CT, H, W, box width in pixels).
 class TmapCache {
  public:
-  // box_w > 0: 5-D map with a box of box_w pixels; box_w < 0: merged 4-D map with -box_w pixels per row
+  // 5-D map of a [B][CT][H][W][8] tensor (or one wide image, B = 1) with a box of box_w pixels
   const CUtensorMap* get(const void* base, int B, int CT, int H, int W, int box_w, int& rc);
   // wide-layout row-segment map of the row-streaming kernel (box of `kc` chunks)
   const CUtensorMap* get_rows(const void* base, int CT, int H, int Wtot, int kc, int& rc);

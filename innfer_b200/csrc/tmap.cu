@@ -35,21 +35,6 @@ int encode_act_tmap(CUtensorMap* out, const void* base, int B, int CT, int H, in
   return (int)r;
 }
 
-int encode_act_tmap_merged(CUtensorMap* out, const void* base, int B, int CT, int H, int W, int box_w,
-                           int box_chunks) {
-  EncodeTiledFn enc = resolve_encode();
-  if (!enc) return -1;
-  if (box_w * 8 > 256) return -2;
-  const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)CT, (cuuint64_t)B};
-  const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)CT * H * W * 16};
-  const cuuint32_t box[4] = {(cuuint32_t)(box_w * 8), (cuuint32_t)kHaloRows, (cuuint32_t)box_chunks, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return (int)r;
-}
-
 int encode_wide_rows_tmap(CUtensorMap* out, const void* base, int CT, int H, int Wtot, int box_chunks) {
   EncodeTiledFn enc = resolve_encode();
   if (!enc) return -1;

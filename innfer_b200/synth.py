@@ -35,3 +35,24 @@ def flop_per_lr_pixel(scale=4, nb=23, nf=64, in_nc=3, out_nc=3):
         mac += res * 9 * nf * nf
     mac += res * 9 * nf * nf + res * 9 * nf * out_nc
     return 2 * mac
+
+
+def bytes_per_lr_pixel(scale=4, nb=23, nf=64, in_nc=3, out_nc=3):
+    """Algorithmic fp16 activation bytes per low-res pixel moved by the conv sequence when every conv
+    reads its real input channels once and writes its output once (residual inputs read once each):
+    the HBM traffic of the layer-by-layer schedule whenever a batch of tiles is larger than L2."""
+    e = 2
+    b = (in_nc + nf) * e                                              # fea_conv
+    rdb = sum((nf + 32 * k + 32) * e for k in range(4)) + (nf + 128 + nf + nf) * e   # conv1..4, conv5 (+x residual)
+    b += nb * (3 * rdb + nf * e)                                      # + RRDB-level residual read
+    b += 3 * nf * e                                                   # LR_conv: in, shortcut, out
+    n_up = {1: 0, 2: 1, 3: 1, 4: 2, 8: 3}[scale]
+    f = 3 if scale == 3 else 2
+    res = 1
+    for _ in range(n_up):
+        b += res * nf * e
+        res *= f * f
+        b += res * nf * e
+    b += res * 2 * nf * e                                             # HR_conv0
+    b += res * (nf + max(out_nc, 4)) * e                              # HR_conv1 (compact 4-channel tile pixels)
+    return b

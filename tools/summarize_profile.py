@@ -34,7 +34,7 @@ for r in rows:
     a[1] += us
     total += us
 with open(os.path.join(out_dir, "%s_launch_summary.md" % tag), "w") as f:
-    f.write("# ncu launch list (%s): one 800x1000 frame (63 tiles, 2 batches), 4x RRDB nb=23 fp16\n\n" % tag)
+    f.write("# ncu launch list (%s): one 800x1000 frame (63 tiles, one batch), 4x RRDB nb=23 fp16\n\n" % tag)
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` over every launch of "
             "`tests/gpu_bringup.py --stage prof` (cold-cache, serialised: compare shares).\n\n")
     f.write("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
@@ -60,7 +60,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "sm__cycles_elapsed.max", "laun
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 want = [w for w in want if w in idx]
-with open(os.path.join(out_dir, "%s_conv_tc_ncu_full.csv" % tag), "w", newline="") as f:
+with open(os.path.join(out_dir, "%s_conv_ncu_full.csv" % tag), "w", newline="") as f:
     w = csv.writer(f)
     w.writerow(["metric", "unit"] + ["launch%d" % i for i in range(len(data))])
     for m in want:
@@ -77,9 +77,9 @@ for d in data:
     rd = fbytes(d[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
     wr = fbytes(d[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
     tr.append(rd + wr)
-with open(os.path.join(out_dir, "conv_tc_traffic.json"), "w") as f:
-    json.dump({"source": "%s_conv_tc_ncu_full.csv (ncu --set full, %d consecutive conv launches of one RDB cycle, "
-                         "batch of 38 tiles)" % (tag, len(data)),
+with open(os.path.join(out_dir, "conv_traffic.json"), "w") as f:
+    json.dump({"source": "%s_conv_ncu_full.csv (ncu --set full, %d consecutive conv launches of one RDB cycle, "
+                         "one batch of 63 tiles = 800x1000 frame)" % (tag, len(data)),
                "dram_bytes_per_launch": tr, "dram_bytes_per_launch_avg": sum(tr) / len(tr)}, f, indent=1)
 print(open(os.path.join(out_dir, "%s_launch_summary.md" % tag)).read()[:1500])
-print(open(os.path.join(out_dir, "%s_conv_tc_ncu_full.csv" % tag)).read()[:3000])
+print(open(os.path.join(out_dir, "%s_conv_ncu_full.csv" % tag)).read()[:3000])
