@@ -73,6 +73,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   uint64_t* tfull_bar = empty_bar + S;
   uint64_t* set_bar = tfull_bar + 2;       // "accumulator set is drained" (4 epilogue warps arrive)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(set_bar + 2);
+  volatile uint32_t* ready_cnt = tmem_slot + 1;   // stages whose barriers the scout warp has seen complete
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
 
   if (threadIdx.x == 0) {
@@ -83,6 +84,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&tfull_bar[i]), 1);
     for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&set_bar[i]), 4);
+    *ready_cnt = 0u;
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < p.nphase * N; i += blockDim.x) s_bias[i] = p.bias[i];  // bias is [phase][N]
@@ -149,21 +151,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     const int J = p.J;
     const bool plain3x3 = (p.nphase == 1) && (p.ph_ntaps[0] == 9);
     int s = 0;
-    uint32_t ph = 0;
     uint32_t it = 0;
+    uint32_t stage_i = 0, ready = 0;
+    const uint32_t ready_addr = smem_u32((const void*)ready_cnt);
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
     for (; ti.valid(); ti.advance(), ++it) {
       const TileCoord c = ti.coord();
       const int ntaps = plain3x3 ? 9 : (int)p.ph_ntaps[c.phase];
       const uint32_t set = it & 1u;
-      // the epilogue must have drained the tile that used this accumulator set two tiles ago
-      mbar_wait(smem_u32(&set_bar[set]), ((it >> 1) & 1u) ^ 1u);
-      tc_fence_after();
       const uint32_t acc0 = tmem_base + set * (uint32_t)(J * N);
-      for (int ks = 0; ks < p.kslabs; ++ks) {
-        mbar_wait(smem_u32(&full_bar[s]), ph);
-        tc_fence_after();
+      for (int ks = 0; ks < p.kslabs; ++ks, ++stage_i) {
+        // stage stage_i is ready when the scout has seen its TMA data (and, for the first stage of a
+        // tile, the accumulator set drained by the epilogue); the count is re-read only when needed
+        if (ready <= stage_i) {
+          uint32_t spins = 0;
+          do {
+            asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(ready) : "r"(ready_addr) : "memory");
+            if (++spins > (1u << 26)) __trap();
+          } while (ready <= stage_i);
+          tc_fence_after();
+        }
         const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
         const uint32_t a_lo = ((sa & 0x3FFFFu) >> 4) | (a_lbo << 16);
         const uint32_t b_lo = (((sa + a_bytes) & 0x3FFFFu) >> 4) | (b_lbo << 16);
@@ -221,13 +229,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         }
         if (leader) umma_commit(smem_u32(&empty_bar[s]));
         __syncwarp();
-        if (++s == S) {
-          s = 0;
-          ph ^= 1u;
-        }
+        if (++s == S) s = 0;
       }
       if (leader) umma_commit(smem_u32(&tfull_bar[set]));
       __syncwarp();
+    }
+  } else if (warp == 6) {
+    // ------------------------------------------------------------ scout
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0, it = 0, done = 0;
+      const uint32_t ready_addr = smem_u32((const void*)ready_cnt);
+      TileIter ti;
+      ti.init(p, blockIdx.x, gridDim.x);
+      for (; ti.valid(); ti.advance(), ++it) {
+        // the epilogue must have drained the tile that used this accumulator set two tiles ago
+        mbar_wait(smem_u32(&set_bar[it & 1u]), ((it >> 1) & 1u) ^ 1u);
+        for (int ks = 0; ks < p.kslabs; ++ks) {
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          if (++s == S) {
+            s = 0;
+            ph ^= 1u;
+          }
+          ++done;
+          asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(ready_addr), "r"(done) : "memory");
+        }
+      }
     }
   } else {
     // ------------------------------------------------------------ epilogue warps
