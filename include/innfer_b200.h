@@ -175,7 +175,9 @@ int innfer_blend(const void* tiles, int H, int W, int patch_size, float step, in
 /* one fused conv_block (architectures/block.py:213-254) [+ nearest Upsample in front,
  * block.py:348-361] [+ LeakyReLU] [+ alpha1*. + res1] on NCHW device tensors; weights host fp32
  * OIHW.  Builds, runs and frees a temporary layer -- a test/bring-up entry point, not a hot path.
- * x [n][Cin][h][w], res1 (or NULL) and y [n][Cout][up*h][up*w] all of `dtype`. */
+ * x [n][Cin][h][w], res1 (or NULL) and y [n][Cout][up*h][up*w] all of `dtype`.
+ * use_fp32_kernel: 0 = fp16 kernels on the tiled layout, 1 = fp32 direct kernel, 2 = fp16 kernels on the wide
+ * batch layout the engine uses (row-streaming kernel for Cout = 32). */
 int innfer_conv3x3(const void* x, int n, int Cin, int hgt, int wid, const float* w_oihw,
                    const float* bias, int Cout, int up, int lrelu, const void* res1, float alpha1,
                    void* y, int dtype, int use_fp32_kernel, void* stream);

@@ -915,9 +915,11 @@ int innfer_conv3x3(const void* x, int n, int Cin, int hgt, int wid, const float*
   std::string err;
   int rc = conv_layer_build(L, w_oihw, bias, Cout, Cin, up, err);
   if (rc) return fail(rc == -2 ? INNFER_E_UNSUPPORTED : INNFER_E_CUDA, err);
+  const bool wide_mode = use_fp32_kernel == 2;   // 0: fp16 tiled layout, 1: fp32 direct kernel, 2: fp16 wide layout
+  if (wide_mode) use_fp32_kernel = 0;
   const size_t esz = use_fp32_kernel ? 4 : 2;
   const int ict = L.Cin_pad / 8, oct = (Cout + 7) / 8;
-  const size_t ipx = (size_t)n * hgt * wid, opx = ipx * up * up;
+  const size_t ipx = wide_mode ? (size_t)hgt * wide_cols(n, wid) : (size_t)n * hgt * wid, opx = ipx * up * up;
   DevBuf bi, bo, br;
   TmapCache cache;
   auto cleanup = [&]() {
@@ -942,6 +944,21 @@ int innfer_conv3x3(const void* x, int n, int Cin, int hgt, int wid, const float*
     }
     if (!rc) rc = conv_direct_run(L, view(bi, ict, 0), n, hgt, wid, view(bo, oct, 0), oct, ep, st);
     if (!rc) rc = launch_chunks_to_nchw_f32(reinterpret_cast<const float*>(bo.p), oct, n, Cout, hgt * up, wid * up, y, to_pix(dtype), st);
+  } else if (wide_mode) {
+    // the production layout of the fp16 path: the n images side by side in one wide image
+    const int pitch = wide_pitch(wid), cols = wide_cols(n, wid);
+    cudaMemsetAsync(bi.p, 0, bi.bytes, st);
+    rc = launch_nchw_to_wide(x, to_pix(dtype), n, Cin, hgt, wid, reinterpret_cast<__half*>(bi.p), ict, pitch, cols, st);
+    if (res1) {
+      cudaMemsetAsync(br.p, 0, br.bytes, st);
+      rc |= launch_nchw_to_wide(res1, to_pix(dtype), n, Cout, hgt, wid, reinterpret_cast<__half*>(br.p), oct, pitch, cols, st);
+      ep.res1 = wview(br, oct, 0, n, wid, 1);
+      ep.alpha1 = alpha1;
+    }
+    if (!rc) rc = conv_layer_run(L, cache, wview(bi, ict, 0, n, wid, 1), n, hgt, wid, wview(bo, oct, 0, n, wid, up), oct, ep,
+                                 prop.multiProcessorCount, st);
+    if (!rc) rc = launch_wide_to_nchw(reinterpret_cast<const __half*>(bo.p), oct, n, Cout, hgt * up, wid * up, pitch * up,
+                                      cols * up, y, to_pix(dtype), st);
   } else {
     rc = launch_nchw_to_chunks(x, to_pix(dtype), n, Cin, hgt, wid, reinterpret_cast<__half*>(bi.p), ict, st);
     if (res1) {

@@ -301,9 +301,15 @@ __global__ void blend_vec4_kernel(const E* __restrict__ tiles, int CT, const __g
   }
 }
 
+// Chunk-pixel strides of a planar-chunk tensor, in 16-byte units (one 8-channel pixel chunk each): image, chunk, row.
+// Tiled [n][CT][H][W][8]: {CT*H*W, H*W, W}; wide [CT][H][Wtot][8] with images `pitch` columns apart: {pitch, H*Wtot, Wtot}.
+struct ChunkStrides {
+  size_t bs, cs, ys;
+};
+
 template <typename T, typename E>
 __global__ void nchw_to_chunks_kernel(const T* __restrict__ src, int n, int C, int H, int W,
-                                      E* __restrict__ dst, int CT) {
+                                      E* __restrict__ dst, int CT, ChunkStrides st) {
   const size_t plane = (size_t)H * W;
   const size_t total = (size_t)n * CT * plane;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -318,13 +324,13 @@ __global__ void nchw_to_chunks_kernel(const T* __restrict__ src, int n, int C, i
       const int c = ch * 8 + e;
       v[e] = c < C ? load_as_float<T>(src, (b * C + c) * plane + pix) : 0.f;
     }
-    store_chunk<E>(dst, i, v);
+    store_chunk<E>(dst, b * st.bs + ch * st.cs + (pix / W) * st.ys + pix % W, v);
   }
 }
 
 template <typename T, typename E>
 __global__ void chunks_to_nchw_kernel(const E* __restrict__ src, int CT, int n, int C, int H, int W,
-                                      T* __restrict__ dst) {
+                                      T* __restrict__ dst, ChunkStrides st) {
   const size_t plane = (size_t)H * W;
   const size_t total = (size_t)n * C * plane;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -333,7 +339,7 @@ __global__ void chunks_to_nchw_kernel(const E* __restrict__ src, int CT, int n, 
     const size_t r = i / plane;
     const int c = (int)(r % C);
     const size_t b = r / C;
-    const float v = load_as_float<E>(src, ((b * CT + c / 8) * plane + pix) * 8 + (c & 7));
+    const float v = load_as_float<E>(src, (b * st.bs + (c / 8) * st.cs + (pix / W) * st.ys + pix % W) * 8 + (c & 7));
     if (sizeof(T) == 2) reinterpret_cast<__half*>(dst)[i] = __float2half_rn(v);
     else reinterpret_cast<float*>(dst)[i] = v;
   }
@@ -414,15 +420,30 @@ int blend_impl(const E* tiles, int CT, const TilePlan& plan, int scale, int C, v
   return (int)cudaGetLastError();
 }
 
+ChunkStrides chunk_strides(int CT, int H, int W, int wide_pitch, int wide_cols) {
+  ChunkStrides st;
+  if (wide_pitch > 0) {
+    st.bs = (size_t)wide_pitch;
+    st.cs = (size_t)H * wide_cols;
+    st.ys = (size_t)wide_cols;
+  } else {
+    st.bs = (size_t)CT * H * W;
+    st.cs = (size_t)H * W;
+    st.ys = (size_t)W;
+  }
+  return st;
+}
+
 template <typename E>
 int nchw_to_chunks_impl(const void* src, PixelDType st, int n, int C, int H, int W, E* dst, int CT,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, int wide_pitch = 0, int wide_cols = 0) {
   const size_t total = (size_t)n * CT * H * W;
   const int block = 256, grid = grid_for(total, block);
+  const ChunkStrides cs = chunk_strides(CT, H, W, wide_pitch, wide_cols);
   if (st == kF16)
-    nchw_to_chunks_kernel<__half, E><<<grid, block, 0, stream>>>(reinterpret_cast<const __half*>(src), n, C, H, W, dst, CT);
+    nchw_to_chunks_kernel<__half, E><<<grid, block, 0, stream>>>(reinterpret_cast<const __half*>(src), n, C, H, W, dst, CT, cs);
   else if (st == kF32)
-    nchw_to_chunks_kernel<float, E><<<grid, block, 0, stream>>>(reinterpret_cast<const float*>(src), n, C, H, W, dst, CT);
+    nchw_to_chunks_kernel<float, E><<<grid, block, 0, stream>>>(reinterpret_cast<const float*>(src), n, C, H, W, dst, CT, cs);
   else
     return -1;
   return (int)cudaGetLastError();
@@ -430,13 +451,14 @@ int nchw_to_chunks_impl(const void* src, PixelDType st, int n, int C, int H, int
 
 template <typename E>
 int chunks_to_nchw_impl(const E* src, int CT, int n, int C, int H, int W, void* dst, PixelDType dt,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, int wide_pitch = 0, int wide_cols = 0) {
   const size_t total = (size_t)n * C * H * W;
   const int block = 256, grid = grid_for(total, block);
+  const ChunkStrides cs = chunk_strides(CT, H, W, wide_pitch, wide_cols);
   if (dt == kF16)
-    chunks_to_nchw_kernel<__half, E><<<grid, block, 0, stream>>>(src, CT, n, C, H, W, reinterpret_cast<__half*>(dst));
+    chunks_to_nchw_kernel<__half, E><<<grid, block, 0, stream>>>(src, CT, n, C, H, W, reinterpret_cast<__half*>(dst), cs);
   else if (dt == kF32)
-    chunks_to_nchw_kernel<float, E><<<grid, block, 0, stream>>>(src, CT, n, C, H, W, reinterpret_cast<float*>(dst));
+    chunks_to_nchw_kernel<float, E><<<grid, block, 0, stream>>>(src, CT, n, C, H, W, reinterpret_cast<float*>(dst), cs);
   else
     return -1;
   return (int)cudaGetLastError();
@@ -475,6 +497,14 @@ int launch_chunks_to_nchw(const __half* src, int CT, int n, int C, int H, int W,
 int launch_chunks_to_nchw_f32(const float* src, int CT, int n, int C, int H, int W, void* dst,
                               PixelDType dt, cudaStream_t stream) {
   return chunks_to_nchw_impl<float>(src, CT, n, C, H, W, dst, dt, stream);
+}
+int launch_nchw_to_wide(const void* src, PixelDType st, int n, int C, int H, int W, __half* dst, int CT, int pitch,
+                        int cols, cudaStream_t stream) {
+  return nchw_to_chunks_impl<__half>(src, st, n, C, H, W, dst, CT, stream, pitch, cols);
+}
+int launch_wide_to_nchw(const __half* src, int CT, int n, int C, int H, int W, int pitch, int cols, void* dst,
+                        PixelDType dt, cudaStream_t stream) {
+  return chunks_to_nchw_impl<__half>(src, CT, n, C, H, W, dst, dt, stream, pitch, cols);
 }
 
 }  // namespace innfer

@@ -53,4 +53,11 @@ int launch_nchw_to_chunks_f32(const void* src, PixelDType st, int n, int C, int 
 int launch_chunks_to_nchw_f32(const float* src, int CT, int n, int C, int H, int W, void* dst,
                               PixelDType dt, cudaStream_t stream);
 
+// NCHW <-> wide layout [CT][H][cols][8] (image b in columns [b*pitch, b*pitch + W)); separator columns are not
+// touched by the first (the caller zeroes the buffer) and skipped by the second.
+int launch_nchw_to_wide(const void* src, PixelDType st, int n, int C, int H, int W, __half* dst, int CT, int pitch,
+                        int cols, cudaStream_t stream);
+int launch_wide_to_nchw(const __half* src, int CT, int n, int C, int H, int W, int pitch, int cols, void* dst,
+                        PixelDType dt, cudaStream_t stream);
+
 }  // namespace innfer

@@ -25,7 +25,7 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 
 
-def conv_case(cin, cout, h, w, n=1, up=1, lrelu=False, res=False, fp32=False, seed=0, verbose=True):
+def conv_case(cin, cout, h, w, n=1, up=1, lrelu=False, res=False, fp32=False, seed=0, verbose=True, wide=False):
     lib = N.load()
     g = torch.Generator().manual_seed(seed)
     x = (torch.rand(n, cin, h, w, generator=g) * 2 - 1)
@@ -40,7 +40,7 @@ def conv_case(cin, cout, h, w, n=1, up=1, lrelu=False, res=False, fp32=False, se
     bc = b.contiguous().numpy()
     rc = lib.innfer_conv3x3(xd.data_ptr(), n, cin, h, w, wc.ctypes.data, bc.ctypes.data, cout, up,
                             int(lrelu), rd.data_ptr() if res else None, 0.2, y.data_ptr(),
-                            N.INNFER_F32 if fp32 else N.INNFER_F16, int(fp32), None)
+                            N.INNFER_F32 if fp32 else N.INNFER_F16, 2 if wide else int(fp32), None)
     if rc != 0:
         print("FAIL rc=%d %s" % (rc, N.last_error()))
         return False
@@ -60,8 +60,8 @@ def conv_case(cin, cout, h, w, n=1, up=1, lrelu=False, res=False, fp32=False, se
     scale = ref.abs().max().item()
     ok = bool(err.max().item() <= tol * max(scale, 1.0)) and bool(torch.isfinite(y).all())
     tag = "PASS" if ok else "FAIL"
-    print("%s conv cin=%d cout=%d %dx%d n=%d up=%d lrelu=%d res=%d fp32=%d: max_err=%.3e mean_err=%.3e ref_max=%.3f"
-          % (tag, cin, cout, h, w, n, up, lrelu, res, fp32, err.max().item(), err.mean().item(), scale))
+    print("%s conv cin=%d cout=%d %dx%d n=%d up=%d lrelu=%d res=%d fp32=%d wide=%d: max_err=%.3e mean_err=%.3e ref_max=%.3f"
+          % (tag, cin, cout, h, w, n, up, lrelu, res, fp32, wide, err.max().item(), err.mean().item(), scale))
     if not ok and verbose:
         bad = err > tol * max(scale, 1.0)
         print("   bad fraction %.4f" % bad.float().mean().item())
@@ -94,6 +94,13 @@ def stage_convs():
     ok &= conv_case(64, 64, 17, 23, up=3, lrelu=True)
     ok &= conv_case(32, 32, 20, 20, lrelu=True)
     ok &= conv_case(64, 32, 200, 200, n=2, lrelu=True)
+    # wide layout (production layout of the fp16 path)
+    for cin, cout in ((64, 32), (96, 32), (128, 32), (160, 32), (192, 64)):
+        ok &= conv_case(cin, cout, 40, 48, n=2, lrelu=cout == 32, res=cout == 64, wide=True)
+    ok &= conv_case(96, 32, 33, 47, n=3, res=True, wide=True)
+    ok &= conv_case(64, 32, 2, 127, n=5, wide=True)
+    ok &= conv_case(64, 64, 24, 40, n=2, up=2, lrelu=True, wide=True)
+    ok &= conv_case(64, 3, 50, 70, n=2, wide=True)
     # fp32 direct kernel
     ok &= conv_case(64, 32, 40, 48, lrelu=True, fp32=True)
     ok &= conv_case(192, 64, 21, 35, res=True, fp32=True)

@@ -35,7 +35,7 @@ def _engine(sd, dev, fp16=True, scale=None):
     return RRDBEngine.from_state_dict(sd, cfg, dev, fp16=fp16)
 
 
-def _conv(native, dev, cin, cout, h, w, n=1, up=1, lrelu=False, res=False, fp32=False, seed=0):
+def _conv(native, dev, cin, cout, h, w, n=1, up=1, lrelu=False, res=False, fp32=False, seed=0, wide=False):
     lib = native.load()
     g = torch.Generator().manual_seed(seed)
     x = torch.rand(n, cin, h, w, generator=g) * 2 - 1
@@ -49,7 +49,7 @@ def _conv(native, dev, cin, cout, h, w, n=1, up=1, lrelu=False, res=False, fp32=
     wc, bc = wgt.contiguous().numpy(), b.contiguous().numpy()
     native.check(lib.innfer_conv3x3(xd.data_ptr(), n, cin, h, w, wc.ctypes.data, bc.ctypes.data, cout, up, int(lrelu),
                                     rd.data_ptr() if res else None, 0.2, y.data_ptr(),
-                                    native.INNFER_F32 if fp32 else native.INNFER_F16, int(fp32), None))
+                                    native.INNFER_F32 if fp32 else native.INNFER_F16, 2 if wide else int(fp32), None))
     torch.cuda.synchronize()
     xr = xd.double().cpu()
     wr = wgt.double() if fp32 else wgt.half().double()
@@ -75,6 +75,26 @@ def test_conv_block_tcgen05(native, dev, cin, cout, h, w, kw):
     """conv_block / upconv_block on the tensor-core kernel vs F.conv2d in fp64 on the same
     fp16-rounded operands: only fp32 accumulation order and the fp16 output rounding differ."""
     y, ref = _conv(native, dev, cin, cout, h, w, **kw)
+    tol = 2e-3 * max(1.0, ref.abs().max().item())
+    assert torch.isfinite(y).all()
+    assert (y - ref).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("cin,cout,h,w,kw", [
+    # row-streaming kernel (Cout = 32): every K-slab specialisation, residual variant, ragged sizes, 1..5 images
+    (64, 32, 16, 40, {}), (64, 32, 40, 48, dict(lrelu=True)), (96, 32, 40, 48, dict(lrelu=True)),
+    (128, 32, 33, 47, dict(lrelu=True, n=3)), (160, 32, 40, 48, dict(lrelu=True)), (160, 32, 21, 35, dict(res=True, n=2)),
+    (32, 32, 20, 20, dict(lrelu=True)), (16, 32, 9, 130, dict(lrelu=True)), (64, 32, 1, 1, {}), (64, 32, 2, 127, dict(n=5)),
+    (64, 32, 7, 200, dict(lrelu=True)), (64, 32, 200, 200, dict(n=2, lrelu=True)), (96, 32, 300, 129, dict(lrelu=True, res=True)),
+    # 9-tap kernel on a wide source: separators, residuals, upsampling phases, N = 16/32/64
+    (192, 64, 40, 48, dict(res=True, n=2)), (3, 64, 33, 47, dict(n=2)), (64, 3, 50, 70, dict(n=2)),
+    (64, 64, 37, 53, dict(n=3, lrelu=True)), (64, 64, 24, 40, dict(up=2, lrelu=True, n=2)),
+    (64, 64, 17, 23, dict(up=3, lrelu=True, n=2)), (64, 16, 19, 21, dict(n=4, lrelu=True)),
+])
+def test_conv_block_wide_layout(native, dev, cin, cout, h, w, kw):
+    """The same convs on the production layout of the fp16 path: n images side by side in one wide image with
+    zero separator columns (conv_rows_kernel for Cout = 32, conv_tc_kernel with separator handling otherwise)."""
+    y, ref = _conv(native, dev, cin, cout, h, w, wide=True, **kw)
     tol = 2e-3 * max(1.0, ref.abs().max().item())
     assert torch.isfinite(y).all()
     assert (y - ref).abs().max().item() <= tol
