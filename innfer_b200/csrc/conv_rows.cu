@@ -3,8 +3,8 @@
 //
 // Replaces (fp16 engine path) conv1..conv4 of ResidualDenseBlock_5C (RRDBNet_arch.py:152-165:
 // Conv2d(k=3,p=1) + LeakyReLU(0.2), Cout = 32), incl. the ESRGAN+ residual adds and, for nf = 32 nets,
-// conv5 with its "*0.2 + x" epilogues.  (COUT = 64, N = 192 works but was measured slower than the
-// 9-tap weight-stationary kernel, see layers.cu.)
+// conv5 with its "*0.2 + x" epilogues; with COUT = 64 (N = 192, two TMEM slots) the residual-free
+// 64 -> 64 convs whose weights fit in shared memory (HR_conv0, SRResNet's first block convs).
 //
 // Wide layout: the B tile images of a batch stand side by side in one image [chunk][H][Wtot][8],
 // image b in columns [b*pitch, b*pitch + Wimg), the `pitch - Wimg` separator columns hold zeros (they
@@ -386,16 +386,41 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         tc_fence_after();
         ROWS_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && ecount < 256) p.trace[2048 + ecount++] = clock64());
         const uint32_t tacc = tmem_base + lane_base + (uint32_t)(slot * N + grp * CH);
-        // all three blocks of this thread's channels are read at once: the slot goes back to the MMA warp
-        // as early as possible, the running sums are updated afterwards
-        uint32_t v0[CH], v1[CH], v2[CH];
+        float o[CH];
+        if constexpr (CH == 16) {
+          // all three blocks of this thread's channels are read at once: the slot goes back to the MMA warp
+          // as early as possible
+          uint32_t v0[16], v1[16], v2[16];
+          tmem_ld16(tacc, v0);
+          tmem_ld16(tacc + COUT, v1);
+          tmem_ld16(tacc + 2 * COUT, v2);
+          tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < CH / 16; ++g) {
-          tmem_ld16(tacc + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v0[g * 16]));
-          tmem_ld16(tacc + COUT + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v1[g * 16]));
-          tmem_ld16(tacc + 2 * COUT + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v2[g * 16]));
+          for (int c = 0; c < 16; ++c) {
+            o[c] = accA[c] + __uint_as_float(v2[c]);
+            accA[c] = accB[c] + __uint_as_float(v1[c]);
+            accB[c] = __uint_as_float(v0[c]);
+          }
+        } else {
+          // COUT = 64: 3 x 32 running values per thread; read through one 16-register buffer to stay
+          // clear of spills (TMEM read latency is ~12 cycles)
+          uint32_t v[16];
+#pragma unroll
+          for (int g = 0; g < CH / 16; ++g) {
+            tmem_ld16(tacc + 2 * COUT + g * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) o[g * 16 + c] = accA[g * 16 + c] + __uint_as_float(v[c]);
+            tmem_ld16(tacc + COUT + g * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) accA[g * 16 + c] = accB[g * 16 + c] + __uint_as_float(v[c]);
+            tmem_ld16(tacc + g * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) accB[g * 16 + c] = __uint_as_float(v[c]);
+          }
         }
-        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&slot_bar[slot]));
@@ -403,17 +428,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           slot = 0;
           ++use;
         }
-        if (r - 1 >= pc.ya) {
-          float o[CH];
-#pragma unroll
-          for (int c = 0; c < CH; ++c) o[c] = accA[c] + __uint_as_float(v2[c]);
-          store_row(r - 1, o);
-        }
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          accA[c] = accB[c] + __uint_as_float(v1[c]);
-          accB[c] = __uint_as_float(v0[c]);
-        }
+        if (r - 1 >= pc.ya) store_row(r - 1, o);
       }
       if (pc.yb == p.H) {   // bottom row: the row below is zero padding
         load_side(p.H - 1);
@@ -472,6 +487,7 @@ int conv_rows_weight_bytes(int nch, int cout) { return (nch / 2) * 3 * 2 * (3 * 
 
 int launch_conv_rows(const CUtensorMap* tmap_in, const ConvRowsParams& p, int cout, int num_sms, cudaStream_t stream) {
   if (cout == 32) return launch_rows_k<32>(tmap_in, p, num_sms, stream);
+  if (cout == 64) return launch_rows_k<64>(tmap_in, p, num_sms, stream);
   return (int)cudaErrorInvalidValue;
 }
 

@@ -254,15 +254,16 @@ const CUtensorMap* TmapCache::get_rows(const void* base, int CT, int H, int Wtot
 // Row-streaming kernel on wide tensors; returns -100 when the conv is not eligible.
 static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, int H, int W, ChunkView out,
                          int out_nchunks, const Epilogue& ep, int num_sms, cudaStream_t stream) {
-  static const int rows_mode = getenv("INNFER_ROWS") ? atoi(getenv("INNFER_ROWS")) : 1;
+  static const int rows_mode = getenv("INNFER_ROWS") ? atoi(getenv("INNFER_ROWS")) : 3;  // bit 0: on, bit 1: Cout = 64 too
   if (!rows_mode || !in.wide() || !out.wide() || L.d_wrows == nullptr || L.up != 1 || ep.compact4 ||
       out_nchunks * 8 != L.Cout || in.pitch != out.pitch || in.Wtot != out.Wtot)
     return -100;
   for (const ChunkView* v : {&ep.res1, &ep.res2})
     if (v->base && (!v->wide() || v->pitch != out.pitch || v->Wtot != out.Wtot)) return -100;
-  // Cout = 64 (N = 192) was measured slower than the 9-tap weight-stationary kernel: N > 128 MMAs run at
-  // ~130 cycles instead of 96 and the 3 x 32 running sums per epilogue thread spill
-  if (L.Cout != 32) return -100;
+  // Cout = 64 (N = 192 MMAs run at ~117 cycles, only two TMEM slots): 1.3x faster than the 9-tap kernel for
+  // residual-free convs (HR_conv0: 3275 -> 2520 us), no gain with residual epilogues (measured, profiles/)
+  if (L.Cout == 64 && (ep.res1.base || ep.res2.base || !(rows_mode & 2))) return -100;
+  if (L.Cout != 32 && L.Cout != 64) return -100;
   const int nch = L.Cin_pad / 8;
   int nsub = (nch + 15) / 16;
   while (nsub <= nch && (nch % nsub != 0 || ((nch / nsub) & 1))) ++nsub;

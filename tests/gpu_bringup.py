@@ -247,11 +247,14 @@ def stage_steady():
     lib = N.load()
     B = int(os.environ.get("INNFER_STEADY_B", "95"))
     cases = ((64, 32, 0), (96, 32, 0), (128, 32, 0), (160, 32, 0), (192, 64, 1), (64, 64, 0))
+    if os.environ.get("INNFER_STEADY_CASES"):
+        cases = tuple(tuple(int(v) for v in c.split(":")) for c in os.environ["INNFER_STEADY_CASES"].split(","))
+    hw = int(os.environ.get("INNFER_STEADY_HW", "200"))
     for cin, cout, res in cases:
-        flop = 2.0 * 9 * cin * cout * B * 200 * 200
+        flop = 2.0 * 9 * cin * cout * B * hw * hw
         ms = ctypes.c_float(0)
-        N.check(lib.innfer_debug_conv_loop(cin, cout, B, 200, 200, res, 20, 50, ctypes.byref(ms)))
-        iters = max(50, int(3000 / (ms.value / 50)))
+        N.check(lib.innfer_debug_conv_loop(cin, cout, B, hw, hw, res, 20, 50, ctypes.byref(ms)))
+        iters = max(50, int(float(os.environ.get('INNFER_STEADY_MS', '3000')) / (ms.value / 50)))
         samples, stop = [], threading.Event()
 
         def sampler():
@@ -262,7 +265,7 @@ def stage_steady():
                 time.sleep(0.05)
         th = threading.Thread(target=sampler)
         th.start()
-        N.check(lib.innfer_debug_conv_loop(cin, cout, B, 200, 200, res, 20, iters, ctypes.byref(ms)))
+        N.check(lib.innfer_debug_conv_loop(cin, cout, B, hw, hw, res, 20, iters, ctypes.byref(ms)))
         stop.set()
         th.join()
         tail = samples[len(samples) // 2:]   # second half of the run: thermally / power settled

@@ -6,7 +6,7 @@ i=0
 for cfg in "$@"; do
   i=$((i+1))
   env $cfg timeout 300 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__cycles_elapsed.max \
-    --clock-control none -k regex:conv_ -s 40 -c 6 --csv --log-file gpurun_out/exp_$i.csv python tests/gpu_bringup.py --stage prof > gpurun_out/exp_$i.log 2>&1
+    --clock-control none -k regex:conv_ -s ${SKIP:-40} -c ${COUNT:-6} --csv --log-file gpurun_out/exp_$i.csv python tests/gpu_bringup.py --stage prof > gpurun_out/exp_$i.log 2>&1
   python - "$cfg" gpurun_out/exp_$i.csv <<'PY'
 import csv, sys
 lines=[l for l in open(sys.argv[2]) if not l.startswith('==')]
