@@ -65,6 +65,18 @@ typedef struct innfer_srresnet_cfg {
   int32_t fp16;
 } innfer_srresnet_cfg;
 
+/* Constructor kwargs of PPON (architectures/PPON_arch.py:17-18) as produced by get_network_G_config
+ * (utils/defaults.py:68-77): nf = 64 (RRBlock_32 is hard-wired to 64 channels), LeakyReLU.  SURVEY.md 8(f) rank 3. */
+typedef struct innfer_ppon_cfg {
+  int32_t in_nc;
+  int32_t out_nc;
+  int32_t nf;            /* 64 */
+  int32_t nb;            /* RRBlock_32 blocks of the content module (24) */
+  int32_t scale;         /* 1, 2, 3, 4, 8 */
+  float alpha;           /* out_p = alpha * PRM(..) + out_s */
+  int32_t fp16;
+} innfer_ppon_cfg;
+
 typedef struct innfer_tile {
   int32_t y0, x0; /* low-res origin of the tile */
 } innfer_tile;
@@ -82,6 +94,10 @@ int innfer_rrdb_create(const innfer_rrdb_cfg* cfg, int device, innfer_rrdb** out
  * tile-range / destroy) works on it unchanged.  Keys: "model.0", "model.1.sub.<i>.res.0|2", "model.1.sub.<nb>",
  * "model.2|5" (pixel-shuffle convs, 4*nf filters), "model.8", "model.10" (4x). */
 int innfer_srresnet_create(const innfer_srresnet_cfg* cfg, int device, innfer_rrdb** out);
+/* PPON handle (same calls as above work on it); the forward result is the third output of PPON.forward, out_p,
+ * which is what run.py uses (run.py:191-192,220-221).  Keys: "CFEM.0", "CFEM.1.sub.<i>.RB<r>.{c1,d1..d8,c2}",
+ * "CFEM.1.sub.<nb>", "SFEM|PFEM.<0|1>.RB<r>.*", "CRM|SRM|PRM.<1,4,6,8>" (4x). */
+int innfer_ppon_create(const innfer_ppon_cfg* cfg, int device, innfer_rrdb** out);
 /* one state-dict entry under its REFERENCE key name ("model.0.weight",
  * "model.1.sub.3.RDB2.conv4.0.bias", "model.1.sub.23.weight", "model.10.bias", ...); host fp32. */
 int innfer_rrdb_load(innfer_rrdb* h, const char* key, const float* host_data, const int64_t* shape,

@@ -31,6 +31,11 @@ class SRResNetCfg(ctypes.Structure):
                 ("fp16", ctypes.c_int32)]
 
 
+class PPONCfg(ctypes.Structure):
+    _fields_ = [("in_nc", ctypes.c_int32), ("out_nc", ctypes.c_int32), ("nf", ctypes.c_int32), ("nb", ctypes.c_int32),
+                ("scale", ctypes.c_int32), ("alpha", ctypes.c_float), ("fp16", ctypes.c_int32)]
+
+
 class Tile(ctypes.Structure):
     _fields_ = [("y0", ctypes.c_int32), ("x0", ctypes.c_int32)]
 
@@ -44,6 +49,7 @@ _PROTOS = {
     "innfer_kernel_launches": (ctypes.c_uint64, []),
     "innfer_rrdb_create": (_i, [ctypes.POINTER(RRDBCfg), _i, ctypes.POINTER(_vp)]),
     "innfer_srresnet_create": (_i, [ctypes.POINTER(SRResNetCfg), _i, ctypes.POINTER(_vp)]),
+    "innfer_ppon_create": (_i, [ctypes.POINTER(PPONCfg), _i, ctypes.POINTER(_vp)]),
     "innfer_rrdb_load": (_i, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(ctypes.c_int64), _i]),
     "innfer_rrdb_finalize": (_i, [_vp]),
     "innfer_rrdb_destroy": (None, [_vp]),

@@ -1,6 +1,6 @@
 """get_network -- mirror of the reference's architectures/__init__.py:5-40 for the hot path."""
 
-_OUT_OF_SCOPE = ("mrrdb_net", "ppon", "pan_net", "unet_net", "resnet_net", "wbcunet_net")
+_OUT_OF_SCOPE = ("mrrdb_net", "pan_net", "unet_net", "resnet_net", "wbcunet_net")
 
 
 def get_network(opt_net):
@@ -12,6 +12,9 @@ def get_network(opt_net):
     if kind == "sr_resnet":
         from . import SRResNet_arch
         return SRResNet_arch.SRResNet(**opt_net)
+    if kind == "ppon":
+        from . import PPON_arch
+        return PPON_arch.PPON(**opt_net)
     if kind in _OUT_OF_SCOPE:
         raise NotImplementedError(
             "Model [%s] exists in the reference but is outside the B200 RRDB hot-path scope "

@@ -2,7 +2,7 @@
 
 Mirror of the hot-path subset of the reference's architectures/block.py: act (81-101),
 get_valid_padding (163-166), ShortcutBlock (183-194), sequential (197-210), conv_block (213-254),
-Upsample (286-331), upconv_block (348-361), conv1x1 (390-391), GaussianNoise (375-388).
+Upsample (286-331), upconv_block (348-361), conv_layer (364-366), conv1x1 (390-391), GaussianNoise (375-388).
 These modules carry the parameters (so load_state_dict sees the reference key names) and execute
 the explicit ``-cpu`` mode; on a CUDA device the owning RRDBNet bypasses them and runs the
 sm_100a engine (innfer_b200.engine).
@@ -109,6 +109,13 @@ class GaussianNoise(nn.Module):
         if self.training and self.sigma != 0:
             x = x + torch.randn_like(x) * (self.sigma * x)
         return x
+
+
+def conv_layer(in_channels, out_channels, kernel_size, stride=1, dilation=1, groups=1):
+    """Bare Conv2d with "same" zero padding for the given dilation (reference block.py:364-366)."""
+    padding = int((kernel_size - 1) / 2) * dilation
+    return nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding=padding, bias=True, dilation=dilation,
+                     groups=groups)
 
 
 def conv1x1(in_planes, out_planes, stride=1):

@@ -26,12 +26,16 @@ struct DirectParams {
   const float* res2;
   int res2_CT, res2_chunk0;
   float alpha2;
+  int dil;              // dilation (taps at multiples of dil), <= MAXD of the instantiation
+  int act_after_res;    // LeakyReLU after the residual adds
+  float* raw;           // optional pre-activation copy (layout of out)
+  int raw_CT, raw_chunk0;
 };
 
-template <int N>
+template <int N, int MAXD>
 __global__ void __launch_bounds__(kTY* kTX)
 conv_direct_kernel(const __grid_constant__ DirectParams p) {
-  __shared__ float s_in[8][kTY + 2][kTX + 2];
+  __shared__ float s_in[8][kTY + 2 * MAXD][kTX + 2 * MAXD];
   __shared__ __align__(16) float s_w[8][9][N];
   const int tx = threadIdx.x % kTX, ty = threadIdx.x / kTX;
   const int ox0 = blockIdx.x * kTX, oy0 = blockIdx.y * kTY, b = blockIdx.z;
@@ -43,9 +47,10 @@ conv_direct_kernel(const __grid_constant__ DirectParams p) {
   for (int cc = 0; cc < p.cin_chunks; ++cc) {
     __syncthreads();
     // halo tile in (possibly upsampled) output coordinates; zero outside [0,Ho)x[0,Wo)
-    for (int i = threadIdx.x; i < (kTY + 2) * (kTX + 2); i += kTY * kTX) {
-      const int hx = i % (kTX + 2), hy = i / (kTX + 2);
-      const int uy = oy0 + hy - 1, ux = ox0 + hx - 1;
+    const int d = p.dil, hw = kTX + 2 * d;
+    for (int i = threadIdx.x; i < (kTY + 2 * d) * hw; i += kTY * kTX) {
+      const int hx = i % hw, hy = i / hw;
+      const int uy = oy0 + hy - d, ux = ox0 + hx - d;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
       if (uy >= 0 && uy < p.Ho && ux >= 0 && ux < p.Wo) {
         const int sy = uy / p.up, sx = ux / p.up;
@@ -64,7 +69,7 @@ conv_direct_kernel(const __grid_constant__ DirectParams p) {
     for (int ci = 0; ci < 8; ++ci) {
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const float v = s_in[ci][ty + t / 3][tx + t % 3];
+        const float v = s_in[ci][ty + (t / 3) * d][tx + (t % 3) * d];
         const float4* wv = reinterpret_cast<const float4*>(&s_w[ci][t][0]);
 #pragma unroll
         for (int n4 = 0; n4 < N / 4; ++n4) {
@@ -87,7 +92,7 @@ conv_direct_kernel(const __grid_constant__ DirectParams p) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float t = acc[ch * 8 + e] + p.bias[ch * 8 + e];
-      if (p.lrelu) t = t > 0.f ? t : t * p.slope;
+      if (p.lrelu && !p.act_after_res) t = t > 0.f ? t : t * p.slope;
       f[e] = t;
     }
     if (p.res1) {
@@ -103,6 +108,15 @@ conv_direct_kernel(const __grid_constant__ DirectParams p) {
       const float4 a = r[0], c = r[1];
       f[0] = f[0] * p.alpha2 + a.x; f[1] = f[1] * p.alpha2 + a.y; f[2] = f[2] * p.alpha2 + a.z; f[3] = f[3] * p.alpha2 + a.w;
       f[4] = f[4] * p.alpha2 + c.x; f[5] = f[5] * p.alpha2 + c.y; f[6] = f[6] * p.alpha2 + c.z; f[7] = f[7] * p.alpha2 + c.w;
+    }
+    if (p.raw) {
+      float4* o = reinterpret_cast<float4*>(p.raw + (((size_t)b * p.raw_CT + p.raw_chunk0 + ch) * oplane + opix) * 8);
+      o[0] = make_float4(f[0], f[1], f[2], f[3]);
+      o[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    if (p.lrelu && p.act_after_res) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * p.slope;
     }
     float4* o = reinterpret_cast<float4*>(
         p.out + (((size_t)b * p.out_CT + p.out_chunk0 + ch) * oplane + opix) * 8);
@@ -163,6 +177,12 @@ int conv_direct_run(const ConvLayer& L, ChunkView in, int B, int H, int W, Chunk
   p.res2_CT = ep.res2.CT;
   p.res2_chunk0 = ep.res2.chunk0;
   p.alpha2 = ep.alpha2;
+  p.dil = L.dil;
+  p.act_after_res = ep.act_after_res ? 1 : 0;
+  p.raw = reinterpret_cast<float*>(ep.raw_out.base);
+  p.raw_CT = ep.raw_out.CT;
+  p.raw_chunk0 = ep.raw_out.chunk0;
+  if (L.dil != 1 && L.N != 32) return -8;   // dilated convs exist for 64 -> 32 only (PPON)
   dim3 grid((p.Wo + kTX - 1) / kTX, (p.Ho + kTY - 1) / kTY, B), block(kTY * kTX);
   const int nsets = L.pixel_shuffle ? L.nphase : 1;
   for (int ph = 0; ph < nsets; ++ph) {
@@ -171,9 +191,12 @@ int conv_direct_run(const ConvLayer& L, ChunkView in, int B, int H, int W, Chunk
     p.w = L.d_w32 + (size_t)ph * L.Cin_pad * 9 * L.N;
     p.bias = L.d_bias + (size_t)ph * L.N;
     switch (L.N) {
-      case 16: conv_direct_kernel<16><<<grid, block, 0, stream>>>(p); break;
-      case 32: conv_direct_kernel<32><<<grid, block, 0, stream>>>(p); break;
-      case 64: conv_direct_kernel<64><<<grid, block, 0, stream>>>(p); break;
+      case 16: conv_direct_kernel<16, 1><<<grid, block, 0, stream>>>(p); break;
+      case 32:
+        if (L.dil == 1) conv_direct_kernel<32, 1><<<grid, block, 0, stream>>>(p);
+        else conv_direct_kernel<32, 8><<<grid, block, 0, stream>>>(p);
+        break;
+      case 64: conv_direct_kernel<64, 1><<<grid, block, 0, stream>>>(p); break;
       default: return -7;
     }
   }

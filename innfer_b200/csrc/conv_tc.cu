@@ -59,8 +59,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int Wh = 8 * p.J + 2;
-  const int a_bytes = conv_tc_a_bytes(p.J);
+  const int Wh = 8 * p.J + 2 * p.dil;              // halo tile: Rh x Wh pixels
+  const int Rh = kPatchRows + 2 * p.dil;
+  const int a_bytes = conv_tc_a_bytes(p.J, p.dil);
   int max_taps = 0;
   for (int i = 0; i < p.nphase; ++i) max_taps = max_taps > p.ph_ntaps[i] ? max_taps : p.ph_ntaps[i];
   const int w_bytes = conv_tc_w_bytes(N, max_taps);
@@ -120,8 +121,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
             mbar_expect_tx(fb, wb);
             bulk_load(dstA + a_bytes, wsrc + (size_t)ks * wb, wb, fb);
           } else {
-            mbar_expect_tx(fb, (uint32_t)(2 * kHaloRows * Wh * 16) + wb);
-            tma_load_5d(dstA, &tmap_in, fb, 0, c.x0 - 1, c.y0 - 1, p.in_chunk0 + 2 * ks, c.b);
+            mbar_expect_tx(fb, (uint32_t)(2 * Rh * Wh * 16) + wb);
+            tma_load_5d(dstA, &tmap_in, fb, 0, c.x0 - p.dil, c.y0 - p.dil, p.in_chunk0 + 2 * ks, c.b);
             bulk_load(dstA + a_bytes, wsrc + (size_t)ks * wb, wb, fb);
           }
           if (++s == S) {
@@ -142,9 +143,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     // descriptor arithmetic stays in the uniform datapath; only the elected lane issues.
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_f16(N);
-    const uint32_t a_lbo = (uint32_t)(kHaloRows * Wh);   // in 16-byte units
+    const uint32_t a_lbo = (uint32_t)(Rh * Wh);          // in 16-byte units
     const uint32_t a_sbo = (uint32_t)Wh;
     const uint32_t a_hi = a_sbo | (1u << 14);            // SBO [32,46) + version=1 [46,48)
+    const uint32_t dil = (uint32_t)p.dil, dil_row = dil * a_sbo;   // tap spacing in pixels / in tile rows
     const uint32_t b_hi = 8u | (1u << 14);               // SBO = 128 B
     const uint32_t b_lbo = (uint32_t)N;                  // N * 16 B
     const uint32_t tap_stride = 2u * N;                  // 16-byte units per tap in the weight stage
@@ -184,7 +186,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
             for (int tp = 0; tp < 9; ++tp) {
               const int hy = tp / 3, hx = tp % 3;
               const uint64_t bd = make_desc64(b_lo + tp * tap_stride, b_hi);
-              const uint32_t at = a_lo + hy * a_sbo + hx;
+              const uint32_t at = a_lo + hy * dil_row + hx * dil;
               const uint32_t accf = tp == 0 ? first : 1u;
               if (tp & 1) {
                 umma_f16_ws<1, true>(acc0, make_desc64(at, a_hi), bd, idesc, accf);
@@ -208,7 +210,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
 #pragma unroll
                 for (int hx = 0; hx < 3; ++hx) {
                   const int tp = hy * 3 + hx;
-                  umma_f16_ss(acc, make_desc64(aj + hy * a_sbo + hx, a_hi),
+                  umma_f16_ss(acc, make_desc64(aj + hy * dil_row + hx * dil, a_hi),
                               make_desc64(b_lo + tp * tap_stride, b_hi), idesc, tp == 0 ? first : 1u);
                 }
               }
@@ -321,7 +323,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 float tv = __uint_as_float(v[ch * 8 + e]) + s_bias[c.phase * N + ch * 8 + e];
-                if (p.lrelu) tv = lrelu_f(tv, p.slope);
+                if (p.lrelu && !p.act_after_res) tv = lrelu_f(tv, p.slope);
                 f[e] = tv;
               }
               if (p.res1 != nullptr) {
@@ -341,6 +343,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
                   f[2 * e] = f[2 * e] * p.alpha2 + rv.x;
                   f[2 * e + 1] = f[2 * e + 1] * p.alpha2 + rv.y;
                 }
+              }
+              if (p.raw != nullptr) {   // pre-activation copy
+                uint4 o;
+                const __half2 h0 = __floats2half2_rn(f[0], f[1]);
+                const __half2 h1 = __floats2half2_rn(f[2], f[3]);
+                const __half2 h2 = __floats2half2_rn(f[4], f[5]);
+                const __half2 h3 = __floats2half2_rn(f[6], f[7]);
+                o.x = *reinterpret_cast<const uint32_t*>(&h0);
+                o.y = *reinterpret_cast<const uint32_t*>(&h1);
+                o.z = *reinterpret_cast<const uint32_t*>(&h2);
+                o.w = *reinterpret_cast<const uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(p.raw + (size_t)img * p.raw_bs + (size_t)(p.raw_chunk0 + ch) * p.raw_cs +
+                                          (size_t)oy * p.raw_ys + (size_t)ox * 8) = o;
+              }
+              if (p.lrelu && p.act_after_res) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = lrelu_f(f[e], p.slope);
               }
               uint4 o;
               const __half2 h0 = __floats2half2_rn(f[0], f[1]);
@@ -362,7 +381,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           // separator column of a wide destination: keep the zero padding between images intact
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch)
-            if (ch < p.out_nchunks) *reinterpret_cast<uint4*>(op + (size_t)ch * p.out_cs) = make_uint4(0u, 0u, 0u, 0u);
+            if (ch < p.out_nchunks) {
+              *reinterpret_cast<uint4*>(op + (size_t)ch * p.out_cs) = make_uint4(0u, 0u, 0u, 0u);
+              if (p.raw != nullptr)
+                *reinterpret_cast<uint4*>(p.raw + (size_t)img * p.raw_bs + (size_t)(p.raw_chunk0 + ch) * p.raw_cs +
+                                          (size_t)oy * p.raw_ys + (size_t)ox * 8) = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
       }
     }
@@ -380,7 +404,7 @@ template <int N>
 int launch_impl(const CUtensorMap* tmap_in, const ConvTcParams& p, int num_sms, cudaStream_t stream) {
   int max_taps = 0;
   for (int i = 0; i < p.nphase; ++i) max_taps = max_taps > p.ph_ntaps[i] ? max_taps : p.ph_ntaps[i];
-  const int stage_bytes = conv_tc_a_bytes(p.J) + conv_tc_w_bytes(N, max_taps);
+  const int stage_bytes = conv_tc_a_bytes(p.J, p.dil) + conv_tc_w_bytes(N, max_taps);
   const size_t smem_bytes = (size_t)p.stages * stage_bytes + kConvTailBytes;
   cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes);

@@ -34,7 +34,6 @@ namespace innfer {
 
 constexpr int kConvThreads = 224;           // + warp 6: scout (does the MMA warp's barrier waits)
 constexpr int kPatchRows = 16;            // rows per CTA patch (= rows of one M=128 sub-patch)
-constexpr int kHaloRows = kPatchRows + 2; // Rh
 constexpr int kMaxPhases = 9;
 constexpr int kMaxTaps = 9;
 constexpr int kConvTailBytes = 4096;       // barriers + TMEM slot + per-phase bias behind the stage ring
@@ -54,6 +53,8 @@ struct ConvTcParams {
   int nslots;      // TMEM accumulator slots of N columns: 2*J (two sets of J, alternate tiles)
   int tmem_cols;   // power of two >= nslots*N
   int debug;       // bit0: skip TMA loads (timing experiments only, garbage results)
+  int dil;         // dilation of a plain 3x3 conv (PPON's d1..d8, block.py:364-366): taps at (hy*dil, hx*dil) of
+                   // a (16 + 2*dil) x (8J + 2*dil) halo tile; 1 for every other conv
   // destination
   __half* out;
   int out_CT, out_chunk0, out_nchunks;
@@ -66,6 +67,12 @@ struct ConvTcParams {
   int out_ys, out_px;
   long long res1_bs, res1_cs, res2_bs, res2_cs;
   int res1_ys, res2_ys;
+  // second destination (or null) with the layout class of `out`: receives the value BEFORE the activation
+  // when act_after_res is set (PPON's running sums add_k feed both the next dilated conv and, activated, c2)
+  __half* raw;
+  long long raw_bs, raw_cs;
+  int raw_ys, raw_chunk0;
+  int act_after_res;   // apply the LeakyReLU after the residual adds instead of before
   // wide SOURCE: B == 1, W == Wtot and a column decomposes as image * sep_pitch + x; columns with
   // x >= sep_w or image >= sep_nimg are separators: never computed, stored as zeros when the
   // destination is wide too (out_zero_sep), skipped otherwise.  sep_pitch == 0: tiled source.
@@ -95,8 +102,8 @@ struct ConvTcParams {
 int launch_conv_tc(const CUtensorMap* tmap_in, const ConvTcParams& p, int N, int num_sms,
                    cudaStream_t stream);
 // Bytes of dynamic smem / stage geometry helpers shared by host and device.
-__host__ __device__ inline int conv_tc_a_bytes(int J) {
-  int b = 2 * kHaloRows * (8 * J + 2) * 16;
+__host__ __device__ inline int conv_tc_a_bytes(int J, int dil) {
+  int b = 2 * (kPatchRows + 2 * dil) * (8 * J + 2 * dil) * 16;
   return (b + 127) & ~127;
 }
 __host__ __device__ inline int conv_tc_w_bytes(int N, int max_taps) { return max_taps * 2 * N * 16; }

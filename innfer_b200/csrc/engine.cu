@@ -81,9 +81,15 @@ struct innfer_rrdb {
   std::vector<ConvLayer> rdb;  // [nb][3][5]
   std::vector<ConvLayer> c1x1; // [nb][3] ESRGAN+ conv1x1 (cfg.plus)
   std::vector<ConvLayer> ups;
+  // PPON (arch 2): residual blocks of 10 convs (c1, d1..d8, c2) -- content module nb*3, then SFEM 6, PFEM 6 --
+  // and the three reconstruction tails (ups..., HR_conv0, HR_conv1) CRM / SRM / PRM
+  float ppon_alpha = 1.f;
+  std::vector<ConvLayer> prb;
+  std::vector<ConvLayer> ptail[3];
   TmapCache cache;
   // workspace
   DevBuf in_tiles, feat, xbuf[3], hrbuf[2], out_tiles, img_in, img_out;
+  DevBuf pbuf[9], paux[2];   // PPON: F, X0..X2, T1, S, E1, E2 (64 channels each), CAT (256); out_c / out_s at HR
   // optional device-side timing of the conv sequence (bench.py roofline)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -101,6 +107,11 @@ struct innfer_rrdb {
     for (auto& l : rdb) conv_layer_free(l);
     for (auto& l : c1x1) conv_layer_free(l);
     for (auto& l : ups) conv_layer_free(l);
+    for (auto& l : prb) conv_layer_free(l);
+    for (auto& t : ptail)
+      for (auto& l : t) conv_layer_free(l);
+    for (auto& b : pbuf) b.release();
+    for (auto& b : paux) b.release();
     in_tiles.release();
     feat.release();
     for (auto& b : xbuf) b.release();
@@ -125,7 +136,7 @@ int set_device(const innfer_rrdb* h) {
 }
 
 int build_layer(innfer_rrdb* h, ConvLayer& L, const std::string& prefix, int Cout, int Cin, int up, int ksize = 3,
-                bool has_bias = true) {
+                bool has_bias = true, int dil = 1) {
   auto wi = h->params.find(prefix + ".weight");
   auto bi = h->params.find(prefix + ".bias");
   if (wi == h->params.end()) return fail(INNFER_E_STATE, "missing key " + prefix + ".weight");
@@ -137,7 +148,7 @@ int build_layer(innfer_rrdb* h, ConvLayer& L, const std::string& prefix, int Cou
     return fail(INNFER_E_INVALID, "size mismatch for " + prefix + ".bias");
   std::string err;
   int rc = conv_layer_build(L, wi->second.data.data(), has_bias ? bi->second.data.data() : nullptr, Cout, Cin, up, err,
-                            ksize);
+                            ksize, dil);
   if (rc) return fail(rc == -2 ? INNFER_E_UNSUPPORTED : INNFER_E_CUDA, prefix + ": " + err);
   if (!h->cfg.fp16) {
     rc = conv_direct_upload(L);
@@ -221,16 +232,24 @@ int ensure_workspace(innfer_rrdb* h, int B, int hgt, int wid) {
   int rc = 0;
   rc |= h->in_tiles.ensure(px * h->in_ct() * e8);
   rc |= h->feat.ensure(px * h->nf_ct() * e8);
-  for (auto& b : h->xbuf) rc |= b.ensure(px * h->cat_ct() * e8);
+  if (h->arch != 2)
+    for (auto& b : h->xbuf) rc |= b.ensure(px * h->cat_ct() * e8);
   const size_t hpx = px * s * s;
   // HR ping-pong buffers: the last upconv output and HR_conv0 output are both full resolution
   for (auto& b : h->hrbuf) rc |= b.ensure(hpx * h->nf_ct() * e8);
+  if (h->arch == 2) {
+    for (int i = 0; i < 8; ++i) rc |= h->pbuf[i].ensure(px * h->nf_ct() * e8);
+    rc |= h->pbuf[8].ensure(px * 32 * e8);
+    for (auto& b : h->paux) rc |= b.ensure(hpx * e8);
+  }
   if (rc) {
     // drop partial allocations so that a retry with a smaller batch starts clean
     h->in_tiles.release();
     h->feat.release();
     for (auto& b : h->xbuf) b.release();
     for (auto& b : h->hrbuf) b.release();
+    for (auto& b : h->pbuf) b.release();
+    for (auto& b : h->paux) b.release();
     return fail(INNFER_E_NOMEM, "workspace allocation failed");
   }
   return 0;
@@ -308,8 +327,132 @@ int forward_tiles_srresnet(innfer_rrdb* h, int B, int hgt, int wid, ChunkView ds
   return run_conv(h, h->hr1, o, B, ch, cw, dst, (h->cfg.out_nc + 7) / 8, last, st);
 }
 
+// PPON.forward (PPON_arch.py:64-76), third output only (out_p; run.py:191-192).  _ResBlock_32 (78-114):
+//   o1 = lrelu(c1(x)); d_k = conv(o1, dilation k); add_k = d_1 + .. + d_{k+1};
+//   out = x + 0.2 * c2(lrelu(cat[d_1, add_1..add_7]))              (c2 is a 1x1 conv over 256 channels)
+// The running sums are the residual epilogue of the dilated convs: conv d_k stores add_{k-1} + d_k twice, raw into a
+// 32-channel scratch (the next conv's residual input) and activated into its slice of the concat buffer.
+// RRBlock_32 (116-127) = three blocks and "*0.2 + x", folded into the third c2's second residual.
+int forward_tiles_ppon(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool compact, cudaStream_t st) {
+  const int nfc = h->nf_ct();
+  int rc;
+  const bool wide = h->cfg.fp16 && wide_enabled();
+  int lvl = 1;
+  auto view = [&](DevBuf& b, int CT, int chunk0) {
+    return wide ? wview(b, CT, chunk0, B, wid, lvl) : ::view(b, CT, chunk0);
+  };
+  DevBuf &F = h->pbuf[0], &T1 = h->pbuf[4], &S = h->pbuf[5], &E1 = h->pbuf[6], &E2 = h->pbuf[7], &CAT = h->pbuf[8];
+  Epilogue plain, act;
+  act.lrelu = true;
+  if (wide) CU_TRY(cudaMemsetAsync(F.p, 0, (size_t)nfc * hgt * wide_cols(B, wid) * 8 * h->esz(), st));
+  if ((rc = run_conv(h, h->fea, ::view(h->in_tiles, h->in_ct(), 0), B, hgt, wid, view(F, nfc, 0), nfc, plain, st))) return rc;
+
+  // one _ResBlock_32: in -> out (+ the RRBlock-level residual for the third block of a RRBlock)
+  auto res_block = [&](const ConvLayer* L, DevBuf& in, DevBuf& out, DevBuf* rrb_in) -> int {
+    int r;
+    if ((r = run_conv(h, L[0], view(in, nfc, 0), B, hgt, wid, view(T1, nfc, 0), nfc, act, st))) return r;
+    for (int k = 0; k < 8; ++k) {
+      Epilogue e;
+      e.lrelu = true;
+      e.act_after_res = true;
+      if (k > 0) {
+        e.res1 = view(S, nfc, 4 * ((k - 1) & 1));
+        e.alpha1 = 1.0f;
+      }
+      if (k < 7) e.raw_out = view(S, nfc, 4 * (k & 1));
+      if ((r = run_conv(h, L[1 + k], view(T1, nfc, 0), B, hgt, wid, view(CAT, 32, 4 * k), 4, e, st))) return r;
+    }
+    Epilogue e2;
+    e2.res1 = view(in, nfc, 0);
+    e2.alpha1 = 0.2f;
+    if (rrb_in) {
+      e2.res2 = view(*rrb_in, nfc, 0);
+      e2.alpha2 = 0.2f;
+    }
+    return run_conv(h, L[9], view(CAT, 32, 0), B, hgt, wid, view(out, nfc, 0), nfc, e2, st);
+  };
+  // a chain of RRBlock_32 starting from `src` (not modified); returns the buffer holding the result
+  auto rr_chain = [&](const ConvLayer* L, int nblocks, DevBuf* src, DevBuf** result) -> int {
+    DevBuf* X[3] = {&h->pbuf[1], &h->pbuf[2], &h->pbuf[3]};
+    DevBuf* cur = src;
+    for (int b = 0; b < nblocks; ++b) {
+      // free rotating buffers: the two that are not `cur`
+      DevBuf* f[2];
+      int n = 0;
+      for (auto* x : X)
+        if (x != cur && n < 2) f[n++] = x;
+      int r;
+      const ConvLayer* Lb = L + (size_t)b * 30;
+      if ((r = res_block(Lb, *cur, *f[0], nullptr))) return r;
+      if ((r = res_block(Lb + 10, *f[0], *f[1], nullptr))) return r;
+      if ((r = res_block(Lb + 20, *f[1], *f[0], cur))) return r;
+      cur = f[0];
+    }
+    *result = cur;
+    return 0;
+  };
+  // reconstruction tail: ups..., HR_conv0, HR_conv1 [* alpha + res]
+  auto tail = [&](const std::vector<ConvLayer>& T, DevBuf& src, const ChunkView* res, float alpha, ChunkView out,
+                  bool out_compact) -> int {
+    int r;
+    lvl = 1;
+    ChunkView cur = view(src, nfc, 0);
+    int ch = hgt, cw = wid, pp = 0;
+    const size_t nups = T.size() - 2;
+    for (size_t i = 0; i < nups; ++i) {
+      lvl *= T[i].up;
+      ChunkView o = view(h->hrbuf[pp], nfc, 0);
+      if ((r = run_conv(h, T[i], cur, B, ch, cw, o, nfc, act, st))) return r;
+      ch *= T[i].up;
+      cw *= T[i].up;
+      cur = o;
+      pp ^= 1;
+    }
+    ChunkView o = view(h->hrbuf[pp], nfc, 0);
+    if ((r = run_conv(h, T[nups], cur, B, ch, cw, o, nfc, act, st))) return r;
+    Epilogue last;
+    last.compact4 = out_compact;
+    if (res) {
+      last.res1 = *res;
+      last.alpha1 = alpha;
+    }
+    r = run_conv(h, T[nups + 1], o, B, ch, cw, out, (h->cfg.out_nc + 7) / 8, last, st);
+    return r;
+  };
+
+  const ConvLayer* L = h->prb.data();
+  DevBuf* res = nullptr;
+  if ((rc = rr_chain(L, h->cfg.nb, &F, &res))) return rc;
+  {  // LR_conv + shortcut -> out_CFEM
+    Epilogue e;
+    e.res1 = view(F, nfc, 0);
+    e.alpha1 = 1.0f;
+    if ((rc = run_conv(h, h->lr_conv, view(*res, nfc, 0), B, hgt, wid, view(E1, nfc, 0), nfc, e, st))) return rc;
+  }
+  const int s = h->cfg.scale;
+  auto hr_view = [&](DevBuf& b) {  // one-chunk tensor at output resolution
+    lvl = s;
+    ChunkView v = view(b, 1, 0);
+    lvl = 1;
+    return v;
+  };
+  const ChunkView out_c = hr_view(h->paux[0]), out_s = hr_view(h->paux[1]);
+  if ((rc = tail(h->ptail[0], E1, nullptr, 1.f, out_c, false))) return rc;               // out_c = CRM(out_CFEM)
+  lvl = 1;
+  if ((rc = rr_chain(L + (size_t)h->cfg.nb * 30, 2, &E1, &res))) return rc;             // SFEM
+  if (res != &E2) {
+    CU_TRY(cudaMemcpyAsync(E2.p, res->p, (size_t)nfc * hgt * (wide ? (size_t)wide_cols(B, wid) : (size_t)B * wid) * 8 * h->esz(),
+                           cudaMemcpyDeviceToDevice, st));
+  }
+  if ((rc = tail(h->ptail[1], E2, &out_c, 1.f, out_s, false))) return rc;               // out_s = SRM(out_SFEM) + out_c
+  lvl = 1;
+  if ((rc = rr_chain(L + (size_t)(h->cfg.nb + 2) * 30, 2, &E2, &res))) return rc;       // PFEM
+  return tail(h->ptail[2], *res, &out_s, h->ppon_alpha, dst, compact);                  // out_p = alpha * PRM(..) + out_s
+}
+
 int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool compact, cudaStream_t st) {
   if (h->arch == 1) return forward_tiles_srresnet(h, B, hgt, wid, dst, compact, st);
+  if (h->arch == 2) return forward_tiles_ppon(h, B, hgt, wid, dst, compact, st);
   const int nfc = h->nf_ct(), catc = h->cat_ct();
   const int gcc = 32 / 8;
   int rc;
@@ -557,6 +700,17 @@ int innfer_srresnet_create(const innfer_srresnet_cfg* cfg, int device, innfer_rr
   return 0;
 }
 
+int innfer_ppon_create(const innfer_ppon_cfg* cfg, int device, innfer_rrdb** out) {
+  if (!cfg || !out) return fail(INNFER_E_INVALID, "null argument");
+  if (cfg->nf != 64) return fail(INNFER_E_UNSUPPORTED, "PPON: nf must be 64 (RRBlock_32 is hard-wired to 64 channels)");
+  innfer_rrdb_cfg base = {cfg->in_nc, cfg->out_nc, cfg->nf, cfg->nb, 32, cfg->scale, 0, cfg->fp16};
+  int rc = innfer_rrdb_create(&base, device, out);
+  if (rc) return rc;
+  (*out)->arch = 2;
+  (*out)->ppon_alpha = cfg->alpha;
+  return 0;
+}
+
 int innfer_rrdb_load(innfer_rrdb* h, const char* key, const float* host_data, const int64_t* shape, int ndim) {
   if (!h || !key || !host_data || !shape || ndim < 1 || ndim > 4) return fail(INNFER_E_INVALID, "bad argument");
   if (h->finalized) return fail(INNFER_E_STATE, "handle already finalized");
@@ -578,6 +732,49 @@ int innfer_rrdb_finalize(innfer_rrdb* h) {
   if ((rc = set_device(h))) return rc;
   const auto& c = h->cfg;
   size_t expected = 0;
+  if (h->arch == 2) {
+    // PPON keys (PPON_arch.py:24-63 through block.sequential's flattening)
+    if ((rc = build_layer(h, h->fea, "CFEM.0", c.nf, c.in_nc, 1))) return rc;
+    expected += 2;
+    const int nblk = (c.nb + 4) * 3;
+    h->prb.resize((size_t)nblk * 10);
+    for (int i = 0; i < c.nb + 4; ++i)
+      for (int r = 0; r < 3; ++r) {
+        char pre[96];
+        if (i < c.nb) snprintf(pre, sizeof pre, "CFEM.1.sub.%d.RB%d", i, r + 1);
+        else if (i < c.nb + 2) snprintf(pre, sizeof pre, "SFEM.%d.RB%d", i - c.nb, r + 1);
+        else snprintf(pre, sizeof pre, "PFEM.%d.RB%d", i - c.nb - 2, r + 1);
+        ConvLayer* L = &h->prb[((size_t)i * 3 + r) * 10];
+        if ((rc = build_layer(h, L[0], std::string(pre) + ".c1", c.nf, c.nf, 1))) return rc;
+        for (int k = 1; k <= 8; ++k)
+          if ((rc = build_layer(h, L[k], std::string(pre) + ".d" + std::to_string(k), c.nf / 2, c.nf, 1, 3, true, k))) return rc;
+        if ((rc = build_layer(h, L[9], std::string(pre) + ".c2", c.nf, c.nf * 4, 1, 1))) return rc;
+        expected += 20;
+      }
+    char key[64];
+    snprintf(key, sizeof key, "CFEM.1.sub.%d", c.nb);
+    if ((rc = build_layer(h, h->lr_conv, key, c.nf, c.nf, 1))) return rc;
+    expected += 2;
+    const char* names[3] = {"CRM", "SRM", "PRM"};
+    for (int t = 0; t < 3; ++t) {
+      h->ptail[t].resize((size_t)h->n_up + 2);
+      for (int i = 0; i < h->n_up; ++i) {
+        snprintf(key, sizeof key, "%s.%d", names[t], 1 + 3 * i);
+        if ((rc = build_layer(h, h->ptail[t][i], key, c.nf, c.nf, h->up_factor))) return rc;
+      }
+      snprintf(key, sizeof key, "%s.%d", names[t], 3 * h->n_up);
+      if ((rc = build_layer(h, h->ptail[t][h->n_up], key, c.nf, c.nf, 1))) return rc;
+      snprintf(key, sizeof key, "%s.%d", names[t], 3 * h->n_up + 2);
+      if ((rc = build_layer(h, h->ptail[t][h->n_up + 1], key, c.out_nc, c.nf, 1))) return rc;
+      expected += 2 * ((size_t)h->n_up + 2);
+    }
+    if (h->params.size() != expected)
+      return fail(INNFER_E_INVALID, "unexpected keys in state dict (" + std::to_string(h->params.size()) +
+                                        " loaded, " + std::to_string(expected) + " expected)");
+    h->params.clear();
+    h->finalized = true;
+    return 0;
+  }
   if ((rc = build_layer(h, h->fea, "model.0", c.nf, c.in_nc, 1))) return rc;
   expected += 2;
   if (h->arch == 1) {

@@ -15,7 +15,7 @@ long long* g_rows_trace = nullptr;  // device buffer of 3072 int64 (innfer_debug
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cout, int Cin, int up,
-                     std::string& err, int ksize) {
+                     std::string& err, int ksize, int dil) {
   // a 1x1 kernel is embedded as the centre tap of a 3x3 one; the tap tables below then keep only
   // taps with a non-zero weight plane, i.e. exactly that centre tap
   std::vector<float> w3;
@@ -32,6 +32,11 @@ int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cou
     err = "kernel size must be 1 or 3";
     return -2;
   }
+  if (dil < 1 || dil > 8 || (dil != 1 && (up != 1 || ksize != 3))) {
+    err = "dilation must be 1..8 and needs a plain 3x3 conv";
+    return -2;
+  }
+  L.dil = dil;
   if (up < 1 || up > 3) {
     err = "unsupported upsample factor (1, 2 or 3 expected)";
     return -2;
@@ -116,7 +121,7 @@ int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cou
   }
   // row-streaming packing (conv_rows.cu): [kslab][dx][kchunk][dy*Cout + co][8]
   std::vector<__half> packed_rows;
-  if (up == 1 && ksize == 3 && (Cout == 32 || Cout == 64)) {
+  if (up == 1 && ksize == 3 && dil == 1 && (Cout == 32 || Cout == 64)) {
     const int NR = 3 * Cout;
     packed_rows.resize((size_t)kslabs * 3 * 2 * NR * 8);
     size_t o = 0;
@@ -221,13 +226,13 @@ void conv_layer_free(ConvLayer& L) {
   L.d_w32 = nullptr;
 }
 
-const CUtensorMap* TmapCache::get(const void* base, int B, int CT, int H, int W, int box_w, int& rc) {
-  auto key = std::make_tuple(base, B, CT, H, W, box_w);
+const CUtensorMap* TmapCache::get(const void* base, int B, int CT, int H, int W, int box_w, int box_h, int& rc) {
+  auto key = std::make_tuple(base, B, CT, H, W, box_w | (box_h << 16));
   auto it = maps_.find(key);
   rc = 0;
   if (it != maps_.end()) return &it->second->m;
   Slot* s = new Slot();
-  rc = encode_act_tmap(&s->m, base, B, CT, H, W, box_w);
+  rc = encode_act_tmap(&s->m, base, B, CT, H, W, box_w, box_h);
   if (rc != 0) {
     delete s;
     return nullptr;
@@ -255,7 +260,8 @@ const CUtensorMap* TmapCache::get_rows(const void* base, int CT, int H, int Wtot
 static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, int H, int W, ChunkView out,
                          int out_nchunks, const Epilogue& ep, int num_sms, cudaStream_t stream) {
   static const int rows_mode = getenv("INNFER_ROWS") ? atoi(getenv("INNFER_ROWS")) : 3;  // bit 0: on, bit 1: Cout = 64 too
-  if (!rows_mode || !in.wide() || !out.wide() || L.d_wrows == nullptr || L.up != 1 || ep.compact4 ||
+  if (!rows_mode || !in.wide() || !out.wide() || L.d_wrows == nullptr || L.up != 1 || L.dil != 1 || ep.compact4 ||
+      ep.act_after_res || ep.raw_out.base ||
       out_nchunks * 8 != L.Cout || in.pitch != out.pitch || in.Wtot != out.Wtot)
     return -100;
   for (const ChunkView* v : {&ep.res1, &ep.res2})
@@ -381,6 +387,13 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
       p.out_ys = (int)(Wo * 4);
       p.out_px = 4;
     }
+    if (ep.raw_out.base) {
+      if (!ep.act_after_res || ep.compact4) return -8;
+      strides(ep.raw_out, p.raw_bs, p.raw_cs, p.raw_ys);
+      p.raw = ep.raw_out.base;
+      p.raw_chunk0 = ep.raw_out.chunk0;
+    }
+    p.act_after_res = ep.act_after_res ? 1 : 0;
     if (ep.res1.base) strides(ep.res1, p.res1_bs, p.res1_cs, p.res1_ys);
     if (ep.res2.base) strides(ep.res2, p.res2_bs, p.res2_cs, p.res2_ys);
   }
@@ -392,7 +405,8 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
   int cols = p.nslots * N, pw = 32;
   while (pw < cols) pw <<= 1;
   p.tmem_cols = pw;
-  const int stage_bytes = conv_tc_a_bytes(J) + conv_tc_w_bytes(N, L.max_taps);
+  p.dil = L.dil;
+  const int stage_bytes = conv_tc_a_bytes(J, L.dil) + conv_tc_w_bytes(N, L.max_taps);
   int S = (232448 - kConvTailBytes) / stage_bytes;
   if (S > 8) S = 8;
   if (S < 2) return -4;
@@ -428,7 +442,7 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
   static const int dbg = getenv("INNFER_DEBUG") ? atoi(getenv("INNFER_DEBUG")) : 64;
   p.debug = dbg;
   int rc = 0;
-  const CUtensorMap* tm = cache.get(in.base, srcB, in.CT, H, srcW, 8 * J + 2, rc);
+  const CUtensorMap* tm = cache.get(in.base, srcB, in.CT, H, srcW, 8 * J + 2 * L.dil, kPatchRows + 2 * L.dil, rc);
   if (!tm) return rc ? rc : -5;
   return launch_conv_tc(tm, p, N, num_sms, stream);
 }

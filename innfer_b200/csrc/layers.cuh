@@ -34,6 +34,7 @@ struct ConvLayer {
   int Cin_pad = 0;         // multiple of 16
   int N = 0;               // padded Cout: 16, 32 or 64
   int up = 1;              // nearest-upsample factor folded in front of the conv (or PixelShuffle factor)
+  int dil = 1;             // dilation (plain 3x3 convs only)
   bool pixel_shuffle = false;  // conv -> PixelShuffle(up) (block.py:333-346): phase = output sub-pixel
   int nphase = 1;
   uint32_t ph_woff[kMaxPhases] = {};
@@ -57,13 +58,15 @@ struct Epilogue {
   ChunkView res1, res2;   // base == nullptr -> unused
   float alpha1 = 1.f, alpha2 = 1.f;
   bool compact4 = false;  // store out channels 0..3 as [tile][H][W][4] (8 bytes per pixel), see ConvTcParams
+  bool act_after_res = false;  // LeakyReLU after the residual adds (PPON running sums) instead of before
+  ChunkView raw_out;      // optional second destination for the pre-activation value (needs act_after_res)
 };
 
 // Build the packed fp16 weights (and phase tables) from OIHW fp32 weights.  `bias` may be null.
 // Returns 0 or a negative error code; `err` receives a message.
 // ksize 3 (default) or 1: a 1x1 conv (ESRGAN+ conv1x1, block.py:390-391) runs as a single centre tap.
 int conv_layer_build(ConvLayer& L, const float* w_oihw, const float* bias, int Cout, int Cin,
-                     int up, std::string& err, int ksize = 3);
+                     int up, std::string& err, int ksize = 3, int dil = 1);
 // conv (Cin -> Cout*r*r) followed by PixelShuffle(r): one 9-tap phase per output sub-pixel (i, j), whose
 // Cout filters are rows c*r*r + i*r + j of the weight tensor; the shuffle becomes output addressing.
 int conv_layer_build_ps(ConvLayer& L, const float* w_oihw, const float* bias, int Cout, int Cin, int r,
@@ -74,7 +77,7 @@ void conv_layer_free(ConvLayer& L);
 class TmapCache {
  public:
   // 5-D map of a [B][CT][H][W][8] tensor (or one wide image, B = 1) with a box of box_w pixels
-  const CUtensorMap* get(const void* base, int B, int CT, int H, int W, int box_w, int& rc);
+  const CUtensorMap* get(const void* base, int B, int CT, int H, int W, int box_w, int box_h, int& rc);
   // wide-layout row-segment map of the row-streaming kernel (box of `kc` chunks)
   const CUtensorMap* get_rows(const void* base, int CT, int H, int Wtot, int kc, int& rc);
   void clear() { maps_.clear(); }

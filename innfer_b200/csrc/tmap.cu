@@ -21,13 +21,13 @@ static EncodeTiledFn resolve_encode() {
   return fn;
 }
 
-int encode_act_tmap(CUtensorMap* out, const void* base, int B, int CT, int H, int W, int box_w) {
+int encode_act_tmap(CUtensorMap* out, const void* base, int B, int CT, int H, int W, int box_w, int box_h) {
   EncodeTiledFn enc = resolve_encode();
   if (!enc) return -1;
   const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)CT, (cuuint64_t)B};
   const cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16,
                                  (cuuint64_t)CT * H * W * 16};
-  const cuuint32_t box[5] = {8, (cuuint32_t)box_w, (cuuint32_t)kHaloRows, 2, 1};
+  const cuuint32_t box[5] = {8, (cuuint32_t)box_w, (cuuint32_t)box_h, 2, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,

@@ -172,3 +172,13 @@ class SRResNetEngine(RRDBEngine):
         c = N.SRResNetCfg(cfg["in_nc"], cfg["out_nc"], cfg["nf"], cfg["nb"], cfg["scale"], mode,
                           float(cfg.get("res_scale", 1.0)), int(self.fp16))
         N.check(self.lib.innfer_srresnet_create(ctypes.byref(c), self.index, ctypes.byref(self._h)))
+
+
+class PPONEngine(RRDBEngine):
+    """Native handle for architectures.PPON_arch.PPON; ``forward`` / ``chop_forward`` return out_p."""
+
+    def _create(self):
+        cfg = self.cfg
+        c = N.PPONCfg(cfg["in_nc"], cfg["out_nc"], cfg["nf"], cfg["nb"], cfg["scale"], float(cfg.get("alpha", 1.0)),
+                      int(self.fp16))
+        N.check(self.lib.innfer_ppon_create(ctypes.byref(c), self.index, ctypes.byref(self._h)))

@@ -121,6 +121,8 @@ class Model:
         with torch.no_grad():
             for i in range(patches.size(0)):
                 pred = self.model(patches[i:i + 1])
+                if self.arch == "ppon":
+                    pred = pred[2]
                 if self.arch == "ts":
                     pred = pred.detach().cpu()
                 outputs.append(pred)
@@ -130,7 +132,8 @@ class Model:
         if self.chop:
             return self.chop_forward(data=data, patch_size=200, step=0.5)
         with torch.no_grad():
-            return self.model(data)
+            out = self.model(data)
+        return out[2] if self.arch == "ppon" else out
 
 
 # ---------------------------------------------------------------------- model path handling

@@ -1,9 +1,9 @@
-"""Network config defaults -- mirror of the reference's utils/defaults.py:3-44 for the ESRGAN
-family (other families are outside the hot-path scope and raise NotImplementedError)."""
+"""Network config defaults -- mirror of the reference's utils/defaults.py:3-44 for the ESRGAN,
+SRResNet and PPON families (the others are outside the hot-path scope and raise NotImplementedError)."""
 
 _RRDB_ALIASES = ("rrdb_net", "esrgan", "esrgan-lite")
 _SRRESNET_ALIASES = ("sr_resnet", "srresnet", "srgan")
-_OTHER_KINDS = ("evsrgan", "mrrdb_net", "mesrgan", "ppon", "pan", "pan_net",
+_OTHER_KINDS = ("evsrgan", "mrrdb_net", "mesrgan", "pan", "pan_net",
                 "unet_net", "unet", "resnet_net", "resnet", "wbcunet", "wbcunet_net")
 
 
@@ -55,6 +55,17 @@ def get_network_G_config(network_G, scale):
             "convtype": opts.pop("convtype", "Conv2D"),
             "finalact": opts.pop("finalact", None),
             "res_scale": opts.pop("res_scale", 1),
+        }
+    if "ppon" in kind:
+        return {
+            "type": "ppon",
+            "in_nc": opts.pop("in_nc", 3),
+            "out_nc": opts.pop("out_nc", 3),
+            "nf": opts.pop("nf", 64),
+            "nb": opts.pop("nb", 24),
+            "upscale": opts.pop("scale", scale),
+            "act_type": opts.pop("net_act", None) or opts.pop("act_type", "leakyrelu"),
+            "alpha": opts.pop("alpha", 1),
         }
     if kind in _OTHER_KINDS or kind.startswith(("unet_", "p2p_", "resnet_", "cg_")):
         raise NotImplementedError(

@@ -196,6 +196,106 @@ def srresnet_forward(sd, x, scale, res_scale=1.0):
         return conv("model.%d" % (4 + 3 * n_up), t)
 
 
+# ----------------------------------------------------------------------------- PPON
+
+
+def ppon_tail_indices(scale):
+    """Flat nn.Sequential indices inside CRM / SRM / PRM: upconv convs, HR_conv0, HR_conv1 (block.py:197-210)."""
+    n_up = {1: 0, 2: 1, 3: 1, 4: 2, 8: 3}[scale]
+    return [1 + 3 * i for i in range(n_up)], 3 * n_up, 3 * n_up + 2
+
+
+def make_ppon_state_dict(scale=4, nb=24, nf=64, in_nc=3, out_nc=3, seed=0, last_bias=0.5):
+    """Default-initialised PPON weights in the construction order of PPON.__init__ (PPON_arch.py:24-48) and
+    _ResBlock_32.__init__ (79-92); the three HR_conv1 biases are set to last_bias / 0 / 0 so that out_p is centred."""
+    torch.manual_seed(seed)
+    sd = OrderedDict()
+
+    def put(name, cout, cin, k=3):
+        w, b = _conv_init(cout, cin, k)
+        sd[name + ".weight"] = w
+        sd[name + ".bias"] = b
+
+    def rrblock(prefix):
+        for r in (1, 2, 3):
+            put("%s.RB%d.c1" % (prefix, r), nf, nf)
+            for d in range(1, 9):
+                put("%s.RB%d.d%d" % (prefix, r, d), nf // 2, nf)
+            put("%s.RB%d.c2" % (prefix, r), nf, nf * 4, 1)
+
+    put("CFEM.0", nf, in_nc)
+    for b in range(nb):
+        rrblock("CFEM.1.sub.%d" % b)
+    put("CFEM.1.sub.%d" % nb, nf, nf)
+    for b in range(2):
+        rrblock("SFEM.%d" % b)
+    for b in range(2):
+        rrblock("PFEM.%d" % b)
+    ups, hr0, hr1 = ppon_tail_indices(scale)
+    for name in ("CRM", "SRM", "PRM"):
+        for i in ups:
+            put("%s.%d" % (name, i), nf, nf)
+    for name in ("CRM", "SRM", "PRM"):
+        put("%s.%d" % (name, hr0), nf, nf)
+        put("%s.%d" % (name, hr1), out_nc, nf)
+    if last_bias is not None:
+        sd["CRM.%d.bias" % hr1].fill_(last_bias)
+    # state_dict() order of the module tree: CFEM, SFEM, PFEM, CRM, SRM, PRM
+    order = [k for p in ("CFEM", "SFEM", "PFEM", "CRM", "SRM", "PRM") for k in sd if k.startswith(p)]
+    return OrderedDict((k, sd[k]) for k in order)
+
+
+def ppon_resblock(sd, prefix, x):
+    """_ResBlock_32.forward (PPON_arch.py:94-114)."""
+    def conv(name, t, dil=1, k=3):
+        return F.conv2d(t, sd["%s.%s.weight" % (prefix, name)], sd["%s.%s.bias" % (prefix, name)],
+                        padding=(k // 2) * dil, dilation=dil)
+    o1 = F.leaky_relu(conv("c1", x), 0.2)
+    parts, run = [], None
+    for d in range(1, 9):
+        t = conv("d%d" % d, o1, d)
+        run = t if run is None else run + t
+        parts.append(run)
+    return x + 0.2 * conv("c2", F.leaky_relu(torch.cat(parts, 1), 0.2), 1, 1)
+
+
+def ppon_rrblock(sd, prefix, x):
+    """RRBlock_32.forward (PPON_arch.py:123-127)."""
+    t = x
+    for r in (1, 2, 3):
+        t = ppon_resblock(sd, "%s.RB%d" % (prefix, r), t)
+    return 0.2 * t + x
+
+
+def ppon_forward(sd, x, scale, alpha=1.0):
+    """PPON.forward (PPON_arch.py:64-76): returns (out_c, out_s, out_p)."""
+    nb = max(int(k.split(".")[3]) for k in sd if k.startswith("CFEM.1.sub.") and k.count(".") == 4)
+    ups, hr0, hr1 = ppon_tail_indices(scale)
+    f = 3 if scale == 3 else 2
+
+    def conv(name, t, act=False):
+        y = F.conv2d(t, sd[name + ".weight"], sd[name + ".bias"], padding=1)
+        return F.leaky_relu(y, 0.2) if act else y
+
+    def tail(name, t):
+        for i in ups:
+            t = conv("%s.%d" % (name, i), F.interpolate(t, scale_factor=float(f), mode="nearest"), True)
+        return conv("%s.%d" % (name, hr1), conv("%s.%d" % (name, hr0), t, True))
+
+    with torch.no_grad():
+        fea = conv("CFEM.0", x)
+        t = fea
+        for b in range(nb):
+            t = ppon_rrblock(sd, "CFEM.1.sub.%d" % b, t)
+        cfem = fea + conv("CFEM.1.sub.%d" % nb, t)
+        out_c = tail("CRM", cfem)
+        sfem = ppon_rrblock(sd, "SFEM.1", ppon_rrblock(sd, "SFEM.0", cfem))
+        out_s = tail("SRM", sfem) + out_c
+        pfem = ppon_rrblock(sd, "PFEM.1", ppon_rrblock(sd, "PFEM.0", sfem))
+        out_p = alpha * tail("PRM", pfem) + out_s
+    return out_c, out_s, out_p
+
+
 # ----------------------------------------------------------------------------- tiling / blending
 
 
@@ -248,11 +348,12 @@ def recompose(patches, height, width, step=0.5, scale=1):
     return out / wsum
 
 
-def chop_forward(sd, x, patch_size=200, step=0.5, forward=None):
+def chop_forward(sd, x, patch_size=200, step=0.5, forward=None, scale=None):
     """Model.chop_forward (run.py:167-202): per-tile forward with batch 1, then recompose."""
     p = min(x.shape[2], x.shape[3], patch_size)
     patches, _, _ = extract_patches(x, p, step)
-    scale = infer_params(sd)["scale"]
+    if scale is None:
+        scale = infer_params(sd)["scale"]
     fwd = forward or (lambda t: rrdbnet_forward(sd, t, scale))
     outs = [fwd(patches[i:i + 1]) for i in range(patches.shape[0])]
     return recompose(torch.cat(outs, 0), x.shape[2], x.shape[3], step=step, scale=scale)

@@ -280,6 +280,35 @@ def stage_steady():
     return True
 
 
+def stage_ppon():
+    """PPON engine vs the oracle (small nets), fp16 and fp32, plus an intermediate check of one residual block."""
+    from innfer_b200.engine import PPONEngine
+    ok = True
+    for scale, nb, hw, fp16 in ((4, 1, (40, 48), True), (2, 2, (36, 44), True), (4, 1, (40, 48), False), (1, 1, (33, 47), True),
+                                (3, 1, (24, 24), True)):
+        sd = O.make_ppon_state_dict(scale=scale, nb=nb, seed=17)
+        eng = PPONEngine.from_state_dict(sd, dict(in_nc=3, out_nc=3, nf=64, nb=nb, scale=scale, alpha=1.0), dev, fp16=fp16)
+        img = np.random.default_rng(18).integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
+        x = O.np2tensor(img)
+        ref = O.ppon_forward(sd, x, scale)[2]
+        y = eng.forward(x.to(dev).half() if fp16 else x.to(dev)).float().cpu()
+        err = (y - ref).abs()
+        du8 = np.abs(O.tensor2np(y).astype(int) - O.tensor2np(ref).astype(int))
+        rel = (err.max() / ref.abs().max()).item()
+        good = du8.max() <= 1 and (fp16 or rel < 1e-4) and bool(torch.isfinite(y).all())
+        ok &= bool(good)
+        print("%s ppon scale=%d nb=%d %s fp16=%d: max_abs=%.3e rel=%.3e u8_maxdiff=%d" % (
+            "PASS" if good else "FAIL", scale, nb, hw, fp16, err.max().item(), rel, du8.max()))
+        yc = eng.chop_forward(x.to(dev).half() if fp16 else x.to(dev), 32, 0.5).float().cpu()
+        refc = O.chop_forward(sd, x, patch_size=32, scale=scale, forward=lambda t: O.ppon_forward(sd, t, scale)[2])
+        d2 = np.abs(O.tensor2np(yc).astype(int) - O.tensor2np(refc).astype(int))
+        good = d2.max() <= 1
+        ok &= bool(good)
+        print("%s ppon chop scale=%d: u8_maxdiff=%d" % ("PASS" if good else "FAIL", scale, d2.max()))
+        eng.close()
+    return ok
+
+
 def stage_pix():
     """HBM-bound kernels at benchmark sizes: image->tiles, blend (+uint8), colour fix (for ncu)."""
     lib = N.load()
@@ -373,6 +402,6 @@ if __name__ == "__main__":
     ap.add_argument("--stage", required=True)
     a = ap.parse_args()
     t0 = time.time()
-    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
+    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "ppon": stage_ppon, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
     print("STAGE %s %s (%.1fs)" % (a.stage, "OK" if ok else "FAILED", time.time() - t0))
     sys.exit(0 if ok else 1)

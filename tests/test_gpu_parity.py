@@ -237,6 +237,43 @@ def test_srresnet_vs_reference_fixture(dev, tmp_path, name, fp16):
     assert np.abs(U.tensor2np(y2).astype(int) - O.tensor2np(ref).astype(int)).max() <= 1
 
 
+@pytest.mark.parametrize("name", ["ppon_s4_nb1_40x48_p32.npz", "ppon_s2_nb2_36x44_p32.npz"])
+@pytest.mark.parametrize("fp16", [True, False])
+def test_ppon_vs_reference_fixture(dev, name, fp16):
+    """PPON: dilated 64->32 convs whose running sums are residual epilogues with a raw and an
+    activated store, 1x1 fusion conv over 256 channels, three reconstruction tails chained by residuals -- through
+    the module mirror on cuda (engine) against the reference fixture."""
+    from innfer_b200 import run as R
+    from innfer_b200.architectures import get_network
+    from innfer_b200.utils import utils as U
+    from innfer_b200.utils.defaults import get_network_G_config
+    g = golden(name)
+    scale, nb = int(g["scale"]), int(g["nb"])
+    sd = O.make_ppon_state_dict(scale=scale, nb=nb, seed=int(g["seed"]))
+    net = get_network(get_network_G_config({"type": "ppon", "nb": nb}, scale)).eval()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+    if fp16:
+        net.half()
+    m = R.Model.__new__(R.Model)
+    m.arch, m.scale, m.model, m.chop = "ppon", scale, net, True
+    img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))
+    x = U.np2tensor(img).to(dev)
+    x = x.half() if fp16 else x
+    y = m.chop_forward(x, patch_size=int(g["patch"]), step=0.5)
+    u8 = U.tensor2np(y)
+    assert np.abs(u8.astype(int) - g["u8"].astype(int)).max() <= 1 and psnr_u8(u8, g["u8"]) >= 50.0
+    if not fp16:
+        assert np.abs(y.cpu().numpy() - g["y"]).max() / np.abs(g["y"]).max() <= 1e-4
+    # un-chopped forward (third output) against the oracle
+    m.chop = False
+    y2 = m(x).float().cpu()
+    ref = O.ppon_forward(sd, U.np2tensor(img), scale)[2]
+    assert np.abs(U.tensor2np(y2).astype(int) - O.tensor2np(ref).astype(int)).max() <= 1
+    if not fp16:
+        assert ((y2 - ref).abs().max() / ref.abs().max()).item() <= 1e-4
+
+
 def test_python_api_model_chain_and_color_fix(dev, tmp_path, monkeypatch):
     """run.Model on cuda (fp16) + chaining + -cf, and the CLI, vs the reference fixture (config 3 shrunk)."""
     import cv2

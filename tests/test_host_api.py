@@ -101,6 +101,29 @@ def test_srresnet_is_detected_and_runs_on_cpu(tmp_path):
     np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)
 
 
+def test_ppon_module_mirror_on_cpu(tmp_path):
+    """The PPON module tree carries the reference's key names and reproduces its three outputs; run.Model probes
+    'CFEM.0.weight' and, like the reference (run.py:157-163), builds the default depth (nb = 24) for it."""
+    g = golden("ppon_s2_nb2_36x44_p32.npz")
+    sd = O.make_ppon_state_dict(scale=2, nb=2, seed=int(g["seed"]))
+    net = get_network(get_network_G_config({"type": "ppon", "nb": 2}, 2)).eval()
+    assert list(net.state_dict().keys()) == list(g["keys"])
+    net.load_state_dict(sd, strict=True)
+    img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))
+    with torch.no_grad():
+        outs = net(U.np2tensor(img))
+    for got, key in zip(outs, ("out_c", "out_s", "out_p")):
+        np.testing.assert_allclose(got.numpy(), g[key], rtol=0, atol=2e-5)
+    m = R.Model.__new__(R.Model)
+    m.arch, m.scale, m.model, m.chop = "ppon", 2, net, True
+    y = m.chop_forward(U.np2tensor(img), patch_size=int(g["patch"]), step=0.5)
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)
+    assert get_network_G_config("ppon", 4) == {"type": "ppon", "in_nc": 3, "out_nc": 3, "nf": 64, "nb": 24, "upscale": 4,
+                                               "act_type": "leakyrelu", "alpha": 1}
+    with pytest.raises(RuntimeError):   # a 2-block checkpoint does not fit the default 24-block network (strict load)
+        R.Model(_save(sd, tmp_path / "2x_ppon.pth"), "infer", 2, device=torch.device("cpu"))
+
+
 def test_infer_params_and_key_mapping(tmp_path):
     g = golden("load_logic.npz")
     for scale, nb in ((1, 2), (2, 3), (4, 23), (8, 1)):
@@ -162,7 +185,7 @@ def test_synth_recipe_matches_reference_init():
 
 def test_unknown_architectures_fail_loudly():
     with pytest.raises(NotImplementedError):
-        get_network({"type": "ppon"})
+        get_network({"type": "pan_net"})
     with pytest.raises(NotImplementedError):
         get_network_G_config({"type": "pan"}, 4)
     with pytest.raises(Exception, match="Could not infer"):

@@ -68,6 +68,24 @@ def test_srresnet_fixture(name):
     np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)
 
 
+@pytest.mark.parametrize("name", ["ppon_s4_nb1_40x48_p32.npz", "ppon_s2_nb2_36x44_p32.npz"])
+def test_ppon_fixture(name):
+    """PPON: oracle weights recipe and forward (third output, run.py:191-192) vs the reference."""
+    g = golden(name)
+    scale = int(g["scale"])
+    sd = O.make_ppon_state_dict(scale=scale, nb=int(g["nb"]), seed=int(g["seed"]))
+    assert list(sd.keys()) == list(g["keys"])
+    np.testing.assert_array_equal(np.array([float(v.double().sum()) for v in sd.values()]), g["wsum"])
+    assert str(g["arch"]) == "ppon"
+    img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))
+    x = O.np2tensor(img)
+    y = O.chop_forward(sd, x, patch_size=int(g["patch"]), scale=scale, forward=lambda t: O.ppon_forward(sd, t, scale)[2])
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)
+    if "out_p" in g.files:
+        for got, key in zip(O.ppon_forward(sd, x, scale), ("out_c", "out_s", "out_p")):
+            np.testing.assert_allclose(got.numpy(), g[key], rtol=0, atol=2e-5)
+
+
 def test_tile_geometry():
     g = golden("tile_geometry.npz")
     for key in g.files:

@@ -47,6 +47,34 @@ def save_model(net, path):
     torch.save(net.state_dict(), path)
 
 
+def ppon_fixtures(td):
+    # ---- G4d: PPON: auto-detected from 'CFEM.0.weight', third output only (run.py:191-192)
+    for scale, nb, (h, w) in ((4, 1, (40, 48)), (2, 2, (36, 44))):
+        torch.manual_seed(17)
+        net = get_network(get_network_G_config({"type": "ppon", "nb": nb}, scale)).eval()
+        _, _, hr1 = O.ppon_tail_indices(scale)
+        with torch.no_grad():
+            net.state_dict()["CRM.%d.bias" % hr1].fill_(0.5)
+        path = os.path.join(td, "%dx_ppon.pth" % scale)
+        save_model(net, path)
+        # Model(...,'infer') keeps the default depth (nb = 24) for ppon (run.py:157-163) and would reject a shallower
+        # checkpoint: wrap the network directly, chop_forward only needs these attributes
+        model = ref_run.Model.__new__(ref_run.Model)
+        model.arch, model.scale, model.model, model.chop, model.device = "ppon", scale, net, True, torch.device("cpu")
+        img = image(18, h, w)
+        y = model.chop_forward(ref_utils.np2tensor(img), patch_size=32, step=0.5)
+        with torch.no_grad():
+            oc, os_, op = net(ref_utils.np2tensor(img))
+        np.savez_compressed(os.path.join(OUT, "ppon_s%d_nb%d_%dx%d_p32.npz" % (scale, nb, h, w)), img_seed=18,
+                            h=h, w=w, patch=32, seed=17, scale=scale, nb=nb, arch=model.arch,
+                            keys=np.array(list(net.state_dict().keys())),
+                            wsum=np.array([float(v.double().sum()) for v in net.state_dict().values()]),
+                            y=y.numpy().astype(np.float32), u8=ref_utils.tensor2np(y.detach()),
+                            **({} if scale == 4 else dict(out_c=oc.numpy().astype(np.float32),
+                                                          out_s=os_.numpy().astype(np.float32),
+                                                          out_p=op.numpy().astype(np.float32))))
+
+
 def main():
     torch.set_num_threads(8)
     # ---- G1: weights recipe: the oracle's make_state_dict must reproduce the reference init.
@@ -132,6 +160,8 @@ def main():
                                 wsum=np.array([float(v.double().sum()) for v in net.state_dict().values()]),
                                 y=y.numpy().astype(np.float32), u8=ref_utils.tensor2np(y.detach()))
 
+        ppon_fixtures(td)
+
     # ---- G5: tile geometry of extract_patches_2d for a list of sizes
     geo = {}
     for (h, w, p) in ((1080, 1920, 200), (720, 1280, 200), (512, 512, 200), (64, 64, 200), (256, 320, 200),
@@ -203,4 +233,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "ppon":
+        torch.set_num_threads(8)
+        with tempfile.TemporaryDirectory() as _td:
+            ppon_fixtures(_td)
+    else:
+        main()
