@@ -309,6 +309,31 @@ def stage_ppon():
     return ok
 
 
+def stage_ppon_time():
+    """PPON at the reference's default depth (nb = 24) on a 1920x1080 frame: device time per frame."""
+    from innfer_b200.engine import PPONEngine
+    sd = O.make_ppon_state_dict(scale=4, nb=24, seed=0)
+    eng = PPONEngine.from_state_dict(sd, dict(in_nc=3, out_nc=3, nf=64, nb=24, scale=4, alpha=1.0), dev, fp16=True)
+    H, W = 1080, 1920
+    din = torch.from_numpy(np.random.default_rng(0).integers(0, 256, (H, W, 3), dtype=np.uint8)).to(dev)
+    dout = torch.empty(4 * H, 4 * W, 3, dtype=torch.uint8, device=dev)
+    mac = 9 * 3 * 64 + 28 * 3 * (9 * 64 * 64 + 8 * 9 * 64 * 32 + 256 * 64) + 9 * 64 * 64 \
+        + 3 * (4 * 9 * 64 * 64 + 16 * 9 * 64 * 64 + 16 * 9 * 64 * 64 + 16 * 9 * 64 * 3)
+    flop = 190 * 200 * 200 * 2.0 * mac
+    for it in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.upscale_u8_device(din, 200, 0.5, out=dout)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print("ppon 1080p nb=24 iter=%d: %.1f ms  %.1f out-Mpix/s  %.1f TFLOP/s (%.1f TFLOP per frame)" %
+              (it, ms, 16 * H * W / ms / 1e3, flop / ms / 1e9, flop / 1e12))
+    print("out mean", dout.float().mean().item(), "launches", N.kernel_launches())
+    eng.close()
+    return True
+
+
 def stage_pix():
     """HBM-bound kernels at benchmark sizes: image->tiles, blend (+uint8), colour fix (for ncu)."""
     lib = N.load()
@@ -402,6 +427,6 @@ if __name__ == "__main__":
     ap.add_argument("--stage", required=True)
     a = ap.parse_args()
     t0 = time.time()
-    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "ppon": stage_ppon, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
+    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "ppon": stage_ppon, "ppon_time": stage_ppon_time, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
     print("STAGE %s %s (%.1fs)" % (a.stage, "OK" if ok else "FAILED", time.time() - t0))
     sys.exit(0 if ok else 1)
