@@ -163,6 +163,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       const int ntaps = plain3x3 ? 9 : (int)p.ph_ntaps[c.phase];
       const uint32_t set = it & 1u;
       const uint32_t acc0 = tmem_base + set * (uint32_t)(J * N);
+      // halo-tile offsets of this phase's taps (16-byte units), once per tile
+      uint32_t aoff[kMaxTaps];
+      if (!plain3x3) {
+#pragma unroll
+        for (int tp = 0; tp < kMaxTaps; ++tp)
+          aoff[tp] = (uint32_t)p.tap_hy[c.phase][tp] * a_sbo + p.tap_hx[c.phase][tp];
+      }
       for (int ks = 0; ks < p.kslabs; ++ks, ++stage_i) {
         // stage stage_i is ready when the scout has seen its TMA data (and, for the first stage of a
         // tile, the accumulator set drained by the epilogue); the count is re-read only when needed
@@ -216,16 +223,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
               }
             }
           }
+        } else if (N == 64 && (p.debug & 64)) {
+          // phase-folded / pixel-shuffle / 1x1 convs (1..9 taps from the phase's table), weight-stationary order
+          if (leader) {
+#pragma unroll
+            for (int tp = 0; tp < kMaxTaps; ++tp) {
+              if (tp < ntaps) {
+                const uint64_t bd = make_desc64(b_lo + tp * tap_stride, b_hi);
+                const uint32_t at = a_lo + aoff[tp];
+                const uint32_t accf = tp == 0 ? first : 1u;
+                if (tp & 1) {
+                  umma_f16_ws<1, true>(acc0, make_desc64(at, a_hi), bd, idesc, accf);
+                  for (int j = 1; j < c.jeff; ++j)
+                    umma_f16_ws<1, false>(acc0 + (uint32_t)(j * N), make_desc64(at + 8u * j, a_hi), bd, idesc, accf);
+                } else {
+                  umma_f16_ws<0, true>(acc0, make_desc64(at, a_hi), bd, idesc, accf);
+                  for (int j = 1; j < c.jeff; ++j)
+                    umma_f16_ws<0, false>(acc0 + (uint32_t)(j * N), make_desc64(at + 8u * j, a_hi), bd, idesc, accf);
+                }
+              }
+            }
+          }
         } else {
           for (int j = 0; j < c.jeff; ++j) {
             const uint32_t acc = acc0 + (uint32_t)(j * N);
             const uint32_t aj = a_lo + 8u * j;
-#pragma unroll 1
-            for (int tp = 0; tp < ntaps; ++tp) {
-              const uint32_t aoff = (uint32_t)p.tap_hy[c.phase][tp] * a_sbo + p.tap_hx[c.phase][tp];
-              if (leader)
-                umma_f16_ss(acc, make_desc64(aj + aoff, a_hi), make_desc64(b_lo + tp * tap_stride, b_hi), idesc,
-                            tp == 0 ? first : 1u);
+            if (leader) {
+#pragma unroll
+              for (int tp = 0; tp < kMaxTaps; ++tp)
+                if (tp < ntaps)
+                  umma_f16_ss(acc, make_desc64(aj + aoff[tp], a_hi), make_desc64(b_lo + tp * tap_stride, b_hi), idesc,
+                              tp == 0 ? first : 1u);
             }
           }
         }

@@ -52,6 +52,7 @@ struct ConvTcParams {
   int stages;      // smem pipeline depth
   int nslots;      // TMEM accumulator slots of N columns: 2*J (two sets of J, alternate tiles)
   int tmem_cols;   // power of two >= nslots*N
+  long long* trace;  // debugging: clock64 samples of CTA 0 (conv_up.cu, -DINNFER_ROWS_TRACE builds), or null
   int debug;       // bit0: skip TMA loads (timing experiments only, garbage results)
   int dil;         // dilation of a plain 3x3 conv (PPON's d1..d8, block.py:364-366): taps at (hy*dil, hx*dil) of
                    // a (16 + 2*dil) x (8J + 2*dil) halo tile; 1 for every other conv
@@ -101,6 +102,10 @@ struct ConvTcParams {
 // Host-side launcher (conv_tc.cu). Returns cudaError_t as int.
 int launch_conv_tc(const CUtensorMap* tmap_in, const ConvTcParams& p, int N, int num_sms,
                    cudaStream_t stream);
+// x2 upsample-folded conv, all four phases per source-tile visit, resident weights (conv_up.cu); N = 64 only.
+int launch_conv_up(const CUtensorMap* tmap_in, const ConvTcParams& p, int num_sms, cudaStream_t stream);
+int conv_up_weight_bytes(int kslabs);
+int conv_up_stage_bytes();
 // Bytes of dynamic smem / stage geometry helpers shared by host and device.
 __host__ __device__ inline int conv_tc_a_bytes(int J, int dil) {
   int b = 2 * (kPatchRows + 2 * dil) * (8 * J + 2 * dil) * 16;

@@ -1,0 +1,313 @@
+// upconv_block (block.py:348-361: nearest Upsample(x2) + 3x3 conv + LeakyReLU) with all four output phases
+// computed in ONE visit of a source tile.
+//
+// The generic 9-tap kernel (conv_tc.cu) treats every output phase (a, b) of the folded conv as a tile of its own:
+// the source halo tile is fetched four times and the phase's weights travel with every pipeline stage, 11x the
+// source bytes in L2 -> shared-memory traffic (ncu: 15 GB for the second upconv of a 63-tile batch) and 20 % tensor
+// pipe.  Here a CTA tile is 16 x 8 source pixels; per 16-channel slab the (18 x 10) halo tile is loaded once and the
+// 4 phases x 4 folded taps issue 16 MMAs (M = 128, N = 64) into four TMEM accumulators (one per phase); the folded
+// weights of the whole conv (4 phases x Cin/16 slabs x 4 taps x 2 KB = 128 KB for 64 -> 64) stay resident in shared
+// memory.  Two accumulator sets (2 x 4 x 64 = 512 TMEM columns) alternate between tiles so that the epilogue -- phase
+// (a, b) of source pixel (y, x) goes to output pixel (2y + a, 2x + b) -- overlaps the next tile's MMAs.
+//
+// Same conventions as conv_tc.cu: planar-chunk fp16 tensors, tiled or wide source (separator columns skipped /
+// stored as zeros), generic destination strides, producer / issuer / 8 epilogue warps / scout.
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+#ifdef INNFER_ROWS_TRACE
+#define UP_TRACE(...) __VA_ARGS__
+#else
+#define UP_TRACE(...)
+#endif
+
+namespace innfer {
+
+namespace {
+
+constexpr int kUpN = 64;
+constexpr int kUpPhases = 4, kUpTaps = 4;
+constexpr int kUpWh = 10, kUpRh = kPatchRows + 2;            // halo tile of a 16 x 8 patch
+constexpr int kUpABytes = 2 * kUpRh * kUpWh * 16;            // 5760 B per 16-channel slab (multiple of 128)
+constexpr uint32_t kUpTapUnits = 2 * kUpN;                   // 16-byte units per (phase, slab, tap) weight block
+constexpr int kUpThreads = 352;                              // producer, issuer, 8 epilogue warps, scout
+constexpr int kUpScoutWarp = 10;
+
+struct UpTile {
+  int b, y0, x0;
+};
+
+// tiles in (image, band, column-patch) order, column-patch fastest
+struct UpIter {
+  long long t, stride, total;
+  int cps, bands;
+  __device__ __forceinline__ void init(const ConvTcParams& p) {
+    cps = p.cps;
+    bands = p.bands;
+    total = (long long)p.B * bands * cps;
+    t = blockIdx.x;
+    stride = gridDim.x;
+  }
+  __device__ __forceinline__ bool valid() const { return t < total; }
+  __device__ __forceinline__ void advance() { t += stride; }
+  __device__ __forceinline__ UpTile coord() const {
+    UpTile c;
+    const long long r = t / cps;
+    c.x0 = (int)(t - r * cps) * 8;
+    c.b = (int)(r / bands);
+    c.y0 = (int)(r - (long long)c.b * bands) * kPatchRows;
+    return c;
+  }
+};
+
+__global__ void __launch_bounds__(kUpThreads, 1)
+conv_up_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const uint32_t w_total = (uint32_t)kUpPhases * p.kslabs * kUpTaps * kUpTapUnits * 16u;
+
+  uint8_t* bar_base = smem + w_total + (size_t)S * kUpABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tfull_bar = empty_bar + S;
+  uint64_t* set_bar = tfull_bar + 2;
+  uint64_t* wfull_bar = set_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
+  volatile uint32_t* ready_cnt = tmem_slot + 1;
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_in);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&tfull_bar[i]), 1);
+    for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&set_bar[i]), 8);
+    mbar_init(smem_u32(wfull_bar), 1);
+    *ready_cnt = 0u;
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < kUpPhases * kUpN; i += blockDim.x) s_bias[i] = p.bias[i];
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512u);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t w_base = smem_u32(smem);
+  const uint32_t ring_base = w_base + w_total;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t wb = smem_u32(wfull_bar);
+      mbar_expect_tx(wb, w_total);
+      for (uint32_t off = 0; off < w_total; off += 32768u) {
+        const uint32_t n = (w_total - off) < 32768u ? (w_total - off) : 32768u;
+        bulk_load(w_base + off, reinterpret_cast<const uint8_t*>(p.w) + off, n, wb);
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      UpIter ti;
+      ti.init(p);
+      for (; ti.valid(); ti.advance()) {
+        const UpTile c = ti.coord();
+        for (int ks = 0; ks < p.kslabs; ++ks) {
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, (uint32_t)kUpABytes);
+          tma_load_5d(ring_base + (uint32_t)s * kUpABytes, &tmap_in, fb, 0, c.x0 - 1, c.y0 - 1, p.in_chunk0 + 2 * ks, c.b);
+          if (++s == S) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (no mbarrier waits: see the scout)
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_f16(kUpN);
+    constexpr uint32_t a_lbo = kUpRh * kUpWh;
+    constexpr uint32_t a_hi = (uint32_t)kUpWh | (1u << 14);      // SBO = one halo-tile row
+    constexpr uint32_t b_hi = 8u | (1u << 14);
+    const uint32_t b_lo0 = ((w_base & 0x3FFFFu) >> 4) | ((uint32_t)kUpN << 16);
+    const uint32_t ph_units = (uint32_t)p.kslabs * kUpTaps * kUpTapUnits;   // weight units per phase
+    uint32_t aoff[kUpPhases][kUpTaps];
+#pragma unroll
+    for (int ph = 0; ph < kUpPhases; ++ph)
+#pragma unroll
+      for (int tp = 0; tp < kUpTaps; ++tp) aoff[ph][tp] = (uint32_t)p.tap_hy[ph][tp] * kUpWh + p.tap_hx[ph][tp];
+    const uint32_t ready_addr = smem_u32((const void*)ready_cnt);
+    uint32_t ready = 0, stage_i = 0, it = 0;
+    int s = 0;
+    mbar_wait(smem_u32(wfull_bar), 0u);
+    UpIter ti;
+    ti.init(p);
+    for (; ti.valid(); ti.advance(), ++it) {
+      const uint32_t set = it & 1u;
+      const uint32_t acc0 = tmem_base + set * (uint32_t)(kUpPhases * kUpN);
+      for (int ks = 0; ks < p.kslabs; ++ks, ++stage_i) {
+        UP_TRACE(if (p.trace && blockIdx.x == 0 && lane == 0 && stage_i < 256) p.trace[stage_i * 4 + 0] = clock64());
+        if (ready <= stage_i) {
+          uint32_t spins = 0;
+          do {
+            asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(ready) : "r"(ready_addr) : "memory");
+            if (++spins > (1u << 26)) __trap();
+          } while (ready <= stage_i);
+          tc_fence_after();
+        }
+        UP_TRACE(if (p.trace && blockIdx.x == 0 && lane == 0 && stage_i < 256) p.trace[stage_i * 4 + 1] = clock64());
+        const uint32_t sa = ring_base + (uint32_t)s * kUpABytes;
+        const uint32_t a_lo = ((sa & 0x3FFFFu) >> 4) | (a_lbo << 16);
+        const uint32_t b_lo = b_lo0 + (uint32_t)ks * (kUpTaps * kUpTapUnits);
+        const uint32_t first = ks != 0 ? 1u : 0u;
+        if (leader) {
+#pragma unroll
+          for (int ph = 0; ph < kUpPhases; ++ph)
+#pragma unroll
+            for (int tp = 0; tp < kUpTaps; ++tp)
+              umma_f16_ss(acc0 + (uint32_t)(ph * kUpN), make_desc64(a_lo + aoff[ph][tp], a_hi),
+                          make_desc64(b_lo + (uint32_t)ph * ph_units + (uint32_t)tp * kUpTapUnits, b_hi), idesc,
+                          tp == 0 ? first : 1u);
+          umma_commit(smem_u32(&empty_bar[s]));
+        }
+        __syncwarp();
+        UP_TRACE(if (p.trace && blockIdx.x == 0 && lane == 0 && stage_i < 256) p.trace[stage_i * 4 + 2] = clock64());
+        if (++s == S) s = 0;
+      }
+      if (leader) umma_commit(smem_u32(&tfull_bar[set]));
+      __syncwarp();
+    }
+  } else if (warp == kUpScoutWarp) {
+    // ------------------------------------------------------------ scout: waits for the issuer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0, it = 0, done = 0;
+      const uint32_t ready_addr = smem_u32((const void*)ready_cnt);
+      UpIter ti;
+      ti.init(p);
+      for (; ti.valid(); ti.advance(), ++it) {
+        mbar_wait(smem_u32(&set_bar[it & 1u]), ((it >> 1) & 1u) ^ 1u);
+        for (int ks = 0; ks < p.kslabs; ++ks) {
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          if (++s == S) {
+            s = 0;
+            ph ^= 1u;
+          }
+          ++done;
+          asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(ready_addr), "r"(done) : "memory");
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int m = q * 32 + lane;
+    const int r = m >> 3, cc = m & 7;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    constexpr int NCH = kUpN / 8;
+    float bias[kUpN];   // the four phases of an upsample-folded conv share one bias vector
+#pragma unroll
+    for (int i = 0; i < kUpN; ++i) bias[i] = s_bias[i];
+    const bool lrelu = p.lrelu != 0;
+    const float slope = p.slope;
+    const int nchunks = p.out_nchunks;
+    uint32_t it = 0;
+    UpIter ti;
+    ti.init(p);
+    for (; ti.valid(); ti.advance(), ++it) {
+      const UpTile c = ti.coord();
+      const int y = c.y0 + r, x = c.x0 + cc;
+      const bool inside = (y < p.H) && (x < p.W);
+      int img = c.b, xi = x;
+      bool valid = inside;
+      if (p.sep_pitch) {
+        img = (int)__umulhi((uint32_t)x, p.sep_magic);
+        xi = x - img * p.sep_pitch;
+        valid = inside && (img < p.sep_nimg) && (xi < p.sep_w);
+      }
+      mbar_wait(smem_u32(&tfull_bar[it & 1u]), (it >> 1) & 1u);
+      tc_fence_after();
+      UP_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < 64) p.trace[2048 + it * 2] = clock64());
+      // Eight epilogue warps: two per TMEM lane quarter, `half` takes the output rows 2y + half, i.e. phases
+      // (half, 0) and (half, 1).  (The epilogue is instruction-bound here: a tile has 9/4 of the outputs per MMA of a
+      // plain 3x3 conv; with four warps it took 7300 cycles per tile against 3000 cycles of MMAs.)
+#pragma unroll 1
+      for (int b = 0; b < 2; ++b) {
+        const int ph = 2 * half + b;
+        const uint32_t tacc = tmem_base + lane_base + (uint32_t)(((it & 1u) * kUpPhases + ph) * kUpN);
+        uint32_t v[kUpN];
+#pragma unroll
+        for (int g = 0; g < kUpN / 16; ++g) tmem_ld16(tacc + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[g * 16]));
+        tmem_ld_wait();
+        if (b == 1) {   // this warp's half of the set is in registers: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&set_bar[it & 1u]));
+          UP_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < 64) p.trace[2048 + it * 2 + 1] = clock64());
+        }
+        const int oy = 2 * y + half, ox = 2 * xi + b;
+        __half* op = p.out + (size_t)img * p.out_bs + (size_t)p.out_chunk0 * p.out_cs + (size_t)oy * p.out_ys + (size_t)ox * 8;
+        if (valid) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            if (ch < nchunks) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float t = __uint_as_float(v[ch * 8 + e]) + bias[ch * 8 + e];
+                if (lrelu) t = t > 0.f ? t : t * slope;
+                f[e] = t;
+              }
+              uint4 o;
+              const __half2 h0 = __floats2half2_rn(f[0], f[1]);
+              const __half2 h1 = __floats2half2_rn(f[2], f[3]);
+              const __half2 h2 = __floats2half2_rn(f[4], f[5]);
+              const __half2 h3 = __floats2half2_rn(f[6], f[7]);
+              o.x = *reinterpret_cast<const uint32_t*>(&h0);
+              o.y = *reinterpret_cast<const uint32_t*>(&h1);
+              o.z = *reinterpret_cast<const uint32_t*>(&h2);
+              o.w = *reinterpret_cast<const uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(op + (size_t)ch * p.out_cs) = o;
+            }
+          }
+        } else if (inside && p.out_zero_sep) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch)
+            if (ch < p.out_nchunks) *reinterpret_cast<uint4*>(op + (size_t)ch * p.out_cs) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+}  // namespace
+
+int conv_up_weight_bytes(int kslabs) { return kUpPhases * kslabs * kUpTaps * (int)kUpTapUnits * 16; }
+int conv_up_stage_bytes() { return kUpABytes; }
+
+int launch_conv_up(const CUtensorMap* tmap_in, const ConvTcParams& p, int num_sms, cudaStream_t stream) {
+  const size_t smem_bytes = (size_t)conv_up_weight_bytes(p.kslabs) + (size_t)p.stages * kUpABytes + kConvTailBytes;
+  cudaError_t e = cudaFuncSetAttribute(conv_up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) return (int)e;
+  const long long tiles = (long long)p.B * p.bands * p.cps;
+  const int grid = tiles < num_sms ? (int)tiles : num_sms;
+  conv_up_kernel<<<grid, kUpThreads, smem_bytes, stream>>>(*tmap_in, p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace innfer

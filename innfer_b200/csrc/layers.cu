@@ -442,6 +442,23 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
   static const int dbg = getenv("INNFER_DEBUG") ? atoi(getenv("INNFER_DEBUG")) : 64;
   p.debug = dbg;
   int rc = 0;
+  {
+    // x2 upconv: all four phases per tile visit with resident weights (conv_up.cu) when they fit
+    static const int up_mode = getenv("INNFER_UP") ? atoi(getenv("INNFER_UP")) : 1;
+    bool four = L.up == 2 && !L.pixel_shuffle && N == 64 && L.nphase == 4;
+    for (int i = 0; i < 4 && four; ++i) four = L.ph_ntaps[i] == 4;
+    const int wb = conv_up_weight_bytes(p.kslabs);
+    int Su = (232448 - kConvTailBytes - wb) / conv_up_stage_bytes();
+    if (up_mode && four && !ep.res1.base && !ep.res2.base && !ep.compact4 && !ep.raw_out.base && Su >= 4) {
+      p.J = 1;
+      p.trace = g_rows_trace;
+      p.cps = (srcW + 7) / 8;
+      p.stages = Su > 12 ? 12 : Su;
+      const CUtensorMap* tmu = cache.get(in.base, srcB, in.CT, H, srcW, 10, kPatchRows + 2, rc);
+      if (!tmu) return rc ? rc : -5;
+      return launch_conv_up(tmu, p, num_sms, stream);
+    }
+  }
   const CUtensorMap* tm = cache.get(in.base, srcB, in.CT, H, srcW, 8 * J + 2 * L.dil, kPatchRows + 2 * L.dil, rc);
   if (!tm) return rc ? rc : -5;
   return launch_conv_tc(tm, p, N, num_sms, stream);

@@ -334,6 +334,27 @@ def stage_ppon_time():
     return True
 
 
+def stage_trace_up():
+    """clock64 trace of CTA 0 of the last conv_up launch of a frame (needs an INNFER_TRACE_BUILD=1 build)."""
+    lib = N.load()
+    buf = torch.zeros(3072 + 148 * 8, dtype=torch.int64, device=dev)
+    lib.innfer_debug_set_trace(ctypes.c_void_p(buf.data_ptr()))
+    os.environ["INNFER_TRACE_NCH"] = "999"
+    stage_prof()
+    lib.innfer_debug_set_trace(None)
+    t = buf.cpu().numpy()
+    m = t[:1024].reshape(256, 4)
+    e = t[2048:2048 + 128].reshape(64, 2)
+    t0 = m[0, 0]
+    print("stage: start | poll | issue | dt | (every 4th stage: epilogue tfull seen, set released)")
+    for i in range(8, 48):
+        extra = ""
+        if i % 4 == 0:
+            extra = " | tile %d epi tfull %d released %d" % (i // 4, e[i // 4, 0] - t0, e[i // 4, 1] - t0)
+        print("%3d: %8d %5d %5d | %5d%s" % (i, m[i, 0] - t0, m[i, 1] - m[i, 0], m[i, 2] - m[i, 1], m[i, 0] - m[i - 1, 0], extra))
+    return True
+
+
 def stage_pix():
     """HBM-bound kernels at benchmark sizes: image->tiles, blend (+uint8), colour fix (for ncu)."""
     lib = N.load()
@@ -427,6 +448,6 @@ if __name__ == "__main__":
     ap.add_argument("--stage", required=True)
     a = ap.parse_args()
     t0 = time.time()
-    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "ppon": stage_ppon, "ppon_time": stage_ppon_time, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
+    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "trace_up": stage_trace_up, "ppon": stage_ppon, "ppon_time": stage_ppon_time, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
     print("STAGE %s %s (%.1fs)" % (a.stage, "OK" if ok else "FAILED", time.time() - t0))
     sys.exit(0 if ok else 1)
