@@ -300,7 +300,6 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     const int grp = (warp - 2) >> 2;                     // which half of the output channels
     const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
     const float* bias = s_bias + grp * CH;
-    const bool nostore = (p.debug & 128) != 0;
     int slot = 0;
     uint32_t use = 0;
     ROWS_TRACE(int ecount = 0);
@@ -315,9 +314,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       const bool real = in_range && (int)b < p.nimg && xi < p.Wimg;   // else separator column: zeros
       const size_t col = (size_t)(xw < 0 ? 0 : xw) * 8;
       __half* const obase = p.out + (size_t)(p.out_chunk0 + grp * (CH / 8)) * p.out_cs + col;
-      const bool noside = (p.debug & 256) != 0;   // timing experiments only
-      const __half* const r1base = (RES && p.res1 && !noside) ? p.res1 + (size_t)(p.res1_chunk0 + grp * (CH / 8)) * p.out_cs + col : nullptr;
-      const __half* const r2base = (RES && p.res2 && !noside) ? p.res2 + (size_t)(p.res2_chunk0 + grp * (CH / 8)) * p.out_cs + col : nullptr;
+      const __half* const r1base = (RES && p.res1) ? p.res1 + (size_t)(p.res1_chunk0 + grp * (CH / 8)) * p.out_cs + col : nullptr;
+      const __half* const r2base = (RES && p.res2) ? p.res2 + (size_t)(p.res2_chunk0 + grp * (CH / 8)) * p.out_cs + col : nullptr;
       float accA[CH], accB[CH];
 #pragma unroll
       for (int c = 0; c < CH; ++c) accA[c] = accB[c] = 0.f;
@@ -333,7 +331,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         }
       };
       auto store_row = [&](int y, const float (&o)[CH]) {
-        if (!in_range || nostore) return;
+        if (!in_range) return;
         const size_t ro = (size_t)y * p.out_ys;
         __half* op = obase + ro;
 #pragma unroll
@@ -461,7 +459,7 @@ int launch_rows_res(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num
 template <int COUT, int KSLABS>
 int launch_rows_impl(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num_sms, cudaStream_t stream) {
   // the residual-free variant (conv1..conv4 of the plain net) keeps its epilogue free of the side-input code
-  return (p.res1 || p.res2 || (p.debug & 512)) ? launch_rows_res<COUT, KSLABS, true>(tmap_in, p, num_sms, stream)
+  return (p.res1 || p.res2) ? launch_rows_res<COUT, KSLABS, true>(tmap_in, p, num_sms, stream)
                             : launch_rows_res<COUT, KSLABS, false>(tmap_in, p, num_sms, stream);
 }
 

@@ -34,7 +34,6 @@ struct ConvRowsParams {
   const float* bias;
   int lrelu;
   float slope;
-  int debug;
   long long* trace;      // debugging: clock64 samples of CTA 0 (see tests/gpu_bringup.py --stage trace), or null
 };
 

@@ -115,16 +115,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
           const uint32_t fb = smem_u32(&full_bar[s]);
           const uint32_t dstA = smem_base + (uint32_t)s * stage_bytes;
-          if (p.debug & 1) {
-            mbar_arrive(fb);
-          } else if (p.debug & 2) {
-            mbar_expect_tx(fb, wb);
-            bulk_load(dstA + a_bytes, wsrc + (size_t)ks * wb, wb, fb);
-          } else {
-            mbar_expect_tx(fb, (uint32_t)(2 * Rh * Wh * 16) + wb);
-            tma_load_5d(dstA, &tmap_in, fb, 0, c.x0 - p.dil, c.y0 - p.dil, p.in_chunk0 + 2 * ks, c.b);
-            bulk_load(dstA + a_bytes, wsrc + (size_t)ks * wb, wb, fb);
-          }
+          mbar_expect_tx(fb, (uint32_t)(2 * Rh * Wh * 16) + wb);
+          tma_load_5d(dstA, &tmap_in, fb, 0, c.x0 - p.dil, c.y0 - p.dil, p.in_chunk0 + 2 * ks, c.b);
+          bulk_load(dstA + a_bytes, wsrc + (size_t)ks * wb, wb, fb);
           if (++s == S) {
             s = 0;
             ph ^= 1u;
@@ -185,7 +178,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         const uint32_t a_lo = ((sa & 0x3FFFFu) >> 4) | (a_lbo << 16);
         const uint32_t b_lo = (((sa + a_bytes) & 0x3FFFFu) >> 4) | (b_lbo << 16);
         const uint32_t first = ks != 0 ? 1u : 0u;
-        if (N == 64 && ntaps == 9 && (p.debug & 64)) {
+        if (N == 64 && ntaps == 9) {
           // weight-stationary order: tap outer, sub-patch inner; the tap's B tile is read from shared
           // memory once (collector fill) and reused for the other sub-patches
           if (leader) {
@@ -223,7 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
               }
             }
           }
-        } else if (N == 64 && (p.debug & 64)) {
+        } else if (N == 64) {
           // phase-folded / pixel-shuffle / 1x1 convs (1..9 taps from the phase's table), weight-stationary order
           if (leader) {
 #pragma unroll

@@ -53,7 +53,6 @@ struct ConvTcParams {
   int nslots;      // TMEM accumulator slots of N columns: 2*J (two sets of J, alternate tiles)
   int tmem_cols;   // power of two >= nslots*N
   long long* trace;  // debugging: clock64 samples of CTA 0 (conv_up.cu, -DINNFER_ROWS_TRACE builds), or null
-  int debug;       // bit0: skip TMA loads (timing experiments only, garbage results)
   int dil;         // dilation of a plain 3x3 conv (PPON's d1..d8, block.py:364-366): taps at (hy*dil, hx*dil) of
                    // a (16 + 2*dil) x (8J + 2*dil) halo tile; 1 for every other conv
   // destination

@@ -307,8 +307,6 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   p.res2 = ep.res2.base;
   p.res2_chunk0 = ep.res2.chunk0;
   p.alpha2 = ep.alpha2;
-  static const int dbg = getenv("INNFER_ROWS_DBG") ? atoi(getenv("INNFER_ROWS_DBG")) : 0;
-  p.debug = dbg;
   static const int trace_nch = getenv("INNFER_TRACE_NCH") ? atoi(getenv("INNFER_TRACE_NCH")) : 0;
   p.trace = (trace_nch == nch) ? g_rows_trace : nullptr;
   int rc = 0;
@@ -438,9 +436,6 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
       p.tap_hx[i][t] = L.tap_hx[i][t];
     }
   }
-  // bit 6 (default on): weight-stationary MMA order for the 9-tap N=64 convs
-  static const int dbg = getenv("INNFER_DEBUG") ? atoi(getenv("INNFER_DEBUG")) : 64;
-  p.debug = dbg;
   int rc = 0;
   {
     // x2 upconv: all four phases per tile visit with resident weights (conv_up.cu) when they fit
