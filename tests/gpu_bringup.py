@@ -355,6 +355,20 @@ def stage_trace_up():
     return True
 
 
+def stage_ppon_prof():
+    """One 800x1000 frame (63 tiles) through a 2-block PPON for ncu launch lists."""
+    from innfer_b200.engine import PPONEngine
+    sd = O.make_ppon_state_dict(scale=4, nb=2, seed=0)
+    eng = PPONEngine.from_state_dict(sd, dict(in_nc=3, out_nc=3, nf=64, nb=2, scale=4, alpha=1.0), dev, fp16=True)
+    H, W = 800, 1000
+    din = torch.from_numpy(np.random.default_rng(0).integers(0, 256, (H, W, 3), dtype=np.uint8)).to(dev)
+    dout = torch.empty(4 * H, 4 * W, 3, dtype=torch.uint8, device=dev)
+    eng.upscale_u8_device(din, 200, 0.5, out=dout)
+    torch.cuda.synchronize()
+    eng.close()
+    return True
+
+
 def stage_pix():
     """HBM-bound kernels at benchmark sizes: image->tiles, blend (+uint8), colour fix (for ncu)."""
     lib = N.load()
@@ -448,6 +462,6 @@ if __name__ == "__main__":
     ap.add_argument("--stage", required=True)
     a = ap.parse_args()
     t0 = time.time()
-    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "trace_up": stage_trace_up, "ppon": stage_ppon, "ppon_time": stage_ppon_time, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
+    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "trace_up": stage_trace_up, "ppon": stage_ppon, "ppon_prof": stage_ppon_prof, "ppon_time": stage_ppon_time, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
     print("STAGE %s %s (%.1fs)" % (a.stage, "OK" if ok else "FAILED", time.time() - t0))
     sys.exit(0 if ok else 1)

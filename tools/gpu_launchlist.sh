@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 tag=$1; shift
 env "$@" timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv \
-    --log-file gpurun_out/launches_$tag.csv python tests/gpu_bringup.py --stage prof > gpurun_out/prof_$tag.log 2>&1
+    --log-file gpurun_out/launches_$tag.csv python tests/gpu_bringup.py --stage ${STAGE:-prof} > gpurun_out/prof_$tag.log 2>&1
 tail -2 gpurun_out/prof_$tag.log
 python - gpurun_out/launches_$tag.csv <<'PY'
 import csv, sys, collections
