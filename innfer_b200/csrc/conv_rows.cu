@@ -52,10 +52,14 @@ struct Piece {
 struct PieceIter {
   long long u, u1;
   int H;
+  // In pair mode (p.pair) the unit of work is a PAIR of neighbouring strips handled by the two CTAs of a cluster;
+  // `m` then counts strip pairs and CTA `rank` works on strip 2m + rank.
   __device__ __forceinline__ void init(const ConvRowsParams& p) {
-    const long long T = (long long)p.nstrips * p.H;
-    u = T * blockIdx.x / gridDim.x;
-    u1 = T * (blockIdx.x + 1) / gridDim.x;
+    const long long worker = p.pair ? (blockIdx.x >> 1) : blockIdx.x;
+    const long long nworkers = p.pair ? (gridDim.x >> 1) : gridDim.x;
+    const long long T = (long long)(p.pair ? (p.nstrips + 1) / 2 : p.nstrips) * p.H;
+    u = T * worker / nworkers;
+    u1 = T * (worker + 1) / nworkers;
     H = p.H;
   }
   __device__ __forceinline__ bool next(Piece& pc) {
@@ -71,10 +75,15 @@ struct PieceIter {
   }
 };
 
-template <int COUT, int KSLABS, bool RES>
+template <int COUT, int KSLABS, bool RES, bool PAIR>
 __global__ void __launch_bounds__(rows_threads(COUT), 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvRowsParams p) {
   constexpr int N = 3 * COUT;                 // dy-major: column dy*COUT + co
+  // PAIR: the two CTAs of a cluster issue M = 256 MMAs (tcgen05 cta_group::2) over two neighbouring strips; each CTA
+  // stages its own strip and keeps only HALF of the weight columns (N / 2 rows of every B tile), which is what lets
+  // conv5's 221 KB of row-streaming weights be resident.  CTA 0 issues, both drain their own accumulators.
+  constexpr int NB = PAIR ? N / 2 : N;        // B-tile rows held by this CTA
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   constexpr int NSLOT = 512 / N;              // 5 (COUT=32) or 2 (COUT=64)
   constexpr int CH = COUT / 2;                // channels per epilogue thread (two warps per lane quarter)
   constexpr int SCOUT_WARP = 10;
@@ -90,15 +99,16 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
 
   const int S = p.stages;
   const uint32_t stage_bytes = (uint32_t)p.kc * kRowPx * 16;
-  const uint32_t w_total = (uint32_t)(p.nch / 2) * 3u * 2u * N * 16u;
+  const uint32_t w_total = (uint32_t)(p.nch / 2) * 3u * 2u * NB * 16u;
   uint8_t* bar_base = smem + w_total + (size_t)S * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tfull_bar = empty_bar + S;            // accumulator of a row is complete
   uint64_t* slot_bar = tfull_bar + NSLOT;         // accumulator slot is drained
   uint64_t* wfull_bar = slot_bar + NSLOT;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 2);   // wfull_bar[1]: PAIR, peer's weights landed
   volatile uint32_t* ready_cnt = tmem_slot + 1;    // stages whose barriers the scout warp has seen complete
+  volatile uint32_t* peer_cnt = tmem_slot + 2;     // PAIR, leader CTA: the same count published by the peer's scout
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
 
   if (threadIdx.x == 0) {
@@ -109,19 +119,27 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     }
     for (int i = 0; i < NSLOT; ++i) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&slot_bar[i]), 8);
+      mbar_init(smem_u32(&slot_bar[i]), PAIR ? 16 : 8);   // PAIR: the leader's barrier counts both CTAs' epilogue warps
     }
     mbar_init(smem_u32(wfull_bar), 1);
+    mbar_init(smem_u32(wfull_bar + 1), 1);
     *ready_cnt = 0u;
+    *peer_cnt = 0u;
     fence_mbar_init();
   }
   if (threadIdx.x < COUT) s_bias[threadIdx.x] = p.bias[threadIdx.x];
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), 512u);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(smem_u32(tmem_slot), 512u);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(smem_u32(tmem_slot), 512u);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers must exist before anything is signalled remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t w_base = smem_u32(smem);
@@ -135,7 +153,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       // bulk copies of at most 32 KB each
       for (uint32_t off = 0; off < w_total; off += 32768u) {
         const uint32_t n = (w_total - off) < 32768u ? (w_total - off) : 32768u;
-        bulk_load(w_base + off, reinterpret_cast<const uint8_t*>(p.w) + off, n, wb);
+        bulk_load(w_base + off, reinterpret_cast<const uint8_t*>(p.w) + (size_t)rank * w_total + off, n, wb);
       }
       int s = 0;
       uint32_t ph = 0;
@@ -144,7 +162,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       it.init(p);
       Piece pc;
       while (it.next(pc)) {
-        const int gx = 8 * pc.m - 1;  // first 16-pixel group of the strip's halo tile (-1 -> zero fill)
+        const int strip = PAIR ? 2 * pc.m + (int)rank : pc.m;
+        const int gx = 8 * strip - 1;  // first 16-pixel group of the strip's halo tile (-1 -> zero fill)
         for (int r = pc.r0; r <= pc.r1; ++r) {
           for (int sub = 0; sub < p.nsub; ++sub) {
             mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
@@ -171,14 +190,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     // in shared memory; this thread re-reads that word only when it runs out of known-ready stages,
     // in the middle of a stage, while the first half of the stage's MMAs is still queued.
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_f16(N);
+    const uint32_t idesc = PAIR ? make_idesc_f16_m256(N) : make_idesc_f16(N);
     constexpr uint32_t a_lbo = kRowPx;                   // 16-byte units between the two K chunks
     constexpr uint32_t a_hi = 8u | (1u << 14);           // SBO = 128 B (8 consecutive pixels)
     constexpr uint32_t b_hi = 8u | (1u << 14);
-    constexpr uint32_t b_blk = 2u * N;                   // 16-byte units per (slab, dx) weight block
+    constexpr uint32_t b_blk = 2u * NB;                  // 16-byte units per (slab, dx) weight block (of this CTA)
     constexpr uint32_t b_sub_step = (uint32_t)KSLABS * 3u * b_blk;
     constexpr int KH = KSLABS > 1 ? KSLABS / 2 : 1;
-    const uint32_t b_lo0 = ((w_base & 0x3FFFFu) >> 4) | ((uint32_t)N << 16);
+    const uint32_t b_lo0 = ((w_base & 0x3FFFFu) >> 4) | ((uint32_t)NB << 16);
     const uint32_t a_step = stage_bytes >> 4;
     const uint32_t a_first = ((ring_base & 0x3FFFFu) >> 4) | (a_lbo << 16);
     const uint32_t a_last = a_first + (uint32_t)(S - 1) * a_step;
@@ -186,6 +205,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     const uint32_t tbar0 = smem_u32(&tfull_bar[0]);
     const uint32_t acc_last = tmem_base + (uint32_t)((NSLOT - 1) * N);
     const uint32_t ready_addr = smem_u32((const void*)ready_cnt);
+    const uint32_t peer_addr = smem_u32((const void*)peer_cnt);
     uint32_t nstage = 0;
     {
       PieceIter it;
@@ -195,16 +215,44 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       nstage *= (uint32_t)p.nsub;
     }
     const int nsub = p.nsub;
+    if (PAIR && rank != 0) nstage = 0;   // only the leader CTA issues MMAs
+    // number of stages known to be ready: in PAIR mode the minimum over both CTAs' scouts
+    auto read_ready = [&]() -> uint32_t {
+      uint32_t v;
+      if constexpr (PAIR) {
+        const uint32_t a = ld_acquire_cluster(ready_addr), b = ld_acquire_cluster(peer_addr);
+        v = a < b ? a : b;
+      } else {
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(ready_addr) : "memory");
+      }
+      return v;
+    };
+    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t accum) {
+      if constexpr (PAIR) umma_f16_ss_pair(d, ad, bd, idesc, accum);
+      else umma_f16_ss(d, ad, bd, idesc, accum);
+    };
+    auto commit = [&](uint32_t bar) {
+      if constexpr (PAIR) umma_commit_pair(bar);   // arrives on the barrier at this offset in BOTH CTAs
+      else umma_commit(bar);
+    };
     uint32_t ready = 0;
     uint32_t a_lo = a_first, ebar = ebar0, tbar = tbar0, acc = tmem_base, b_lo = b_lo0;
     int sub = 0;
     mbar_wait(smem_u32(wfull_bar), 0u);
+    if constexpr (PAIR) {
+      // the leader must not issue before the PEER's weights have landed: the peer's issuer warp forwards that event
+      if (rank != 0) {
+        if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(wfull_bar + 1), 0));
+      } else {
+        mbar_wait_cluster(smem_u32(wfull_bar + 1), 0u);
+      }
+    }
     ROWS_TRACE(if (p.trace && lane == 0) p.trace[3072 + blockIdx.x * 8 + 2] = clock64());
     for (uint32_t i = 0; i < nstage; ++i) {
       if (ready <= i) {   // only at the very start, or when the producer is behind
         uint32_t spins = 0;
         do {
-          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(ready) : "r"(ready_addr) : "memory");
+          ready = read_ready();
           if (++spins > (1u << 26)) __trap();
         } while (ready <= i);
         tc_fence_after();
@@ -216,13 +264,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         for (int kk = 0; kk < KH; ++kk) {
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx)
-            umma_f16_ss(acc, make_desc64(a_lo + (uint32_t)(kk * 2 * a_lbo + dx), a_hi),
-                        make_desc64(b_lo + (uint32_t)((kk * 3 + dx) * b_blk), b_hi), idesc,
-                        (kk | dx) == 0 ? (sub != 0 ? 1u : 0u) : 1u);
+            mma(acc, make_desc64(a_lo + (uint32_t)(kk * 2 * a_lbo + dx), a_hi),
+                make_desc64(b_lo + (uint32_t)((kk * 3 + dx) * b_blk), b_hi), (kk | dx) == 0 ? (sub != 0 ? 1u : 0u) : 1u);
         }
       }
       if (ready <= i + 1 && i + 1 < nstage) {   // look ahead while the pipe is busy with the first half
-        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(ready) : "r"(ready_addr) : "memory");
+        ready = read_ready();
         tc_fence_after();
       }
       const bool row_end = sub == nsub - 1;
@@ -231,11 +278,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         for (int kk = KH; kk < KSLABS; ++kk) {
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx)
-            umma_f16_ss(acc, make_desc64(a_lo + (uint32_t)(kk * 2 * a_lbo + dx), a_hi),
-                        make_desc64(b_lo + (uint32_t)((kk * 3 + dx) * b_blk), b_hi), idesc, 1u);
+            mma(acc, make_desc64(a_lo + (uint32_t)(kk * 2 * a_lbo + dx), a_hi),
+                make_desc64(b_lo + (uint32_t)((kk * 3 + dx) * b_blk), b_hi), 1u);
         }
-        umma_commit(ebar);
-        if (row_end) umma_commit(tbar);
+        commit(ebar);
+        if (row_end) commit(tbar);
       }
       __syncwarp();
       if (a_lo == a_last) {
@@ -277,8 +324,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       int slot = 0;
       uint32_t use = 0;
       uint32_t done = 0;
+      // PAIR: the leader's scout also waits for the accumulator slots (its barriers count the epilogue warps of both
+      // CTAs); the peer's scout only follows its own stage ring and publishes the count into the LEADER's memory
+      const uint32_t pub_addr = (PAIR && rank != 0) ? map_to_cta(smem_u32((const void*)peer_cnt), 0)
+                                                    : smem_u32((const void*)ready_cnt);
       for (long long r = 0; r < nrows; ++r) {
-        mbar_wait(smem_u32(&slot_bar[slot]), (use & 1u) ^ 1u);
+        if (!PAIR) mbar_wait(smem_u32(&slot_bar[slot]), (use & 1u) ^ 1u);
+        else if (rank == 0) mbar_wait_cluster(smem_u32(&slot_bar[slot]), (use & 1u) ^ 1u);
         if (++slot == NSLOT) {
           slot = 0;
           ++use;
@@ -290,7 +342,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             ph ^= 1u;
           }
           ++done;
-          asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32((const void*)ready_cnt)), "r"(done) : "memory");
+          if constexpr (PAIR) st_release_cluster(pub_addr, done);
+          else asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(pub_addr), "r"(done) : "memory");
         }
       }
     }
@@ -307,7 +360,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     it.init(p);
     Piece pc;
     while (it.next(pc)) {
-      const int xw = 128 * pc.m - 15 + q4 * 32 + lane;   // wide column of this thread's TMEM lane
+      const int strip = PAIR ? 2 * pc.m + (int)rank : pc.m;
+      const int xw = 128 * strip - 15 + q4 * 32 + lane;   // wide column of this thread's TMEM lane
       const bool in_range = xw >= 0 && xw < p.Wtot;
       const uint32_t b = __umulhi((uint32_t)(xw < 0 ? 0 : xw), p.magic);
       const int xi = xw - (int)b * p.pitch;
@@ -421,7 +475,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&slot_bar[slot]));
+        if (lane == 0) {
+          if (PAIR && rank != 0) mbar_arrive_cluster(map_to_cta(smem_u32(&slot_bar[slot]), 0));
+          else mbar_arrive(smem_u32(&slot_bar[slot]));
+        }
         if (++slot == NSLOT) {
           slot = 0;
           ++use;
@@ -437,30 +494,57 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // neither CTA may leave while the other still signals / reads it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512u);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512u);
+    else tmem_dealloc(tmem_base, 512u);
   }
   ROWS_TRACE(if (p.trace && threadIdx.x == 0) p.trace[3072 + blockIdx.x * 8 + 4] = clock64());
 }
 
-template <int COUT, int KSLABS, bool RES>
+template <int COUT, int KSLABS, bool RES, bool PAIR>
 int launch_rows_res(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num_sms, cudaStream_t stream) {
-  const size_t smem_bytes = conv_rows_weight_bytes(p.nch, COUT) + (size_t)p.stages * conv_rows_stage_bytes(p.kc) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(conv_rows_kernel<COUT, KSLABS, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_bytes);
+  const size_t smem_bytes = conv_rows_weight_bytes(p.nch, COUT) / (PAIR ? 2 : 1) + (size_t)p.stages * conv_rows_stage_bytes(p.kc) + 1024;
+  auto kern = conv_rows_kernel<COUT, KSLABS, RES, PAIR>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int)e;
-  const long long T = (long long)p.nstrips * p.H;
-  const int grid = T < num_sms ? (int)T : num_sms;
-  conv_rows_kernel<COUT, KSLABS, RES><<<grid, rows_threads(COUT), smem_bytes, stream>>>(*tmap_in, p);
-  return (int)cudaGetLastError();
+  const long long T = (long long)(PAIR ? (p.nstrips + 1) / 2 : p.nstrips) * p.H;
+  int grid = T < num_sms ? (int)T : num_sms;
+  if (!PAIR) {
+    kern<<<grid, rows_threads(COUT), smem_bytes, stream>>>(*tmap_in, p);
+    return (int)cudaGetLastError();
+  }
+  // one cluster of two CTAs per worker
+  long long workers = num_sms / 2;
+  if (T < workers) workers = T;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * workers));
+  cfg.blockDim = dim3(rows_threads(COUT));
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, kern, *tmap_in, p);
 }
 
 template <int COUT, int KSLABS>
 int launch_rows_impl(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num_sms, cudaStream_t stream) {
   // the residual-free variant (conv1..conv4 of the plain net) keeps its epilogue free of the side-input code
-  return (p.res1 || p.res2) ? launch_rows_res<COUT, KSLABS, true>(tmap_in, p, num_sms, stream)
-                            : launch_rows_res<COUT, KSLABS, false>(tmap_in, p, num_sms, stream);
+  const bool res = p.res1 || p.res2;
+  if (p.pair) {
+    if constexpr (COUT == 64 && KSLABS == 6)   // conv5 of the nf = 64 net is the one conv that needs the pair
+      return res ? launch_rows_res<COUT, KSLABS, true, true>(tmap_in, p, num_sms, stream)
+                 : launch_rows_res<COUT, KSLABS, false, true>(tmap_in, p, num_sms, stream);
+    return (int)cudaErrorInvalidValue;
+  }
+  return res ? launch_rows_res<COUT, KSLABS, true, false>(tmap_in, p, num_sms, stream)
+             : launch_rows_res<COUT, KSLABS, false, false>(tmap_in, p, num_sms, stream);
 }
 
 template <int COUT>

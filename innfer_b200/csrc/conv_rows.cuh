@@ -29,11 +29,12 @@ struct ConvRowsParams {
   const __half* res2;
   int res1_chunk0, res2_chunk0;
   float alpha1, alpha2;
-  // weights [slab][dx][2][dy*COUT + co][8] fp16, bias [COUT]
+  // weights [slab][dx][2][dy*COUT + co][8] fp16 (pair: [half][slab][dx][2][rows of that half][8]), bias [COUT]
   const __half* w;
   const float* bias;
   int lrelu;
   float slope;
+  int pair;              // 1: clusters of two CTAs, M = 256 MMAs, half of the weight columns per CTA (conv_rows.cu)
   long long* trace;      // debugging: clock64 samples of CTA 0 (see tests/gpu_bringup.py --stage trace), or null
 };
 

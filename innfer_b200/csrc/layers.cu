@@ -135,6 +135,20 @@ int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cou
               packed_rows[o++] = __float2half_rn(v);
             }
   }
+  // CTA-pair packing: [half][kslab][dx][kchunk][row of that half][8]
+  std::vector<__half> packed_pair;
+  if (!packed_rows.empty() && Cout == 64 && Cin > 64) {
+    const int NR = 3 * Cout, NH = NR / 2;
+    packed_pair.resize(packed_rows.size());
+    size_t o = 0;
+    for (int half = 0; half < 2; ++half)
+      for (int ks = 0; ks < kslabs; ++ks)
+        for (int dx = 0; dx < 3; ++dx)
+          for (int kc = 0; kc < 2; ++kc)
+            for (int n = 0; n < NH; ++n)
+              for (int e = 0; e < 8; ++e)
+                packed_pair[o++] = packed_rows[((((size_t)ks * 3 + dx) * 2 + kc) * NR + half * NH + n) * 8 + e];
+  }
   L.w_bytes = packed.size() * sizeof(__half);
   std::vector<float> hb((size_t)L.nphase * N, 0.f);
   if (bias)
@@ -149,6 +163,10 @@ int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cou
       (e = cudaMalloc(&L.d_bias, hb.size() * sizeof(float))) != cudaSuccess ||
       (e = cudaMemcpy(L.d_w, packed.data(), L.w_bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemcpy(L.d_bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (!packed_pair.empty() &&
+       ((e = cudaMalloc(&L.d_wrows_pair, packed_pair.size() * sizeof(__half))) != cudaSuccess ||
+        (e = cudaMemcpy(L.d_wrows_pair, packed_pair.data(), packed_pair.size() * sizeof(__half), cudaMemcpyHostToDevice)) !=
+            cudaSuccess)) ||
       (!packed_rows.empty() &&
        ((e = cudaMalloc(&L.d_wrows, packed_rows.size() * sizeof(__half))) != cudaSuccess ||
         (e = cudaMemcpy(L.d_wrows, packed_rows.data(), packed_rows.size() * sizeof(__half), cudaMemcpyHostToDevice)) !=
@@ -220,6 +238,8 @@ void conv_layer_free(ConvLayer& L) {
   if (L.d_bias) cudaFree(L.d_bias);
   if (L.d_w32) cudaFree(L.d_w32);
   if (L.d_wrows) cudaFree(L.d_wrows);
+  if (L.d_wrows_pair) cudaFree(L.d_wrows_pair);
+  L.d_wrows_pair = nullptr;
   L.d_wrows = nullptr;
   L.d_w = nullptr;
   L.d_bias = nullptr;
@@ -259,7 +279,7 @@ const CUtensorMap* TmapCache::get_rows(const void* base, int CT, int H, int Wtot
 // Row-streaming kernel on wide tensors; returns -100 when the conv is not eligible.
 static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, int H, int W, ChunkView out,
                          int out_nchunks, const Epilogue& ep, int num_sms, cudaStream_t stream) {
-  static const int rows_mode = getenv("INNFER_ROWS") ? atoi(getenv("INNFER_ROWS")) : 3;  // bit 0: on, bit 1: Cout = 64 too
+  static const int rows_mode = getenv("INNFER_ROWS") ? atoi(getenv("INNFER_ROWS")) : 3;  // bit 0: on, bit 1: Cout = 64 too, bit 2: CTA pairs
   if (!rows_mode || !in.wide() || !out.wide() || L.d_wrows == nullptr || L.up != 1 || L.dil != 1 || ep.compact4 ||
       ep.act_after_res || ep.raw_out.base ||
       out_nchunks * 8 != L.Cout || in.pitch != out.pitch || in.Wtot != out.Wtot)
@@ -268,17 +288,24 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
     if (v->base && (!v->wide() || v->pitch != out.pitch || v->Wtot != out.Wtot)) return -100;
   // Cout = 64 (N = 192 MMAs run at ~117 cycles, only two TMEM slots): 1.3x faster than the 9-tap kernel for
   // residual-free convs (HR_conv0: 3275 -> 2520 us), no gain with residual epilogues (measured, profiles/)
-  if (L.Cout == 64 && (ep.res1.base || ep.res2.base || !(rows_mode & 2))) return -100;
   if (L.Cout != 32 && L.Cout != 64) return -100;
+  if (L.Cout == 64 && !(rows_mode & 2)) return -100;
   const int nch = L.Cin_pad / 8;
   int nsub = (nch + 15) / 16;
   while (nsub <= nch && (nch % nsub != 0 || ((nch / nsub) & 1))) ++nsub;
   if (nsub > nch) return -100;
   const int kc = nch / nsub;
-  const int wbytes = conv_rows_weight_bytes(nch, L.Cout);
+  int wbytes = conv_rows_weight_bytes(nch, L.Cout);
   int S = (232448 - 1024 - wbytes) / conv_rows_stage_bytes(kc);
+  // conv5 of the nf = 64 net (192 -> 64): 221 KB of weights only fit when a CTA pair shares them
+  const bool pair = S < 3 && L.d_wrows_pair != nullptr && (rows_mode & 4) && L.Cout == 64 && kc == 12;
+  if (pair) {
+    wbytes /= 2;
+    S = (232448 - 1024 - wbytes) / conv_rows_stage_bytes(kc);
+  }
   if (S < 3) return -100;
   if (S > 8) S = 8;
+  if (L.Cout == 64 && !pair && (ep.res1.base || ep.res2.base)) return -100;
   ConvRowsParams p;
   std::memset(&p, 0, sizeof(p));
   p.H = H;
@@ -297,7 +324,8 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   p.out_cs = (long long)H * out.Wtot * 8;
   p.out_ys = out.Wtot * 8;
   p.out_chunk0 = out.chunk0;
-  p.w = L.d_wrows;
+  p.w = pair ? L.d_wrows_pair : L.d_wrows;
+  p.pair = pair ? 1 : 0;
   p.bias = L.d_bias;
   p.lrelu = ep.lrelu ? 1 : 0;
   p.slope = ep.slope;

@@ -45,6 +45,7 @@ struct ConvLayer {
   int max_taps = 0;
   __half* d_w = nullptr;   // device, packed [phase][kslab][tap][2][N][8]
   __half* d_wrows = nullptr; // device, row-streaming packing [kslab][dx][2][dy*Cout+co][8] (Cout 32/64, plain 3x3)
+  __half* d_wrows_pair = nullptr;  // same, split in two halves of the N columns for the CTA-pair mode (Cout 64, Cin > 64)
   float* d_bias = nullptr; // device, [nphase][N]
   size_t w_bytes = 0;
   // fp32 copies (OIHW + bias) kept on the device for the fp32-mode direct kernel
