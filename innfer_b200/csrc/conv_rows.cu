@@ -538,7 +538,7 @@ int launch_rows_impl(const CUtensorMap* tmap_in, const ConvRowsParams& p, int nu
   // the residual-free variant (conv1..conv4 of the plain net) keeps its epilogue free of the side-input code
   const bool res = p.res1 || p.res2;
   if (p.pair) {
-    if constexpr (COUT == 64 && KSLABS == 6)   // conv5 of the nf = 64 net is the one conv that needs the pair
+    if constexpr (COUT == 64 && KSLABS == 6)   // conv5 of the nf = 64 net is the one conv that needs (and gains from) the pair
       return res ? launch_rows_res<COUT, KSLABS, true, true>(tmap_in, p, num_sms, stream)
                  : launch_rows_res<COUT, KSLABS, false, true>(tmap_in, p, num_sms, stream);
     return (int)cudaErrorInvalidValue;

@@ -279,7 +279,7 @@ const CUtensorMap* TmapCache::get_rows(const void* base, int CT, int H, int Wtot
 // Row-streaming kernel on wide tensors; returns -100 when the conv is not eligible.
 static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, int H, int W, ChunkView out,
                          int out_nchunks, const Epilogue& ep, int num_sms, cudaStream_t stream) {
-  static const int rows_mode = getenv("INNFER_ROWS") ? atoi(getenv("INNFER_ROWS")) : 3;  // bit 0: on, bit 1: Cout = 64 too, bit 2: CTA pairs
+  static const int rows_mode = getenv("INNFER_ROWS") ? atoi(getenv("INNFER_ROWS")) : 7;  // bit 0: on, bit 1: Cout = 64 too, bit 2: CTA pairs (conv5)
   if (!rows_mode || !in.wide() || !out.wide() || L.d_wrows == nullptr || L.up != 1 || L.dil != 1 || ep.compact4 ||
       ep.act_after_res || ep.raw_out.base ||
       out_nchunks * 8 != L.Cout || in.pitch != out.pitch || in.Wtot != out.Wtot)
@@ -298,6 +298,8 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   int wbytes = conv_rows_weight_bytes(nch, L.Cout);
   int S = (232448 - 1024 - wbytes) / conv_rows_stage_bytes(kc);
   // conv5 of the nf = 64 net (192 -> 64): 221 KB of weights only fit when a CTA pair shares them
+  // (pairs for the short row stages of conv1..conv4 were measured 2.5x slower: the cross-CTA signalling per row is not
+  // amortised over 12..30 MMAs)
   const bool pair = S < 3 && L.d_wrows_pair != nullptr && (rows_mode & 4) && L.Cout == 64 && kc == 12;
   if (pair) {
     wbytes /= 2;
