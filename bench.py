@@ -290,7 +290,7 @@ def main():
         hbm_achieved = bytes_step * args.steps / (conv_ms * 1e-3) / 1e9
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic,
-                "kernel": "conv_rows_kernel<32,K> + conv_tc_kernel<N> (all %d conv launches of a step)" % (conv_launches // args.steps),
+                "kernel": "conv_rows_kernel<32|64,K,RES,PAIR> (+ conv_up / conv_tc for 6 tail convs): all %d conv launches of a step" % (conv_launches // args.steps),
                 "flop_per_launch_avg": flop_step * args.steps / conv_launches,
                 "avg_launch_ms": conv_ms / conv_launches, "peak_source": peak_src,
                 "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
