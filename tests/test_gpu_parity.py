@@ -86,8 +86,11 @@ def test_conv_block_tcgen05(native, dev, cin, cout, h, w, kw):
     (128, 32, 33, 47, dict(lrelu=True, n=3)), (160, 32, 40, 48, dict(lrelu=True)), (160, 32, 21, 35, dict(res=True, n=2)),
     (32, 32, 20, 20, dict(lrelu=True)), (16, 32, 9, 130, dict(lrelu=True)), (64, 32, 1, 1, {}), (64, 32, 2, 127, dict(n=5)),
     (64, 32, 7, 200, dict(lrelu=True)), (64, 32, 200, 200, dict(n=2, lrelu=True)), (96, 32, 300, 129, dict(lrelu=True, res=True)),
-    # 9-tap kernel on a wide source: separators, residuals, upsampling phases, N = 16/32/64
-    (192, 64, 40, 48, dict(res=True, n=2)), (3, 64, 33, 47, dict(n=2)), (64, 3, 50, 70, dict(n=2)),
+    # conv5 shape: CTA-pair mode of the row kernel (cta_group::2), one and several strip pairs, odd strip count
+    (192, 64, 40, 48, dict(res=True, n=2)), (192, 64, 33, 200, dict(res=True, n=3)), (192, 64, 9, 130, dict(n=2)),
+    # residual-free 64 -> 64 on the row kernel (N = 192), with residual on the 9-tap kernel
+    (64, 64, 21, 150, dict(lrelu=True, n=2)), (64, 64, 21, 150, dict(res=True, n=2)),
+    # 9-tap kernel on a wide source: separators, upsampling phases (conv_up for x2), N = 16/32/64 (3, 64, 33, 47, dict(n=2)), (64, 3, 50, 70, dict(n=2)),
     (64, 64, 37, 53, dict(n=3, lrelu=True)), (64, 64, 24, 40, dict(up=2, lrelu=True, n=2)),
     (64, 64, 17, 23, dict(up=3, lrelu=True, n=2)), (64, 16, 19, 21, dict(n=4, lrelu=True)),
 ])
