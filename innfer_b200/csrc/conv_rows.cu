@@ -4,7 +4,9 @@
 // Replaces (fp16 engine path) conv1..conv4 of ResidualDenseBlock_5C (RRDBNet_arch.py:152-165:
 // Conv2d(k=3,p=1) + LeakyReLU(0.2), Cout = 32), incl. the ESRGAN+ residual adds and, for nf = 32 nets,
 // conv5 with its "*0.2 + x" epilogues; with COUT = 64 (N = 192, two TMEM slots) the residual-free
-// 64 -> 64 convs whose weights fit in shared memory (HR_conv0, SRResNet's first block convs).
+// 64 -> 64 convs whose weights fit in shared memory (HR_conv0, SRResNet's first block convs) and, as
+// clusters of two CTAs (PAIR, tcgen05 cta_group::2), conv5 of the nf = 64 net with both residual
+// epilogues (RRDBNet_arch.py:98,165), whose weights only fit when the pair shares them.
 //
 // Wide layout: the B tile images of a batch stand side by side in one image [chunk][H][Wtot][8],
 // image b in columns [b*pitch, b*pitch + Wimg), the `pitch - Wimg` separator columns hold zeros (they
