@@ -87,7 +87,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   constexpr int NB = PAIR ? N / 2 : N;        // B-tile rows held by this CTA
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   constexpr int NSLOT = 512 / N;              // 5 (COUT=32) or 2 (COUT=64)
-  constexpr int CH = COUT / 2;                // channels per epilogue thread (two warps per lane quarter)
+  // channels per epilogue thread: two warps per lane quarter share COUT; COUT = 16 (the net's last conv, N = 48) is
+  // drained by ONE warp per quarter, the other four epilogue warps idle
+  constexpr int CH = COUT == 16 ? 16 : COUT / 2;
+  constexpr int NGRP = COUT == 16 ? 1 : 2;
   constexpr int SCOUT_WARP = 10;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -121,7 +124,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     }
     for (int i = 0; i < NSLOT; ++i) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&slot_bar[i]), PAIR ? 16 : 8);   // PAIR: the leader's barrier counts both CTAs' epilogue warps
+      mbar_init(smem_u32(&slot_bar[i]), (PAIR ? 8 : 4) * NGRP);   // PAIR: the leader's barrier counts both CTAs' warps
     }
     mbar_init(smem_u32(wfull_bar), 1);
     mbar_init(smem_u32(wfull_bar + 1), 1);
@@ -353,6 +356,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     // ------------------------------------------------------------ epilogue warps
     const int q4 = warp & 3;
     const int grp = (warp - 2) >> 2;                     // which half of the output channels
+    if (grp < NGRP) {
     const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
     const float* bias = s_bias + grp * CH;
     int slot = 0;
@@ -369,9 +373,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       const int xi = xw - (int)b * p.pitch;
       const bool real = in_range && (int)b < p.nimg && xi < p.Wimg;   // else separator column: zeros
       const size_t col = (size_t)(xw < 0 ? 0 : xw) * 8;
-      __half* const obase = p.out + (size_t)(p.out_chunk0 + grp * (CH / 8)) * p.out_cs + col;
-      const __half* const r1base = (RES && p.res1) ? p.res1 + (size_t)(p.res1_chunk0 + grp * (CH / 8)) * p.out_cs + col : nullptr;
-      const __half* const r2base = (RES && p.res2) ? p.res2 + (size_t)(p.res2_chunk0 + grp * (CH / 8)) * p.out_cs + col : nullptr;
+      // wide: image * pitch + xi == xw, so this is xw * 8 for separator columns too
+      __half* const obase = p.out + (size_t)b * p.out_bs + (size_t)(p.out_chunk0 + grp * (CH / 8)) * p.out_cs +
+                            (size_t)(xw < 0 ? 0 : xi) * p.out_px;
+      const __half* const r1base = (RES && p.res1) ? p.res1 + (size_t)(p.res1_chunk0 + grp * (CH / 8)) * p.res_cs + col : nullptr;
+      const __half* const r2base = (RES && p.res2) ? p.res2 + (size_t)(p.res2_chunk0 + grp * (CH / 8)) * p.res_cs + col : nullptr;
+      const int nchunks = p.out_nchunks - grp * (CH / 8);   // chunks of this thread that exist in the destination
       float accA[CH], accB[CH];
 #pragma unroll
       for (int c = 0; c < CH; ++c) accA[c] = accB[c] = 0.f;
@@ -379,24 +386,25 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       // accumulator wait, loaded chunk by chunk in store_row (keeps the live register set small)
       auto load_side = [&](int y) {
         if (!RES || !real || y < pc.ya) return;
-        const size_t ro = (size_t)y * p.out_ys;
+        const size_t ro = (size_t)y * p.res_ys;
 #pragma unroll
         for (int ch = 0; ch < CH / 8; ++ch) {
-          if (r1base) asm volatile("prefetch.global.L2 [%0];" ::"l"(r1base + ro + (size_t)ch * p.out_cs));
-          if (r2base) asm volatile("prefetch.global.L2 [%0];" ::"l"(r2base + ro + (size_t)ch * p.out_cs));
+          if (r1base) asm volatile("prefetch.global.L2 [%0];" ::"l"(r1base + ro + (size_t)ch * p.res_cs));
+          if (r2base) asm volatile("prefetch.global.L2 [%0];" ::"l"(r2base + ro + (size_t)ch * p.res_cs));
         }
       };
       auto store_row = [&](int y, const float (&o)[CH]) {
-        if (!in_range) return;
-        const size_t ro = (size_t)y * p.out_ys;
-        __half* op = obase + ro;
+        if (!in_range || !(real || p.out_wide)) return;
+        const size_t ro = (size_t)y * p.res_ys;
+        __half* op = obase + (size_t)y * p.out_ys;
 #pragma unroll
         for (int ch = 0; ch < CH / 8; ++ch) {
+          if (ch >= nchunks) break;
           uint4 pk = make_uint4(0u, 0u, 0u, 0u);
           if (real) {
             uint4 s1, s2;
-            if (r1base) s1 = *reinterpret_cast<const uint4*>(r1base + ro + (size_t)ch * p.out_cs);
-            if (r2base) s2 = *reinterpret_cast<const uint4*>(r2base + ro + (size_t)ch * p.out_cs);
+            if (r1base) s1 = *reinterpret_cast<const uint4*>(r1base + ro + (size_t)ch * p.res_cs);
+            if (r2base) s2 = *reinterpret_cast<const uint4*>(r2base + ro + (size_t)ch * p.res_cs);
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = o[ch * 8 + e] + bias[ch * 8 + e];
@@ -431,7 +439,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             pk.z = *reinterpret_cast<const uint32_t*>(&h2);
             pk.w = *reinterpret_cast<const uint32_t*>(&h3);
           }
-          *reinterpret_cast<uint4*>(op + (size_t)ch * p.out_cs) = pk;
+          if (p.out_compact4) *reinterpret_cast<uint2*>(op) = make_uint2(pk.x, pk.y);
+          else *reinterpret_cast<uint4*>(op + (size_t)ch * p.out_cs) = pk;
         }
       };
       for (int r = pc.r0; r <= pc.r1; ++r) {
@@ -491,6 +500,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         load_side(p.H - 1);
         store_row(p.H - 1, accA);
       }
+    }
     }
   }
 
@@ -570,6 +580,7 @@ int conv_rows_stage_bytes(int kc) { return kc * kRowPx * 16; }
 int conv_rows_weight_bytes(int nch, int cout) { return (nch / 2) * 3 * 2 * (3 * cout) * 16; }
 
 int launch_conv_rows(const CUtensorMap* tmap_in, const ConvRowsParams& p, int cout, int num_sms, cudaStream_t stream) {
+  if (cout == 16) return p.kc == 8 ? launch_rows_impl<16, 4>(tmap_in, p, num_sms, stream) : (int)cudaErrorInvalidValue;
   if (cout == 32) return launch_rows_k<32>(tmap_in, p, num_sms, stream);
   if (cout == 64) return launch_rows_k<64>(tmap_in, p, num_sms, stream);
   return (int)cudaErrorInvalidValue;

@@ -18,11 +18,18 @@ struct ConvRowsParams {
   int nsub;                // nch / kc stages per row
   int nstrips;             // ceil((Wtot + 15) / 128); strip m covers columns [128m - 15, 128m + 113)
   int stages;              // shared-memory ring depth
-  // destination, wide layout with the same geometry
+  // destination: address = out + image * out_bs + chunk * out_cs + row * out_ys + column_in_image * out_px (elements).
+  // Wide (same geometry as the source): bs = pitch*8, cs = H*Wtot*8, ys = Wtot*8, px = 8, separator columns are stored
+  // as zeros (out_wide).  Tiled [B][CT][H][W][8] and compact [B][H][W][4] (out_compact4, channels 0..3) destinations
+  // receive real pixels only -- the last conv of a net, possibly into a peer GPU's tile buffer.
   __half* out;
-  long long out_cs;        // elements between chunks
-  int out_ys;              // elements between rows (Wtot * 8)
-  int out_chunk0;
+  long long out_bs, out_cs;
+  int out_ys, out_px;
+  int out_chunk0, out_nchunks;
+  int out_wide, out_compact4;
+  // residual tensors are wide with the source's geometry
+  long long res_cs;
+  int res_ys;
   // optional residuals, wide tensors of the destination's geometry (same row / chunk strides):
   //   t = lrelu(acc + bias);  t = t*alpha1 + res1;  t = t*alpha2 + res2
   const __half* res1;

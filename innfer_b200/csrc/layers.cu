@@ -121,8 +121,9 @@ int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cou
   }
   // row-streaming packing (conv_rows.cu): [kslab][dx][kchunk][dy*Cout + co][8]
   std::vector<__half> packed_rows;
-  if (up == 1 && ksize == 3 && dil == 1 && (Cout == 32 || Cout == 64)) {
-    const int NR = 3 * Cout;
+  if (up == 1 && ksize == 3 && dil == 1 && (Cout == 32 || Cout == 64 || Cout <= 16)) {
+    const int CR = Cout <= 16 ? 16 : Cout;   // output channels as the kernel sees them (zero rows beyond Cout)
+    const int NR = 3 * CR;
     packed_rows.resize((size_t)kslabs * 3 * 2 * NR * 8);
     size_t o = 0;
     for (int ks = 0; ks < kslabs; ++ks)
@@ -130,8 +131,8 @@ int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cou
         for (int kc = 0; kc < 2; ++kc)
           for (int n = 0; n < NR; ++n)
             for (int e = 0; e < 8; ++e) {
-              const int ci = ks * 16 + kc * 8 + e, dy = n / Cout, co = n % Cout;
-              const float v = ci < Cin ? w[(((size_t)co * Cin + ci) * 3 + dy) * 3 + dx] : 0.f;
+              const int ci = ks * 16 + kc * 8 + e, dy = n / CR, co = n % CR;
+              const float v = (ci < Cin && co < Cout) ? w[(((size_t)co * Cin + ci) * 3 + dy) * 3 + dx] : 0.f;
               packed_rows[o++] = __float2half_rn(v);
             }
   }
@@ -280,34 +281,36 @@ const CUtensorMap* TmapCache::get_rows(const void* base, int CT, int H, int Wtot
 static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, int H, int W, ChunkView out,
                          int out_nchunks, const Epilogue& ep, int num_sms, cudaStream_t stream) {
   static const int rows_mode = getenv("INNFER_ROWS") ? atoi(getenv("INNFER_ROWS")) : 7;  // bit 0: on, bit 1: Cout = 64 too, bit 2: CTA pairs (conv5)
-  if (!rows_mode || !in.wide() || !out.wide() || L.d_wrows == nullptr || L.up != 1 || L.dil != 1 || ep.compact4 ||
-      ep.act_after_res || ep.raw_out.base ||
-      out_nchunks * 8 != L.Cout || in.pitch != out.pitch || in.Wtot != out.Wtot)
+  const int CR = L.Cout <= 16 ? 16 : L.Cout;   // kernel instantiation: 16 (the net's last conv), 32 or 64
+  if (!rows_mode || !in.wide() || L.d_wrows == nullptr || L.up != 1 || L.dil != 1 || ep.act_after_res || ep.raw_out.base ||
+      out_nchunks != (L.Cout + 7) / 8 || (out.wide() && (in.pitch != out.pitch || in.Wtot != out.Wtot)) ||
+      (ep.compact4 && (out.wide() || L.Cout > 4)))
     return -100;
   for (const ChunkView* v : {&ep.res1, &ep.res2})
-    if (v->base && (!v->wide() || v->pitch != out.pitch || v->Wtot != out.Wtot)) return -100;
+    if (v->base && (!v->wide() || v->pitch != in.pitch || v->Wtot != in.Wtot)) return -100;
   // Cout = 64 (N = 192 MMAs run at ~117 cycles, only two TMEM slots): 1.3x faster than the 9-tap kernel for
-  // residual-free convs (HR_conv0: 3275 -> 2520 us), no gain with residual epilogues (measured, profiles/)
-  if (L.Cout != 32 && L.Cout != 64) return -100;
-  if (L.Cout == 64 && !(rows_mode & 2)) return -100;
+  // residual-free convs (HR_conv0: 3275 -> 2520 us), no gain with residual epilogues unless on a CTA pair
+  if (CR != 16 && CR != 32 && CR != 64) return -100;
+  if (CR == 64 && !(rows_mode & 2)) return -100;
+  if (CR == 16 && (!(rows_mode & 2) || L.Cin_pad != 64)) return -100;
   const int nch = L.Cin_pad / 8;
   int nsub = (nch + 15) / 16;
   while (nsub <= nch && (nch % nsub != 0 || ((nch / nsub) & 1))) ++nsub;
   if (nsub > nch) return -100;
   const int kc = nch / nsub;
-  int wbytes = conv_rows_weight_bytes(nch, L.Cout);
+  int wbytes = conv_rows_weight_bytes(nch, CR);
   int S = (232448 - 1024 - wbytes) / conv_rows_stage_bytes(kc);
   // conv5 of the nf = 64 net (192 -> 64): 221 KB of weights only fit when a CTA pair shares them
   // (pairs for the short row stages of conv1..conv4 were measured 2.5x slower: the cross-CTA signalling per row is not
   // amortised over 12..30 MMAs)
-  const bool pair = S < 3 && L.d_wrows_pair != nullptr && (rows_mode & 4) && L.Cout == 64 && kc == 12;
+  const bool pair = S < 3 && L.d_wrows_pair != nullptr && (rows_mode & 4) && CR == 64 && kc == 12;
   if (pair) {
     wbytes /= 2;
     S = (232448 - 1024 - wbytes) / conv_rows_stage_bytes(kc);
   }
   if (S < 3) return -100;
   if (S > 8) S = 8;
-  if (L.Cout == 64 && !pair && (ep.res1.base || ep.res2.base)) return -100;
+  if (CR == 64 && !pair && (ep.res1.base || ep.res2.base)) return -100;
   ConvRowsParams p;
   std::memset(&p, 0, sizeof(p));
   p.H = H;
@@ -323,9 +326,26 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   p.nstrips = (in.Wtot + 15 + 127) / 128;
   p.stages = S;
   p.out = out.base;
-  p.out_cs = (long long)H * out.Wtot * 8;
-  p.out_ys = out.Wtot * 8;
+  p.out_px = 8;
+  if (out.wide()) {
+    p.out_bs = (long long)out.pitch * 8;
+    p.out_cs = (long long)H * out.Wtot * 8;
+    p.out_ys = out.Wtot * 8;
+    p.out_wide = 1;
+  } else if (ep.compact4) {
+    p.out_bs = (long long)H * W * 4;
+    p.out_ys = W * 4;
+    p.out_px = 4;
+    p.out_compact4 = 1;
+  } else {
+    p.out_bs = (long long)out.CT * H * W * 8;
+    p.out_cs = (long long)H * W * 8;
+    p.out_ys = W * 8;
+  }
   p.out_chunk0 = out.chunk0;
+  p.out_nchunks = out_nchunks;
+  p.res_cs = (long long)H * in.Wtot * 8;
+  p.res_ys = in.Wtot * 8;
   p.w = pair ? L.d_wrows_pair : L.d_wrows;
   p.pair = pair ? 1 : 0;
   p.bias = L.d_bias;
@@ -342,7 +362,7 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   int rc = 0;
   const CUtensorMap* tm = cache.get_rows(in.base, in.CT, H, in.Wtot, kc, rc);
   if (!tm) return rc ? rc : -5;
-  return launch_conv_rows(tm, p, L.Cout, num_sms, stream);
+  return launch_conv_rows(tm, p, CR, num_sms, stream);
 }
 
 int choose_J(int W, int N) {
