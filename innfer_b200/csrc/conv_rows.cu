@@ -382,8 +382,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       float accA[CH], accB[CH];
 #pragma unroll
       for (int c = 0; c < CH; ++c) accA[c] = accB[c] = 0.f;
-      // residual inputs of one output row: prefetched into L2 before the
-      // accumulator wait, loaded chunk by chunk in store_row (keeps the live register set small)
+      // residual inputs of one output row: prefetched into L2 one row stage ahead, loaded chunk by chunk in
+      // store_row (keeps the live register set small)
       auto load_side = [&](int y) {
         if (!RES || !real || y < pc.ya) return;
         const size_t ro = (size_t)y * p.res_ys;
@@ -444,7 +444,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         }
       };
       for (int r = pc.r0; r <= pc.r1; ++r) {
-        load_side(r - 1);
+        load_side(r);   // row r is finished one iteration (one whole row stage) later: enough to cover an HBM miss
         mbar_wait(smem_u32(&tfull_bar[slot]), use & 1u);
         tc_fence_after();
         ROWS_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && ecount < 256) p.trace[2048 + ecount++] = clock64());
@@ -497,7 +497,6 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         if (r - 1 >= pc.ya) store_row(r - 1, o);
       }
       if (pc.yb == p.H) {   // bottom row: the row below is zero padding
-        load_side(p.H - 1);
         store_row(p.H - 1, accA);
       }
     }
