@@ -43,7 +43,9 @@ namespace {
 // warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue (two per TMEM lane quarter, each half of the
 // output channels), 10 = scout.  352 threads leave the epilogue threads 184 registers (COUT = 64 keeps
 // 3 x 32 running sums per thread).
-__host__ __device__ constexpr int rows_threads(int) { return 352; }
+// The CTA-pair kernel (conv5) runs 16 epilogue warps of 16 channels each (608 threads, 96 registers): its residual
+// epilogue is latency-bound and gains from more warps in flight.
+__host__ __device__ constexpr int rows_threads(int /*cout*/, bool pair) { return pair ? 608 : 352; }
 constexpr int kRowPx = 144;        // pixels per staged row segment: 9 groups of 16 (strip of 128 + halo)
 
 struct Piece {
@@ -78,7 +80,7 @@ struct PieceIter {
 };
 
 template <int COUT, int KSLABS, bool RES, bool PAIR>
-__global__ void __launch_bounds__(rows_threads(COUT), 1)
+__global__ void __launch_bounds__(rows_threads(COUT, PAIR), 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvRowsParams p) {
   constexpr int N = 3 * COUT;                 // dy-major: column dy*COUT + co
   // PAIR: the two CTAs of a cluster issue M = 256 MMAs (tcgen05 cta_group::2) over two neighbouring strips; each CTA
@@ -89,9 +91,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   constexpr int NSLOT = 512 / N;              // 5 (COUT=32) or 2 (COUT=64)
   // channels per epilogue thread: two warps per lane quarter share COUT; COUT = 16 (the net's last conv, N = 48) is
   // drained by ONE warp per quarter, the other four epilogue warps idle
-  constexpr int CH = COUT == 16 ? 16 : COUT / 2;
-  constexpr int NGRP = COUT == 16 ? 1 : 2;
-  constexpr int SCOUT_WARP = 10;
+  constexpr int CH = (COUT == 16 || PAIR) ? 16 : COUT / 2;
+  constexpr int NGRP = COUT / CH;              // active epilogue warps per lane quarter
+  constexpr int SCOUT_WARP = PAIR ? 2 + 4 * NGRP : 10;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -397,14 +399,22 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         if (!in_range || !(real || p.out_wide)) return;
         const size_t ro = (size_t)y * p.res_ys;
         __half* op = obase + (size_t)y * p.out_ys;
+        // all residual loads of the row are issued before the first use: one exposed L2 round trip per row instead of
+        // one per chunk (measured: 3 200 cycles per row for 4 chunks x 2 residuals when loaded chunk by chunk)
+        uint4 s1v[CH / 8], s2v[CH / 8];
+        if (RES && real) {
+#pragma unroll
+          for (int ch = 0; ch < CH / 8; ++ch) {
+            if (r1base && ch < nchunks) s1v[ch] = *reinterpret_cast<const uint4*>(r1base + ro + (size_t)ch * p.res_cs);
+            if (r2base && ch < nchunks) s2v[ch] = *reinterpret_cast<const uint4*>(r2base + ro + (size_t)ch * p.res_cs);
+          }
+        }
 #pragma unroll
         for (int ch = 0; ch < CH / 8; ++ch) {
           if (ch >= nchunks) break;
           uint4 pk = make_uint4(0u, 0u, 0u, 0u);
           if (real) {
-            uint4 s1, s2;
-            if (r1base) s1 = *reinterpret_cast<const uint4*>(r1base + ro + (size_t)ch * p.res_cs);
-            if (r2base) s2 = *reinterpret_cast<const uint4*>(r2base + ro + (size_t)ch * p.res_cs);
+            const uint4 s1 = s1v[ch], s2 = s2v[ch];
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = o[ch * 8 + e] + bias[ch * 8 + e];
@@ -449,10 +459,40 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         tc_fence_after();
         ROWS_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && ecount < 256) p.trace[2048 + ecount++] = clock64());
         const uint32_t tacc = tmem_base + lane_base + (uint32_t)(slot * N + grp * CH);
-        float o[CH];
-        if constexpr (CH == 16) {
-          // all three blocks of this thread's channels are read at once: the slot goes back to the MMA warp
-          // as early as possible
+        auto release_slot = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR && rank != 0) mbar_arrive_cluster(map_to_cta(smem_u32(&slot_bar[slot]), 0));
+            else mbar_arrive(smem_u32(&slot_bar[slot]));
+          }
+          if (++slot == NSLOT) {
+            slot = 0;
+            ++use;
+          }
+        };
+        if constexpr (PAIR) {
+          // 16 channels per thread, one 16-register TMEM buffer, the finished row completed in accA and stored before
+          // the other two blocks are read (96 registers per thread with 608 threads: a separate copy would spill)
+          uint32_t v[16];
+          tmem_ld16(tacc + 2 * COUT, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) accA[c] += __uint_as_float(v[c]);
+          if (r - 1 >= pc.ya) store_row(r - 1, accA);
+          tmem_ld16(tacc + COUT, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) accA[c] = accB[c] + __uint_as_float(v[c]);
+          tmem_ld16(tacc, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) accB[c] = __uint_as_float(v[c]);
+          release_slot();
+        } else if constexpr (CH == 16) {
+          // all three blocks of this thread's channels are read at once and the slot goes back to the MMA warp
+          // before the finished row is stored
+          float o[CH];
           uint32_t v0[16], v1[16], v2[16];
           tmem_ld16(tacc, v0);
           tmem_ld16(tacc + COUT, v1);
@@ -464,16 +504,24 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             accA[c] = accB[c] + __uint_as_float(v1[c]);
             accB[c] = __uint_as_float(v0[c]);
           }
+          release_slot();
+          if (r - 1 >= pc.ya) store_row(r - 1, o);
         } else {
-          // COUT = 64: 3 x 32 running values per thread; read through one 16-register buffer to stay
-          // clear of spills (TMEM read latency is ~12 cycles)
+          // COUT = 64: 3 x 32 running values per thread, read through one 16-register buffer.  The finished row is
+          // completed IN accA and stored before the other two blocks are read, so that no separate copy of it is
+          // live while the residuals of the row are in registers (no spills: they would go to L2 here); the slot is
+          // released after the store, which the second TMEM slot and the ~3 500-cycle row stages absorb.
           uint32_t v[16];
 #pragma unroll
           for (int g = 0; g < CH / 16; ++g) {
             tmem_ld16(tacc + 2 * COUT + g * 16, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 16; ++c) o[g * 16 + c] = accA[g * 16 + c] + __uint_as_float(v[c]);
+            for (int c = 0; c < 16; ++c) accA[g * 16 + c] += __uint_as_float(v[c]);
+          }
+          if (r - 1 >= pc.ya) store_row(r - 1, accA);
+#pragma unroll
+          for (int g = 0; g < CH / 16; ++g) {
             tmem_ld16(tacc + COUT + g * 16, v);
             tmem_ld_wait();
 #pragma unroll
@@ -483,18 +531,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
 #pragma unroll
             for (int c = 0; c < 16; ++c) accB[g * 16 + c] = __uint_as_float(v[c]);
           }
+          release_slot();
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (PAIR && rank != 0) mbar_arrive_cluster(map_to_cta(smem_u32(&slot_bar[slot]), 0));
-          else mbar_arrive(smem_u32(&slot_bar[slot]));
-        }
-        if (++slot == NSLOT) {
-          slot = 0;
-          ++use;
-        }
-        if (r - 1 >= pc.ya) store_row(r - 1, o);
       }
       if (pc.yb == p.H) {   // bottom row: the row below is zero padding
         store_row(p.H - 1, accA);
@@ -523,7 +561,7 @@ int launch_rows_res(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num
   const long long T = (long long)(PAIR ? (p.nstrips + 1) / 2 : p.nstrips) * p.H;
   int grid = T < num_sms ? (int)T : num_sms;
   if (!PAIR) {
-    kern<<<grid, rows_threads(COUT), smem_bytes, stream>>>(*tmap_in, p);
+    kern<<<grid, rows_threads(COUT, false), smem_bytes, stream>>>(*tmap_in, p);
     return (int)cudaGetLastError();
   }
   // one cluster of two CTAs per worker
@@ -531,7 +569,7 @@ int launch_rows_res(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num
   if (T < workers) workers = T;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * workers));
-  cfg.blockDim = dim3(rows_threads(COUT));
+  cfg.blockDim = dim3(rows_threads(COUT, true));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr;

@@ -214,6 +214,10 @@ def stage_trace():
               % (np.median(c[:, 2] - c[:, 1]), (c[:, 2] - c[:, 1]).max(), np.median(c[:, 3] - c[:, 2]), (c[:, 3] - c[:, 2]).min(),
                  (c[:, 3] - c[:, 2]).max(), np.median(c[:, 4] - c[:, 3]), (c[:, 4] - c[:, 3]).max(), (c[:, 0] - g0).max(),
                  c[:, 5].min(), c[:, 5].max()))
+        lead = c[c[:, 5] > 0]
+        lt = np.sort(lead[:, 3] - lead[:, 2])
+        print("  issuing CTAs %d: loop cycles min %.0f p10 %.0f median %.0f p90 %.0f max %.0f" % (
+            len(lead), lt[0], lt[len(lt) // 10], lt[len(lt) // 2], lt[(9 * len(lt)) // 10], lt[-1]))
         per = (c[:, 3] - c[:, 2]) / np.maximum(c[:, 5], 1)
         print("  cycles per stage by CTA: min %.0f median %.0f max %.0f; total kernel cycles (max over CTAs) %.0f"
               % (per.min(), np.median(per), per.max(), (c[:, 4] - c[:, 1]).max()))
@@ -227,6 +231,14 @@ def stage_trace():
             break
         print("%3d: %8d %5d %5d %5d | %5d | %8d | %8d" % (i, m[i, 0] - t0, m[i, 1] - m[i, 0], m[i, 2] - m[i, 1], m[i, 3] - m[i, 2],
                                                   m[i, 0] - m[i - 1, 0] if i else 0, prod[i] - t0, epi[i] - t0))
+    ep = np.stack([t[2048:2304], t[2304:2560], t[2560:2816]], 1)
+    k = int((ep[:, 0] != 0).sum())
+    if k > 40:
+        d = ep[8:k - 2]
+        print("epilogue warp 2 (cycles, median): tfull->released %.0f, store_row %.0f, row period %.0f" % (
+            np.median(d[:, 1] - d[:, 0]), np.median(d[:, 2] - d[:, 1]), np.median(np.diff(d[:, 0]))))
+        print("  store_row samples:", [int(v) for v in (d[:24, 2] - d[:24, 1])])
+        print("  idle before tfull (prev store end -> tfull seen):", [int(v) for v in (d[1:25, 0] - d[:24, 2])])
     n = int((m[:, 0] != 0).sum())
     w = t[2560:3072].reshape(256, 2)
     print("ready counter seen at stages 100..123:", [int(v) for v in w[100:124, 0]])
