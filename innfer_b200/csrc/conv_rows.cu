@@ -104,6 +104,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     p.trace[3072 + blockIdx.x * 8 + 1] = clock64();
   });
 
+  // Programmatic dependent launch (p.pdl): let the next conv of the stream take this SM as soon as this CTA leaves it;
+  // everything below up to pdl_wait() touches only this kernel's own constants (weights, bias), shared memory and TMEM.
+  pdl_launch_dependents();
   const int S = p.stages;
   const uint32_t stage_bytes = (uint32_t)p.kc * kRowPx * 16;
   const uint32_t w_total = (uint32_t)(p.nch / 2) * 3u * 2u * NB * 16u;
@@ -151,6 +154,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t w_base = smem_u32(smem);
   const uint32_t ring_base = w_base + w_total;
+  // activations (TMA loads, residual reads, output stores) belong to the previous kernels of the stream: every warp but
+  // the producer, which first starts the weight copies, waits for them here
+  if (warp != 0) pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -162,6 +168,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         const uint32_t n = (w_total - off) < 32768u ? (w_total - off) : 32768u;
         bulk_load(w_base + off, reinterpret_cast<const uint8_t*>(p.w) + (size_t)rank * w_total + off, n, wb);
       }
+      pdl_wait();
       int s = 0;
       uint32_t ph = 0;
       ROWS_TRACE(int tcount = 0);
@@ -559,26 +566,29 @@ int launch_rows_res(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int)e;
   const long long T = (long long)(PAIR ? (p.nstrips + 1) / 2 : p.nstrips) * p.H;
-  int grid = T < num_sms ? (int)T : num_sms;
-  if (!PAIR) {
-    kern<<<grid, rows_threads(COUT, false), smem_bytes, stream>>>(*tmap_in, p);
-    return (int)cudaGetLastError();
-  }
-  // one cluster of two CTAs per worker
-  long long workers = num_sms / 2;
+  long long workers = PAIR ? num_sms / 2 : num_sms;   // PAIR: one cluster of two CTAs per worker
   if (T < workers) workers = T;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(2 * workers));
-  cfg.blockDim = dim3(rows_threads(COUT, true));
+  cfg.gridDim = dim3((unsigned)(PAIR ? 2 * workers : workers));
+  cfg.blockDim = dim3(rows_threads(COUT, PAIR));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeClusterDimension;
-  attr.val.clusterDim.x = 2;
-  attr.val.clusterDim.y = 1;
-  attr.val.clusterDim.z = 1;
-  cfg.attrs = &attr;
-  cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (p.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
   return (int)cudaLaunchKernelEx(&cfg, kern, *tmap_in, p);
 }
 

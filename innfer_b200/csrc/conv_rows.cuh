@@ -42,6 +42,7 @@ struct ConvRowsParams {
   int lrelu;
   float slope;
   int pair;              // 1: clusters of two CTAs, M = 256 MMAs, half of the weight columns per CTA (conv_rows.cu)
+  int pdl;               // 1: programmatic dependent launch -- the prologue overlaps the previous kernel's tail
   long long* trace;      // debugging: clock64 samples of CTA 0 (see tests/gpu_bringup.py --stage trace), or null
 };
 

@@ -348,6 +348,8 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   p.res_ys = in.Wtot * 8;
   p.w = pair ? L.d_wrows_pair : L.d_wrows;
   p.pair = pair ? 1 : 0;
+  static const int pdl = getenv("INNFER_PDL") ? atoi(getenv("INNFER_PDL")) : 1;   // A/B switch
+  p.pdl = pdl;
   p.bias = L.d_bias;
   p.lrelu = ep.lrelu ? 1 : 0;
   p.slope = ep.slope;

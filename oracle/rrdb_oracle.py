@@ -296,6 +296,139 @@ def ppon_forward(sd, x, scale, alpha=1.0):
     return out_c, out_s, out_p
 
 
+# ----------------------------------------------------------------------------- PAN
+
+
+def pan_upsample_indices(scale):
+    """Indices of (upconv, PA.conv, HRconv) inside PAN.upsample and whether HRconv is followed by the LeakyReLU.
+
+    pa_upconv_block (PAN_arch.py:11-20) puts the SAME LeakyReLU instance twice into its Sequential.  With one
+    block (scale 2, 3) B.sequential returns that Sequential as is (block.py:199-202) and both run; with several
+    blocks it is flattened through ``children()`` (block.py:204-207), which yields a module once, so the
+    activation after HRconv disappears and a block contributes five entries."""
+    n_up = {1: 0, 2: 1, 3: 1, 4: 2, 8: 3}[scale]
+    if n_up == 1:
+        return [(1, 2, 4)], True
+    return [(5 * i + 1, 5 * i + 2, 5 * i + 4) for i in range(n_up)], False
+
+
+def make_pan_state_dict(scale=4, nb=16, nf=40, unf=24, in_nc=3, out_nc=3, seed=0, gamma=0.7, self_attention=True,
+                        double_scpa=False):
+    """Default-initialised PAN weights in the construction order of PAN.__init__ (PAN_arch.py:107-169): conv_first,
+    SCPA blocks (conv1_a, conv1_b, k1, PACnv k2/k3/k4, conv3 -- SCPA.__init__ 66-84), trunk_conv, the FSA Conv1d
+    projections (block.py:421-431), the upsampler blocks, conv_last.  FSA.gamma initialises to 0 (which would switch
+    the attention branch off), so it is set to ``gamma`` here."""
+    torch.manual_seed(seed)
+    sd = OrderedDict()
+    if scale == 1:
+        unf = nf
+    gw = nf // 2
+
+    def put(name, cout, cin, k=3, bias=True, conv1d=False):
+        if conv1d:
+            conv = torch.nn.Conv1d(cin, cout, 1)
+        else:
+            conv = torch.nn.Conv2d(cin, cout, k, 1, k // 2, bias=bias)
+        sd[name + ".weight"] = conv.weight.detach().clone()
+        if bias:
+            sd[name + ".bias"] = conv.bias.detach().clone()
+
+    def trunk(name):
+        for b in range(nb):
+            pre = "%s.%d." % (name, b)
+            put(pre + "conv1_a", gw, nf, 1, False)
+            put(pre + "conv1_b", gw, nf, 1, False)
+            put(pre + "k1.0", gw, gw, 3, False)
+            put(pre + "PACnv.k2", gw, gw, 1)
+            put(pre + "PACnv.k3", gw, gw, 3, False)
+            put(pre + "PACnv.k4", gw, gw, 3, False)
+            put(pre + "conv3", nf, 2 * gw, 1, False)
+
+    put("conv_first", nf, in_nc)
+    trunk("SCPA_trunk")
+    put("trunk_conv", nf, nf)
+    if double_scpa:
+        trunk("SCPA_trunk2")
+        put("trunk_conv2", nf, nf)
+    if self_attention:
+        sd["FSA.gamma"] = torch.full((1,), float(gamma))
+        put("FSA.conv_f", nf // 8, nf, conv1d=True)
+        put("FSA.conv_g", nf // 8, nf, conv1d=True)
+        put("FSA.conv_h", nf, nf, conv1d=True)
+    blocks, _ = pan_upsample_indices(scale)
+    cin = nf
+    for (iu, ia, ih) in blocks:
+        put("upsample.%d" % iu, unf, cin)
+        put("upsample.%d.conv" % ia, unf, unf, 1)
+        put("upsample.%d" % ih, unf, unf)
+        cin = unf
+    put("conv_last", out_nc, unf)
+    return sd
+
+
+def pan_self_attention(sd, x, poolsize=4):
+    """SelfAttentionBlock.forward with max_pool (block.py:434-473): attention over the 4x4-max-pooled map, bicubic
+    resize of the result back to the input size, gamma * out + input."""
+    b, c, hgt, wid = x.shape
+    p = F.max_pool2d(x, poolsize, poolsize)
+    n = p.shape[2] * p.shape[3]
+    v = p.reshape(b, c, n)
+    f = torch.einsum("oc,bcn->bon", sd["FSA.conv_f.weight"][:, :, 0], v) + sd["FSA.conv_f.bias"][None, :, None]
+    g = torch.einsum("oc,bcn->bon", sd["FSA.conv_g.weight"][:, :, 0], v) + sd["FSA.conv_g.bias"][None, :, None]
+    h = torch.einsum("oc,bcn->bon", sd["FSA.conv_h.weight"][:, :, 0], v) + sd["FSA.conv_h.bias"][None, :, None]
+    s = torch.einsum("bci,bcj->bij", f, g)            # s[i, j] = <f_i, g_j>
+    att = torch.softmax(s, dim=-1)
+    o = torch.einsum("bcj,bij->bci", h, att).reshape(b, c, p.shape[2], p.shape[3])
+    o = F.interpolate(o, size=(hgt, wid), mode="bicubic", align_corners=False)
+    return sd["FSA.gamma"] * o + x
+
+
+def pan_scpa(sd, pre, x):
+    """SCPA.forward (PAN_arch.py:86-103) with PACnv.forward (48-57)."""
+    def c(name, t, k):
+        return F.conv2d(t, sd[pre + name + ".weight"], sd.get(pre + name + ".bias"), padding=k // 2)
+
+    a = F.leaky_relu(c("conv1_a", x, 1), 0.2)
+    bb = F.leaky_relu(c("conv1_b", x, 1), 0.2)
+    a = F.leaky_relu(c("k1.0", a, 3), 0.2)
+    y = torch.sigmoid(c("PACnv.k2", bb, 1))
+    bb = F.leaky_relu(c("PACnv.k4", c("PACnv.k3", bb, 3) * y, 3), 0.2)
+    return c("conv3", torch.cat([a, bb], 1), 1) + x
+
+
+def pan_forward(sd, x, scale):
+    """PAN.forward (PAN_arch.py:171-222), 'nearest' upsampler."""
+    def conv(name, t):
+        w = sd[name + ".weight"]
+        return F.conv2d(t, w, sd.get(name + ".bias"), padding=w.shape[-1] // 2)
+
+    def trunk(name, conv_name, t):
+        nb = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith(name + "."))
+        for b in range(nb):
+            t = pan_scpa(sd, "%s.%d." % (name, b), t)
+        return conv(conv_name, t)
+
+    with torch.no_grad():
+        fea = conv("conv_first", x)
+        t = trunk("SCPA_trunk", "trunk_conv", fea)
+        if "trunk_conv2.weight" in sd:
+            t = trunk("SCPA_trunk2", "trunk_conv2", t)
+        fea = fea + t
+        if "FSA.gamma" in sd:
+            fea = pan_self_attention(sd, fea)
+        blocks, hr_act = pan_upsample_indices(scale)
+        f = 3 if scale == 3 else 2
+        for (iu, ia, ih) in blocks:
+            u = conv("upsample.%d" % iu, F.interpolate(fea, scale_factor=float(f), mode="nearest"))
+            u = F.leaky_relu(u * torch.sigmoid(conv("upsample.%d.conv" % ia, u)), 0.2)
+            fea = conv("upsample.%d" % ih, u)
+            if hr_act:
+                fea = F.leaky_relu(fea, 0.2)
+        out = conv("conv_last", fea)
+        ilr = F.interpolate(x, scale_factor=float(scale), mode="bilinear", align_corners=True) if scale > 1 else x
+        return out + ilr
+
+
 # ----------------------------------------------------------------------------- tiling / blending
 
 

@@ -86,6 +86,28 @@ def test_ppon_fixture(name):
             np.testing.assert_allclose(got.numpy(), g[key], rtol=0, atol=2e-5)
 
 
+PAN_FIXTURES = ["pan_s4_nb2_40x48_p32.npz", "pan_s2_nb1_36x44_p32.npz", "pan_s3_nb1_24x28_p32.npz",
+                "pan_s1_nb1_33x40_p32.npz"]
+
+
+@pytest.mark.parametrize("name", PAN_FIXTURES)
+def test_pan_fixture(name):
+    """PAN: oracle weights recipe, whole-image forward and chop_forward vs the reference."""
+    g = golden(name)
+    scale = int(g["scale"])
+    sd = O.make_pan_state_dict(scale=scale, nb=int(g["nb"]), seed=int(g["seed"]), gamma=float(g["gamma"]))
+    assert sorted(sd.keys()) == sorted(g["keys"])
+    np.testing.assert_array_equal(np.array([float(sd[k].double().sum()) for k in g["keys"]]), g["wsum"])
+    assert str(g["arch"]) == "pan"
+    x = O.np2tensor(synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"])))
+    np.testing.assert_allclose(O.pan_forward(sd, x, scale).numpy(), g["whole"], rtol=0, atol=2e-5)
+    y = O.chop_forward(sd, x, patch_size=int(g["patch"]), scale=scale, forward=lambda t: O.pan_forward(sd, t, scale))
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)
+    # the attention branch is live in these fixtures (FSA.gamma initialises to 0 in the reference)
+    sd0 = dict(sd, **{"FSA.gamma": sd["FSA.gamma"] * 0})
+    assert (O.pan_forward(sd0, x, scale) - O.pan_forward(sd, x, scale)).abs().max() > 1e-3
+
+
 def test_tile_geometry():
     g = golden("tile_geometry.npz")
     for key in g.files:

@@ -75,6 +75,28 @@ def ppon_fixtures(td):
                                                           out_p=op.numpy().astype(np.float32))))
 
 
+def pan_fixtures(td):
+    # ---- G4e: PAN: auto-detected from 'SCPA_trunk.0.conv1_a.weight' (run.py:50-53); pixel and
+    # self attention, bicubic / bilinear resampling.  Scale 2 keeps the LeakyReLU after HRconv, scale 4 loses it.
+    for scale, nb, (h, w) in ((4, 2, (40, 48)), (2, 1, (36, 44)), (3, 1, (24, 28)), (1, 1, (33, 40))):
+        torch.manual_seed(23)
+        net = get_network(get_network_G_config({"type": "pan", "nb": nb}, scale)).eval()
+        with torch.no_grad():
+            net.FSA.gamma.fill_(0.7)
+        model = ref_run.Model.__new__(ref_run.Model)
+        model.arch, model.scale, model.model, model.chop, model.device = "pan", scale, net, True, torch.device("cpu")
+        img = image(24, h, w)
+        y = model.chop_forward(ref_utils.np2tensor(img), patch_size=32, step=0.5)
+        with torch.no_grad():
+            whole = net(ref_utils.np2tensor(img))
+        np.savez_compressed(os.path.join(OUT, "pan_s%d_nb%d_%dx%d_p32.npz" % (scale, nb, h, w)), img_seed=24,
+                            h=h, w=w, patch=32, seed=23, gamma=0.7, scale=scale, nb=nb, arch=model.arch,
+                            keys=np.array(list(net.state_dict().keys())),
+                            wsum=np.array([float(v.double().sum()) for v in net.state_dict().values()]),
+                            y=y.numpy().astype(np.float32), u8=ref_utils.tensor2np(y.detach()),
+                            whole=whole.numpy().astype(np.float32))
+
+
 def main():
     torch.set_num_threads(8)
     # ---- G1: weights recipe: the oracle's make_state_dict must reproduce the reference init.
@@ -161,6 +183,7 @@ def main():
                                 y=y.numpy().astype(np.float32), u8=ref_utils.tensor2np(y.detach()))
 
         ppon_fixtures(td)
+        pan_fixtures(td)
 
     # ---- G5: tile geometry of extract_patches_2d for a list of sizes
     geo = {}
@@ -233,9 +256,9 @@ def main():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "ppon":
+    if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] in ("ppon", "pan"):
         torch.set_num_threads(8)
         with tempfile.TemporaryDirectory() as _td:
-            ppon_fixtures(_td)
+            (ppon_fixtures if sys.argv[2] == "ppon" else pan_fixtures)(_td)
     else:
         main()
