@@ -77,6 +77,20 @@ typedef struct innfer_ppon_cfg {
   int32_t fp16;
 } innfer_ppon_cfg;
 
+/* Constructor kwargs of PAN (architectures/PAN_arch.py:104-106) as produced by get_network_G_config
+ * (utils/defaults.py:78-89); ups_inter_mode is 'nearest'.  SURVEY.md 8(f) rank 3. */
+typedef struct innfer_pan_cfg {
+  int32_t in_nc;
+  int32_t out_nc;          /* == in_nc (the bilinear skip adds the input image to the output) */
+  int32_t nf;              /* 40; multiple of 8, at most 64 */
+  int32_t unf;             /* 24; channels of the upsampling stages (nf when scale == 1) */
+  int32_t nb;              /* SCPA blocks per trunk (16) */
+  int32_t scale;           /* 1, 2, 3, 4, 8 */
+  int32_t self_attention;  /* FSA block (max-pooled self attention) after the trunk */
+  int32_t double_scpa;     /* second SCPA trunk + trunk_conv2 */
+  int32_t fp16;
+} innfer_pan_cfg;
+
 typedef struct innfer_tile {
   int32_t y0, x0; /* low-res origin of the tile */
 } innfer_tile;
@@ -98,6 +112,11 @@ int innfer_srresnet_create(const innfer_srresnet_cfg* cfg, int device, innfer_rr
  * which is what run.py uses (run.py:191-192,220-221).  Keys: "CFEM.0", "CFEM.1.sub.<i>.RB<r>.{c1,d1..d8,c2}",
  * "CFEM.1.sub.<nb>", "SFEM|PFEM.<0|1>.RB<r>.*", "CRM|SRM|PRM.<1,4,6,8>" (4x). */
 int innfer_ppon_create(const innfer_ppon_cfg* cfg, int device, innfer_rrdb** out);
+/* PAN handle (same calls as above work on it).  Keys: "conv_first", "SCPA_trunk.<i>.{conv1_a,conv1_b,k1.0,
+ * PACnv.k2,PACnv.k3,PACnv.k4,conv3}", "trunk_conv", "FSA.{gamma,conv_f,conv_g,conv_h}", "upsample.<1,2.conv,4,..>",
+ * "conv_last"; with several upsampling stages the reference drops the LeakyReLU after HRconv (block.py:204-207
+ * flattens through children(), which yields the shared activation instance once) and so does this path. */
+int innfer_pan_create(const innfer_pan_cfg* cfg, int device, innfer_rrdb** out);
 /* one state-dict entry under its REFERENCE key name ("model.0.weight",
  * "model.1.sub.3.RDB2.conv4.0.bias", "model.1.sub.23.weight", "model.10.bias", ...); host fp32. */
 int innfer_rrdb_load(innfer_rrdb* h, const char* key, const float* host_data, const int64_t* shape,

@@ -36,6 +36,11 @@ class PPONCfg(ctypes.Structure):
                 ("scale", ctypes.c_int32), ("alpha", ctypes.c_float), ("fp16", ctypes.c_int32)]
 
 
+class PANCfg(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("in_nc", "out_nc", "nf", "unf", "nb", "scale", "self_attention", "double_scpa", "fp16")]
+
+
 class Tile(ctypes.Structure):
     _fields_ = [("y0", ctypes.c_int32), ("x0", ctypes.c_int32)]
 
@@ -50,6 +55,7 @@ _PROTOS = {
     "innfer_rrdb_create": (_i, [ctypes.POINTER(RRDBCfg), _i, ctypes.POINTER(_vp)]),
     "innfer_srresnet_create": (_i, [ctypes.POINTER(SRResNetCfg), _i, ctypes.POINTER(_vp)]),
     "innfer_ppon_create": (_i, [ctypes.POINTER(PPONCfg), _i, ctypes.POINTER(_vp)]),
+    "innfer_pan_create": (_i, [ctypes.POINTER(PANCfg), _i, ctypes.POINTER(_vp)]),
     "innfer_rrdb_load": (_i, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(ctypes.c_int64), _i]),
     "innfer_rrdb_finalize": (_i, [_vp]),
     "innfer_rrdb_destroy": (None, [_vp]),

@@ -1,6 +1,6 @@
 """get_network -- mirror of the reference's architectures/__init__.py:5-40 for the hot path."""
 
-_OUT_OF_SCOPE = ("mrrdb_net", "pan_net", "unet_net", "resnet_net", "wbcunet_net")
+_OUT_OF_SCOPE = ("mrrdb_net", "unet_net", "resnet_net", "wbcunet_net")
 
 
 def get_network(opt_net):
@@ -15,6 +15,9 @@ def get_network(opt_net):
     if kind == "ppon":
         from . import PPON_arch
         return PPON_arch.PPON(**opt_net)
+    if kind == "pan_net":
+        from . import PAN_arch
+        return PAN_arch.PAN(**opt_net)
     if kind in _OUT_OF_SCOPE:
         raise NotImplementedError(
             "Model [%s] exists in the reference but is outside the B200 RRDB hot-path scope "

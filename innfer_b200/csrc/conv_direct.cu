@@ -28,6 +28,7 @@ struct DirectParams {
   float alpha2;
   int dil;              // dilation (taps at multiples of dil), <= MAXD of the instantiation
   int act_after_res;    // LeakyReLU after the residual adds
+  int gate;             // res1 multiplies sigmoid(conv) instead of being added
   float* raw;           // optional pre-activation copy (layout of out)
   int raw_CT, raw_chunk0;
 };
@@ -99,8 +100,14 @@ conv_direct_kernel(const __grid_constant__ DirectParams p) {
       const float4* r = reinterpret_cast<const float4*>(
           p.res1 + (((size_t)b * p.res1_CT + p.res1_chunk0 + ch) * oplane + opix) * 8);
       const float4 a = r[0], c = r[1];
-      f[0] = f[0] * p.alpha1 + a.x; f[1] = f[1] * p.alpha1 + a.y; f[2] = f[2] * p.alpha1 + a.z; f[3] = f[3] * p.alpha1 + a.w;
-      f[4] = f[4] * p.alpha1 + c.x; f[5] = f[5] * p.alpha1 + c.y; f[6] = f[6] * p.alpha1 + c.z; f[7] = f[7] * p.alpha1 + c.w;
+      if (p.gate) {   // res1 * sigmoid(conv)
+        const float rv[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = rv[e] * (1.f / (1.f + expf(-f[e])));
+      } else {
+        f[0] = f[0] * p.alpha1 + a.x; f[1] = f[1] * p.alpha1 + a.y; f[2] = f[2] * p.alpha1 + a.z; f[3] = f[3] * p.alpha1 + a.w;
+        f[4] = f[4] * p.alpha1 + c.x; f[5] = f[5] * p.alpha1 + c.y; f[6] = f[6] * p.alpha1 + c.z; f[7] = f[7] * p.alpha1 + c.w;
+      }
     }
     if (p.res2) {
       const float4* r = reinterpret_cast<const float4*>(
@@ -179,6 +186,8 @@ int conv_direct_run(const ConvLayer& L, ChunkView in, int B, int H, int W, Chunk
   p.alpha2 = ep.alpha2;
   p.dil = L.dil;
   p.act_after_res = ep.act_after_res ? 1 : 0;
+  p.gate = ep.gate ? 1 : 0;
+  if (ep.gate && !ep.res1.base) return -9;
   p.raw = reinterpret_cast<float*>(ep.raw_out.base);
   p.raw_CT = ep.raw_out.CT;
   p.raw_chunk0 = ep.raw_out.chunk0;

@@ -352,8 +352,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 rv = __half22float2(hp[e]);
-                  f[2 * e] = f[2 * e] * p.alpha1 + rv.x;
-                  f[2 * e + 1] = f[2 * e + 1] * p.alpha1 + rv.y;
+                  if (p.gate) {
+                    f[2 * e] = rv.x / (1.f + __expf(-f[2 * e]));
+                    f[2 * e + 1] = rv.y / (1.f + __expf(-f[2 * e + 1]));
+                  } else {
+                    f[2 * e] = f[2 * e] * p.alpha1 + rv.x;
+                    f[2 * e + 1] = f[2 * e + 1] * p.alpha1 + rv.y;
+                  }
                 }
               }
               if (p.res2 != nullptr) {

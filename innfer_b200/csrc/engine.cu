@@ -14,6 +14,7 @@
 #include "color_fix.cuh"
 #include "conv_direct.cuh"
 #include "layers.cuh"
+#include "pan_ops.cuh"
 #include "pixel_ops.cuh"
 
 using namespace innfer;
@@ -23,10 +24,14 @@ namespace {
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 
+thread_local int g_code = 0;
+
 int fail(int code, const std::string& msg) {
   g_err = msg;
+  g_code = code;
   return code;
 }
+int g_err_code() { return g_code; }   // code of the last fail() on this thread
 int cuda_fail(cudaError_t e, const char* what) {
   return fail(INNFER_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
@@ -67,7 +72,7 @@ PixelDType to_pix(int dtype) { return dtype == INNFER_F16 ? kF16 : (dtype == INN
 
 struct innfer_rrdb {
   innfer_rrdb_cfg cfg;
-  int arch = 0;            // 0: RRDBNet (ESRGAN), 1: SRResNet (SRGAN generator)
+  int arch = 0;            // 0: RRDBNet (ESRGAN), 1: SRResNet (SRGAN generator), 2: PPON, 3: PAN
   float res_scale = 1.f;   // SRResNet residual scaling
   bool ps_mode = true;     // SRResNet upsampler: pixelshuffle (default) or upconv
   int device = 0;
@@ -86,6 +91,13 @@ struct innfer_rrdb {
   float ppon_alpha = 1.f;
   std::vector<ConvLayer> prb;
   std::vector<ConvLayer> ptail[3];
+  // PAN (arch 3): conv_first = fea, conv_last = hr1; prb = SCPA convs [trunk][nb][conv1ab, k1, k3, k2, k4, conv3];
+  // ptail[0] = trunk_conv(s); ups = [stage][upconv, PA conv, HRconv]; the FSA projections as one fp32 matrix
+  int pan_unf = 24;
+  bool pan_sa = true, pan_double = false, pan_hr_act = false;
+  float pan_gamma = 0.f;
+  float* d_pan_w = nullptr;
+  float* d_pan_b = nullptr;
   TmapCache cache;
   // workspace
   DevBuf in_tiles, feat, xbuf[3], hrbuf[2], out_tiles, img_in, img_out;
@@ -112,6 +124,8 @@ struct innfer_rrdb {
       for (auto& l : t) conv_layer_free(l);
     for (auto& b : pbuf) b.release();
     for (auto& b : paux) b.release();
+    if (d_pan_w) cudaFree(d_pan_w);
+    if (d_pan_b) cudaFree(d_pan_b);
     in_tiles.release();
     feat.release();
     for (auto& b : xbuf) b.release();
@@ -177,6 +191,130 @@ int build_ps_layer(innfer_rrdb* h, ConvLayer& L, const std::string& prefix, int 
   return 0;
 }
 
+// layer from weights assembled on the host (PAN: merged / re-indexed 1x1 convs); `bias` may be null
+int build_custom(innfer_rrdb* h, ConvLayer& L, const std::string& what, const std::vector<float>& w, const float* bias,
+                 int Cout, int Cin, int ksize) {
+  std::string err;
+  int rc = conv_layer_build(L, w.data(), bias, Cout, Cin, 1, err, ksize, 1);
+  if (rc) return fail(rc == -2 ? INNFER_E_UNSUPPORTED : INNFER_E_CUDA, what + ": " + err);
+  if (!h->cfg.fp16) {
+    rc = conv_direct_upload(L);
+    if (rc) return fail(INNFER_E_CUDA, what + ": fp32 weight upload failed");
+  }
+  return 0;
+}
+
+// a loaded parameter with exactly this shape, or null (error recorded)
+const Param* need_param(innfer_rrdb* h, const std::string& key, std::initializer_list<int64_t> shape) {
+  auto it = h->params.find(key);
+  if (it == h->params.end()) {
+    fail(INNFER_E_STATE, "missing key " + key);
+    return nullptr;
+  }
+  if (it->second.shape != std::vector<int64_t>(shape)) {
+    fail(INNFER_E_INVALID, "size mismatch for " + key);
+    return nullptr;
+  }
+  return &it->second;
+}
+
+// PAN keys (PAN_arch.py:107-169; upsampler indices through block.sequential, block.py:197-210)
+int finalize_pan(innfer_rrdb* h) {
+  const auto& c = h->cfg;
+  const int nf = c.nf, gw = nf / 2, G = (gw + 15) / 16 * 16, unf = h->pan_unf;
+  int rc;
+  size_t expected = 0;
+  if ((rc = build_layer(h, h->fea, "conv_first", nf, c.in_nc, 1))) return rc;
+  expected += 2;
+  const int ntrunk = h->pan_double ? 2 : 1;
+  h->prb.resize((size_t)ntrunk * c.nb * 6);
+  h->ptail[0].resize(ntrunk);
+  for (int t = 0; t < ntrunk; ++t) {
+    const std::string tn = t ? "SCPA_trunk2." : "SCPA_trunk.";
+    for (int b = 0; b < c.nb; ++b) {
+      const std::string pre = tn + std::to_string(b) + ".";
+      ConvLayer* L = &h->prb[((size_t)t * c.nb + b) * 6];
+      const Param* wa = need_param(h, pre + "conv1_a.weight", {gw, nf, 1, 1});
+      const Param* wb = need_param(h, pre + "conv1_b.weight", {gw, nf, 1, 1});
+      const Param* w3 = need_param(h, pre + "conv3.weight", {nf, 2 * gw, 1, 1});
+      if (!wa || !wb || !w3) return g_err_code();
+      // both 1x1 input convs as one: rows [0, gw) = conv1_a, [G, G + gw) = conv1_b, zero rows in between
+      std::vector<float> wab((size_t)2 * G * nf, 0.f);
+      for (int r = 0; r < gw; ++r)
+        for (int k = 0; k < nf; ++k) {
+          wab[(size_t)r * nf + k] = wa->data[(size_t)r * nf + k];
+          wab[(size_t)(G + r) * nf + k] = wb->data[(size_t)r * nf + k];
+        }
+      if ((rc = build_custom(h, L[0], pre + "conv1_a|b", wab, nullptr, 2 * G, nf, 1))) return rc;
+      if ((rc = build_layer(h, L[1], pre + "k1.0", gw, gw, 1, 3, false))) return rc;
+      if ((rc = build_layer(h, L[2], pre + "PACnv.k3", gw, gw, 1, 3, false))) return rc;
+      if ((rc = build_layer(h, L[3], pre + "PACnv.k2", gw, gw, 1, 1, true))) return rc;
+      if ((rc = build_layer(h, L[4], pre + "PACnv.k4", gw, gw, 1, 3, false))) return rc;
+      // conv3 reads the padded concat: input channel k of branch a sits at k, of branch b at G + k
+      std::vector<float> wc((size_t)nf * 2 * G, 0.f);
+      for (int r = 0; r < nf; ++r)
+        for (int k = 0; k < gw; ++k) {
+          wc[(size_t)r * 2 * G + k] = w3->data[(size_t)r * 2 * gw + k];
+          wc[(size_t)r * 2 * G + G + k] = w3->data[(size_t)r * 2 * gw + gw + k];
+        }
+      if ((rc = build_custom(h, L[5], pre + "conv3", wc, nullptr, nf, 2 * G, 1))) return rc;
+      expected += 8;
+    }
+    if ((rc = build_layer(h, h->ptail[0][t], t ? "trunk_conv2" : "trunk_conv", nf, nf, 1))) return rc;
+    expected += 2;
+  }
+  if (h->pan_sa) {
+    const int cq = nf / 8;
+    const Param* ga = need_param(h, "FSA.gamma", {1});
+    const Param* wf = need_param(h, "FSA.conv_f.weight", {cq, nf, 1});
+    const Param* bf = need_param(h, "FSA.conv_f.bias", {cq});
+    const Param* wg = need_param(h, "FSA.conv_g.weight", {cq, nf, 1});
+    const Param* bg = need_param(h, "FSA.conv_g.bias", {cq});
+    const Param* wh = need_param(h, "FSA.conv_h.weight", {nf, nf, 1});
+    const Param* bh = need_param(h, "FSA.conv_h.bias", {nf});
+    if (!ga || !wf || !bf || !wg || !bg || !wh || !bh) return g_err_code();
+    expected += 7;
+    h->pan_gamma = ga->data[0];
+    constexpr int R = 2 * kPanQK + kPanRow;
+    std::vector<float> wcat((size_t)R * kPanRow, 0.f), bcat(R, 0.f);
+    for (int r = 0; r < cq; ++r) {
+      for (int k = 0; k < nf; ++k) {
+        wcat[(size_t)r * kPanRow + k] = wf->data[(size_t)r * nf + k];
+        wcat[(size_t)(kPanQK + r) * kPanRow + k] = wg->data[(size_t)r * nf + k];
+      }
+      bcat[r] = bf->data[r];
+      bcat[kPanQK + r] = bg->data[r];
+    }
+    for (int r = 0; r < nf; ++r) {
+      for (int k = 0; k < nf; ++k) wcat[(size_t)(2 * kPanQK + r) * kPanRow + k] = wh->data[(size_t)r * nf + k];
+      bcat[2 * kPanQK + r] = bh->data[r];
+    }
+    CU_TRY(cudaMalloc(&h->d_pan_w, wcat.size() * sizeof(float)));
+    CU_TRY(cudaMalloc(&h->d_pan_b, bcat.size() * sizeof(float)));
+    CU_TRY(cudaMemcpy(h->d_pan_w, wcat.data(), wcat.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->d_pan_b, bcat.data(), bcat.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  // one stage: its Sequential is used as is and keeps both activations; several: flattened, five entries per stage
+  h->pan_hr_act = h->n_up == 1;
+  h->ups.resize((size_t)h->n_up * 3);
+  for (int i = 0; i < h->n_up; ++i) {
+    const int base = h->n_up == 1 ? 0 : 5 * i;
+    ConvLayer* L = &h->ups[(size_t)i * 3];
+    if ((rc = build_layer(h, L[0], "upsample." + std::to_string(base + 1), unf, i ? unf : nf, h->up_factor))) return rc;
+    if ((rc = build_layer(h, L[1], "upsample." + std::to_string(base + 2) + ".conv", unf, unf, 1, 1))) return rc;
+    if ((rc = build_layer(h, L[2], "upsample." + std::to_string(base + 4), unf, unf, 1))) return rc;
+    expected += 6;
+  }
+  if ((rc = build_layer(h, h->hr1, "conv_last", c.out_nc, h->n_up ? unf : nf, 1))) return rc;
+  expected += 2;
+  if (h->params.size() != expected)
+    return fail(INNFER_E_INVALID, "unexpected keys in state dict (" + std::to_string(h->params.size()) + " loaded, " +
+                                      std::to_string(expected) + " expected)");
+  h->params.clear();
+  h->finalized = true;
+  return 0;
+}
+
 // run one conv in the handle's precision mode
 int run_conv(innfer_rrdb* h, const ConvLayer& L, ChunkView in, int B, int H, int W, ChunkView out,
              int out_nchunks, const Epilogue& ep, cudaStream_t st) {
@@ -231,6 +369,27 @@ int ensure_workspace(innfer_rrdb* h, int B, int hgt, int wid) {
   const int s = h->cfg.scale;
   int rc = 0;
   rc |= h->in_tiles.ensure(px * h->in_ct() * e8);
+  if (h->arch == 3) {
+    // PAN: trunk buffers (channels padded to 16), the two SCPA branch pairs, PACnv scratch, HR ping-pong, ILR, attention
+    const int nfC = (h->cfg.nf + 15) / 16 * 2, gc = (h->cfg.nf / 2 + 15) / 16 * 2, ufC = (h->pan_unf + 15) / 16 * 2;
+    for (int i = 0; i < 3; ++i) rc |= h->pbuf[i].ensure(px * nfC * e8);
+    for (int i = 3; i < 5; ++i) rc |= h->pbuf[i].ensure(px * 2 * gc * e8);
+    for (int i = 5; i < 7; ++i) rc |= h->pbuf[i].ensure(px * gc * e8);
+    const size_t hpx3 = px * s * s;
+    if (s > 1)
+      for (auto& b : h->hrbuf) rc |= b.ensure(hpx3 * ufC * e8);
+    rc |= h->paux[0].ensure(hpx3 * e8);
+    const size_t npool = (size_t)B * (hgt / 4) * (wid / 4);
+    rc |= h->paux[1].ensure((npool + 1) * (3 * kPanRow + 2 * kPanQK) * sizeof(float));
+    if (rc) {
+      h->in_tiles.release();
+      for (auto& b : h->hrbuf) b.release();
+      for (auto& b : h->pbuf) b.release();
+      for (auto& b : h->paux) b.release();
+      return fail(INNFER_E_NOMEM, "workspace allocation failed");
+    }
+    return 0;
+  }
   rc |= h->feat.ensure(px * h->nf_ct() * e8);
   if (h->arch != 2)
     for (auto& b : h->xbuf) rc |= b.ensure(px * h->cat_ct() * e8);
@@ -450,7 +609,127 @@ int forward_tiles_ppon(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, b
   return tail(h->ptail[2], *res, &out_s, h->ppon_alpha, dst, compact);                  // out_p = alpha * PRM(..) + out_s
 }
 
+// PAN.forward (PAN_arch.py:171-222) on the tiled layout.  SCPA (86-103) as six convs:
+//   AB = lrelu(conv1_a | conv1_b (x))            one 1x1 conv, each branch padded to a multiple of 16 channels
+//   CD[a] = lrelu(k1(AB[a]));  T = k3(AB[b]);  G = T * sigmoid(k2(AB[b]))   (gate epilogue);  CD[b] = lrelu(k4(G))
+//   x' = conv3(CD) + x                           1x1 conv over the padded concat (weights re-indexed at load time)
+// then trunk_conv + fea, the max-pooled self-attention block (pan_ops.cu), the pixel-attention upsampling stages
+// (upconv with the nearest upsample folded in, u * sigmoid(conv1x1(u)) -> lrelu, HRconv) and conv_last + bilinear ILR.
+int forward_tiles_pan(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool compact, cudaStream_t st) {
+  const auto& c = h->cfg;
+  const int nfc = c.nf / 8, nfC = (c.nf + 15) / 16 * 2, gc = (c.nf / 2 + 15) / 16 * 2;
+  const int ufc = (h->pan_unf + 7) / 8, ufC = (h->pan_unf + 15) / 16 * 2;
+  const size_t e8 = 8 * h->esz();
+  const bool f16 = c.fp16 != 0;
+  int rc;
+  DevBuf *X0 = &h->pbuf[0], *X1 = &h->pbuf[1], *X2 = &h->pbuf[2];
+  DevBuf &AB = h->pbuf[3], &CD = h->pbuf[4], &T = h->pbuf[5], &G = h->pbuf[6];
+  // chunks [first, CT) of every image are read (against zero weights) but never written: keep them finite
+  auto zero_pad = [&](DevBuf& b, int CT, int first, size_t plane_px) -> int {
+    if (first >= CT) return 0;
+    CU_TRY(cudaMemset2DAsync(reinterpret_cast<uint8_t*>(b.p) + (size_t)first * plane_px * e8, (size_t)CT * plane_px * e8, 0,
+                             (size_t)(CT - first) * plane_px * e8, (size_t)B, st));
+    return 0;
+  };
+  const size_t lr_px = (size_t)hgt * wid;
+  for (DevBuf* x : {X0, X1, X2})
+    if ((rc = zero_pad(*x, nfC, nfc, lr_px))) return rc;
+  Epilogue plain, act;
+  act.lrelu = true;
+  if ((rc = run_conv(h, h->fea, view(h->in_tiles, h->in_ct(), 0), B, hgt, wid, view(*X0, nfC, 0), nfc, plain, st))) return rc;
+  DevBuf* cur = X0;
+  const int ntrunk = h->pan_double ? 2 : 1;
+  for (int t = 0; t < ntrunk; ++t) {
+    for (int b = 0; b < c.nb; ++b) {
+      const ConvLayer* L = &h->prb[((size_t)t * c.nb + b) * 6];
+      DevBuf* nxt = (cur == X1) ? X2 : X1;
+      if ((rc = run_conv(h, L[0], view(*cur, nfC, 0), B, hgt, wid, view(AB, 2 * gc, 0), 2 * gc, act, st))) return rc;
+      if ((rc = run_conv(h, L[1], view(AB, 2 * gc, 0), B, hgt, wid, view(CD, 2 * gc, 0), gc, act, st))) return rc;
+      if ((rc = run_conv(h, L[2], view(AB, 2 * gc, gc), B, hgt, wid, view(T, gc, 0), gc, plain, st))) return rc;
+      Epilogue gate;
+      gate.gate = true;
+      gate.res1 = view(T, gc, 0);
+      if ((rc = run_conv(h, L[3], view(AB, 2 * gc, gc), B, hgt, wid, view(G, gc, 0), gc, gate, st))) return rc;
+      if ((rc = run_conv(h, L[4], view(G, gc, 0), B, hgt, wid, view(CD, 2 * gc, gc), gc, act, st))) return rc;
+      Epilogue res;
+      res.res1 = view(*cur, nfC, 0);
+      if ((rc = run_conv(h, L[5], view(CD, 2 * gc, 0), B, hgt, wid, view(*nxt, nfC, 0), nfc, res, st))) return rc;
+      cur = nxt;
+    }
+    DevBuf* nxt = (cur == X1) ? X2 : X1;
+    Epilogue e;
+    if (t == ntrunk - 1) e.res1 = view(*X0, nfC, 0);   // fea + trunk (PAN_arch.py:180-185)
+    if ((rc = run_conv(h, h->ptail[0][t], view(*cur, nfC, 0), B, hgt, wid, view(*nxt, nfC, 0), nfc, e, st))) return rc;
+    cur = nxt;
+  }
+  if (h->pan_sa) {
+    const int hp = hgt / 4, wp = wid / 4;
+    if (hp < 1 || wp < 1) return fail(INNFER_E_UNSUPPORTED, "PAN self-attention needs images of at least 4x4 pixels");
+    const size_t n = (size_t)B * hp * wp;
+    float* pooled = reinterpret_cast<float*>(h->paux[1].p);
+    float* hv = pooled + n * kPanRow;
+    float* att = hv + n * kPanRow;
+    float* fq = att + n * kPanRow;
+    float* gk = fq + n * kPanQK;
+    DevBuf* nxt = (cur == X1) ? X2 : X1;
+    int r;
+    if (f16) r = launch_pan_maxpool(reinterpret_cast<const __half*>(cur->p), nfC, nfc, B, hgt, wid, 4, pooled, st);
+    else r = launch_pan_maxpool(reinterpret_cast<const float*>(cur->p), nfC, nfc, B, hgt, wid, 4, pooled, st);
+    if (!r) r = launch_pan_proj(pooled, (long long)n, nfc * 8, h->d_pan_w, h->d_pan_b, fq, gk, hv, st);
+    if (!r) r = launch_pan_attention(fq, gk, hv, B, hp * wp, nfc * 8, att, st);
+    if (!r) {
+      if (f16)
+        r = launch_pan_bicubic_add(att, hp, wp, reinterpret_cast<const __half*>(cur->p), nfC,
+                                   reinterpret_cast<__half*>(nxt->p), nfC, nfc, B, hgt, wid, h->pan_gamma, st);
+      else
+        r = launch_pan_bicubic_add(att, hp, wp, reinterpret_cast<const float*>(cur->p), nfC,
+                                   reinterpret_cast<float*>(nxt->p), nfC, nfc, B, hgt, wid, h->pan_gamma, st);
+    }
+    g_launches.fetch_add(4, std::memory_order_relaxed);
+    if (r) return fail(INNFER_E_CUDA, "PAN self-attention launch failed");
+    cur = nxt;
+  }
+  ChunkView curv = view(*cur, nfC, 0);
+  int ch = hgt, cw = wid;
+  DevBuf *P = &h->hrbuf[0], *Q = &h->hrbuf[1];
+  for (int i = 0; i < h->n_up; ++i) {
+    const ConvLayer* L = &h->ups[(size_t)i * 3];
+    const int f = L[0].up;
+    const size_t px = (size_t)(ch * f) * (cw * f);
+    if ((rc = zero_pad(*P, ufC, ufc, px))) return rc;
+    if ((rc = run_conv(h, L[0], curv, B, ch, cw, view(*P, ufC, 0), ufc, plain, st))) return rc;
+    ch *= f;
+    cw *= f;
+    if ((rc = zero_pad(*Q, ufC, ufc, px))) return rc;   // Q held this stage's input until the upconv above
+    Epilogue pa;                                        // lrelu(u * sigmoid(conv1x1(u)))
+    pa.gate = true;
+    pa.res1 = view(*P, ufC, 0);
+    pa.lrelu = true;
+    pa.act_after_res = true;
+    if ((rc = run_conv(h, L[1], view(*P, ufC, 0), B, ch, cw, view(*Q, ufC, 0), ufc, pa, st))) return rc;
+    if ((rc = run_conv(h, L[2], view(*Q, ufC, 0), B, ch, cw, view(*P, ufC, 0), ufc, h->pan_hr_act ? act : plain, st))) return rc;
+    curv = view(*P, ufC, 0);
+    DevBuf* tmp = P;
+    P = Q;
+    Q = tmp;
+  }
+  {
+    int r;
+    if (f16) r = launch_pan_bilinear(reinterpret_cast<const __half*>(h->in_tiles.p), h->in_ct(), B, hgt, wid, c.scale,
+                                     reinterpret_cast<__half*>(h->paux[0].p), st);
+    else r = launch_pan_bilinear(reinterpret_cast<const float*>(h->in_tiles.p), h->in_ct(), B, hgt, wid, c.scale,
+                                 reinterpret_cast<float*>(h->paux[0].p), st);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (r) return fail(INNFER_E_CUDA, "PAN bilinear launch failed");
+  }
+  Epilogue last;
+  last.compact4 = compact;
+  last.res1 = view(h->paux[0], 1, 0);
+  return run_conv(h, h->hr1, curv, B, ch, cw, dst, (c.out_nc + 7) / 8, last, st);
+}
+
 int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool compact, cudaStream_t st) {
+  if (h->arch == 3) return forward_tiles_pan(h, B, hgt, wid, dst, compact, st);
   if (h->arch == 1) return forward_tiles_srresnet(h, B, hgt, wid, dst, compact, st);
   if (h->arch == 2) return forward_tiles_ppon(h, B, hgt, wid, dst, compact, st);
   const int nfc = h->nf_ct(), catc = h->cat_ct();
@@ -711,6 +990,24 @@ int innfer_ppon_create(const innfer_ppon_cfg* cfg, int device, innfer_rrdb** out
   return 0;
 }
 
+int innfer_pan_create(const innfer_pan_cfg* cfg, int device, innfer_rrdb** out) {
+  if (!cfg || !out) return fail(INNFER_E_INVALID, "null argument");
+  if (cfg->nf < 8 || cfg->nf > 64 || cfg->nf % 8) return fail(INNFER_E_UNSUPPORTED, "PAN: nf must be a multiple of 8, at most 64");
+  const int unf = cfg->scale == 1 ? cfg->nf : cfg->unf;   // PAN_arch.py:111-112
+  if (unf < 1 || unf > 64) return fail(INNFER_E_UNSUPPORTED, "PAN: unf must be in 1..64");
+  if (cfg->in_nc != cfg->out_nc || cfg->in_nc > 8)
+    return fail(INNFER_E_UNSUPPORTED, "PAN: in_nc must equal out_nc (the bilinear skip is added to the output) and be <= 8");
+  innfer_rrdb_cfg base = {cfg->in_nc, cfg->out_nc, 64, cfg->nb, 32, cfg->scale, 0, cfg->fp16};
+  int rc = innfer_rrdb_create(&base, device, out);
+  if (rc) return rc;
+  (*out)->cfg.nf = cfg->nf;
+  (*out)->arch = 3;
+  (*out)->pan_unf = unf;
+  (*out)->pan_sa = cfg->self_attention != 0;
+  (*out)->pan_double = cfg->double_scpa != 0;
+  return 0;
+}
+
 int innfer_rrdb_load(innfer_rrdb* h, const char* key, const float* host_data, const int64_t* shape, int ndim) {
   if (!h || !key || !host_data || !shape || ndim < 1 || ndim > 4) return fail(INNFER_E_INVALID, "bad argument");
   if (h->finalized) return fail(INNFER_E_STATE, "handle already finalized");
@@ -732,6 +1029,7 @@ int innfer_rrdb_finalize(innfer_rrdb* h) {
   if ((rc = set_device(h))) return rc;
   const auto& c = h->cfg;
   size_t expected = 0;
+  if (h->arch == 3) return finalize_pan(h);
   if (h->arch == 2) {
     // PPON keys (PPON_arch.py:24-63 through block.sequential's flattening)
     if ((rc = build_layer(h, h->fea, "CFEM.0", c.nf, c.in_nc, 1))) return rc;

@@ -61,6 +61,7 @@ struct Epilogue {
   bool compact4 = false;  // store out channels 0..3 as [tile][H][W][4] (8 bytes per pixel), see ConvTcParams
   bool act_after_res = false;  // LeakyReLU after the residual adds (PPON running sums) instead of before
   ChunkView raw_out;      // optional second destination for the pre-activation value (needs act_after_res)
+  bool gate = false;      // pixel attention (PAN_arch.py:22-36,48-57): v = res1 * sigmoid(conv + bias) instead of the add
 };
 
 // Build the packed fp16 weights (and phase tables) from OIHW fp32 weights.  `bias` may be null.

@@ -182,3 +182,13 @@ class PPONEngine(RRDBEngine):
         c = N.PPONCfg(cfg["in_nc"], cfg["out_nc"], cfg["nf"], cfg["nb"], cfg["scale"], float(cfg.get("alpha", 1.0)),
                       int(self.fp16))
         N.check(self.lib.innfer_ppon_create(ctypes.byref(c), self.index, ctypes.byref(self._h)))
+
+
+class PANEngine(RRDBEngine):
+    """Native handle for architectures.PAN_arch.PAN (same execution API as RRDBEngine)."""
+
+    def _create(self):
+        cfg = self.cfg
+        c = N.PANCfg(cfg["in_nc"], cfg["out_nc"], cfg["nf"], cfg["unf"], cfg["nb"], cfg["scale"],
+                     int(bool(cfg.get("self_attention", True))), int(bool(cfg.get("double_scpa", False))), int(self.fp16))
+        N.check(self.lib.innfer_pan_create(ctypes.byref(c), self.index, ctypes.byref(self._h)))

@@ -1,9 +1,9 @@
-"""Network config defaults -- mirror of the reference's utils/defaults.py:3-44 for the ESRGAN,
-SRResNet and PPON families (the others are outside the hot-path scope and raise NotImplementedError)."""
+"""Network config defaults -- mirror of the reference's utils/defaults.py:3-89 for the ESRGAN,
+SRResNet, PPON and PAN families (the others are outside the hot-path scope and raise NotImplementedError)."""
 
 _RRDB_ALIASES = ("rrdb_net", "esrgan", "esrgan-lite")
 _SRRESNET_ALIASES = ("sr_resnet", "srresnet", "srgan")
-_OTHER_KINDS = ("evsrgan", "mrrdb_net", "mesrgan", "pan", "pan_net",
+_OTHER_KINDS = ("evsrgan", "mrrdb_net", "mesrgan",
                 "unet_net", "unet", "resnet_net", "resnet", "wbcunet", "wbcunet_net")
 
 
@@ -66,6 +66,19 @@ def get_network_G_config(network_G, scale):
             "upscale": opts.pop("scale", scale),
             "act_type": opts.pop("net_act", None) or opts.pop("act_type", "leakyrelu"),
             "alpha": opts.pop("alpha", 1),
+        }
+    if kind in ("pan_net", "pan"):
+        return {
+            "type": "pan_net",
+            "in_nc": opts.pop("in_nc", 3),
+            "out_nc": opts.pop("out_nc", 3),
+            "nf": opts.pop("nf", 40),
+            "unf": opts.pop("unf", 24),
+            "nb": opts.pop("nb", 16),
+            "scale": opts.pop("scale", scale),
+            "self_attention": opts.pop("self_attention", True),
+            "double_scpa": opts.pop("double_scpa", False),
+            "ups_inter_mode": opts.pop("ups_inter_mode", "nearest"),
         }
     if kind in _OTHER_KINDS or kind.startswith(("unet_", "p2p_", "resnet_", "cg_")):
         raise NotImplementedError(

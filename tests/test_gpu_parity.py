@@ -277,6 +277,63 @@ def test_ppon_vs_reference_fixture(dev, name, fp16):
         assert ((y2 - ref).abs().max() / ref.abs().max()).item() <= 1e-4
 
 
+@pytest.mark.parametrize("name", ["pan_s4_nb2_40x48_p32.npz", "pan_s2_nb1_36x44_p32.npz", "pan_s3_nb1_24x28_p32.npz",
+                                  "pan_s1_nb1_33x40_p32.npz"])
+@pytest.mark.parametrize("fp16", [True, False])
+def test_pan_vs_reference_fixture(dev, name, fp16):
+    """PAN: SCPA blocks (merged 1x1 branches, sigmoid-gate epilogue, re-indexed 1x1 fusion), the
+    max-pooled self-attention block with its bicubic resize, pixel-attention upsampling stages (with the reference's
+    dropped-activation quirk at scale 4) and the bilinear skip -- module mirror on cuda vs the reference fixture."""
+    from innfer_b200 import run as R
+    from innfer_b200.architectures import get_network
+    from innfer_b200.utils import utils as U
+    from innfer_b200.utils.defaults import get_network_G_config
+    g = golden(name)
+    scale, nb = int(g["scale"]), int(g["nb"])
+    sd = O.make_pan_state_dict(scale=scale, nb=nb, seed=int(g["seed"]), gamma=float(g["gamma"]))
+    net = get_network(get_network_G_config({"type": "pan", "nb": nb}, scale)).eval()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+    if fp16:
+        net.half()
+    m = R.Model.__new__(R.Model)
+    m.arch, m.scale, m.model, m.chop = "pan", scale, net, True
+    img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))
+    x = U.np2tensor(img).to(dev)
+    x = x.half() if fp16 else x
+    y = m.chop_forward(x, patch_size=int(g["patch"]), step=0.5)
+    u8 = U.tensor2np(y)
+    assert np.abs(u8.astype(int) - g["u8"].astype(int)).max() <= 1 and psnr_u8(u8, g["u8"]) >= 50.0
+    if not fp16:
+        assert np.abs(y.cpu().numpy() - g["y"]).max() / np.abs(g["y"]).max() <= 1e-4
+    # un-chopped forward against the reference output of the whole image
+    m.chop = False
+    y2 = m(x).float().cpu().numpy()
+    assert np.abs(U.tensor2np(torch.from_numpy(y2)).astype(int) - O.tensor2np(torch.from_numpy(g["whole"])).astype(int)).max() <= 1
+    if not fp16:
+        assert np.abs(y2 - g["whole"]).max() / np.abs(g["whole"]).max() <= 1e-4
+
+
+def test_pan_attention_branch_is_live(dev):
+    """gamma = 0 (the reference's initial value) and gamma = 0.7 must differ on the CUDA path as they do in the oracle,
+    and a batch of two images must equal two single forwards (attention and resampling are per image)."""
+    from innfer_b200.architectures import get_network
+    from innfer_b200.utils.defaults import get_network_G_config
+    outs = []
+    x = torch.rand(2, 3, 28, 36, generator=torch.Generator().manual_seed(3))
+    for gamma in (0.0, 0.7):
+        sd = O.make_pan_state_dict(scale=2, nb=1, seed=9, gamma=gamma)
+        net = get_network(get_network_G_config({"type": "pan", "nb": 1}, 2)).eval()
+        net.load_state_dict(sd, strict=True)
+        y = net.to(dev)(x.to(dev)).cpu()
+        ref = O.pan_forward(sd, x, 2)
+        assert ((y - ref).abs().max() / ref.abs().max()).item() <= 1e-4
+        outs.append(y)
+        one = net(x[1:2].to(dev)).cpu()
+        assert torch.equal(one, y[1:2])
+    assert (outs[0] - outs[1]).abs().max().item() > 1e-3
+
+
 def test_python_api_model_chain_and_color_fix(dev, tmp_path, monkeypatch):
     """run.Model on cuda (fp16) + chaining + -cf, and the CLI, vs the reference fixture (config 3 shrunk)."""
     import cv2

@@ -124,6 +124,31 @@ def test_ppon_module_mirror_on_cpu(tmp_path):
         R.Model(_save(sd, tmp_path / "2x_ppon.pth"), "infer", 2, device=torch.device("cpu"))
 
 
+@pytest.mark.parametrize("name", ["pan_s4_nb2_40x48_p32.npz", "pan_s2_nb1_36x44_p32.npz"])
+def test_pan_module_mirror_on_cpu(name, tmp_path):
+    """The PAN module tree carries the reference's key names (including the upsampler indices that depend on how
+    block.sequential flattens: five entries per stage at scale 4, six at scale 2) and reproduces its output; run.Model
+    probes 'SCPA_trunk.0.conv1_a.weight' and builds the default depth (nb = 16) for it (run.py:50-53,157-163)."""
+    g = golden(name)
+    scale, nb = int(g["scale"]), int(g["nb"])
+    sd = O.make_pan_state_dict(scale=scale, nb=nb, seed=int(g["seed"]), gamma=float(g["gamma"]))
+    net = get_network(get_network_G_config({"type": "pan", "nb": nb}, scale)).eval()
+    assert list(net.state_dict().keys()) == list(g["keys"])
+    net.load_state_dict(sd, strict=True)
+    img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))
+    with torch.no_grad():
+        np.testing.assert_allclose(net(U.np2tensor(img)).numpy(), g["whole"], rtol=0, atol=2e-5)
+    m = R.Model.__new__(R.Model)
+    m.arch, m.scale, m.model, m.chop = "pan", scale, net, True
+    y = m.chop_forward(U.np2tensor(img), patch_size=int(g["patch"]), step=0.5)
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=2e-5)
+    assert get_network_G_config("pan", 4) == {
+        "type": "pan_net", "in_nc": 3, "out_nc": 3, "nf": 40, "unf": 24, "nb": 16, "scale": 4, "self_attention": True,
+        "double_scpa": False, "ups_inter_mode": "nearest"}
+    with pytest.raises(RuntimeError):   # a shallow checkpoint does not fit the default 16-block network (strict load)
+        R.Model(_save(sd, tmp_path / ("%dx_pan.pth" % scale)), "infer", scale, device=torch.device("cpu"))
+
+
 def test_infer_params_and_key_mapping(tmp_path):
     g = golden("load_logic.npz")
     for scale, nb in ((1, 2), (2, 3), (4, 23), (8, 1)):
@@ -185,9 +210,9 @@ def test_synth_recipe_matches_reference_init():
 
 def test_unknown_architectures_fail_loudly():
     with pytest.raises(NotImplementedError):
-        get_network({"type": "pan_net"})
+        get_network({"type": "unet_net"})
     with pytest.raises(NotImplementedError):
-        get_network_G_config({"type": "pan"}, 4)
+        get_network_G_config({"type": "unet_256"}, 1)
     with pytest.raises(Exception, match="Could not infer"):
         m = R.Model.__new__(R.Model)
         m.__dict__.update(model_path="x", arch="infer", scale=None, in_nc=3, out_nc=3, device="cpu", eval=True,
