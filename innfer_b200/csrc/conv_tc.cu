@@ -353,8 +353,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
                 for (int e = 0; e < 4; ++e) {
                   const float2 rv = __half22float2(hp[e]);
                   if (p.gate) {
-                    f[2 * e] = rv.x / (1.f + __expf(-f[2 * e]));
-                    f[2 * e + 1] = rv.y / (1.f + __expf(-f[2 * e + 1]));
+                    // approximate division: the IEEE one takes its slow path (a call) for the zero padding channels
+                    f[2 * e] = __fdividef(rv.x, 1.f + __expf(-f[2 * e]));
+                    f[2 * e + 1] = __fdividef(rv.y, 1.f + __expf(-f[2 * e + 1]));
                   } else {
                     f[2 * e] = f[2 * e] * p.alpha1 + rv.x;
                     f[2 * e + 1] = f[2 * e + 1] * p.alpha1 + rv.y;

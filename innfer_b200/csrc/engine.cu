@@ -279,14 +279,14 @@ int finalize_pan(innfer_rrdb* h) {
     std::vector<float> wcat((size_t)R * kPanRow, 0.f), bcat(R, 0.f);
     for (int r = 0; r < cq; ++r) {
       for (int k = 0; k < nf; ++k) {
-        wcat[(size_t)r * kPanRow + k] = wf->data[(size_t)r * nf + k];
-        wcat[(size_t)(kPanQK + r) * kPanRow + k] = wg->data[(size_t)r * nf + k];
+        wcat[(size_t)k * R + r] = wf->data[(size_t)r * nf + k];   // transposed: [input channel][row]
+        wcat[(size_t)k * R + kPanQK + r] = wg->data[(size_t)r * nf + k];
       }
       bcat[r] = bf->data[r];
       bcat[kPanQK + r] = bg->data[r];
     }
     for (int r = 0; r < nf; ++r) {
-      for (int k = 0; k < nf; ++k) wcat[(size_t)(2 * kPanQK + r) * kPanRow + k] = wh->data[(size_t)r * nf + k];
+      for (int k = 0; k < nf; ++k) wcat[(size_t)k * R + 2 * kPanQK + r] = wh->data[(size_t)r * nf + k];
       bcat[2 * kPanQK + r] = bh->data[r];
     }
     CU_TRY(cudaMalloc(&h->d_pan_w, wcat.size() * sizeof(float)));

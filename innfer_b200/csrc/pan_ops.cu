@@ -68,10 +68,10 @@ __global__ void pan_proj_kernel(const float* __restrict__ pooled, long long npix
   if (idx >= npix * R) return;
   const long long i = idx / R;
   const int j = (int)(idx % R);
-  const float* xr = pooled + i * kPanRow;
-  const float* wr = wcat + (size_t)j * kPanRow;
+  const float* xr = pooled + i * kPanRow;   // the same address across most of a warp (broadcast)
+  const float* wr = wcat + j;               // [channel][row]: consecutive rows -> consecutive addresses
   float s = 0.f;
-  for (int c = 0; c < nfp; ++c) s = fmaf(xr[c], wr[c], s);
+  for (int c = 0; c < nfp; ++c) s = fmaf(xr[c], wr[(size_t)c * R], s);
   s += bcat[j];
   if (j < kPanQK) f[i * kPanQK + j] = s;
   else if (j < 2 * kPanQK) g[i * kPanQK + j - kPanQK] = s;
@@ -133,8 +133,15 @@ pan_attention_kernel(const float* __restrict__ f, const float* __restrict__ g, c
       for (int e = 0; e < kPanQK; ++e) s = fmaf(q[e], s_g[j][e], s);
       const float p = expf(s - m);
       l += p;
+      const float4* hrow = reinterpret_cast<const float4*>(&s_h[j][0]);   // 16-byte broadcast loads
 #pragma unroll
-      for (int c = 0; c < NFP; ++c) acc[c] = fmaf(p, s_h[j][c], acc[c]);
+      for (int c4 = 0; c4 < NFP / 4; ++c4) {
+        const float4 v = hrow[c4];
+        acc[4 * c4 + 0] = fmaf(p, v.x, acc[4 * c4 + 0]);
+        acc[4 * c4 + 1] = fmaf(p, v.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(p, v.z, acc[4 * c4 + 2]);
+        acc[4 * c4 + 3] = fmaf(p, v.w, acc[4 * c4 + 3]);
+      }
     }
   }
   if (!live) return;

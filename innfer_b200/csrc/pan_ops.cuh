@@ -16,8 +16,9 @@ constexpr int kPanQK = 8;     // floats per pooled pixel in the query / key arra
 template <typename T>
 int launch_pan_maxpool(const T* x, int CT, int nchunks, int B, int H, int W, int pool, float* pooled, cudaStream_t st);
 
-// The three 1x1 Conv1d projections (block.py:452-454).  wcat: [2 * kPanQK + kPanRow][kPanRow] fp32, rows 0..7 =
-// conv_f, 8..15 = conv_g, 16.. = conv_h (zero rows / columns beyond the real sizes), bcat the matching biases.
+// The three 1x1 Conv1d projections (block.py:452-454).  wcat: the [2 * kPanQK + kPanRow] x [kPanRow] fp32 matrix with
+// rows 0..7 = conv_f, 8..15 = conv_g, 16.. = conv_h (zero rows / columns beyond the real sizes), stored TRANSPOSED
+// ([input channel][row]); bcat the matching biases.
 // nfp = channels rounded up to 8 (columns of `pooled` that the max-pool wrote).
 int launch_pan_proj(const float* pooled, long long npix, int nfp, const float* wcat, const float* bcat, float* f, float* g,
                     float* hv, cudaStream_t st);

@@ -346,6 +346,32 @@ def stage_ppon_time():
     return True
 
 
+def stage_pan_time():
+    """PAN at the reference's defaults (nf 40, unf 24, nb 16, self attention) on a 1920x1080 frame, fp16 and fp32:
+    device time per frame, and the share of the attention kernels (profile of one 95-tile batch via CUDA events)."""
+    from innfer_b200.engine import PANEngine
+    sd = O.make_pan_state_dict(scale=4, nb=16, seed=0)
+    H, W = 1080, 1920
+    din = torch.from_numpy(np.random.default_rng(0).integers(0, 256, (H, W, 3), dtype=np.uint8)).to(dev)
+    dout = torch.empty(4 * H, 4 * W, 3, dtype=torch.uint8, device=dev)
+    for fp16 in (True, False):
+        eng = PANEngine.from_state_dict(sd, dict(in_nc=3, out_nc=3, nf=40, unf=24, nb=16, scale=4, self_attention=True,
+                                                 double_scpa=False), dev, fp16=fp16)
+        for it in range(3):
+            l0 = N.kernel_launches()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.upscale_u8_device(din, 200, 0.5, out=dout)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            print("pan 1080p %s iter=%d: %.1f ms  %.1f out-Mpix/s  (%d launches)" %
+                  ("fp16" if fp16 else "fp32", it, ms, 16 * H * W / ms / 1e3, N.kernel_launches() - l0))
+        print("out mean", dout.float().mean().item())
+        eng.close()
+    return True
+
+
 def stage_trace_up():
     """clock64 trace of CTA 0 of the last conv_up launch of a frame (needs an INNFER_TRACE_BUILD=1 build)."""
     lib = N.load()
@@ -372,6 +398,21 @@ def stage_ppon_prof():
     from innfer_b200.engine import PPONEngine
     sd = O.make_ppon_state_dict(scale=4, nb=2, seed=0)
     eng = PPONEngine.from_state_dict(sd, dict(in_nc=3, out_nc=3, nf=64, nb=2, scale=4, alpha=1.0), dev, fp16=True)
+    H, W = 800, 1000
+    din = torch.from_numpy(np.random.default_rng(0).integers(0, 256, (H, W, 3), dtype=np.uint8)).to(dev)
+    dout = torch.empty(4 * H, 4 * W, 3, dtype=torch.uint8, device=dev)
+    eng.upscale_u8_device(din, 200, 0.5, out=dout)
+    torch.cuda.synchronize()
+    eng.close()
+    return True
+
+
+def stage_pan_prof():
+    """One 800x1000 frame (63 tiles) through the default PAN (nb = 16) for ncu launch lists."""
+    from innfer_b200.engine import PANEngine
+    sd = O.make_pan_state_dict(scale=4, nb=16, seed=0)
+    eng = PANEngine.from_state_dict(sd, dict(in_nc=3, out_nc=3, nf=40, unf=24, nb=16, scale=4, self_attention=True,
+                                             double_scpa=False), dev, fp16=True)
     H, W = 800, 1000
     din = torch.from_numpy(np.random.default_rng(0).integers(0, 256, (H, W, 3), dtype=np.uint8)).to(dev)
     dout = torch.empty(4 * H, 4 * W, 3, dtype=torch.uint8, device=dev)
@@ -474,6 +515,6 @@ if __name__ == "__main__":
     ap.add_argument("--stage", required=True)
     a = ap.parse_args()
     t0 = time.time()
-    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "trace_up": stage_trace_up, "ppon": stage_ppon, "ppon_prof": stage_ppon_prof, "ppon_time": stage_ppon_time, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
+    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "trace_up": stage_trace_up, "ppon": stage_ppon, "ppon_prof": stage_ppon_prof, "ppon_time": stage_ppon_time, "pan_time": stage_pan_time, "pan_prof": stage_pan_prof, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
     print("STAGE %s %s (%.1fs)" % (a.stage, "OK" if ok else "FAILED", time.time() - t0))
     sys.exit(0 if ok else 1)

@@ -314,6 +314,41 @@ def test_pan_vs_reference_fixture(dev, name, fp16):
         assert np.abs(y2 - g["whole"]).max() / np.abs(g["whole"]).max() <= 1e-4
 
 
+@pytest.mark.parametrize("kw,scale,hw,patch,fp16", [
+    (dict(nb=16), 4, (210, 260), 200, True),                       # reference defaults, 200-pixel tiles: 2500 x 2500 attention
+    (dict(nb=1, double_scpa=True), 2, (40, 52), 32, False),        # second trunk + trunk_conv2
+    (dict(nb=2, self_attention=False), 4, (36, 44), 32, False),    # no FSA block
+    (dict(nb=1, nf=64, unf=32), 2, (40, 52), 32, True),            # widest supported trunk
+    (dict(nb=1, nf=64, unf=32), 8, (20, 24), 32, False),           # three upsampling stages
+    (dict(nb=2, nf=16, unf=8, in_nc=1, out_nc=1), 2, (37, 45), 200, False),   # 8-channel branches, grey images
+])
+def test_pan_variants_vs_oracle(dev, kw, scale, hw, patch, fp16):
+    """PAN configurations beyond the reference fixtures against the (fixture-pinned) oracle, chop_forward included."""
+    from innfer_b200.architectures import get_network
+    from innfer_b200.utils import utils as U
+    from innfer_b200.utils.defaults import get_network_G_config
+    from innfer_b200 import run as R
+    sd = O.make_pan_state_dict(scale=scale, seed=31, **kw)
+    net = get_network(get_network_G_config(dict({"type": "pan"}, **kw), scale)).eval()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+    if fp16:
+        net.half()
+    nc = kw.get("in_nc", 3)
+    x = torch.rand(1, nc, *hw, generator=torch.Generator().manual_seed(4))
+    ref = O.chop_forward(sd, x, patch_size=patch, scale=scale, forward=lambda t: O.pan_forward(sd, t, scale))
+    m = R.Model.__new__(R.Model)
+    m.arch, m.scale, m.model, m.chop = "pan", scale, net, True
+    xd = x.to(dev).half() if fp16 else x.to(dev)
+    y = m.chop_forward(xd, patch_size=patch, step=0.5).float().cpu()
+    if fp16:
+        a, b = (y.clamp(0, 1) * 255).round(), (ref.clamp(0, 1) * 255).round()
+        assert (a - b).abs().max().item() <= 1
+        assert 10 * np.log10(255.0 ** 2 / max(((a - b) ** 2).mean().item(), 1e-12)) >= 50.0
+    else:
+        assert ((y - ref).abs().max() / ref.abs().max()).item() <= 1e-4
+
+
 def test_pan_attention_branch_is_live(dev):
     """gamma = 0 (the reference's initial value) and gamma = 0.7 must differ on the CUDA path as they do in the oracle,
     and a batch of two images must equal two single forwards (attention and resampling are per image)."""
