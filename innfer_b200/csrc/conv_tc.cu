@@ -72,7 +72,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tfull_bar = empty_bar + S;
-  uint64_t* set_bar = tfull_bar + 2;       // "accumulator set is drained" (4 epilogue warps arrive)
+  uint64_t* set_bar = tfull_bar + 2;       // "accumulator set is drained" (8 epilogue warps arrive)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(set_bar + 2);
   volatile uint32_t* ready_cnt = tmem_slot + 1;   // stages whose barriers the scout warp has seen complete
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
@@ -84,7 +84,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&tfull_bar[i]), 1);
-    for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&set_bar[i]), 4);
+    for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&set_bar[i]), 8);
     *ready_cnt = 0u;
     fence_mbar_init();
   }
@@ -257,7 +257,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       if (leader) umma_commit(smem_u32(&tfull_bar[set]));
       __syncwarp();
     }
-  } else if (warp == 6) {
+  } else if (warp == kConvScoutWarp) {
     // ------------------------------------------------------------ scout
     if (lane == 0) {
       int s = 0;
@@ -282,6 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   } else {
     // ------------------------------------------------------------ epilogue warps
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;   // sub-tiles j = grp, grp + 2, ... of every tile
     const int m = q * 32 + lane;
     const int r = m >> 3, cc = m & 7;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -296,7 +297,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       const int y = c.y0 + r;
       const int oy = y * p.up + p.ph_a[c.phase];
       const uint32_t sb = smem_u32(&set_bar[it & 1]);
-      for (int j = 0; j < c.jeff; ++j) {
+      if (grp >= c.jeff) {   // nothing of this tile for this group: its share of the set is "drained"
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sb);
+      }
+      for (int j = grp; j < c.jeff; j += 2) {
         const uint32_t tacc = tmem_base + lane_base + (uint32_t)(((it & 1) * p.J + j) * N);
         const int x = c.x0 + 8 * j + cc;
         const bool inside = (y < p.H) && (x < p.W);
@@ -329,7 +334,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
 #pragma unroll
         for (int g = 0; g < N / 16; ++g) tmem_ld16(tacc + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[g * 16]));
         tmem_ld_wait();
-        if (j == c.jeff - 1) {  // last accumulator of the tile is in registers: release the set
+        if (j + 2 >= c.jeff) {  // this group's last accumulator of the tile is in registers: release its share of the set
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(sb);

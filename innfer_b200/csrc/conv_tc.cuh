@@ -20,8 +20,9 @@
 // one.  The epilogue (bias, LeakyReLU, up to two scaled residual adds, fp16 pack) reads them with
 // tcgen05.ld and stores 16-byte channel chunks straight into the destination chunk slice.
 //
-// Warp roles (224 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4), warp 6 = scout: it waits on the stage and
+// Warp roles (352 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4; two groups of four warps that take the 128-pixel
+// sub-tiles of a tile alternately), warp 10 = scout: it waits on the stage and
 // accumulator-set barriers for the issuer and publishes the number of ready stages in shared memory
 // (an mbarrier wait on the issuing thread costs 170-260 cycles even when already satisfied).
 #pragma once
@@ -32,7 +33,8 @@
 
 namespace innfer {
 
-constexpr int kConvThreads = 224;           // + warp 6: scout (does the MMA warp's barrier waits)
+constexpr int kConvThreads = 352;         // producer, issuer, 8 epilogue warps, scout (does the issuer's barrier waits)
+constexpr int kConvScoutWarp = 10;
 constexpr int kPatchRows = 16;            // rows per CTA patch (= rows of one M=128 sub-patch)
 constexpr int kMaxPhases = 9;
 constexpr int kMaxTaps = 9;

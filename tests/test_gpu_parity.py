@@ -518,3 +518,34 @@ def test_full_size_properties_1080p(dev):
     out2 = eng.upscale_u8(shifted, 200, 0.5)
     assert np.array_equal(out[:, 800:6800], out2[:, 400:6400])
     eng.close()
+
+
+@pytest.mark.parametrize("family,n", [("srresnet", 2), ("pan", 2), ("ppon", 1)])
+def test_config4_small_models_on_512x512_batches(dev, family, n):
+    """BASELINE configs[3]: 4x SRResNet / PAN / PPON on 512x512 batches through the un-chopped batch forward
+    (fp16), against the oracle (SRResNet and PAN at their default depth, PPON with one content block to keep the CPU
+    side short).  PAN attends over the whole 128x128 pooled map here (16384 x 16384 attention per image)."""
+    from innfer_b200.architectures import get_network
+    from innfer_b200.utils.defaults import get_network_G_config
+    x = torch.rand(n, 3, 512, 512, generator=torch.Generator().manual_seed(11))
+    if family == "srresnet":
+        sd = O.make_srresnet_state_dict(scale=4, nb=16, seed=12)
+        net = get_network(get_network_G_config({"type": "sr_resnet", "nb": 16}, 4))
+        ref = O.srresnet_forward(sd, x, 4)
+    elif family == "pan":
+        sd = O.make_pan_state_dict(scale=4, nb=16, seed=12)
+        net = get_network(get_network_G_config({"type": "pan"}, 4))
+        ref = torch.cat([O.pan_forward(sd, x[i:i + 1], 4) for i in range(n)])
+    else:
+        sd = O.make_ppon_state_dict(scale=4, nb=1, seed=12)
+        net = get_network(get_network_G_config({"type": "ppon", "nb": 1}, 4))
+        ref = O.ppon_forward(sd, x, 4)[2]
+    net.load_state_dict(sd, strict=True)
+    net = net.eval().to(dev).half()
+    with torch.no_grad():
+        y = net(x.to(dev).half())
+    y = (y[2] if family == "ppon" else y).float().cpu()
+    assert y.shape == (n, 3, 2048, 2048)
+    a, b = (y.clamp(0, 1) * 255).round(), (ref.clamp(0, 1) * 255).round()
+    assert (a - b).abs().max().item() <= 1
+    assert 10 * np.log10(255.0 ** 2 / max(((a - b) ** 2).mean().item(), 1e-12)) >= 50.0
