@@ -96,11 +96,18 @@ conv_direct_kernel(const __grid_constant__ DirectParams p) {
       if (p.lrelu && !p.act_after_res) t = t > 0.f ? t : t * p.slope;
       f[e] = t;
     }
+    if (p.gate == 2 && ch < N / 16) {   // merged PACnv: column c times sigmoid(column N/2 + c)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float gv = acc[N / 2 + ch * 8 + e] + p.bias[N / 2 + ch * 8 + e];
+        f[e] *= 1.f / (1.f + expf(-gv));
+      }
+    }
     if (p.res1) {
       const float4* r = reinterpret_cast<const float4*>(
           p.res1 + (((size_t)b * p.res1_CT + p.res1_chunk0 + ch) * oplane + opix) * 8);
       const float4 a = r[0], c = r[1];
-      if (p.gate) {   // res1 * sigmoid(conv)
+      if (p.gate == 1) {   // res1 * sigmoid(conv)
         const float rv[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] = rv[e] * (1.f / (1.f + expf(-f[e])));
@@ -186,8 +193,9 @@ int conv_direct_run(const ConvLayer& L, ChunkView in, int B, int H, int W, Chunk
   p.alpha2 = ep.alpha2;
   p.dil = L.dil;
   p.act_after_res = ep.act_after_res ? 1 : 0;
-  p.gate = ep.gate ? 1 : 0;
+  p.gate = ep.gate ? 1 : (ep.self_gate ? 2 : 0);
   if (ep.gate && !ep.res1.base) return -9;
+  if (ep.self_gate && (ep.gate || out_nchunks > L.N / 16)) return -9;
   p.raw = reinterpret_cast<float*>(ep.raw_out.base);
   p.raw_CT = ep.raw_out.CT;
   p.raw_chunk0 = ep.raw_out.chunk0;

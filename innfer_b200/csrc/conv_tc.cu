@@ -352,12 +352,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
                 if (p.lrelu && !p.act_after_res) tv = lrelu_f(tv, p.slope);
                 f[e] = tv;
               }
+              if (p.gate == 2) {
+                constexpr int PC = (NCH / 2 > 0 ? NCH / 2 : 1);   // chunks per half
+                if (ch < PC) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float gv = __uint_as_float(v[(ch + PC) * 8 + e]) + s_bias[c.phase * N + (ch + PC) * 8 + e];
+                    f[e] = __fdividef(f[e], 1.f + __expf(-gv));
+                  }
+                }
+              }
               if (p.res1 != nullptr) {
                 const __half2* hp = reinterpret_cast<const __half2*>(&r1[ch]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 rv = __half22float2(hp[e]);
-                  if (p.gate) {
+                  if (p.gate == 1) {
                     // approximate division: the IEEE one takes its slow path (a call) for the zero padding channels
                     f[2 * e] = __fdividef(rv.x, 1.f + __expf(-f[2 * e]));
                     f[2 * e + 1] = __fdividef(rv.y, 1.f + __expf(-f[2 * e + 1]));

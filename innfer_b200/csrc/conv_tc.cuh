@@ -75,7 +75,8 @@ struct ConvTcParams {
   long long raw_bs, raw_cs;
   int raw_ys, raw_chunk0;
   int act_after_res;   // apply the LeakyReLU after the residual adds instead of before
-  int gate;            // res1 multiplies sigmoid(conv + bias) instead of being added (PAN pixel attention)
+  int gate;            // 1: res1 multiplies sigmoid(conv + bias) instead of being added (PAN pixel attention);
+                       // 2: column c is multiplied by sigmoid(column N/2 + c) of the same accumulator (merged PACnv)
   // wide SOURCE: B == 1, W == Wtot and a column decomposes as image * sep_pitch + x; columns with
   // x >= sep_w or image >= sep_nimg are separators: never computed, stored as zeros when the
   // destination is wide too (out_zero_sep), skipped otherwise.  sep_pitch == 0: tiled source.

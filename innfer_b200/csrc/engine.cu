@@ -91,7 +91,7 @@ struct innfer_rrdb {
   float ppon_alpha = 1.f;
   std::vector<ConvLayer> prb;
   std::vector<ConvLayer> ptail[3];
-  // PAN (arch 3): conv_first = fea, conv_last = hr1; prb = SCPA convs [trunk][nb][conv1ab, k1, k3, k2, k4, conv3];
+  // PAN (arch 3): conv_first = fea, conv_last = hr1; prb = SCPA convs [trunk][nb][conv1ab, k1, k3|k2, k4, conv3];
   // ptail[0] = trunk_conv(s); ups = [stage][upconv, PA conv, HRconv]; the FSA projections as one fp32 matrix
   int pan_unf = 24;
   bool pan_sa = true, pan_double = false, pan_hr_act = false;
@@ -227,13 +227,13 @@ int finalize_pan(innfer_rrdb* h) {
   if ((rc = build_layer(h, h->fea, "conv_first", nf, c.in_nc, 1))) return rc;
   expected += 2;
   const int ntrunk = h->pan_double ? 2 : 1;
-  h->prb.resize((size_t)ntrunk * c.nb * 6);
+  h->prb.resize((size_t)ntrunk * c.nb * 5);
   h->ptail[0].resize(ntrunk);
   for (int t = 0; t < ntrunk; ++t) {
     const std::string tn = t ? "SCPA_trunk2." : "SCPA_trunk.";
     for (int b = 0; b < c.nb; ++b) {
       const std::string pre = tn + std::to_string(b) + ".";
-      ConvLayer* L = &h->prb[((size_t)t * c.nb + b) * 6];
+      ConvLayer* L = &h->prb[((size_t)t * c.nb + b) * 5];
       const Param* wa = need_param(h, pre + "conv1_a.weight", {gw, nf, 1, 1});
       const Param* wb = need_param(h, pre + "conv1_b.weight", {gw, nf, 1, 1});
       const Param* w3 = need_param(h, pre + "conv3.weight", {nf, 2 * gw, 1, 1});
@@ -247,9 +247,22 @@ int finalize_pan(innfer_rrdb* h) {
         }
       if ((rc = build_custom(h, L[0], pre + "conv1_a|b", wab, nullptr, 2 * G, nf, 1))) return rc;
       if ((rc = build_layer(h, L[1], pre + "k1.0", gw, gw, 1, 3, false))) return rc;
-      if ((rc = build_layer(h, L[2], pre + "PACnv.k3", gw, gw, 1, 3, false))) return rc;
-      if ((rc = build_layer(h, L[3], pre + "PACnv.k2", gw, gw, 1, 1, true))) return rc;
-      if ((rc = build_layer(h, L[4], pre + "PACnv.k4", gw, gw, 1, 3, false))) return rc;
+      // PACnv's k3 (3x3) and k2 (1x1, bias) read the same tensor: one conv with 2 * G outputs, k2 as the centre tap of
+      // rows [G, G + gw); the epilogue multiplies column c by sigmoid(column G + c) (Epilogue.self_gate)
+      const Param* w_k3 = need_param(h, pre + "PACnv.k3.weight", {gw, gw, 3, 3});
+      const Param* w_k2 = need_param(h, pre + "PACnv.k2.weight", {gw, gw, 1, 1});
+      const Param* b_k2 = need_param(h, pre + "PACnv.k2.bias", {gw});
+      if (!w_k3 || !w_k2 || !b_k2) return g_err_code();
+      std::vector<float> wpa((size_t)2 * G * gw * 9, 0.f), bpa((size_t)2 * G, 0.f);
+      for (int r = 0; r < gw; ++r) {
+        for (int k = 0; k < gw; ++k) {
+          for (int t = 0; t < 9; ++t) wpa[((size_t)r * gw + k) * 9 + t] = w_k3->data[((size_t)r * gw + k) * 9 + t];
+          wpa[((size_t)(G + r) * gw + k) * 9 + 4] = w_k2->data[(size_t)r * gw + k];
+        }
+        bpa[G + r] = b_k2->data[r];
+      }
+      if ((rc = build_custom(h, L[2], pre + "PACnv.k3|k2", wpa, bpa.data(), 2 * G, gw, 3))) return rc;
+      if ((rc = build_layer(h, L[3], pre + "PACnv.k4", gw, gw, 1, 3, false))) return rc;
       // conv3 reads the padded concat: input channel k of branch a sits at k, of branch b at G + k
       std::vector<float> wc((size_t)nf * 2 * G, 0.f);
       for (int r = 0; r < nf; ++r)
@@ -257,7 +270,7 @@ int finalize_pan(innfer_rrdb* h) {
           wc[(size_t)r * 2 * G + k] = w3->data[(size_t)r * 2 * gw + k];
           wc[(size_t)r * 2 * G + G + k] = w3->data[(size_t)r * 2 * gw + gw + k];
         }
-      if ((rc = build_custom(h, L[5], pre + "conv3", wc, nullptr, nf, 2 * G, 1))) return rc;
+      if ((rc = build_custom(h, L[4], pre + "conv3", wc, nullptr, nf, 2 * G, 1))) return rc;
       expected += 8;
     }
     if ((rc = build_layer(h, h->ptail[0][t], t ? "trunk_conv2" : "trunk_conv", nf, nf, 1))) return rc;
@@ -374,7 +387,7 @@ int ensure_workspace(innfer_rrdb* h, int B, int hgt, int wid) {
     const int nfC = (h->cfg.nf + 15) / 16 * 2, gc = (h->cfg.nf / 2 + 15) / 16 * 2, ufC = (h->pan_unf + 15) / 16 * 2;
     for (int i = 0; i < 3; ++i) rc |= h->pbuf[i].ensure(px * nfC * e8);
     for (int i = 3; i < 5; ++i) rc |= h->pbuf[i].ensure(px * 2 * gc * e8);
-    for (int i = 5; i < 7; ++i) rc |= h->pbuf[i].ensure(px * gc * e8);
+    rc |= h->pbuf[5].ensure(px * gc * e8);
     const size_t hpx3 = px * s * s;
     if (s > 1)
       for (auto& b : h->hrbuf) rc |= b.ensure(hpx3 * ufC * e8);
@@ -609,9 +622,10 @@ int forward_tiles_ppon(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, b
   return tail(h->ptail[2], *res, &out_s, h->ppon_alpha, dst, compact);                  // out_p = alpha * PRM(..) + out_s
 }
 
-// PAN.forward (PAN_arch.py:171-222) on the tiled layout.  SCPA (86-103) as six convs:
+// PAN.forward (PAN_arch.py:171-222) on the tiled layout.  SCPA (86-103) as five convs:
 //   AB = lrelu(conv1_a | conv1_b (x))            one 1x1 conv, each branch padded to a multiple of 16 channels
-//   CD[a] = lrelu(k1(AB[a]));  T = k3(AB[b]);  G = T * sigmoid(k2(AB[b]))   (gate epilogue);  CD[b] = lrelu(k4(G))
+//   CD[a] = lrelu(k1(AB[a]));  G = k3(AB[b]) * sigmoid(k2(AB[b]))   (k3 | k2 as one conv, self-gate epilogue);
+//   CD[b] = lrelu(k4(G))
 //   x' = conv3(CD) + x                           1x1 conv over the padded concat (weights re-indexed at load time)
 // then trunk_conv + fea, the max-pooled self-attention block (pan_ops.cu), the pixel-attention upsampling stages
 // (upconv with the nearest upsample folded in, u * sigmoid(conv1x1(u)) -> lrelu, HRconv) and conv_last + bilinear ILR.
@@ -623,7 +637,7 @@ int forward_tiles_pan(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bo
   const bool f16 = c.fp16 != 0;
   int rc;
   DevBuf *X0 = &h->pbuf[0], *X1 = &h->pbuf[1], *X2 = &h->pbuf[2];
-  DevBuf &AB = h->pbuf[3], &CD = h->pbuf[4], &T = h->pbuf[5], &G = h->pbuf[6];
+  DevBuf &AB = h->pbuf[3], &CD = h->pbuf[4], &G = h->pbuf[5];
   // chunks [first, CT) of every image are read (against zero weights) but never written: keep them finite
   auto zero_pad = [&](DevBuf& b, int CT, int first, size_t plane_px) -> int {
     if (first >= CT) return 0;
@@ -641,19 +655,17 @@ int forward_tiles_pan(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bo
   const int ntrunk = h->pan_double ? 2 : 1;
   for (int t = 0; t < ntrunk; ++t) {
     for (int b = 0; b < c.nb; ++b) {
-      const ConvLayer* L = &h->prb[((size_t)t * c.nb + b) * 6];
+      const ConvLayer* L = &h->prb[((size_t)t * c.nb + b) * 5];
       DevBuf* nxt = (cur == X1) ? X2 : X1;
       if ((rc = run_conv(h, L[0], view(*cur, nfC, 0), B, hgt, wid, view(AB, 2 * gc, 0), 2 * gc, act, st))) return rc;
       if ((rc = run_conv(h, L[1], view(AB, 2 * gc, 0), B, hgt, wid, view(CD, 2 * gc, 0), gc, act, st))) return rc;
-      if ((rc = run_conv(h, L[2], view(AB, 2 * gc, gc), B, hgt, wid, view(T, gc, 0), gc, plain, st))) return rc;
       Epilogue gate;
-      gate.gate = true;
-      gate.res1 = view(T, gc, 0);
-      if ((rc = run_conv(h, L[3], view(AB, 2 * gc, gc), B, hgt, wid, view(G, gc, 0), gc, gate, st))) return rc;
-      if ((rc = run_conv(h, L[4], view(G, gc, 0), B, hgt, wid, view(CD, 2 * gc, gc), gc, act, st))) return rc;
+      gate.self_gate = true;
+      if ((rc = run_conv(h, L[2], view(AB, 2 * gc, gc), B, hgt, wid, view(G, gc, 0), gc, gate, st))) return rc;
+      if ((rc = run_conv(h, L[3], view(G, gc, 0), B, hgt, wid, view(CD, 2 * gc, gc), gc, act, st))) return rc;
       Epilogue res;
       res.res1 = view(*cur, nfC, 0);
-      if ((rc = run_conv(h, L[5], view(CD, 2 * gc, 0), B, hgt, wid, view(*nxt, nfC, 0), nfc, res, st))) return rc;
+      if ((rc = run_conv(h, L[4], view(CD, 2 * gc, 0), B, hgt, wid, view(*nxt, nfC, 0), nfc, res, st))) return rc;
       cur = nxt;
     }
     DevBuf* nxt = (cur == X1) ? X2 : X1;

@@ -282,7 +282,7 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
                          int out_nchunks, const Epilogue& ep, int num_sms, cudaStream_t stream) {
   static const int rows_mode = getenv("INNFER_ROWS") ? atoi(getenv("INNFER_ROWS")) : 7;  // bit 0: on, bit 1: Cout = 64 too, bit 2: CTA pairs (conv5)
   const int CR = L.Cout <= 16 ? 16 : L.Cout;   // kernel instantiation: 16 (the net's last conv), 32 or 64
-  if (!rows_mode || !in.wide() || L.d_wrows == nullptr || L.up != 1 || L.dil != 1 || ep.act_after_res || ep.raw_out.base || ep.gate ||
+  if (!rows_mode || !in.wide() || L.d_wrows == nullptr || L.up != 1 || L.dil != 1 || ep.act_after_res || ep.raw_out.base || ep.gate || ep.self_gate ||
       out_nchunks != (L.Cout + 7) / 8 || (out.wide() && (in.pitch != out.pitch || in.Wtot != out.Wtot)) ||
       (ep.compact4 && (out.wide() || L.Cout > 4)))
     return -100;
@@ -444,8 +444,9 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
       p.raw_chunk0 = ep.raw_out.chunk0;
     }
     p.act_after_res = ep.act_after_res ? 1 : 0;
-    p.gate = ep.gate ? 1 : 0;
+    p.gate = ep.gate ? 1 : (ep.self_gate ? 2 : 0);
     if (ep.gate && !ep.res1.base) return -9;
+    if (ep.self_gate && (ep.gate || out_nchunks > N / 16 || L.nphase != 1)) return -9;
     if (ep.res1.base) strides(ep.res1, p.res1_bs, p.res1_cs, p.res1_ys);
     if (ep.res2.base) strides(ep.res2, p.res2_bs, p.res2_cs, p.res2_ys);
   }
