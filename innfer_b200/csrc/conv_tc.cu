@@ -58,6 +58,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();   // the next kernel of the stream may take this SM as soon as this CTA leaves it
 
   const int Wh = 8 * p.J + 2 * p.dil;              // halo tile: Rh x Wh pixels
   const int Rh = kPatchRows + 2 * p.dil;
@@ -100,6 +101,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
 
   const uint32_t smem_base = smem_u32(smem);
 
+  // programmatic dependent launch: everything above touched only constants (bias), shared memory and TMEM; the warps
+  // that read or write activations wait here for the previous kernel of the stream
+  if (warp != 1 && warp != kConvScoutWarp) pdl_wait();
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -453,8 +457,17 @@ int launch_impl(const CUtensorMap* tmap_in, const ConvTcParams& p, int num_sms, 
   if (e != cudaSuccess) return (int)e;
   const int num_tiles = p.B * p.bands * p.cps * p.nphase;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  conv_tc_kernel<N><<<grid, kConvThreads, smem_bytes, stream>>>(*tmap_in, p);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, conv_tc_kernel<N>, *tmap_in, p);
 }
 
 }  // namespace

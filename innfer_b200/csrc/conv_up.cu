@@ -65,6 +65,7 @@ conv_up_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();   // the next kernel of the stream may take this SM as soon as this CTA leaves it
   const int S = p.stages;
   const uint32_t w_total = (uint32_t)kUpPhases * p.kslabs * kUpTaps * kUpTapUnits * 16u;
 
@@ -111,6 +112,7 @@ conv_up_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         const uint32_t n = (w_total - off) < 32768u ? (w_total - off) : 32768u;
         bulk_load(w_base + off, reinterpret_cast<const uint8_t*>(p.w) + off, n, wb);
       }
+      pdl_wait();   // weights are constants; the activations below belong to the previous kernel of the stream
       int s = 0;
       uint32_t ph = 0;
       UpIter ti;
@@ -207,6 +209,7 @@ conv_up_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     }
   } else {
     // ------------------------------------------------------------ epilogue warps
+    pdl_wait();
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int m = q * 32 + lane;
@@ -306,8 +309,17 @@ int launch_conv_up(const CUtensorMap* tmap_in, const ConvTcParams& p, int num_sm
   if (e != cudaSuccess) return (int)e;
   const long long tiles = (long long)p.B * p.bands * p.cps;
   const int grid = tiles < num_sms ? (int)tiles : num_sms;
-  conv_up_kernel<<<grid, kUpThreads, smem_bytes, stream>>>(*tmap_in, p);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kUpThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, conv_up_kernel, *tmap_in, p);
 }
 
 }  // namespace innfer

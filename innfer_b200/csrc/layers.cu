@@ -459,6 +459,8 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
   while (pw < cols) pw <<= 1;
   p.tmem_cols = pw;
   p.dil = L.dil;
+  static const int pdl = getenv("INNFER_PDL") ? atoi(getenv("INNFER_PDL")) : 1;   // A/B switch, as for conv_rows
+  p.pdl = pdl;
   const int stage_bytes = conv_tc_a_bytes(J, L.dil) + conv_tc_w_bytes(N, L.max_taps);
   int S = (232448 - kConvTailBytes) / stage_bytes;
   if (S > 8) S = 8;

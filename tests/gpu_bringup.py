@@ -372,6 +372,41 @@ def stage_pan_time():
     return True
 
 
+def stage_lat():
+    """Latency of small single-tile inputs (BASELINE configs[0] size, 64x64, and one 200x200 tile): launch-gap bound,
+    which is what programmatic dependent launch addresses (A/B with INNFER_PDL=0)."""
+    from innfer_b200.engine import PANEngine
+    sd = O.make_state_dict(scale=4, nb=23, seed=0)
+    h = make_handle(sd, fp16=True)
+    lib = N.load()
+    psd = O.make_pan_state_dict(scale=4, nb=16, seed=0)
+    pan = PANEngine.from_state_dict(psd, dict(in_nc=3, out_nc=3, nf=40, unf=24, nb=16, scale=4, self_attention=True,
+                                              double_scpa=False), dev, fp16=True)
+    for hw in (64, 200):
+        din = torch.from_numpy(np.random.default_rng(0).integers(0, 256, (hw, hw, 3), dtype=np.uint8)).to(dev)
+        dout = torch.empty(4 * hw, 4 * hw, 3, dtype=torch.uint8, device=dev)
+        for name in ("rrdb", "pan"):
+            best, host = 1e9, 1e9
+            for it in range(6):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                t0 = time.perf_counter()
+                if name == "rrdb":
+                    lib.innfer_rrdb_upscale_u8_device(h, din.data_ptr(), hw, hw, 200, 0.5, dout.data_ptr(), None)
+                else:
+                    pan.upscale_u8_device(din, 200, 0.5, out=dout)
+                t1 = time.perf_counter()
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    best = min(best, e0.elapsed_time(e1))
+                    host = min(host, (t1 - t0) * 1e3)
+            print("lat %s %dx%d: %.3f ms on the device, %.3f ms of host enqueue" % (name, hw, hw, best, host))
+    pan.close()
+    return True
+
+
 def stage_trace_up():
     """clock64 trace of CTA 0 of the last conv_up launch of a frame (needs an INNFER_TRACE_BUILD=1 build)."""
     lib = N.load()
@@ -515,6 +550,6 @@ if __name__ == "__main__":
     ap.add_argument("--stage", required=True)
     a = ap.parse_args()
     t0 = time.time()
-    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "trace_up": stage_trace_up, "ppon": stage_ppon, "ppon_prof": stage_ppon_prof, "ppon_time": stage_ppon_time, "pan_time": stage_pan_time, "pan_prof": stage_pan_prof, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
+    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "trace_up": stage_trace_up, "ppon": stage_ppon, "ppon_prof": stage_ppon_prof, "ppon_time": stage_ppon_time, "pan_time": stage_pan_time, "lat": stage_lat, "pan_prof": stage_pan_prof, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
     print("STAGE %s %s (%.1fs)" % (a.stage, "OK" if ok else "FAILED", time.time() - t0))
     sys.exit(0 if ok else 1)
