@@ -347,8 +347,14 @@ int run_conv(innfer_rrdb* h, const ConvLayer& L, ChunkView in, int B, int H, int
   return 0;
 }
 
-// Wide layout geometry (layers.cuh: ChunkView): images `wid + 1` columns apart, rows padded to 16 columns.
-int wide_pitch(int wid) { return wid + 1; }
+// Wide layout geometry (layers.cuh: ChunkView): images `wid + sep` columns apart, rows padded to 16 columns.  The
+// separator must be as wide as the horizontal reach of the widest conv of the net: 1 column for the plain 3x3 convs,
+// 8 for PPON's dilated convs (a single zero column let the taps at distance 2..8 read the neighbouring tile).
+// Set per call from the handle (ensure_workspace / forward_tiles); the separator columns are kept zero by every
+// kernel that writes a wide tensor.
+thread_local int g_wide_sep = 1;
+int wide_sep_of(const innfer_rrdb* h) { return h->arch == 2 ? 8 : 1; }
+int wide_pitch(int wid) { return wid + g_wide_sep; }
 int wide_cols(int B, int wid) { return (B * wide_pitch(wid) + 15) / 16 * 16; }
 
 ChunkView wview(DevBuf& b, int CT, int chunk0, int B, int wid, int up) {
@@ -376,6 +382,7 @@ ChunkView view(DevBuf& b, int CT, int chunk0) {
 }
 
 int ensure_workspace(innfer_rrdb* h, int B, int hgt, int wid) {
+  g_wide_sep = wide_sep_of(h);
   // sized for the wide layout of the fp16 path (one separator column per image, row padded to 16)
   const size_t px = (size_t)hgt * wide_cols(B, wid);
   const size_t e8 = 8 * h->esz();
@@ -432,6 +439,7 @@ int ensure_workspace(innfer_rrdb* h, int B, int hgt, int wid) {
 int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool compact, cudaStream_t st);
 
 int forward_tiles(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool compact, cudaStream_t st) {
+  g_wide_sep = wide_sep_of(h);
   if (!h->profiling) return forward_tiles_impl(h, B, hgt, wid, dst, compact, st);
   cudaEvent_t a, b;
   CU_TRY(cudaEventCreate(&a));
@@ -1410,6 +1418,7 @@ int innfer_conv3x3(const void* x, int n, int Cin, int hgt, int wid, const float*
                    int Cout, int up, int lrelu, const void* res1, float alpha1, void* y, int dtype,
                    int use_fp32_kernel, void* stream) {
   if (!x || !w_oihw || !y) return fail(INNFER_E_INVALID, "null argument");
+  g_wide_sep = 1;
   if (dtype != INNFER_F16 && dtype != INNFER_F32) return fail(INNFER_E_INVALID, "dtype must be F16 or F32");
   if (res1 && up != 1) return fail(INNFER_E_INVALID, "residual needs up == 1");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1489,6 +1498,7 @@ int innfer_conv3x3(const void* x, int n, int Cin, int hgt, int wid, const float*
 // `warm` untimed launches.  Long runs show the kernel's power-limited steady state.
 int innfer_debug_conv_loop(int Cin, int Cout, int B, int H, int W, int with_res, int warm, int iters, float* ms_out) {
   if (!ms_out) return fail(INNFER_E_INVALID, "null argument");
+  g_wide_sep = 1;
   int dev = 0;
   CU_TRY(cudaGetDevice(&dev));
   cudaDeviceProp prop;

@@ -549,3 +549,34 @@ def test_config4_small_models_on_512x512_batches(dev, family, n):
     a, b = (y.clamp(0, 1) * 255).round(), (ref.clamp(0, 1) * 255).round()
     assert (a - b).abs().max().item() <= 1
     assert 10 * np.log10(255.0 ** 2 / max(((a - b) ** 2).mean().item(), 1e-12)) >= 50.0
+
+
+@pytest.mark.parametrize("family", ["ppon", "pan", "srresnet"])
+def test_batch_forward_equals_single_forwards(dev, family):
+    """Images of a batch sit side by side in the wide layout (fp16 path): nothing may leak across the separator,
+    whatever the reach of the taps (PPON's dilated convs reach 8 pixels).  A batch of three must equal three singles
+    bit for bit, and the oracle within the fp16 tolerance."""
+    from innfer_b200.architectures import get_network
+    from innfer_b200.utils.defaults import get_network_G_config
+    x = torch.rand(3, 3, 24, 20, generator=torch.Generator().manual_seed(21))
+    if family == "ppon":
+        sd = O.make_ppon_state_dict(scale=2, nb=1, seed=22)
+        net = get_network(get_network_G_config({"type": "ppon", "nb": 1}, 2))
+        ref = O.ppon_forward(sd, x, 2)[2]
+    elif family == "pan":
+        sd = O.make_pan_state_dict(scale=2, nb=2, seed=22)
+        net = get_network(get_network_G_config({"type": "pan", "nb": 2}, 2))
+        ref = torch.cat([O.pan_forward(sd, x[i:i + 1], 2) for i in range(3)])
+    else:
+        sd = O.make_srresnet_state_dict(scale=2, nb=2, seed=22)
+        net = get_network(get_network_G_config({"type": "sr_resnet", "nb": 2}, 2))
+        ref = O.srresnet_forward(sd, x, 2)
+    net.load_state_dict(sd, strict=True)
+    net = net.eval().to(dev).half()
+    pick = (lambda t: t[2]) if family == "ppon" else (lambda t: t)
+    with torch.no_grad():
+        y = pick(net(x.to(dev).half())).float().cpu()
+        for i in range(3):
+            assert torch.equal(pick(net(x[i:i + 1].to(dev).half())).float().cpu(), y[i:i + 1]), "image %d" % i
+    a, b = (y.clamp(0, 1) * 255).round(), (ref.clamp(0, 1) * 255).round()
+    assert (a - b).abs().max().item() <= 1
