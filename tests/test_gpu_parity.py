@@ -580,3 +580,33 @@ def test_batch_forward_equals_single_forwards(dev, family):
             assert torch.equal(pick(net(x[i:i + 1].to(dev).half())).float().cpu(), y[i:i + 1]), "image %d" % i
     a, b = (y.clamp(0, 1) * 255).round(), (ref.clamp(0, 1) * 255).round()
     assert (a - b).abs().max().item() <= 1
+
+
+@pytest.mark.parametrize("fp16", [True, False])
+def test_ppon_dilated_branch_with_amplified_weights(dev, fp16):
+    """With default-initialised weights PPON's dilated convs move the output by about 2/255, so the 1/255 tolerance
+    says little about them.  Here their weights are 8x larger (they move the output by > 10/255, asserted), on a batch
+    of two images, and the tolerance stays 1/255 (fp16) / 1e-4 relative (fp32)."""
+    import re
+    from innfer_b200.architectures import get_network
+    from innfer_b200.utils.defaults import get_network_G_config
+    x = torch.rand(2, 3, 24, 28, generator=torch.Generator().manual_seed(5))
+    sd = O.make_ppon_state_dict(scale=2, nb=1, seed=22)
+    for k in sd:
+        if re.search(r"\.d\d\.weight$", k):
+            sd[k] = sd[k] * 8
+    ref = O.ppon_forward(sd, x, 2)[2]
+    sd0 = {k: (v * 0 if re.search(r"\.d[2-8]\.weight$", k) else v) for k, v in sd.items()}
+    assert (ref - O.ppon_forward(sd0, x, 2)[2]).abs().max().item() > 10 / 255
+    net = get_network(get_network_G_config({"type": "ppon", "nb": 1}, 2))
+    net.load_state_dict(sd, strict=True)
+    net = net.eval().to(dev)
+    xd = x.to(dev)
+    if fp16:
+        net, xd = net.half(), xd.half()
+    with torch.no_grad():
+        y = net(xd)[2].float().cpu()
+    if fp16:
+        assert (y - ref).abs().max().item() <= 1 / 255
+    else:
+        assert ((y - ref).abs().max() / ref.abs().max()).item() <= 1e-4
