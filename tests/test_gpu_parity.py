@@ -612,22 +612,24 @@ def test_ppon_dilated_branch_with_amplified_weights(dev, fp16):
         assert ((y - ref).abs().max() / ref.abs().max()).item() <= 1e-4
 
 
+@pytest.mark.parametrize("plus", [False, True])
 @pytest.mark.parametrize("fp16", [True, False])
-def test_rrdb_dense_blocks_with_amplified_weights(dev, fp16):
+def test_rrdb_dense_blocks_with_amplified_weights(dev, fp16, plus):
     """With default-initialised weights the inner convs of the dense blocks (conv2..conv4) move the 4x RRDB output by
     0.2/255 only (0.2 residual scaling twice), so the 1/255 tolerance of the fixture tests does not see them.  Here the
     dense-block weights are 4x larger: conv2..conv4 move the output by > 8/255 (asserted); batch of three images through
     the production layout, tolerance 1/255 (fp16) / 1e-4 relative (fp32)."""
     import re
     x = torch.rand(3, 3, 24, 28, generator=torch.Generator().manual_seed(5))
-    sd = O.make_state_dict(scale=4, nb=3, seed=3)
+    sd = O.make_state_dict(scale=4, nb=3, seed=3, plus=plus)   # plus: ESRGAN+ (conv1x1 branch, amplified too)
     for k in sd:
-        if re.search(r"RDB\d\.conv\d\.0\.weight$", k):
+        if re.search(r"RDB\d\.conv\d\.0\.weight$|conv1x1\.weight$", k):
             sd[k] = sd[k] * 4
     ref = O.rrdbnet_forward(sd, x)
     sd0 = {k: (v * 0 if re.search(r"RDB\d\.conv[2-4]\.0\.weight$", k) else v) for k, v in sd.items()}
     assert (ref - O.rrdbnet_forward(sd0, x)).abs().max().item() > 8 / 255
-    eng = _engine(sd, dev, fp16=fp16)
+    from innfer_b200.engine import RRDBEngine
+    eng = RRDBEngine.from_state_dict(sd, dict(in_nc=3, out_nc=3, nf=64, nb=3, gc=32, scale=4, plus=plus), dev, fp16=fp16)
     xd = x.to(dev).half() if fp16 else x.to(dev)
     y = eng.forward(xd).float().cpu()
     eng.close()
