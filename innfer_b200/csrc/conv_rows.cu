@@ -58,13 +58,16 @@ struct PieceIter {
   int H;
   // In pair mode (p.pair) the unit of work is a PAIR of neighbouring strips handled by the two CTAs of a cluster;
   // `m` then counts strip pairs and CTA `rank` works on strip 2m + rank.
-  __device__ __forceinline__ void init(const ConvRowsParams& p) {
+  // Dilation d > 1 (DILV kernels): the rows of one residue class c = y mod d form a sub-image of H = ceil(p.H / d)
+  // "virtual" rows in which the vertical taps are neighbours again; `m` then counts (strip, class) pairs,
+  // m = strip * d + c, and virtual row k is image row c + k * d (rows >= p.H read as zeros and are not stored).
+  __device__ __forceinline__ void init(const ConvRowsParams& p, int d = 1) {
     const long long worker = p.pair ? (blockIdx.x >> 1) : blockIdx.x;
     const long long nworkers = p.pair ? (gridDim.x >> 1) : gridDim.x;
-    const long long T = (long long)(p.pair ? (p.nstrips + 1) / 2 : p.nstrips) * p.H;
+    H = (p.H + d - 1) / d;
+    const long long T = (long long)(p.pair ? (p.nstrips + 1) / 2 : p.nstrips * d) * H;
     u = T * worker / nworkers;
     u1 = T * (worker + 1) / nworkers;
-    H = p.H;
   }
   __device__ __forceinline__ bool next(Piece& pc) {
     if (u >= u1) return false;
@@ -79,7 +82,7 @@ struct PieceIter {
   }
 };
 
-template <int COUT, int KSLABS, bool RES, bool PAIR>
+template <int COUT, int KSLABS, bool RES, bool PAIR, bool DILV = false>
 __global__ void __launch_bounds__(rows_threads(COUT, PAIR), 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvRowsParams p) {
   constexpr int N = 3 * COUT;                 // dy-major: column dy*COUT + co
@@ -108,6 +111,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   // everything below up to pdl_wait() touches only this kernel's own constants (weights, bias), shared memory and TMEM.
   pdl_launch_dependents();
   const int S = p.stages;
+  const int dl = DILV ? p.dil : 1;   // dilation (compile-time 1 for every kernel of the plain nets)
   const uint32_t stage_bytes = (uint32_t)p.kc * kRowPx * 16;
   const uint32_t w_total = (uint32_t)(p.nch / 2) * 3u * 2u * NB * 16u;
   uint8_t* bar_base = smem + w_total + (size_t)S * stage_bytes;
@@ -173,17 +177,19 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       uint32_t ph = 0;
       ROWS_TRACE(int tcount = 0);
       PieceIter it;
-      it.init(p);
+      it.init(p, dl);
       Piece pc;
       while (it.next(pc)) {
-        const int strip = PAIR ? 2 * pc.m + (int)rank : pc.m;
+        const int strip = PAIR ? 2 * pc.m + (int)rank : (DILV ? pc.m / dl : pc.m);
+        const int cres = DILV ? pc.m % dl : 0;
         const int gx = 8 * strip - 1;  // first 16-pixel group of the strip's halo tile (-1 -> zero fill)
         for (int r = pc.r0; r <= pc.r1; ++r) {
           for (int sub = 0; sub < p.nsub; ++sub) {
             mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
             const uint32_t fb = smem_u32(&full_bar[s]);
             mbar_expect_tx(fb, stage_bytes);
-            tma_load_4d(ring_base + (uint32_t)s * stage_bytes, &tmap_in, fb, 0, gx, r, p.in_chunk0 + sub * p.kc);
+            tma_load_4d(ring_base + (uint32_t)s * stage_bytes, &tmap_in, fb, 0, gx, DILV ? cres + r * dl : r,
+                        p.in_chunk0 + sub * p.kc);
             ROWS_TRACE(if (p.trace && blockIdx.x == 0 && tcount < 256) p.trace[1024 + tcount++] = clock64());
             if (++s == S) {
               s = 0;
@@ -205,6 +211,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     // in the middle of a stage, while the first half of the stage's MMAs is still queued.
     const bool leader = elect_one();
     const uint32_t idesc = PAIR ? make_idesc_f16_m256(N) : make_idesc_f16(N);
+    const uint32_t dxu = DILV ? (uint32_t)p.dil : 1u;    // pixels (16-byte units) between the horizontal taps
     constexpr uint32_t a_lbo = kRowPx;                   // 16-byte units between the two K chunks
     constexpr uint32_t a_hi = 8u | (1u << 14);           // SBO = 128 B (8 consecutive pixels)
     constexpr uint32_t b_hi = 8u | (1u << 14);
@@ -223,7 +230,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     uint32_t nstage = 0;
     {
       PieceIter it;
-      it.init(p);
+      it.init(p, dl);
       Piece pc;
       while (it.next(pc)) nstage += (uint32_t)(pc.r1 - pc.r0 + 1);
       nstage *= (uint32_t)p.nsub;
@@ -272,13 +279,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         tc_fence_after();
       }
       if (leader) {
-        // TMEM lane l is output column 128m - 15 + l; its tap dx reads pixel l + dx of the staged
-        // segment, which starts at column 128m - 16
+        // TMEM lane l is output column 128m - 16 + d + l (d = 1: 128m - 15 + l); its tap dx reads pixel l + dx * d of
+        // the staged segment, which starts at column 128m - 16
 #pragma unroll
         for (int kk = 0; kk < KH; ++kk) {
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx)
-            mma(acc, make_desc64(a_lo + (uint32_t)(kk * 2 * a_lbo + dx), a_hi),
+            mma(acc, make_desc64(a_lo + (uint32_t)(kk * 2 * a_lbo) + (uint32_t)dx * dxu, a_hi),
                 make_desc64(b_lo + (uint32_t)((kk * 3 + dx) * b_blk), b_hi), (kk | dx) == 0 ? (sub != 0 ? 1u : 0u) : 1u);
         }
       }
@@ -292,7 +299,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         for (int kk = KH; kk < KSLABS; ++kk) {
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx)
-            mma(acc, make_desc64(a_lo + (uint32_t)(kk * 2 * a_lbo + dx), a_hi),
+            mma(acc, make_desc64(a_lo + (uint32_t)(kk * 2 * a_lbo) + (uint32_t)dx * dxu, a_hi),
                 make_desc64(b_lo + (uint32_t)((kk * 3 + dx) * b_blk), b_hi), 1u);
         }
         commit(ebar);
@@ -329,7 +336,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       long long nrows = 0;
       {
         PieceIter it;
-        it.init(p);
+        it.init(p, dl);
         Piece pc;
         while (it.next(pc)) nrows += pc.r1 - pc.r0 + 1;
       }
@@ -372,11 +379,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     uint32_t use = 0;
     ROWS_TRACE(int ecount = 0);
     PieceIter it;
-    it.init(p);
+    it.init(p, dl);
     Piece pc;
     while (it.next(pc)) {
-      const int strip = PAIR ? 2 * pc.m + (int)rank : pc.m;
-      const int xw = 128 * strip - 15 + q4 * 32 + lane;   // wide column of this thread's TMEM lane
+      const int strip = PAIR ? 2 * pc.m + (int)rank : (DILV ? pc.m / dl : pc.m);
+      const int cres = DILV ? pc.m % dl : 0;
+      const int Hv = DILV ? (p.H + dl - 1) / dl : p.H;    // rows of the (virtual) image the pieces walk
+      const int xw = 128 * strip - 16 + dl + q4 * 32 + lane;   // wide column of this thread's TMEM lane
       const bool in_range = xw >= 0 && xw < p.Wtot;
       const uint32_t b = __umulhi((uint32_t)(xw < 0 ? 0 : xw), p.magic);
       const int xi = xw - (int)b * p.pitch;
@@ -395,7 +404,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       // store_row (keeps the live register set small)
       auto load_side = [&](int y) {
         if (!RES || !real || y < pc.ya) return;
-        const size_t ro = (size_t)y * p.res_ys;
+        const int yr = DILV ? cres + y * dl : y;
+        if (DILV && yr >= p.H) return;
+        const size_t ro = (size_t)yr * p.res_ys;
 #pragma unroll
         for (int ch = 0; ch < CH / 8; ++ch) {
           if (r1base) asm volatile("prefetch.global.L2 [%0];" ::"l"(r1base + ro + (size_t)ch * p.res_cs));
@@ -404,8 +415,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       };
       auto store_row = [&](int y, const float (&o)[CH]) {
         if (!in_range || !(real || p.out_wide)) return;
-        const size_t ro = (size_t)y * p.res_ys;
-        __half* op = obase + (size_t)y * p.out_ys;
+        const int yr = DILV ? cres + y * dl : y;   // image row of virtual row y
+        if (DILV && yr >= p.H) return;
+        const size_t ro = (size_t)yr * p.res_ys;
+        __half* op = obase + (size_t)yr * p.out_ys;
         // all residual loads of the row are issued before the first use: one exposed L2 round trip per row instead of
         // one per chunk (measured: 3 200 cycles per row for 4 chunks x 2 residuals when loaded chunk by chunk)
         uint4 s1v[CH / 8], s2v[CH / 8];
@@ -425,7 +438,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = o[ch * 8 + e] + bias[ch * 8 + e];
-            if (p.lrelu) {
+            if (p.lrelu && !(DILV && p.act_after_res)) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * p.slope;
             }
@@ -447,6 +460,22 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
                 f[2 * e + 1] = f[2 * e + 1] * p.alpha2 + v.y;
               }
             }
+            if constexpr (DILV) {
+              if (p.raw) {   // pre-activation copy (PPON: the running sum the next dilated conv adds to)
+                uint4 rk;
+                const __half2 r0 = __floats2half2_rn(f[0], f[1]), r1 = __floats2half2_rn(f[2], f[3]);
+                const __half2 r2 = __floats2half2_rn(f[4], f[5]), r3 = __floats2half2_rn(f[6], f[7]);
+                rk.x = *reinterpret_cast<const uint32_t*>(&r0);
+                rk.y = *reinterpret_cast<const uint32_t*>(&r1);
+                rk.z = *reinterpret_cast<const uint32_t*>(&r2);
+                rk.w = *reinterpret_cast<const uint32_t*>(&r3);
+                *reinterpret_cast<uint4*>(p.raw + (size_t)(p.raw_chunk0 + grp * (CH / 8) + ch) * p.res_cs + ro + col) = rk;
+              }
+              if (p.lrelu && p.act_after_res) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * p.slope;
+              }
+            }
             const __half2 h0 = __floats2half2_rn(f[0], f[1]);
             const __half2 h1 = __floats2half2_rn(f[2], f[3]);
             const __half2 h2 = __floats2half2_rn(f[4], f[5]);
@@ -455,6 +484,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             pk.y = *reinterpret_cast<const uint32_t*>(&h1);
             pk.z = *reinterpret_cast<const uint32_t*>(&h2);
             pk.w = *reinterpret_cast<const uint32_t*>(&h3);
+          } else if (DILV && p.raw) {   // separator column: keep the zero padding of the second destination too
+            *reinterpret_cast<uint4*>(p.raw + (size_t)(p.raw_chunk0 + grp * (CH / 8) + ch) * p.res_cs + ro + col) =
+                make_uint4(0u, 0u, 0u, 0u);
           }
           if (p.out_compact4) *reinterpret_cast<uint2*>(op) = make_uint2(pk.x, pk.y);
           else *reinterpret_cast<uint4*>(op + (size_t)ch * p.out_cs) = pk;
@@ -541,8 +573,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           release_slot();
         }
       }
-      if (pc.yb == p.H) {   // bottom row: the row below is zero padding
-        store_row(p.H - 1, accA);
+      if (pc.yb == Hv) {   // bottom row: the row below is zero padding
+        store_row(Hv - 1, accA);
       }
     }
     }
@@ -559,13 +591,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   ROWS_TRACE(if (p.trace && threadIdx.x == 0) p.trace[3072 + blockIdx.x * 8 + 4] = clock64());
 }
 
-template <int COUT, int KSLABS, bool RES, bool PAIR>
+template <int COUT, int KSLABS, bool RES, bool PAIR, bool DILV = false>
 int launch_rows_res(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num_sms, cudaStream_t stream) {
   const size_t smem_bytes = conv_rows_weight_bytes(p.nch, COUT) / (PAIR ? 2 : 1) + (size_t)p.stages * conv_rows_stage_bytes(p.kc) + 1024;
-  auto kern = conv_rows_kernel<COUT, KSLABS, RES, PAIR>;
+  auto kern = conv_rows_kernel<COUT, KSLABS, RES, PAIR, DILV>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int)e;
-  const long long T = (long long)(PAIR ? (p.nstrips + 1) / 2 : p.nstrips) * p.H;
+  const int dl = DILV ? p.dil : 1;
+  const long long T = (long long)(PAIR ? (p.nstrips + 1) / 2 : p.nstrips * dl) * ((p.H + dl - 1) / dl);
   long long workers = PAIR ? num_sms / 2 : num_sms;   // PAIR: one cluster of two CTAs per worker
   if (T < workers) workers = T;
   cudaLaunchConfig_t cfg = {};
@@ -596,6 +629,14 @@ template <int COUT, int KSLABS>
 int launch_rows_impl(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num_sms, cudaStream_t stream) {
   // the residual-free variant (conv1..conv4 of the plain net) keeps its epilogue free of the side-input code
   const bool res = p.res1 || p.res2;
+  if (p.act_after_res || p.raw || p.dil != 1) {   // PPON's dilated 64 -> 32 convs
+    if constexpr (COUT == 32 && KSLABS == 4) {
+      if (p.pair || p.res2 || p.dil < 1 || p.dil > 8) return (int)cudaErrorInvalidValue;
+      return res ? launch_rows_res<COUT, KSLABS, true, false, true>(tmap_in, p, num_sms, stream)
+                 : launch_rows_res<COUT, KSLABS, false, false, true>(tmap_in, p, num_sms, stream);
+    }
+    return (int)cudaErrorInvalidValue;
+  }
   if (p.pair) {
     if constexpr (COUT == 64 && KSLABS == 6)   // conv5 of the nf = 64 net is the one conv that needs (and gains from) the pair
       return res ? launch_rows_res<COUT, KSLABS, true, true>(tmap_in, p, num_sms, stream)

@@ -42,6 +42,12 @@ struct ConvRowsParams {
   int lrelu;
   float slope;
   int pair;              // 1: clusters of two CTAs, M = 256 MMAs, half of the weight columns per CTA (conv_rows.cu)
+  // dilated variant (PPON's 64 -> 32 convs, conv_rows.cu DILV): taps at distance `dil` (1..8; the separator between the
+  // images must be at least that wide), LeakyReLU AFTER the res1 add, optional second store of the pre-activation value
+  int dil;
+  int act_after_res;
+  __half* raw;           // wide tensor with the geometry of res1 / res2 (res_cs, res_ys), or null
+  int raw_chunk0;
   int pdl;               // 1: programmatic dependent launch -- the prologue overlaps the previous kernel's tail
   long long* trace;      // debugging: clock64 samples of CTA 0 (see tests/gpu_bringup.py --stage trace), or null
 };

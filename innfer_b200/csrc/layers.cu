@@ -121,7 +121,7 @@ int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cou
   }
   // row-streaming packing (conv_rows.cu): [kslab][dx][kchunk][dy*Cout + co][8]
   std::vector<__half> packed_rows;
-  if (up == 1 && ksize == 3 && dil == 1 && (Cout == 32 || Cout == 64 || Cout <= 16)) {
+  if (up == 1 && ksize == 3 && (Cout == 32 || Cout == 64 || Cout <= 16)) {   // the packing does not depend on the dilation
     const int CR = Cout <= 16 ? 16 : Cout;   // output channels as the kernel sees them (zero rows beyond Cout)
     const int NR = 3 * CR;
     packed_rows.resize((size_t)kslabs * 3 * 2 * NR * 8);
@@ -282,7 +282,17 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
                          int out_nchunks, const Epilogue& ep, int num_sms, cudaStream_t stream) {
   static const int rows_mode = getenv("INNFER_ROWS") ? atoi(getenv("INNFER_ROWS")) : 7;  // bit 0: on, bit 1: Cout = 64 too, bit 2: CTA pairs (conv5)
   const int CR = L.Cout <= 16 ? 16 : L.Cout;   // kernel instantiation: 16 (the net's last conv), 32 or 64
-  if (!rows_mode || !in.wide() || L.d_wrows == nullptr || L.up != 1 || L.dil != 1 || ep.act_after_res || ep.raw_out.base || ep.gate || ep.self_gate ||
+  // dilated variant (PPON): 64 -> 32, LeakyReLU after the res1 add, optional raw second store; the separator between
+  // the images must cover the reach of the taps.  INNFER_ROWS bit 3 (default on) enables it.
+  const bool dilv = L.dil != 1 || ep.act_after_res || ep.raw_out.base;
+  if (dilv) {
+    static const int dil_mode = getenv("INNFER_ROWS_DIL") ? atoi(getenv("INNFER_ROWS_DIL")) : 1;
+    if (!dil_mode || !in.wide() || CR != 32 || L.Cin_pad != 64 || !ep.act_after_res || ep.res2.base || ep.compact4 ||
+        !out.wide() || in.pitch - W < L.dil || (ep.res1.base && ep.alpha1 != 1.f))
+      return -100;
+    if (ep.raw_out.base && (!ep.raw_out.wide() || ep.raw_out.pitch != in.pitch || ep.raw_out.Wtot != in.Wtot)) return -100;
+  }
+  if (!rows_mode || !in.wide() || L.d_wrows == nullptr || L.up != 1 || ep.gate || ep.self_gate ||
       out_nchunks != (L.Cout + 7) / 8 || (out.wide() && (in.pitch != out.pitch || in.Wtot != out.Wtot)) ||
       (ep.compact4 && (out.wide() || L.Cout > 4)))
     return -100;
@@ -359,6 +369,10 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   p.res2 = ep.res2.base;
   p.res2_chunk0 = ep.res2.chunk0;
   p.alpha2 = ep.alpha2;
+  p.dil = L.dil;
+  p.act_after_res = ep.act_after_res ? 1 : 0;
+  p.raw = ep.raw_out.base;
+  p.raw_chunk0 = ep.raw_out.chunk0;
   static const int trace_nch = getenv("INNFER_TRACE_NCH") ? atoi(getenv("INNFER_TRACE_NCH")) : 0;
   p.trace = (trace_nch == nch) ? g_rows_trace : nullptr;
   int rc = 0;
