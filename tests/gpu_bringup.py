@@ -407,6 +407,31 @@ def stage_lat():
     return True
 
 
+def stage_srres_time():
+    """SRResNet at the reference's defaults (nf 64, nb 16, pixel-shuffle upsampler) on a 1920x1080 frame, fp16."""
+    from innfer_b200.engine import SRResNetEngine
+    sd = O.make_srresnet_state_dict(scale=4, nb=16, seed=0)
+    eng = SRResNetEngine.from_state_dict(sd, dict(in_nc=3, out_nc=3, nf=64, nb=16, scale=4, upsample_mode="pixelshuffle",
+                                                  res_scale=1.0), dev, fp16=True)
+    H, W = 1080, 1920
+    din = torch.from_numpy(np.random.default_rng(0).integers(0, 256, (H, W, 3), dtype=np.uint8)).to(dev)
+    dout = torch.empty(4 * H, 4 * W, 3, dtype=torch.uint8, device=dev)
+    mac = 9 * 3 * 64 + 33 * 9 * 64 * 64 + 9 * 64 * 256 + 4 * 9 * 64 * 256 + 16 * 9 * 64 * 64 + 16 * 9 * 64 * 3
+    flop = 190 * 200 * 200 * 2.0 * mac
+    for it in range(3):
+        l0 = N.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.upscale_u8_device(din, 200, 0.5, out=dout)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print("srresnet 1080p nb=16 iter=%d: %.1f ms  %.1f out-Mpix/s  %.1f TFLOP/s  (%d launches)" %
+              (it, ms, 16 * H * W / ms / 1e3, flop / ms / 1e9, N.kernel_launches() - l0))
+    eng.close()
+    return True
+
+
 def stage_trace_up():
     """clock64 trace of CTA 0 of the last conv_up launch of a frame (needs an INNFER_TRACE_BUILD=1 build)."""
     lib = N.load()
@@ -550,6 +575,6 @@ if __name__ == "__main__":
     ap.add_argument("--stage", required=True)
     a = ap.parse_args()
     t0 = time.time()
-    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "trace_up": stage_trace_up, "ppon": stage_ppon, "ppon_prof": stage_ppon_prof, "ppon_time": stage_ppon_time, "pan_time": stage_pan_time, "lat": stage_lat, "pan_prof": stage_pan_prof, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
+    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "trace_up": stage_trace_up, "ppon": stage_ppon, "ppon_prof": stage_ppon_prof, "ppon_time": stage_ppon_time, "pan_time": stage_pan_time, "srres_time": stage_srres_time, "lat": stage_lat, "pan_prof": stage_pan_prof, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
     print("STAGE %s %s (%.1fs)" % (a.stage, "OK" if ok else "FAILED", time.time() - t0))
     sys.exit(0 if ok else 1)
