@@ -54,6 +54,11 @@ def test_abi_rejects_bad_arguments_without_gpu():
     h = ctypes.c_void_p()
     assert lib.innfer_rrdb_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -2
     assert b"nf" in lib.innfer_last_error()
+    # PAN: nf must be a multiple of 8 (<= 64); the bilinear skip needs in_nc == out_nc
+    pan = _native.PANCfg(3, 3, 44, 24, 16, 4, 1, 0, 1)
+    assert lib.innfer_pan_create(ctypes.byref(pan), 0, ctypes.byref(h)) == -2 and b"nf" in lib.innfer_last_error()
+    pan = _native.PANCfg(3, 1, 40, 24, 16, 4, 1, 0, 1)
+    assert lib.innfer_pan_create(ctypes.byref(pan), 0, ctypes.byref(h)) == -2 and b"in_nc" in lib.innfer_last_error()
 
 
 def test_state_dict_keys_and_cpu_forward_match_reference(tmp_path):
