@@ -195,6 +195,7 @@ int conv_direct_run(const ConvLayer& L, ChunkView in, int B, int H, int W, Chunk
   p.act_after_res = ep.act_after_res ? 1 : 0;
   p.gate = ep.gate ? 1 : (ep.self_gate ? 2 : 0);
   if (ep.gate && !ep.res1.base) return -9;
+  if (ep.res1_unact) return -9;   // fp16 paths only
   if (ep.self_gate && (ep.gate || out_nchunks > L.N / 16)) return -9;
   p.raw = reinterpret_cast<float*>(ep.raw_out.base);
   p.raw_CT = ep.raw_out.CT;

@@ -446,7 +446,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
               const __half2* hp = reinterpret_cast<const __half2*>(&s1);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 v = __half22float2(hp[e]);
+                float2 v = __half22float2(hp[e]);
+                if (DILV && p.res1_unact) {   // the side input is the activated copy of the value
+                  const float inv = 1.f / p.slope;
+                  v.x = v.x > 0.f ? v.x : v.x * inv;
+                  v.y = v.y > 0.f ? v.y : v.y * inv;
+                }
                 f[2 * e] = f[2 * e] * p.alpha1 + v.x;
                 f[2 * e + 1] = f[2 * e + 1] * p.alpha1 + v.y;
               }

@@ -46,6 +46,7 @@ struct ConvRowsParams {
   // images must be at least that wide), LeakyReLU AFTER the res1 add, optional second store of the pre-activation value
   int dil;
   int act_after_res;
+  int res1_unact;        // res1 holds LeakyReLU(v) of the value to add: undo it (v > 0 ? v : v / slope)
   __half* raw;           // wide tensor with the geometry of res1 / res2 (res_cs, res_ys), or null
   int raw_chunk0;
   int pdl;               // 1: programmatic dependent launch -- the prologue overlaps the previous kernel's tail

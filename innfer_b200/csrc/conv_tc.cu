@@ -370,7 +370,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
                 const __half2* hp = reinterpret_cast<const __half2*>(&r1[ch]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float2 rv = __half22float2(hp[e]);
+                  float2 rv = __half22float2(hp[e]);
+                  if (p.res1_unact) {
+                    const float inv = 1.f / p.slope;
+                    rv.x = rv.x > 0.f ? rv.x : rv.x * inv;
+                    rv.y = rv.y > 0.f ? rv.y : rv.y * inv;
+                  }
                   if (p.gate == 1) {
                     // approximate division: the IEEE one takes its slow path (a call) for the zero padding channels
                     f[2 * e] = __fdividef(rv.x, 1.f + __expf(-f[2 * e]));

@@ -76,6 +76,7 @@ struct ConvTcParams {
   int raw_ys, raw_chunk0;
   int act_after_res;   // apply the LeakyReLU after the residual adds instead of before
   int pdl;             // programmatic dependent launch (ptx.cuh: pdl_wait): the prologue overlaps the previous kernel's tail
+  int res1_unact;      // res1 holds LeakyReLU(v) of the value to add: undo it (v > 0 ? v : v / slope)
   int gate;            // 1: res1 multiplies sigmoid(conv + bias) instead of being added (PAN pixel attention);
                        // 2: column c is multiplied by sigmoid(column N/2 + c) of the same accumulator (merged PACnv)
   // wide SOURCE: B == 1, W == Wtot and a column decomposes as image * sep_pitch + x; columns with

@@ -535,11 +535,21 @@ int forward_tiles_ppon(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, b
       Epilogue e;
       e.lrelu = true;
       e.act_after_res = true;
+      // fp16: the running sum add_{k-1} is read back from its ACTIVATED copy in the concat buffer (LeakyReLU is
+      // invertible: v > 0 ? v : v / 0.2), which saves the raw second store -- these convs are bandwidth-bound.
+      // INNFER_PPON_RAW=1 (and the fp32 mode) keep the raw scratch copy.
+      static const bool keep_raw = getenv("INNFER_PPON_RAW") && atoi(getenv("INNFER_PPON_RAW"));
+      const bool unact = h->cfg.fp16 && !keep_raw;
       if (k > 0) {
-        e.res1 = view(S, nfc, 4 * ((k - 1) & 1));
+        if (unact) {
+          e.res1 = view(CAT, 32, 4 * (k - 1));
+          e.res1_unact = true;
+        } else {
+          e.res1 = view(S, nfc, 4 * ((k - 1) & 1));
+        }
         e.alpha1 = 1.0f;
       }
-      if (k < 7) e.raw_out = view(S, nfc, 4 * (k & 1));
+      if (k < 7 && !unact) e.raw_out = view(S, nfc, 4 * (k & 1));
       if ((r = run_conv(h, L[1 + k], view(T1, nfc, 0), B, hgt, wid, view(CAT, 32, 4 * k), 4, e, st))) return r;
     }
     Epilogue e2;

@@ -292,6 +292,7 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
       return -100;
     if (ep.raw_out.base && (!ep.raw_out.wide() || ep.raw_out.pitch != in.pitch || ep.raw_out.Wtot != in.Wtot)) return -100;
   }
+  if (ep.res1_unact && !dilv) return -100;
   if (!rows_mode || !in.wide() || L.d_wrows == nullptr || L.up != 1 || ep.gate || ep.self_gate ||
       out_nchunks != (L.Cout + 7) / 8 || (out.wide() && (in.pitch != out.pitch || in.Wtot != out.Wtot)) ||
       (ep.compact4 && (out.wide() || L.Cout > 4)))
@@ -371,6 +372,7 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   p.alpha2 = ep.alpha2;
   p.dil = L.dil;
   p.act_after_res = ep.act_after_res ? 1 : 0;
+  p.res1_unact = ep.res1_unact ? 1 : 0;
   p.raw = ep.raw_out.base;
   p.raw_chunk0 = ep.raw_out.chunk0;
   static const int trace_nch = getenv("INNFER_TRACE_NCH") ? atoi(getenv("INNFER_TRACE_NCH")) : 0;
@@ -459,6 +461,7 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
     }
     p.act_after_res = ep.act_after_res ? 1 : 0;
     p.gate = ep.gate ? 1 : (ep.self_gate ? 2 : 0);
+    p.res1_unact = ep.res1_unact ? 1 : 0;
     if (ep.gate && !ep.res1.base) return -9;
     if (ep.self_gate && (ep.gate || out_nchunks > N / 16 || L.nphase != 1)) return -9;
     if (ep.res1.base) strides(ep.res1, p.res1_bs, p.res1_cs, p.res1_ys);

@@ -61,6 +61,8 @@ struct Epilogue {
   bool compact4 = false;  // store out channels 0..3 as [tile][H][W][4] (8 bytes per pixel), see ConvTcParams
   bool act_after_res = false;  // LeakyReLU after the residual adds (PPON running sums) instead of before
   ChunkView raw_out;      // optional second destination for the pre-activation value (needs act_after_res)
+  bool res1_unact = false; // res1 holds LeakyReLU_slope(v): the add uses v itself (PPON fp16: the running sum is read
+                           // back from its activated copy in the concat buffer, which saves the raw second store)
   bool gate = false;      // pixel attention (PAN_arch.py:22-36,48-57): v = res1 * sigmoid(conv + bias) instead of the add
   bool self_gate = false; // PACnv with k3 and k2 merged into one conv (rows [0, N/2) = k3, [N/2, N) = k2 at the centre
                           // tap): v[c] = conv[c] * sigmoid(conv[N/2 + c] + bias[N/2 + c]); out_nchunks <= N/16
