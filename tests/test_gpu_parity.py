@@ -637,3 +637,31 @@ def test_rrdb_dense_blocks_with_amplified_weights(dev, fp16, plus):
         assert (y - ref).abs().max().item() <= 1 / 255
     else:
         assert ((y - ref).abs().max() / ref.abs().max()).item() <= 1e-4
+
+
+@pytest.mark.parametrize("family", ["ppon", "pan", "srresnet"])
+def test_chop_is_independent_of_the_tile_batch_size(dev, family):
+    """chop_forward pushes the tiles through the net in batches (wide layout): the result must not depend on how many
+    tiles share a batch -- 20 tiles at once, three at a time, one at a time, bit for bit."""
+    from innfer_b200.architectures import get_network
+    from innfer_b200.utils.defaults import get_network_G_config
+    x = torch.rand(1, 3, 72, 88, generator=torch.Generator().manual_seed(41))
+    if family == "ppon":
+        sd = O.make_ppon_state_dict(scale=2, nb=1, seed=42)
+        net = get_network(get_network_G_config({"type": "ppon", "nb": 1}, 2))
+    elif family == "pan":
+        sd = O.make_pan_state_dict(scale=2, nb=2, seed=42)
+        net = get_network(get_network_G_config({"type": "pan", "nb": 2}, 2))
+    else:
+        sd = O.make_srresnet_state_dict(scale=2, nb=2, seed=42)
+        net = get_network(get_network_G_config({"type": "sr_resnet", "nb": 2}, 2))
+    net.load_state_dict(sd, strict=True)
+    net = net.eval().to(dev).half()
+    xd = x.to(dev).half()
+    eng = net._engine(xd.device, xd.dtype)
+    outs = []
+    for mb in (95, 3, 1):
+        eng.set_max_batch(mb)
+        outs.append(net.chop_forward_native(xd, 32, 0.5).cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert outs[0].shape == (1, 3, 144, 176) and torch.isfinite(outs[0].float()).all()
