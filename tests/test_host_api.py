@@ -225,6 +225,8 @@ def test_unknown_architectures_fail_loudly():
         torch.save({"weird.weight": torch.zeros(1)}, "/tmp/_innfer_weird.pth")
         m.model_path = "/tmp/_innfer_weird.pth"
         m.load_model()
+    with pytest.raises(NotImplementedError):   # PAN: only the default 'nearest' upsampler is built
+        get_network(get_network_G_config({"type": "pan", "ups_inter_mode": "bilinear"}, 4))
     cfg = get_network_G_config("esrgan-lite", 2)
     assert (cfg["nf"], cfg["nb"], cfg["upscale"], cfg["type"]) == (32, 12, 2, "rrdb_net")
 
