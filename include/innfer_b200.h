@@ -134,6 +134,12 @@ int innfer_rrdb_set_max_batch(innfer_rrdb* h, int max_tiles);
  * kernels launched inside them.  Used by bench.py for the roofline line; no reference equivalent. */
 int innfer_rrdb_profile(innfer_rrdb* h, int enable);
 int innfer_rrdb_profile_read(innfer_rrdb* h, double* conv_ms, uint64_t* conv_launches);
+/* innfer_rrdb_profile(h, 2): events around EVERY conv launch, accumulated per kernel family (kernel, Cin->Cout,
+ * flags).  The events defeat the programmatic-dependent-launch overlap of consecutive convs, so these are the times
+ * of isolated launches; mode 1 times the real schedule.  innfer_rrdb_profile_families writes one line per family,
+ * "name\tlaunches\ttotal_ms\talgorithmic_flop\talgorithmic_bytes\n", into buf (if cap suffices); *needed = bytes
+ * required including the terminating NUL. */
+int innfer_rrdb_profile_families(innfer_rrdb* h, char* buf, uint64_t cap, uint64_t* needed);
 
 /* ---- forward: replaces RRDBNet.forward on one batch (RRDBNet_arch.py:50-62) -------------------
  * x: device NCHW [n][in_nc][h][w], y: device NCHW [n][out_nc][scale*h][scale*w]; dtype INNFER_F16
@@ -145,17 +151,24 @@ int innfer_rrdb_forward(innfer_rrdb* h, const void* x, int n, int hgt, int wid, 
  *      recompose_tensor (run.py:167-202, utils/utils.py:318-445) -------------------------------
  * x: device NCHW [1][in_nc][H][W]; y: device NCHW [1][out_nc][scale*H][scale*W]. */
 int innfer_rrdb_chop_forward(innfer_rrdb* h, const void* x, int H, int W, int patch_size,
-                             float step, void* y, int dtype, void* stream);
+                             double step, void* y, int dtype, void* stream);
+
+/* same with independent element types at the two ends: x INNFER_F16/F32 (NCHW) or INNFER_U8 (HWC BGR, np2tensor
+ * fused), y INNFER_F16/F32 (NCHW) or INNFER_U8 (HWC BGR, tensor2np fused).  This is what lets a model chain
+ * (run.py:424-426: `for mod in models: t_out = mod(t_out)`) stay on the device: uint8 frame -> fp16 tensor ->
+ * ... -> uint8 frame, with float tensors between the models exactly as in the reference. */
+int innfer_rrdb_chop_forward_ex(innfer_rrdb* h, const void* x, int x_dtype, int H, int W, int patch_size,
+                                double step, void* y, int y_dtype, void* stream);
 
 /* ---- image in, image out: np2tensor -> chop_forward -> tensor2np fused (run.py:421-431,
  *      utils/utils.py:164-248).  img: HOST uint8 HWC BGR [H][W][3]; out: HOST uint8 HWC BGR
  *      [scale*H][scale*W][3].  Copies run on `stream`; the call returns after the result landed
  *      in `out` (it synchronises the stream). */
 int innfer_rrdb_upscale_u8(innfer_rrdb* h, const uint8_t* img, int H, int W, int patch_size,
-                           float step, uint8_t* out, void* stream);
+                           double step, uint8_t* out, void* stream);
 /* same with DEVICE uint8 buffers and no synchronisation */
 int innfer_rrdb_upscale_u8_device(innfer_rrdb* h, const uint8_t* img, int H, int W, int patch_size,
-                                  float step, uint8_t* out, void* stream);
+                                  double step, uint8_t* out, void* stream);
 
 /* ---- tile-sharded execution across GPUs (the reference is single-GPU and runs the
  *      tile loop of run.py:187-197 serially).  One process per GPU; the frame's owner exposes its
@@ -164,16 +177,19 @@ int innfer_rrdb_upscale_u8_device(innfer_rrdb* h, const uint8_t* img, int H, int
  *      owner's buffer (peer stores over NVLink, no NCCL, no staging copy); the owner then blends.
  *      Results are bit-identical for any number of ranks. ------------------------------------- */
 /* owner: (re)allocate the handle's tile buffer for an HxW frame; returns its device pointer */
-int innfer_rrdb_tile_buffer(innfer_rrdb* h, int H, int W, int patch_size, float step, void** ptr,
+int innfer_rrdb_tile_buffer(innfer_rrdb* h, int H, int W, int patch_size, double step, void** ptr,
                             uint64_t* bytes, uint64_t* bytes_per_tile);
+/* size of the tile buffer of an HxW frame (what a rank must allocate, with innfer_device_alloc, to own frames) */
+int innfer_rrdb_tile_bytes(innfer_rrdb* h, int H, int W, int patch_size, double step, uint64_t* bytes_total,
+                           uint64_t* bytes_per_tile, int* ntiles);
 /* any rank: tiles [t_begin, t_end) of the frame `img` (device or peer pointer; INNFER_U8 HWC BGR or
  * NCHW F16/F32) -> tiles_base + t * bytes_per_tile (device or peer pointer) */
 int innfer_rrdb_forward_tile_range(innfer_rrdb* h, const void* img, int img_dtype, int H, int W,
-                                   int patch_size, float step, int t_begin, int t_end,
+                                   int patch_size, double step, int t_begin, int t_end,
                                    void* tiles_base, void* stream);
 /* owner: recompose_tensor (+ tensor2np for INNFER_U8) over a complete tile buffer */
 int innfer_rrdb_blend_tiles(innfer_rrdb* h, const void* tiles_base, int H, int W, int patch_size,
-                            float step, void* dst, int dst_dtype, void* stream);
+                            double step, void* dst, int dst_dtype, void* stream);
 /* CUDA IPC plumbing for the two calls above (handles are 64 opaque bytes) */
 int innfer_ipc_export(const void* device_ptr, uint8_t handle[64]);
 int innfer_ipc_open(const uint8_t handle[64], void** device_ptr);
@@ -182,6 +198,16 @@ int innfer_ipc_close(void* device_ptr);
  * caching allocator) */
 int innfer_device_alloc(int device, uint64_t bytes, void** ptr);
 int innfer_device_free(void* ptr);
+int innfer_device_memset(void* ptr, int value, uint64_t bytes); /* synchronous */
+/* cudaMemcpyAsync(cudaMemcpyDefault) on `stream`: pinned host <-> device and device <-> peer-mapped device copies */
+int innfer_memcpy_async(void* dst, const void* src, uint64_t bytes, void* stream);
+/* Stream-ordered cross-GPU flags (csrc/sync_ops.cu): `flags` is a HOST array of n (<= 32) device pointers to
+ * uint32 counters (local or peer-mapped).  signal: after all earlier work of `stream`, store `value` into each
+ * (system-scope release).  wait: hold `stream` until every counter has reached `value`; if that takes longer than
+ * timeout_ms the kernel increments *err_flag (device uint32, may be NULL) and lets the stream continue, so a
+ * protocol bug cannot hang the GPU.  These replace host barriers in the tile-sharded mode. */
+int innfer_stream_signal(void* const* flags, int n, uint32_t value, void* stream);
+int innfer_stream_wait(void* const* flags, int n, uint32_t value, void* err_flag, uint64_t timeout_ms, void* stream);
 
 /* Debugging aid (not part of the reference-facing surface): device buffer of 3072 int64 that receives
  * clock64 samples of CTA 0 of the row-streaming conv kernel selected by INNFER_TRACE_NCH; NULL disables. */
@@ -195,18 +221,21 @@ int innfer_device_upload(void* device_dst, const void* host_src, uint64_t bytes,
 /* ---- tiling geometry: replaces the index arithmetic of extract_patches_2d
  *      (utils/utils.py:349-365).  Writes up to `cap` tiles in row-major order; *n = tile count,
  *      *tile_size = min(H, W, patch_size). */
-int innfer_tiles_plan(int H, int W, int patch_size, float step, innfer_tile* out, int cap, int* n,
+int innfer_tiles_plan(int H, int W, int patch_size, double step, innfer_tile* out, int cap, int* n,
                       int* tile_size);
 
 /* ---- standalone operators (used by the parity tests, same kernels as the network) ----------- */
 /* image -> tiles: np2tensor + extract_patches_2d.  src device: NCHW fp16/fp32 [1][C][H][W] or
  * uint8 HWC BGR; dst device planar-chunk tiles [ntiles][ceil(C/16)*2][p][p][8] fp16. */
 int innfer_image_to_tiles(const void* src, int src_dtype, int C, int H, int W, int patch_size,
-                          float step, void* dst_tiles, void* stream);
+                          double step, void* dst_tiles, void* stream);
 /* recompose_tensor (+ tensor2np when dst_dtype is INNFER_U8).  tiles: device planar-chunk
  * [ntiles][1][P][P][8] fp16 with P = scale*min(H,W,patch_size). */
-int innfer_blend(const void* tiles, int H, int W, int patch_size, float step, int scale, int C,
+int innfer_blend(const void* tiles, int H, int W, int patch_size, double step, int scale, int C,
                  void* dst, int dst_dtype, void* stream);
+/* same for fp32 tiles [ntiles][1][P][P][8] float (the -no_fp16 mode keeps fp32 through the blend) */
+int innfer_blend_f32(const float* tiles, int H, int W, int patch_size, double step, int scale, int C, void* dst,
+                     int dst_dtype, void* stream);
 /* one fused conv_block (architectures/block.py:213-254) [+ nearest Upsample in front,
  * block.py:348-361] [+ LeakyReLU] [+ alpha1*. + res1] on NCHW device tensors; weights host fp32
  * OIHW.  Builds, runs and frees a temporary layer -- a test/bring-up entry point, not a hot path.

@@ -47,7 +47,8 @@ class Tile(ctypes.Structure):
 
 _LIB = None
 
-_vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+_vp, _i, _f, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double
+_u64, _u32 = ctypes.c_uint64, ctypes.c_uint32
 _PROTOS = {
     "innfer_last_error": (ctypes.c_char_p, []),
     "innfer_version": (ctypes.c_char_p, []),
@@ -62,14 +63,22 @@ _PROTOS = {
     "innfer_rrdb_set_max_batch": (_i, [_vp, _i]),
     "innfer_rrdb_profile": (_i, [_vp, _i]),
     "innfer_rrdb_profile_read": (_i, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
+    "innfer_rrdb_profile_families": (_i, [_vp, ctypes.c_char_p, _u64, ctypes.POINTER(_u64)]),
+    "innfer_rrdb_chop_forward_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _i, _vp]),
+    "innfer_rrdb_tile_bytes": (_i, [_vp, _i, _i, _i, _d, ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_i)]),
+    "innfer_device_memset": (_i, [_vp, _i, _u64]),
+    "innfer_memcpy_async": (_i, [_vp, _vp, _u64, _vp]),
+    "innfer_stream_signal": (_i, [ctypes.POINTER(_vp), _i, _u32, _vp]),
+    "innfer_stream_wait": (_i, [ctypes.POINTER(_vp), _i, _u32, _vp, _u64, _vp]),
+    "innfer_blend_f32": (_i, [_vp, _i, _i, _i, _d, _i, _i, _vp, _i, _vp]),
     "innfer_rrdb_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
-    "innfer_rrdb_chop_forward": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _i, _vp]),
-    "innfer_rrdb_upscale_u8": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
-    "innfer_rrdb_upscale_u8_device": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
-    "innfer_rrdb_tile_buffer": (_i, [_vp, _i, _i, _i, _f, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_uint64),
+    "innfer_rrdb_chop_forward": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _i, _vp]),
+    "innfer_rrdb_upscale_u8": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp]),
+    "innfer_rrdb_upscale_u8_device": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp]),
+    "innfer_rrdb_tile_buffer": (_i, [_vp, _i, _i, _i, _d, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_uint64),
                                      ctypes.POINTER(ctypes.c_uint64)]),
-    "innfer_rrdb_forward_tile_range": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp, _vp]),
-    "innfer_rrdb_blend_tiles": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _i, _vp]),
+    "innfer_rrdb_forward_tile_range": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _i, _i, _vp, _vp]),
+    "innfer_rrdb_blend_tiles": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _i, _vp]),
     "innfer_ipc_export": (_i, [_vp, _vp]),
     "innfer_ipc_open": (_i, [_vp, ctypes.POINTER(_vp)]),
     "innfer_ipc_close": (_i, [_vp]),
@@ -78,10 +87,10 @@ _PROTOS = {
     "innfer_debug_set_trace": (_i, [_vp]),
     "innfer_debug_conv_loop": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_float)]),
     "innfer_device_upload": (_i, [_vp, _vp, ctypes.c_uint64, _vp]),
-    "innfer_tiles_plan": (_i, [_i, _i, _i, _f, ctypes.POINTER(Tile), _i, ctypes.POINTER(_i),
+    "innfer_tiles_plan": (_i, [_i, _i, _i, _d, ctypes.POINTER(Tile), _i, ctypes.POINTER(_i),
                                ctypes.POINTER(_i)]),
-    "innfer_image_to_tiles": (_i, [_vp, _i, _i, _i, _i, _i, _f, _vp, _vp]),
-    "innfer_blend": (_i, [_vp, _i, _i, _i, _f, _i, _i, _vp, _i, _vp]),
+    "innfer_image_to_tiles": (_i, [_vp, _i, _i, _i, _i, _i, _d, _vp, _vp]),
+    "innfer_blend": (_i, [_vp, _i, _i, _i, _d, _i, _i, _vp, _i, _vp]),
     "innfer_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _f, _vp, _i, _i, _vp]),
     "innfer_color_fix": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp]),
     "innfer_color_fix_host": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i]),

@@ -12,6 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import block as B
+from ._native import NativeEngineMixin
 
 
 class PA(nn.Module):
@@ -86,7 +87,9 @@ def pa_upconv_block(nf, unf, upscale_factor=2, mode="nearest"):
                         nn.Conv2d(unf, unf, 3, 1, 1), a)
 
 
-class PAN(nn.Module):
+class PAN(NativeEngineMixin, nn.Module):
+    _engine_class = "PANEngine"
+
     def __init__(self, in_nc, out_nc, nf, unf, nb, scale=4, self_attention=True, double_scpa=False,
                  ups_inter_mode="nearest"):
         super().__init__()
@@ -112,27 +115,6 @@ class PAN(nn.Module):
         stages = [pa_upconv_block(nf if i == 0 else unf, unf, 3 if scale == 3 else 2) for i in range(n_upscale)]
         self.upsample = B.sequential(*stages)
         self.conv_last = nn.Conv2d(unf, out_nc, 3, 1, 1)
-        self._engines = {}
-
-    def _engine(self, device, dtype):
-        from ..engine import PANEngine
-        key = (str(device), dtype)
-        eng = self._engines.get(key)
-        if eng is None:
-            eng = PANEngine.from_module(self, device, fp16=(dtype == torch.float16))
-            self._engines = {key: eng}
-        return eng
-
-    def load_state_dict(self, *a, **k):
-        self._engines = {}
-        return super().load_state_dict(*a, **k)
-
-    def _apply(self, fn, *a, **k):
-        self._engines = {}
-        return super()._apply(fn, *a, **k)
-
-    def chop_forward_native(self, x, patch_size, step):
-        return self._engine(x.device, x.dtype).chop_forward(x, patch_size, step)
 
     def forward(self, x):
         if x.is_cuda:

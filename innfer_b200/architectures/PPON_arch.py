@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import block as B
+from ._native import NativeEngineMixin
 
 
 class _ResBlock_32(nn.Module):
@@ -46,7 +47,9 @@ class RRBlock_32(nn.Module):
         return self.RB3(self.RB2(self.RB1(x))).mul(0.2) + x
 
 
-class PPON(nn.Module):
+class PPON(NativeEngineMixin, nn.Module):
+    _engine_class = "PPONEngine"
+
     def __init__(self, in_nc, nf, nb, out_nc, upscale=4, act_type="lrelu", alpha=1.0):
         super().__init__()
         if nf != 64:
@@ -70,27 +73,6 @@ class PPON(nn.Module):
         self.CRM = B.sequential(*ups[0], *heads[0])
         self.SRM = B.sequential(*ups[1], *heads[1])
         self.PRM = B.sequential(*ups[2], *heads[2])
-        self._engines = {}
-
-    def _engine(self, device, dtype):
-        from ..engine import PPONEngine
-        key = (str(device), dtype)
-        eng = self._engines.get(key)
-        if eng is None:
-            eng = PPONEngine.from_module(self, device, fp16=(dtype == torch.float16))
-            self._engines = {key: eng}
-        return eng
-
-    def load_state_dict(self, *a, **k):
-        self._engines = {}
-        return super().load_state_dict(*a, **k)
-
-    def _apply(self, fn, *a, **k):
-        self._engines = {}
-        return super()._apply(fn, *a, **k)
-
-    def chop_forward_native(self, x, patch_size, step):
-        return self._engine(x.device, x.dtype).chop_forward(x, patch_size, step)
 
     def forward(self, x):
         if x.is_cuda:

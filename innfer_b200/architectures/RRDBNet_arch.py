@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from . import block as B
+from ._native import NativeEngineMixin
 
 
 class ResidualDenseBlock_5C(nn.Module):
@@ -57,7 +58,9 @@ class RRDB(nn.Module):
         return self.RDB3(self.RDB2(self.RDB1(x))) * 0.2 + x
 
 
-class RRDBNet(nn.Module):
+class RRDBNet(NativeEngineMixin, nn.Module):
+    _engine_class = "RRDBEngine"
+
     def __init__(self, in_nc, out_nc, nf, nb, nr=3, gc=32, upscale=4, norm_type=None, act_type="leakyrelu",
                  mode="CNA", upsample_mode="upconv", convtype="Conv2D", finalact=None, gaussian_noise=False,
                  plus=False):
@@ -81,29 +84,6 @@ class RRDBNet(nn.Module):
         hr0 = B.conv_block(nf, nf, kernel_size=3, norm_type=None, act_type=act_type, convtype=convtype)
         hr1 = B.conv_block(nf, out_nc, kernel_size=3, norm_type=None, act_type=None, convtype=convtype)
         self.model = B.sequential(fea, B.ShortcutBlock(B.sequential(*blocks, lr_conv)), *ups, hr0, hr1)
-        self._engines = {}
-
-    # -- engine plumbing ---------------------------------------------------------------------
-    def _engine(self, device, dtype):
-        from ..engine import RRDBEngine
-        key = (str(device), dtype)
-        eng = self._engines.get(key)
-        if eng is None:
-            eng = RRDBEngine.from_module(self, device, fp16=(dtype == torch.float16))
-            self._engines = {key: eng}  # one resident engine per module
-        return eng
-
-    def load_state_dict(self, *a, **k):
-        self._engines = {}
-        return super().load_state_dict(*a, **k)
-
-    def _apply(self, fn, *a, **k):
-        self._engines = {}
-        return super()._apply(fn, *a, **k)
-
-    def chop_forward_native(self, x, patch_size, step):
-        """extract_patches_2d -> forward -> recompose_tensor in one native call (CUDA only)."""
-        return self._engine(x.device, x.dtype).chop_forward(x, patch_size, step)
 
     def forward(self, x, outm=None):
         if x.is_cuda:

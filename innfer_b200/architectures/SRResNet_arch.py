@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import block as B
+from ._native import NativeEngineMixin
 
 
 class ResNetBlock(nn.Module):
@@ -32,7 +33,9 @@ class ResNetBlock(nn.Module):
         return x + self.res(x).mul(self.res_scale)
 
 
-class SRResNet(nn.Module):
+class SRResNet(NativeEngineMixin, nn.Module):
+    _engine_class = "SRResNetEngine"
+
     def __init__(self, in_nc, out_nc, nf, nb, upscale=4, norm_type="batch", act_type="relu", mode="NAC",
                  res_scale=1, upsample_mode="upconv", convtype="Conv2D", finalact=None):
         super().__init__()
@@ -59,27 +62,6 @@ class SRResNet(nn.Module):
         hr0 = B.conv_block(nf, nf, kernel_size=3, norm_type=None, act_type=act_type)
         hr1 = B.conv_block(nf, out_nc, kernel_size=3, norm_type=None, act_type=None)
         self.model = B.sequential(fea, B.ShortcutBlock(B.sequential(*blocks, lr_conv)), *ups, hr0, hr1)
-        self._engines = {}
-
-    def _engine(self, device, dtype):
-        from ..engine import SRResNetEngine
-        key = (str(device), dtype)
-        eng = self._engines.get(key)
-        if eng is None:
-            eng = SRResNetEngine.from_module(self, device, fp16=(dtype == torch.float16))
-            self._engines = {key: eng}
-        return eng
-
-    def load_state_dict(self, *a, **k):
-        self._engines = {}
-        return super().load_state_dict(*a, **k)
-
-    def _apply(self, fn, *a, **k):
-        self._engines = {}
-        return super()._apply(fn, *a, **k)
-
-    def chop_forward_native(self, x, patch_size, step):
-        return self._engine(x.device, x.dtype).chop_forward(x, patch_size, step)
 
     def forward(self, x, outm=None):
         y = self._engine(x.device, x.dtype).forward(x) if x.is_cuda else self.model(x)

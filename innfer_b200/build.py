@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libinnfer_b200.so"
-SOURCES = ["conv_tc.cu", "conv_rows.cu", "conv_up.cu", "tmap.cu", "layers.cu", "pixel_ops.cu", "conv_direct.cu", "color_fix.cu", "pan_ops.cu",
+SOURCES = ["sync_ops.cu", "conv_tc.cu", "conv_rows.cu", "conv_up.cu", "tmap.cu", "layers.cu", "pixel_ops.cu", "conv_direct.cu", "color_fix.cu", "pan_ops.cu",
            "engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

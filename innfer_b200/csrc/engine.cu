@@ -16,6 +16,7 @@
 #include "layers.cuh"
 #include "pan_ops.cuh"
 #include "pixel_ops.cuh"
+#include "sync_ops.cuh"
 
 using namespace innfer;
 
@@ -103,15 +104,26 @@ struct innfer_rrdb {
   DevBuf in_tiles, feat, xbuf[3], hrbuf[2], out_tiles, img_in, img_out;
   DevBuf pbuf[9], paux[2];   // PPON: F, X0..X2, T1, S, E1, E2 (64 channels each), CAT (256); out_c / out_s at HR
   // optional device-side timing of the conv sequence (bench.py roofline)
-  bool profiling = false;
+  int profiling = 0;   // 1: events around every per-batch conv sequence; 2: around every conv launch, per kernel family
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   uint64_t prof_conv_launches = 0;
+  struct FamStat {
+    uint64_t launches = 0;
+    double flop = 0, bytes = 0;   // algorithmic: real channels only, reference conv arithmetic
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  };
+  std::map<std::string, FamStat> fam;
   // fp32-mode workspace lives in the same buffers (sized in bytes)
   ~innfer_rrdb() {
     for (auto& e : prof_events) {
       cudaEventDestroy(e.first);
       cudaEventDestroy(e.second);
     }
+    for (auto& f : fam)
+      for (auto& e : f.second.ev) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+      }
     conv_layer_free(fea);
     conv_layer_free(lr_conv);
     conv_layer_free(hr0);
@@ -143,11 +155,25 @@ struct innfer_rrdb {
 
 namespace {
 
-int set_device(const innfer_rrdb* h) {
-  cudaError_t e = cudaSetDevice(h->device);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-  return 0;
-}
+// Every exported entry point that needs the handle's device makes it current for the duration of the call and
+// restores the caller's device afterwards (a process may drive several GPUs; torch keeps its own notion of the
+// current device and must not find it changed behind its back).
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int d) : dev(d) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define GUARD_DEVICE(d)  \
+  DeviceGuard _guard(d); \
+  if (_guard.err != cudaSuccess) return cuda_fail(_guard.err, "cudaSetDevice")
 
 int build_layer(innfer_rrdb* h, ConvLayer& L, const std::string& prefix, int Cout, int Cin, int up, int ksize = 3,
                 bool has_bias = true, int dil = 1) {
@@ -332,10 +358,33 @@ int finalize_pan(innfer_rrdb* h) {
 int run_conv(innfer_rrdb* h, const ConvLayer& L, ChunkView in, int B, int H, int W, ChunkView out,
              int out_nchunks, const Epilogue& ep, cudaStream_t st) {
   int rc;
+  cudaEvent_t ea = nullptr, eb = nullptr;
+  if (h->profiling == 2) {
+    // per-launch events: they also defeat the programmatic-dependent-launch overlap of consecutive convs, so the
+    // times of this mode are those of isolated launches (the per-batch mode 1 times the real schedule)
+    if (cudaEventCreate(&ea) != cudaSuccess || cudaEventCreate(&eb) != cudaSuccess) return fail(INNFER_E_CUDA, "cudaEventCreate");
+    cudaEventRecord(ea, st);
+  }
   if (h->cfg.fp16) {
     rc = conv_layer_run(L, h->cache, in, B, H, W, out, out_nchunks, ep, h->num_sms, st);
   } else {
+    g_last_conv_kernel = "conv_direct";
     rc = conv_direct_run(L, in, B, H, W, out, out_nchunks, ep, st);
+  }
+  if (h->profiling == 2) {
+    cudaEventRecord(eb, st);
+    char name[96];
+    snprintf(name, sizeof name, "%s %d->%d%s%s%s", g_last_conv_kernel, L.Cin, L.Cout, L.up > 1 ? (L.up == 2 ? " up2" : " up3") : "",
+             (ep.res1.base || ep.res2.base) ? " +res" : "", ep.compact4 ? " compact" : "");
+    auto& f = h->fam[name];
+    f.launches += 1;
+    // the reference conv: k*k*Cin*Cout MACs per output pixel (after the nearest upsample / pixel shuffle), real pixels only
+    const double opx = (double)B * H * W * L.up * L.up;
+    const int taps = (L.max_taps == 1 && L.up == 1) ? 1 : 9;
+    f.flop += 2.0 * taps * L.Cin * (double)L.Cout * opx;
+    const double e = (double)h->esz();
+    f.bytes += ((double)L.Cin * B * H * W + (double)L.Cout * opx * (1 + (ep.res1.base ? 1 : 0) + (ep.res2.base ? 1 : 0))) * e;
+    f.ev.emplace_back(ea, eb);
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (rc != 0) {
@@ -440,7 +489,7 @@ int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, b
 
 int forward_tiles(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool compact, cudaStream_t st) {
   g_wide_sep = wide_sep_of(h);
-  if (!h->profiling) return forward_tiles_impl(h, B, hgt, wid, dst, compact, st);
+  if (h->profiling != 1) return forward_tiles_impl(h, B, hgt, wid, dst, compact, st);
   cudaEvent_t a, b;
   CU_TRY(cudaEventCreate(&a));
   CU_TRY(cudaEventCreate(&b));
@@ -923,16 +972,16 @@ int blend_tiles(innfer_rrdb* h, const void* tiles_base, const TilePlan& plan, vo
   else
     rc = launch_blend_f32(reinterpret_cast<const float*>(tiles_base), oct, plan, h->cfg.scale, h->cfg.out_nc, dst, dt, stream);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  if (rc == -2) return fail(INNFER_E_UNSUPPORTED, "tile size with negative blend core (odd tile size)");
+  if (rc == -2) return fail(INNFER_E_UNSUPPORTED, "blend geometry not reproducible: negative blend core or an HR tile grid that differs from the LR one (utils.py:396-411)");
   if (rc) return fail(INNFER_E_CUDA, "blend launch failed");
   return 0;
 }
 
-int make_plan_checked(innfer_rrdb* h, int H, int W, int patch, float step, TilePlan& plan) {
+int make_plan_checked(innfer_rrdb* h, int H, int W, int patch, double step, TilePlan& plan) {
   if (!h->finalized) return fail(INNFER_E_STATE, "innfer_rrdb_finalize has not been called");
-  if (!(step >= 0.5f && step <= 1.0f)) return fail(INNFER_E_INVALID, "step must be in [0.5, 1.0]");
+  // recompose_tensor's own assertion (utils.py:391); Model.chop_forward defaults to 1.0, __call__ passes 0.5
+  if (!(step >= 0.5 && step <= 1.0)) return fail(INNFER_E_INVALID, "step must be in [0.5, 1.0]");
   if (make_tile_plan(H, W, patch, step, plan)) return fail(INNFER_E_INVALID, "cannot tile this image size");
-  if (step != 0.5f) return fail(INNFER_E_UNSUPPORTED, "only step=0.5 (run.py:214-215) is implemented");
   return 0;
 }
 
@@ -943,7 +992,7 @@ size_t tile_bytes(const innfer_rrdb* h, const TilePlan& plan) {
   return (size_t)oct * P * P * 8 * h->esz();
 }
 
-int chop_impl(innfer_rrdb* h, const void* src, PixelDType st, int H, int W, int patch, float step, void* dst,
+int chop_impl(innfer_rrdb* h, const void* src, PixelDType st, int H, int W, int patch, double step, void* dst,
               PixelDType dt, cudaStream_t stream) {
   TilePlan plan;
   int rc;
@@ -979,10 +1028,9 @@ int innfer_rrdb_create(const innfer_rrdb_cfg* cfg, int device, innfer_rrdb** out
     case 8: n_up = 3; break;
     default: return fail(INNFER_E_UNSUPPORTED, "scale must be 1, 2, 3, 4 or 8");
   }
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  GUARD_DEVICE(device);
   cudaDeviceProp prop;
-  e = cudaGetDeviceProperties(&prop, device);
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
   if (prop.major != 10)
     return fail(INNFER_E_UNSUPPORTED, "this library contains sm_100a code only; device is not compute capability 10.x");
@@ -1056,7 +1104,7 @@ int innfer_rrdb_finalize(innfer_rrdb* h) {
   if (!h) return fail(INNFER_E_INVALID, "null handle");
   if (h->finalized) return 0;
   int rc;
-  if ((rc = set_device(h))) return rc;
+  GUARD_DEVICE(h->device);
   const auto& c = h->cfg;
   size_t expected = 0;
   if (h->arch == 3) return finalize_pan(h);
@@ -1192,7 +1240,7 @@ int innfer_rrdb_finalize(innfer_rrdb* h) {
 
 void innfer_rrdb_destroy(innfer_rrdb* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   delete h;
 }
 
@@ -1210,7 +1258,34 @@ int innfer_rrdb_profile(innfer_rrdb* h, int enable) {
   }
   h->prof_events.clear();
   h->prof_conv_launches = 0;
-  h->profiling = enable != 0;
+  for (auto& f : h->fam)
+    for (auto& e : f.second.ev) {
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
+    }
+  h->fam.clear();
+  h->profiling = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
+  return 0;
+}
+
+int innfer_rrdb_profile_families(innfer_rrdb* h, char* buf, uint64_t cap, uint64_t* needed) {
+  if (!h || !needed) return fail(INNFER_E_INVALID, "null argument");
+  std::string out;
+  for (auto& kv : h->fam) {
+    double ms = 0.0;
+    for (auto& e : kv.second.ev) {
+      CU_TRY(cudaEventSynchronize(e.second));
+      float t = 0.f;
+      CU_TRY(cudaEventElapsedTime(&t, e.first, e.second));
+      ms += t;
+    }
+    char line[256];
+    snprintf(line, sizeof line, "%s\t%llu\t%.6f\t%.6e\t%.6e\n", kv.first.c_str(), (unsigned long long)kv.second.launches, ms,
+             kv.second.flop, kv.second.bytes);
+    out += line;
+  }
+  *needed = out.size() + 1;
+  if (buf && cap >= out.size() + 1) std::memcpy(buf, out.c_str(), out.size() + 1);
   return 0;
 }
 
@@ -1234,7 +1309,7 @@ int innfer_rrdb_forward(innfer_rrdb* h, const void* x, int n, int hgt, int wid, 
   if (dtype != INNFER_F16 && dtype != INNFER_F32) return fail(INNFER_E_INVALID, "dtype must be F16 or F32");
   if (n < 1 || hgt < 1 || wid < 1) return fail(INNFER_E_INVALID, "bad shape");
   int rc;
-  if ((rc = set_device(h))) return rc;
+  GUARD_DEVICE(h->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int s = h->cfg.scale;
   const int oct = (h->cfg.out_nc + 7) / 8;
@@ -1266,29 +1341,41 @@ int innfer_rrdb_forward(innfer_rrdb* h, const void* x, int n, int hgt, int wid, 
   return 0;
 }
 
-int innfer_rrdb_chop_forward(innfer_rrdb* h, const void* x, int H, int W, int patch_size, float step, void* y,
+int innfer_rrdb_chop_forward(innfer_rrdb* h, const void* x, int H, int W, int patch_size, double step, void* y,
                              int dtype, void* stream) {
   if (!h || !x || !y) return fail(INNFER_E_INVALID, "null argument");
   if (dtype != INNFER_F16 && dtype != INNFER_F32) return fail(INNFER_E_INVALID, "dtype must be F16 or F32");
   int rc;
-  if ((rc = set_device(h))) return rc;
+  GUARD_DEVICE(h->device);
   return chop_impl(h, x, to_pix(dtype), H, W, patch_size, step, y, to_pix(dtype), reinterpret_cast<cudaStream_t>(stream));
 }
 
-int innfer_rrdb_upscale_u8_device(innfer_rrdb* h, const uint8_t* img, int H, int W, int patch_size, float step,
+int innfer_rrdb_chop_forward_ex(innfer_rrdb* h, const void* x, int x_dtype, int H, int W, int patch_size, double step,
+                                void* y, int y_dtype, void* stream) {
+  if (!h || !x || !y) return fail(INNFER_E_INVALID, "null argument");
+  for (int d : {x_dtype, y_dtype}) {
+    if (d != INNFER_F16 && d != INNFER_F32 && d != INNFER_U8) return fail(INNFER_E_INVALID, "dtype must be F16, F32 or U8");
+  }
+  if (x_dtype == INNFER_U8 && h->cfg.in_nc != 3) return fail(INNFER_E_INVALID, "uint8 input needs a 3-channel model");
+  if (y_dtype == INNFER_U8 && h->cfg.out_nc != 3) return fail(INNFER_E_INVALID, "uint8 output needs a 3-channel model");
+  GUARD_DEVICE(h->device);
+  return chop_impl(h, x, to_pix(x_dtype), H, W, patch_size, step, y, to_pix(y_dtype), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int innfer_rrdb_upscale_u8_device(innfer_rrdb* h, const uint8_t* img, int H, int W, int patch_size, double step,
                                   uint8_t* out, void* stream) {
   if (!h || !img || !out) return fail(INNFER_E_INVALID, "null argument");
   if (h->cfg.in_nc != 3 || h->cfg.out_nc != 3) return fail(INNFER_E_INVALID, "uint8 path needs 3-channel models");
   int rc;
-  if ((rc = set_device(h))) return rc;
+  GUARD_DEVICE(h->device);
   return chop_impl(h, img, kU8, H, W, patch_size, step, out, kU8, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int innfer_rrdb_upscale_u8(innfer_rrdb* h, const uint8_t* img, int H, int W, int patch_size, float step,
+int innfer_rrdb_upscale_u8(innfer_rrdb* h, const uint8_t* img, int H, int W, int patch_size, double step,
                            uint8_t* out, void* stream) {
   if (!h || !img || !out) return fail(INNFER_E_INVALID, "null argument");
   int rc;
-  if ((rc = set_device(h))) return rc;
+  GUARD_DEVICE(h->device);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int s = h->cfg.scale;
   const size_t ib = (size_t)H * W * 3, ob = ib * s * s;
@@ -1302,11 +1389,11 @@ int innfer_rrdb_upscale_u8(innfer_rrdb* h, const uint8_t* img, int H, int W, int
   return 0;
 }
 
-int innfer_rrdb_tile_buffer(innfer_rrdb* h, int H, int W, int patch_size, float step, void** ptr, uint64_t* bytes,
+int innfer_rrdb_tile_buffer(innfer_rrdb* h, int H, int W, int patch_size, double step, void** ptr, uint64_t* bytes,
                             uint64_t* bytes_per_tile) {
   if (!h || !ptr || !bytes) return fail(INNFER_E_INVALID, "null argument");
   int rc;
-  if ((rc = set_device(h))) return rc;
+  GUARD_DEVICE(h->device);
   TilePlan plan;
   if ((rc = make_plan_checked(h, H, W, patch_size, step, plan))) return rc;
   const size_t tb = tile_bytes(h, plan), total = (size_t)plan.nty * plan.ntx * tb;
@@ -1317,11 +1404,24 @@ int innfer_rrdb_tile_buffer(innfer_rrdb* h, int H, int W, int patch_size, float 
   return 0;
 }
 
+int innfer_rrdb_tile_bytes(innfer_rrdb* h, int H, int W, int patch_size, double step, uint64_t* bytes_total,
+                           uint64_t* bytes_per_tile, int* ntiles) {
+  if (!h || !bytes_total) return fail(INNFER_E_INVALID, "null argument");
+  TilePlan plan;
+  int rc;
+  if ((rc = make_plan_checked(h, H, W, patch_size, step, plan))) return rc;
+  const size_t tb = tile_bytes(h, plan);
+  *bytes_total = (uint64_t)plan.nty * plan.ntx * tb;
+  if (bytes_per_tile) *bytes_per_tile = tb;
+  if (ntiles) *ntiles = plan.nty * plan.ntx;
+  return 0;
+}
+
 int innfer_rrdb_forward_tile_range(innfer_rrdb* h, const void* img, int img_dtype, int H, int W, int patch_size,
-                                   float step, int t_begin, int t_end, void* tiles_base, void* stream) {
+                                   double step, int t_begin, int t_end, void* tiles_base, void* stream) {
   if (!h || !img || !tiles_base) return fail(INNFER_E_INVALID, "null argument");
   int rc;
-  if ((rc = set_device(h))) return rc;
+  GUARD_DEVICE(h->device);
   TilePlan plan;
   if ((rc = make_plan_checked(h, H, W, patch_size, step, plan))) return rc;
   if (t_begin < 0 || t_end > plan.nty * plan.ntx || t_begin > t_end) return fail(INNFER_E_INVALID, "bad tile range");
@@ -1329,11 +1429,11 @@ int innfer_rrdb_forward_tile_range(innfer_rrdb* h, const void* img, int img_dtyp
   return compute_tiles(h, img, to_pix(img_dtype), plan, t_begin, t_end, tiles_base, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int innfer_rrdb_blend_tiles(innfer_rrdb* h, const void* tiles_base, int H, int W, int patch_size, float step, void* dst,
+int innfer_rrdb_blend_tiles(innfer_rrdb* h, const void* tiles_base, int H, int W, int patch_size, double step, void* dst,
                             int dst_dtype, void* stream) {
   if (!h || !tiles_base || !dst) return fail(INNFER_E_INVALID, "null argument");
   int rc;
-  if ((rc = set_device(h))) return rc;
+  GUARD_DEVICE(h->device);
   TilePlan plan;
   if ((rc = make_plan_checked(h, H, W, patch_size, step, plan))) return rc;
   return blend_tiles(h, tiles_base, plan, dst, to_pix(dst_dtype), reinterpret_cast<cudaStream_t>(stream));
@@ -1364,7 +1464,7 @@ int innfer_ipc_close(void* device_ptr) {
 
 int innfer_device_alloc(int device, uint64_t bytes, void** ptr) {
   if (!ptr) return fail(INNFER_E_INVALID, "null argument");
-  CU_TRY(cudaSetDevice(device));
+  GUARD_DEVICE(device);
   CU_TRY(cudaMalloc(ptr, bytes));
   return 0;
 }
@@ -1377,12 +1477,42 @@ int innfer_device_upload(void* device_dst, const void* host_src, uint64_t bytes,
   return 0;
 }
 
+int innfer_device_memset(void* ptr, int value, uint64_t bytes) {
+  if (!ptr) return fail(INNFER_E_INVALID, "null argument");
+  CU_TRY(cudaMemset(ptr, value, bytes));
+  CU_TRY(cudaDeviceSynchronize());
+  return 0;
+}
+
+int innfer_memcpy_async(void* dst, const void* src, uint64_t bytes, void* stream) {
+  if (!dst || !src) return fail(INNFER_E_INVALID, "null argument");
+  CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int innfer_stream_signal(void* const* flags, int n, uint32_t value, void* stream) {
+  if (!flags || n < 1 || n > kMaxSyncFlags) return fail(INNFER_E_INVALID, "bad flag list");
+  int rc = launch_signal(reinterpret_cast<uint32_t* const*>(flags), n, value, reinterpret_cast<cudaStream_t>(stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (rc) return fail(INNFER_E_CUDA, "signal launch failed");
+  return 0;
+}
+
+int innfer_stream_wait(void* const* flags, int n, uint32_t value, void* err_flag, uint64_t timeout_ms, void* stream) {
+  if (!flags || n < 1 || n > kMaxSyncFlags) return fail(INNFER_E_INVALID, "bad flag list");
+  int rc = launch_wait(reinterpret_cast<uint32_t* const*>(flags), n, value, reinterpret_cast<uint32_t*>(err_flag),
+                       (unsigned long long)timeout_ms * 1000000ull, reinterpret_cast<cudaStream_t>(stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (rc) return fail(INNFER_E_CUDA, "wait launch failed");
+  return 0;
+}
+
 int innfer_device_free(void* ptr) {
   if (ptr) CU_TRY(cudaFree(ptr));
   return 0;
 }
 
-int innfer_tiles_plan(int H, int W, int patch_size, float step, innfer_tile* out, int cap, int* n, int* tile_size) {
+int innfer_tiles_plan(int H, int W, int patch_size, double step, innfer_tile* out, int cap, int* n, int* tile_size) {
   TilePlan plan;
   if (make_tile_plan(H, W, patch_size, step, plan)) return fail(INNFER_E_INVALID, "cannot tile this image size");
   const int nt = plan.nty * plan.ntx;
@@ -1397,7 +1527,7 @@ int innfer_tiles_plan(int H, int W, int patch_size, float step, innfer_tile* out
   return 0;
 }
 
-int innfer_image_to_tiles(const void* src, int src_dtype, int C, int H, int W, int patch_size, float step,
+int innfer_image_to_tiles(const void* src, int src_dtype, int C, int H, int W, int patch_size, double step,
                           void* dst_tiles, void* stream) {
   if (!src || !dst_tiles) return fail(INNFER_E_INVALID, "null argument");
   TilePlan plan;
@@ -1410,16 +1540,29 @@ int innfer_image_to_tiles(const void* src, int src_dtype, int C, int H, int W, i
   return 0;
 }
 
-int innfer_blend(const void* tiles, int H, int W, int patch_size, float step, int scale, int C, void* dst,
+int innfer_blend(const void* tiles, int H, int W, int patch_size, double step, int scale, int C, void* dst,
                  int dst_dtype, void* stream) {
   if (!tiles || !dst) return fail(INNFER_E_INVALID, "null argument");
-  if (step != 0.5f) return fail(INNFER_E_UNSUPPORTED, "only step=0.5 is implemented");
+  if (!(step >= 0.5 && step <= 1.0)) return fail(INNFER_E_INVALID, "step must be in [0.5, 1.0]");
   TilePlan plan;
   if (make_tile_plan(H, W, patch_size, step, plan)) return fail(INNFER_E_INVALID, "cannot tile this image size");
   int rc = launch_blend(reinterpret_cast<const __half*>(tiles), 1, plan, scale, C, dst, to_pix(dst_dtype),
                         reinterpret_cast<cudaStream_t>(stream));
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  if (rc == -2) return fail(INNFER_E_UNSUPPORTED, "tile size with negative blend core (odd tile size)");
+  if (rc == -2) return fail(INNFER_E_UNSUPPORTED, "blend geometry not reproducible: negative blend core or an HR tile grid that differs from the LR one (utils.py:396-411)");
+  if (rc) return fail(INNFER_E_CUDA, "blend launch failed");
+  return 0;
+}
+
+int innfer_blend_f32(const float* tiles, int H, int W, int patch_size, double step, int scale, int C, void* dst,
+                     int dst_dtype, void* stream) {
+  if (!tiles || !dst) return fail(INNFER_E_INVALID, "null argument");
+  if (!(step >= 0.5 && step <= 1.0)) return fail(INNFER_E_INVALID, "step must be in [0.5, 1.0]");
+  TilePlan plan;
+  if (make_tile_plan(H, W, patch_size, step, plan)) return fail(INNFER_E_INVALID, "cannot tile this image size");
+  int rc = launch_blend_f32(tiles, 1, plan, scale, C, dst, to_pix(dst_dtype), reinterpret_cast<cudaStream_t>(stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (rc == -2) return fail(INNFER_E_UNSUPPORTED, "blend geometry not reproducible: negative blend core or an HR tile grid that differs from the LR one (utils.py:396-411)");
   if (rc) return fail(INNFER_E_CUDA, "blend launch failed");
   return 0;
 }
@@ -1584,7 +1727,7 @@ int innfer_color_fix(const uint8_t* lr, int h, int w, const uint8_t* sr, int H, 
 
 int innfer_color_fix_host(const uint8_t* lr, int h, int w, const uint8_t* sr, int H, int W, uint8_t* out, int device) {
   if (!lr || !sr || !out) return fail(INNFER_E_INVALID, "null argument");
-  CU_TRY(cudaSetDevice(device));
+  GUARD_DEVICE(device);
   DevBuf dl, ds, dout;
   const size_t lb = (size_t)h * w * 3, sb = (size_t)H * W * 3;
   if (dl.ensure(lb) || ds.ensure(sb) || dout.ensure(sb)) {

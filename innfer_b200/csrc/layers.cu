@@ -10,6 +10,7 @@
 
 namespace innfer {
 
+thread_local const char* g_last_conv_kernel = "";   // which kernel the last conv_layer_run picked (profiling)
 long long* g_rows_trace = nullptr;  // device buffer of 3072 int64 (innfer_debug_set_trace), debugging only
 
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -380,6 +381,7 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   int rc = 0;
   const CUtensorMap* tm = cache.get_rows(in.base, in.CT, H, in.Wtot, kc, rc);
   if (!tm) return rc ? rc : -5;
+  g_last_conv_kernel = pair ? "conv_rows_pair" : (dilv ? "conv_rows_dil" : "conv_rows");
   return launch_conv_rows(tm, p, CR, num_sms, stream);
 }
 
@@ -525,11 +527,13 @@ int conv_layer_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int B, in
       p.stages = Su > 12 ? 12 : Su;
       const CUtensorMap* tmu = cache.get(in.base, srcB, in.CT, H, srcW, 10, kPatchRows + 2, rc);
       if (!tmu) return rc ? rc : -5;
+      g_last_conv_kernel = "conv_up";
       return launch_conv_up(tmu, p, num_sms, stream);
     }
   }
   const CUtensorMap* tm = cache.get(in.base, srcB, in.CT, H, srcW, 8 * J + 2 * L.dil, kPatchRows + 2 * L.dil, rc);
   if (!tm) return rc ? rc : -5;
+  g_last_conv_kernel = "conv_tc";
   return launch_conv_tc(tm, p, N, num_sms, stream);
 }
 

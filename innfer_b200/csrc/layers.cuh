@@ -94,6 +94,7 @@ class TmapCache {
 };
 
 extern long long* g_rows_trace;
+extern thread_local const char* g_last_conv_kernel;   // "conv_rows", "conv_rows_pair", "conv_rows_dil", "conv_up" or "conv_tc"
 
 // Pick the number of 8-pixel sub-patches per CTA for an image of width W and accumulator width N.
 int choose_J(int W, int N);

@@ -4,7 +4,7 @@
 
 namespace innfer {
 
-int make_tile_plan(int H, int W, int patch, float step, TilePlan& plan) {
+int make_tile_plan(int H, int W, int patch, double step, TilePlan& plan) {
   if (H <= 0 || W <= 0 || patch <= 0) return -1;
   int p = H < W ? H : W;
   if (patch < p) p = patch;
@@ -15,6 +15,7 @@ int make_tile_plan(int H, int W, int patch, float step, TilePlan& plan) {
   int s = (int)((double)p * (double)step);
   if (s < 1) return -1;
   plan.step = s;
+  plan.stepf = (double)step;
   auto fill = [&](int L, int* o, int& n) -> int {
     n = 0;
     const int cnt = (L - p) / s + 1;  // tensor.unfold window count
@@ -136,6 +137,7 @@ struct BlendGeom {
 
 // torch.linspace(0.1, 1.0, n) in fp32 (symmetric evaluation), then ones, then linspace(1.0, 0.1, n)
 __device__ __forceinline__ float blend_profile(int i, int P, int n) {
+  if (n == 1) return i == 0 ? 0.1f : 1.0f;   // linspace(a, b, 1) == [a]: ramp-in [0.1], ramp-out [1.0]
   const float step = n > 1 ? (1.0f - 0.1f) / (float)(n - 1) : 0.f;
   if (i < n) {
     return (i < n / 2) ? 0.1f + step * (float)i : 1.0f - step * (float)(n - 1 - i);
@@ -383,13 +385,25 @@ int blend_impl(const E* tiles, int CT, const TilePlan& plan, int scale, int C, v
   g.Hs = plan.H * scale;
   g.Ws = plan.W * scale;
   g.P = plan.p * scale;
-  // recompose_tensor (utils.py:396-399): overlap = scale*int(round((1-step)*(P/scale))), step 0.5;
-  // Python's round() is round-half-to-even, as is nearbyint in the default rounding mode.
-  g.overlap = scale * (int)std::nearbyint(0.5 * ((double)g.P / (double)scale));
-  g.eff = (int)(0.5 * (double)g.P);
+  // recompose_tensor (utils.py:396-399): overlap = scale*int(round((1-step)*(P/scale))), eff = int(step*P), all in
+  // Python float (double) arithmetic; Python's round() is round-half-to-even, as is nearbyint in the default mode.
+  const double sf = plan.stepf;
+  g.overlap = scale * (int)std::nearbyint((1.0 - sf) * ((double)g.P / (double)scale));
+  g.eff = (int)(sf * (double)g.P);
   if (g.P - 2 * g.overlap < 0 || g.eff < 1) return -2;
   g.nty = plan.nty;
   g.ntx = plan.ntx;
+  // the reference re-derives the tile grid from the HR sizes (utils.py:405-411); when that disagrees with the grid
+  // the tiles were cut on (possible for step != 0.5 with odd products) its patch index runs off: refuse loudly
+  {
+    const int stride = (int)((double)g.P * sf);
+    if (stride < 1) return -2;
+    auto count = [&](int full) {
+      const int span = (full > g.P ? full : g.P) - g.P;
+      return 1 + span / stride + (span % stride != 0 ? 1 : 0);
+    };
+    if (count(g.Hs) != plan.nty || count(g.Ws) != plan.ntx) return -2;
+  }
   for (int i = 0; i < plan.nty; ++i) {
     const int o = i * g.eff;
     g.oys[i] = o < g.Hs - g.P ? o : g.Hs - g.P;

@@ -16,12 +16,13 @@ struct TilePlan {
   int H, W;        // image size
   int p;           // tile size = min(H, W, patch)
   int step;        // int(p * step)
+  double stepf;    // the step factor itself (0.5 .. 1.0): recompose_tensor derives its overlap from it
   int nty, ntx;    // tiles per axis
   int ys[kMaxTilesPerAxis];
   int xs[kMaxTilesPerAxis];
 };
 // Fills the plan following extract_patches_2d (utils.py:349-362). Returns 0 or negative error.
-int make_tile_plan(int H, int W, int patch, float step, TilePlan& plan);
+int make_tile_plan(int H, int W, int patch, double step, TilePlan& plan);
 
 enum PixelDType { kF16 = 0, kF32 = 1, kU8 = 2 };
 

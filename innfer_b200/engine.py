@@ -78,7 +78,8 @@ class RRDBEngine:
         N.check(self.lib.innfer_rrdb_set_max_batch(self._h, int(n)))
 
     def profile_reset(self, enable=True):
-        """Start (or stop) device-side timing of the conv sequence; see innfer_rrdb_profile."""
+        """Start (1 / True), start per-launch family timing (2) or stop (0) device-side timing of the conv
+        sequence; see innfer_rrdb_profile."""
         N.check(self.lib.innfer_rrdb_profile(self._h, int(enable)))
 
     def profile_read(self):
@@ -112,8 +113,9 @@ class RRDBEngine:
         n, _, h, w = x.shape
         s = self.cfg["scale"]
         y = torch.empty((n, self.cfg["out_nc"], s * h, s * w), dtype=x.dtype, device=x.device)
-        N.check(self.lib.innfer_rrdb_forward(self._h, x.data_ptr(), n, h, w, y.data_ptr(), _dtype_code(x.dtype),
-                                             _stream_ptr(x.device)))
+        with torch.cuda.device(self.index):
+            N.check(self.lib.innfer_rrdb_forward(self._h, x.data_ptr(), n, h, w, y.data_ptr(), _dtype_code(x.dtype),
+                                                 _stream_ptr(x.device)))
         return y
 
     def chop_forward(self, x, patch_size=200, step=0.5):
@@ -124,18 +126,35 @@ class RRDBEngine:
         _, _, H, W = x.shape
         s = self.cfg["scale"]
         y = torch.empty((1, self.cfg["out_nc"], s * H, s * W), dtype=x.dtype, device=x.device)
-        N.check(self.lib.innfer_rrdb_chop_forward(self._h, x.data_ptr(), H, W, int(patch_size), float(step),
-                                                  y.data_ptr(), _dtype_code(x.dtype), _stream_ptr(x.device)))
+        with torch.cuda.device(self.index):
+            N.check(self.lib.innfer_rrdb_chop_forward(self._h, x.data_ptr(), H, W, int(patch_size), float(step),
+                                                      y.data_ptr(), _dtype_code(x.dtype), _stream_ptr(x.device)))
         return y
+
+    def _check_u8_out(self, out, H, W, device):
+        """A caller-supplied uint8 [s*H, s*W, 3] result buffer: host (numpy / CPU tensor) or on `device`."""
+        s = self.cfg["scale"]
+        shape = (s * H, s * W, 3)
+        if isinstance(out, torch.Tensor):
+            ok = out.dtype == torch.uint8 and tuple(out.shape) == shape and out.is_contiguous()
+            on_dev = out.is_cuda and (out.device.index is None or out.device.index == self.index)
+            ok = ok and (on_dev if device else not out.is_cuda)
+        else:
+            ok = (not device and isinstance(out, np.ndarray) and out.dtype == np.uint8 and out.shape == shape
+                  and out.flags["C_CONTIGUOUS"] and out.flags["WRITEABLE"])
+        if not ok:
+            raise ValueError("`out` must be a contiguous uint8 %s %s" % (shape, "tensor on %s" % self.device if device
+                                                                        else "host array"))
+        return out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
 
     def upscale_u8(self, img, patch_size=200, step=0.5, out=None):
         """np2tensor -> chop_forward -> tensor2np fused.  ``img``: HOST uint8 HWC BGR array (numpy, or
         a pinned CPU torch tensor); returns a HOST uint8 array [s*H, s*W, 3].  H2D and D2H copies are
         part of the call."""
         if isinstance(img, torch.Tensor):
+            if img.dtype != torch.uint8 or img.is_cuda or not img.is_contiguous() or img.dim() != 3:
+                raise ValueError("expected a contiguous CPU uint8 HWC tensor")
             src_ptr, (H, W, C) = img.data_ptr(), img.shape
-            if img.dtype != torch.uint8 or img.is_cuda or not img.is_contiguous():
-                raise ValueError("expected a contiguous CPU uint8 tensor")
         else:
             img = np.ascontiguousarray(img)
             if img.dtype != np.uint8 or img.ndim != 3:
@@ -146,20 +165,68 @@ class RRDBEngine:
         s = self.cfg["scale"]
         if out is None:
             out = np.empty((s * H, s * W, 3), dtype=np.uint8)
-        dst_ptr = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
+        dst_ptr = self._check_u8_out(out, H, W, device=False)
         with torch.cuda.device(self.index):
             N.check(self.lib.innfer_rrdb_upscale_u8(self._h, src_ptr, H, W, int(patch_size), float(step), dst_ptr,
                                                     _stream_ptr(self.device)))
         return out
 
+    def _check_u8_device_image(self, img):
+        if not isinstance(img, torch.Tensor) or img.dtype != torch.uint8 or not img.is_cuda or img.dim() != 3 \
+                or img.shape[2] != 3 or not img.is_contiguous() or \
+                (img.device.index is not None and img.device.index != self.index):
+            raise ValueError("expected a contiguous uint8 [H, W, 3] tensor on %s" % self.device)
+        return img.shape[0], img.shape[1]
+
     def upscale_u8_device(self, img, patch_size=200, step=0.5, out=None):
         """Same with DEVICE uint8 tensors (no copies, no synchronisation)."""
-        H, W, _ = img.shape
+        H, W = self._check_u8_device_image(img)
         s = self.cfg["scale"]
         if out is None:
             out = torch.empty((s * H, s * W, 3), dtype=torch.uint8, device=img.device)
-        N.check(self.lib.innfer_rrdb_upscale_u8_device(self._h, img.data_ptr(), H, W, int(patch_size), float(step),
-                                                       out.data_ptr(), _stream_ptr(img.device)))
+        dst = self._check_u8_out(out, H, W, device=True)
+        with torch.cuda.device(self.index):
+            N.check(self.lib.innfer_rrdb_upscale_u8_device(self._h, img.data_ptr(), H, W, int(patch_size), float(step),
+                                                           dst, _stream_ptr(img.device)))
+        return out
+
+    def chop_forward_ex(self, x, patch_size=200, step=0.5, out_u8=False):
+        """chop_forward with independent element types at the two ends (innfer_rrdb_chop_forward_ex): ``x`` is a
+        device uint8 [H, W, 3] BGR image (np2tensor fused) or a [1, C, H, W] fp16/fp32 tensor; the result is a
+        device uint8 [s*H, s*W, 3] BGR image (tensor2np fused) if ``out_u8`` else a [1, C, s*H, s*W] tensor of the
+        engine's precision.  Lets a model chain stay on the device with float tensors between the models."""
+        s = self.cfg["scale"]
+        if x.dtype == torch.uint8:
+            H, W = self._check_u8_device_image(x)
+            xcode = N.INNFER_U8
+        else:
+            x = self._check_input(x)
+            if x.shape[0] != 1:
+                raise ValueError("chop_forward expects batch size 1")
+            H, W = x.shape[2], x.shape[3]
+            xcode = _dtype_code(x.dtype)
+        if out_u8:
+            y = torch.empty((s * H, s * W, 3), dtype=torch.uint8, device=x.device)
+            ycode = N.INNFER_U8
+        else:
+            dt = torch.float16 if self.fp16 else torch.float32
+            y = torch.empty((1, self.cfg["out_nc"], s * H, s * W), dtype=dt, device=x.device)
+            ycode = _dtype_code(dt)
+        with torch.cuda.device(self.index):
+            N.check(self.lib.innfer_rrdb_chop_forward_ex(self._h, x.data_ptr(), xcode, H, W, int(patch_size), float(step),
+                                                         y.data_ptr(), ycode, _stream_ptr(x.device)))
+        return y
+
+    def profile_families(self):
+        """Per kernel family since profile_reset(2): {name: (launches, total ms, algorithmic FLOP, algorithmic bytes)}."""
+        need = ctypes.c_uint64()
+        N.check(self.lib.innfer_rrdb_profile_families(self._h, None, 0, ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        N.check(self.lib.innfer_rrdb_profile_families(self._h, buf, need.value, ctypes.byref(need)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms, flop, nbytes = line.split("\t")
+            out[name] = (int(n), float(ms), float(flop), float(nbytes))
         return out
 
 

@@ -13,7 +13,7 @@ import torch
 
 from .architectures import get_network
 from .utils.defaults import get_network_G_config
-from .utils.utils import (color_fix, extract_patches_2d, get_images_paths, get_models_paths, mod2normal, np2tensor,
+from .utils.utils import (color_fix, color_fix_device, extract_patches_2d, get_images_paths, get_models_paths, mod2normal, np2tensor,
                           read_img, recompose_tensor, save_img, save_img_comp, swa2normal, tensor2np)
 
 # key that identifies each architecture family, probed in the reference's order (run.py:50-72)
@@ -183,6 +183,64 @@ def get_scale_name(model_path, scale=None):
 default_extras = {"meval": True, "strict": True, "normalize": False}
 
 
+# ---------------------------------------------------------------------- fused device path of the CLI loop
+def native_chain(models, device, fp16):
+    """The engines of a model chain if the whole per-image loop of run.py:421-434 can stay on the device
+    (np2tensor -> [chop_forward per model] -> tensor2np [-> color_fix]), else None.  That needs a CUDA device, chop
+    mode, and every model to be a 3-channel network with a native engine."""
+    if torch.device(device).type != "cuda":
+        return None
+    dtype = torch.float16 if fp16 else torch.float32
+    engines = []
+    for m in models:
+        net = m.model
+        if m.arch == "ts" or not m.chop or not hasattr(net, "native_engine") or m.in_nc != 3 or m.out_nc != 3:
+            return None
+        engines.append(net.native_engine(device, dtype))
+    return engines
+
+
+class ChainRunner:
+    """uint8 HWC BGR frame in, uint8 frame out, everything in between on the device: H2D of the frame from a pinned
+    staging buffer, image -> tiles (np2tensor fused) -> model 1 -> fp16/fp32 tensor -> ... -> last model -> blend to
+    uint8 (tensor2np fused) -> optional -cf colour fix (three kernels) -> one D2H into pinned memory."""
+
+    def __init__(self, engines, device, cf=False, patch_size=200, step=0.5):
+        self.engines, self.device, self.cf = engines, torch.device(device), cf
+        self.patch_size, self.step = patch_size, step
+        self._pin_in = self._pin_out = None
+
+    def _pinned(self, attr, shape):
+        buf = getattr(self, attr)
+        if buf is None or tuple(buf.shape) != tuple(shape):
+            buf = torch.empty(shape, dtype=torch.uint8).pin_memory()
+            setattr(self, attr, buf)
+        return buf
+
+    def run_device(self, d_img):
+        """Device uint8 [H,W,3] -> device uint8 [S*H,S*W,3] (no synchronisation)."""
+        x = d_img
+        for i, eng in enumerate(self.engines):
+            x = eng.chop_forward_ex(x, self.patch_size, self.step, out_u8=(i == len(self.engines) - 1))
+        if self.cf:
+            x = color_fix_device(d_img, x)
+        return x
+
+    def __call__(self, img):
+        """Host uint8 HWC BGR numpy image -> host uint8 numpy image (a view of the runner's pinned result buffer,
+        valid until the next call)."""
+        if img.dtype != "uint8" or img.ndim != 3 or img.shape[2] != 3:
+            raise ValueError("expected a uint8 HWC 3-channel image")
+        stage = self._pinned("_pin_in", img.shape)
+        stage.numpy()[...] = img
+        d_img = stage.to(self.device, non_blocking=True)
+        d_out = self.run_device(d_img)
+        res = self._pinned("_pin_out", d_out.shape)
+        res.copy_(d_out, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return res.numpy()
+
+
 def build_parser():
     p = argparse.ArgumentParser()
     p.add_argument("-models", "-m", type=str, required=True, help="Path to models.")
@@ -227,11 +285,23 @@ def main(argv=None):
             m.model.half()
         models.append(m)
 
+    engines = None if normalize else native_chain(models, device, fp16)
+    runner = ChainRunner(engines, device, cf=args.cf) if engines else None
+
     for image_path in get_images_paths(args.input):
         name = osp.splitext(osp.basename(image_path))[0]
         img = read_img(image_path)
         if img is None:
             print(f"Error reading image {image_path}, skipping.")
+            continue
+        if runner is not None and img.dtype == "uint8" and img.ndim == 3 and img.shape[2] == 3:
+            # 3-channel uint8 image through 3-channel native models: the whole loop body below as one device pipeline
+            img_out = runner(img).copy()
+            out_path = osp.join(args.output, f"{name:s}.png")
+            if args.comp:
+                save_img_comp([img, img_out], out_path)
+            else:
+                save_img(img_out, out_path)
             continue
         t_img = np2tensor(img, normalize=normalize).to(device)
         t_img = t_img.half() if fp16 else t_img

@@ -176,6 +176,26 @@ def color_fix(imgA, imgB, device=None):
     return linear2srgb(low + b)
 
 
+def color_fix_device(lr, sr, out=None):
+    """color_fix on DEVICE uint8 HWC tensors (lr [h,w,3], sr [H,W,3]) -> device uint8 [H,W,3]; the three native
+    kernels of innfer_color_fix on the current stream, no host round trip."""
+    from .. import _native as N
+    for t in (lr, sr):
+        if not isinstance(t, torch.Tensor) or t.dtype != torch.uint8 or not t.is_cuda or t.dim() != 3 or t.shape[2] != 3 \
+                or not t.is_contiguous():
+            raise ValueError("color_fix_device expects contiguous CUDA uint8 [H, W, 3] tensors")
+    if lr.device != sr.device:
+        raise ValueError("both images must live on the same device")
+    if out is None:
+        out = torch.empty_like(sr)
+    elif out.dtype != torch.uint8 or out.shape != sr.shape or out.device != sr.device or not out.is_contiguous():
+        raise ValueError("`out` must match the SR image")
+    with torch.cuda.device(sr.device):
+        N.check(N.load().innfer_color_fix(lr.data_ptr(), lr.shape[0], lr.shape[1], sr.data_ptr(), sr.shape[0], sr.shape[1],
+                                          out.data_ptr(), torch.cuda.current_stream(sr.device).cuda_stream))
+    return out
+
+
 # ------------------------------------------------------------------------------------ tiling
 def _tile_starts(length, size, stride):
     starts = list(range(0, length - size + 1, stride))
@@ -236,21 +256,41 @@ def recompose_tensor(patches, height, width, step=None, scale=1):
 
 
 def _recompose_native(patches, height, width, step, scale):
+    """CUDA branch of recompose_tensor: the gather-blend kernel, in the tiles' own precision (fp16 tiles blend from
+    fp16, fp32 tiles from fp32), one image at a time for a batch (final_batch_size = n // tiles per image,
+    utils.py:412 of the reference)."""
+    import ctypes
+
     from .. import _native as N
     lib = N.load()
-    n, ch, P, _ = patches.shape
+    n, ch, P, Pw = patches.shape
+    if P != Pw:
+        raise ValueError("square tiles expected, got %dx%d" % (P, Pw))
     if ch > 8:
         raise ValueError("native blend supports up to 8 channels")
+    if patches.dtype not in (torch.float16, torch.float32):
+        raise TypeError("native blend expects float16 or float32 tiles, got %s" % patches.dtype)
+    if P % scale:
+        raise ValueError("tile size %d is not a multiple of the scale %d" % (P, scale))
     p = P // scale
-    # tiles -> planar-chunk [n][1][P][P][8] fp16
-    chunks = torch.zeros(n, 1, P, P, 8, dtype=torch.float16, device=patches.device)
-    chunks[:, 0, :, :, :ch] = patches.permute(0, 2, 3, 1).to(torch.float16)
-    out = torch.empty(1, ch, scale * height, scale * width, dtype=patches.dtype, device=patches.device)
-    code = N.INNFER_F16 if patches.dtype == torch.float16 else N.INNFER_F32
+    nt, ts = ctypes.c_int(), ctypes.c_int()
+    N.check(lib.innfer_tiles_plan(height, width, p, float(step), None, 0, ctypes.byref(nt), ctypes.byref(ts)))
+    if ts.value != p or nt.value < 1 or n % nt.value:
+        raise ValueError("%d tiles of %d px do not cover a %dx%d image (%d tiles of %d px per image expected)"
+                         % (n, p, height, width, nt.value, ts.value))
+    batch = n // nt.value
+    f16 = patches.dtype == torch.float16
+    # tiles -> planar-chunk [n][1][P][P][8]
+    chunks = torch.zeros(n, 1, P, P, 8, dtype=patches.dtype, device=patches.device)
+    chunks[:, 0, :, :, :ch] = patches.permute(0, 2, 3, 1)
+    out = torch.empty(batch, ch, scale * height, scale * width, dtype=patches.dtype, device=patches.device)
+    code = N.INNFER_F16 if f16 else N.INNFER_F32
+    fn = lib.innfer_blend if f16 else lib.innfer_blend_f32
     stream = torch.cuda.current_stream(patches.device).cuda_stream
     with torch.cuda.device(patches.device):
-        N.check(lib.innfer_blend(chunks.data_ptr(), height, width, p, float(step), scale, ch, out.data_ptr(), code,
-                                 stream))
+        for b in range(batch):
+            N.check(fn(chunks[b * nt.value:(b + 1) * nt.value].data_ptr(), height, width, p, float(step), scale, ch,
+                       out[b].data_ptr(), code, stream))
     return out
 
 

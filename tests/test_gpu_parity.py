@@ -665,3 +665,149 @@ def test_chop_is_independent_of_the_tile_batch_size(dev, family):
         outs.append(net.chop_forward_native(xd, 32, 0.5).cpu())
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     assert outs[0].shape == (1, 3, 144, 176) and torch.isfinite(outs[0].float()).all()
+
+
+# ------------------------------------------------------------------------------------------------ round 2
+def _steps_cases():
+    g = golden("chop_steps.npz")
+    out = []
+    for key in [k for k in g.files if k.startswith("y_")]:
+        parts = key[2:].split("_")
+        scale, (h, w), patch = int(parts[0][1:]), [int(v) for v in parts[1].split("x")], int(parts[2][1:])
+        out.append((key[2:], scale, h, w, patch, float(parts[3].replace("step", "").replace("p", "."))))
+    return out
+
+
+@pytest.mark.parametrize("fp16", [True, False])
+def test_chop_forward_other_steps_vs_reference_fixture(dev, fp16):
+    """step in (0.5, 1.0] through the native chop path (Model.chop_forward's own default is 1.0, run.py:167):
+    overlap, effective stride and the edge-anchored tiles follow utils.py:349-362,396-443."""
+    g = golden("chop_steps.npz")
+    for key, scale, h, w, patch, step in _steps_cases():
+        sd = O.make_state_dict(scale=scale, nb=int(g["nb"]), seed=int(g["seed"]))
+        img = synth_image(int(g["img_seed"]), h, w)
+        eng = _engine(sd, dev, fp16=fp16, scale=scale)
+        x = O.np2tensor(img).to(dev, torch.float16 if fp16 else torch.float32)
+        y = eng.chop_forward(x, patch, step)
+        u8 = O.tensor2np(y)
+        assert np.abs(u8.astype(int) - g["u8_" + key].astype(int)).max() <= 1, key
+        assert psnr_u8(u8, g["u8_" + key]) >= 50.0, key
+        if not fp16:
+            assert np.abs(y.cpu().numpy() - g["y_" + key]).max() / np.abs(g["y_" + key]).max() <= 1e-4, key
+        if fp16:   # fused uint8 path with the same step
+            u8b = eng.upscale_u8(img, patch, step)
+            assert np.abs(u8b.astype(int) - g["u8_" + key].astype(int)).max() <= 1, key
+        eng.close()
+
+
+def test_recompose_tensor_cuda_other_steps_fp32_and_batches(dev):
+    """utils.recompose_tensor on CUDA tiles: step != 0.5, fp32 tiles stay fp32 (1e-6 of the reference), fp16 tiles
+    within fp16 rounding, a batch of two images, and a wrong tile count is rejected."""
+    from innfer_b200.utils import utils as U
+    rec = golden("recompose_steps.npz")
+    for key in rec.files:
+        parts = key.split("_")
+        h, w, p, s = (int(v) for v in parts[1:5])
+        step = float(parts[5].replace("p", "."))
+        pp = min(h, w, p)
+        n = len(O.tile_origins(h, pp, step)) * len(O.tile_origins(w, pp, step))
+        tiles = torch.rand(n, 3, s * pp, s * pp, generator=torch.Generator().manual_seed(13))
+        got = U.recompose_tensor(tiles.to(dev), h, w, step=step, scale=s)
+        assert got.dtype == torch.float32
+        np.testing.assert_allclose(got.cpu().numpy(), rec[key], atol=2e-6, err_msg=key)
+        got16 = U.recompose_tensor(tiles.to(dev, torch.float16), h, w, step=step, scale=s)
+        assert got16.dtype == torch.float16
+        np.testing.assert_allclose(got16.float().cpu().numpy(), rec[key], atol=2e-3, err_msg=key)
+        two = U.recompose_tensor(torch.cat([tiles, tiles.flip(0)], 0).to(dev), h, w, step=step, scale=s)
+        assert two.shape[0] == 2
+        np.testing.assert_allclose(two[0].cpu().numpy(), rec[key][0], atol=2e-6)
+        want1 = U.recompose_tensor(tiles.flip(0), h, w, step=step, scale=s)
+        np.testing.assert_allclose(two[1].cpu().numpy(), want1[0].numpy(), atol=2e-6)
+        if n > 1:
+            with pytest.raises(ValueError):
+                U.recompose_tensor(tiles[:-1].to(dev), h, w, step=step, scale=s)
+
+
+def test_chain_runner_device_pipeline_vs_reference_fixture(dev):
+    """run.ChainRunner (what the CLI and bench.py --workload chain use): uint8 frame -> 1x net -> fp16 tensor -> 4x net
+    -> uint8 -> -cf, all on the device, against the reference's chain fixture."""
+    from innfer_b200 import run as R
+    from innfer_b200.engine import RRDBEngine
+    g = golden("chain_1x4x_cf_40x56.npz")
+    img = synth_image(7, 40, 56)
+    engines = []
+    for scale, seed in ((1, 5), (4, 6)):
+        sd = O.make_state_dict(scale=scale, nb=1, seed=seed)
+        engines.append(RRDBEngine.from_state_dict(sd, dict(in_nc=3, out_nc=3, nf=64, nb=1, gc=32, scale=scale, plus=False),
+                                                  dev, fp16=True))
+    plain = R.ChainRunner(engines, dev, cf=False, patch_size=200, step=0.5)(img).copy()
+    assert np.abs(plain.astype(int) - g["u8"].astype(int)).max() <= 1
+    assert psnr_u8(plain, g["u8"]) >= 50.0
+    fixed = R.ChainRunner(engines, dev, cf=True, patch_size=200, step=0.5)(img).copy()
+    d = np.abs(fixed.astype(int) - g["cf"].astype(int))
+    assert d.max() <= 3 and (d > 1).mean() < 0.02      # see test_python_api_model_chain_and_color_fix
+    # the intermediate tensor is a float tensor as in the reference, not a quantised image
+    mid = engines[0].chop_forward_ex(torch.from_numpy(img).to(dev), 200, 0.5, out_u8=False)
+    assert mid.dtype == torch.float16 and tuple(mid.shape) == (1, 3, 40, 56)
+    for e in engines:
+        e.close()
+
+
+def test_u8_wrappers_validate_their_buffers(dev):
+    sd = O.make_state_dict(scale=4, nb=1, seed=1)
+    eng = _engine(sd, dev)
+    img = torch.from_numpy(synth_image(1, 24, 32)).to(dev)
+    with pytest.raises(ValueError):
+        eng.upscale_u8_device(img.float())
+    with pytest.raises(ValueError):
+        eng.upscale_u8_device(img[:, :, :2])
+    with pytest.raises(ValueError):
+        eng.upscale_u8_device(img, out=torch.empty(96, 128, 3, dtype=torch.uint8))          # host buffer
+    with pytest.raises(ValueError):
+        eng.upscale_u8_device(img, out=torch.empty(95, 128, 3, dtype=torch.uint8, device=dev))
+    with pytest.raises(ValueError):
+        eng.upscale_u8(img.cpu().numpy(), out=np.empty((96, 127, 3), np.uint8))
+    out = eng.upscale_u8_device(img, 200, 0.5)
+    assert tuple(out.shape) == (96, 128, 3)
+    eng.close()
+
+
+def test_stream_flags_signal_wait_and_timeout(native, dev):
+    """csrc/sync_ops.cu on one device: a wait released by a signal from another stream, and a wait nobody releases
+    raising the error word after its timeout instead of hanging."""
+    lib = native.load()
+    flags = torch.zeros(8, dtype=torch.int32, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    marker = torch.zeros(1, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    arr = (ctypes.c_void_p * 2)(flags.data_ptr(), flags.data_ptr() + 4)
+    native.check(lib.innfer_stream_wait(arr, 2, 5, ctypes.c_void_p(flags.data_ptr() + 28), 20000, ctypes.c_void_p(s1.cuda_stream)))
+    with torch.cuda.stream(s1):
+        marker.add_(1)
+    assert not s1.query()                 # held by the wait kernel
+    native.check(lib.innfer_stream_signal(arr, 2, 5, ctypes.c_void_p(s2.cuda_stream)))
+    s1.synchronize()
+    assert int(marker.item()) == 1 and flags[:2].tolist() == [5, 5] and int(flags[7].item()) == 0
+    arr1 = (ctypes.c_void_p * 1)(flags.data_ptr() + 8)
+    native.check(lib.innfer_stream_wait(arr1, 1, 1, ctypes.c_void_p(flags.data_ptr() + 28), 50, ctypes.c_void_p(s1.cuda_stream)))
+    s1.synchronize()
+    assert int(flags[7].item()) == 1
+
+
+def test_profile_families_account_for_every_conv(dev):
+    from innfer_b200 import synth
+    sd = O.make_state_dict(scale=4, nb=2, seed=1)
+    eng = _engine(sd, dev)
+    img = torch.from_numpy(synth_image(2, 64, 96)).to(dev)
+    eng.upscale_u8_device(img, 32, 0.5)
+    eng.profile_reset(2)
+    eng.upscale_u8_device(img, 32, 0.5)
+    torch.cuda.synchronize()
+    fam = eng.profile_families()
+    eng.profile_reset(0)
+    ntiles = 3 * 5
+    assert sum(v[0] for v in fam.values()) == 2 * 15 + 6
+    flop = sum(v[2] for v in fam.values())
+    assert abs(flop - ntiles * 32 * 32 * synth.flop_per_lr_pixel(4, 2, 64)) / flop < 1e-9
+    assert all(v[1] > 0 for v in fam.values())
+    eng.close()

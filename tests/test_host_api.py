@@ -246,6 +246,63 @@ def test_np2tensor_tensor2np_colorfix_host():
         np.testing.assert_allclose(U.recompose_tensor(tiles, h, w, step=0.5, scale=s).numpy(), rec[key], atol=1e-6)
 
 
+def test_recompose_tensor_other_steps_and_batches():
+    """CPU recompose_tensor against reference fixtures for step != 0.5, and final_batch_size > 1 (utils.py:412)."""
+    rec = golden("recompose_steps.npz")
+    for key in rec.files:
+        parts = key.split("_")
+        h, w, p, s = (int(v) for v in parts[1:5])
+        step = float(parts[5].replace("p", "."))
+        pp = min(h, w, p)
+        n = len(O.tile_origins(h, pp, step)) * len(O.tile_origins(w, pp, step))
+        tiles = torch.rand(n, 3, s * pp, s * pp, generator=torch.Generator().manual_seed(13))
+        got = U.recompose_tensor(tiles, h, w, step=step, scale=s)
+        np.testing.assert_allclose(got.numpy(), rec[key], atol=1e-6)
+        two = U.recompose_tensor(torch.cat([tiles, tiles.flip(0)], 0), h, w, step=step, scale=s)
+        assert two.shape[0] == 2
+        np.testing.assert_allclose(two[0].numpy(), rec[key][0], atol=1e-6)
+
+
+def test_engine_cache_follows_the_parameters_and_is_not_pickled():
+    """The native engine of a mirror module is keyed on the parameters' storage and version counters and is left
+    out of deep copies / pickles.  No GPU needed: the fingerprint logic is host code."""
+    import copy
+    import pickle
+    net = get_network(get_network_G_config({"type": "esrgan", "nb": 1}, 4))
+    fp0 = net._fingerprint()
+    with torch.no_grad():
+        next(net.parameters()).mul_(1.0)          # in-place edit: version counter moves
+    assert net._fingerprint() != fp0
+    fp1 = net._fingerprint()
+    net.load_state_dict(net.state_dict())
+    assert net._fingerprint() != fp1
+    fp2 = net._fingerprint()
+    net.half()
+    assert net._fingerprint() != fp2
+
+    class FakeEngine:
+        closed = False
+
+        def close(self):
+            self.closed = True
+    fake = FakeEngine()
+    net.__dict__["_engines"] = {("cuda:0", torch.float16): (net._fingerprint(), fake)}
+    clone = copy.deepcopy(net)
+    assert clone.__dict__["_engines"] == {} and not fake.closed
+    again = pickle.loads(pickle.dumps(net))
+    assert again.__dict__["_engines"] == {}
+    assert set(again.state_dict()) == set(net.state_dict())
+    net.invalidate_engine()
+    assert fake.closed and net.__dict__["_engines"] == {}
+
+
+def test_native_chain_needs_cuda_and_three_channel_native_models(tmp_path):
+    """run.native_chain: the fused device loop is only taken for CUDA + chop + 3-channel native models."""
+    torch.save(O.make_state_dict(scale=4, nb=1, seed=6), tmp_path / "4x_a.pth")
+    m = R.Model(str(tmp_path / "4x_a.pth"), "infer", None, device=torch.device("cpu"))
+    assert R.native_chain([m], torch.device("cpu"), True) is None
+
+
 def test_cli_cpu_end_to_end(tmp_path, monkeypatch):
     """python run.py -m jpeg+fatal -cf -cpu on a tiny image (config 3, shrunk)."""
     import cv2

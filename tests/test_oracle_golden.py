@@ -130,6 +130,37 @@ def test_recompose_matches_reference():
         np.testing.assert_allclose(out.numpy(), g[key], rtol=0, atol=1e-6)
 
 
+def _step_key(key):
+    """'..._32_4_0p75' -> (ints..., 0.75)"""
+    parts = key.split("_")
+    return parts[:-1], float(parts[-1].replace("p", "."))
+
+
+def test_recompose_with_other_steps_matches_reference():
+    g = golden("recompose_steps.npz")
+    for key in g.files:
+        head, step = _step_key(key)
+        h, w, p, s = (int(v) for v in head[1:])
+        pp = min(h, w, p)
+        n = len(O.tile_origins(h, pp, step)) * len(O.tile_origins(w, pp, step))
+        tiles = torch.rand(n, 3, s * pp, s * pp, generator=torch.Generator().manual_seed(13))
+        out = O.recompose(tiles, h, w, step=step, scale=s)
+        np.testing.assert_allclose(out.numpy(), g[key], rtol=0, atol=1e-6)
+
+
+def test_chop_forward_with_other_steps_matches_reference():
+    g = golden("chop_steps.npz")
+    for key in [k for k in g.files if k.startswith("y_")]:
+        head, step = _step_key(key[2:].replace("step", ""))
+        scale = int(head[0][1:])
+        h, w = (int(v) for v in head[1].split("x"))
+        patch = int(head[2][1:])
+        sd = O.make_state_dict(scale=scale, nb=int(g["nb"]), seed=int(g["seed"]))
+        img = synth_image(int(g["img_seed"]), h, w)
+        y = O.chop_forward(sd, O.np2tensor(img), patch_size=patch, step=step)
+        np.testing.assert_allclose(y.numpy(), g[key], rtol=0, atol=2e-5)
+
+
 def test_chain_and_color_fix():
     g = golden("chain_1x4x_cf_40x56.npz")
     img = synth_image(int(g["img_seed"]), int(g["h"]), int(g["w"]))

@@ -97,8 +97,41 @@ def pan_fixtures(td):
                             whole=whole.numpy().astype(np.float32))
 
 
+def steps_fixtures(td):
+    # ---- G3b: chop_forward / recompose_tensor with step != 0.5 (Model.chop_forward's own default is 1.0,
+    # run.py:167; recompose_tensor accepts [0.5, 1.0], utils.py:391): overlap, effective stride and the
+    # edge-anchored extra tiles all change with the step
+    out = {}
+    for scale, nb, (h, w), patch, step in ((4, 1, (40, 56), 32, 1.0), (4, 1, (40, 56), 32, 0.75), (2, 1, (50, 70), 32, 0.75),
+                                           (1, 1, (80, 64), 32, 0.625), (2, 1, (44, 36), 20, 0.9), (4, 1, (30, 52), 200, 1.0)):
+        net = ref_net(scale, nb, seed=21)
+        path = os.path.join(td, "%dx_steps.pth" % scale)
+        save_model(net, path)
+        model = ref_run.Model(path, "infer", None, device=torch.device("cpu"), chop=True)
+        img = image(31, h, w)
+        y = model.chop_forward(ref_utils.np2tensor(img), patch_size=patch, step=step)
+        key = "s%d_%dx%d_p%d_step%s" % (scale, h, w, patch, str(step).replace(".", "p"))
+        out["y_" + key] = y.numpy().astype(np.float32)
+        out["u8_" + key] = ref_utils.tensor2np(y.detach())
+    np.savez_compressed(os.path.join(OUT, "chop_steps.npz"), nb=1, seed=21, img_seed=31, **out)
+    rec = {}
+    for (h, w, p, s, step) in ((40, 56, 32, 4, 1.0), (40, 56, 32, 4, 0.75), (50, 70, 32, 2, 0.75), (80, 64, 32, 1, 0.625),
+                               (44, 36, 20, 2, 0.9), (33, 47, 16, 1, 0.95), (130, 90, 200, 1, 0.8)):
+        pp = min(h, w, p)
+        ys, xs = O.tile_origins(h, pp, step), O.tile_origins(w, pp, step)
+        g = torch.Generator().manual_seed(13)
+        tiles = torch.rand(len(ys) * len(xs), 3, s * pp, s * pp, generator=g)
+        rec["out_%d_%d_%d_%d_%s" % (h, w, p, s, str(step).replace(".", "p"))] = \
+            ref_utils.recompose_tensor(tiles, h, w, step=step, scale=s).numpy()
+    np.savez_compressed(os.path.join(OUT, "recompose_steps.npz"), **rec)
+
+
 def main():
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "steps":
+        with tempfile.TemporaryDirectory() as td:
+            steps_fixtures(td)
+        return
     # ---- G1: weights recipe: the oracle's make_state_dict must reproduce the reference init.
     checks = {}
     for scale, nb in ((4, 2), (1, 1), (2, 1), (8, 1), (3, 1)):
@@ -136,6 +169,8 @@ def main():
             np.savez_compressed(os.path.join(OUT, "chop_s%d_nb%d_%dx%d_p%d.npz" % (scale, nb, h, w, patch)),
                                 img_seed=3, h=h, w=w, patch=patch, scale=scale, nb=nb, seed=1,
                                 y=y.numpy().astype(np.float32), u8=ref_utils.tensor2np(y.detach()))
+
+        steps_fixtures(td)
 
         # ---- G4: chain 1x + 4x with -cf (config 3, shrunk): run.py semantics by hand
         n1 = ref_net(1, 1, seed=5)
