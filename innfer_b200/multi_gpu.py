@@ -88,6 +88,14 @@ class NativeTileBackend:
         self.h_out = [torch.empty((self.scale * H, self.scale * W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
         self.h_in = [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
         self._stage_ev = [None, None]   # completion of the last H2D out of each staging slot
+        # Launch both flag kernels once while nothing blocks: with CUDA's lazy module loading the FIRST launch of a
+        # kernel may have to wait for running kernels, and a spinning wait kernel is exactly what must not be waited
+        # for (measured: a signal first launched behind a running wait arrived only after the wait's timeout).
+        scratch = (ctypes.c_void_p * 1)(self.flags_ptr + 4 * 3 * MAX_RANKS)
+        with torch.cuda.device(self.dev):
+            N.check(self.lib.innfer_stream_signal(scratch, 1, 0, ctypes.c_void_p(self.s_up.cuda_stream)))
+            N.check(self.lib.innfer_stream_wait(scratch, 1, 0, None, 1000, ctypes.c_void_p(self.s_up.cuda_stream)))
+            torch.cuda.synchronize(self.dev)
         self._done = {}
         self._nown = 0
 

@@ -780,16 +780,31 @@ def test_stream_flags_signal_wait_and_timeout(native, dev):
     s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     marker = torch.zeros(1, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
+    err = ctypes.c_void_p(flags.data_ptr() + 28)
+    # both kernels once with nothing blocking: with CUDA's lazy module loading the FIRST launch of a kernel can wait
+    # for running kernels to finish, i.e. a signal first launched while a wait spins would arrive only after the
+    # wait's timeout (NativeTileBackend warms both up the same way)
+    scratch = (ctypes.c_void_p * 1)(flags.data_ptr() + 12)
+    native.check(lib.innfer_stream_signal(scratch, 1, 1, ctypes.c_void_p(s2.cuda_stream)))
+    native.check(lib.innfer_stream_wait(scratch, 1, 1, err, 20000, ctypes.c_void_p(s2.cuda_stream)))
+    s2.synchronize()
     arr = (ctypes.c_void_p * 2)(flags.data_ptr(), flags.data_ptr() + 4)
-    native.check(lib.innfer_stream_wait(arr, 2, 5, ctypes.c_void_p(flags.data_ptr() + 28), 20000, ctypes.c_void_p(s1.cuda_stream)))
+    native.check(lib.innfer_stream_wait(arr, 2, 5, err, 20000, ctypes.c_void_p(s1.cuda_stream)))
     with torch.cuda.stream(s1):
         marker.add_(1)
-    assert not s1.query()                 # held by the wait kernel
+    import time
+    time.sleep(0.1)
+    with torch.cuda.stream(s2):
+        seen = marker.clone()
+    s2.synchronize()
+    assert int(seen.item()) == 0          # the add is held behind the wait kernel
     native.check(lib.innfer_stream_signal(arr, 2, 5, ctypes.c_void_p(s2.cuda_stream)))
+    t0 = time.time()
     s1.synchronize()
+    assert time.time() - t0 < 5.0
     assert int(marker.item()) == 1 and flags[:2].tolist() == [5, 5] and int(flags[7].item()) == 0
     arr1 = (ctypes.c_void_p * 1)(flags.data_ptr() + 8)
-    native.check(lib.innfer_stream_wait(arr1, 1, 1, ctypes.c_void_p(flags.data_ptr() + 28), 50, ctypes.c_void_p(s1.cuda_stream)))
+    native.check(lib.innfer_stream_wait(arr1, 1, 1, err, 50, ctypes.c_void_p(s1.cuda_stream)))
     s1.synchronize()
     assert int(flags[7].item()) == 1
 
