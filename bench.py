@@ -76,27 +76,37 @@ class ClockSampler:
         except Exception:
             pass
 
-    def start(self):
-        self.rows = []
+    def start(self, settle=0.0):
+        """Starts sampling; `settle` seconds are slept so that nvidia-smi is up before a short timed region begins
+        (samples are filtered to the [mark_begin(), stop()] window by their arrival time)."""
+        self.rows, self.t_begin = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", self.sel, "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, args=(self.proc,), daemon=True).start()
         except OSError:
             self.proc = None
+        if settle:
+            time.sleep(settle)
+
+    def mark_begin(self):
+        self.t_begin = time.time()
 
     def _read(self, proc):
         for line in proc.stdout:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 6:
-                self.rows.append(parts)
+                self.rows.append(parts + [time.time()])
 
     def stop(self):
+        t_end = time.time()
         if self.proc is not None:
             self.proc.terminate()
             self.proc = None
         rows = list(self.rows)
+        if self.t_begin is not None:
+            rows = [r for r in rows if self.t_begin <= r[-1] <= t_end + 0.05]
         sm = sorted(int(r[0]) for r in rows if r[0].isdigit())
         mx = [int(r[1]) for r in rows if r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -316,7 +326,9 @@ def run_tile_sharded(args, eng, dist, rank, world, dev, warm, single_ms, ref_sha
     dist.barrier()
     torch.cuda.synchronize(dev)
     sampler = ClockSampler(dev.index)
-    sampler.start()
+    sampler.start(settle=0.7)
+    dist.barrier()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for s in (be.s_up, be.s_bl):
         s.wait_stream(be.s_cmp)

@@ -1,6 +1,7 @@
-"""get_network -- mirror of the reference's architectures/__init__.py:5-40 for the hot path."""
+"""get_network -- mirror of the reference's architectures/__init__.py:5-40 (ESRGAN, SRResNet, PPON, PAN, pix2pix UNet
+and CycleGAN ResNet generators; MRRDBNet checkpoints are converted to RRDBNet by run.Model, WBC is out of scope)."""
 
-_OUT_OF_SCOPE = ("mrrdb_net", "unet_net", "resnet_net", "wbcunet_net")
+_OUT_OF_SCOPE = ("mrrdb_net", "wbcunet_net")
 
 
 def get_network(opt_net):
@@ -18,6 +19,12 @@ def get_network(opt_net):
     if kind == "pan_net":
         from . import PAN_arch
         return PAN_arch.PAN(**opt_net)
+    if kind == "unet_net":
+        from . import UNet_arch
+        return UNet_arch.UnetGenerator(**opt_net)
+    if kind == "resnet_net":
+        from . import ResNet_arch
+        return ResNet_arch.ResnetGenerator(**opt_net)
     if kind in _OUT_OF_SCOPE:
         raise NotImplementedError(
             "Model [%s] exists in the reference but is outside the B200 RRDB hot-path scope "

@@ -17,8 +17,13 @@ class NativeEngineMixin:
 
     _engine_class = "RRDBEngine"
 
+    def _engine_key_extra(self):
+        """Module state other than the parameters that the engine bakes in (e.g. train/eval mode of norm layers)."""
+        return ()
+
     def _fingerprint(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        fp = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return fp + tuple((b.data_ptr(), b._version) for b in self.buffers()) + tuple(self._engine_key_extra())
 
     def _engine(self, device, dtype):
         from .. import engine as E

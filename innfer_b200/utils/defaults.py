@@ -1,10 +1,9 @@
 """Network config defaults -- mirror of the reference's utils/defaults.py:3-89 for the ESRGAN,
-SRResNet, PPON and PAN families (the others are outside the hot-path scope and raise NotImplementedError)."""
+SRResNet, PPON, PAN, pix2pix UNet and CycleGAN ResNet families (the others raise NotImplementedError)."""
 
 _RRDB_ALIASES = ("rrdb_net", "esrgan", "esrgan-lite")
 _SRRESNET_ALIASES = ("sr_resnet", "srresnet", "srgan")
-_OTHER_KINDS = ("evsrgan", "mrrdb_net", "mesrgan",
-                "unet_net", "unet", "resnet_net", "resnet", "wbcunet", "wbcunet_net")
+_OTHER_KINDS = ("evsrgan", "mrrdb_net", "mesrgan", "wbcunet", "wbcunet_net")
 
 
 def get_network_G_config(network_G, scale):
@@ -80,7 +79,34 @@ def get_network_G_config(network_G, scale):
             "double_scpa": opts.pop("double_scpa", False),
             "ups_inter_mode": opts.pop("ups_inter_mode", "nearest"),
         }
-    if kind in _OTHER_KINDS or kind.startswith(("unet_", "p2p_", "resnet_", "cg_")):
+    if kind not in _OTHER_KINDS and "wbcunet" not in kind and ("unet" in kind or "p2p" in kind):
+        # pix2pix UNet (defaults.py:90-112)
+        downs = 7 if kind in ("unet_128", "p2p_128") else 8
+        return {
+            "type": "unet_net",
+            "input_nc": opts.pop("in_nc", 3),
+            "output_nc": opts.pop("out_nc", 3),
+            "num_downs": opts.pop("num_downs", downs),
+            "ngf": opts.pop("ngf", 64),
+            "norm_type": opts.pop("norm_type", "batch"),
+            "use_dropout": opts.pop("use_dropout", False),
+            "upsample_mode": opts.pop("upsample_mode", "deconv"),
+        }
+    if kind not in _OTHER_KINDS and (("resnet" in kind and kind != "sr_resnet") or "cg" in kind):
+        # CycleGAN ResNet (defaults.py:113-131)
+        blocks = 6 if kind in ("resnet_6blocks", "resnet_6", "cg_6") else 9
+        return {
+            "type": "resnet_net",
+            "input_nc": opts.pop("in_nc", 3),
+            "output_nc": opts.pop("out_nc", 3),
+            "n_blocks": opts.pop("n_blocks", blocks),
+            "ngf": opts.pop("ngf", 64),
+            "norm_type": opts.pop("norm_type", "instance"),
+            "use_dropout": opts.pop("use_dropout", False),
+            "upsample_mode": opts.pop("upsample_mode", "deconv"),
+            "padding_type": opts.pop("padding_type", "reflect"),
+        }
+    if kind in _OTHER_KINDS or "wbcunet" in kind:
         raise NotImplementedError(
             "generator [%s] exists in the reference but is outside the B200 RRDB hot-path scope" % kind)
     raise NotImplementedError("Generator model [%s] not recognized" % kind)

@@ -105,3 +105,91 @@ def norm_range(x):
 def denorm_range(x):
     """utils.denorm (utils.py:136-150): [-1, 1] -> [0, 1], clamped."""
     return ((x + 1.0) / 2.0).clamp(0, 1)
+
+
+# ----------------------------------------------------------------------------- seeded weights
+def make_unet_state_dict(num_downs=8, ngf=64, in_nc=3, out_nc=3, norm="batch", seed=0):
+    """The state dict UnetGenerator(...) has after torch.manual_seed(seed): torch's default initialisation of the
+    convs drawn in the reference's construction order (innermost level first, down conv before transposed conv,
+    UNet_arch.py:47-66,108-116).  BatchNorm: weight 1, bias 0, running stats 0 / 1."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    bias = norm == "instance"
+    chans = [(ngf * 8, ngf * 8)] * (num_downs - 4) + [(ngf * 4, ngf * 8), (ngf * 2, ngf * 4), (ngf, ngf * 2), (out_nc, ngf)]
+    built = []                        # innermost first: (outer_nc, inner_nc, down, up)
+    for idx, (outer, inner) in enumerate(chans):
+        innermost, outermost = idx == 0, idx == len(chans) - 1
+        down = nn.Conv2d(in_nc if outermost else outer, inner, 4, 2, 1, bias=bias)
+        up = nn.ConvTranspose2d(inner if innermost else inner * 2, outer, 4, 2, 1, bias=True if outermost else bias)
+        built.append((outer, inner, down, up))
+    sd = {}
+    levels = unet_keys(num_downs)
+    for depth, L in enumerate(levels):
+        outer, inner, down, up = built[len(built) - 1 - depth]
+        for name, mod in ((L["down"], down), (L["up"], up)):
+            sd[name + ".weight"] = mod.weight.detach().clone()
+            if mod.bias is not None:
+                sd[name + ".bias"] = mod.bias.detach().clone()
+        if norm == "batch":
+            for name, c in ((L["dnorm"], inner), (L["unorm"], outer)):
+                if name:
+                    sd[name + ".weight"], sd[name + ".bias"] = torch.ones(c), torch.zeros(c)
+                    sd[name + ".running_mean"], sd[name + ".running_var"] = torch.zeros(c), torch.ones(c)
+                    sd[name + ".num_batches_tracked"] = torch.tensor(0)
+    return sd
+
+
+def make_resnet_state_dict(n_blocks=9, ngf=64, in_nc=3, out_nc=3, norm="instance", seed=0):
+    """Same for ResnetGenerator (ResNet_arch.py:55-91): modules are created front to back."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    bias = norm == "instance"
+    sd = {}
+
+    def put(name, mod):
+        sd[name + ".weight"] = mod.weight.detach().clone()
+        if mod.bias is not None:
+            sd[name + ".bias"] = mod.bias.detach().clone()
+
+    def put_norm(name, c):
+        if norm == "batch":
+            sd[name + ".weight"], sd[name + ".bias"] = torch.ones(c), torch.zeros(c)
+            sd[name + ".running_mean"], sd[name + ".running_var"] = torch.zeros(c), torch.ones(c)
+            sd[name + ".num_batches_tracked"] = torch.tensor(0)
+
+    put("model.1", nn.Conv2d(in_nc, ngf, 7, bias=bias))
+    put_norm("model.2", ngf)
+    ch = ngf
+    for i in (4, 7):
+        put("model.%d" % i, nn.Conv2d(ch, ch * 2, 3, 2, 1, bias=bias))
+        put_norm("model.%d" % (i + 1), ch * 2)
+        ch *= 2
+    for b in range(n_blocks):
+        p = "model.%d.conv_block" % (10 + b)
+        for j in (1, 5):
+            put("%s.%d" % (p, j), nn.Conv2d(ch, ch, 3, bias=bias))
+            put_norm("%s.%d" % (p, j + 1), ch)
+    i = 10 + n_blocks
+    for _ in range(2):
+        put("model.%d" % i, nn.ConvTranspose2d(ch, ch // 2, 3, 2, 1, output_padding=1, bias=bias))
+        put_norm("model.%d" % (i + 1), ch // 2)
+        ch //= 2
+        i += 3
+    put("model.%d" % (i + 1), nn.Conv2d(ngf, out_nc, 7))
+    return sd
+
+
+def randomize_norms(sd, seed):
+    """Make the norm layers visible to a parity test: affine weights U(0.5, 1.5), biases U(-0.3, 0.3), running means
+    N(0, 0.2), running variances U(0.5, 1.5), drawn in key order from a private generator.  In place; returns sd."""
+    g = torch.Generator().manual_seed(seed)
+    for key in list(sd):
+        if not key.endswith(".running_mean"):
+            continue
+        base = key[:-len(".running_mean")]
+        c = sd[key].numel()
+        sd[base + ".weight"].copy_(torch.rand(c, generator=g) + 0.5)
+        sd[base + ".bias"].copy_(torch.rand(c, generator=g) * 0.6 - 0.3)
+        sd[base + ".running_mean"].copy_(torch.randn(c, generator=g) * 0.2)
+        sd[base + ".running_var"].copy_(torch.rand(c, generator=g) + 0.5)
+    return sd
