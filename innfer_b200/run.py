@@ -13,8 +13,8 @@ import torch
 
 from .architectures import get_network
 from .utils.defaults import get_network_G_config
-from .utils.utils import (color_fix, color_fix_device, extract_patches_2d, get_images_paths, get_models_paths, mod2normal, np2tensor,
-                          read_img, recompose_tensor, save_img, save_img_comp, swa2normal, tensor2np)
+from .utils.utils import (color_fix, color_fix_device, extract_patches_2d, get_images_paths, get_models_paths,
+                          linear_resize, mod2normal, np2tensor, read_img, recompose_tensor, save_img, save_img_comp, swa2normal, tensor2np)
 
 # key that identifies each architecture family, probed in the reference's order (run.py:50-72)
 _ARCH_PROBES = (
@@ -181,6 +181,10 @@ def get_scale_name(model_path, scale=None):
 
 
 default_extras = {"meval": True, "strict": True, "normalize": False}
+# run.py:299-309 of the reference: pix2pix keeps its norm layers in training mode and, like cyclegan, works on images
+# normalised to [-1, 1]; cyclegan loads non-strictly (running statistics saved by PyTorch < 0.4 InstanceNorm layers)
+pix2pix_extras = {"meval": False, "strict": True, "normalize": True}
+cyclegan_extras = {"meval": True, "strict": False, "normalize": True}
 
 
 # ---------------------------------------------------------------------- fused device path of the CLI loop
@@ -261,14 +265,17 @@ def main(argv=None):
     args = build_parser().parse_args(argv)
     gpu = args.no_gpu                      # store_false flags: True means "use the GPU"
     fp16 = False if args.arch == "ts" else (args.no_fp16 and gpu)
-    for marker in ("unet_", "p2p_", "resnet_", "cg_", "wbc"):
-        if marker in args.arch or (marker == "wbc" and marker in args.models):
-            raise NotImplementedError(
-                "architecture family '%s' exists in the reference but is outside the B200 RRDB hot-path scope"
-                % marker)
-    meval, strict = default_extras["meval"], default_extras["strict"]
-    normalize = default_extras["normalize"] or args.norm
-    chop = True
+    if "wbc" in args.arch or "wbc" in args.models:
+        raise NotImplementedError("the WBC (white-box cartoonisation) family exists in the reference but is outside the "
+                                  "scope of this engine (SURVEY.md section 8f)")
+    extras, chop, resize = default_extras, True, False
+    if "unet_" in args.arch or "p2p_" in args.arch:          # run.py:347-356
+        extras, chop = pix2pix_extras, False
+        resize = next((n for n in (512, 256, 128) if str(n) in args.arch), False)
+    elif "resnet_" in args.arch or "cg_" in args.arch:       # run.py:357-360
+        extras = cyclegan_extras
+    meval, strict = extras["meval"], extras["strict"]
+    normalize = extras["normalize"] or args.norm
 
     if gpu:
         if not torch.cuda.is_available():
@@ -294,6 +301,8 @@ def main(argv=None):
         if img is None:
             print(f"Error reading image {image_path}, skipping.")
             continue
+        if resize:
+            img = linear_resize(img, resize)
         if runner is not None and img.dtype == "uint8" and img.ndim == 3 and img.shape[2] == 3:
             # 3-channel uint8 image through 3-channel native models: the whole loop body below as one device pipeline
             img_out = runner(img).copy()

@@ -145,6 +145,16 @@ def modcrop(img_in, scale):
     return img[:h - h % scale, :w - w % scale]
 
 
+def linear_resize(img, st=256):
+    """Resize (bicubic, in linear light) up to the next multiple of ``st`` in both dimensions, as run.py does for the
+    pix2pix UNets whose depth fixes the input granularity (utils.py:267-275 of the reference)."""
+    h, w = img.shape[0:2]
+    if h % st or w % st:
+        oh, ow = -(-h // st) * st, -(-w // st) * st
+        img = linear2srgb(cv2.resize(srgb2linear(img), dsize=(ow, oh), interpolation=cv2.INTER_CUBIC))
+    return img
+
+
 # ------------------------------------------------------------------------------------ colour fix
 def color_fix(imgA, imgB, device=None):
     """Add the low-frequency difference (LR - downscaled SR) back to SR in linear light.

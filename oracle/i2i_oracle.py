@@ -181,9 +181,9 @@ def make_resnet_state_dict(n_blocks=9, ngf=64, in_nc=3, out_nc=3, norm="instance
 
 def randomize_norms(sd, seed):
     """Make the norm layers visible to a parity test: affine weights U(0.5, 1.5), biases U(-0.3, 0.3), running means
-    N(0, 0.2), running variances U(0.5, 1.5), drawn in key order from a private generator.  In place; returns sd."""
+    N(0, 0.2), running variances U(0.5, 1.5), drawn in SORTED key order from a private generator.  In place; returns sd."""
     g = torch.Generator().manual_seed(seed)
-    for key in list(sd):
+    for key in sorted(sd):
         if not key.endswith(".running_mean"):
             continue
         base = key[:-len(".running_mean")]

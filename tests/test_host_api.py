@@ -215,9 +215,9 @@ def test_synth_recipe_matches_reference_init():
 
 def test_unknown_architectures_fail_loudly():
     with pytest.raises(NotImplementedError):
-        get_network({"type": "unet_net"})
+        get_network({"type": "wbcunet_net"})
     with pytest.raises(NotImplementedError):
-        get_network_G_config({"type": "unet_256"}, 1)
+        get_network({"type": "mrrdb_net"})
     with pytest.raises(Exception, match="Could not infer"):
         m = R.Model.__new__(R.Model)
         m.__dict__.update(model_path="x", arch="infer", scale=None, in_nc=3, out_nc=3, device="cpu", eval=True,
@@ -319,7 +319,7 @@ def test_cli_cpu_end_to_end(tmp_path, monkeypatch):
     d = np.abs(out.astype(int) - g["cf"].astype(int))
     assert d.max() <= 1 and (d > 0).mean() < 0.01
     with pytest.raises(NotImplementedError):
-        R.main(["-m", "jpeg", "-a", "unet_256", "-cpu"])
+        R.main(["-m", "jpeg", "-a", "wbcunet", "-cpu"])
 
 
 def test_cuda_request_never_falls_back(tmp_path, monkeypatch):

@@ -126,8 +126,64 @@ def steps_fixtures(td):
     np.savez_compressed(os.path.join(OUT, "recompose_steps.npz"), **rec)
 
 
+def i2i_fixtures(td):
+    """G8: pix2pix UNet / CycleGAN ResNet generators (BASELINE configs[4]) through the reference's
+    get_network and run.Model with the extras run.py applies to these families (run.py:295-361)."""
+    from oracle import i2i_oracle as I
+    out = {}
+    # -- raw module forwards on small configurations: train-mode BatchNorm (pix2pix runs with meval False), eval-mode
+    #    BatchNorm, InstanceNorm UNet, batch of two; inputs in [-1, 1]
+    for tag, kw, seed, shape, train in (("unet_d5_bn_train", {"type": "unet_256", "num_downs": 5, "ngf": 8}, 41, (2, 3, 32, 64), True),
+                                        ("unet_d6_bn_eval", {"type": "unet_256", "num_downs": 6, "ngf": 8}, 42, (1, 3, 64, 128), False),
+                                        ("unet_d5_in", {"type": "unet_128", "num_downs": 5, "ngf": 16, "norm_type": "instance"}, 43, (1, 3, 64, 96), True),
+                                        ("resnet_b2_in", {"type": "resnet_9blocks", "n_blocks": 2, "ngf": 16}, 44, (2, 3, 40, 52), False),
+                                        ("resnet_b1_bn_eval", {"type": "resnet_6blocks", "n_blocks": 1, "ngf": 8, "norm_type": "batch"}, 45, (1, 3, 36, 28), False),
+                                        ("resnet_b1_bn_train", {"type": "resnet_6blocks", "n_blocks": 1, "ngf": 8, "norm_type": "batch"}, 46, (2, 3, 24, 32), True)):
+        torch.manual_seed(seed)
+        net = get_network(get_network_G_config(dict(kw), 1))
+        I.randomize_norms(net.state_dict(), seed + 100)
+        net.train(train)
+        x = torch.rand(*shape, generator=torch.Generator().manual_seed(seed)) * 2 - 1
+        with torch.no_grad():
+            y = net(x.clone())
+        out["y_" + tag] = y.numpy().astype(np.float32)
+        out["wsum_" + tag] = np.array([float(v.double().sum()) for k, v in sorted(net.state_dict().items())
+                                       if "num_batches" not in k and "running" not in k])
+    # -- full-size networks through run.Model as `run.py -a unet_256` / `-a resnet_9blocks -norm` would drive them
+    torch.manual_seed(51)
+    net = get_network(get_network_G_config({"type": "unet_256"}, 1))
+    I.randomize_norms(net.state_dict(), 151)
+    path = os.path.join(td, "1x_p2p.pth")
+    save_model(net, path)
+    model = ref_run.Model(path, "unet_256", None, device=torch.device("cpu"), meval=False, strict=True, chop=False)
+    img = ref_utils.linear_resize(image(52, 200, 256), 256)          # run.py:412-413
+    out["resized_unet256"] = img
+    t = ref_utils.np2tensor(img, normalize=True)
+    y = model(t.clone())
+    out["y_unet256"] = y.detach().numpy().astype(np.float32)
+    out["u8_unet256"] = ref_utils.tensor2np(y.detach(), denormalize=True)
+
+    torch.manual_seed(53)
+    net = get_network(get_network_G_config({"type": "resnet_9blocks"}, 1))
+    path = os.path.join(td, "1x_cg.pth")
+    save_model(net, path)
+    model = ref_run.Model(path, "resnet_9blocks", None, device=torch.device("cpu"), meval=True, strict=False, chop=True)
+    img = image(54, 64, 96)
+    t = ref_utils.np2tensor(img, normalize=True)
+    y = model.chop_forward(t.clone(), patch_size=32, step=0.5)        # 3 x 5 tiles of 32 px
+    out["y_resnet9_chop32"] = y.detach().numpy().astype(np.float32)
+    out["u8_resnet9_chop32"] = ref_utils.tensor2np(y.detach(), denormalize=True)
+    y = model(t.clone())                                              # __call__: one 64-px tile
+    out["y_resnet9_call"] = y.detach().numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "i2i.npz"), **out)
+
+
 def main():
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "i2i":
+        with tempfile.TemporaryDirectory() as td:
+            i2i_fixtures(td)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "steps":
         with tempfile.TemporaryDirectory() as td:
             steps_fixtures(td)
@@ -171,6 +227,7 @@ def main():
                                 y=y.numpy().astype(np.float32), u8=ref_utils.tensor2np(y.detach()))
 
         steps_fixtures(td)
+        i2i_fixtures(td)
 
         # ---- G4: chain 1x + 4x with -cf (config 3, shrunk): run.py semantics by hand
         n1 = ref_net(1, 1, seed=5)
