@@ -91,6 +91,22 @@ typedef struct innfer_pan_cfg {
   int32_t fp16;
 } innfer_pan_cfg;
 
+/* Constructor kwargs of UnetGenerator (architectures/UNet_arch.py:21-22) / ResnetGenerator
+ * (architectures/ResNet_arch.py:20-22) as produced by get_network_G_config (utils/defaults.py:99-135), plus the one piece
+ * of module state that changes the arithmetic: run.py:297 keeps pix2pix in training mode (meval False), where
+ * BatchNorm2d normalises with the statistics of the batch.  upsample_mode 'deconv', padding 'reflect', no dropout.
+ * SURVEY.md 8(f) rank 4. */
+typedef struct innfer_i2i_cfg {
+  int32_t kind;   /* 0: UnetGenerator (pix2pix), 1: ResnetGenerator (CycleGAN) */
+  int32_t in_nc;
+  int32_t out_nc;
+  int32_t ngf;    /* multiple of 8 */
+  int32_t depth;  /* num_downs (5..12) or n_blocks */
+  int32_t norm;   /* 0: BatchNorm2d, 1: InstanceNorm2d (then the convolutions carry a bias) */
+  int32_t train;  /* BatchNorm2d: 1 = batch statistics (module.training), 0 = running statistics */
+  int32_t fp16;
+} innfer_i2i_cfg;
+
 typedef struct innfer_tile {
   int32_t y0, x0; /* low-res origin of the tile */
 } innfer_tile;
@@ -117,6 +133,12 @@ int innfer_ppon_create(const innfer_ppon_cfg* cfg, int device, innfer_rrdb** out
  * "conv_last"; with several upsampling stages the reference drops the LeakyReLU after HRconv (block.py:204-207
  * flattens through children(), which yields the shared activation instance once) and so does this path. */
 int innfer_pan_create(const innfer_pan_cfg* cfg, int device, innfer_rrdb** out);
+/* pix2pix UNet / CycleGAN ResNet generator handle (scale 1; the same calls as above work on it).  Keys: UNet
+ * "model.model.0", "model.model.1.model.{1,2,3.model...,5,6}", ..., "model.model.3"; ResNet "model.1|2", "model.4|5",
+ * "model.7|8", "model.<10+b>.conv_block.{1,2,5,6}", "model.<10+nb>|<11+nb>", "model.<13+nb>|<14+nb>", "model.<17+nb>".
+ * innfer_rrdb_forward treats its batch as ONE reference call (train-mode BatchNorm statistics over the batch);
+ * chop_forward treats every tile as its own call, as run.py:187-197 does. */
+int innfer_i2i_create(const innfer_i2i_cfg* cfg, int device, innfer_rrdb** out);
 /* one state-dict entry under its REFERENCE key name ("model.0.weight",
  * "model.1.sub.3.RDB2.conv4.0.bias", "model.1.sub.23.weight", "model.10.bias", ...); host fp32. */
 int innfer_rrdb_load(innfer_rrdb* h, const char* key, const float* host_data, const int64_t* shape,
@@ -245,6 +267,18 @@ int innfer_blend_f32(const float* tiles, int H, int W, int patch_size, double st
 int innfer_conv3x3(const void* x, int n, int Cin, int hgt, int wid, const float* w_oihw,
                    const float* bias, int Cout, int up, int lrelu, const void* res1, float alpha1,
                    void* y, int dtype, int use_fp32_kernel, void* stream);
+
+/* one layer of the image-to-image generators on NCHW device tensors, through the same kernels as the networks
+ * (csrc/i2i.cu): nn.Conv2d / nn.ConvTranspose2d (UNet_arch.py:108-137, ResNet_arch.py:52-88) with kernel k, stride 1|2,
+ * zero or reflection padding (ReflectionPad2d(pad) in front of an unpadded conv), optional bias; then optionally
+ * norm: 1 InstanceNorm2d, 2 BatchNorm2d with batch statistics (affine norm_weight / norm_bias, null = 1 / 0); then
+ * act: 0 none, 1 ReLU, 2 LeakyReLU(0.2), 3 tanh.  final_path 1 runs bias + act in the conv epilogue (the route of a
+ * network's last layer), 0 through the fp32 scratch + normalisation kernels.  w is host fp32 OIHW (IOHW for transposed),
+ * x [n][Cin][h][w], y [n][Cout][h'][w'] device tensors of `dtype` (F16: tcgen05 kernel, F32: direct kernel).
+ * Synchronises the stream -- a test/bring-up entry point, not a hot path. */
+int innfer_gen_conv(const void* x, int n, int Cin, int hgt, int wid, const float* w, const float* bias, int Cout, int k,
+                    int stride, int pad, int transposed, int out_pad, int reflect, int norm, const float* norm_weight,
+                    const float* norm_bias, int act, int final_path, void* y, int dtype, void* stream);
 
 /* ---- -cf colour correction: replaces color_fix (utils/utils.py:278-315) with srgb2linear /
  *      linear2srgb (utils/colors.py:29-60), cv2.resize(INTER_CUBIC) and cv2.GaussianBlur((3,3),0).

@@ -41,6 +41,10 @@ class PANCfg(ctypes.Structure):
                 ("in_nc", "out_nc", "nf", "unf", "nb", "scale", "self_attention", "double_scpa", "fp16")]
 
 
+class I2ICfg(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("kind", "in_nc", "out_nc", "ngf", "depth", "norm", "train", "fp16")]
+
+
 class Tile(ctypes.Structure):
     _fields_ = [("y0", ctypes.c_int32), ("x0", ctypes.c_int32)]
 
@@ -57,6 +61,7 @@ _PROTOS = {
     "innfer_srresnet_create": (_i, [ctypes.POINTER(SRResNetCfg), _i, ctypes.POINTER(_vp)]),
     "innfer_ppon_create": (_i, [ctypes.POINTER(PPONCfg), _i, ctypes.POINTER(_vp)]),
     "innfer_pan_create": (_i, [ctypes.POINTER(PANCfg), _i, ctypes.POINTER(_vp)]),
+    "innfer_i2i_create": (_i, [ctypes.POINTER(I2ICfg), _i, ctypes.POINTER(_vp)]),
     "innfer_rrdb_load": (_i, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(ctypes.c_int64), _i]),
     "innfer_rrdb_finalize": (_i, [_vp]),
     "innfer_rrdb_destroy": (None, [_vp]),
@@ -92,6 +97,7 @@ _PROTOS = {
     "innfer_image_to_tiles": (_i, [_vp, _i, _i, _i, _i, _i, _d, _vp, _vp]),
     "innfer_blend": (_i, [_vp, _i, _i, _i, _d, _i, _i, _vp, _i, _vp]),
     "innfer_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _f, _vp, _i, _i, _vp]),
+    "innfer_gen_conv": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp]),
     "innfer_color_fix": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp]),
     "innfer_color_fix_host": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i]),
 }

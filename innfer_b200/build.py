@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libinnfer_b200.so"
 SOURCES = ["sync_ops.cu", "conv_tc.cu", "conv_rows.cu", "conv_up.cu", "tmap.cu", "layers.cu", "pixel_ops.cu", "conv_direct.cu", "color_fix.cu", "pan_ops.cu",
-           "engine.cu"]
+           "i2i.cu", "engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -13,6 +13,7 @@
 #include "../../include/innfer_b200.h"
 #include "color_fix.cuh"
 #include "conv_direct.cuh"
+#include "i2i.cuh"
 #include "layers.cuh"
 #include "pan_ops.cuh"
 #include "pixel_ops.cuh"
@@ -73,7 +74,11 @@ PixelDType to_pix(int dtype) { return dtype == INNFER_F16 ? kF16 : (dtype == INN
 
 struct innfer_rrdb {
   innfer_rrdb_cfg cfg;
-  int arch = 0;            // 0: RRDBNet (ESRGAN), 1: SRResNet (SRGAN generator), 2: PPON, 3: PAN
+  int arch = 0;            // 0: RRDBNet (ESRGAN), 1: SRResNet (SRGAN generator), 2: PPON, 3: PAN, 4: pix2pix UNet / CycleGAN ResNet
+  // image-to-image generators (arch 4): the whole network lives in csrc/i2i.cu
+  I2ICfg i2i_cfg;
+  std::unique_ptr<I2INet> i2i;
+  bool i2i_per_sample = false;   // the batch is a list of tiles the reference would run one by one (chop_forward)
   float res_scale = 1.f;   // SRResNet residual scaling
   bool ps_mode = true;     // SRResNet upsampler: pixelshuffle (default) or upconv
   int device = 0;
@@ -438,6 +443,7 @@ int ensure_workspace(innfer_rrdb* h, int B, int hgt, int wid) {
   const int s = h->cfg.scale;
   int rc = 0;
   rc |= h->in_tiles.ensure(px * h->in_ct() * e8);
+  if (h->arch == 4) return rc ? fail(INNFER_E_NOMEM, "workspace allocation failed") : 0;   // I2INet sizes its own buffers
   if (h->arch == 3) {
     // PAN: trunk buffers (channels padded to 16), the two SCPA branch pairs, PACnv scratch, HR ping-pong, ILR, attention
     const int nfC = (h->cfg.nf + 15) / 16 * 2, gc = (h->cfg.nf / 2 + 15) / 16 * 2, ufC = (h->pan_unf + 15) / 16 * 2;
@@ -807,7 +813,27 @@ int forward_tiles_pan(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bo
   return run_conv(h, h->hr1, curv, B, ch, cw, dst, (c.out_nc + 7) / 8, last, st);
 }
 
+int i2i_code(int rc) {   // I2INet's codes (i2i.cuh) -> INNFER_E_*
+  switch (rc) {
+    case -1: return INNFER_E_INVALID;
+    case -2: return INNFER_E_UNSUPPORTED;
+    case -3: return INNFER_E_CUDA;
+    case -4: return INNFER_E_STATE;
+    default: return INNFER_E_NOMEM;
+  }
+}
+
+int forward_tiles_i2i(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool compact, cudaStream_t st) {
+  std::string err;
+  const uint64_t l0 = h->i2i->launches();
+  const int rc = h->i2i->forward(h->in_tiles.p, h->in_ct(), B, hgt, wid, GenView{dst.base, dst.CT, dst.chunk0}, compact,
+                                 h->i2i_per_sample, st, err);
+  g_launches.fetch_add(h->i2i->launches() - l0, std::memory_order_relaxed);
+  return rc ? fail(i2i_code(rc), err) : 0;
+}
+
 int forward_tiles_impl(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bool compact, cudaStream_t st) {
+  if (h->arch == 4) return forward_tiles_i2i(h, B, hgt, wid, dst, compact, st);
   if (h->arch == 3) return forward_tiles_pan(h, B, hgt, wid, dst, compact, st);
   if (h->arch == 1) return forward_tiles_srresnet(h, B, hgt, wid, dst, compact, st);
   if (h->arch == 2) return forward_tiles_ppon(h, B, hgt, wid, dst, compact, st);
@@ -929,6 +955,7 @@ int compute_tiles(innfer_rrdb* h, const void* src, PixelDType st, const TilePlan
   const int p = plan.p, s = h->cfg.scale;
   const int n = t_end - t_begin;
   if (n <= 0) return 0;
+  h->i2i_per_sample = true;   // the reference runs the tiles one by one (run.py:187-197)
   int B = pick_batch(h, n, p);
   int rc;
   // Workspace grows with the batch (about 215 MB per 200x200 tile at 4x): when the device cannot
@@ -1086,6 +1113,31 @@ int innfer_pan_create(const innfer_pan_cfg* cfg, int device, innfer_rrdb** out) 
   return 0;
 }
 
+int innfer_i2i_create(const innfer_i2i_cfg* cfg, int device, innfer_rrdb** out) {
+  if (!cfg || !out) return fail(INNFER_E_INVALID, "null argument");
+  if (cfg->kind != 0 && cfg->kind != 1) return fail(INNFER_E_INVALID, "kind must be 0 (UnetGenerator) or 1 (ResnetGenerator)");
+  if (cfg->norm != 0 && cfg->norm != 1) return fail(INNFER_E_INVALID, "norm must be 0 (batch) or 1 (instance)");
+  if (cfg->ngf < 8 || cfg->ngf % 8) return fail(INNFER_E_UNSUPPORTED, "ngf must be a multiple of 8");
+  if (cfg->kind == 0 && (cfg->depth < 5 || cfg->depth > 12)) return fail(INNFER_E_UNSUPPORTED, "num_downs must be in [5, 12]");
+  if (cfg->kind == 1 && (cfg->depth < 0 || cfg->depth > 64)) return fail(INNFER_E_UNSUPPORTED, "n_blocks must be in [0, 64]");
+  innfer_rrdb_cfg base = {cfg->in_nc, cfg->out_nc, 64, 1, 32, 1, 0, cfg->fp16};
+  int rc = innfer_rrdb_create(&base, device, out);
+  if (rc) return rc;
+  innfer_rrdb* h = *out;
+  h->arch = 4;
+  h->cfg.nf = cfg->ngf;
+  h->cfg.nb = cfg->depth;
+  h->i2i_cfg.kind = cfg->kind;
+  h->i2i_cfg.in_nc = cfg->in_nc;
+  h->i2i_cfg.out_nc = cfg->out_nc;
+  h->i2i_cfg.ngf = cfg->ngf;
+  h->i2i_cfg.depth = cfg->depth;
+  h->i2i_cfg.norm = cfg->norm;
+  h->i2i_cfg.train = cfg->train != 0;
+  h->i2i_cfg.fp16 = cfg->fp16 != 0;
+  return 0;
+}
+
 int innfer_rrdb_load(innfer_rrdb* h, const char* key, const float* host_data, const int64_t* shape, int ndim) {
   if (!h || !key || !host_data || !shape || ndim < 1 || ndim > 4) return fail(INNFER_E_INVALID, "bad argument");
   if (h->finalized) return fail(INNFER_E_STATE, "handle already finalized");
@@ -1108,6 +1160,27 @@ int innfer_rrdb_finalize(innfer_rrdb* h) {
   const auto& c = h->cfg;
   size_t expected = 0;
   if (h->arch == 3) return finalize_pan(h);
+  if (h->arch == 4) {
+    // keys of UnetGenerator / ResnetGenerator (UNet_arch.py:120-158, ResNet_arch.py:55-91); entries the network does not
+    // use (InstanceNorm running statistics of old checkpoints, num_batches_tracked) are the host's strict / non-strict
+    // business (run.py:299-309) and are ignored here
+    h->i2i.reset(new I2INet(h->i2i_cfg, h->num_sms));
+    std::string err;
+    size_t consumed = 0;
+    auto get = [h](const std::string& key, std::vector<int64_t>& shape) -> const float* {
+      auto it = h->params.find(key);
+      if (it == h->params.end()) return nullptr;
+      shape = it->second.shape;
+      return it->second.data.data();
+    };
+    if ((rc = h->i2i->build(get, err, &consumed))) {
+      h->i2i.reset();
+      return fail(i2i_code(rc), err);
+    }
+    h->params.clear();
+    h->finalized = true;
+    return 0;
+  }
   if (h->arch == 2) {
     // PPON keys (PPON_arch.py:24-63 through block.sequential's flattening)
     if ((rc = build_layer(h, h->fea, "CFEM.0", c.nf, c.in_nc, 1))) return rc;
@@ -1313,6 +1386,9 @@ int innfer_rrdb_forward(innfer_rrdb* h, const void* x, int n, int hgt, int wid, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int s = h->cfg.scale;
   const int oct = (h->cfg.out_nc + 7) / 8;
+  h->i2i_per_sample = false;   // one reference call on the whole batch: train-mode BatchNorm sees all of it
+  if (h->arch == 4 && n > h->max_batch && h->i2i_cfg.norm == 0 && h->i2i_cfg.train)
+    return fail(INNFER_E_UNSUPPORTED, "batch statistics need the whole batch in one pass: raise max_batch");
   // batch images one at a time through max_batch-sized groups
   for (int b0 = 0; b0 < n; b0 += h->max_batch) {
     const int nb = (n - b0) < h->max_batch ? (n - b0) : h->max_batch;
@@ -1649,6 +1725,84 @@ int innfer_conv3x3(const void* x, int n, int Cin, int hgt, int wid, const float*
 // Debugging / measurement aid: `iters` back-to-back launches of ONE 3x3 conv (Cin -> Cout, + LeakyReLU,
 // optional residual) on a wide batch of B images of H x W random pixels, timed with CUDA events after
 // `warm` untimed launches.  Long runs show the kernel's power-limited steady state.
+int innfer_gen_conv(const void* x, int n, int Cin, int hgt, int wid, const float* w, const float* bias, int Cout, int k,
+                    int stride, int pad, int transposed, int out_pad, int reflect, int norm, const float* norm_weight,
+                    const float* norm_bias, int act, int final_path, void* y, int dtype, void* stream) {
+  if (!x || !w || !y) return fail(INNFER_E_INVALID, "null argument");
+  if (dtype != INNFER_F16 && dtype != INNFER_F32) return fail(INNFER_E_INVALID, "dtype must be F16 or F32");
+  if (n < 1 || Cin < 1 || Cout < 1 || hgt < 1 || wid < 1 || norm < 0 || norm > 2 || act < 0 || act > 3)
+    return fail(INNFER_E_INVALID, "bad argument");
+  if (norm && final_path) return fail(INNFER_E_INVALID, "the last-layer path has no norm");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(INNFER_E_UNSUPPORTED, "device is not compute capability 10.x");
+  I2ICfg c;
+  c.kind = 2;
+  c.in_nc = Cin;
+  c.out_nc = Cout;
+  c.norm = norm == 1 ? 1 : 0;
+  c.train = 1;
+  c.fp16 = dtype == INNFER_F16;
+  c.sl_cout = Cout; c.sl_k = k; c.sl_stride = stride; c.sl_pad = pad; c.sl_transposed = transposed; c.sl_out_pad = out_pad;
+  c.sl_reflect = reflect; c.sl_bias = bias != nullptr; c.sl_norm = norm != 0; c.sl_act = act; c.sl_final = final_path;
+  I2INet net(c, prop.multiProcessorCount);
+  const std::vector<float> ones((size_t)Cout, 1.f), zeros((size_t)Cout, 0.f);
+  auto get = [&](const std::string& key, std::vector<int64_t>& shape) -> const float* {
+    if (key == "conv.weight") {
+      shape = transposed ? std::vector<int64_t>{Cin, Cout, k, k} : std::vector<int64_t>{Cout, Cin, k, k};
+      return w;
+    }
+    shape = {Cout};
+    if (key == "conv.bias") return bias;
+    if (key == "norm.weight") return norm_weight ? norm_weight : ones.data();
+    if (key == "norm.bias") return norm_bias ? norm_bias : zeros.data();
+    if (key == "norm.running_mean") return zeros.data();
+    if (key == "norm.running_var") return ones.data();
+    return nullptr;
+  };
+  std::string err;
+  size_t consumed = 0;
+  int rc = net.build(get, err, &consumed);
+  if (rc) return fail(i2i_code(rc), err);
+  if ((rc = net.check_size(hgt, wid, err))) return fail(i2i_code(rc), err);
+  const int Ho = net.out_size(hgt), Wo = net.out_size(wid);
+  const int ict = (Cin + 7) / 8, oct = (Cout + 7) / 8;
+  const size_t esz = dtype == INNFER_F16 ? 2 : 4;
+  DevBuf in, out;
+  if (in.ensure((size_t)n * ict * hgt * wid * 8 * esz) || out.ensure((size_t)n * oct * Ho * Wo * 8 * esz)) {
+    in.release();
+    out.release();
+    return fail(INNFER_E_NOMEM, "temporary allocation failed");
+  }
+  if (dtype == INNFER_F16)
+    rc = launch_nchw_to_chunks(x, kF16, n, Cin, hgt, wid, reinterpret_cast<__half*>(in.p), ict, st);
+  else
+    rc = launch_nchw_to_chunks_f32(x, kF32, n, Cin, hgt, wid, reinterpret_cast<float*>(in.p), ict, st);
+  if (!rc) {
+    rc = net.forward(in.p, ict, n, hgt, wid, GenView{out.p, oct, 0}, false, false, st, err);
+    if (rc) rc = fail(i2i_code(rc), err);
+  } else {
+    rc = fail(INNFER_E_CUDA, "nchw_to_chunks launch failed");
+  }
+  if (!rc) {
+    int e2;
+    if (dtype == INNFER_F16)
+      e2 = launch_chunks_to_nchw(reinterpret_cast<const __half*>(out.p), oct, n, Cout, Ho, Wo, y, kF16, st);
+    else
+      e2 = launch_chunks_to_nchw_f32(reinterpret_cast<const float*>(out.p), oct, n, Cout, Ho, Wo, y, kF32, st);
+    if (e2) rc = fail(INNFER_E_CUDA, "chunks_to_nchw launch failed");
+  }
+  g_launches.fetch_add(net.launches() + 2, std::memory_order_relaxed);
+  const cudaError_t se = cudaStreamSynchronize(st);
+  in.release();
+  out.release();
+  if (!rc && se != cudaSuccess) return cuda_fail(se, "innfer_gen_conv");
+  return rc;
+}
+
 int innfer_debug_conv_loop(int Cin, int Cout, int B, int H, int W, int with_res, int warm, int iters, float* ms_out) {
   if (!ms_out) return fail(INNFER_E_INVALID, "null argument");
   g_wide_sep = 1;

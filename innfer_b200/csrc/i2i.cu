@@ -1,0 +1,1106 @@
+// pix2pix UnetGenerator / CycleGAN ResnetGenerator on sm_100a.  See i2i.cuh for the design notes.
+//
+// Reference semantics restated here (file:line relative to the reference tree):
+//   architectures/UNet_arch.py:98-165   UnetSkipConnectionBlock: [LeakyReLU(0.2, inplace), Conv2d(4, 2, 1), norm,
+//                                       submodule, ReLU(inplace), ConvTranspose2d(4, 2, 1), norm], cat([x, model(x)])
+//   architectures/ResNet_arch.py:55-91  ReflectionPad2d(3) + Conv2d(7), two Conv2d(3, 2, 1), ResnetBlocks,
+//                                       two ConvTranspose2d(3, 2, 1, output_padding 1), ReflectionPad2d(3) + Conv2d(7), Tanh
+//   architectures/ResNet_arch.py:113-151 ResnetBlock: x + [pad, conv, norm, ReLU, pad, conv, norm](x)
+//   torch.nn.BatchNorm2d / InstanceNorm2d: eps 1e-5, biased variance; BatchNorm in training mode (run.py:297,
+//   pix2pix_extras meval False) normalises with the statistics of the batch it is given.
+#include "i2i.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "ptx.cuh"
+
+namespace innfer {
+
+namespace {
+
+constexpr int kGenThreads = 160;            // warps 0..3: operand gather, then epilogue; warp 4: TMEM owner + MMA issuer
+constexpr int kGenABytes = 8 * 128 * 16;    // one K-step of A: 8 K-chunks x 128 pixels x 16 bytes
+constexpr int kGenTailBytes = 256;          // barriers + TMEM slot behind the stage ring
+constexpr float kNormEps = 1e-5f;
+constexpr float kLreluSlope = 0.2f;
+
+__host__ __device__ constexpr int gen_stages(int NT) { return NT >= 128 ? 3 : 4; }
+
+struct GenConvParams {
+  const void* in;            // [B][*][Hin][Win][8] fp16 (tensor-core kernel) or fp32 (direct kernel)
+  long long in_bs, in_cs;    // elements per image / per chunk plane
+  int Hin, Win;
+  void* out;
+  long long out_bs, out_cs;
+  long long split_stride;    // elements between split-K partial tensors (raw fp32 only)
+  int Hout, Wout;
+  int out_mode;              // 0: chunks of the kernel's element type, 1: raw fp32 chunks, 2: compact [B][H][W][4] fp16
+  int out_chunk0, out_nchunks;
+  int B, nphase, nsplit;
+  int Hp[kGenMaxPhases], Wp[kGenMaxPhases], Mp[kGenMaxPhases];
+  int py[kGenMaxPhases], px[kGenMaxPhases], ntaps[kGenMaxPhases], ksteps[kGenMaxPhases];
+  long long woff[kGenMaxPhases];   // element offset of the phase inside w
+  int ostep, istep;
+  int cin_chunks, in_chunk0, cout_pad;
+  int reflect, act;
+  const void* w;
+  const float* bias;
+  int8_t offy[kGenMaxPhases][kGenMaxTaps], offx[kGenMaxPhases][kGenMaxTaps];
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case kActRelu: return fmaxf(v, 0.f);
+    case kActLrelu: return v > 0.f ? v : v * kLreluSlope;
+    case kActTanh: return tanhf(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ int reflect_index(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+// ------------------------------------------------------------------------------------------------ tensor-core conv
+template <int NT>
+__global__ void __launch_bounds__(kGenThreads) gen_conv_tc_kernel(const __grid_constant__ GenConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int S = gen_stages(NT);
+  constexpr int D = S - 1;                       // cp.async groups a gather thread keeps in flight
+  constexpr uint32_t B_BYTES = 8u * NT * 16u;
+  constexpr uint32_t STAGE = kGenABytes + B_BYTES;
+  constexpr uint32_t TCOLS = NT < 32 ? 32u : (uint32_t)NT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ph = (int)blockIdx.z / p.nsplit, split = (int)blockIdx.z - ph * p.nsplit;
+  const int Mp = p.Mp[ph];
+  if ((int)blockIdx.x * 128 >= Mp) return;       // phases of a transposed conv differ by at most one row / column
+  const int KS = p.ksteps[ph];
+  const int k0 = (int)((long long)KS * split / p.nsplit), k1 = (int)((long long)KS * (split + 1) / p.nsplit);
+  const int nk = k1 - k0;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)S * STAGE);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tfull_bar = empty_bar + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 128 + 1);   // every gather thread + the weight copy's expect_tx
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(tfull_bar), 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(tmem_slot), TCOLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ gather: thread <-> output pixel (row of the M tile)
+    const int tid = threadIdx.x;
+    const int m = (int)blockIdx.x * 128 + tid;
+    const bool valid = m < Mp;
+    const int Wp = p.Wp[ph], HWp = p.Hp[ph] * Wp;
+    int b = 0, oyp = 0, oxp = 0;
+    if (valid) {
+      b = m / HWp;
+      const int r = m - b * HWp;
+      oyp = r / Wp;
+      oxp = r - oyp * Wp;
+    }
+    const int iy0 = oyp * p.istep, ix0 = oxp * p.istep;
+    const __half* inb = reinterpret_cast<const __half*>(p.in) + (size_t)b * p.in_bs + (size_t)p.in_chunk0 * p.in_cs;
+    const int ntaps = p.ntaps[ph];
+    const int8_t* offy = p.offy[ph];
+    const int8_t* offx = p.offx[ph];
+    int tap = (k0 * 8) / p.cin_chunks;
+    int chunk = k0 * 8 - tap * p.cin_chunks;
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(reinterpret_cast<const __half*>(p.w) + p.woff[ph]) +
+                          ((size_t)blockIdx.y * KS + k0) * B_BYTES;
+    for (int i = 0; i < nk; ++i) {
+      const int s = i % S;
+      mbar_wait(smem_u32(&empty_bar[s]), (((uint32_t)(i / S)) & 1u) ^ 1u);
+      const uint32_t a_dst = smem_base + (uint32_t)s * STAGE;
+      if (tid == 0) {
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        mbar_expect_tx(fb, B_BYTES);
+        bulk_load(a_dst + kGenABytes, wsrc + (size_t)i * B_BYTES, B_BYTES, fb);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const void* src = p.in;
+        uint32_t sz = 0;
+        if (valid && tap < ntaps) {
+          int iy = iy0 + offy[tap], ix = ix0 + offx[tap];
+          if (p.reflect) {
+            iy = reflect_index(iy, p.Hin);
+            ix = reflect_index(ix, p.Win);
+          }
+          if ((unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win) {
+            src = inb + (size_t)chunk * p.in_cs + ((size_t)iy * p.Win + ix) * 8;
+            sz = 16;
+          }
+        }
+        cp_async_16(a_dst + (uint32_t)j * 2048u + (uint32_t)tid * 16u, src, sz);   // sz 0: zero fill (padding, K tail)
+        if (++chunk == p.cin_chunks) {
+          chunk = 0;
+          ++tap;
+        }
+      }
+      cp_async_commit();
+      if (i >= D) {
+        cp_async_wait<D>();            // the copies of K-step i - D have landed
+        fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        mbar_arrive(smem_u32(&full_bar[(i - D) % S]));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (int i = nk > D ? nk - D : 0; i < nk; ++i) mbar_arrive(smem_u32(&full_bar[i % S]));
+
+    // ------------------------------------------------------------ epilogue: TMEM lane = pixel row = this thread
+    mbar_wait(smem_u32(tfull_bar), 0u);
+    tc_fence_after();
+    const int oy = oyp * p.ostep + p.py[ph], ox = oxp * p.ostep + p.px[ph];
+    const size_t pix = (size_t)oy * p.Wout + ox;
+    const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < NT; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tacc + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (!valid) continue;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int gc = (int)blockIdx.y * (NT / 8) + c0 / 8 + hh;
+        if (gc >= p.out_nchunks) continue;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float t = __uint_as_float(v[hh * 8 + e]);
+          if (split == 0) t += p.bias[gc * 8 + e];
+          f[e] = apply_act(t, p.act);
+        }
+        if (p.out_mode == 1) {
+          float* op = reinterpret_cast<float*>(p.out) + (size_t)split * p.split_stride + (size_t)b * p.out_bs +
+                      (size_t)(p.out_chunk0 + gc) * p.out_cs + pix * 8;
+          *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+          *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        } else if (p.out_mode == 0) {
+          __half* op = reinterpret_cast<__half*>(p.out) + (size_t)b * p.out_bs + (size_t)(p.out_chunk0 + gc) * p.out_cs + pix * 8;
+          uint4 o;
+          __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+          __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+          o.x = *reinterpret_cast<uint32_t*>(&h0);
+          o.y = *reinterpret_cast<uint32_t*>(&h1);
+          o.z = *reinterpret_cast<uint32_t*>(&h2);
+          o.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(op) = o;
+        } else if (gc == 0) {
+          __half* op = reinterpret_cast<__half*>(p.out) + ((size_t)b * p.Hout * p.Wout + pix) * 4;
+          uint2 o;
+          __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+          o.x = *reinterpret_cast<uint32_t*>(&h0);
+          o.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(op) = o;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc_f16(NT);
+    for (int i = 0; i < nk; ++i) {
+      const int s = i % S;
+      mbar_wait(smem_u32(&full_bar[s]), ((uint32_t)(i / S)) & 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_base + (uint32_t)s * STAGE;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          // A: [K-chunk][pixel][8]: 8-row groups 128 B apart (SBO), K-chunks 2048 B apart (LBO); B: [K-chunk][n][8]
+          const uint64_t adesc = make_smem_desc(sa + (uint32_t)kk * 4096u, 2048u, 128u);
+          const uint64_t bdesc = make_smem_desc(sa + kGenABytes + (uint32_t)kk * 2u * NT * 16u, (uint32_t)NT * 16u, 128u);
+          umma_f16_ss(tmem_base, adesc, bdesc, idesc, (i | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));   // the stage is free once these MMAs have read it
+      }
+      __syncwarp();
+    }
+    if (lane == 0) umma_commit(smem_u32(tfull_bar));
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TCOLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fp32 direct conv
+// -no_fp16 mode (correctness mode, CUDA cores): thread <-> (output pixel, 8 output channels), FMAs in a fixed order.
+__global__ void __launch_bounds__(128) gen_conv_direct_kernel(const __grid_constant__ GenConvParams p) {
+  const int ph = blockIdx.z, oc = blockIdx.y;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= p.Mp[ph]) return;
+  const int Wp = p.Wp[ph], HWp = p.Hp[ph] * Wp;
+  const int b = m / HWp;
+  const int r = m - b * HWp;
+  const int oyp = r / Wp, oxp = r - oyp * Wp;
+  const float* inb = reinterpret_cast<const float*>(p.in) + (size_t)b * p.in_bs + (size_t)p.in_chunk0 * p.in_cs;
+  const float* wbase = reinterpret_cast<const float*>(p.w) + p.woff[ph] + oc * 8;
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = p.bias[oc * 8 + o];
+  for (int t = 0; t < p.ntaps[ph]; ++t) {
+    int iy = oyp * p.istep + p.offy[ph][t], ix = oxp * p.istep + p.offx[ph][t];
+    if (p.reflect) {
+      iy = reflect_index(iy, p.Hin);
+      ix = reflect_index(ix, p.Win);
+    }
+    if ((unsigned)iy >= (unsigned)p.Hin || (unsigned)ix >= (unsigned)p.Win) continue;
+    const float* ip = inb + ((size_t)iy * p.Win + ix) * 8;
+    const float* wt = wbase + (size_t)t * p.cin_chunks * 8 * p.cout_pad;
+    for (int c = 0; c < p.cin_chunks; ++c) {
+      const float4 a0 = *reinterpret_cast<const float4*>(ip + (size_t)c * p.in_cs);
+      const float4 a1 = *reinterpret_cast<const float4*>(ip + (size_t)c * p.in_cs + 4);
+      const float x[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float* wr = wt + (size_t)(c * 8 + e) * p.cout_pad;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wr + 4));
+        acc[0] = fmaf(x[e], w0.x, acc[0]);
+        acc[1] = fmaf(x[e], w0.y, acc[1]);
+        acc[2] = fmaf(x[e], w0.z, acc[2]);
+        acc[3] = fmaf(x[e], w0.w, acc[3]);
+        acc[4] = fmaf(x[e], w1.x, acc[4]);
+        acc[5] = fmaf(x[e], w1.y, acc[5]);
+        acc[6] = fmaf(x[e], w1.z, acc[6]);
+        acc[7] = fmaf(x[e], w1.w, acc[7]);
+      }
+    }
+  }
+  const int oy = oyp * p.ostep + p.py[ph], ox = oxp * p.ostep + p.px[ph];
+  float* op = reinterpret_cast<float*>(p.out) + (size_t)b * p.out_bs + (size_t)(p.out_chunk0 + oc) * p.out_cs +
+              ((size_t)oy * p.Wout + ox) * 8;
+  *reinterpret_cast<float4*>(op) = make_float4(apply_act(acc[0], p.act), apply_act(acc[1], p.act), apply_act(acc[2], p.act),
+                                               apply_act(acc[3], p.act));
+  *reinterpret_cast<float4*>(op + 4) = make_float4(apply_act(acc[4], p.act), apply_act(acc[5], p.act),
+                                                   apply_act(acc[6], p.act), apply_act(acc[7], p.act));
+}
+
+// ------------------------------------------------------------------------------------------------ normalisation
+// The value of a raw pixel chunk: split-K partial tensors summed in index order (the same order everywhere).
+__device__ __forceinline__ void load_raw8(const float* p, int nsplit, long long split_stride, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 c = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+  for (int s = 1; s < nsplit; ++s) {
+    const float4 d = *reinterpret_cast<const float4*>(p + (size_t)s * split_stride);
+    const float4 e = *reinterpret_cast<const float4*>(p + (size_t)s * split_stride + 4);
+    v[0] += d.x; v[1] += d.y; v[2] += d.z; v[3] += d.w;
+    v[4] += e.x; v[5] += e.y; v[6] += e.z; v[7] += e.w;
+  }
+}
+
+// grid (slices, chunks, B), 256 threads: per-channel sum and sum of squares of one slice of pixels, in double, reduced
+// in a fixed order.  part: [B][chunks][slices][16] (8 sums, 8 sums of squares).
+__global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict__ raw, int nsplit, long long split_stride,
+                                                         long long bs, long long cs, int HW, double* __restrict__ part) {
+  const int slice = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z, nslices = gridDim.x;
+  const float* base = raw + (size_t)b * bs + (size_t)chunk * cs;
+  const int len = (HW + nslices - 1) / nslices;
+  const int start = slice * len, end = min(HW, start + len);
+  double s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.0;
+  for (int px = start + (int)threadIdx.x; px < end; px += 256) {
+    float v[8];
+    load_raw8(base + (size_t)px * 8, nsplit, split_stride, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s[e] += (double)v[e];
+      q[e] += (double)v[e] * (double)v[e];
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s[e] += __shfl_xor_sync(0xffffffffu, s[e], off);
+      q[e] += __shfl_xor_sync(0xffffffffu, q[e], off);
+    }
+  __shared__ double sh[8][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sh[warp][e] = s[e];
+      sh[warp][8 + e] = q[e];
+    }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x];
+    part[(((size_t)b * gridDim.y + chunk) * nslices + slice) * 16 + threadIdx.x] = t;
+  }
+}
+
+// one thread per (image, channel) [per_sample] or per channel [batch statistics]: (scale, shift) of y = x * scale + shift
+__global__ void norm_finalize_kernel(const double* __restrict__ part, int B, int chunks, int nslices, int HW, int per_sample,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float2* __restrict__ ss) {
+  const int C8 = chunks * 8;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (per_sample ? B * C8 : C8)) return;
+  const int c = idx % C8, b0 = per_sample ? idx / C8 : 0, b1 = per_sample ? b0 + 1 : B;
+  double S = 0.0, Q = 0.0;
+  for (int b = b0; b < b1; ++b)
+    for (int sl = 0; sl < nslices; ++sl) {
+      const double* pp = part + (((size_t)b * chunks + c / 8) * nslices + sl) * 16;
+      S += pp[c % 8];
+      Q += pp[8 + c % 8];
+    }
+  const double n = (double)(b1 - b0) * (double)HW;
+  const double mean = S / n;
+  double var = Q / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + (double)kNormEps);
+  const double g = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
+  const float2 o = make_float2((float)(g * rstd), (float)(be - mean * g * rstd));
+  for (int b = b0; b < b1; ++b) ss[(size_t)b * C8 + c] = o;
+}
+
+struct ApplyParams {
+  const float* raw;
+  int nsplit;
+  long long split_stride, raw_bs, raw_cs;
+  int B, chunks, HW;
+  const float2* ss;    // null: identity
+  int ss_per_sample;   // 1: [B][C], 0: [C]
+  void* out_a;
+  long long a_bs, a_cs;
+  int act_a;
+  void* out_b;         // optional second copy with its own activation
+  long long b_bs, b_cs;
+  int act_b;
+  const void* res;     // optional residual, added before the activation
+  long long r_bs, r_cs;
+};
+
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&f)[8], int act);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&f)[8], int act) {
+  *reinterpret_cast<float4*>(p) = make_float4(apply_act(f[0], act), apply_act(f[1], act), apply_act(f[2], act), apply_act(f[3], act));
+  *reinterpret_cast<float4*>(p + 4) = make_float4(apply_act(f[4], act), apply_act(f[5], act), apply_act(f[6], act), apply_act(f[7], act));
+}
+template <>
+__device__ __forceinline__ void store8<__half>(__half* p, const float (&f)[8], int act) {
+  __half2 h0 = __floats2half2_rn(apply_act(f[0], act), apply_act(f[1], act));
+  __half2 h1 = __floats2half2_rn(apply_act(f[2], act), apply_act(f[3], act));
+  __half2 h2 = __floats2half2_rn(apply_act(f[4], act), apply_act(f[5], act));
+  __half2 h3 = __floats2half2_rn(apply_act(f[6], act), apply_act(f[7], act));
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&h0);
+  o.y = *reinterpret_cast<uint32_t*>(&h1);
+  o.z = *reinterpret_cast<uint32_t*>(&h2);
+  o.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), c = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = c.x; f[5] = c.y; f[6] = c.z; f[7] = c.w;
+}
+__device__ __forceinline__ void load8(const __half* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __half22float2(h[e]);
+    f[2 * e] = t.x;
+    f[2 * e + 1] = t.y;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) norm_apply_kernel(const __grid_constant__ ApplyParams p) {
+  const long long total = (long long)p.B * p.chunks * p.HW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(idx % p.HW);
+    const long long r = idx / p.HW;
+    const int chunk = (int)(r % p.chunks), b = (int)(r / p.chunks);
+    float v[8];
+    load_raw8(p.raw + (size_t)b * p.raw_bs + (size_t)chunk * p.raw_cs + (size_t)px * 8, p.nsplit, p.split_stride, v);
+    if (p.ss) {
+      const float2* ss = p.ss + ((size_t)(p.ss_per_sample ? b : 0) * p.chunks + chunk) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float2 t = ss[e];
+        v[e] = fmaf(v[e], t.x, t.y);
+      }
+    }
+    if (p.res) {
+      float rv[8];
+      load8(reinterpret_cast<const T*>(p.res) + (size_t)b * p.r_bs + (size_t)chunk * p.r_cs + (size_t)px * 8, rv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += rv[e];
+    }
+    store8<T>(reinterpret_cast<T*>(p.out_a) + (size_t)b * p.a_bs + (size_t)chunk * p.a_cs + (size_t)px * 8, v, p.act_a);
+    if (p.out_b)
+      store8<T>(reinterpret_cast<T*>(p.out_b) + (size_t)b * p.b_bs + (size_t)chunk * p.b_cs + (size_t)px * 8, v, p.act_b);
+  }
+}
+
+// eval-mode BatchNorm: (scale, shift) from the running statistics
+std::vector<float> running_scale_shift(const float* gamma, const float* beta, const float* mean, const float* var, int C) {
+  std::vector<float> ss((size_t)2 * C);
+  for (int c = 0; c < C; ++c) {
+    const double rstd = 1.0 / std::sqrt((double)var[c] + (double)kNormEps);
+    const double sc = (double)gamma[c] * rstd;
+    ss[2 * c] = (float)sc;
+    ss[2 * c + 1] = (float)((double)beta[c] - (double)mean[c] * sc);
+  }
+  return ss;
+}
+
+template <int NT>
+cudaError_t launch_tc(const GenConvParams& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = (size_t)gen_stages(NT) * (kGenABytes + 8 * NT * 16) + kGenTailBytes;
+  cudaError_t e = cudaFuncSetAttribute(gen_conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  gen_conv_tc_kernel<NT><<<grid, kGenThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// ==================================================================================================== host side
+I2INet::~I2INet() {
+  for (void* p : owned_) cudaFree(p);
+  for (auto* v : {&dbuf_, &cat_, &rb_})
+    for (auto& b : *v)
+      if (b.p) cudaFree(b.p);
+  for (Buf* b : {&raw_, &inner_, &a_, &b_, &stats_, &ss_})
+    if (b->p) cudaFree(b->p);
+}
+
+int I2INet::need(Buf& b, size_t bytes) {
+  if (bytes <= b.bytes) return 0;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+  const size_t want = (bytes + 255) & ~(size_t)255;
+  if (cudaMalloc(&b.p, want) != cudaSuccess) {
+    cudaGetLastError();
+    err_ = "workspace allocation of " + std::to_string(want) + " bytes failed";
+    return -5;
+  }
+  b.bytes = want;
+  return 0;
+}
+
+int I2INet::check_size(int H, int W, std::string& err) const {
+  if (cfg_.kind == 2) {
+    if (down_[0].out_h(H) < 1 || down_[0].out_h(W) < 1 || (down_[0].reflect && (H <= down_[0].pad || W <= down_[0].pad))) {
+      err = "input too small for this convolution";
+      return -1;
+    }
+    return 0;
+  }
+  if (cfg_.kind == 0) {
+    const int g = 1 << cfg_.depth;
+    if (H % g || W % g) {
+      err = "UnetGenerator with num_downs " + std::to_string(cfg_.depth) + " needs image sizes that are multiples of " +
+            std::to_string(g) + " (run.py:412-413 resizes to multiples of the -a size for pix2pix)";
+      return -1;
+    }
+  } else if (H % 4 || W % 4 || H < 8 || W < 8) {
+    err = "ResnetGenerator needs image (tile) sizes that are multiples of 4, at least 8";
+    return -1;
+  }
+  return 0;
+}
+
+int I2INet::build_conv(const ParamLookup& get, const std::string& name, GenConv& L, int Cout, int Cin, int k, int stride,
+                       int pad, bool transposed, int out_pad, bool reflect, bool has_bias, std::string& err, size_t* consumed) {
+  std::vector<int64_t> ws, bshape;
+  const float* w = get(name + ".weight", ws);
+  if (!w) {
+    err = "missing key " + name + ".weight";
+    return -4;
+  }
+  const std::vector<int64_t> want = transposed ? std::vector<int64_t>{Cin, Cout, k, k} : std::vector<int64_t>{Cout, Cin, k, k};
+  if (ws != want) {
+    err = "size mismatch for " + name + ".weight";
+    return -1;
+  }
+  const float* bias = nullptr;
+  if (has_bias) {
+    bias = get(name + ".bias", bshape);
+    if (!bias) {
+      err = "missing key " + name + ".bias";
+      return -4;
+    }
+    if (bshape != std::vector<int64_t>{Cout}) {
+      err = "size mismatch for " + name + ".bias";
+      return -1;
+    }
+  }
+  *consumed += has_bias ? 2 : 1;
+  if (k * k > kGenMaxTaps || stride < 1 || stride > 2 || (transposed && stride * stride > kGenMaxPhases)) {
+    err = name + ": unsupported kernel size / stride";
+    return -2;
+  }
+  L.Cin = Cin; L.Cout = Cout; L.k = k; L.stride = stride; L.pad = pad; L.out_pad = out_pad;
+  L.transposed = transposed; L.reflect = reflect;
+  L.cin_chunks = (Cin + 7) / 8;
+  L.cout_chunks = (Cout + 7) / 8;
+  L.NT = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128));
+  L.ntiles = (Cout + L.NT - 1) / L.NT;
+  // taps of every phase; tapk = ky * k + kx of each tap (host only)
+  std::vector<int> tapk[kGenMaxPhases];
+  if (!transposed) {
+    L.nphase = 1; L.ostep = 1; L.istep = stride;
+    L.ph_py[0] = L.ph_px[0] = 0;
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx) {
+        const int t = (int)tapk[0].size();
+        L.offy[0][t] = (int8_t)(ky - pad);
+        L.offx[0][t] = (int8_t)(kx - pad);
+        tapk[0].push_back(ky * k + kx);
+      }
+  } else {
+    // out[iy * s - pad + ky] += in[iy] * w[ky]: the outputs of parity class (py, px) use the taps with
+    // ky = (py + pad) mod s (+ s, + 2s, ...) and read in[oy' + (py + pad - ky) / s]
+    L.nphase = stride * stride; L.ostep = stride; L.istep = 1;
+    for (int py = 0; py < stride; ++py)
+      for (int px = 0; px < stride; ++px) {
+        const int ph = py * stride + px;
+        L.ph_py[ph] = py;
+        L.ph_px[ph] = px;
+        for (int ky = (py + pad) % stride; ky < k; ky += stride)
+          for (int kx = (px + pad) % stride; kx < k; kx += stride) {
+            const int t = (int)tapk[ph].size();
+            L.offy[ph][t] = (int8_t)((py + pad - ky) / stride);
+            L.offx[ph][t] = (int8_t)((px + pad - kx) / stride);
+            tapk[ph].push_back(ky * k + kx);
+          }
+      }
+  }
+  auto weight = [&](int co, int ci, int kk) -> float {
+    return transposed ? w[((size_t)ci * Cout + co) * k * k + kk] : w[((size_t)co * Cin + ci) * k * k + kk];
+  };
+  size_t n16 = 0, n32 = 0;
+  for (int ph = 0; ph < L.nphase; ++ph) {
+    L.ph_ntaps[ph] = (int)tapk[ph].size();
+    L.ph_ksteps[ph] = std::max(1, (L.ph_ntaps[ph] * L.cin_chunks + 7) / 8);
+    L.ph_woff16[ph] = n16;
+    L.ph_woff32[ph] = n32;
+    n16 += (size_t)L.ntiles * L.ph_ksteps[ph] * 8 * L.NT * 8;
+    n32 += (size_t)L.ph_ntaps[ph] * L.cin_chunks * 8 * L.cout_chunks * 8;
+  }
+  cudaError_t e;
+  if (cfg_.fp16) {
+    std::vector<__half> pk(n16);
+    for (int ph = 0; ph < L.nphase; ++ph)
+      for (int nt = 0; nt < L.ntiles; ++nt)
+        for (int ks = 0; ks < L.ph_ksteps[ph]; ++ks)
+          for (int j = 0; j < 8; ++j) {
+            const int q = ks * 8 + j, tap = q / L.cin_chunks, chunk = q % L.cin_chunks;
+            __half* dst = pk.data() + L.ph_woff16[ph] + ((((size_t)nt * L.ph_ksteps[ph] + ks) * 8 + j) * L.NT) * 8;
+            for (int n = 0; n < L.NT; ++n)
+              for (int ee = 0; ee < 8; ++ee) {
+                const int co = nt * L.NT + n, ci = chunk * 8 + ee;
+                const float v = (tap < L.ph_ntaps[ph] && co < Cout && ci < Cin) ? weight(co, ci, tapk[ph][tap]) : 0.f;
+                dst[(size_t)n * 8 + ee] = __float2half_rn(v);
+              }
+          }
+    e = cudaMalloc(&L.d_w16, n16 * sizeof(__half));
+    if (e == cudaSuccess) {
+      owned_.push_back(L.d_w16);
+      e = cudaMemcpy(L.d_w16, pk.data(), n16 * sizeof(__half), cudaMemcpyHostToDevice);
+    }
+  } else {
+    const int cip = L.cin_chunks * 8, cop = L.cout_chunks * 8;
+    std::vector<float> pk(n32, 0.f);
+    for (int ph = 0; ph < L.nphase; ++ph)
+      for (int t = 0; t < L.ph_ntaps[ph]; ++t)
+        for (int ci = 0; ci < Cin; ++ci)
+          for (int co = 0; co < Cout; ++co)
+            pk[L.ph_woff32[ph] + ((size_t)t * cip + ci) * cop + co] = weight(co, ci, tapk[ph][t]);
+    e = cudaMalloc(&L.d_w32, n32 * sizeof(float));
+    if (e == cudaSuccess) {
+      owned_.push_back(L.d_w32);
+      e = cudaMemcpy(L.d_w32, pk.data(), n32 * sizeof(float), cudaMemcpyHostToDevice);
+    }
+  }
+  if (e != cudaSuccess) {
+    err = name + ": weight upload failed: " + cudaGetErrorString(e);
+    return -3;
+  }
+  const int nb = std::max(L.ntiles * L.NT, L.cout_chunks * 8);
+  std::vector<float> hb((size_t)nb, 0.f);
+  if (bias) std::copy(bias, bias + Cout, hb.begin());
+  e = cudaMalloc(&L.d_bias, hb.size() * sizeof(float));
+  if (e == cudaSuccess) {
+    owned_.push_back(L.d_bias);
+    e = cudaMemcpy(L.d_bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) {
+    err = name + ": bias upload failed: " + cudaGetErrorString(e);
+    return -3;
+  }
+  return 0;
+}
+
+int I2INet::build_norm(const ParamLookup& get, const std::string& name, Norm& n, int C, std::string& err, size_t* consumed) {
+  n.C = C;
+  if (C % 8) {
+    err = name + ": normalised channel counts must be multiples of 8 (ngf a multiple of 8)";
+    return -2;
+  }
+  if (cfg_.norm == 1) return 0;   // InstanceNorm2d: no parameters, statistics per image always
+  std::vector<int64_t> sh;
+  const float* g = get(name + ".weight", sh);
+  if (!g || sh != std::vector<int64_t>{C}) {
+    err = (g ? "size mismatch for " : "missing key ") + name + ".weight";
+    return g ? -1 : -4;
+  }
+  const float* b = get(name + ".bias", sh);
+  if (!b || sh != std::vector<int64_t>{C}) {
+    err = (b ? "size mismatch for " : "missing key ") + name + ".bias";
+    return b ? -1 : -4;
+  }
+  const float* rm = get(name + ".running_mean", sh);
+  if (!rm || sh != std::vector<int64_t>{C}) {
+    err = (rm ? "size mismatch for " : "missing key ") + name + ".running_mean";
+    return rm ? -1 : -4;
+  }
+  const float* rv = get(name + ".running_var", sh);
+  if (!rv || sh != std::vector<int64_t>{C}) {
+    err = (rv ? "size mismatch for " : "missing key ") + name + ".running_var";
+    return rv ? -1 : -4;
+  }
+  *consumed += 4;
+  n.affine = true;
+  n.running = !cfg_.train;
+  auto up = [&](const float* src, size_t count, float** dst) -> bool {
+    if (cudaMalloc(dst, count * sizeof(float)) != cudaSuccess) return false;
+    owned_.push_back(*dst);
+    return cudaMemcpy(*dst, src, count * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  bool ok = up(g, C, &n.d_gamma) && up(b, C, &n.d_beta);
+  if (ok && n.running) {
+    const std::vector<float> ss = running_scale_shift(g, b, rm, rv, C);
+    ok = up(ss.data(), ss.size(), &n.d_ss);
+  }
+  if (!ok) {
+    cudaGetLastError();
+    err = name + ": upload failed";
+    return -3;
+  }
+  return 0;
+}
+
+int I2INet::build(const ParamLookup& get, std::string& err, size_t* consumed) {
+  *consumed = 0;
+  if (cfg_.kind == 2) {
+    down_.resize(1);
+    dnorm_.resize(1);
+    int rc = build_conv(get, "conv", down_[0], cfg_.sl_cout, cfg_.in_nc, cfg_.sl_k, cfg_.sl_stride, cfg_.sl_pad,
+                        cfg_.sl_transposed != 0, cfg_.sl_out_pad, cfg_.sl_reflect != 0, cfg_.sl_bias != 0, err, consumed);
+    if (!rc && cfg_.sl_norm) rc = build_norm(get, "norm", dnorm_[0], cfg_.sl_cout, err, consumed);
+    return rc;
+  }
+  const int ngf = cfg_.ngf;
+  if (ngf % 8 || ngf < 8) {
+    err = "ngf must be a multiple of 8";
+    return -2;
+  }
+  if (cfg_.in_nc < 1 || cfg_.in_nc > 16 || cfg_.out_nc < 1 || cfg_.out_nc > 8) {
+    err = "in_nc must be <= 16 and out_nc <= 8";
+    return -2;
+  }
+  const bool bias = cfg_.norm == 1;   // use_bias = norm_layer == InstanceNorm2d (UNet_arch.py:100-103, ResNet_arch.py:47-50)
+  int rc;
+  if (cfg_.kind == 0) {
+    const int D = cfg_.depth;
+    if (D < 5 || D > 12) {
+      err = "num_downs must be in [5, 12]";
+      return -2;
+    }
+    down_.resize(D);
+    up_.resize(D);
+    dnorm_.resize(D);
+    unorm_.resize(D);
+    auto inner_nc = [&](int i) { return ngf * std::min(1 << i, 8); };
+    std::string prefix = "model.model";
+    for (int i = 0; i < D; ++i) {
+      const bool outer = i == 0, innermost = i == D - 1;
+      const int inner = inner_nc(i), outer_nc = outer ? cfg_.out_nc : inner_nc(i - 1);
+      const int cin = outer ? cfg_.in_nc : outer_nc;
+      // Sequential indices (UNet_arch.py:120-158): outermost [down, sub, relu, up, tanh]; middle [lrelu, down, norm, sub,
+      // relu, up, norm]; innermost [lrelu, down, relu, up, norm]
+      const std::string dn = prefix + (outer ? ".0" : ".1");
+      const std::string un = prefix + (outer ? ".3" : (innermost ? ".3" : ".5"));
+      if ((rc = build_conv(get, dn, down_[i], inner, cin, 4, 2, 1, false, 0, false, bias, err, consumed))) return rc;
+      if ((rc = build_conv(get, un, up_[i], outer_nc, innermost ? inner : 2 * inner, 4, 2, 1, true, 0, false,
+                           outer ? true : bias, err, consumed)))
+        return rc;
+      if (!outer && !innermost && (rc = build_norm(get, prefix + ".2", dnorm_[i], inner, err, consumed))) return rc;
+      if (!outer && (rc = build_norm(get, prefix + (innermost ? ".4" : ".6"), unorm_[i], outer_nc, err, consumed))) return rc;
+      prefix += outer ? ".1.model" : ".3.model";
+    }
+  } else {
+    const int nb = cfg_.depth;
+    if (nb < 0 || nb > 64) {
+      err = "n_blocks must be in [0, 64]";
+      return -2;
+    }
+    const int nconv = 3 + 2 * nb + 3;
+    down_.resize(nconv);
+    dnorm_.resize(nconv);
+    int li = 0;
+    auto key = [](int i) { return "model." + std::to_string(i); };
+    if ((rc = build_conv(get, key(1), down_[li], ngf, cfg_.in_nc, 7, 1, 3, false, 0, true, bias, err, consumed))) return rc;
+    if ((rc = build_norm(get, key(2), dnorm_[li], ngf, err, consumed))) return rc;
+    ++li;
+    int ch = ngf;
+    for (int d = 0; d < 2; ++d, ++li) {
+      if ((rc = build_conv(get, key(4 + 3 * d), down_[li], ch * 2, ch, 3, 2, 1, false, 0, false, bias, err, consumed))) return rc;
+      if ((rc = build_norm(get, key(5 + 3 * d), dnorm_[li], ch * 2, err, consumed))) return rc;
+      ch *= 2;
+    }
+    for (int b = 0; b < nb; ++b) {
+      const std::string p = key(10 + b) + ".conv_block";
+      if ((rc = build_conv(get, p + ".1", down_[li], ch, ch, 3, 1, 1, false, 0, true, bias, err, consumed))) return rc;
+      if ((rc = build_norm(get, p + ".2", dnorm_[li], ch, err, consumed))) return rc;
+      ++li;
+      if ((rc = build_conv(get, p + ".5", down_[li], ch, ch, 3, 1, 1, false, 0, true, bias, err, consumed))) return rc;
+      if ((rc = build_norm(get, p + ".6", dnorm_[li], ch, err, consumed))) return rc;
+      ++li;
+    }
+    int idx = 10 + nb;
+    for (int u = 0; u < 2; ++u, ++li, idx += 3) {
+      if ((rc = build_conv(get, key(idx), down_[li], ch / 2, ch, 3, 2, 1, true, 1, false, bias, err, consumed))) return rc;
+      if ((rc = build_norm(get, key(idx + 1), dnorm_[li], ch / 2, err, consumed))) return rc;
+      ch /= 2;
+    }
+    if ((rc = build_conv(get, key(idx + 1), down_[li], cfg_.out_nc, ngf, 7, 1, 3, false, 0, true, true, err, consumed))) return rc;
+  }
+  return 0;
+}
+
+namespace {
+
+void fill_params(GenConvParams& p, const GenConv& L, GenView in, int B, int Hin, int Win, int Hout, int Wout, size_t esz_in) {
+  (void)esz_in;
+  memset(&p, 0, sizeof p);
+  p.in = in.base;
+  p.in_cs = (long long)Hin * Win * 8;
+  p.in_bs = (long long)in.CT * p.in_cs;
+  p.in_chunk0 = in.chunk0;
+  p.Hin = Hin; p.Win = Win; p.Hout = Hout; p.Wout = Wout;
+  p.B = B;
+  p.nphase = L.nphase;
+  p.nsplit = 1;
+  p.ostep = L.ostep; p.istep = L.istep;
+  p.cin_chunks = L.cin_chunks;
+  p.cout_pad = L.cout_chunks * 8;
+  p.reflect = L.reflect ? 1 : 0;
+  p.out_nchunks = L.cout_chunks;
+  p.bias = L.d_bias;
+  for (int ph = 0; ph < L.nphase; ++ph) {
+    p.py[ph] = L.ph_py[ph];
+    p.px[ph] = L.ph_px[ph];
+    p.Hp[ph] = (Hout - L.ph_py[ph] + L.ostep - 1) / L.ostep;
+    p.Wp[ph] = (Wout - L.ph_px[ph] + L.ostep - 1) / L.ostep;
+    p.Mp[ph] = B * p.Hp[ph] * p.Wp[ph];
+    p.ntaps[ph] = L.ph_ntaps[ph];
+    p.ksteps[ph] = L.ph_ksteps[ph];
+    memcpy(p.offy[ph], L.offy[ph], kGenMaxTaps);
+    memcpy(p.offx[ph], L.offx[ph], kGenMaxTaps);
+  }
+}
+
+int max_m(const GenConvParams& p) {
+  int m = 0;
+  for (int ph = 0; ph < p.nphase; ++ph) m = std::max(m, p.Mp[ph]);
+  return m;
+}
+
+cudaError_t launch_conv(const GenConv& L, GenConvParams& p, bool fp16, cudaStream_t st) {
+  if (fp16) {
+    p.w = L.d_w16;
+    for (int ph = 0; ph < L.nphase; ++ph) p.woff[ph] = (long long)L.ph_woff16[ph];
+    const dim3 grid((unsigned)((max_m(p) + 127) / 128), (unsigned)L.ntiles, (unsigned)(L.nphase * p.nsplit));
+    switch (L.NT) {
+      case 16: return launch_tc<16>(p, grid, st);
+      case 32: return launch_tc<32>(p, grid, st);
+      case 64: return launch_tc<64>(p, grid, st);
+      default: return launch_tc<128>(p, grid, st);
+    }
+  }
+  p.w = L.d_w32;
+  for (int ph = 0; ph < L.nphase; ++ph) p.woff[ph] = (long long)L.ph_woff32[ph];
+  const dim3 grid((unsigned)((max_m(p) + 127) / 128), (unsigned)L.cout_chunks, (unsigned)L.nphase);
+  gen_conv_direct_kernel<<<grid, 128, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+int I2INet::conv_raw(const GenConv& L, GenView in, int B, int Hin, int Win, Raw& raw, cudaStream_t st) {
+  const int Hout = L.out_h(Hin), Wout = L.out_h(Win);
+  GenConvParams p;
+  fill_params(p, L, in, B, Hin, Win, Hout, Wout, esz());
+  // split K across CTAs when the layer has too few output tiles to fill the GPU (inner levels of the UNet)
+  int nsplit = 1;
+  if (cfg_.fp16) {
+    const int ctas = ((max_m(p) + 127) / 128) * L.ntiles * L.nphase;
+    int ksmin = 1 << 30;
+    for (int ph = 0; ph < L.nphase; ++ph) ksmin = std::min(ksmin, L.ph_ksteps[ph]);
+    if (ctas * 2 <= num_sms_ && ksmin >= 4)
+      nsplit = std::max(1, std::min({ksmin / 2, kGenMaxSplit, (num_sms_ + ctas - 1) / ctas}));
+  }
+  const size_t per = (size_t)B * L.cout_chunks * Hout * Wout * 8;
+  int rc = need(raw_, per * nsplit * sizeof(float));
+  if (rc) return rc;
+  raw.p = reinterpret_cast<float*>(raw_.p);
+  raw.nsplit = nsplit;
+  raw.split_stride = per;
+  p.out = raw.p;
+  p.out_cs = (long long)Hout * Wout * 8;
+  p.out_bs = (long long)L.cout_chunks * p.out_cs;
+  p.out_chunk0 = 0;
+  p.out_mode = 1;
+  p.nsplit = nsplit;
+  p.split_stride = (long long)per;
+  p.act = kActNone;
+  const cudaError_t e = launch_conv(L, p, cfg_.fp16 != 0, st);
+  ++launches_;
+  if (e != cudaSuccess) {
+    err_ = std::string("conv launch failed: ") + cudaGetErrorString(e);
+    return -3;
+  }
+  return 0;
+}
+
+int I2INet::conv_final(const GenConv& L, GenView in, int B, int Hin, int Win, GenView out, int act, bool compact4,
+                       cudaStream_t st) {
+  const int Hout = L.out_h(Hin), Wout = L.out_h(Win);
+  GenConvParams p;
+  fill_params(p, L, in, B, Hin, Win, Hout, Wout, esz());
+  p.out = out.base;
+  p.out_cs = (long long)Hout * Wout * 8;
+  p.out_bs = (long long)out.CT * p.out_cs;
+  p.out_chunk0 = out.chunk0;
+  p.out_mode = compact4 ? 2 : 0;
+  p.act = act;
+  if (compact4 && !cfg_.fp16) {
+    err_ = "compact tiles exist in fp16 mode only";
+    return -1;
+  }
+  const cudaError_t e = launch_conv(L, p, cfg_.fp16 != 0, st);
+  ++launches_;
+  if (e != cudaSuccess) {
+    err_ = std::string("conv launch failed: ") + cudaGetErrorString(e);
+    return -3;
+  }
+  return 0;
+}
+
+int I2INet::norm_apply(const Norm* n, const Raw& raw, int B, int C, int H, int W, bool per_sample, int act_a, GenView out_a,
+                       int act_b, const GenView* out_b, const GenView* res, cudaStream_t st) {
+  const int chunks = (C + 7) / 8, HW = H * W;
+  const long long cs = (long long)HW * 8;
+  ApplyParams p;
+  memset(&p, 0, sizeof p);
+  p.raw = raw.p;
+  p.nsplit = raw.nsplit;
+  p.split_stride = (long long)raw.split_stride;
+  p.raw_cs = cs;
+  p.raw_bs = (long long)chunks * cs;
+  p.B = B; p.chunks = chunks; p.HW = HW;
+  if (n) {
+    if (n->running) {
+      p.ss = reinterpret_cast<const float2*>(n->d_ss);
+      p.ss_per_sample = 0;
+    } else {
+      // InstanceNorm2d, or BatchNorm2d in training mode (per image when every image is its own reference call)
+      const bool ps = cfg_.norm == 1 || per_sample;
+      const int nslices = std::max(1, std::min(64, (HW + 4095) / 4096));
+      int rc = need(stats_, (size_t)B * chunks * nslices * 16 * sizeof(double));
+      if (!rc) rc = need(ss_, (size_t)B * chunks * 8 * sizeof(float2));
+      if (rc) return rc;
+      norm_stats_kernel<<<dim3((unsigned)nslices, (unsigned)chunks, (unsigned)B), 256, 0, st>>>(
+          raw.p, raw.nsplit, (long long)raw.split_stride, p.raw_bs, p.raw_cs, HW, reinterpret_cast<double*>(stats_.p));
+      const int nthreads = (ps ? B : 1) * chunks * 8;
+      norm_finalize_kernel<<<(nthreads + 127) / 128, 128, 0, st>>>(reinterpret_cast<const double*>(stats_.p), B, chunks, nslices,
+                                                                  HW, ps ? 1 : 0, n->d_gamma, n->d_beta,
+                                                                  reinterpret_cast<float2*>(ss_.p));
+      launches_ += 2;
+      p.ss = reinterpret_cast<const float2*>(ss_.p);
+      p.ss_per_sample = 1;
+    }
+  }
+  p.out_a = reinterpret_cast<uint8_t*>(out_a.base) + (size_t)out_a.chunk0 * cs * esz();
+  p.a_cs = cs;
+  p.a_bs = (long long)out_a.CT * cs;
+  p.act_a = act_a;
+  if (out_b) {
+    p.out_b = reinterpret_cast<uint8_t*>(out_b->base) + (size_t)out_b->chunk0 * cs * esz();
+    p.b_cs = cs;
+    p.b_bs = (long long)out_b->CT * cs;
+    p.act_b = act_b;
+  }
+  if (res) {
+    p.res = reinterpret_cast<const uint8_t*>(res->base) + (size_t)res->chunk0 * cs * esz();
+    p.r_cs = cs;
+    p.r_bs = (long long)res->CT * cs;
+  }
+  const long long total = (long long)B * chunks * HW;
+  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, (long long)num_sms_ * 16);
+  if (cfg_.fp16)
+    norm_apply_kernel<__half><<<blocks, 256, 0, st>>>(p);
+  else
+    norm_apply_kernel<float><<<blocks, 256, 0, st>>>(p);
+  ++launches_;
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    err_ = std::string("norm launch failed: ") + cudaGetErrorString(e);
+    return -3;
+  }
+  return 0;
+}
+
+int I2INet::forward_unet(const void* in, int in_CT, int B, int H, int W, GenView out, bool compact4, bool per_sample,
+                         cudaStream_t st) {
+  const int D = cfg_.depth;
+  auto inner_nc = [&](int i) { return cfg_.ngf * std::min(1 << i, 8); };
+  int rc;
+  dbuf_.resize(D);
+  cat_.resize(D);
+  for (int i = 1; i < D; ++i) {   // x_i has inner_nc(i - 1) channels at (H >> i) x (W >> i)
+    const size_t n = (size_t)B * inner_nc(i - 1) * (H >> i) * (W >> i) * esz();
+    if ((rc = need(dbuf_[i], n)) || (rc = need(cat_[i], 2 * n))) return rc;
+  }
+  GenView cur{const_cast<void*>(in), in_CT, 0};
+  Raw raw;
+  // down: d_i = downconv_i(lrelu(x_i)) [+ norm]; lrelu(d_i) feeds the next level, relu(d_i) = relu(lrelu(d_i)) is the skip
+  // half of what the next level returns after the in-place ReLU in front of this level's transposed conv
+  for (int i = 0; i < D; ++i) {
+    const int hi = H >> i, wi = W >> i, C = inner_nc(i);
+    if ((rc = conv_raw(down_[i], cur, B, hi, wi, raw, st))) return rc;
+    if (i < D - 1) {
+      const GenView a = view(dbuf_[i + 1], C / 8, 0), skip = view(cat_[i + 1], 2 * C / 8, 0);
+      if ((rc = norm_apply(i > 0 ? &dnorm_[i] : nullptr, raw, B, C, hi / 2, wi / 2, per_sample, kActLrelu, a, kActRelu, &skip,
+                           nullptr, st)))
+        return rc;
+      cur = a;
+    } else {
+      if ((rc = need(inner_, (size_t)B * C * (hi / 2) * (wi / 2) * esz()))) return rc;
+      const GenView o = view(inner_, C / 8, 0);
+      if ((rc = norm_apply(nullptr, raw, B, C, hi / 2, wi / 2, per_sample, kActRelu, o, 0, nullptr, nullptr, st))) return rc;
+      cur = o;
+    }
+  }
+  // up: y_i = norm(upconv_i(relu(inner))) goes, already passed through the next ReLU, behind the skip half
+  for (int i = D - 1; i >= 1; --i) {
+    const int hin = H >> (i + 1), win = W >> (i + 1), X = inner_nc(i - 1);
+    if ((rc = conv_raw(up_[i], cur, B, hin, win, raw, st))) return rc;
+    const GenView o = view(cat_[i], 2 * X / 8, X / 8);
+    if ((rc = norm_apply(&unorm_[i], raw, B, X, H >> i, W >> i, per_sample, kActRelu, o, 0, nullptr, nullptr, st))) return rc;
+    cur = view(cat_[i], 2 * X / 8, 0);
+  }
+  return conv_final(up_[0], cur, B, H >> 1, W >> 1, out, kActTanh, compact4, st);
+}
+
+int I2INet::forward_resnet(const void* in, int in_CT, int B, int H, int W, GenView out, bool compact4, bool per_sample,
+                           cudaStream_t st) {
+  const int ngf = cfg_.ngf, nb = cfg_.depth;
+  const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4;
+  int rc;
+  rb_.resize(3);
+  if ((rc = need(a_, (size_t)B * ngf * H * W * esz())) || (rc = need(b_, (size_t)B * 2 * ngf * H1 * W1 * esz()))) return rc;
+  for (auto& b : rb_)
+    if ((rc = need(b, (size_t)B * 4 * ngf * H2 * W2 * esz()))) return rc;
+  Raw raw;
+  int li = 0;
+  GenView x{const_cast<void*>(in), in_CT, 0};
+  const GenView va = view(a_, ngf / 8, 0), vb = view(b_, 2 * ngf / 8, 0);
+  if ((rc = conv_raw(down_[li], x, B, H, W, raw, st))) return rc;
+  if ((rc = norm_apply(&dnorm_[li], raw, B, ngf, H, W, per_sample, kActRelu, va, 0, nullptr, nullptr, st))) return rc;
+  ++li;
+  if ((rc = conv_raw(down_[li], va, B, H, W, raw, st))) return rc;
+  if ((rc = norm_apply(&dnorm_[li], raw, B, 2 * ngf, H1, W1, per_sample, kActRelu, vb, 0, nullptr, nullptr, st))) return rc;
+  ++li;
+  int y = 0, t = 1, y2 = 2;
+  const int C = 4 * ngf;
+  if ((rc = conv_raw(down_[li], vb, B, H1, W1, raw, st))) return rc;
+  if ((rc = norm_apply(&dnorm_[li], raw, B, C, H2, W2, per_sample, kActRelu, view(rb_[y], C / 8, 0), 0, nullptr, nullptr, st)))
+    return rc;
+  ++li;
+  for (int b = 0; b < nb; ++b) {
+    const GenView vy = view(rb_[y], C / 8, 0), vt = view(rb_[t], C / 8, 0), vy2 = view(rb_[y2], C / 8, 0);
+    if ((rc = conv_raw(down_[li], vy, B, H2, W2, raw, st))) return rc;
+    if ((rc = norm_apply(&dnorm_[li], raw, B, C, H2, W2, per_sample, kActRelu, vt, 0, nullptr, nullptr, st))) return rc;
+    ++li;
+    if ((rc = conv_raw(down_[li], vt, B, H2, W2, raw, st))) return rc;
+    if ((rc = norm_apply(&dnorm_[li], raw, B, C, H2, W2, per_sample, kActNone, vy2, 0, nullptr, &vy, st))) return rc;
+    ++li;
+    std::swap(y, y2);
+  }
+  if ((rc = conv_raw(down_[li], view(rb_[y], C / 8, 0), B, H2, W2, raw, st))) return rc;
+  if ((rc = norm_apply(&dnorm_[li], raw, B, 2 * ngf, H1, W1, per_sample, kActRelu, vb, 0, nullptr, nullptr, st))) return rc;
+  ++li;
+  if ((rc = conv_raw(down_[li], vb, B, H1, W1, raw, st))) return rc;
+  if ((rc = norm_apply(&dnorm_[li], raw, B, ngf, H, W, per_sample, kActRelu, va, 0, nullptr, nullptr, st))) return rc;
+  ++li;
+  return conv_final(down_[li], va, B, H, W, out, kActTanh, compact4, st);
+}
+
+int I2INet::forward(const void* in, int in_CT, int B, int H, int W, GenView out, bool compact4, bool per_sample, cudaStream_t st,
+                    std::string& err) {
+  int rc = check_size(H, W, err);
+  if (rc) return rc;
+  err_.clear();
+  if (cfg_.kind == 2) {
+    GenView x{const_cast<void*>(in), in_CT, 0};
+    if (cfg_.sl_final) {
+      rc = conv_final(down_[0], x, B, H, W, out, cfg_.sl_act, compact4, st);
+    } else {
+      Raw raw;
+      rc = conv_raw(down_[0], x, B, H, W, raw, st);
+      if (!rc)
+        rc = norm_apply(cfg_.sl_norm ? &dnorm_[0] : nullptr, raw, B, cfg_.sl_cout, down_[0].out_h(H), down_[0].out_h(W),
+                        per_sample, cfg_.sl_act, out, 0, nullptr, nullptr, st);
+    }
+    if (rc) err = err_;
+    return rc;
+  }
+  rc = cfg_.kind == 0 ? forward_unet(in, in_CT, B, H, W, out, compact4, per_sample, st)
+                      : forward_resnet(in, in_CT, B, H, W, out, compact4, per_sample, st);
+  if (rc) err = err_;
+  return rc;
+}
+
+}  // namespace innfer

@@ -259,3 +259,37 @@ class PANEngine(RRDBEngine):
         c = N.PANCfg(cfg["in_nc"], cfg["out_nc"], cfg["nf"], cfg["unf"], cfg["nb"], cfg["scale"],
                      int(bool(cfg.get("self_attention", True))), int(bool(cfg.get("double_scpa", False))), int(self.fp16))
         N.check(self.lib.innfer_pan_create(ctypes.byref(c), self.index, ctypes.byref(self._h)))
+
+
+class _I2IEngine(RRDBEngine):
+    """Native handle for the image-to-image generators (scale 1).  ``cfg`` carries ``train``: BatchNorm2d in training
+    mode (run.py:297 keeps pix2pix that way) normalises with the statistics of the batch."""
+
+    _kind = 0
+    _depth_key = "num_downs"
+
+    @classmethod
+    def from_module(cls, module, device, fp16=True):
+        return cls.from_state_dict(module.state_dict(), dict(module.cfg, train=bool(module.training)), device, fp16)
+
+    def _create(self):
+        cfg = self.cfg
+        c = N.I2ICfg(self._kind, cfg["in_nc"], cfg["out_nc"], cfg["ngf"], cfg[self._depth_key],
+                     {"batch": 0, "instance": 1}[cfg["norm"]], int(bool(cfg.get("train", False))), int(self.fp16))
+        N.check(self.lib.innfer_i2i_create(ctypes.byref(c), self.index, ctypes.byref(self._h)))
+
+    def load(self, key, tensor):
+        if tensor.dim() == 0:      # BatchNorm2d.num_batches_tracked: bookkeeping, not arithmetic
+            return
+        super().load(key, tensor)
+
+
+class UNetEngine(_I2IEngine):
+    """architectures.UNet_arch.UnetGenerator (pix2pix)."""
+
+
+class ResNetGenEngine(_I2IEngine):
+    """architectures.ResNet_arch.ResnetGenerator (CycleGAN)."""
+
+    _kind = 1
+    _depth_key = "n_blocks"

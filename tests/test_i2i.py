@@ -101,6 +101,93 @@ def _u8(y):
     return U.tensor2np(y.detach().float().cpu(), denormalize=True)
 
 
+def _gen_conv(dev, cin, cout, h, w, k, stride=1, pad=1, transposed=False, out_pad=0, reflect=False, bias=True, norm=0, act=0,
+              final=False, n=1, fp32=False, seed=0):
+    """One layer through innfer_gen_conv (csrc/i2i.cu kernels) and the same layer in torch fp64 on the same operands."""
+    import torch.nn.functional as F
+    from innfer_b200 import _native as native
+    lib = native.load()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, cin, h, w, generator=g) * 2 - 1
+    wshape = (cin, cout, k, k) if transposed else (cout, cin, k, k)
+    fan = cin * k * k / (stride * stride if transposed else 1)
+    wgt = (torch.rand(*wshape, generator=g) * 2 - 1) * (2.0 / np.sqrt(fan))
+    b = (torch.rand(cout, generator=g) - 0.5) if bias else None
+    gam = torch.rand(cout, generator=g) + 0.5
+    bet = torch.rand(cout, generator=g) - 0.5
+    dt = torch.float32 if fp32 else torch.float16
+    xd = x.to(dev, dt)
+    xr = xd.double().cpu()
+    wr = wgt.double() if fp32 else wgt.half().double()
+    br = b.double() if bias else None
+    if transposed:
+        ref = F.conv_transpose2d(xr, wr, br, stride=stride, padding=pad, output_padding=out_pad)
+    elif reflect:
+        ref = F.conv2d(F.pad(xr, (pad,) * 4, mode="reflect"), wr, br, stride=stride)
+    else:
+        ref = F.conv2d(xr, wr, br, stride=stride, padding=pad)
+    if norm == 1:
+        ref = F.instance_norm(ref, eps=1e-5)
+    elif norm == 2:
+        ref = F.batch_norm(ref, None, None, gam.double(), bet.double(), training=True, eps=1e-5)
+    ref = {0: lambda t: t, 1: F.relu, 2: lambda t: F.leaky_relu(t, 0.2), 3: torch.tanh}[act](ref)
+    y = torch.empty(ref.shape, device=dev, dtype=dt)
+    wc = wgt.contiguous().numpy()
+    bc = b.contiguous().numpy() if bias else None
+    gc, bec = gam.contiguous().numpy(), bet.contiguous().numpy()
+    native.check(lib.innfer_gen_conv(xd.data_ptr(), n, cin, h, w, wc.ctypes.data, bc.ctypes.data if bias else None, cout, k,
+                                     stride, pad, int(transposed), out_pad, int(reflect), norm,
+                                     gc.ctypes.data if norm == 2 else None, bec.ctypes.data if norm == 2 else None, act,
+                                     int(final), y.data_ptr(), native.INNFER_F32 if fp32 else native.INNFER_F16, None))
+    torch.cuda.synchronize()
+    return y.double().cpu(), ref
+
+
+GEN_CONVS = [
+    # UNet: 4x4 stride-2 convolutions (first layer 3 channels; N tiles of 64 / 128; LeakyReLU from the apply kernel)
+    dict(cin=3, cout=64, h=64, w=64, k=4, stride=2, bias=False),
+    dict(cin=64, cout=128, h=32, w=48, k=4, stride=2, bias=False, norm=2, act=2, n=2),
+    dict(cin=16, cout=24, h=20, w=36, k=4, stride=2, norm=1, act=2),
+    # inner UNet levels: almost no pixels, long K -> split-K partial tensors
+    dict(cin=512, cout=512, h=4, w=4, k=4, stride=2, bias=False, act=1),
+    dict(cin=256, cout=256, h=2, w=2, k=4, stride=2, norm=2, act=1, n=3),
+    # UNet: 4x4 stride-2 transposed convolutions (four output phases of 2x2 taps)
+    dict(cin=1024, cout=512, h=2, w=2, k=4, stride=2, transposed=True, bias=False, norm=2, act=1, n=2),
+    dict(cin=128, cout=64, h=16, w=24, k=4, stride=2, transposed=True, bias=False, norm=2, act=1),
+    dict(cin=128, cout=3, h=32, w=32, k=4, stride=2, transposed=True, act=3, final=True),
+    # ResNet: reflection-padded 7x7 first / last convolutions, stride-2 3x3, reflection-padded 3x3, 3x3 transposed
+    dict(cin=3, cout=64, h=40, w=52, k=7, pad=3, reflect=True, norm=1, act=1),
+    dict(cin=64, cout=3, h=40, w=52, k=7, pad=3, reflect=True, act=3, final=True),
+    dict(cin=64, cout=128, h=40, w=52, k=3, stride=2, norm=1, act=1),
+    dict(cin=64, cout=128, h=13, w=17, k=3, stride=2, bias=False),
+    dict(cin=256, cout=256, h=16, w=20, k=3, reflect=True, norm=1, act=1, n=2),
+    dict(cin=32, cout=32, h=9, w=11, k=3, reflect=True, bias=False, norm=2),
+    dict(cin=256, cout=128, h=10, w=13, k=3, stride=2, transposed=True, out_pad=1, norm=1, act=1),
+    dict(cin=64, cout=32, h=12, w=12, k=3, stride=2, transposed=True, out_pad=1, bias=False, norm=2, act=1, n=2),
+    # more than one M tile per image and per phase, several images
+    dict(cin=64, cout=64, h=50, w=70, k=3, reflect=True, act=1, n=3),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", GEN_CONVS, ids=lambda c: "-".join("%s%s" % (k, v) for k, v in c.items()))
+def test_generator_layer_tcgen05(dev, cfg):
+    """Every layer type of the two generators on the tcgen05 kernel (cp.async gather, split-K, phases) + the
+    normalisation kernels against torch fp64 on the same fp16-rounded operands."""
+    y, ref = _gen_conv(dev, **cfg)
+    assert torch.isfinite(y).all()
+    tol = 2e-3 * max(1.0, ref.abs().max().item())
+    assert (y - ref).abs().max().item() <= tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [c for i, c in enumerate(GEN_CONVS) if i in (0, 2, 5, 7, 8, 9, 13, 15)],
+                         ids=lambda c: "-".join("%s%s" % (k, v) for k, v in c.items()))
+def test_generator_layer_fp32_kernel(dev, cfg):
+    y, ref = _gen_conv(dev, fp32=True, **cfg)
+    assert ((y - ref).abs().max() / ref.abs().max()).item() <= 1e-5
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("fp16", [True, False])
 @pytest.mark.parametrize("tag,family,kw,seed,shape,train", SMALL)
