@@ -47,6 +47,8 @@ WORKLOADS = {
     "chain": {"H": 720, "W": 1280, "chain": [1, 4], "cf": True, "tiles": 84,
               "name": "chained 1x RRDB (23 blocks) + 4x RRDB (23 blocks) fp16 with -cf colour fix, synthetic 1280x720 "
                       "frames, chop_forward 200px tiles step 0.5 (84 + 84 tiles/frame)"},
+    "i2i": {"name": "pix2pix unet_256 (train-mode BatchNorm, whole image) and CycleGAN resnet_9blocks (InstanceNorm), ngf 64, "
+                    "random-init, fp16, synthetic 256x256 and 1024x1024 images, batch 1; headline = resnet_9blocks at 1024x1024"},
 }
 H, W = WORKLOADS["frame"]["H"], WORKLOADS["frame"]["W"]
 WORKLOAD = WORKLOADS["frame"]["name"]
@@ -471,6 +473,71 @@ def run_chain(args, dev, warm):
     print(json.dumps(line), flush=True)
 
 
+def run_i2i(args, dev, warm):
+    """BASELINE configs[4]: the two image-to-image generators at 256x256 and 1024x1024 through the nn.Module mirrors (the
+    objects run.Model holds); beside each the same module's torch ops on this GPU (PyTorch-dispatched cuDNN, fp16)."""
+    from innfer_b200 import _native as N
+    from innfer_b200 import synth
+    from innfer_b200.architectures import get_network
+    from innfer_b200.utils.defaults import get_network_G_config
+    torch.backends.cudnn.benchmark = True
+    peaks, peak_src = measured_peaks()
+    peak = float(peaks["bf16_tflops_sustained"])
+    cases, head = [], None
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    launches0 = N.kernel_launches()
+    for family, arch in (("unet", "unet_256"), ("resnet", "resnet_9blocks")):
+        torch.manual_seed(0)
+        net = get_network(get_network_G_config({"type": arch}, 1)).train(family == "unet").to(dev).half()
+        for size in (256, 1024):
+            x_host = (torch.rand(1, 3, size, size, generator=torch.Generator().manual_seed(size)) * 2 - 1).half().pin_memory()
+            y_host = torch.empty(1, 3, size, size, dtype=torch.float16).pin_memory()
+            x = x_host.to(dev)
+            flop = synth.i2i_flop(family, size, size)
+            rec = {"net": arch, "size": size, "flop": flop}
+            with torch.no_grad():
+                for name, fn in (("ours", lambda t: net(t)), ("torch_gpu", lambda t: net.model(t.clone()))):
+                    for _ in range(max(warm, 3)):
+                        fn(x)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(args.steps):
+                        y = fn(x)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / args.steps
+                    rec[name] = {"ms": ms, "mpix_s": size * size / ms / 1e3, "tflops": flop / ms / 1e9}
+                    if name == "ours":
+                        rec["frac_of_sustained_tensor_peak"] = flop / ms / 1e9 / peak
+                        t0 = time.perf_counter()
+                        for _ in range(args.steps):       # end to end: pinned host tensor in, pinned host tensor out
+                            y_host.copy_(net(x_host.to(dev, non_blocking=True)), non_blocking=True)
+                            torch.cuda.current_stream().synchronize()
+                        rec["e2e_ms"] = (time.perf_counter() - t0) * 1e3 / args.steps
+                rec["ours_over_torch_gpu"] = rec["torch_gpu"]["ms"] / rec["ours"]["ms"]
+            cases.append(rec)
+            if family == "resnet" and size == 1024:
+                head = rec
+        net.invalidate_engine()
+    clocks = sampler.stop()
+    line = {"metric": "output Mpix/s", "value": head["ours"]["mpix_s"], "unit": "Mpix/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(warm, 3), "ms_per_step": head["ours"]["ms"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOADS["i2i"]["name"],
+                       "l2": "activations of one 1024x1024 image (up to 134 MB per tensor) exceed L2 at the outer layers; "
+                             "256x256 images are L2 resident (launch-latency bound)"},
+            "e2e": {"value": 1024 * 1024 / head["e2e_ms"] / 1e3, "unit": "Mpix/s", "ms_per_step": head["e2e_ms"],
+                    "h2d_bytes_per_step": 3 * 1024 * 1024 * 2, "d2h_bytes_per_step": 3 * 1024 * 1024 * 2},
+            "gpu_launches": int(N.kernel_launches() - launches0), "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": head["ours"]["tflops"], "peak": peak, "unit": "TFLOP/s",
+                         "frac": head["ours"]["tflops"] / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "all kernels of one resnet_9blocks forward at 1024x1024 (convolutions + normalisation)"},
+            "cases": cases, "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -510,6 +577,11 @@ def main():
         if world > 1:
             raise SystemExit("--workload chain is a single-GPU workload")
         run_chain(args, dev, warm)
+        return
+    if args.workload == "i2i":
+        if world > 1:
+            raise SystemExit("--workload i2i is a single-GPU workload")
+        run_i2i(args, dev, warm)
         return
     dist = None
     if world > 1:

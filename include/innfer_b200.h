@@ -280,6 +280,10 @@ int innfer_gen_conv(const void* x, int n, int Cin, int hgt, int wid, const float
                     int stride, int pad, int transposed, int out_pad, int reflect, int norm, const float* norm_weight,
                     const float* norm_bias, int act, int final_path, void* y, int dtype, void* stream);
 
+/* launches of the halo-tile variant of the generator convolution by this process (the parity tests use it to know
+ * which of the two tensor-core kernels served a layer; INNFER_I2I_HALO=0|2 in the environment forces the choice) */
+uint64_t innfer_debug_i2i_halo_launches(void);
+
 /* ---- -cf colour correction: replaces color_fix (utils/utils.py:278-315) with srgb2linear /
  *      linear2srgb (utils/colors.py:29-60), cv2.resize(INTER_CUBIC) and cv2.GaussianBlur((3,3),0).
  *      lr: device uint8 [h][w][3]; sr: device uint8 [H][W][3]; out: device uint8 [H][W][3].

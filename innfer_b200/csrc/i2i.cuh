@@ -46,6 +46,14 @@ struct GenConv {
   __half* d_w16 = nullptr;   // [phase][ntile][kstep][8 K-chunks][NT][8] fp16 (tensor-core kernel)
   float* d_w32 = nullptr;    // [phase][tap][cin_chunks * 8][cout_chunks * 8] fp32 (direct kernel, -no_fp16 mode)
   float* d_bias = nullptr;   // [ntiles * NT] (zeros when the layer has no bias)
+  // halo-tile kernel (gen_conv_halo_kernel): per phase the taps address up to four parity planes of one gathered input
+  // tile; plane p holds input pixels (istep * (y0 + r + pl_r0) + pl_py, istep * (x0 + c + pl_c0) + pl_px)
+  int NTh = 0, ntiles_h = 0, nslabs = 0;    // N tile (bounded by the shared-memory stage), ceil(cin_chunks / 2)
+  int h_nplanes[kGenMaxPhases] = {}, h_rext[kGenMaxPhases] = {}, h_cext[kGenMaxPhases] = {};
+  int8_t h_pl_py[kGenMaxPhases][4] = {}, h_pl_px[kGenMaxPhases][4] = {}, h_pl_r0[kGenMaxPhases][4] = {}, h_pl_c0[kGenMaxPhases][4] = {};
+  int8_t h_tap_pl[kGenMaxPhases][kGenMaxTaps] = {}, h_tap_dr[kGenMaxPhases][kGenMaxTaps] = {}, h_tap_dc[kGenMaxPhases][kGenMaxTaps] = {};
+  size_t ph_woffh[kGenMaxPhases] = {};
+  __half* d_w16h = nullptr;  // [phase][ntile][16-channel slab][tap][2 K-chunks][NTh][8] fp16
   int out_h(int Hin) const {
     return transposed ? (Hin - 1) * stride - 2 * pad + k + out_pad : (Hin + 2 * pad - k) / stride + 1;
   }
@@ -73,6 +81,8 @@ struct I2ICfg {
 
 // key lookup into the loaded state dict: returns the data and fills `shape`, or nullptr
 using ParamLookup = std::function<const float*(const std::string& key, std::vector<int64_t>& shape)>;
+
+uint64_t i2i_halo_launches();   // launches of the halo-tile kernel by this process (tests: which kernel served a layer)
 
 class I2INet {
  public:

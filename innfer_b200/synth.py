@@ -56,3 +56,27 @@ def bytes_per_lr_pixel(scale=4, nb=23, nf=64, in_nc=3, out_nc=3):
     b += res * 2 * nf * e                                             # HR_conv0
     b += res * (nf + max(out_nc, 4)) * e                              # HR_conv1 (compact 4-channel tile pixels)
     return b
+
+
+def i2i_flop(kind, H, W, ngf=64, depth=None, in_nc=3, out_nc=3):
+    """Algorithmic conv FLOPs of one H x W image through UnetGenerator (kind 'unet', depth = num_downs, default 8) or
+    ResnetGenerator (kind 'resnet', depth = n_blocks, default 9): 2 x MACs of every (transposed) convolution
+    (architectures/UNet_arch.py:47-66, ResNet_arch.py:55-91)."""
+    mac = 0
+    if kind == "unet":
+        D = 8 if depth is None else depth
+        inner = [ngf * min(2 ** i, 8) for i in range(D)]
+        for i in range(D):
+            outer = out_nc if i == 0 else inner[i - 1]
+            cin = in_nc if i == 0 else outer
+            px = (H >> (i + 1)) * (W >> (i + 1))          # pixels at the bottom of level i
+            mac += px * 16 * cin * inner[i]               # 4x4 stride-2 conv
+            mac += px * 16 * (inner[i] if i == D - 1 else 2 * inner[i]) * outer   # 4x4 stride-2 transposed conv
+        return 2 * mac
+    nb = 9 if depth is None else depth
+    px = H * W
+    mac += px * 49 * in_nc * ngf + px * 49 * ngf * out_nc
+    mac += (px // 4) * 9 * ngf * 2 * ngf + (px // 16) * 9 * 2 * ngf * 4 * ngf
+    mac += nb * 2 * (px // 16) * 9 * 4 * ngf * 4 * ngf
+    mac += (px // 16) * 9 * 4 * ngf * 2 * ngf + (px // 4) * 9 * 2 * ngf * ngf
+    return 2 * mac

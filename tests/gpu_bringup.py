@@ -570,11 +570,69 @@ def stage_time():
     return True
 
 
+def _i2i_net(family, ngf=64, seed=0):
+    from innfer_b200.architectures import get_network
+    from innfer_b200.utils.defaults import get_network_G_config
+    torch.manual_seed(seed)
+    net = get_network(get_network_G_config({"type": "unet_256" if family == "unet" else "resnet_9blocks", "ngf": ngf}, 1))
+    return net.train(family == "unet")     # run.py:295-309: pix2pix stays in training mode, cyclegan in eval mode
+
+
+def stage_i2i_time():
+    """BASELINE configs[4]: unet_256 and resnet_9blocks (ngf 64) at 256x256 and 1024x1024, fp16, batch 1: device time of
+    the engine's forward, and of the same module through torch's own CUDA ops (cuDNN) on the same GPU."""
+    from innfer_b200 import synth
+    torch.backends.cudnn.benchmark = True
+    for family in ("unet", "resnet"):
+        net = _i2i_net(family).to(dev).half()
+        for size in (256, 1024):
+            x = (torch.rand(1, 3, size, size, generator=torch.Generator().manual_seed(1)) * 2 - 1).to(dev, torch.float16)
+            flop = synth.i2i_flop(family, size, size)
+            res = {}
+            with torch.no_grad():
+                for name, fn in (("ours", lambda t: net(t)), ("torch", lambda t: net.model(t.clone()))):
+                    for _ in range(3):
+                        y = fn(x)
+                    torch.cuda.synchronize()
+                    l0 = N.kernel_launches()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    iters = 20
+                    e0.record()
+                    for _ in range(iters):
+                        y = fn(x)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / iters
+                    res[name] = (ms, y.float())
+                    print("i2i %s %dx%d fp16 %-5s: %8.3f ms  %7.1f TFLOP/s  (%d launches/forward)" %
+                          (family, size, size, name, ms, flop / ms / 1e9, (N.kernel_launches() - l0) // iters))
+            d = (res["ours"][1] - res["torch"][1]).abs().max().item()
+            print("i2i %s %dx%d: max |ours - torch fp16| = %.4f, speed-up over torch/cuDNN %.2fx" %
+                  (family, size, size, d, res["torch"][0] / res["ours"][0]))
+        net.invalidate_engine()
+        del net
+    return True
+
+
+def stage_i2i_prof():
+    """One forward of each generator at 1024x1024 (after a warm-up at the same size) for ncu launch lists."""
+    for family in ("unet", "resnet"):
+        net = _i2i_net(family).to(dev).half()
+        x = (torch.rand(1, 3, 1024, 1024, generator=torch.Generator().manual_seed(1)) * 2 - 1).to(dev, torch.float16)
+        with torch.no_grad():
+            net(x)
+            torch.cuda.synchronize()
+            net(x)
+        torch.cuda.synchronize()
+        net.invalidate_engine()
+    return True
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--stage", required=True)
     a = ap.parse_args()
     t0 = time.time()
-    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "trace_up": stage_trace_up, "ppon": stage_ppon, "ppon_prof": stage_ppon_prof, "ppon_time": stage_ppon_time, "pan_time": stage_pan_time, "srres_time": stage_srres_time, "lat": stage_lat, "pan_prof": stage_pan_prof, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3}[a.stage]()
+    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "trace_up": stage_trace_up, "ppon": stage_ppon, "ppon_prof": stage_ppon_prof, "ppon_time": stage_ppon_time, "pan_time": stage_pan_time, "srres_time": stage_srres_time, "lat": stage_lat, "pan_prof": stage_pan_prof, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3, "i2i_time": stage_i2i_time, "i2i_prof": stage_i2i_prof}[a.stage]()
     print("STAGE %s %s (%.1fs)" % (a.stage, "OK" if ok else "FAILED", time.time() - t0))
     sys.exit(0 if ok else 1)

@@ -166,15 +166,33 @@ GEN_CONVS = [
     dict(cin=64, cout=32, h=12, w=12, k=3, stride=2, transposed=True, out_pad=1, bias=False, norm=2, act=1, n=2),
     # more than one M tile per image and per phase, several images
     dict(cin=64, cout=64, h=50, w=70, k=3, reflect=True, act=1, n=3),
+    # halo-tile geometry: odd chunk count (second K-chunk of the last slab empty), ragged right / bottom edges, N tile 128 x 2
+    dict(cin=24, cout=40, h=37, w=45, k=3, reflect=True, norm=1, act=1),
+    dict(cin=40, cout=256, h=70, w=41, k=4, stride=2, bias=False, norm=2, act=2),
+    dict(cin=136, cout=72, h=21, w=19, k=4, stride=2, transposed=True, norm=2, act=1, n=2),
+    dict(cin=8, cout=8, h=33, w=130, k=7, pad=3, reflect=True, act=3, final=True, n=2),
 ]
 
 
+# layers of GEN_CONVS whose geometry the halo-tile kernel takes (at least 8 x 8 output pixels per phase)
+HALO_CASES = (0, 1, 2, 6, 7, 8, 9, 10, 12, 13, 14, 15, 16, 17, 18, 19, 20)
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["im2col", "halo"])
 @pytest.mark.parametrize("cfg", GEN_CONVS, ids=lambda c: "-".join("%s%s" % (k, v) for k, v in c.items()))
-def test_generator_layer_tcgen05(dev, cfg):
-    """Every layer type of the two generators on the tcgen05 kernel (cp.async gather, split-K, phases) + the
-    normalisation kernels against torch fp64 on the same fp16-rounded operands."""
+def test_generator_layer_tcgen05(dev, cfg, kernel, monkeypatch):
+    """Every layer type of the two generators on both tcgen05 kernels -- im2col gather with split-K, and the halo-tile
+    variant (parity planes for stride 2, phases for transposed convolutions) -- + the normalisation kernels against
+    torch fp64 on the same fp16-rounded operands."""
+    from innfer_b200 import _native as native
+    idx = GEN_CONVS.index(cfg)
+    if kernel == "halo" and idx not in HALO_CASES:
+        pytest.skip("too few output pixels for 16 x 8 patches: served by the im2col kernel")
+    monkeypatch.setenv("INNFER_I2I_HALO", "2" if kernel == "halo" else "0")
+    n0 = native.load().innfer_debug_i2i_halo_launches()
     y, ref = _gen_conv(dev, **cfg)
+    assert (native.load().innfer_debug_i2i_halo_launches() - n0 == 1) == (kernel == "halo")
     assert torch.isfinite(y).all()
     tol = 2e-3 * max(1.0, ref.abs().max().item())
     assert (y - ref).abs().max().item() <= tol
