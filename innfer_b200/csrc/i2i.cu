@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 
 #include "ptx.cuh"
 
@@ -56,6 +57,10 @@ struct GenConvParams {
   int bands[kGenMaxPhases], cps[kGenMaxPhases], nplanes[kGenMaxPhases], Rpl[kGenMaxPhases], Wpl[kGenMaxPhases];
   int8_t pl_py[kGenMaxPhases][4], pl_px[kGenMaxPhases][4], pl_r0[kGenMaxPhases][4], pl_c0[kGenMaxPhases][4];
   uint16_t tap_aoff[kGenMaxPhases][kGenMaxTaps];   // 16-byte units inside one K-chunk block of the gathered tile
+  // fused normalisation statistics (raw outputs only): per CTA tile the per-channel sum and sum of squares of its valid
+  // pixels go to stats[((b * out_nchunks + chunk) * stat_slices + slice) * 16 + {e, 8 + e}], slice = slice0[phase] + tile
+  double* stats;
+  int stat_slices, slice0[kGenMaxPhases];
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -296,7 +301,8 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tfull_bar = empty_bar + S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
-  int32_t* tbl = reinterpret_cast<int32_t*>(smem + (size_t)S * STAGE + 128);
+  float* red = reinterpret_cast<float*>(smem + (size_t)S * STAGE + 128);            // [2][4 warps][32]: statistics exchange
+  int32_t* tbl = reinterpret_cast<int32_t*>(smem + (size_t)S * STAGE + 128 + 1024);
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 128 + 1);
@@ -373,12 +379,17 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
     const int oyp = y0 + r;
     const int oy = oyp * p.ostep + p.py[ph];
     const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int j = 0; j < jeff; ++j) {
-      const int oxp = x0 + 8 * j + c;
-      const bool valid = oyp < Hp && oxp < Wp;
-      const size_t pix = (size_t)oy * p.Wout + (size_t)(oxp * p.ostep + p.px[ph]);
+    const bool want_stats = p.stats != nullptr;
+    int grp = 0;
 #pragma unroll 1
-      for (int c0 = 0; c0 < NT; c0 += 16) {
+    for (int c0 = 0; c0 < NT; c0 += 16, ++grp) {
+      float sq[32];   // [0, 16): sums of this thread's pixels (one per sub-patch), [16, 32): sums of squares
+#pragma unroll
+      for (int e = 0; e < 32; ++e) sq[e] = 0.f;
+      for (int j = 0; j < jeff; ++j) {
+        const int oxp = x0 + 8 * j + c;
+        const bool valid = oyp < Hp && oxp < Wp;
+        const size_t pix = (size_t)oy * p.Wout + (size_t)(oxp * p.ostep + p.px[ph]);
         uint32_t v[16];
         tmem_ld16(tacc + (uint32_t)(j * NT + c0), v);
         tmem_ld_wait();
@@ -389,7 +400,11 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
           if (gc >= p.out_nchunks) continue;
           float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = apply_act(__uint_as_float(v[hh * 8 + e]) + p.bias[gc * 8 + e], p.act);
+          for (int e = 0; e < 8; ++e) {
+            f[e] = apply_act(__uint_as_float(v[hh * 8 + e]) + p.bias[gc * 8 + e], p.act);
+            sq[hh * 8 + e] += f[e];
+            sq[16 + hh * 8 + e] = fmaf(f[e], f[e], sq[16 + hh * 8 + e]);
+          }
           if (p.out_mode == 1) {
             float* op = reinterpret_cast<float*>(p.out) + (size_t)b * p.out_bs + (size_t)(p.out_chunk0 + gc) * p.out_cs + pix * 8;
             *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
@@ -411,6 +426,31 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
             o.x = *reinterpret_cast<uint32_t*>(&h0);
             o.y = *reinterpret_cast<uint32_t*>(&h1);
             *reinterpret_cast<uint2*>(op) = o;
+          }
+        }
+      }
+      if (want_stats) {
+        // transpose-reduce: 32 values per lane -> lane l holds the warp's total of value l (31 shuffles, fixed order)
+#pragma unroll
+        for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            const float send = upper ? sq[i] : sq[i + n];
+            const float keep = upper ? sq[i + n] : sq[i];
+            sq[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        float* rb = red + (grp & 1) * 128;
+        rb[warp * 32 + lane] = sq[0];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 0) {
+          const float tot = ((rb[lane] + rb[32 + lane]) + rb[64 + lane]) + rb[96 + lane];
+          const int ch = (int)blockIdx.y * NT + c0 + (lane & 15);
+          const int chunk = ch >> 3;
+          if (chunk < p.out_nchunks) {
+            const int slice = p.slice0[ph] + band * cps + cp;
+            p.stats[(((size_t)b * p.out_nchunks + chunk) * p.stat_slices + slice) * 16 + (lane < 16 ? 0 : 8) + (ch & 7)] = (double)tot;
           }
         }
       }
@@ -561,19 +601,18 @@ __global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict
   }
 }
 
-// one warp per (image, channel) [per_sample] or per channel [batch statistics]: lanes take the partial sums in a strided
-// order, then a shuffle tree -- a fixed summation order, so the statistics are bit-reproducible.
-// (scale, shift) of y = x * scale + shift.
+// one 128-thread block per (image, channel) [per_sample] or per channel [batch statistics]: threads take the partial sums
+// in a strided order, then a shuffle tree and a 4-term sum -- a fixed summation order, so the statistics are
+// bit-reproducible.  (scale, shift) of y = x * scale + shift.
 __global__ void __launch_bounds__(128) norm_finalize_kernel(const double* __restrict__ part, int B, int chunks, int nslices, int HW,
                                                             int per_sample, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float2* __restrict__ ss) {
   const int C8 = chunks * 8;
-  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (idx >= (per_sample ? B * C8 : C8)) return;
+  const int idx = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = idx % C8, b0 = per_sample ? idx / C8 : 0, b1 = per_sample ? b0 + 1 : B;
   double S = 0.0, Q = 0.0;
   const int n_part = (b1 - b0) * nslices;
-  for (int i = lane; i < n_part; i += 32) {
+  for (int i = threadIdx.x; i < n_part; i += 128) {
     const int b = b0 + i / nslices, sl = i - (i / nslices) * nslices;
     const double* pp = part + (((size_t)b * chunks + c / 8) * nslices + sl) * 16;
     S += pp[c % 8];
@@ -584,7 +623,15 @@ __global__ void __launch_bounds__(128) norm_finalize_kernel(const double* __rest
     S += __shfl_xor_sync(0xffffffffu, S, off);
     Q += __shfl_xor_sync(0xffffffffu, Q, off);
   }
-  if (lane != 0) return;
+  __shared__ double sh[4][2];
+  if (lane == 0) {
+    sh[warp][0] = S;
+    sh[warp][1] = Q;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  S = ((sh[0][0] + sh[1][0]) + sh[2][0]) + sh[3][0];
+  Q = ((sh[0][1] + sh[1][1]) + sh[2][1]) + sh[3][1];
   const double n = (double)(b1 - b0) * (double)HW;
   const double mean = S / n;
   double var = Q / n - mean * mean;
@@ -708,6 +755,7 @@ cudaError_t launch_halo_s(const GenConvParams& p, dim3 grid, size_t smem, cudaSt
 template <int NT>
 cudaError_t launch_halo(const GenConvParams& p, int stages, dim3 grid, size_t smem, cudaStream_t st) {
   switch (stages) {
+    case 1: return launch_halo_s<NT, 1>(p, grid, smem, st);
     case 2: return launch_halo_s<NT, 2>(p, grid, smem, st);
     case 3: return launch_halo_s<NT, 3>(p, grid, smem, st);
     default: return launch_halo_s<NT, 4>(p, grid, smem, st);
@@ -1194,20 +1242,44 @@ bool halo_geometry_ok(const GenConv& L, const GenConvParams& p) {
 bool halo_setup(const GenConv& L, GenConvParams& p, int num_sms, dim3& grid, size_t& smem, int& stages) {
   const int mode = halo_mode();
   if (mode == 0 || p.nsplit != 1 || !halo_geometry_ok(L, p)) return false;
-  int J = L.NTh >= 128 ? 2 : 4, max_tiles = 0;
+  // sub-patches per CTA: 4 x NT accumulator columns must fit TMEM's 512.  With NT = 128 that is the whole TMEM (one CTA per
+  // SM, no second CTA to hide the epilogue) but it halves the weight bytes per MMA, which is what bounds the wide layers
+  // (every CTA re-reads the slab's weights from L2): taken when there is more than a wave of such tiles and it fits.
+  int J = 4, max_tiles = 0;
+  if (L.NTh >= 128) {
+    long long tiles4 = 0;
+    for (int ph = 0; ph < L.nphase; ++ph) tiles4 += (long long)p.B * ((p.Hp[ph] + 15) / 16) * ((p.Wp[ph] + 31) / 32) * L.ntiles_h;
+    const char* ej = getenv("INNFER_I2I_J");
+    J = ej ? atoi(ej) : 2;   // measured (resnet_9blocks 1024x1024): J = 4 is 1.0 ms per forward SLOWER than J = 2
+    (void)tiles4;
+    if (J != 4) J = 2;
+  }
   for (int ph = 0; ph < L.nphase; ++ph) J = std::min(J, (p.Wp[ph] + 7) / 8);
-  size_t stage = 0, tbl = 0;
+  size_t stage = 0, tail = 0;
+  for (;;) {
+    stage = 0;
+    size_t tbl = 0;
+    max_tiles = 0;
+    bool ok = true;
+    for (int ph = 0; ph < L.nphase; ++ph) {
+      p.bands[ph] = (p.Hp[ph] + 15) / 16;
+      p.cps[ph] = (p.Wp[ph] + 8 * J - 1) / (8 * J);
+      max_tiles = std::max(max_tiles, p.B * p.bands[ph] * p.cps[ph]);
+      p.nplanes[ph] = L.h_nplanes[ph];
+      p.Rpl[ph] = 16 + L.h_rext[ph];
+      p.Wpl[ph] = 8 * J + L.h_cext[ph];
+      const size_t npos = (size_t)p.nplanes[ph] * p.Rpl[ph] * p.Wpl[ph];
+      if (npos > 16000) ok = false;
+      stage = std::max(stage, ((2 * npos * 16 + 127) & ~(size_t)127) + (size_t)L.ph_ntaps[ph] * 2 * L.NTh * 16);
+      tbl = std::max(tbl, npos * 4);
+    }
+    stage = (stage + 127) & ~(size_t)127;
+    tail = 128 + 1024 + ((tbl + 127) & ~(size_t)127);
+    if (ok && (L.nslabs == 1 ? 1 : 2) * stage + tail <= kSmemMax) break;
+    if (J <= 1) return false;
+    J /= 2;   // a narrower patch needs a smaller tile
+  }
   for (int ph = 0; ph < L.nphase; ++ph) {
-    p.bands[ph] = (p.Hp[ph] + 15) / 16;
-    p.cps[ph] = (p.Wp[ph] + 8 * J - 1) / (8 * J);
-    max_tiles = std::max(max_tiles, p.B * p.bands[ph] * p.cps[ph]);
-    p.nplanes[ph] = L.h_nplanes[ph];
-    p.Rpl[ph] = 16 + L.h_rext[ph];
-    p.Wpl[ph] = 8 * J + L.h_cext[ph];
-    const size_t npos = (size_t)p.nplanes[ph] * p.Rpl[ph] * p.Wpl[ph];
-    if (npos > 16000) return false;
-    stage = std::max(stage, ((2 * npos * 16 + 127) & ~(size_t)127) + (size_t)L.ph_ntaps[ph] * 2 * L.NTh * 16);
-    tbl = std::max(tbl, npos * 4);
     for (int pl = 0; pl < 4; ++pl) {
       p.pl_py[ph][pl] = L.h_pl_py[ph][pl];
       p.pl_px[ph][pl] = L.h_pl_px[ph][pl];
@@ -1219,14 +1291,20 @@ bool halo_setup(const GenConv& L, GenConvParams& p, int num_sms, dim3& grid, siz
                                      L.h_tap_dc[ph][t]);
   }
   if (mode != 2 && max_tiles * L.ntiles_h * L.nphase * 4 < num_sms) return false;   // too few CTAs: im2col kernel
-  stage = (stage + 127) & ~(size_t)127;
-  const size_t tail = 128 + ((tbl + 127) & ~(size_t)127);
-  if (2 * stage + tail > kSmemMax) return false;
-  if (2 * stage + tail <= kSmemHalf)
-    stages = 2;
-  else
-    stages = (int)std::min<size_t>(4, (kSmemMax - tail) / stage);
-  stages = std::max(2, std::min(stages, std::max(2, L.nslabs)));
+  p.stat_slices = 0;
+  for (int ph = 0; ph < L.nphase; ++ph) {
+    p.slice0[ph] = p.stat_slices;
+    p.stat_slices += p.bands[ph] * p.cps[ph];
+  }
+  if (L.nslabs == 1) {
+    stages = 1;       // a single 16-channel slab (the 3-channel first layer): nothing to pipeline, keep the CTA small
+  } else {
+    if (2 * stage + tail <= kSmemHalf && J * L.NTh <= 256)
+      stages = 2;     // two CTAs per SM: one CTA's epilogue overlaps the other's main loop
+    else
+      stages = (int)std::min<size_t>(4, (kSmemMax - tail) / stage);
+    stages = std::max(2, std::min(stages, L.nslabs));
+  }
   p.J = J;
   p.nslabs = L.nslabs;
   p.stage_bytes = (unsigned)stage;
@@ -1240,13 +1318,22 @@ bool halo_setup(const GenConv& L, GenConvParams& p, int num_sms, dim3& grid, siz
   return true;
 }
 
-cudaError_t launch_conv(const GenConv& L, GenConvParams& p, bool fp16, int num_sms, cudaStream_t st) {
+// `stats_alloc` (optional): called with the number of doubles the fused statistics of this launch need; returns the
+// buffer (or null: no fused statistics).  *stat_slices receives the slice count when the statistics were fused.
+cudaError_t launch_conv(const GenConv& L, GenConvParams& p, bool fp16, int num_sms, cudaStream_t st,
+                        const std::function<double*(size_t)>* stats_alloc = nullptr, int* stat_slices = nullptr) {
+  if (stat_slices) *stat_slices = 0;
+  p.stats = nullptr;
   if (fp16) {
     dim3 hgrid;
     size_t hsmem = 0;
     int hstages = 0;
     if (halo_setup(L, p, num_sms, hgrid, hsmem, hstages)) {
       g_halo_launches.fetch_add(1, std::memory_order_relaxed);
+      if (stats_alloc && p.out_mode == 1) {
+        p.stats = (*stats_alloc)((size_t)p.B * p.out_nchunks * p.stat_slices * 16);
+        if (p.stats && stat_slices) *stat_slices = p.stat_slices;
+      }
       switch (L.NTh) {
         case 16: return launch_halo<16>(p, hstages, hgrid, hsmem, st);
         case 32: return launch_halo<32>(p, hstages, hgrid, hsmem, st);
@@ -1273,7 +1360,7 @@ cudaError_t launch_conv(const GenConv& L, GenConvParams& p, bool fp16, int num_s
 
 }  // namespace
 
-int I2INet::conv_raw(const GenConv& L, GenView in, int B, int Hin, int Win, Raw& raw, cudaStream_t st) {
+int I2INet::conv_raw(const GenConv& L, GenView in, int B, int Hin, int Win, Raw& raw, cudaStream_t st, bool want_stats) {
   const int Hout = L.out_h(Hin), Wout = L.out_h(Win);
   GenConvParams p;
   fill_params(p, L, in, B, Hin, Win, Hout, Wout, esz());
@@ -1300,7 +1387,16 @@ int I2INet::conv_raw(const GenConv& L, GenView in, int B, int Hin, int Win, Raw&
   p.nsplit = nsplit;
   p.split_stride = (long long)per;
   p.act = kActNone;
-  const cudaError_t e = launch_conv(L, p, cfg_.fp16 != 0, num_sms_, st);
+  // statistics of the norm layer that follows, fused into the halo kernel's epilogue when that kernel takes the layer
+  static const bool fuse = !(getenv("INNFER_I2I_FUSED_STATS") && atoi(getenv("INNFER_I2I_FUSED_STATS")) == 0);
+  int alloc_rc = 0;
+  const std::function<double*(size_t)> alloc = [&](size_t n) -> double* {
+    alloc_rc = need(stats_, n * sizeof(double));
+    return alloc_rc ? nullptr : reinterpret_cast<double*>(stats_.p);
+  };
+  raw.stat_slices = 0;
+  const cudaError_t e = launch_conv(L, p, cfg_.fp16 != 0, num_sms_, st, want_stats && fuse ? &alloc : nullptr, &raw.stat_slices);
+  if (alloc_rc) return alloc_rc;
   ++launches_;
   if (e != cudaSuccess) {
     err_ = std::string("conv launch failed: ") + cudaGetErrorString(e);
@@ -1352,17 +1448,19 @@ int I2INet::norm_apply(const Norm* n, const Raw& raw, int B, int C, int H, int W
     } else {
       // InstanceNorm2d, or BatchNorm2d in training mode (per image when every image is its own reference call)
       const bool ps = cfg_.norm == 1 || per_sample;
-      const int nslices = std::max(1, std::min(64, (HW + 4095) / 4096));
-      int rc = need(stats_, (size_t)B * chunks * nslices * 16 * sizeof(double));
+      const int nslices = raw.stat_slices ? raw.stat_slices : std::max(1, std::min(64, (HW + 4095) / 4096));
+      int rc = raw.stat_slices ? 0 : need(stats_, (size_t)B * chunks * nslices * 16 * sizeof(double));
       if (!rc) rc = need(ss_, (size_t)B * chunks * 8 * sizeof(float2));
       if (rc) return rc;
-      norm_stats_kernel<<<dim3((unsigned)nslices, (unsigned)chunks, (unsigned)B), 256, 0, st>>>(
-          raw.p, raw.nsplit, (long long)raw.split_stride, p.raw_bs, p.raw_cs, HW, reinterpret_cast<double*>(stats_.p));
-      const int nthreads = (ps ? B : 1) * chunks * 8 * 32;
-      norm_finalize_kernel<<<(nthreads + 127) / 128, 128, 0, st>>>(reinterpret_cast<const double*>(stats_.p), B, chunks, nslices,
+      if (!raw.stat_slices) {   // the conv kernel did not leave per-tile partial sums: one pass over the raw tensor
+        norm_stats_kernel<<<dim3((unsigned)nslices, (unsigned)chunks, (unsigned)B), 256, 0, st>>>(
+            raw.p, raw.nsplit, (long long)raw.split_stride, p.raw_bs, p.raw_cs, HW, reinterpret_cast<double*>(stats_.p));
+        ++launches_;
+      }
+      norm_finalize_kernel<<<(ps ? B : 1) * chunks * 8, 128, 0, st>>>(reinterpret_cast<const double*>(stats_.p), B, chunks, nslices,
                                                                   HW, ps ? 1 : 0, n->d_gamma, n->d_beta,
                                                                   reinterpret_cast<float2*>(ss_.p));
-      launches_ += 2;
+      ++launches_;
       p.ss = reinterpret_cast<const float2*>(ss_.p);
       p.ss_per_sample = 1;
     }
@@ -1414,7 +1512,7 @@ int I2INet::forward_unet(const void* in, int in_CT, int B, int H, int W, GenView
   // half of what the next level returns after the in-place ReLU in front of this level's transposed conv
   for (int i = 0; i < D; ++i) {
     const int hi = H >> i, wi = W >> i, C = inner_nc(i);
-    if ((rc = conv_raw(down_[i], cur, B, hi, wi, raw, st))) return rc;
+    if ((rc = conv_raw(down_[i], cur, B, hi, wi, raw, st, i > 0 && i < D - 1 && !dnorm_[i].running))) return rc;
     if (i < D - 1) {
       const GenView a = view(dbuf_[i + 1], C / 8, 0), skip = view(cat_[i + 1], 2 * C / 8, 0);
       if ((rc = norm_apply(i > 0 ? &dnorm_[i] : nullptr, raw, B, C, hi / 2, wi / 2, per_sample, kActLrelu, a, kActRelu, &skip,
@@ -1431,7 +1529,7 @@ int I2INet::forward_unet(const void* in, int in_CT, int B, int H, int W, GenView
   // up: y_i = norm(upconv_i(relu(inner))) goes, already passed through the next ReLU, behind the skip half
   for (int i = D - 1; i >= 1; --i) {
     const int hin = H >> (i + 1), win = W >> (i + 1), X = inner_nc(i - 1);
-    if ((rc = conv_raw(up_[i], cur, B, hin, win, raw, st))) return rc;
+    if ((rc = conv_raw(up_[i], cur, B, hin, win, raw, st, !unorm_[i].running))) return rc;
     const GenView o = view(cat_[i], 2 * X / 8, X / 8);
     if ((rc = norm_apply(&unorm_[i], raw, B, X, H >> i, W >> i, per_sample, kActRelu, o, 0, nullptr, nullptr, st))) return rc;
     cur = view(cat_[i], 2 * X / 8, 0);
@@ -1452,32 +1550,32 @@ int I2INet::forward_resnet(const void* in, int in_CT, int B, int H, int W, GenVi
   int li = 0;
   GenView x{const_cast<void*>(in), in_CT, 0};
   const GenView va = view(a_, ngf / 8, 0), vb = view(b_, 2 * ngf / 8, 0);
-  if ((rc = conv_raw(down_[li], x, B, H, W, raw, st))) return rc;
+  if ((rc = conv_raw(down_[li], x, B, H, W, raw, st, !dnorm_[li].running))) return rc;
   if ((rc = norm_apply(&dnorm_[li], raw, B, ngf, H, W, per_sample, kActRelu, va, 0, nullptr, nullptr, st))) return rc;
   ++li;
-  if ((rc = conv_raw(down_[li], va, B, H, W, raw, st))) return rc;
+  if ((rc = conv_raw(down_[li], va, B, H, W, raw, st, !dnorm_[li].running))) return rc;
   if ((rc = norm_apply(&dnorm_[li], raw, B, 2 * ngf, H1, W1, per_sample, kActRelu, vb, 0, nullptr, nullptr, st))) return rc;
   ++li;
   int y = 0, t = 1, y2 = 2;
   const int C = 4 * ngf;
-  if ((rc = conv_raw(down_[li], vb, B, H1, W1, raw, st))) return rc;
+  if ((rc = conv_raw(down_[li], vb, B, H1, W1, raw, st, !dnorm_[li].running))) return rc;
   if ((rc = norm_apply(&dnorm_[li], raw, B, C, H2, W2, per_sample, kActRelu, view(rb_[y], C / 8, 0), 0, nullptr, nullptr, st)))
     return rc;
   ++li;
   for (int b = 0; b < nb; ++b) {
     const GenView vy = view(rb_[y], C / 8, 0), vt = view(rb_[t], C / 8, 0), vy2 = view(rb_[y2], C / 8, 0);
-    if ((rc = conv_raw(down_[li], vy, B, H2, W2, raw, st))) return rc;
+    if ((rc = conv_raw(down_[li], vy, B, H2, W2, raw, st, !dnorm_[li].running))) return rc;
     if ((rc = norm_apply(&dnorm_[li], raw, B, C, H2, W2, per_sample, kActRelu, vt, 0, nullptr, nullptr, st))) return rc;
     ++li;
-    if ((rc = conv_raw(down_[li], vt, B, H2, W2, raw, st))) return rc;
+    if ((rc = conv_raw(down_[li], vt, B, H2, W2, raw, st, !dnorm_[li].running))) return rc;
     if ((rc = norm_apply(&dnorm_[li], raw, B, C, H2, W2, per_sample, kActNone, vy2, 0, nullptr, &vy, st))) return rc;
     ++li;
     std::swap(y, y2);
   }
-  if ((rc = conv_raw(down_[li], view(rb_[y], C / 8, 0), B, H2, W2, raw, st))) return rc;
+  if ((rc = conv_raw(down_[li], view(rb_[y], C / 8, 0), B, H2, W2, raw, st, !dnorm_[li].running))) return rc;
   if ((rc = norm_apply(&dnorm_[li], raw, B, 2 * ngf, H1, W1, per_sample, kActRelu, vb, 0, nullptr, nullptr, st))) return rc;
   ++li;
-  if ((rc = conv_raw(down_[li], vb, B, H1, W1, raw, st))) return rc;
+  if ((rc = conv_raw(down_[li], vb, B, H1, W1, raw, st, !dnorm_[li].running))) return rc;
   if ((rc = norm_apply(&dnorm_[li], raw, B, ngf, H, W, per_sample, kActRelu, va, 0, nullptr, nullptr, st))) return rc;
   ++li;
   return conv_final(down_[li], va, B, H, W, out, kActTanh, compact4, st);
@@ -1494,7 +1592,7 @@ int I2INet::forward(const void* in, int in_CT, int B, int H, int W, GenView out,
       rc = conv_final(down_[0], x, B, H, W, out, cfg_.sl_act, compact4, st);
     } else {
       Raw raw;
-      rc = conv_raw(down_[0], x, B, H, W, raw, st);
+      rc = conv_raw(down_[0], x, B, H, W, raw, st, cfg_.sl_norm && !dnorm_[0].running);
       if (!rc)
         rc = norm_apply(cfg_.sl_norm ? &dnorm_[0] : nullptr, raw, B, cfg_.sl_cout, down_[0].out_h(H), down_[0].out_h(W),
                         per_sample, cfg_.sl_act, out, 0, nullptr, nullptr, st);

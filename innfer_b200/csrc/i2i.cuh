@@ -117,13 +117,14 @@ class I2INet {
     float* p = nullptr;
     int nsplit = 1;
     size_t split_stride = 0;   // elements
+    int stat_slices = 0;       // > 0: the conv kernel left per-tile partial sums of the norm statistics in stats_
   };
   int build_conv(const ParamLookup& get, const std::string& name, GenConv& L, int Cout, int Cin, int k, int stride, int pad,
                  bool transposed, int out_pad, bool reflect, bool has_bias, std::string& err, size_t* consumed);
   int build_norm(const ParamLookup& get, const std::string& name, Norm& n, int C, std::string& err, size_t* consumed);
   int need(Buf& b, size_t bytes);
   // convolution into the raw fp32 scratch (split-K allowed)
-  int conv_raw(const GenConv& L, GenView in, int B, int Hin, int Win, Raw& raw, cudaStream_t st);
+  int conv_raw(const GenConv& L, GenView in, int B, int Hin, int Win, Raw& raw, cudaStream_t st, bool want_stats = false);
   // convolution with bias + activation straight into a tensor of the network's precision (the last layer)
   int conv_final(const GenConv& L, GenView in, int B, int Hin, int Win, GenView out, int act, bool compact4, cudaStream_t st);
   // out_a = act_a(norm(raw) [+ res]), optionally out_b = act_b(same); norm == nullptr: identity
