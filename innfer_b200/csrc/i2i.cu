@@ -61,6 +61,7 @@ struct GenConvParams {
   // pixels go to stats[((b * out_nchunks + chunk) * stat_slices + slice) * 16 + {e, 8 + e}], slice = slice0[phase] + tile
   double* stats;
   int stat_slices, slice0[kGenMaxPhases];
+  int debug;   // INNFER_I2I_DEBUG bit mask for timing experiments (wrong results): 1 no MMA, 2 no A gather, 4 no weight copy
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -302,7 +303,9 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
   uint64_t* tfull_bar = empty_bar + S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
   float* red = reinterpret_cast<float*>(smem + (size_t)S * STAGE + 128);            // [2][4 warps][32]: statistics exchange
-  int32_t* tbl = reinterpret_cast<int32_t*>(smem + (size_t)S * STAGE + 128 + 1024);
+  float* s_bias = reinterpret_cast<float*>(smem + (size_t)S * STAGE + 128 + 1024);   // [NT] bias of this N tile
+  int32_t* tbl = reinterpret_cast<int32_t*>(smem + (size_t)S * STAGE + 128 + 1024 + 512);
+  if (threadIdx.x < NT) s_bias[threadIdx.x] = (p.debug & 32) ? 0.f : p.bias[blockIdx.y * NT + threadIdx.x];
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 128 + 1);
@@ -346,8 +349,12 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
       const uint32_t a_dst = smem_base + (uint32_t)s * STAGE;
       if (tid == 0) {
         const uint32_t fb = smem_u32(&full_bar[s]);
-        mbar_expect_tx(fb, B_BYTES);
-        bulk_load(a_dst + A_BYTES, wsrc + (size_t)i * B_BYTES, B_BYTES, fb);
+        if (p.debug & 4) {
+          mbar_arrive(fb);
+        } else {
+          mbar_expect_tx(fb, B_BYTES);
+          bulk_load(a_dst + A_BYTES, wsrc + (size_t)i * B_BYTES, B_BYTES, fb);
+        }
       }
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
@@ -355,7 +362,7 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
         const bool cv = chunk < p.cin_chunks;   // odd chunk counts: the second K-chunk of the last slab is zeros
         const __half* cb = inb + (size_t)chunk * p.in_cs;
         const uint32_t dst = a_dst + (uint32_t)kc * (uint32_t)Npos * 16u;
-        for (int pos = tid; pos < Npos; pos += 128) {
+        for (int pos = tid; pos < ((p.debug & 2) ? 0 : Npos); pos += 128) {
           const int off = tbl[pos];
           const bool ok = cv && off >= 0;
           cp_async_16(dst + (uint32_t)pos * 16u, ok ? (const void*)(cb + off) : p.in, ok ? 16u : 0u);
@@ -379,20 +386,25 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
     const int oyp = y0 + r;
     const int oy = oyp * p.ostep + p.py[ph];
     const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const bool want_stats = p.stats != nullptr;
+    const bool want_stats = p.stats != nullptr && !(p.debug & 8);
     int grp = 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < NT; c0 += 16, ++grp) {
       float sq[32];   // [0, 16): sums of this thread's pixels (one per sub-patch), [16, 32): sums of squares
 #pragma unroll
       for (int e = 0; e < 32; ++e) sq[e] = 0.f;
-      for (int j = 0; j < jeff; ++j) {
+      uint32_t vv[4][16];   // the group's 16 columns of every sub-patch: one TMEM round trip instead of J
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < jeff) tmem_ld16(tacc + (uint32_t)(j * NT + c0), vv[j]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j >= jeff) continue;
+        const uint32_t(&v)[16] = vv[j];
         const int oxp = x0 + 8 * j + c;
         const bool valid = oyp < Hp && oxp < Wp;
         const size_t pix = (size_t)oy * p.Wout + (size_t)(oxp * p.ostep + p.px[ph]);
-        uint32_t v[16];
-        tmem_ld16(tacc + (uint32_t)(j * NT + c0), v);
-        tmem_ld_wait();
         if (!valid) continue;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -401,11 +413,13 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
           float f[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            f[e] = apply_act(__uint_as_float(v[hh * 8 + e]) + p.bias[gc * 8 + e], p.act);
+            f[e] = apply_act(__uint_as_float(v[hh * 8 + e]) + s_bias[c0 + hh * 8 + e], p.act);
             sq[hh * 8 + e] += f[e];
             sq[16 + hh * 8 + e] = fmaf(f[e], f[e], sq[16 + hh * 8 + e]);
           }
-          if (p.out_mode == 1) {
+          if (p.debug & 16) {
+            if (f[0] == 123.456f) p.stats[0] = 1.0;
+          } else if (p.out_mode == 1) {
             float* op = reinterpret_cast<float*>(p.out) + (size_t)b * p.out_bs + (size_t)(p.out_chunk0 + gc) * p.out_cs + pix * 8;
             *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
             *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
@@ -469,7 +483,7 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
         for (int tp = 0; tp < ntaps; ++tp) {
           const uint32_t aoff = (uint32_t)p.tap_aoff[ph][tp] * 16u;
           const uint64_t bdesc = make_smem_desc(sb + (uint32_t)tp * 2u * NT * 16u, (uint32_t)NT * 16u, 128u);
-          for (int j = 0; j < jeff; ++j) {
+          for (int j = 0; j < ((p.debug & 1) ? 0 : jeff); ++j) {
             const uint64_t adesc = make_smem_desc(sa + aoff + (uint32_t)j * 128u, lbo, sbo);
             umma_f16_ss(tmem_base + (uint32_t)(j * NT), adesc, bdesc, idesc, (i | tp) != 0 ? 1u : 0u);
           }
@@ -1242,6 +1256,7 @@ bool halo_geometry_ok(const GenConv& L, const GenConvParams& p) {
 bool halo_setup(const GenConv& L, GenConvParams& p, int num_sms, dim3& grid, size_t& smem, int& stages) {
   const int mode = halo_mode();
   if (mode == 0 || p.nsplit != 1 || !halo_geometry_ok(L, p)) return false;
+  p.debug = getenv("INNFER_I2I_DEBUG") ? atoi(getenv("INNFER_I2I_DEBUG")) : 0;
   // sub-patches per CTA: 4 x NT accumulator columns must fit TMEM's 512.  With NT = 128 that is the whole TMEM (one CTA per
   // SM, no second CTA to hide the epilogue) but it halves the weight bytes per MMA, which is what bounds the wide layers
   // (every CTA re-reads the slab's weights from L2): taken when there is more than a wave of such tiles and it fits.
@@ -1274,7 +1289,7 @@ bool halo_setup(const GenConv& L, GenConvParams& p, int num_sms, dim3& grid, siz
       tbl = std::max(tbl, npos * 4);
     }
     stage = (stage + 127) & ~(size_t)127;
-    tail = 128 + 1024 + ((tbl + 127) & ~(size_t)127);
+    tail = 128 + 1024 + 512 + ((tbl + 127) & ~(size_t)127);
     if (ok && (L.nslabs == 1 ? 1 : 2) * stage + tail <= kSmemMax) break;
     if (J <= 1) return false;
     J /= 2;   // a narrower patch needs a smaller tile
@@ -1303,6 +1318,7 @@ bool halo_setup(const GenConv& L, GenConvParams& p, int num_sms, dim3& grid, siz
       stages = 2;     // two CTAs per SM: one CTA's epilogue overlaps the other's main loop
     else
       stages = (int)std::min<size_t>(4, (kSmemMax - tail) / stage);
+    if (getenv("INNFER_I2I_STAGES")) stages = std::min<int>(atoi(getenv("INNFER_I2I_STAGES")), (int)((kSmemMax - tail) / stage));
     stages = std::max(2, std::min(stages, L.nslabs));
   }
   p.J = J;
