@@ -76,7 +76,12 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// the mbarrier receives one arrival (counted in its init value) when all cp.async copies this thread has issued so far
+// have landed: the gather threads never block on their own copies
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -89,7 +94,6 @@ template <int NT>
 __global__ void __launch_bounds__(kGenThreads) gen_conv_tc_kernel(const __grid_constant__ GenConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int S = gen_stages(NT);
-  constexpr int D = S - 1;                       // cp.async groups a gather thread keeps in flight
   constexpr uint32_t B_BYTES = 8u * NT * 16u;
   constexpr uint32_t STAGE = kGenABytes + B_BYTES;
   constexpr uint32_t TCOLS = NT < 32 ? 32u : (uint32_t)NT;
@@ -175,16 +179,9 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_tc_kernel(const __grid_c
           ++tap;
         }
       }
-      cp_async_commit();
-      if (i >= D) {
-        cp_async_wait<D>();            // the copies of K-step i - D have landed
-        fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
-        mbar_arrive(smem_u32(&full_bar[(i - D) % S]));
-      }
+      cp_async_mbar_arrive(smem_u32(&full_bar[s]));   // arrives when this thread's copies of the K-step have landed
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (int i = nk > D ? nk - D : 0; i < nk; ++i) mbar_arrive(smem_u32(&full_bar[i % S]));
+    cp_async_wait_all();
 
     // ------------------------------------------------------------ epilogue: TMEM lane = pixel row = this thread
     mbar_wait(smem_u32(tfull_bar), 0u);
@@ -240,6 +237,7 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_tc_kernel(const __grid_c
     for (int i = 0; i < nk; ++i) {
       const int s = i % S;
       mbar_wait(smem_u32(&full_bar[s]), ((uint32_t)(i / S)) & 1u);
+      fence_proxy_async_smem();   // the gather's generic-proxy writes (visible through the barrier) -> async-proxy reads
       tc_fence_after();
       if (lane == 0) {
         const uint32_t sa = smem_base + (uint32_t)s * STAGE;
@@ -277,7 +275,6 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_tc_kernel(const __grid_c
 template <int NT, int S>
 __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid_constant__ GenConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int D = S - 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ph = blockIdx.z;
   const int bands = p.bands[ph], cps = p.cps[ph];
@@ -368,16 +365,9 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
           cp_async_16(dst + (uint32_t)pos * 16u, ok ? (const void*)(cb + off) : p.in, ok ? 16u : 0u);
         }
       }
-      cp_async_commit();
-      if (i >= D) {
-        cp_async_wait<D>();
-        fence_proxy_async_smem();
-        mbar_arrive(smem_u32(&full_bar[(i - D) % S]));
-      }
+      cp_async_mbar_arrive(smem_u32(&full_bar[s]));   // arrives when this thread's copies have landed
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (int i = nslabs > D ? nslabs - D : 0; i < nslabs; ++i) mbar_arrive(smem_u32(&full_bar[i % S]));
+    cp_async_wait_all();
 
     // ------------------------------------------------------------ epilogue: lane m = pixel (m / 8, m % 8) of a sub-patch
     mbar_wait(smem_u32(tfull_bar), 0u);
@@ -476,6 +466,7 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
     for (int i = 0; i < nslabs; ++i) {
       const int s = i % S;
       mbar_wait(smem_u32(&full_bar[s]), ((uint32_t)(i / S)) & 1u);
+      fence_proxy_async_smem();   // the gather's generic-proxy writes (visible through the barrier) -> async-proxy reads
       tc_fence_after();
       if (lane == 0) {
         const uint32_t sa = smem_base + (uint32_t)s * STAGE;
