@@ -1353,7 +1353,7 @@ int innfer_rrdb_profile_families(innfer_rrdb* h, char* buf, uint64_t cap, uint64
       ms += t;
     }
     char line[256];
-    snprintf(line, sizeof line, "%s\t%llu\t%.6f\t%.6e\t%.6e\n", kv.first.c_str(), (unsigned long long)kv.second.launches, ms,
+    snprintf(line, sizeof line, "%s\t%llu\t%.6f\t%.17g\t%.17g\n", kv.first.c_str(), (unsigned long long)kv.second.launches, ms,
              kv.second.flop, kv.second.bytes);
     out += line;
   }

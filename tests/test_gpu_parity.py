@@ -788,6 +788,13 @@ def test_stream_flags_signal_wait_and_timeout(native, dev):
     native.check(lib.innfer_stream_signal(scratch, 1, 1, ctypes.c_void_p(s2.cuda_stream)))
     native.check(lib.innfer_stream_wait(scratch, 1, 1, err, 20000, ctypes.c_void_p(s2.cuda_stream)))
     s2.synchronize()
+    # ... and the same for the torch kernels this test launches around the spinning wait (int32 add / copy): their
+    # first launch would sit in the module loader until the wait's timeout and then see the add already done
+    with torch.cuda.stream(s1):
+        marker.add_(0)
+    with torch.cuda.stream(s2):
+        marker.clone()
+    torch.cuda.synchronize()
     arr = (ctypes.c_void_p * 2)(flags.data_ptr(), flags.data_ptr() + 4)
     native.check(lib.innfer_stream_wait(arr, 2, 5, err, 20000, ctypes.c_void_p(s1.cuda_stream)))
     with torch.cuda.stream(s1):

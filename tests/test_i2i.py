@@ -277,3 +277,27 @@ def test_config5_sizes_1024_against_oracle(dev):
         a, r = _u8(y), _u8(ref)
         assert np.abs(a.astype(int) - r.astype(int)).max() <= 1, family
         assert psnr_u8(a, r) >= 50.0, family
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("arch,shape", [("resnet_9blocks", (72, 100)), ("unet_256", (200, 256))])
+def test_cli_gpu_matches_cli_cpu(dev, tmp_path, monkeypatch, arch, shape):
+    """`python run.py -m <model> -a <arch>` on the GPU (fp16 engine) against the same command with -cpu (torch modules,
+    fp32): pix2pix resizes to a multiple of 256 and runs the whole image in training mode, cyclegan chops."""
+    import cv2
+    from innfer_b200 import run as R
+    (tmp_path / "models").mkdir()
+    (tmp_path / "input").mkdir()
+    for d in ("out_gpu", "out_cpu"):
+        (tmp_path / d).mkdir()
+    sd = (I.randomize_norms(I.make_unet_state_dict(seed=71), 171) if arch == "unet_256" else I.make_resnet_state_dict(seed=72))
+    torch.save(sd, tmp_path / "models" / "1x_rand_i2i.pth")
+    cv2.imwrite(str(tmp_path / "input" / "a.png"), synth_image(73, *shape))
+    monkeypatch.chdir(tmp_path)
+    R.main(["-m", "i2i", "-a", arch, "-i", "input", "-o", "out_gpu"])
+    R.main(["-m", "i2i", "-a", arch, "-i", "input", "-o", "out_cpu", "-cpu"])
+    a = cv2.imread(str(tmp_path / "out_gpu" / "a.png"), cv2.IMREAD_UNCHANGED)
+    b = cv2.imread(str(tmp_path / "out_cpu" / "a.png"), cv2.IMREAD_UNCHANGED)
+    assert a.shape == b.shape and a.shape[0] % 4 == 0
+    assert np.abs(a.astype(int) - b.astype(int)).max() <= 1
+    assert psnr_u8(a, b) >= 50.0
