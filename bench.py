@@ -517,6 +517,18 @@ def run_i2i(args, dev, warm):
                             torch.cuda.current_stream().synchronize()
                         rec["e2e_ms"] = (time.perf_counter() - t0) * 1e3 / args.steps
                 rec["ours_over_torch_gpu"] = rec["torch_gpu"]["ms"] / rec["ours"]["ms"]
+                if family == "resnet":
+                    # what `run.py -a resnet_9blocks` does per image: uint8 frame in, chop_forward over 200 px tiles
+                    # (step 0.5), uint8 frame out -- ChainRunner with the [-1, 1] mapping folded into the engine
+                    from innfer_b200.run import ChainRunner
+                    frame = synth_frame(size, size, size)
+                    runner = ChainRunner([net.native_engine(dev, torch.float16, unit_io=True)], dev)
+                    for _ in range(2):
+                        runner(frame)
+                    t0 = time.perf_counter()
+                    for _ in range(args.steps):
+                        runner(frame)
+                    rec["cli_chop_e2e_ms"] = (time.perf_counter() - t0) * 1e3 / args.steps
             cases.append(rec)
             if family == "resnet" and size == 1024:
                 head = rec

@@ -105,6 +105,11 @@ typedef struct innfer_i2i_cfg {
   int32_t norm;   /* 0: BatchNorm2d, 1: InstanceNorm2d (then the convolutions carry a bias) */
   int32_t train;  /* BatchNorm2d: 1 = batch statistics (module.training), 0 = running statistics */
   int32_t fp16;
+  int32_t unit_io; /* 1 (ResnetGenerator only): images in [0, 1] at both ends -- the [-1, 1] normalisation run.py wraps
+                    * around these networks (np2tensor(normalize) / tensor2np(denormalize), utils.py:136-161,
+                    * run.py:420,430) folded into the first conv (doubled weights, bias - sum of weights: exact with
+                    * reflection padding) and the last layer ((tanh + 1) / 2), so that innfer_rrdb_upscale_u8 /
+                    * chop_forward_ex serve the CLI loop on uint8 frames like they do for the SR networks */
 } innfer_i2i_cfg;
 
 typedef struct innfer_tile {

@@ -42,7 +42,7 @@ class PANCfg(ctypes.Structure):
 
 
 class I2ICfg(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int32) for n in ("kind", "in_nc", "out_nc", "ngf", "depth", "norm", "train", "fp16")]
+    _fields_ = [(n, ctypes.c_int32) for n in ("kind", "in_nc", "out_nc", "ngf", "depth", "norm", "train", "fp16", "unit_io")]
 
 
 class Tile(ctypes.Structure):

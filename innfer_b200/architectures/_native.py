@@ -25,10 +25,12 @@ class NativeEngineMixin:
         fp = tuple((p.data_ptr(), p._version) for p in self.parameters())
         return fp + tuple((b.data_ptr(), b._version) for b in self.buffers()) + tuple(self._engine_key_extra())
 
-    def _engine(self, device, dtype):
+    def _engine(self, device, dtype, **variant):
+        """``variant``: extra keyword arguments of the engine class's ``from_module`` (e.g. ``unit_io=True`` for the
+        generators that run.py wraps in a [-1, 1] normalisation)."""
         from .. import engine as E
         cache = self.__dict__.setdefault("_engines", {})
-        key = (str(device), dtype)
+        key = (str(device), dtype) + tuple(sorted(variant.items()))
         fp = self._fingerprint()
         hit = cache.get(key)
         if hit is not None and hit[0] == fp:
@@ -36,7 +38,7 @@ class NativeEngineMixin:
         for _, old in cache.values():   # one resident engine per module
             old.close()
         cache.clear()
-        eng = getattr(E, self._engine_class).from_module(self, device, fp16=(dtype == torch.float16))
+        eng = getattr(E, self._engine_class).from_module(self, device, fp16=(dtype == torch.float16), **variant)
         cache[key] = (fp, eng)
         return eng
 
@@ -46,9 +48,9 @@ class NativeEngineMixin:
             old.close()
         self.__dict__["_engines"] = {}
 
-    def native_engine(self, device, dtype=torch.float16):
+    def native_engine(self, device, dtype=torch.float16, **variant):
         """The engine serving CUDA tensors of this dtype (built on first use)."""
-        return self._engine(torch.device(device), dtype)
+        return self._engine(torch.device(device), dtype, **variant)
 
     def chop_forward_native(self, x, patch_size, step):
         """extract_patches_2d -> forward -> recompose_tensor in one native call (CUDA only)."""

@@ -1120,6 +1120,8 @@ int innfer_i2i_create(const innfer_i2i_cfg* cfg, int device, innfer_rrdb** out) 
   if (cfg->ngf < 8 || cfg->ngf % 8) return fail(INNFER_E_UNSUPPORTED, "ngf must be a multiple of 8");
   if (cfg->kind == 0 && (cfg->depth < 5 || cfg->depth > 12)) return fail(INNFER_E_UNSUPPORTED, "num_downs must be in [5, 12]");
   if (cfg->kind == 1 && (cfg->depth < 0 || cfg->depth > 64)) return fail(INNFER_E_UNSUPPORTED, "n_blocks must be in [0, 64]");
+  if (cfg->unit_io && cfg->kind != 1)
+    return fail(INNFER_E_UNSUPPORTED, "unit_io needs reflection padding at the first conv: ResnetGenerator only");
   innfer_rrdb_cfg base = {cfg->in_nc, cfg->out_nc, 64, 1, 32, 1, 0, cfg->fp16};
   int rc = innfer_rrdb_create(&base, device, out);
   if (rc) return rc;
@@ -1135,6 +1137,7 @@ int innfer_i2i_create(const innfer_i2i_cfg* cfg, int device, innfer_rrdb** out) 
   h->i2i_cfg.norm = cfg->norm;
   h->i2i_cfg.train = cfg->train != 0;
   h->i2i_cfg.fp16 = cfg->fp16 != 0;
+  h->i2i_cfg.unit_io = cfg->unit_io != 0;
   return 0;
 }
 

@@ -69,6 +69,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case kActRelu: return fmaxf(v, 0.f);
     case kActLrelu: return v > 0.f ? v : v * kLreluSlope;
     case kActTanh: return tanhf(v);
+    case kActTanh01: return 0.5f * tanhf(v) + 0.5f;
     default: return v;
   }
 }
@@ -1123,6 +1124,10 @@ int I2INet::build(const ParamLookup& get, std::string& err, size_t* consumed) {
   }
   const bool bias = cfg_.norm == 1;   // use_bias = norm_layer == InstanceNorm2d (UNet_arch.py:100-103, ResNet_arch.py:47-50)
   int rc;
+  if (cfg_.unit_io && cfg_.kind != 1) {
+    err = "unit_io (normalisation folded into the network) needs reflection padding: ResnetGenerator only";
+    return -2;
+  }
   if (cfg_.kind == 0) {
     const int D = cfg_.depth;
     if (D < 5 || D > 12) {
@@ -1162,7 +1167,43 @@ int I2INet::build(const ParamLookup& get, std::string& err, size_t* consumed) {
     dnorm_.resize(nconv);
     int li = 0;
     auto key = [](int i) { return "model." + std::to_string(i); };
-    if ((rc = build_conv(get, key(1), down_[li], ngf, cfg_.in_nc, 7, 1, 3, false, 0, true, bias, err, consumed))) return rc;
+    if (cfg_.unit_io) {
+      // conv(w, 2x - 1) + b == conv(2w, x) + (b - sum over taps and input channels of w)
+      std::vector<int64_t> ws, bs;
+      const float* w = get(key(1) + ".weight", ws);
+      if (!w || ws != std::vector<int64_t>{ngf, cfg_.in_nc, 7, 7}) {
+        err = (w ? "size mismatch for " : "missing key ") + key(1) + ".weight";
+        return w ? -1 : -4;
+      }
+      const float* b0 = bias ? get(key(1) + ".bias", bs) : nullptr;
+      if (bias && (!b0 || bs != std::vector<int64_t>{ngf})) {
+        err = (b0 ? "size mismatch for " : "missing key ") + key(1) + ".bias";
+        return b0 ? -1 : -4;
+      }
+      const size_t per = (size_t)cfg_.in_nc * 49;
+      std::vector<float> w2((size_t)ngf * per), b2((size_t)ngf);
+      for (int co = 0; co < ngf; ++co) {
+        double sum = 0.0;
+        for (size_t i = 0; i < per; ++i) {
+          sum += (double)w[co * per + i];
+          w2[co * per + i] = 2.f * w[co * per + i];
+        }
+        b2[co] = (float)((b0 ? (double)b0[co] : 0.0) - sum);
+      }
+      const ParamLookup folded = [&](const std::string& k, std::vector<int64_t>& shape) -> const float* {
+        if (k == key(1) + ".weight") {
+          shape = {ngf, cfg_.in_nc, 7, 7};
+          return w2.data();
+        }
+        shape = {ngf};
+        return b2.data();
+      };
+      size_t dummy = 0;
+      if ((rc = build_conv(folded, key(1), down_[li], ngf, cfg_.in_nc, 7, 1, 3, false, 0, true, true, err, &dummy))) return rc;
+      *consumed += bias ? 2 : 1;
+    } else if ((rc = build_conv(get, key(1), down_[li], ngf, cfg_.in_nc, 7, 1, 3, false, 0, true, bias, err, consumed))) {
+      return rc;
+    }
     if ((rc = build_norm(get, key(2), dnorm_[li], ngf, err, consumed))) return rc;
     ++li;
     int ch = ngf;
@@ -1585,7 +1626,7 @@ int I2INet::forward_resnet(const void* in, int in_CT, int B, int H, int W, GenVi
   if ((rc = conv_raw(down_[li], vb, B, H1, W1, raw, st, !dnorm_[li].running))) return rc;
   if ((rc = norm_apply(&dnorm_[li], raw, B, ngf, H, W, per_sample, kActRelu, va, 0, nullptr, nullptr, st))) return rc;
   ++li;
-  return conv_final(down_[li], va, B, H, W, out, kActTanh, compact4, st);
+  return conv_final(down_[li], va, B, H, W, out, cfg_.unit_io ? kActTanh01 : kActTanh, compact4, st);
 }
 
 int I2INet::forward(const void* in, int in_CT, int B, int H, int W, GenView out, bool compact4, bool per_sample, cudaStream_t st,

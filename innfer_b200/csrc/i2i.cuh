@@ -26,7 +26,7 @@ constexpr int kGenMaxTaps = 49;   // 7 x 7
 constexpr int kGenMaxPhases = 4;  // stride-2 transposed convolutions: one phase per output parity class
 constexpr int kGenMaxSplit = 16;  // split-K partial tensors
 
-enum GenAct { kActNone = 0, kActRelu = 1, kActLrelu = 2, kActTanh = 3 };
+enum GenAct { kActNone = 0, kActRelu = 1, kActLrelu = 2, kActTanh = 3, kActTanh01 = 4 /* (tanh(v) + 1) / 2 */ };
 
 // One convolution or transposed convolution with its packed weights.
 struct GenConv {
@@ -71,6 +71,11 @@ struct I2ICfg {
   int norm = 0;       // 0: BatchNorm2d, 1: InstanceNorm2d
   int train = 0;      // BatchNorm: 1 = statistics of the batch (module in training mode, run.py:297), 0 = running statistics
   int fp16 = 1;
+  // images in [0, 1] at both ends: the [-1, 1] normalisation run.py applies around these networks (np2tensor(normalize),
+  // tensor2np(denormalize); utils.py:136-161) folded into the network -- first conv on 2x - 1 == conv with doubled
+  // weights and bias - sum(w) (exact with reflection padding: every tap sees a real pixel), last layer (tanh + 1) / 2.
+  // ResnetGenerator only (the UNet's first conv pads with zeros, which are 0.5 in image units).
+  int unit_io = 0;
   // kind 2: ONE convolution [+ norm] [+ activation] under the keys "conv" / "norm" -- the operator-level entry point
   // innfer_gen_conv of the parity tests (same kernels and code paths as the networks)
   int sl_cout = 0, sl_k = 3, sl_stride = 1, sl_pad = 1, sl_transposed = 0, sl_out_pad = 0, sl_reflect = 0, sl_bias = 1;

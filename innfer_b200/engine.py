@@ -269,13 +269,15 @@ class _I2IEngine(RRDBEngine):
     _depth_key = "num_downs"
 
     @classmethod
-    def from_module(cls, module, device, fp16=True):
-        return cls.from_state_dict(module.state_dict(), dict(module.cfg, train=bool(module.training)), device, fp16)
+    def from_module(cls, module, device, fp16=True, unit_io=False):
+        cfg = dict(module.cfg, train=bool(module.training), unit_io=bool(unit_io))
+        return cls.from_state_dict(module.state_dict(), cfg, device, fp16)
 
     def _create(self):
         cfg = self.cfg
         c = N.I2ICfg(self._kind, cfg["in_nc"], cfg["out_nc"], cfg["ngf"], cfg[self._depth_key],
-                     {"batch": 0, "instance": 1}[cfg["norm"]], int(bool(cfg.get("train", False))), int(self.fp16))
+                     {"batch": 0, "instance": 1}[cfg["norm"]], int(bool(cfg.get("train", False))), int(self.fp16),
+                     int(bool(cfg.get("unit_io", False))))
         N.check(self.lib.innfer_i2i_create(ctypes.byref(c), self.index, ctypes.byref(self._h)))
 
     def load(self, key, tensor):

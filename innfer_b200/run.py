@@ -188,10 +188,12 @@ cyclegan_extras = {"meval": True, "strict": False, "normalize": True}
 
 
 # ---------------------------------------------------------------------- fused device path of the CLI loop
-def native_chain(models, device, fp16):
+def native_chain(models, device, fp16, normalize=False):
     """The engines of a model chain if the whole per-image loop of run.py:421-434 can stay on the device
     (np2tensor -> [chop_forward per model] -> tensor2np [-> color_fix]), else None.  That needs a CUDA device, chop
-    mode, and every model to be a 3-channel network with a native engine."""
+    mode, and every model to be a 3-channel network with a native engine.  With ``normalize`` (images mapped to [-1, 1]
+    around the chain, run.py:420,430) it needs a single CycleGAN generator, whose engine folds the mapping into its first
+    and last layer (``unit_io``); every other case keeps the tensor interface."""
     if torch.device(device).type != "cuda":
         return None
     dtype = torch.float16 if fp16 else torch.float32
@@ -200,7 +202,13 @@ def native_chain(models, device, fp16):
         net = m.model
         if m.arch == "ts" or not m.chop or not hasattr(net, "native_engine") or m.in_nc != 3 or m.out_nc != 3:
             return None
-        engines.append(net.native_engine(device, dtype))
+        if normalize:
+            from .architectures.ResNet_arch import ResnetGenerator
+            if len(models) != 1 or not isinstance(net, ResnetGenerator):
+                return None
+            engines.append(net.native_engine(device, dtype, unit_io=True))
+        else:
+            engines.append(net.native_engine(device, dtype))
     return engines
 
 
@@ -292,7 +300,7 @@ def main(argv=None):
             m.model.half()
         models.append(m)
 
-    engines = None if normalize else native_chain(models, device, fp16)
+    engines = native_chain(models, device, fp16, normalize=normalize)
     runner = ChainRunner(engines, device, cf=args.cf) if engines else None
 
     for image_path in get_images_paths(args.input):
