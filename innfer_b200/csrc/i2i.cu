@@ -74,6 +74,11 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// the activations a norm layer can be followed by (no tanh: 16 inlined copies of it were most of the apply kernel's code)
+__device__ __forceinline__ float apply_act_light(float v, int act) {
+  return act == kActRelu ? fmaxf(v, 0.f) : (act == kActLrelu ? (v > 0.f ? v : v * kLreluSlope) : v);
+}
+
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -91,7 +96,7 @@ __device__ __forceinline__ void cp_async_wait() {
 __device__ __forceinline__ int reflect_index(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
 // ------------------------------------------------------------------------------------------------ tensor-core conv
-template <int NT>
+template <int NT, bool RAW>
 __global__ void __launch_bounds__(kGenThreads) gen_conv_tc_kernel(const __grid_constant__ GenConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int S = gen_stages(NT);
@@ -196,39 +201,40 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_tc_kernel(const __grid_c
       tmem_ld16(tacc + (uint32_t)c0, v);
       tmem_ld_wait();
       if (!valid) continue;
-#pragma unroll
+#pragma unroll 1
       for (int hh = 0; hh < 2; ++hh) {
         const int gc = (int)blockIdx.y * (NT / 8) + c0 / 8 + hh;
         if (gc >= p.out_nchunks) continue;
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          float t = __uint_as_float(v[hh * 8 + e]);
+          float t = __uint_as_float(hh ? v[8 + e] : v[e]);
           if (split == 0) t += p.bias[gc * 8 + e];
-          f[e] = apply_act(t, p.act);
+          f[e] = RAW ? t : apply_act(t, p.act);
         }
-        if (p.out_mode == 1) {
+        if constexpr (RAW) {
           float* op = reinterpret_cast<float*>(p.out) + (size_t)split * p.split_stride + (size_t)b * p.out_bs +
                       (size_t)(p.out_chunk0 + gc) * p.out_cs + pix * 8;
           *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
           *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
-        } else if (p.out_mode == 0) {
-          __half* op = reinterpret_cast<__half*>(p.out) + (size_t)b * p.out_bs + (size_t)(p.out_chunk0 + gc) * p.out_cs + pix * 8;
-          uint4 o;
+        } else {
           __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
           __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
-          o.x = *reinterpret_cast<uint32_t*>(&h0);
-          o.y = *reinterpret_cast<uint32_t*>(&h1);
-          o.z = *reinterpret_cast<uint32_t*>(&h2);
-          o.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(op) = o;
-        } else if (gc == 0) {
-          __half* op = reinterpret_cast<__half*>(p.out) + ((size_t)b * p.Hout * p.Wout + pix) * 4;
-          uint2 o;
-          __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
-          o.x = *reinterpret_cast<uint32_t*>(&h0);
-          o.y = *reinterpret_cast<uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(op) = o;
+          if (p.out_mode == 0) {
+            __half* op = reinterpret_cast<__half*>(p.out) + (size_t)b * p.out_bs + (size_t)(p.out_chunk0 + gc) * p.out_cs + pix * 8;
+            uint4 o;
+            o.x = *reinterpret_cast<uint32_t*>(&h0);
+            o.y = *reinterpret_cast<uint32_t*>(&h1);
+            o.z = *reinterpret_cast<uint32_t*>(&h2);
+            o.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(op) = o;
+          } else if (gc == 0) {
+            __half* op = reinterpret_cast<__half*>(p.out) + ((size_t)b * p.Hout * p.Wout + pix) * 4;
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&h0);
+            o.y = *reinterpret_cast<uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(op) = o;
+          }
         }
       }
     }
@@ -273,7 +279,10 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_tc_kernel(const __grid_c
 // SWIZZLE_NONE descriptor into it (rows of a core matrix = 8 consecutive pixels, SBO = tile row pitch, LBO = K-chunk
 // block).  M = 128 is a 16 x 8 pixel sub-patch; J sub-patches side by side share the tile and the weights.  Against the
 // im2col gather above this moves k*k/1.4 times fewer activation bytes (3x3: 6.4x, 7x7: 20x).
-template <int NT, int S>
+// RAW: fp32 output for a norm layer (no activation, optional fused statistics); !RAW: a network's last layer (bias +
+// activation, fp16 chunks or compact tile pixels).  Two kernels because tanh inlined 64 times into one shared epilogue
+// made the function 214 KB of code -- an instruction-cache problem, not an arithmetic one.
+template <int NT, int S, bool RAW>
 __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid_constant__ GenConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -377,85 +386,110 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
     const int oyp = y0 + r;
     const int oy = oyp * p.ostep + p.py[ph];
     const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const bool want_stats = p.stats != nullptr && !(p.debug & 8);
-    int grp = 0;
+    if constexpr (RAW) {
+      const bool want_stats = p.stats != nullptr && !(p.debug & 8);
+      int grp = 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < NT; c0 += 16, ++grp) {
-      float sq[32];   // [0, 16): sums of this thread's pixels (one per sub-patch), [16, 32): sums of squares
+      for (int c0 = 0; c0 < NT; c0 += 16, ++grp) {
+        float sq[32];   // [0, 16): sums of this thread's pixels (one per sub-patch), [16, 32): sums of squares
 #pragma unroll
-      for (int e = 0; e < 32; ++e) sq[e] = 0.f;
-      uint32_t vv[4][16];   // the group's 16 columns of every sub-patch: one TMEM round trip instead of J
+        for (int e = 0; e < 32; ++e) sq[e] = 0.f;
+        uint32_t vv[4][16];   // the group's 16 columns of every sub-patch: one TMEM round trip instead of J
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j < jeff) tmem_ld16(tacc + (uint32_t)(j * NT + c0), vv[j]);
-      tmem_ld_wait();
+        for (int j = 0; j < 4; ++j)
+          if (j < jeff) tmem_ld16(tacc + (uint32_t)(j * NT + c0), vv[j]);
+        tmem_ld_wait();
+        float bias16[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j >= jeff) continue;
-        const uint32_t(&v)[16] = vv[j];
-        const int oxp = x0 + 8 * j + c;
-        const bool valid = oyp < Hp && oxp < Wp;
-        const size_t pix = (size_t)oy * p.Wout + (size_t)(oxp * p.ostep + p.px[ph]);
-        if (!valid) continue;
+        for (int e = 0; e < 16; ++e) bias16[e] = s_bias[c0 + e];
+        const int gc0 = (int)blockIdx.y * (NT / 8) + c0 / 8;
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int gc = (int)blockIdx.y * (NT / 8) + c0 / 8 + hh;
-          if (gc >= p.out_nchunks) continue;
-          float f[8];
+        for (int j = 0; j < 4; ++j) {
+          if (j >= jeff) continue;
+          const int oxp = x0 + 8 * j + c;
+          if (!(oyp < Hp && oxp < Wp)) continue;
+          const size_t pix = (size_t)oy * p.Wout + (size_t)(oxp * p.ostep + p.px[ph]);
+          float* op = reinterpret_cast<float*>(p.out) + (size_t)b * p.out_bs + (size_t)(p.out_chunk0 + gc0) * p.out_cs + pix * 8;
+          float f[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            f[e] = apply_act(__uint_as_float(v[hh * 8 + e]) + s_bias[c0 + hh * 8 + e], p.act);
-            sq[hh * 8 + e] += f[e];
-            sq[16 + hh * 8 + e] = fmaf(f[e], f[e], sq[16 + hh * 8 + e]);
+          for (int e = 0; e < 16; ++e) {
+            f[e] = __uint_as_float(vv[j][e]) + bias16[e];
+            sq[e] += f[e];
+            sq[16 + e] = fmaf(f[e], f[e], sq[16 + e]);
           }
-          if (p.debug & 16) {
-            if (f[0] == 123.456f) p.stats[0] = 1.0;
-          } else if (p.out_mode == 1) {
-            float* op = reinterpret_cast<float*>(p.out) + (size_t)b * p.out_bs + (size_t)(p.out_chunk0 + gc) * p.out_cs + pix * 8;
-            *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
-            *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
-          } else if (p.out_mode == 0) {
-            __half* op = reinterpret_cast<__half*>(p.out) + (size_t)b * p.out_bs + (size_t)(p.out_chunk0 + gc) * p.out_cs + pix * 8;
-            uint4 o;
-            __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
-            __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
-            o.x = *reinterpret_cast<uint32_t*>(&h0);
-            o.y = *reinterpret_cast<uint32_t*>(&h1);
-            o.z = *reinterpret_cast<uint32_t*>(&h2);
-            o.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(op) = o;
-          } else if (gc == 0) {
-            __half* op = reinterpret_cast<__half*>(p.out) + ((size_t)b * p.Hout * p.Wout + pix) * 4;
-            uint2 o;
-            __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
-            o.x = *reinterpret_cast<uint32_t*>(&h0);
-            o.y = *reinterpret_cast<uint32_t*>(&h1);
-            *reinterpret_cast<uint2*>(op) = o;
+          if (!(p.debug & 16)) {
+            if (gc0 < p.out_nchunks) {
+              *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            }
+            if (gc0 + 1 < p.out_nchunks) {
+              *reinterpret_cast<float4*>(op + p.out_cs) = make_float4(f[8], f[9], f[10], f[11]);
+              *reinterpret_cast<float4*>(op + p.out_cs + 4) = make_float4(f[12], f[13], f[14], f[15]);
+            }
+          }
+        }
+        if (want_stats) {
+          // transpose-reduce: 32 values per lane -> lane l holds the warp's total of value l (31 shuffles, fixed order)
+#pragma unroll
+          for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              const float send = upper ? sq[i] : sq[i + n];
+              const float keep = upper ? sq[i + n] : sq[i];
+              sq[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          float* rb = red + (grp & 1) * 128;
+          rb[warp * 32 + lane] = sq[0];
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (warp == 0) {
+            const float tot = ((rb[lane] + rb[32 + lane]) + rb[64 + lane]) + rb[96 + lane];
+            const int ch = (int)blockIdx.y * NT + c0 + (lane & 15);
+            const int chunk = ch >> 3;
+            if (chunk < p.out_nchunks) {
+              const int slice = p.slice0[ph] + band * cps + cp;
+              p.stats[(((size_t)b * p.out_nchunks + chunk) * p.stat_slices + slice) * 16 + (lane < 16 ? 0 : 8) + (ch & 7)] = (double)tot;
+            }
           }
         }
       }
-      if (want_stats) {
-        // transpose-reduce: 32 values per lane -> lane l holds the warp's total of value l (31 shuffles, fixed order)
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+#pragma unroll 1
+        for (int j = 0; j < jeff; ++j) {
+          uint32_t v[16];
+          tmem_ld16(tacc + (uint32_t)(j * NT + c0), v);
+          tmem_ld_wait();
+          const int oxp = x0 + 8 * j + c;
+          if (!(oyp < Hp && oxp < Wp)) continue;
+          const size_t pix = (size_t)oy * p.Wout + (size_t)(oxp * p.ostep + p.px[ph]);
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh) {
+            const int gc = (int)blockIdx.y * (NT / 8) + c0 / 8 + hh;
+            if (gc >= p.out_nchunks) continue;
+            float f[8];
 #pragma unroll
-        for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
-          const bool upper = (lane & off) != 0;
-#pragma unroll
-          for (int i = 0; i < n; ++i) {
-            const float send = upper ? sq[i] : sq[i + n];
-            const float keep = upper ? sq[i + n] : sq[i];
-            sq[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-          }
-        }
-        float* rb = red + (grp & 1) * 128;
-        rb[warp * 32 + lane] = sq[0];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (warp == 0) {
-          const float tot = ((rb[lane] + rb[32 + lane]) + rb[64 + lane]) + rb[96 + lane];
-          const int ch = (int)blockIdx.y * NT + c0 + (lane & 15);
-          const int chunk = ch >> 3;
-          if (chunk < p.out_nchunks) {
-            const int slice = p.slice0[ph] + band * cps + cp;
-            p.stats[(((size_t)b * p.out_nchunks + chunk) * p.stat_slices + slice) * 16 + (lane < 16 ? 0 : 8) + (ch & 7)] = (double)tot;
+            for (int e = 0; e < 8; ++e)
+              f[e] = apply_act(__uint_as_float(hh ? v[8 + e] : v[e]) + s_bias[c0 + hh * 8 + e], p.act);
+            __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+            __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+            if (p.out_mode == 0) {
+              __half* op = reinterpret_cast<__half*>(p.out) + (size_t)b * p.out_bs + (size_t)(p.out_chunk0 + gc) * p.out_cs + pix * 8;
+              uint4 o;
+              o.x = *reinterpret_cast<uint32_t*>(&h0);
+              o.y = *reinterpret_cast<uint32_t*>(&h1);
+              o.z = *reinterpret_cast<uint32_t*>(&h2);
+              o.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(op) = o;
+            } else if (gc == 0) {
+              __half* op = reinterpret_cast<__half*>(p.out) + ((size_t)b * p.Hout * p.Wout + pix) * 4;
+              uint2 o;
+              o.x = *reinterpret_cast<uint32_t*>(&h0);
+              o.y = *reinterpret_cast<uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(op) = o;
+            }
           }
         }
       }
@@ -669,15 +703,15 @@ template <typename T>
 __device__ __forceinline__ void store8(T* p, const float (&f)[8], int act);
 template <>
 __device__ __forceinline__ void store8<float>(float* p, const float (&f)[8], int act) {
-  *reinterpret_cast<float4*>(p) = make_float4(apply_act(f[0], act), apply_act(f[1], act), apply_act(f[2], act), apply_act(f[3], act));
-  *reinterpret_cast<float4*>(p + 4) = make_float4(apply_act(f[4], act), apply_act(f[5], act), apply_act(f[6], act), apply_act(f[7], act));
+  *reinterpret_cast<float4*>(p) = make_float4(apply_act_light(f[0], act), apply_act_light(f[1], act), apply_act_light(f[2], act), apply_act_light(f[3], act));
+  *reinterpret_cast<float4*>(p + 4) = make_float4(apply_act_light(f[4], act), apply_act_light(f[5], act), apply_act_light(f[6], act), apply_act_light(f[7], act));
 }
 template <>
 __device__ __forceinline__ void store8<__half>(__half* p, const float (&f)[8], int act) {
-  __half2 h0 = __floats2half2_rn(apply_act(f[0], act), apply_act(f[1], act));
-  __half2 h1 = __floats2half2_rn(apply_act(f[2], act), apply_act(f[3], act));
-  __half2 h2 = __floats2half2_rn(apply_act(f[4], act), apply_act(f[5], act));
-  __half2 h3 = __floats2half2_rn(apply_act(f[6], act), apply_act(f[7], act));
+  __half2 h0 = __floats2half2_rn(apply_act_light(f[0], act), apply_act_light(f[1], act));
+  __half2 h1 = __floats2half2_rn(apply_act_light(f[2], act), apply_act_light(f[3], act));
+  __half2 h2 = __floats2half2_rn(apply_act_light(f[4], act), apply_act_light(f[5], act));
+  __half2 h3 = __floats2half2_rn(apply_act_light(f[6], act), apply_act_light(f[7], act));
   uint4 o;
   o.x = *reinterpret_cast<uint32_t*>(&h0);
   o.y = *reinterpret_cast<uint32_t*>(&h1);
@@ -742,21 +776,29 @@ std::vector<float> running_scale_shift(const float* gamma, const float* beta, co
   return ss;
 }
 
-template <int NT>
-cudaError_t launch_tc(const GenConvParams& p, dim3 grid, cudaStream_t st) {
+template <int NT, bool RAW>
+cudaError_t launch_tc_r(const GenConvParams& p, dim3 grid, cudaStream_t st) {
   constexpr size_t smem = (size_t)gen_stages(NT) * (kGenABytes + 8 * NT * 16) + kGenTailBytes;
-  cudaError_t e = cudaFuncSetAttribute(gen_conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(gen_conv_tc_kernel<NT, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  gen_conv_tc_kernel<NT><<<grid, kGenThreads, smem, st>>>(p);
+  gen_conv_tc_kernel<NT, RAW><<<grid, kGenThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
+template <int NT>
+cudaError_t launch_tc(const GenConvParams& p, dim3 grid, cudaStream_t st) {
+  return p.out_mode == 1 ? launch_tc_r<NT, true>(p, grid, st) : launch_tc_r<NT, false>(p, grid, st);
+}
 
+template <int NT, int S, bool RAW>
+cudaError_t launch_halo_r(const GenConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(gen_conv_halo_kernel<NT, S, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  gen_conv_halo_kernel<NT, S, RAW><<<grid, kGenThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
 template <int NT, int S>
 cudaError_t launch_halo_s(const GenConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(gen_conv_halo_kernel<NT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  gen_conv_halo_kernel<NT, S><<<grid, kGenThreads, smem, st>>>(p);
-  return cudaGetLastError();
+  return p.out_mode == 1 ? launch_halo_r<NT, S, true>(p, grid, smem, st) : launch_halo_r<NT, S, false>(p, grid, smem, st);
 }
 template <int NT>
 cudaError_t launch_halo(const GenConvParams& p, int stages, dim3 grid, size_t smem, cudaStream_t st) {

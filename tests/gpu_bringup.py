@@ -332,15 +332,17 @@ def stage_ppon_time():
     mac = 9 * 3 * 64 + 28 * 3 * (9 * 64 * 64 + 8 * 9 * 64 * 32 + 256 * 64) + 9 * 64 * 64 \
         + 3 * (4 * 9 * 64 * 64 + 16 * 9 * 64 * 64 + 16 * 9 * 64 * 64 + 16 * 9 * 64 * 3)
     flop = 190 * 200 * 200 * 2.0 * mac
-    for it in range(3):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        eng.upscale_u8_device(din, 200, 0.5, out=dout)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        print("ppon 1080p nb=24 iter=%d: %.1f ms  %.1f out-Mpix/s  %.1f TFLOP/s (%.1f TFLOP per frame)" %
-              (it, ms, 16 * H * W / ms / 1e3, flop / ms / 1e9, flop / 1e12))
+    for mb in [int(v) for v in os.environ.get("INNFER_MB", "95").split(",")]:
+        eng.set_max_batch(mb)
+        for it in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.upscale_u8_device(din, 200, 0.5, out=dout)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            print("ppon 1080p nb=24 max_batch=%d iter=%d: %.1f ms  %.1f out-Mpix/s  %.1f TFLOP/s (%.1f TFLOP per frame)" %
+                  (mb, it, ms, 16 * H * W / ms / 1e3, flop / ms / 1e9, flop / 1e12))
     print("out mean", dout.float().mean().item(), "launches", N.kernel_launches())
     eng.close()
     return True
