@@ -533,6 +533,20 @@ def run_i2i(args, dev, warm):
             if family == "resnet" and size == 1024:
                 head = rec
         net.invalidate_engine()
+        if not args.no_cpu_baseline:
+            # the reference's -cpu mode for the same module (torch fp32 ops on the host cores), bounded: one 256x256 image
+            cpu_net = net.float().cpu()
+            xc = (torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(256)) * 2 - 1)
+            with torch.no_grad():
+                cpu_net.model(xc.clone())
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    cpu_net.model(xc.clone())
+                cpu_ms = (time.perf_counter() - t0) * 1e3 / 3
+            for rec in cases:
+                if rec["net"] == arch:
+                    rec["cpu_256_ms"] = cpu_ms
+                    rec["cpu_cores"] = host_threads()
     clocks = sampler.stop()
     line = {"metric": "output Mpix/s", "value": head["ours"]["mpix_s"], "unit": "Mpix/s", "n_gpus": 1, "steps": args.steps,
             "warmup": max(warm, 3), "ms_per_step": head["ours"]["ms"], "higher_is_better": True, "scaling": "weak",
@@ -546,7 +560,11 @@ def run_i2i(args, dev, warm):
             "roofline": {"bound": "tensor", "achieved": head["ours"]["tflops"], "peak": peak, "unit": "TFLOP/s",
                          "frac": head["ours"]["tflops"] / peak, "traffic": None, "peak_source": peak_src,
                          "kernel": "all kernels of one resnet_9blocks forward at 1024x1024 (convolutions + normalisation)"},
-            "cases": cases, "cpu_baseline": None}
+            "cases": cases,
+            "cpu_baseline": (None if args.no_cpu_baseline else
+                             {"value": 256 * 256 / head["cpu_256_ms"] / 1e3, "unit": "Mpix/s", "cores": head["cpu_cores"],
+                              "kind": "port", "sample": "resnet_9blocks, one 256x256 image through the nn.Module mirror's torch "
+                              "fp32 modules on the host (the -cpu mode; identical module tree and arithmetic to the reference's)"})}
     print(json.dumps(line), flush=True)
 
 
