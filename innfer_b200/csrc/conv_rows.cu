@@ -25,6 +25,9 @@
 //
 // Work split: the nstrips * H (strip, row) units are cut into 148 equal contiguous ranges; a range is
 // a few "pieces" (strip, [ya, yb)), each of which reads input rows ya-1 .. yb.
+#include <cstdio>
+#include <cstdlib>
+
 #include "conv_rows.cuh"
 #include "ptx.cuh"
 
@@ -211,7 +214,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     // in the middle of a stage, while the first half of the stage's MMAs is still queued.
     const bool leader = elect_one();
     const uint32_t idesc = PAIR ? make_idesc_f16_m256(N) : make_idesc_f16(N);
-    const uint32_t dxu = DILV ? (uint32_t)p.dil : 1u;    // pixels (16-byte units) between the horizontal taps
+    const uint32_t dxu = p.dbg_dx0 == 1 ? 0u : (DILV ? (uint32_t)p.dil : 1u);    // pixels (16-byte units) between the horizontal taps
     constexpr uint32_t a_lbo = kRowPx;                   // 16-byte units between the two K chunks
     constexpr uint32_t a_hi = 8u | (1u << 14);           // SBO = 128 B (8 consecutive pixels)
     constexpr uint32_t b_hi = 8u | (1u << 14);
@@ -611,8 +614,35 @@ int launch_rows_res(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num
   cfg.blockDim = dim3(rows_threads(COUT, PAIR));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int na = 0;
+  // INNFER_L2_PERSIST=1 (experiment): mark this conv's wide output chunks as persisting in L2, so that the next conv of
+  // the dense block -- which reads them together with everything before them -- finds them there.  Pays only if a
+  // batch's 32-channel slice fits the persisting carve-out (innfer_rrdb_set_max_batch / INNFER_MB <= ~28 tiles).
+  static const int l2_persist = getenv("INNFER_L2_PERSIST") ? atoi(getenv("INNFER_L2_PERSIST")) : 0;
+  if (l2_persist && p.out_wide) {
+    static size_t max_window = 0, carve = 0;
+    if (!max_window) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceProp prop;
+      cudaGetDeviceProperties(&prop, dev);
+      max_window = (size_t)prop.accessPolicyMaxWindowSize;
+      carve = (size_t)prop.persistingL2CacheMaxSize;
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+      fprintf(stderr, "innfer: L2 persisting carve-out %zu MB, max window %zu MB\n", carve >> 20, max_window >> 20);
+    }
+    const size_t bytes = (size_t)p.out_nchunks * (size_t)p.out_cs * sizeof(__half);
+    if (bytes <= max_window) {
+      attr[na].id = cudaLaunchAttributeAccessPolicyWindow;
+      attr[na].val.accessPolicyWindow.base_ptr = p.out + (size_t)p.out_chunk0 * p.out_cs;
+      attr[na].val.accessPolicyWindow.num_bytes = bytes;
+      attr[na].val.accessPolicyWindow.hitRatio = bytes <= carve ? 1.f : (float)carve / (float)bytes;
+      attr[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      ++na;
+    }
+  }
   if (PAIR) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 2;

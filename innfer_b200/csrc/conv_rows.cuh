@@ -51,6 +51,8 @@ struct ConvRowsParams {
   int raw_chunk0;
   int pdl;               // 1: programmatic dependent launch -- the prologue overlaps the previous kernel's tail
   long long* trace;      // debugging: clock64 samples of CTA 0 (see tests/gpu_bringup.py --stage trace), or null
+  int dbg_dx0;           // timing experiment (INNFER_ROWS_DX0=1, wrong results): all three horizontal taps read the 128-byte
+                         // aligned window, to measure what the 16/32-byte shifted A descriptors cost
 };
 
 int launch_conv_rows(const CUtensorMap* tmap_in, const ConvRowsParams& p, int cout, int num_sms, cudaStream_t stream);
