@@ -47,6 +47,9 @@ WORKLOADS = {
     "chain": {"H": 720, "W": 1280, "chain": [1, 4], "cf": True, "tiles": 84,
               "name": "chained 1x RRDB (23 blocks) + 4x RRDB (23 blocks) fp16 with -cf colour fix, synthetic 1280x720 "
                       "frames, chop_forward 200px tiles step 0.5 (84 + 84 tiles/frame)"},
+    "small": {"name": "4x SRResNet (16 blocks) / PAN (16 SCPA, self attention) / PPON (24 blocks) at their get_network_G_config "
+                      "defaults, random-init, fp16, synthetic 512x512 frames, chop_forward 200px tiles step 0.5 (25 tiles/frame); "
+                      "headline = SRResNet"},
     "i2i": {"name": "pix2pix unet_256 (train-mode BatchNorm, whole image) and CycleGAN resnet_9blocks (InstanceNorm), ngf 64, "
                     "random-init, fp16, synthetic 256x256 and 1024x1024 images, batch 1; headline = resnet_9blocks at 1024x1024"},
 }
@@ -473,6 +476,85 @@ def run_chain(args, dev, warm):
     print(json.dumps(line), flush=True)
 
 
+def run_small(args, dev, warm):
+    """BASELINE configs[3]: the small SR families on 512x512 frames through run.Model / ChainRunner (the CLI's device loop);
+    beside each the unmodified reference (baseline/_ref) on the same GPU: its Model.__call__ (per-tile loop, PyTorch-dispatched
+    cuDNN fp16) wrapped in np2tensor / tensor2np as its main() does."""
+    from innfer_b200 import _native as N
+    from innfer_b200 import run as R
+    from innfer_b200.architectures import get_network
+    from innfer_b200.utils.defaults import get_network_G_config
+    torch.backends.cudnn.benchmark = True
+    ref = load_reference()
+    size = 512
+    frames = [synth_frame(20 + i, size, size) for i in range(2)]
+    d_in = [torch.from_numpy(f).to(dev) for f in frames]
+    out_pix = SCALE * size * SCALE * size
+    cases = []
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    launches0 = N.kernel_launches()
+    td = tempfile.TemporaryDirectory()
+    for arch in ("srgan", "pan", "ppon"):
+        torch.manual_seed(0)
+        net = get_network(get_network_G_config({"type": arch}, SCALE))
+        path = os.path.join(td.name, "%dx_rand_%s.pth" % (SCALE, arch))
+        torch.save(net.state_dict(), path)
+        m = R.Model(path, "infer", SCALE if arch != "srgan" else None, device=dev)
+        m.model.half()
+        runner = R.ChainRunner(R.native_chain([m], dev, True), dev)
+        for i in range(max(warm, 3)):
+            runner.run_device(d_in[i % 2])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            runner.run_device(d_in[i % 2])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        for i in range(2):
+            res = runner(frames[i % 2])
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            res = runner(frames[i % 2])
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        rec = {"net": arch, "ms": ms, "mpix_s": out_pix / ms / 1e3, "e2e_ms": e2e_ms,
+               "checksum": int(np.asarray(res)[::97, ::89].astype(np.int64).sum())}
+        if ref is not None and not args.no_torch_gpu:
+            from utils.utils import np2tensor, tensor2np      # the reference's own (baseline/_ref on sys.path)
+            rm = ref.Model(path, "infer", SCALE if arch != "srgan" else None, device=dev)
+            rm.model.half()
+
+            def one(img):
+                return tensor2np(rm(np2tensor(img).to(dev).half()).detach())
+            one(frames[0])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(2):
+                out = one(frames[i % 2])
+            torch.cuda.synchronize()
+            ref_ms = (time.perf_counter() - t0) * 1e3 / 2
+            rec["torch_gpu_reference_ms"] = ref_ms
+            rec["ours_e2e_over_reference_gpu"] = ref_ms / e2e_ms
+            rec["max_abs_u8_diff_vs_reference_gpu_fp16"] = int(np.abs(np.asarray(out).astype(int) - np.asarray(runner(frames[1])).astype(int)).max())
+            del rm
+        cases.append(rec)
+        del runner, m
+    clocks = sampler.stop()
+    head = cases[0]
+    line = {"metric": "output Mpix/s", "value": head["mpix_s"], "unit": "Mpix/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(warm, 3), "ms_per_step": head["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOADS["small"]["name"],
+                       "l2": "25 tiles of activations (hundreds of MB for the 64-channel nets) exceed L2; two alternating frames"},
+            "e2e": {"value": out_pix / head["e2e_ms"] / 1e3, "unit": "Mpix/s", "ms_per_step": head["e2e_ms"],
+                    "h2d_bytes_per_step": size * size * 3, "d2h_bytes_per_step": out_pix * 3},
+            "gpu_launches": int(N.kernel_launches() - launches0), "clocks": clocks, "roofline": None, "cases": cases,
+            "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
+
+
 def run_i2i(args, dev, warm):
     """BASELINE configs[4]: the two image-to-image generators at 256x256 and 1024x1024 through the nn.Module mirrors (the
     objects run.Model holds); beside each the same module's torch ops on this GPU (PyTorch-dispatched cuDNN, fp16)."""
@@ -607,6 +689,11 @@ def main():
         if world > 1:
             raise SystemExit("--workload chain is a single-GPU workload")
         run_chain(args, dev, warm)
+        return
+    if args.workload == "small":
+        if world > 1:
+            raise SystemExit("--workload small is a single-GPU workload")
+        run_small(args, dev, warm)
         return
     if args.workload == "i2i":
         if world > 1:
