@@ -288,6 +288,9 @@ int innfer_gen_conv(const void* x, int n, int Cin, int hgt, int wid, const float
 /* launches of the halo-tile variant of the generator convolution by this process (the parity tests use it to know
  * which of the two tensor-core kernels served a layer; INNFER_I2I_HALO=0|2 in the environment forces the choice) */
 uint64_t innfer_debug_i2i_halo_launches(void);
+/* forwards of the image-to-image generators served by replaying a recorded CUDA graph (small shapes: the launch sequence of
+ * a (buffers, shape) combination is recorded the second time it is seen; INNFER_I2I_GRAPH=0 disables, 2 records every size) */
+uint64_t innfer_debug_i2i_graph_replays(void);
 
 /* ---- -cf colour correction: replaces color_fix (utils/utils.py:278-315) with srgb2linear /
  *      linear2srgb (utils/colors.py:29-60), cv2.resize(INTER_CUBIC) and cv2.GaussianBlur((3,3),0).

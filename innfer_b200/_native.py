@@ -99,6 +99,7 @@ _PROTOS = {
     "innfer_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _f, _vp, _i, _i, _vp]),
     "innfer_gen_conv": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp]),
     "innfer_debug_i2i_halo_launches": (ctypes.c_uint64, []),
+    "innfer_debug_i2i_graph_replays": (ctypes.c_uint64, []),
     "innfer_color_fix": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp]),
     "innfer_color_fix_host": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i]),
 }

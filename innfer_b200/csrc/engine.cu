@@ -1807,6 +1807,7 @@ int innfer_gen_conv(const void* x, int n, int Cin, int hgt, int wid, const float
 }
 
 uint64_t innfer_debug_i2i_halo_launches(void) { return i2i_halo_launches(); }
+uint64_t innfer_debug_i2i_graph_replays(void) { return i2i_graph_replays(); }
 
 int innfer_debug_conv_loop(int Cin, int Cout, int B, int H, int W, int with_res, int warm, int iters, float* ms_out) {
   if (!ms_out) return fail(INNFER_E_INVALID, "null argument");

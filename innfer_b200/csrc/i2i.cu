@@ -779,8 +779,14 @@ std::vector<float> running_scale_shift(const float* gamma, const float* beta, co
 template <int NT, bool RAW>
 cudaError_t launch_tc_r(const GenConvParams& p, dim3 grid, cudaStream_t st) {
   constexpr size_t smem = (size_t)gen_stages(NT) * (kGenABytes + 8 * NT * 16) + kGenTailBytes;
-  cudaError_t e = cudaFuncSetAttribute(gen_conv_tc_kernel<NT, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static bool attr_set[64] = {};   // once per kernel and device (not per launch: launches may be recorded into a CUDA graph)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(gen_conv_tc_kernel<NT, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
   gen_conv_tc_kernel<NT, RAW><<<grid, kGenThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
@@ -791,8 +797,15 @@ cudaError_t launch_tc(const GenConvParams& p, dim3 grid, cudaStream_t st) {
 
 template <int NT, int S, bool RAW>
 cudaError_t launch_halo_r(const GenConvParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(gen_conv_halo_kernel<NT, S, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static bool attr_set[64] = {};   // once per kernel and device, at the largest size any launch asks for
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(gen_conv_halo_kernel<NT, S, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(227 * 1024));
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
   gen_conv_halo_kernel<NT, S, RAW><<<grid, kGenThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
@@ -811,15 +824,19 @@ cudaError_t launch_halo(const GenConvParams& p, int stages, dim3 grid, size_t sm
 }
 
 std::atomic<uint64_t> g_halo_launches{0};
+std::atomic<uint64_t> g_graph_replays{0};
 constexpr size_t kSmemMax = 227 * 1024;
 constexpr size_t kSmemHalf = 113 * 1024;   // two CTAs per SM: one CTA's epilogue overlaps the other's main loop
 
 }  // namespace
 
 uint64_t i2i_halo_launches() { return g_halo_launches.load(); }
+uint64_t i2i_graph_replays() { return g_graph_replays.load(); }
 
 // ==================================================================================================== host side
 I2INet::~I2INet() {
+  drop_graphs();
+  if (cap_) cudaStreamDestroy(cap_);
   for (void* p : owned_) cudaFree(p);
   for (auto* v : {&dbuf_, &cat_, &rb_})
     for (auto& b : *v)
@@ -830,6 +847,11 @@ I2INet::~I2INet() {
 
 int I2INet::need(Buf& b, size_t bytes) {
   if (bytes <= b.bytes) return 0;
+  if (capturing_) {   // cannot happen: a shape is captured only after an eager run of the same shape sized every buffer
+    err_ = "internal: workspace growth during graph capture";
+    return -3;
+  }
+  drop_graphs();      // recorded launches point into the buffers that are about to move
   if (b.p) cudaFree(b.p);
   b.p = nullptr;
   b.bytes = 0;
@@ -1671,12 +1693,10 @@ int I2INet::forward_resnet(const void* in, int in_CT, int B, int H, int W, GenVi
   return conv_final(down_[li], va, B, H, W, out, cfg_.unit_io ? kActTanh01 : kActTanh, compact4, st);
 }
 
-int I2INet::forward(const void* in, int in_CT, int B, int H, int W, GenView out, bool compact4, bool per_sample, cudaStream_t st,
-                    std::string& err) {
-  int rc = check_size(H, W, err);
-  if (rc) return rc;
-  err_.clear();
+int I2INet::forward_eager(const void* in, int in_CT, int B, int H, int W, GenView out, bool compact4, bool per_sample,
+                          cudaStream_t st) {
   if (cfg_.kind == 2) {
+    int rc;
     GenView x{const_cast<void*>(in), in_CT, 0};
     if (cfg_.sl_final) {
       rc = conv_final(down_[0], x, B, H, W, out, cfg_.sl_act, compact4, st);
@@ -1687,11 +1707,80 @@ int I2INet::forward(const void* in, int in_CT, int B, int H, int W, GenView out,
         rc = norm_apply(cfg_.sl_norm ? &dnorm_[0] : nullptr, raw, B, cfg_.sl_cout, down_[0].out_h(H), down_[0].out_h(W),
                         per_sample, cfg_.sl_act, out, 0, nullptr, nullptr, st);
     }
+    return rc;
+  }
+  return cfg_.kind == 0 ? forward_unet(in, in_CT, B, H, W, out, compact4, per_sample, st)
+                        : forward_resnet(in, in_CT, B, H, W, out, compact4, per_sample, st);
+}
+
+void I2INet::drop_graphs() {
+  for (auto& kv : graphs_)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  graphs_.clear();
+}
+
+// Small problems are launch-latency bound (resnet_9blocks at 256x256: 91 launches in 1.1 ms): the launch sequence of a
+// (pointers, shape) combination is recorded into a CUDA graph the second time it is seen and replayed from then on.
+// The first call runs eagerly and sizes every buffer; a later buffer growth drops all graphs.  INNFER_I2I_GRAPH=0 disables.
+int I2INet::forward(const void* in, int in_CT, int B, int H, int W, GenView out, bool compact4, bool per_sample, cudaStream_t st,
+                    std::string& err) {
+  int rc = check_size(H, W, err);
+  if (rc) return rc;
+  err_.clear();
+  static const int graph_mode = getenv("INNFER_I2I_GRAPH") ? atoi(getenv("INNFER_I2I_GRAPH")) : 1;
+  const bool small = (long long)B * H * W <= (graph_mode == 2 ? (1ll << 40) : 512ll * 512);
+  if (!graph_mode || cfg_.kind == 2 || !small) {
+    rc = forward_eager(in, in_CT, B, H, W, out, compact4, per_sample, st);
     if (rc) err = err_;
     return rc;
   }
-  rc = cfg_.kind == 0 ? forward_unet(in, in_CT, B, H, W, out, compact4, per_sample, st)
-                      : forward_resnet(in, in_CT, B, H, W, out, compact4, per_sample, st);
+  const GraphKey key{in, out.base, in_CT, B, H, W, out.CT, out.chunk0, compact4, per_sample};
+  auto it = graphs_.find(key);
+  if (it == graphs_.end()) {   // first sight: eager (allocations, kernel attributes), remember the shape
+    rc = forward_eager(in, in_CT, B, H, W, out, compact4, per_sample, st);
+    if (rc) {
+      err = err_;
+      return rc;
+    }
+    graphs_[key] = GraphEntry{};
+    return 0;
+  }
+  if (!it->second.exec && !it->second.failed) {
+    // record on an internal stream (the caller's may be the legacy default stream, which cannot be captured)
+    if (!cap_ && cudaStreamCreateWithFlags(&cap_, cudaStreamNonBlocking) != cudaSuccess) cap_ = nullptr;
+    cudaGraph_t graph = nullptr;
+    const uint64_t l0 = launches_;
+    bool ok = cap_ && cudaStreamBeginCapture(cap_, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      capturing_ = true;
+      rc = forward_eager(in, in_CT, B, H, W, out, compact4, per_sample, cap_);
+      capturing_ = false;
+      ok = cudaStreamEndCapture(cap_, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
+    }
+    const uint64_t recorded = launches_ - l0;
+    launches_ = l0;   // nothing ran yet
+    if (ok) ok = cudaGraphInstantiate(&it->second.exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      it->second.exec = nullptr;
+      it->second.failed = true;   // keep serving this shape eagerly
+    } else {
+      it->second.launches = recorded;
+    }
+  }
+  if (it->second.exec) {
+    const cudaError_t e = cudaGraphLaunch(it->second.exec, st);
+    if (e != cudaSuccess) {
+      err = std::string("graph launch failed: ") + cudaGetErrorString(e);
+      return -3;
+    }
+    launches_ += it->second.launches;
+    ++graph_replays_;
+    g_graph_replays.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
+  rc = forward_eager(in, in_CT, B, H, W, out, compact4, per_sample, st);
   if (rc) err = err_;
   return rc;
 }

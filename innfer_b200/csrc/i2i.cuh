@@ -17,7 +17,9 @@
 #include <stdint.h>
 
 #include <functional>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 namespace innfer {
@@ -87,6 +89,7 @@ struct I2ICfg {
 // key lookup into the loaded state dict: returns the data and fills `shape`, or nullptr
 using ParamLookup = std::function<const float*(const std::string& key, std::vector<int64_t>& shape)>;
 
+uint64_t i2i_graph_replays();   // forwards of the generators served by replaying a recorded CUDA graph (this process)
 uint64_t i2i_halo_launches();   // launches of the halo-tile kernel by this process (tests: which kernel served a layer)
 
 class I2INet {
@@ -105,6 +108,7 @@ class I2INet {
   int check_size(int H, int W, std::string& err) const;
   int out_size(int n) const { return cfg_.kind == 2 ? down_[0].out_h(n) : n; }
   uint64_t launches() const { return launches_; }
+  uint64_t graph_replays() const { return graph_replays_; }   // forwards served by replaying a recorded CUDA graph
 
  private:
   struct Norm {
@@ -137,8 +141,30 @@ class I2INet {
                  int act_b, const GenView* out_b, const GenView* res, cudaStream_t st);
   int forward_unet(const void* in, int in_CT, int B, int H, int W, GenView out, bool compact4, bool per_sample, cudaStream_t st);
   int forward_resnet(const void* in, int in_CT, int B, int H, int W, GenView out, bool compact4, bool per_sample, cudaStream_t st);
+  int forward_eager(const void* in, int in_CT, int B, int H, int W, GenView out, bool compact4, bool per_sample, cudaStream_t st);
+  void drop_graphs();
   size_t esz() const { return cfg_.fp16 ? 2 : 4; }
   GenView view(Buf& b, int CT, int chunk0) const { return GenView{b.p, CT, chunk0}; }
+  // CUDA graphs of whole forwards, keyed by everything the recorded launches depend on
+  struct GraphKey {
+    const void* in;
+    void* out;
+    int in_CT, B, H, W, out_CT, out_chunk0;
+    bool compact4, per_sample;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(in, out, in_CT, B, H, W, out_CT, out_chunk0, compact4, per_sample) <
+             std::tie(o.in, o.out, o.in_CT, o.B, o.H, o.W, o.out_CT, o.out_chunk0, o.compact4, o.per_sample);
+    }
+  };
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches = 0;
+    bool failed = false;
+  };
+  std::map<GraphKey, GraphEntry> graphs_;
+  cudaStream_t cap_ = nullptr;
+  bool capturing_ = false;
+  uint64_t graph_replays_ = 0;
 
   I2ICfg cfg_;
   int num_sms_ = 148;

@@ -301,3 +301,27 @@ def test_cli_gpu_matches_cli_cpu(dev, tmp_path, monkeypatch, arch, shape):
     assert a.shape == b.shape and a.shape[0] % 4 == 0
     assert np.abs(a.astype(int) - b.astype(int)).max() <= 1
     assert psnr_u8(a, b) >= 50.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family,kw,seed,shape", [("unet", dict(num_downs=5, ngf=8, norm="batch"), 81, (1, 3, 64, 96)),
+                                                  ("resnet", dict(n_blocks=2, ngf=16, norm="instance"), 82, (2, 3, 40, 52))])
+def test_graph_replay_is_bit_identical(dev, family, kw, seed, shape):
+    """Small forwards are recorded into a CUDA graph the second time a (buffers, shape) combination is seen: the eager
+    first call, the recording call and the replays must give the same bits, for a new input in the same buffers too."""
+    from innfer_b200 import _native as native
+    lib = native.load()
+    sd = _state_dict(family, kw, seed)
+    net = _mirror(family, kw, sd, True).to(dev).half()
+    x = _input(seed, shape).to(dev, torch.float16)
+    n0 = lib.innfer_debug_i2i_graph_replays()
+    with torch.no_grad():
+        ys = [net(x).clone() for _ in range(4)]
+        y_other = net(-x)
+        y_back = net(x)
+    assert lib.innfer_debug_i2i_graph_replays() - n0 >= 4
+    for y in ys[1:] + [y_back]:
+        assert torch.equal(y, ys[0])
+    assert not torch.equal(y_other, ys[0])
+    ref = _oracle(family, sd, _input(seed, shape), kw, True)
+    assert (ys[0].float().cpu() - ref).abs().max().item() < 0.02

@@ -7,15 +7,23 @@ counts = collections.Counter()
 other = []
 kind = None
 threads = []
+pending = []       # raw lines of the record being read
+unmatched = []     # records that did not yield two thread lines
+headers = 0
 for line in sys.stdin:
-    m = re.search(r"Potential (\w+) hazard detected at (__shared__|__global__|\w+)", line)
+    m = re.search(r"(?:Potential )?(\w+) hazard detected at (__shared__|__global__|\w+)", line)
     if m:
-        kind, threads = m.group(1) + " " + m.group(2), []
+        if kind is not None and len(unmatched) < 5:
+            unmatched.append(pending)
+        headers += 1
+        kind, threads, pending = m.group(1) + " " + m.group(2), [], [line.rstrip()]
         continue
-    m = re.search(r"(Read|Write) Thread .* at (.*?)\+0x[0-9a-f]+ in (\S+)", line)
+    if kind is not None:
+        pending.append(line.rstrip())
+    m = re.search(r"(Read|Write) Thread .* at (.*?)\+0x[0-9a-f]+(?: in (\S+))?", line)
     if m and kind:
         kern = re.sub(r"\(.*", "", m.group(2)).split("::")[-1]
-        threads.append("%s %s @ %s" % (m.group(1), kern, m.group(3)))
+        threads.append("%s %s @ %s" % (m.group(1), kern, m.group(3) or "?"))
         if len(threads) == 2:
             counts[(kind, threads[0], threads[1])] += 1
             kind = None
@@ -25,6 +33,9 @@ for line in sys.stdin:
 print("racecheck hazards folded by (kind, first access, second access):")
 for (k, a, b), n in counts.most_common():
     print("%9d  %-16s %s  |  %s" % (n, k, a, b))
-print("total hazards: %d" % sum(counts.values()))
+print("total hazards folded: %d of %d hazard records" % (sum(counts.values()), headers))
+for rec in unmatched:
+    print("---- record without two thread lines:")
+    print("\n".join(rec[:8]))
 print("---- other output")
 print("\n".join(other[-12:]))
