@@ -61,6 +61,7 @@ struct GenConvParams {
   // pixels go to stats[((b * out_nchunks + chunk) * stat_slices + slice) * 16 + {e, 8 + e}], slice = slice0[phase] + tile
   double* stats;
   int stat_slices, slice0[kGenMaxPhases];
+  int split_for_halo;   // nsplit was chosen for the halo-tile kernel (else a split launch belongs to the im2col kernel)
   int debug;   // INNFER_I2I_DEBUG bit mask for timing experiments (wrong results): 1 no MMA, 2 no A gather, 4 no weight copy
 };
 
@@ -286,7 +287,8 @@ template <int NT, int S, bool RAW>
 __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid_constant__ GenConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ph = blockIdx.z;
+  // split-K (raw outputs only): the 16-channel slabs [i0, i0 + nslabs) of this CTA go to partial tensor `split`
+  const int ph = (int)blockIdx.z / p.nsplit, split = (int)blockIdx.z - ph * p.nsplit;
   const int bands = p.bands[ph], cps = p.cps[ph];
   int t = blockIdx.x;
   if (t >= p.B * bands * cps) return;
@@ -303,7 +305,8 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
   const uint32_t A_BYTES = (2u * (uint32_t)Npos * 16u + 127u) & ~127u;
   const uint32_t B_BYTES = (uint32_t)ntaps * 2u * NT * 16u;
   const uint32_t STAGE = p.stage_bytes;
-  const int nslabs = p.nslabs;
+  const int i0 = (int)((long long)p.nslabs * split / p.nsplit);
+  const int nslabs = (int)((long long)p.nslabs * (split + 1) / p.nsplit) - i0;
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)S * STAGE);
   uint64_t* empty_bar = full_bar + S;
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
     const int tid = threadIdx.x;
     const __half* inb = reinterpret_cast<const __half*>(p.in) + (size_t)b * p.in_bs + (size_t)p.in_chunk0 * p.in_cs;
     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(reinterpret_cast<const __half*>(p.w) + p.woff[ph]) +
-                          (size_t)blockIdx.y * nslabs * B_BYTES;
+                          ((size_t)blockIdx.y * p.nslabs + i0) * B_BYTES;
     for (int i = 0; i < nslabs; ++i) {
       const int s = i % S;
       mbar_wait(smem_u32(&empty_bar[s]), (((uint32_t)(i / S)) & 1u) ^ 1u);
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
       }
 #pragma unroll
       for (int kc = 0; kc < 2; ++kc) {
-        const int chunk = 2 * i + kc;
+        const int chunk = 2 * (i0 + i) + kc;
         const bool cv = chunk < p.cin_chunks;   // odd chunk counts: the second K-chunk of the last slab is zeros
         const __half* cb = inb + (size_t)chunk * p.in_cs;
         const uint32_t dst = a_dst + (uint32_t)kc * (uint32_t)Npos * 16u;
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
         tmem_ld_wait();
         float bias16[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) bias16[e] = s_bias[c0 + e];
+        for (int e = 0; e < 16; ++e) bias16[e] = split == 0 ? s_bias[c0 + e] : 0.f;
         const int gc0 = (int)blockIdx.y * (NT / 8) + c0 / 8;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -409,7 +412,8 @@ __global__ void __launch_bounds__(kGenThreads) gen_conv_halo_kernel(const __grid
           const int oxp = x0 + 8 * j + c;
           if (!(oyp < Hp && oxp < Wp)) continue;
           const size_t pix = (size_t)oy * p.Wout + (size_t)(oxp * p.ostep + p.px[ph]);
-          float* op = reinterpret_cast<float*>(p.out) + (size_t)b * p.out_bs + (size_t)(p.out_chunk0 + gc0) * p.out_cs + pix * 8;
+          float* op = reinterpret_cast<float*>(p.out) + (size_t)split * p.split_stride + (size_t)b * p.out_bs +
+                      (size_t)(p.out_chunk0 + gc0) * p.out_cs + pix * 8;
           float f[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
@@ -1351,7 +1355,7 @@ bool halo_geometry_ok(const GenConv& L, const GenConvParams& p) {
 // The halo-tile kernel when the layer has enough pixels to fill 16 x 8J patches and CTAs; fills p's halo fields.
 bool halo_setup(const GenConv& L, GenConvParams& p, int num_sms, dim3& grid, size_t& smem, int& stages) {
   const int mode = halo_mode();
-  if (mode == 0 || p.nsplit != 1 || !halo_geometry_ok(L, p)) return false;
+  if (mode == 0 || (p.nsplit != 1 && !(p.split_for_halo && p.out_mode == 1)) || !halo_geometry_ok(L, p)) return false;
   p.debug = getenv("INNFER_I2I_DEBUG") ? atoi(getenv("INNFER_I2I_DEBUG")) : 0;
   // sub-patches per CTA: 4 x NT accumulator columns must fit TMEM's 512.  With NT = 128 that is the whole TMEM (one CTA per
   // SM, no second CTA to hide the epilogue) but it halves the weight bytes per MMA, which is what bounds the wide layers
@@ -1401,7 +1405,7 @@ bool halo_setup(const GenConv& L, GenConvParams& p, int num_sms, dim3& grid, siz
       p.tap_aoff[ph][t] = (uint16_t)((size_t)L.h_tap_pl[ph][t] * p.Rpl[ph] * p.Wpl[ph] + (size_t)L.h_tap_dr[ph][t] * p.Wpl[ph] +
                                      L.h_tap_dc[ph][t]);
   }
-  if (mode != 2 && max_tiles * L.ntiles_h * L.nphase * 4 < num_sms) return false;   // too few CTAs: im2col kernel
+  if (mode != 2 && max_tiles * L.ntiles_h * L.nphase * p.nsplit * 4 < num_sms) return false;   // too few CTAs: im2col kernel
   p.stat_slices = 0;
   for (int ph = 0; ph < L.nphase; ++ph) {
     p.slice0[ph] = p.stat_slices;
@@ -1424,7 +1428,7 @@ bool halo_setup(const GenConv& L, GenConvParams& p, int num_sms, dim3& grid, siz
   while (cols < J * L.NTh) cols *= 2;
   p.tmem_cols = cols;
   smem = (size_t)stages * stage + tail;
-  grid = dim3((unsigned)max_tiles, (unsigned)L.ntiles_h, (unsigned)L.nphase);
+  grid = dim3((unsigned)max_tiles, (unsigned)L.ntiles_h, (unsigned)(L.nphase * p.nsplit));
   p.w = L.d_w16h;
   for (int ph = 0; ph < L.nphase; ++ph) p.woff[ph] = (long long)L.ph_woffh[ph];
   return true;
@@ -1442,7 +1446,7 @@ cudaError_t launch_conv(const GenConv& L, GenConvParams& p, bool fp16, int num_s
     int hstages = 0;
     if (halo_setup(L, p, num_sms, hgrid, hsmem, hstages)) {
       g_halo_launches.fetch_add(1, std::memory_order_relaxed);
-      if (stats_alloc && p.out_mode == 1) {
+      if (stats_alloc && p.out_mode == 1 && p.nsplit == 1) {
         p.stats = (*stats_alloc)((size_t)p.B * p.out_nchunks * p.stat_slices * 16);
         if (p.stats && stat_slices) *stat_slices = p.stat_slices;
       }
@@ -1478,7 +1482,21 @@ int I2INet::conv_raw(const GenConv& L, GenView in, int B, int Hin, int Win, Raw&
   fill_params(p, L, in, B, Hin, Win, Hout, Wout, esz());
   // split K across CTAs when the layer has too few output tiles to fill the GPU (inner levels of the UNet)
   int nsplit = 1;
-  if (cfg_.fp16) {
+  bool halo_split = false;
+  if (cfg_.fp16 && halo_mode() != 0 && halo_geometry_ok(L, p)) {
+    // mid-size layers (UNet 256 -> 512 at 64 x 64: 64 tiles for 148 SMs, 16 slabs of 100 KB each): the halo kernel with
+    // the slabs of a tile split over up to four CTAs
+    int J = L.NTh >= 128 ? 2 : 4, tiles = 0;
+    for (int ph = 0; ph < L.nphase; ++ph) J = std::min(J, (p.Wp[ph] + 7) / 8);
+    for (int ph = 0; ph < L.nphase; ++ph) tiles += p.B * ((p.Hp[ph] + 15) / 16) * ((p.Wp[ph] + 8 * J - 1) / (8 * J));
+    const int ctas = tiles * L.ntiles_h;
+    static const int hs = getenv("INNFER_I2I_HALO_SPLIT") ? atoi(getenv("INNFER_I2I_HALO_SPLIT")) : 1;
+    if (hs && ctas * 4 >= num_sms_ && ctas < num_sms_ && L.nslabs >= 8) {
+      nsplit = std::max(1, std::min({4, num_sms_ / ctas, L.nslabs / 4}));
+      halo_split = nsplit > 1;
+    }
+  }
+  if (cfg_.fp16 && !halo_split) {
     const int ctas = ((max_m(p) + 127) / 128) * L.ntiles * L.nphase;
     int ksmin = 1 << 30;
     for (int ph = 0; ph < L.nphase; ++ph) ksmin = std::min(ksmin, L.ph_ksteps[ph]);
@@ -1497,6 +1515,7 @@ int I2INet::conv_raw(const GenConv& L, GenView in, int B, int Hin, int Win, Raw&
   p.out_chunk0 = 0;
   p.out_mode = 1;
   p.nsplit = nsplit;
+  p.split_for_halo = halo_split ? 1 : 0;
   p.split_stride = (long long)per;
   p.act = kActNone;
   // statistics of the norm layer that follows, fused into the halo kernel's epilogue when that kernel takes the layer
@@ -1742,6 +1761,7 @@ int I2INet::forward(const void* in, int in_CT, int B, int H, int W, GenView out,
       err = err_;
       return rc;
     }
+    if (graphs_.size() >= 64) drop_graphs();   // a caller that keeps changing buffers: do not hoard recordings
     graphs_[key] = GraphEntry{};
     return 0;
   }

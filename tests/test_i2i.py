@@ -171,11 +171,14 @@ GEN_CONVS = [
     dict(cin=40, cout=256, h=70, w=41, k=4, stride=2, bias=False, norm=2, act=2),
     dict(cin=136, cout=72, h=21, w=19, k=4, stride=2, transposed=True, norm=2, act=1, n=2),
     dict(cin=8, cout=8, h=33, w=130, k=7, pad=3, reflect=True, act=3, final=True, n=2),
+    # under one wave of halo tiles with a long K: the slabs of a tile split over two CTAs (fp32 partial tensors)
+    dict(cin=128, cout=256, h=64, w=96, k=3, reflect=True, norm=1, act=1),
+    dict(cin=256, cout=256, h=64, w=64, k=4, stride=2, bias=False, norm=2, act=2, n=2),
 ]
 
 
 # layers of GEN_CONVS whose geometry the halo-tile kernel takes (at least 8 x 8 output pixels per phase)
-HALO_CASES = (0, 1, 2, 6, 7, 8, 9, 10, 12, 13, 14, 15, 16, 17, 18, 19, 20)
+HALO_CASES = (0, 1, 2, 6, 7, 8, 9, 10, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22)
 
 
 @pytest.mark.gpu
