@@ -1,5 +1,7 @@
 #include "pixel_ops.cuh"
 
+#include <vector>
+
 #include <cmath>
 
 namespace innfer {
@@ -229,12 +231,55 @@ __global__ void blend_kernel(const E* __restrict__ tiles, int CT, const __grid_c
 // 4 (every reference geometry with an even tile size and scale 4; checked on the host): one thread
 // produces 4 consecutive pixels, which share their covering tiles, and stores 12 bytes (uint8 HWC)
 // or 8 bytes per channel plane (fp16 NCHW) at once.  Same accumulation order as the scalar kernel.
+// The profile of one tile axis, evaluated once per geometry by the same device function the scalar kernel calls per
+// pixel (so both kernels see identical floats): prof[i] = blend_profile(i, P, overlap).
+__global__ void blend_profile_table_kernel(int P, int overlap, float* __restrict__ prof) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) prof[i] = blend_profile(i, P, overlap);
+}
+
+// The tiles covering position v of one axis, in the reference's accumulation order (regular tiles ascending, then the
+// edge-anchored last tile): indices into t[], local coordinates into l[]; returns the count (<= 4).
+__device__ __forceinline__ int covering_axis(int v, int P, int eff, int nt, const int* origins, int (&t)[4], int (&l)[4]) {
+  const int hi = min(v / eff, nt - 1);
+  const int lo = max(0, (v - P) / eff);
+  int n = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int a = pass == 0 ? lo : nt - 1;
+    const int b = pass == 0 ? hi : (hi < nt - 1 ? nt - 1 : nt - 2);
+    for (int i = a; i <= b; ++i) {
+      const int loc = v - origins[i];
+      if (loc < 0 || loc >= P || n >= 3) continue;
+      t[n] = i;
+      l[n] = loc;
+      ++n;
+    }
+  }
+  return n;
+}
+
 template <int DT, typename E, bool COMPACT>
 __global__ void blend_vec4_kernel(const E* __restrict__ tiles, int CT, const __grid_constant__ BlendGeom g,
-                                  void* __restrict__ dst) {
+                                  const float* __restrict__ prof, void* __restrict__ dst) {
   const int X0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int Y = blockIdx.y;
+  // the row's covering tiles and their vertical weights are the same for the whole block
+  __shared__ int s_ny, s_ty[4], s_ly[4];
+  __shared__ float s_wy[4];
+  if (threadIdx.x == 0) {
+    int t[4], l[4];
+    const int n = covering_axis(Y, g.P, g.eff, g.nty, g.oys, t, l);
+    s_ny = n;
+    for (int i = 0; i < n; ++i) {
+      s_ty[i] = t[i];
+      s_ly[i] = l[i];
+      s_wy[i] = prof[l[i]];
+    }
+  }
+  __syncthreads();
   if (X0 >= g.Ws) return;
+  int tx[4], lx[4];
+  const int nx = covering_axis(X0, g.P, g.eff, g.ntx, g.oxs, tx, lx);   // 4 consecutive pixels share their tiles
   float acc[4][3];
   float wsum[4];
 #pragma unroll
@@ -242,38 +287,51 @@ __global__ void blend_vec4_kernel(const E* __restrict__ tiles, int CT, const __g
     wsum[k] = 0.f;
     acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
   }
-  for_each_covering_tile(g, Y, X0, [&](int ty, int tx, int ly, int lx) {
-    const float wy = blend_profile(ly, g.P, g.overlap);
-    const size_t t = (size_t)ty * g.ntx + tx;
-    if (COMPACT) {
-      // 4 pixels x 4 halves = 32 contiguous, 32-byte aligned bytes (lx and P are multiples of 4)
-      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(tiles) +
-                                                        ((t * g.P + ly) * g.P + lx) * 4);
-      const uint4 a = src[0], b = src[1];
-      const uint32_t raw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  const int ny = s_ny;
+  // at most three tiles cover a position per axis (two regular ones + the edge-anchored last one); fixed trip counts
+  // with predicates keep tx / lx in registers
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float w = blend_profile(lx + k, g.P, g.overlap) * wy;
-        const float2 rg = __half22float2(*reinterpret_cast<const __half2*>(&raw[2 * k]));
-        const float2 bx = __half22float2(*reinterpret_cast<const __half2*>(&raw[2 * k + 1]));
-        acc[k][0] += rg.x * w;
-        acc[k][1] += rg.y * w;
-        acc[k][2] += bx.x * w;
-        wsum[k] += w;
-      }
-    } else {
+  for (int iy = 0; iy < 3; ++iy) {
+    if (iy >= ny) break;
+    const float wy = s_wy[iy];
+    const int ly = s_ly[iy];
+    const size_t trow = (size_t)s_ty[iy] * g.ntx;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float w = blend_profile(lx + k, g.P, g.overlap) * wy;
-        float f[8];
-        load_chunk<E>(tiles, (t * CT * g.P + ly) * g.P + lx + k, f);
-        acc[k][0] += f[0] * w;
-        acc[k][1] += f[1] * w;
-        acc[k][2] += f[2] * w;
-        wsum[k] += w;
+    for (int ix = 0; ix < 3; ++ix) {
+      if (ix >= nx) break;
+      const size_t t = trow + tx[ix];
+      const float4 wx = *reinterpret_cast<const float4*>(prof + lx[ix]);   // lx and the table are 16-byte aligned
+      const float w4[4] = {wx.x * wy, wx.y * wy, wx.z * wy, wx.w * wy};
+      if (COMPACT) {
+        // 4 pixels x 4 halves = 32 contiguous, 32-byte aligned bytes (lx and P are multiples of 4)
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(tiles) +
+                                                          ((t * g.P + ly) * g.P + lx[ix]) * 4);
+        const uint4 a = src[0], b = src[1];
+        const uint32_t raw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float w = w4[k];
+          const float2 rg = __half22float2(*reinterpret_cast<const __half2*>(&raw[2 * k]));
+          const float2 bx = __half22float2(*reinterpret_cast<const __half2*>(&raw[2 * k + 1]));
+          acc[k][0] += rg.x * w;
+          acc[k][1] += rg.y * w;
+          acc[k][2] += bx.x * w;
+          wsum[k] += w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float w = w4[k];
+          float f[8];
+          load_chunk<E>(tiles, (t * CT * g.P + ly) * g.P + lx[ix] + k, f);
+          acc[k][0] += f[0] * w;
+          acc[k][1] += f[1] * w;
+          acc[k][2] += f[2] * w;
+          wsum[k] += w;
+        }
       }
     }
-  });
+  }
   const size_t plane = (size_t)g.Hs * g.Ws;
   const size_t pix = (size_t)Y * g.Ws + X0;
   if (DT == kU8) {
@@ -377,6 +435,30 @@ int image_to_tiles_impl(const void* src, PixelDType st, int C, const TilePlan& p
   return (int)cudaGetLastError();
 }
 
+// Per (device, tile size, overlap) profile table of the vector blend kernel; built on first use on the caller's stream
+// (later launches on other streams of the same device find it complete: the build is tiny and the first launch that
+// needs it is ordered behind it; the cache is per thread like the rest of the per-call scratch).
+const float* blend_profile_table(int P, int overlap, cudaStream_t stream) {
+  struct Entry {
+    int dev, P, overlap;
+    float* p;
+  };
+  static thread_local std::vector<Entry> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  for (const Entry& e : cache)
+    if (e.dev == dev && e.P == P && e.overlap == overlap) return e.p;
+  float* p = nullptr;
+  if (cudaMalloc(&p, ((size_t)P + 4) * sizeof(float)) != cudaSuccess) return nullptr;
+  blend_profile_table_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, overlap, p);
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) {
+    cudaFree(p);
+    return nullptr;
+  }
+  cache.push_back(Entry{dev, P, overlap, p});
+  return p;
+}
+
 template <typename E>
 int blend_impl(const E* tiles, int CT, const TilePlan& plan, int scale, int C, void* dst, PixelDType dt,
                cudaStream_t stream) {
@@ -416,9 +498,14 @@ int blend_impl(const E* tiles, int CT, const TilePlan& plan, int scale, int C, v
   bool vec = (C == 3) && (g.P % 4 == 0) && (g.Ws % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
   for (int i = 0; i < g.ntx && vec; ++i) vec = (g.oxs[i] % 4 == 0);
   dim3 block(128), grid(vec ? (g.Ws / 4 + 127) / 128 : (g.Ws + 127) / 128, g.Hs);
+  const float* prof = nullptr;
+  if (vec) {
+    prof = blend_profile_table(g.P, g.overlap, stream);
+    if (!prof) return (int)cudaErrorMemoryAllocation;
+  }
 #define INNFER_BLEND_LAUNCH(DT, COMPACT)                                                        \
   do {                                                                                          \
-    if (vec) blend_vec4_kernel<DT, E, COMPACT><<<grid, block, 0, stream>>>(tiles, CT, g, dst);  \
+    if (vec) blend_vec4_kernel<DT, E, COMPACT><<<grid, block, 0, stream>>>(tiles, CT, g, prof, dst);  \
     else blend_kernel<DT, E, COMPACT><<<grid, block, 0, stream>>>(tiles, CT, g, C, dst);        \
   } while (0)
   if (CT == 0) {
