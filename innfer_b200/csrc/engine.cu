@@ -761,7 +761,10 @@ int forward_tiles_pan(innfer_rrdb* h, int B, int hgt, int wid, ChunkView dst, bo
     if (f16) r = launch_pan_maxpool(reinterpret_cast<const __half*>(cur->p), nfC, nfc, B, hgt, wid, 4, pooled, st);
     else r = launch_pan_maxpool(reinterpret_cast<const float*>(cur->p), nfC, nfc, B, hgt, wid, 4, pooled, st);
     if (!r) r = launch_pan_proj(pooled, (long long)n, nfc * 8, h->d_pan_w, h->d_pan_b, fq, gk, hv, st);
-    if (!r) r = launch_pan_attention(fq, gk, hv, B, hp * wp, nfc * 8, att, st);
+    // fp16 mode: the contraction on the tensor cores (INNFER_PAN_ATT_TC=0: the fp32 CUDA-core kernel, as in fp32 mode)
+    static const int att_tc = getenv("INNFER_PAN_ATT_TC") ? atoi(getenv("INNFER_PAN_ATT_TC")) : 1;
+    if (!r) r = (f16 && att_tc) ? launch_pan_attention_tc(fq, gk, hv, B, hp * wp, nfc * 8, att, st)
+                                : launch_pan_attention(fq, gk, hv, B, hp * wp, nfc * 8, att, st);
     if (!r) {
       if (f16)
         r = launch_pan_bicubic_add(att, hp, wp, reinterpret_cast<const __half*>(cur->p), nfC,

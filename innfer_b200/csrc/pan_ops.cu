@@ -1,5 +1,9 @@
 #include "pan_ops.cuh"
 
+#include <cstdlib>
+
+#include "ptx.cuh"
+
 #include <math_constants.h>
 #include <stdint.h>
 
@@ -151,6 +155,211 @@ pan_attention_kernel(const float* __restrict__ f, const float* __restrict__ g, c
   for (int c = 0; c < NFP; ++c) o[c] = acc[c] * inv;
 }
 
+
+// ------------------------------------------------------------------------------------------------ attention on tcgen05
+// The same contraction (block.py:456-461) as two tensor-core GEMMs per block of 128 keys with an online softmax between
+// them (fp16 operands, fp32 accumulation in TMEM, fp32 softmax in registers):
+//     S[128 q x 128 k] = Q[128 x 16] K[128 x 16]^T            one M = 128, N = 128, K = 16 MMA (channels 8..15 are zero)
+//     P = exp(S - rowmax), running rowmax / rowsum, previous output rescaled
+//     O[128 q x NV]   += P[128 x 128] V[128 k x NV]             eight M = 128, N = NV, K = 16 MMAs
+// 128 threads own one query row each (= TMEM lane): they stage K / V^T of the block into the SWIZZLE_NONE K-major operand
+// layouts (fp32 -> fp16), read S, write P as the A operand of the second GEMM, and fold the block's O into their
+// registers.  One more warp issues the MMAs.  The phases of a block are sequential (two CTAs per SM overlap each other).
+constexpr int kAttThreads = 160;
+
+template <int NV>   // value channels rounded up to 16
+__global__ void __launch_bounds__(kAttThreads, 2)
+pan_attention_tc_kernel(const float* __restrict__ f, const float* __restrict__ g, const float* __restrict__ hv, int n, int nfp,
+                        float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // [Q: 2 x 128 x 16 B][K: 2 x 128 x 16 B][P: 16 x 128 x 16 B][Vt: 16 x NV x 16 B][barriers]
+  constexpr uint32_t kQ = 0, kK = 4096, kP = 8192, kV = 8192 + 32768, kBar = kV + 16u * NV * 16u;
+  constexpr uint32_t TCOLS = 256;   // S: columns [0, 128), O block: [128, 128 + NV)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * 128;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kBar);
+  uint64_t* o_bar = s_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_bar + 1);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(s_bar), 1);
+    mbar_init(smem_u32(o_bar), 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(tmem_slot), TCOLS);
+    tmem_relinquish();
+  }
+  const float* fb = f + (size_t)b * n * kPanQK;
+  const float* gb = g + (size_t)b * n * kPanQK;
+  const float* hb = hv + (size_t)b * n * kPanRow;
+  const int tid = threadIdx.x;
+  auto pack8 = [](const float* v) {
+    uint4 o;
+    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&h0);
+    o.y = *reinterpret_cast<uint32_t*>(&h1);
+    o.z = *reinterpret_cast<uint32_t*>(&h2);
+    o.w = *reinterpret_cast<uint32_t*>(&h3);
+    return o;
+  };
+  if (warp < 4) {
+    // Q: row tid, K-chunk 0 = its 8 projection values, K-chunk 1 = zeros
+    float v[8];
+    const int i = q0 + tid;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = i < n ? fb[(size_t)i * kPanQK + e] : 0.f;
+    *reinterpret_cast<uint4*>(smem + kQ + tid * 16) = pack8(v);
+    *reinterpret_cast<uint4*>(smem + kQ + 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(smem + kK + 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);   // K-chunk 1 of every key block
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sbase = smem_u32(smem);
+  const int nblocks = (n + 127) / 128;
+  float m_run = -CUDART_INF_F, l_run = 0.f;
+  float o_acc[NV];
+#pragma unroll
+  for (int c = 0; c < NV; ++c) o_acc[c] = 0.f;
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  for (int kb = 0; kb < nblocks; ++kb) {
+    const int j0 = kb * 128;
+    if (warp < 4) {
+      // ---- stage the key block: K rows (B operand [K-chunk][key][8]) and V transposed (B operand [key chunk][channel][8 keys])
+      {
+        float v[8];
+        const int j = j0 + tid;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = j < n ? gb[(size_t)j * kPanQK + e] : 0.f;
+        *reinterpret_cast<uint4*>(smem + kK + tid * 16) = pack8(v);
+      }
+      // thread -> (key chunk kc = 8 keys, channel c): NV x 16 items, coalesced over channels for a fixed key
+      for (int it = tid; it < 16 * NV; it += 128) {
+        const int kc = it / NV, c = it - kc * NV;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = j0 + kc * 8 + e;
+          v[e] = (j < n && c < nfp) ? hb[(size_t)j * kPanRow + c] : 0.f;
+        }
+        *reinterpret_cast<uint4*>(smem + kV + ((uint32_t)kc * NV + c) * 16) = pack8(v);
+      }
+      fence_proxy_async_smem();
+    }
+    __syncthreads();
+    if (warp == 4) {
+      // ---- S = Q K^T
+      if (lane == 0) {
+        tc_fence_after();
+        const uint64_t ad = make_smem_desc(sbase + kQ, 2048u, 128u);
+        const uint64_t bd = make_smem_desc(sbase + kK, 2048u, 128u);
+        umma_f16_ss(tmem_base, ad, bd, make_idesc_f16(128), 0u);
+        umma_commit(smem_u32(s_bar));
+      }
+      __syncwarp();
+    } else {
+      mbar_wait(smem_u32(s_bar), (uint32_t)kb & 1u);
+      tc_fence_after();
+      // ---- online softmax over this block's 128 keys; P goes to shared memory as the next A operand
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+      float sv[128];
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 16) tmem_ld16(trow + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&sv[c0]));
+      tmem_ld_wait();
+      float mx = m_run;
+#pragma unroll
+      for (int j = 0; j < 128; ++j) {
+        if (j0 + j >= n) sv[j] = -CUDART_INF_F;
+        mx = fmaxf(mx, sv[j]);
+      }
+      const float alpha = exp2f((m_run - mx) * kLog2e);   // 0 for the first block (m_run = -inf)
+      m_run = mx;
+      float psum = 0.f;
+#pragma unroll
+      for (int kc = 0; kc < 16; ++kc) {
+        float pv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          pv[e] = exp2f((sv[kc * 8 + e] - mx) * kLog2e);
+          psum += pv[e];
+        }
+        *reinterpret_cast<uint4*>(smem + kP + ((uint32_t)kc * 128 + tid) * 16) = pack8(pv);
+      }
+      l_run = l_run * alpha + psum;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) o_acc[c] *= alpha;
+      fence_proxy_async_smem();
+      tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+      // ---- O_block = P V
+      if (lane == 0) {
+        tc_fence_after();
+        const uint32_t idesc = make_idesc_f16(NV);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t ad = make_smem_desc(sbase + kP + (uint32_t)kk * 4096u, 2048u, 128u);
+          const uint64_t bd = make_smem_desc(sbase + kV + (uint32_t)kk * 2u * NV * 16u, (uint32_t)NV * 16u, 128u);
+          umma_f16_ss(tmem_base + 128u, ad, bd, idesc, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(o_bar));
+      }
+      __syncwarp();
+    } else {
+      mbar_wait(smem_u32(o_bar), (uint32_t)kb & 1u);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + 128u;
+      uint32_t ov[NV];
+#pragma unroll
+      for (int c0 = 0; c0 < NV; c0 += 16) tmem_ld16(trow + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(&ov[c0]));
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < NV; ++c) o_acc[c] += __uint_as_float(ov[c]);
+      tc_fence_before();
+    }
+    __syncthreads();   // the operand buffers and both accumulators are free again
+  }
+  if (warp < 4) {
+    const int i = q0 + tid;
+    if (i < n) {
+      const float inv = 1.f / l_run;
+      float* o = out + ((size_t)b * n + i) * kPanRow;
+#pragma unroll
+      for (int c = 0; c < NV; ++c)
+        if (c < nfp) o[c] = o_acc[c] * inv;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TCOLS);
+  }
+}
+
+template <int NV>
+int launch_att_tc(const float* f, const float* g, const float* hv, int B, int n, int nfp, float* out, cudaStream_t st) {
+  constexpr size_t smem = 8192 + 32768 + 16 * NV * 16 + 64;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(pan_attention_tc_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)   // two CTAs per SM hide each other's sequential phases: ask for the shared-memory carve-out they need
+      e = cudaFuncSetAttribute(pan_attention_tc_kernel<NV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev & 63] = true;
+  }
+  dim3 grid((unsigned)((n + 127) / 128), (unsigned)B);
+  pan_attention_tc_kernel<NV><<<grid, kAttThreads, smem, st>>>(f, g, hv, n, nfp, out);
+  return (int)cudaGetLastError();
+}
+
 // torch's cubic convolution coefficients (A = -0.75) for the taps at floor(src) - 1 .. floor(src) + 2
 __device__ __forceinline__ void cubic_coeffs(float t, float c[4]) {
   const float A = -0.75f;
@@ -259,6 +468,15 @@ int launch_pan_proj(const float* pooled, long long npix, int nfp, const float* w
   const long long total = npix * (2 * kPanQK + kPanRow);
   pan_proj_kernel<<<blocks_for(total, 256), 256, 0, st>>>(pooled, npix, nfp, wcat, bcat, f, g, hv);
   return (int)cudaGetLastError();
+}
+
+int launch_pan_attention_tc(const float* f, const float* g, const float* hv, int B, int n, int nfp, float* out,
+                            cudaStream_t st) {
+  if (nfp <= 16) return launch_att_tc<16>(f, g, hv, B, n, nfp, out, st);
+  if (nfp <= 32) return launch_att_tc<32>(f, g, hv, B, n, nfp, out, st);
+  if (nfp <= 48) return launch_att_tc<48>(f, g, hv, B, n, nfp, out, st);
+  if (nfp <= 64) return launch_att_tc<64>(f, g, hv, B, n, nfp, out, st);
+  return -2;
 }
 
 int launch_pan_attention(const float* f, const float* g, const float* hv, int B, int n, int nfp, float* out,

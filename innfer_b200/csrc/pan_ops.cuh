@@ -28,6 +28,11 @@ int launch_pan_proj(const float* pooled, long long npix, int nfp, const float* w
 int launch_pan_attention(const float* f, const float* g, const float* hv, int B, int n, int nfp, float* out,
                          cudaStream_t st);
 
+// The same on the tensor cores (fp16 engine mode): S = Q K^T and O = P V as tcgen05 MMAs with fp32 accumulators in TMEM,
+// online softmax in fp32 registers between them (pan_ops.cu).
+int launch_pan_attention_tc(const float* f, const float* g, const float* hv, int B, int n, int nfp, float* out,
+                            cudaStream_t st);
+
 // y = gamma * bicubic_resize(att, (H, W), align_corners=False) + x  (block.py:463-468): att [B][hp*wp][kPanRow].
 template <typename T>
 int launch_pan_bicubic_add(const float* att, int hp, int wp, const T* x, int x_CT, T* y, int y_CT, int nchunks,
