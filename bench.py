@@ -528,13 +528,14 @@ def run_small(args, dev, warm):
 
             def one(img):
                 return tensor2np(rm(np2tensor(img).to(dev).half()).detach())
-            one(frames[0])
+            for i in range(2):            # cudnn.benchmark autotunes per shape: keep that out of the timed frames
+                one(frames[i % 2])
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            for i in range(2):
+            for i in range(3):
                 out = one(frames[i % 2])
             torch.cuda.synchronize()
-            ref_ms = (time.perf_counter() - t0) * 1e3 / 2
+            ref_ms = (time.perf_counter() - t0) * 1e3 / 3
             rec["torch_gpu_reference_ms"] = ref_ms
             rec["ours_e2e_over_reference_gpu"] = ref_ms / e2e_ms
             rec["max_abs_u8_diff_vs_reference_gpu_fp16"] = int(np.abs(np.asarray(out).astype(int) - np.asarray(runner(frames[1])).astype(int)).max())

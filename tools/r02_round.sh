@@ -1,7 +1,12 @@
 #!/bin/bash
-# Round-2 record run (one gpurun call): whole GPU suite, i2i bench workload, i2i launch list + ncu captures of its kernels
+# Round-2 record run (one gpurun call): whole GPU suite, smoke, the four bench workloads, reference arm
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -8 > gpurun_out/r02b_pytest.log; tail -4 gpurun_out/r02b_pytest.log
-timeout 600 python bench.py --workload i2i --steps 20 --warmup 3 > gpurun_out/r02b_bench_i2i.json 2> gpurun_out/r02b_bench_i2i.err; tail -c 600 gpurun_out/r02b_bench_i2i.json
-STAGE=i2i_prof bash tools/gpu_launchlist.sh r02b_i2i 2>&1 | tail -9
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gen_conv|norm_" -s 230 -c 12 -f -o gpurun_out/r02b_i2i_kernels python tests/gpu_bringup.py --stage i2i_prof > gpurun_out/r02b_i2i_ncu.log 2>&1; tail -2 gpurun_out/r02b_i2i_ncu.log
+T=${TAG:-r02d}
+timeout 1500 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -6 > gpurun_out/${T}_pytest.log; tail -3 gpurun_out/${T}_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python bench.py --steps 8 --warmup 3 > gpurun_out/${T}_bench_n1.json 2> gpurun_out/${T}_bench_n1.err; tail -c 400 gpurun_out/${T}_bench_n1.json; echo
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference_arm.json 2>/dev/null; tail -c 300 gpurun_out/${T}_bench_reference_arm.json; echo
+timeout 600 python bench.py --workload chain --steps 8 > gpurun_out/${T}_bench_chain.json 2>/dev/null; tail -c 200 gpurun_out/${T}_bench_chain.json; echo
+timeout 600 python bench.py --workload small --steps 5 > gpurun_out/${T}_bench_small.json 2>/dev/null; tail -c 200 gpurun_out/${T}_bench_small.json; echo
+timeout 600 python bench.py --workload i2i --steps 20 > gpurun_out/${T}_bench_i2i.json 2>/dev/null; tail -c 200 gpurun_out/${T}_bench_i2i.json; echo
+for st in pan_time ppon_time srres_time; do timeout 300 python tests/gpu_bringup.py --stage $st 2>&1 | grep "iter=2" ; done
