@@ -1,5 +1,6 @@
 #include "pixel_ops.cuh"
 
+#include <algorithm>
 #include <vector>
 
 #include <cmath>
@@ -566,6 +567,33 @@ int chunks_to_nchw_impl(const E* src, int CT, int n, int C, int H, int W, void* 
 }
 
 }  // namespace
+
+namespace {
+__global__ void __launch_bounds__(256) axpy_f16_kernel(uint4* __restrict__ dst, const uint4* __restrict__ a,
+                                                       const uint4* __restrict__ b, float alpha, size_t n16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 ua = a[i], ub = b[i];
+    const __half2* ha = reinterpret_cast<const __half2*>(&ua);
+    const __half2* hb = reinterpret_cast<const __half2*>(&ub);
+    uint4 o;
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 x = __half22float2(ha[e]), y = __half22float2(hb[e]);
+      ho[e] = __floats2half2_rn(fmaf(alpha, y.x, x.x), fmaf(alpha, y.y, x.y));
+    }
+    dst[i] = o;
+  }
+}
+}  // namespace
+
+int launch_axpy_f16(__half* dst, const __half* a, const __half* b, float alpha, size_t n16, cudaStream_t stream) {
+  const int block = 256;
+  const unsigned grid = (unsigned)std::min<size_t>((n16 + block - 1) / block, 148u * 16u);
+  axpy_f16_kernel<<<grid, block, 0, stream>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(a),
+                                              reinterpret_cast<const uint4*>(b), alpha, n16);
+  return (int)cudaGetLastError();
+}
 
 int launch_image_to_tiles(const void* src, PixelDType st, int C, const TilePlan& plan, int t0, int nt,
                           __half* dst, int CT, cudaStream_t stream) {

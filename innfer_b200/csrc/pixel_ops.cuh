@@ -54,6 +54,9 @@ int launch_nchw_to_chunks_f32(const void* src, PixelDType st, int n, int C, int 
 int launch_chunks_to_nchw_f32(const float* src, int CT, int n, int C, int H, int W, void* dst,
                               PixelDType dt, cudaStream_t stream);
 
+// dst = a + alpha * b over n16 16-byte groups of fp16 (whole wide / tiled tensors of equal geometry; dst may alias a)
+int launch_axpy_f16(__half* dst, const __half* a, const __half* b, float alpha, size_t n16, cudaStream_t stream);
+
 // NCHW <-> wide layout [CT][H][cols][8] (image b in columns [b*pitch, b*pitch + W)); separator columns are not
 // touched by the first (the caller zeroes the buffer) and skipped by the second.
 int launch_nchw_to_wide(const void* src, PixelDType st, int n, int C, int H, int W, __half* dst, int CT, int pitch,
