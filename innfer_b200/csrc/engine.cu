@@ -529,11 +529,10 @@ int forward_tiles_srresnet(innfer_rrdb* h, int B, int hgt, int wid, ChunkView ds
   for (int b = 0; b < h->cfg.nb; ++b) {
     const ConvLayer* L = &h->rdb[(size_t)b * 2];
     if ((rc = run_conv(h, L[0], cur, B, hgt, wid, view(h->xbuf[T], nfc, 0), nfc, relu, st))) return rc;
-    // fp16 wide layout: the second conv without its residual epilogue -- that keeps it on the row-streaming kernel, which
-    // has no gain from a residual epilogue for Cout = 64 (the 9-tap kernel that serves it runs at 0.3 of the tensor
-    // roof) -- and the scaled add as one elementwise pass (one more fp16 rounding per block; fixtures unchanged within
-    // 1/255).  Measured 54.2 -> 51.0 ms per 1080p frame; INNFER_SRRES_SPLIT=0 restores the fused epilogue.
-    static const int split = getenv("INNFER_SRRES_SPLIT") ? atoi(getenv("INNFER_SRRES_SPLIT")) : 1;
+    // INNFER_SRRES_SPLIT=1 (experiment): the second conv without its residual epilogue + the scaled add as one elementwise
+    // pass (one more fp16 rounding per block).  Measured per 1080p frame: 9-tap kernel with residual epilogue 53.3 ms,
+    // this split 51.0 ms, row kernel WITH the residual epilogue (INNFER_ROWS64_RES, the default) 49.4 ms.
+    static const int split = getenv("INNFER_SRRES_SPLIT") ? atoi(getenv("INNFER_SRRES_SPLIT")) : 0;
     if (split && wide) {
       if ((rc = run_conv(h, L[1], view(h->xbuf[T], nfc, 0), B, hgt, wid, view(h->xbuf[Y], nfc, 0), nfc, plain, st))) return rc;
       const size_t n16 = (size_t)nfc * hgt * wide_cols(B, wid);

@@ -322,7 +322,10 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   }
   if (S < 3) return -100;
   if (S > 8) S = 8;
-  if (CR == 64 && !pair && (ep.res1.base || ep.res2.base)) return -100;
+  // Cout = 64 with ONE residual input on the row kernel (round 2: SRResNet's block convs 53.3 -> 49.4 ms per 1080p frame
+  // against the 9-tap kernel; INNFER_ROWS64_RES=0 restores that); two residuals stay on the CTA pair / 9-tap kernel
+  static const int rows64res = getenv("INNFER_ROWS64_RES") ? atoi(getenv("INNFER_ROWS64_RES")) : 1;
+  if (CR == 64 && !pair && (ep.res1.base || ep.res2.base) && !(rows64res && !ep.res2.base)) return -100;
   ConvRowsParams p;
   std::memset(&p, 0, sizeof(p));
   p.H = H;
