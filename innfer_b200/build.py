@@ -19,6 +19,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
 
+if os.environ.get("INNFER_EXPERIMENTS_BUILD"):  # timing experiments that produce wrong results (INNFER_I2I_DEBUG, INNFER_ROWS_DX0)
+    NVCC_FLAGS.append("-DINNFER_EXPERIMENTS")
 if os.environ.get("INNFER_TRACE_BUILD"):  # debugging build: clock64 tracing inside conv_rows (tests/gpu_bringup.py --stage trace)
     NVCC_FLAGS.append("-DINNFER_ROWS_TRACE")
 

@@ -1356,7 +1356,9 @@ bool halo_geometry_ok(const GenConv& L, const GenConvParams& p) {
 bool halo_setup(const GenConv& L, GenConvParams& p, int num_sms, dim3& grid, size_t& smem, int& stages) {
   const int mode = halo_mode();
   if (mode == 0 || (p.nsplit != 1 && !(p.split_for_halo && p.out_mode == 1)) || !halo_geometry_ok(L, p)) return false;
+#ifdef INNFER_EXPERIMENTS   // timing experiments that switch parts of the kernel off (wrong results): special builds only
   p.debug = getenv("INNFER_I2I_DEBUG") ? atoi(getenv("INNFER_I2I_DEBUG")) : 0;
+#endif
   // sub-patches per CTA: 4 x NT accumulator columns must fit TMEM's 512.  With NT = 128 that is the whole TMEM (one CTA per
   // SM, no second CTA to hide the epilogue) but it halves the weight bytes per MMA, which is what bounds the wide layers
   // (every CTA re-reads the slab's weights from L2): taken when there is more than a wave of such tiles and it fits.

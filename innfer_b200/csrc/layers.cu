@@ -381,8 +381,10 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   p.raw_chunk0 = ep.raw_out.chunk0;
   static const int trace_nch = getenv("INNFER_TRACE_NCH") ? atoi(getenv("INNFER_TRACE_NCH")) : 0;
   p.trace = (trace_nch == nch) ? g_rows_trace : nullptr;
+#ifdef INNFER_EXPERIMENTS   // timing experiment with wrong results: special builds only (INNFER_EXPERIMENTS_BUILD=1)
   static const int dbg_dx0 = getenv("INNFER_ROWS_DX0") ? atoi(getenv("INNFER_ROWS_DX0")) : 0;
   p.dbg_dx0 = dbg_dx0;
+#endif
   int rc = 0;
   const CUtensorMap* tm = cache.get_rows(in.base, in.CT, H, in.Wtot, kc, rc);
   if (!tm) return rc ? rc : -5;
