@@ -46,11 +46,13 @@ int cuda_fail(cudaError_t e, const char* what) {
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  unsigned gen = 0;   // bumped whenever the allocation changes (what is known about the old contents is void)
   int ensure(size_t need) {
     if (need <= bytes) return 0;
     if (p) cudaFree(p);
     p = nullptr;
     bytes = 0;
+    ++gen;
     cudaError_t e = cudaMalloc(&p, need);
     if (e != cudaSuccess) return (int)e;
     bytes = need;
@@ -60,6 +62,7 @@ struct DevBuf {
     if (p) cudaFree(p);
     p = nullptr;
     bytes = 0;
+    ++gen;
   }
 };
 
@@ -107,6 +110,11 @@ struct innfer_rrdb {
   TmapCache cache;
   // workspace
   DevBuf in_tiles, feat, xbuf[3], hrbuf[2], out_tiles, img_in, img_out;
+  // uint8 frames with <= 8 channels fill only chunk 0 of every input tile: the other chunks of in_tiles are known to
+  // hold zeros for allocation generation `in_pad_gen` and tile size `in_pad_p` (zero-filled once, invalidated by
+  // other writers)
+  unsigned in_pad_gen = ~0u;
+  int in_pad_p = 0;
   DevBuf pbuf[9], paux[2];   // PPON: F, X0..X2, T1, S, E1, E2 (64 channels each), CAT (256); out_c / out_s at HR
   // optional device-side timing of the conv sequence (bench.py roofline)
   int profiling = 0;   // 1: events around every per-batch conv sequence; 2: around every conv launch, per kernel family
@@ -985,14 +993,21 @@ int compute_tiles(innfer_rrdb* h, const void* src, PixelDType st, const TilePlan
   const int oct = (h->cfg.out_nc + 7) / 8;
   const bool compact = compact_tiles(h);
   const size_t tile_out_elems = compact ? (size_t)(s * p) * (s * p) * 4 : (size_t)oct * (s * p) * (s * p) * 8;
+  const bool skip_pad = st == kU8 && h->cfg.in_nc <= 8 && h->in_ct() > 1;
+  if (skip_pad && (h->in_pad_gen != h->in_tiles.gen || h->in_pad_p != p)) {
+    if (cudaMemsetAsync(h->in_tiles.p, 0, h->in_tiles.bytes, stream) != cudaSuccess)
+      return fail(INNFER_E_CUDA, "input tile zero fill failed");
+    h->in_pad_gen = h->in_tiles.gen;
+    h->in_pad_p = p;
+  }
   for (int t0 = t_begin; t0 < t_end; t0 += B) {
     const int nb = (t_end - t0) < B ? (t_end - t0) : B;
     if (h->cfg.fp16) {
       rc = launch_image_to_tiles(src, st, h->cfg.in_nc, plan, t0, nb, reinterpret_cast<__half*>(h->in_tiles.p),
-                                 h->in_ct(), stream);
+                                 h->in_ct(), stream, skip_pad);
     } else {
       rc = launch_image_to_tiles_f32(src, st, h->cfg.in_nc, plan, t0, nb, reinterpret_cast<float*>(h->in_tiles.p),
-                                     h->in_ct(), stream);
+                                     h->in_ct(), stream, skip_pad);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (rc) return fail(INNFER_E_CUDA, "image_to_tiles launch failed");
@@ -1418,6 +1433,7 @@ int innfer_rrdb_forward(innfer_rrdb* h, const void* x, int n, int hgt, int wid, 
     const size_t out_off = (size_t)b0 * h->cfg.out_nc * s * hgt * s * wid * (dtype == INNFER_F16 ? 2 : 4);
     const void* xs = reinterpret_cast<const uint8_t*>(x) + in_off;
     void* ys = reinterpret_cast<uint8_t*>(y) + out_off;
+    h->in_pad_gen = ~0u;   // another tile geometry is written over the buffer
     if (h->cfg.fp16)
       rc = launch_nchw_to_chunks(xs, to_pix(dtype), nb, h->cfg.in_nc, hgt, wid, reinterpret_cast<__half*>(h->in_tiles.p), h->in_ct(), st);
     else

@@ -128,6 +128,65 @@ __global__ void image_to_tiles_kernel(const void* __restrict__ src_, int C, cons
   }
 }
 
+// uint8 HWC source with at most 8 channels (the CLI's path: np2tensor + bgr_to_rgb + extract_patches_2d + .half(),
+// utils.py:164-194,318-369): a block is (4 tile rows) x (64 pixel columns), the 256 possible `v / 255` values come from
+// a shared-memory table filled with the same expression the generic kernel evaluates (bit-identical), every thread
+// converts one pixel at a time and stores its 16-byte chunk; chunks past the image's channels are zero fill.
+// No 64-bit index arithmetic, no per-pixel division: 62 -> 13 us per 95-tile batch (profiles/r02e_pixel_kernels.md).
+template <typename E>
+__global__ void __launch_bounds__(256)
+image_to_tiles_u8_kernel(const uint8_t* __restrict__ src, int C, const __grid_constant__ TileGeom g, int t0, int nt,
+                         E* __restrict__ dst, int CT, int CTW) {
+  __shared__ E lut[256];
+  {
+    const float f = (float)threadIdx.x / 255.0f;
+    if constexpr (sizeof(E) == 2) lut[threadIdx.x] = __float2half_rn(f);
+    else lut[threadIdx.x] = f;
+  }
+  __syncthreads();
+  const int p = g.p;
+  const size_t plane = (size_t)p * p;                  // pixels per (tile, chunk) plane
+  const int nrows = nt * p;
+  // persistent blocks: the table is built once per block, every quarter of the block walks (tile, row) pairs
+  for (int r = blockIdx.x * 4 + (threadIdx.x >> 6); r < nrows; r += gridDim.x * 4) {
+    const int tl = r / p, y = r - tl * p;
+    const int t = tl + t0;
+    const int ty = t / g.ntx, tx = t - ty * g.ntx;
+    const uint8_t* srow = src + ((size_t)(g.ys[ty] + y) * g.W + g.xs[tx]) * C;
+    E* drow = dst + (((size_t)tl * CT) * plane + (size_t)y * p) * 8;
+    for (int x0 = threadIdx.x & 63; x0 < p; x0 += 256) {
+      // up to four pixels per thread with all their byte loads in flight before the first table lookup
+      uint8_t raw[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int x = x0 + 64 * k;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) raw[k][e] = (e < C && x < p) ? srow[x * C + (C - 1 - e)] : (uint8_t)0;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int x = x0 + 64 * k;
+        if (x >= p) break;
+        __align__(16) E v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = lut[raw[k][e]];   // lut[0] == +0 for the padding channels
+        E* d = drow + (size_t)x * 8;
+        if constexpr (sizeof(E) == 2) {
+          *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(v);
+          for (int ch = 1; ch < CTW; ++ch) *reinterpret_cast<uint4*>(d + (size_t)ch * plane * 8) = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+          reinterpret_cast<uint4*>(d)[0] = reinterpret_cast<const uint4*>(v)[0];
+          reinterpret_cast<uint4*>(d)[1] = reinterpret_cast<const uint4*>(v)[1];
+          for (int ch = 1; ch < CTW; ++ch) {
+            uint4* z = reinterpret_cast<uint4*>(d + (size_t)ch * plane * 8);
+            z[0] = z[1] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      }
+    }
+  }
+}
+
 struct BlendGeom {
   int Hs, Ws;      // full output size
   int P;           // HR tile size
@@ -414,7 +473,7 @@ int grid_for(size_t total, int block) {
 
 template <typename E>
 int image_to_tiles_impl(const void* src, PixelDType st, int C, const TilePlan& plan, int t0, int nt, E* dst,
-                        int CT, cudaStream_t stream) {
+                        int CT, cudaStream_t stream, bool skip_pad) {
   TileGeom g;
   g.H = plan.H;
   g.W = plan.W;
@@ -431,6 +490,9 @@ int image_to_tiles_impl(const void* src, PixelDType st, int C, const TilePlan& p
     image_to_tiles_kernel<__half, false, E><<<grid, block, 0, stream>>>(src, C, g, t0, nt, dst, CT);
   else if (st == kF32)
     image_to_tiles_kernel<float, false, E><<<grid, block, 0, stream>>>(src, C, g, t0, nt, dst, CT);
+  else if (C <= 8 && (long long)nt * plan.p < (1ll << 31) - 8)
+    image_to_tiles_u8_kernel<E><<<(unsigned)std::min<long long>(((long long)nt * plan.p + 3) / 4, 148 * 8), 256, 0, stream>>>(
+        reinterpret_cast<const uint8_t*>(src), C, g, t0, nt, dst, CT, skip_pad ? 1 : CT);
   else
     image_to_tiles_kernel<float, true, E><<<grid, block, 0, stream>>>(src, C, g, t0, nt, dst, CT);
   return (int)cudaGetLastError();
@@ -596,12 +658,12 @@ int launch_axpy_f16(__half* dst, const __half* a, const __half* b, float alpha, 
 }
 
 int launch_image_to_tiles(const void* src, PixelDType st, int C, const TilePlan& plan, int t0, int nt,
-                          __half* dst, int CT, cudaStream_t stream) {
-  return image_to_tiles_impl<__half>(src, st, C, plan, t0, nt, dst, CT, stream);
+                          __half* dst, int CT, cudaStream_t stream, bool skip_pad) {
+  return image_to_tiles_impl<__half>(src, st, C, plan, t0, nt, dst, CT, stream, skip_pad);
 }
 int launch_image_to_tiles_f32(const void* src, PixelDType st, int C, const TilePlan& plan, int t0, int nt,
-                              float* dst, int CT, cudaStream_t stream) {
-  return image_to_tiles_impl<float>(src, st, C, plan, t0, nt, dst, CT, stream);
+                              float* dst, int CT, cudaStream_t stream, bool skip_pad) {
+  return image_to_tiles_impl<float>(src, st, C, plan, t0, nt, dst, CT, stream, skip_pad);
 }
 int launch_blend(const __half* tiles, int CT, const TilePlan& plan, int scale, int C, void* dst,
                  PixelDType dt, cudaStream_t stream) {

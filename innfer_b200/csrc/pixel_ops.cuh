@@ -29,8 +29,10 @@ enum PixelDType { kF16 = 0, kF32 = 1, kU8 = 2 };
 // src: NCHW image [1][C][H][W] (fp16/fp32, already RGB in [0,1]) or uint8 HWC BGR (C==3, /255 and
 // channel flip applied).  dst: tiles [nt][CT][p][p][8] fp16, channels >= C zero-filled; tiles
 // [t0, t0+nt) of the row-major plan are produced.
+// skip_pad (uint8 sources with C <= 8 only; ignored otherwise): write chunk 0 only -- the caller guarantees that the
+// other chunks of dst already hold zeros (the engine zero-fills its tile buffer once per tile geometry).
 int launch_image_to_tiles(const void* src, PixelDType st, int C, const TilePlan& plan, int t0, int nt,
-                          __half* dst, int CT, cudaStream_t stream);
+                          __half* dst, int CT, cudaStream_t stream, bool skip_pad = false);
 
 // tiles: [ntiles][CT][P][P][8] fp16 (P = scale*p), channel c of chunk 0 is output channel c.
 // dst: NCHW [1][C][scale*H][scale*W] fp16/fp32, or uint8 HWC BGR with clip(255x).round().
@@ -46,7 +48,7 @@ int launch_chunks_to_nchw(const __half* src, int CT, int n, int C, int H, int W,
 
 // fp32-mode flavours: identical semantics on [..][8] float chunks (32 bytes per chunk pixel).
 int launch_image_to_tiles_f32(const void* src, PixelDType st, int C, const TilePlan& plan, int t0,
-                              int nt, float* dst, int CT, cudaStream_t stream);
+                              int nt, float* dst, int CT, cudaStream_t stream, bool skip_pad = false);
 int launch_blend_f32(const float* tiles, int CT, const TilePlan& plan, int scale, int C, void* dst,
                      PixelDType dt, cudaStream_t stream);
 int launch_nchw_to_chunks_f32(const void* src, PixelDType st, int n, int C, int H, int W, float* dst,

@@ -428,6 +428,27 @@ def test_color_fix_kernels_vs_reference_fixture(native, dev):
         U.color_fix(g["sr_a"], g["lr_a"], device=dev)  # LR larger than SR: numpy would not broadcast
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("hw,HW", [((64, 80), (256, 320)), ((45, 60), (112, 144)), ((100, 150), (101, 160)),
+                                   ((33, 40), (264, 320)), ((50, 70), (100, 1024)), ((7, 5), (35, 16)), ((30, 40), (61, 100))])
+def test_color_fix_tiled_kernel_vs_oracle(native, dev, hw, HW):
+    """SR widths that are multiples of 4 take the tiled up-sampling kernel (shared-memory separable bicubic): several
+    tile columns / rows, ragged last tiles, non-integer and near-1 ratios, clamped borders; against the CPU oracle
+    (utils.py:278-315) within the path's 1 LSB."""
+    from innfer_b200.utils import utils as U
+    rng = np.random.default_rng(hw[0] * 1000 + HW[1])
+    lr = rng.integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
+    # a smooth SR image plus noise so that the correction is neither trivial nor saturating everywhere
+    yy, xx = np.mgrid[0:HW[0], 0:HW[1]]
+    base = (96 + 64 * np.sin(yy / 17.0)[..., None] + 48 * np.cos(xx / 11.0)[..., None] + np.array([0, 20, -20])).clip(0, 255)
+    sr = (base + rng.integers(-12, 13, base.shape)).clip(0, 255).astype(np.uint8)
+    got = U.color_fix(lr, sr, device=dev)
+    want = O.color_fix(lr, sr)
+    d = np.abs(got.astype(int) - want.astype(int))
+    assert d.max() <= 1
+    assert (d > 0).mean() < 0.02
+
+
 def test_pixel_kernels_tiles_and_blend(native, dev):
     lib = native.load()
     H, W, p = 50, 70, 32
