@@ -48,7 +48,10 @@ namespace {
 // 3 x 32 running sums per thread).
 // The CTA-pair kernel (conv5) runs 16 epilogue warps of 16 channels each (608 threads, 96 registers): its residual
 // epilogue is latency-bound and gains from more warps in flight.
-__host__ __device__ constexpr int rows_threads(int /*cout*/, bool pair) { return pair ? 608 : 352; }
+// PPON's dilated convs (WEPI, "wide epilogue") also run 16 epilogue warps, of 8 channels each: with 12 MMAs per row
+// their residual epilogue is the critical path and two warps per scheduler cannot hide its latencies (ncu: 1.4
+// instructions per cycle and SM, 2 250 cycles per row for 660 cycles of MMAs).
+__host__ __device__ constexpr int rows_threads(int /*cout*/, bool wide_epi) { return wide_epi ? 608 : 352; }
 constexpr int kRowPx = 144;        // pixels per staged row segment: 9 groups of 16 (strip of 128 + halo)
 
 struct Piece {
@@ -85,8 +88,8 @@ struct PieceIter {
   }
 };
 
-template <int COUT, int KSLABS, bool RES, bool PAIR, bool DILV = false>
-__global__ void __launch_bounds__(rows_threads(COUT, PAIR), 1)
+template <int COUT, int KSLABS, bool RES, bool PAIR, bool DILV = false, bool WE = false>
+__global__ void __launch_bounds__(rows_threads(COUT, PAIR || DILV || WE), 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvRowsParams p) {
   constexpr int N = 3 * COUT;                 // dy-major: column dy*COUT + co
   // PAIR: the two CTAs of a cluster issue M = 256 MMAs (tcgen05 cta_group::2) over two neighbouring strips; each CTA
@@ -97,9 +100,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   constexpr int NSLOT = 512 / N;              // 5 (COUT=32) or 2 (COUT=64)
   // channels per epilogue thread: two warps per lane quarter share COUT; COUT = 16 (the net's last conv, N = 48) is
   // drained by ONE warp per quarter, the other four epilogue warps idle
-  constexpr int CH = (COUT == 16 || PAIR) ? 16 : COUT / 2;
+  constexpr bool WEPI = PAIR || DILV || WE;    // 16 epilogue warps (608 threads)
+  static_assert(!WE || COUT == 32, "the wide epilogue of single CTAs splits 32 channels over four warp groups");
+  constexpr int CH = WEPI ? COUT / 4 : (COUT == 16 ? 16 : COUT / 2);
   constexpr int NGRP = COUT / CH;              // active epilogue warps per lane quarter
-  constexpr int SCOUT_WARP = PAIR ? 2 + 4 * NGRP : 10;
+  constexpr int SCOUT_WARP = WEPI ? 2 + 4 * NGRP : 10;
+  static_assert(!DILV || COUT == 32, "the dilated variant exists for 64 -> 32 convs");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -398,7 +404,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       __half* const obase = p.out + (size_t)b * p.out_bs + (size_t)(p.out_chunk0 + grp * (CH / 8)) * p.out_cs +
                             (size_t)(xw < 0 ? 0 : xi) * p.out_px;
       const __half* const r1base = (RES && p.res1) ? p.res1 + (size_t)(p.res1_chunk0 + grp * (CH / 8)) * p.res_cs + col : nullptr;
-      const __half* const r2base = (RES && p.res2) ? p.res2 + (size_t)(p.res2_chunk0 + grp * (CH / 8)) * p.res_cs + col : nullptr;
+      // (the dilated kernels never get a second residual: layers.cu refuses it)
+      const __half* const r2base = (RES && !DILV && p.res2) ? p.res2 + (size_t)(p.res2_chunk0 + grp * (CH / 8)) * p.res_cs + col : nullptr;
       const int nchunks = p.out_nchunks - grp * (CH / 8);   // chunks of this thread that exist in the destination
       float accA[CH], accB[CH];
 #pragma unroll
@@ -416,7 +423,21 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           if (r2base) asm volatile("prefetch.global.L2 [%0];" ::"l"(r2base + ro + (size_t)ch * p.res_cs));
         }
       };
-      auto store_row = [&](int y, const float (&o)[CH]) {
+      // residual inputs of one output row, straight into registers (issued a whole row stage before their use by the
+      // CH = 16 epilogue below: the round trip hides behind the accumulator wait of the next row)
+      auto load_res = [&](int y, uint4 (&s1v)[CH / 8], uint4 (&s2v)[CH / 8]) {
+        if (!RES || !real || y < pc.ya) return;
+        const int yr = DILV ? cres + y * dl : y;
+        if (DILV && yr >= p.H) return;
+        const size_t ro = (size_t)yr * p.res_ys;
+#pragma unroll
+        for (int ch = 0; ch < CH / 8; ++ch) {
+          if (r1base && ch < nchunks) s1v[ch] = *reinterpret_cast<const uint4*>(r1base + ro + (size_t)ch * p.res_cs);
+          if (r2base && ch < nchunks) s2v[ch] = *reinterpret_cast<const uint4*>(r2base + ro + (size_t)ch * p.res_cs);
+        }
+      };
+      auto store_row_impl = [&](int y, const float (&o)[CH], const bool use_pre, const uint4 (&pre1)[CH / 8],
+                                const uint4 (&pre2)[CH / 8]) {
         if (!in_range || !(real || p.out_wide)) return;
         const int yr = DILV ? cres + y * dl : y;   // image row of virtual row y
         if (DILV && yr >= p.H) return;
@@ -426,10 +447,18 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         // one per chunk (measured: 3 200 cycles per row for 4 chunks x 2 residuals when loaded chunk by chunk)
         uint4 s1v[CH / 8], s2v[CH / 8];
         if (RES && real) {
+          if (use_pre) {
 #pragma unroll
-          for (int ch = 0; ch < CH / 8; ++ch) {
-            if (r1base && ch < nchunks) s1v[ch] = *reinterpret_cast<const uint4*>(r1base + ro + (size_t)ch * p.res_cs);
-            if (r2base && ch < nchunks) s2v[ch] = *reinterpret_cast<const uint4*>(r2base + ro + (size_t)ch * p.res_cs);
+            for (int ch = 0; ch < CH / 8; ++ch) {
+              s1v[ch] = pre1[ch];
+              s2v[ch] = pre2[ch];
+            }
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < CH / 8; ++ch) {
+              if (r1base && ch < nchunks) s1v[ch] = *reinterpret_cast<const uint4*>(r1base + ro + (size_t)ch * p.res_cs);
+              if (r2base && ch < nchunks) s2v[ch] = *reinterpret_cast<const uint4*>(r2base + ro + (size_t)ch * p.res_cs);
+            }
           }
         }
 #pragma unroll
@@ -500,8 +529,18 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           else *reinterpret_cast<uint4*>(op + (size_t)ch * p.out_cs) = pk;
         }
       };
+      auto store_row = [&](int y, const float (&o)[CH]) {
+        const uint4 none[CH / 8] = {};
+        store_row_impl(y, o, false, none, none);
+      };
+      // PPON's dilated convs (12 MMAs per row, their epilogue is the critical path): residuals in registers one row
+      // ahead.  Elsewhere the 16 extra registers spill (168 per thread at 352 threads), so the L2 prefetch stays.
+      constexpr bool kRegPrefetch = RES && DILV;
+      uint4 cur1[CH / 8] = {}, cur2[CH / 8] = {};   // kRegPrefetch: residuals of the row stored in this iteration
       for (int r = pc.r0; r <= pc.r1; ++r) {
-        load_side(r);   // row r is finished one iteration (one whole row stage) later: enough to cover an HBM miss
+        uint4 nxt1[CH / 8] = {}, nxt2[CH / 8] = {};
+        if constexpr (kRegPrefetch) load_res(r, nxt1, nxt2);   // row r is stored one iteration (one row stage) later
+        else load_side(r);   // row r is finished one iteration (one whole row stage) later: enough to cover an HBM miss
         mbar_wait(smem_u32(&tfull_bar[slot]), use & 1u);
         tc_fence_after();
         ROWS_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && ecount < 256) p.trace[2048 + ecount++] = clock64());
@@ -536,6 +575,31 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
 #pragma unroll
           for (int c = 0; c < 16; ++c) accB[c] = __uint_as_float(v[c]);
           release_slot();
+        } else if constexpr (CH == 8) {
+          // dilated kernels: 8 channels per thread, all three blocks at once, slot released before the row is stored
+          float o[CH];
+          uint32_t v0[8], v1[8], v2[8];
+          tmem_ld8(tacc, v0);
+          tmem_ld8(tacc + COUT, v1);
+          tmem_ld8(tacc + 2 * COUT, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            o[c] = accA[c] + __uint_as_float(v2[c]);
+            accA[c] = accB[c] + __uint_as_float(v1[c]);
+            accB[c] = __uint_as_float(v0[c]);
+          }
+          release_slot();
+          if constexpr (kRegPrefetch) {
+            if (r - 1 >= pc.ya) store_row_impl(r - 1, o, true, cur1, cur2);
+#pragma unroll
+            for (int ch = 0; ch < CH / 8; ++ch) {
+              cur1[ch] = nxt1[ch];
+              cur2[ch] = nxt2[ch];
+            }
+          } else {
+            if (r - 1 >= pc.ya) store_row(r - 1, o);
+          }
         } else if constexpr (CH == 16) {
           // all three blocks of this thread's channels are read at once and the slot goes back to the MMA warp
           // before the finished row is stored
@@ -552,7 +616,16 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             accB[c] = __uint_as_float(v0[c]);
           }
           release_slot();
-          if (r - 1 >= pc.ya) store_row(r - 1, o);
+          if constexpr (kRegPrefetch) {
+            if (r - 1 >= pc.ya) store_row_impl(r - 1, o, true, cur1, cur2);
+#pragma unroll
+            for (int ch = 0; ch < CH / 8; ++ch) {
+              cur1[ch] = nxt1[ch];
+              cur2[ch] = nxt2[ch];
+            }
+          } else {
+            if (r - 1 >= pc.ya) store_row(r - 1, o);
+          }
         } else {
           // COUT = 64: 3 x 32 running values per thread, read through one 16-register buffer.  The finished row is
           // completed IN accA and stored before the other two blocks are read, so that no separate copy of it is
@@ -582,7 +655,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         }
       }
       if (pc.yb == Hv) {   // bottom row: the row below is zero padding
-        store_row(Hv - 1, accA);
+        if constexpr (kRegPrefetch) store_row_impl(Hv - 1, accA, true, cur1, cur2);
+        else store_row(Hv - 1, accA);
       }
     }
     }
@@ -599,10 +673,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   ROWS_TRACE(if (p.trace && threadIdx.x == 0) p.trace[3072 + blockIdx.x * 8 + 4] = clock64());
 }
 
-template <int COUT, int KSLABS, bool RES, bool PAIR, bool DILV = false>
+template <int COUT, int KSLABS, bool RES, bool PAIR, bool DILV = false, bool WE = false>
 int launch_rows_res(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num_sms, cudaStream_t stream) {
   const size_t smem_bytes = conv_rows_weight_bytes(p.nch, COUT) / (PAIR ? 2 : 1) + (size_t)p.stages * conv_rows_stage_bytes(p.kc) + 1024;
-  auto kern = conv_rows_kernel<COUT, KSLABS, RES, PAIR, DILV>;
+  auto kern = conv_rows_kernel<COUT, KSLABS, RES, PAIR, DILV, WE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int)e;
   const int dl = DILV ? p.dil : 1;
@@ -611,7 +685,7 @@ int launch_rows_res(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num
   if (T < workers) workers = T;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(PAIR ? 2 * workers : workers));
-  cfg.blockDim = dim3(rows_threads(COUT, PAIR));
+  cfg.blockDim = dim3(rows_threads(COUT, PAIR || DILV || WE));
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[3];
@@ -677,6 +751,13 @@ int launch_rows_impl(const CUtensorMap* tmap_in, const ConvRowsParams& p, int nu
       return res ? launch_rows_res<COUT, KSLABS, true, true>(tmap_in, p, num_sms, stream)
                  : launch_rows_res<COUT, KSLABS, false, true>(tmap_in, p, num_sms, stream);
     return (int)cudaErrorInvalidValue;
+  }
+  if constexpr (COUT == 32) {
+    // 16 epilogue warps of 8 channels for the Cout = 32 convs (conv1..conv4 of a dense block): INNFER_ROWS_WEPI bit 0
+    // for the residual-free ones, bit 1 for those with residual inputs (ESRGAN+, nf = 32 nets)
+    static const int wepi = getenv("INNFER_ROWS_WEPI") ? atoi(getenv("INNFER_ROWS_WEPI")) : 3;
+    if (!res && (wepi & 1)) return launch_rows_res<COUT, KSLABS, false, false, false, true>(tmap_in, p, num_sms, stream);
+    if (res && (wepi & 2)) return launch_rows_res<COUT, KSLABS, true, false, false, true>(tmap_in, p, num_sms, stream);
   }
   return res ? launch_rows_res<COUT, KSLABS, true, false>(tmap_in, p, num_sms, stream)
              : launch_rows_res<COUT, KSLABS, false, false>(tmap_in, p, num_sms, stream);

@@ -165,7 +165,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       if (!plain3x3) {
 #pragma unroll
         for (int tp = 0; tp < kMaxTaps; ++tp)
-          aoff[tp] = (uint32_t)p.tap_hy[c.phase][tp] * a_sbo + p.tap_hx[c.phase][tp];
+          aoff[tp] = (uint32_t)p.tap_hy[c.phase][tp] * dil_row + p.tap_hx[c.phase][tp] * dil;   // dil = 0: halo-free 1x1
       }
       for (int ks = 0; ks < p.kslabs; ++ks, ++stage_i) {
         // stage stage_i is ready when the scout has seen its TMA data (and, for the first stage of a

@@ -56,7 +56,7 @@ struct ConvTcParams {
   int tmem_cols;   // power of two >= nslots*N
   long long* trace;  // debugging: clock64 samples of CTA 0 (conv_up.cu, -DINNFER_ROWS_TRACE builds), or null
   int dil;         // dilation of a plain 3x3 conv (PPON's d1..d8, block.py:364-366): taps at (hy*dil, hx*dil) of
-                   // a (16 + 2*dil) x (8J + 2*dil) halo tile; 1 for every other conv
+                   // a (16 + 2*dil) x (8J + 2*dil) halo tile; 1 for every other conv, 0 for 1x1 convs (no halo)
   // destination
   __half* out;
   int out_CT, out_chunk0, out_nchunks;

@@ -35,6 +35,7 @@ struct ConvLayer {
   int N = 0;               // padded Cout: 16, 32 or 64
   int up = 1;              // nearest-upsample factor folded in front of the conv (or PixelShuffle factor)
   int dil = 1;             // dilation (plain 3x3 convs only)
+  bool centre_only = false;  // 1x1 conv: the only tap is the centre one, the tensor-core kernel needs no halo
   bool pixel_shuffle = false;  // conv -> PixelShuffle(up) (block.py:333-346): phase = output sub-pixel
   int nphase = 1;
   uint32_t ph_woff[kMaxPhases] = {};

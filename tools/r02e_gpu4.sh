@@ -1,0 +1,7 @@
+#!/bin/bash
+# round 2e: PPON-related GPU tests + PPON launch list
+mkdir -p gpurun_out
+python -m pytest tests -x -q -m gpu -k "ppon or PPON or batch_forward or small" > gpurun_out/r02e_pytest_ppon.log 2>&1; tail -3 gpurun_out/r02e_pytest_ppon.log
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active
+ncu --metrics $M --clock-control none --csv --log-file gpurun_out/r02e_ppon.csv python tests/gpu_bringup.py --stage ppon_prof > gpurun_out/r02e_ppon.log 2>&1
+tail -n 1 gpurun_out/r02e_ppon.log
