@@ -11,7 +11,7 @@
 // (a, b) of source pixel (y, x) goes to output pixel (2y + a, 2x + b) -- overlaps the next tile's MMAs.
 //
 // Same conventions as conv_tc.cu: planar-chunk fp16 tensors, tiled or wide source (separator columns skipped /
-// stored as zeros), generic destination strides, producer / issuer / 8 epilogue warps / scout.
+// stored as zeros), generic destination strides, producer / issuer / 16 epilogue warps / scout.
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 
@@ -30,8 +30,8 @@ constexpr int kUpPhases = 4, kUpTaps = 4;
 constexpr int kUpWh = 10, kUpRh = kPatchRows + 2;            // halo tile of a 16 x 8 patch
 constexpr int kUpABytes = 2 * kUpRh * kUpWh * 16;            // 5760 B per 16-channel slab (multiple of 128)
 constexpr uint32_t kUpTapUnits = 2 * kUpN;                   // 16-byte units per (phase, slab, tap) weight block
-constexpr int kUpThreads = 352;                              // producer, issuer, 8 epilogue warps, scout
-constexpr int kUpScoutWarp = 10;
+constexpr int kUpThreads = 608;                              // producer, issuer, 16 epilogue warps, scout
+constexpr int kUpScoutWarp = 18;
 
 struct UpTile {
   int b, y0, x0;
@@ -86,7 +86,7 @@ conv_up_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&tfull_bar[i]), 1);
-    for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&set_bar[i]), 8);
+    for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&set_bar[i]), 16);
     mbar_init(smem_u32(wfull_bar), 1);
     *ready_cnt = 0u;
     fence_mbar_init();
@@ -211,14 +211,11 @@ conv_up_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     // ------------------------------------------------------------ epilogue warps
     pdl_wait();
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int ph = (warp - 2) >> 2;          // output phase (a, b) = (ph >> 1, ph & 1) of this warp
+    const int pa = ph >> 1, pb = ph & 1;
     const int m = q * 32 + lane;
     const int r = m >> 3, cc = m & 7;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    constexpr int NCH = kUpN / 8;
-    float bias[kUpN];   // the four phases of an upsample-folded conv share one bias vector
-#pragma unroll
-    for (int i = 0; i < kUpN; ++i) bias[i] = s_bias[i];
     const bool lrelu = p.lrelu != 0;
     const float slope = p.slope;
     const int nchunks = p.out_nchunks;
@@ -239,35 +236,40 @@ conv_up_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       mbar_wait(smem_u32(&tfull_bar[it & 1u]), (it >> 1) & 1u);
       tc_fence_after();
       UP_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < 64) p.trace[2048 + it * 2] = clock64());
-      // Eight epilogue warps: two per TMEM lane quarter, `half` takes the output rows 2y + half, i.e. phases
-      // (half, 0) and (half, 1).  (The epilogue is instruction-bound here: a tile has 9/4 of the outputs per MMA of a
-      // plain 3x3 conv; with four warps it took 7300 cycles per tile against 3000 cycles of MMAs.)
-#pragma unroll 1
-      for (int b = 0; b < 2; ++b) {
-        const int ph = 2 * half + b;
-        const uint32_t tacc = tmem_base + lane_base + (uint32_t)(((it & 1u) * kUpPhases + ph) * kUpN);
-        uint32_t v[kUpN];
+      // Sixteen epilogue warps: four per TMEM lane quarter, one per output phase (a, b); a thread drains the 64
+      // channels of its source pixel's phase in two halves of 32 and stores them to output pixel (2y + a, 2x + b).
+      // (The epilogue is latency / instruction bound: a tile has 9/4 of the outputs per MMA of a plain 3x3 conv; four
+      // warps took 7300 cycles per tile, eight 3600, against ~2100-3000 cycles of MMAs.)
+      const uint32_t tacc = tmem_base + lane_base + (uint32_t)(((it & 1u) * kUpPhases + ph) * kUpN);
+      const int oy = 2 * y + pa, ox = 2 * xi + pb;
+      __half* op = p.out + (size_t)img * p.out_bs + (size_t)p.out_chunk0 * p.out_cs + (size_t)oy * p.out_ys + (size_t)ox * 8;
 #pragma unroll
-        for (int g = 0; g < kUpN / 16; ++g) tmem_ld16(tacc + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[g * 16]));
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t v[32];
+        tmem_ld16(tacc + hf * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        tmem_ld16(tacc + hf * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
         tmem_ld_wait();
-        if (b == 1) {   // this warp's half of the set is in registers: hand it back
+        if (hf == 1) {   // this warp's part of the set is in registers: hand it back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&set_bar[it & 1u]));
           UP_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < 64) p.trace[2048 + it * 2 + 1] = clock64());
         }
-        const int oy = 2 * y + half, ox = 2 * xi + b;
-        __half* op = p.out + (size_t)img * p.out_bs + (size_t)p.out_chunk0 * p.out_cs + (size_t)oy * p.out_ys + (size_t)ox * 8;
         if (valid) {
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) {
+          for (int k = 0; k < 4; ++k) {
+            const int ch = hf * 4 + k;
             if (ch < nchunks) {
-              float f[8];
+              // (the bias table sits 8 bytes past a 16-byte boundary: 8-byte reads, the same address for the warp)
+              const float2* bp = reinterpret_cast<const float2*>(s_bias + ch * 8);
+              const float2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+              float f[8] = {__uint_as_float(v[k * 8 + 0]) + b0.x, __uint_as_float(v[k * 8 + 1]) + b0.y,
+                            __uint_as_float(v[k * 8 + 2]) + b1.x, __uint_as_float(v[k * 8 + 3]) + b1.y,
+                            __uint_as_float(v[k * 8 + 4]) + b2.x, __uint_as_float(v[k * 8 + 5]) + b2.y,
+                            __uint_as_float(v[k * 8 + 6]) + b3.x, __uint_as_float(v[k * 8 + 7]) + b3.y};
+              if (lrelu) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float t = __uint_as_float(v[ch * 8 + e]) + bias[ch * 8 + e];
-                if (lrelu) t = t > 0.f ? t : t * slope;
-                f[e] = t;
+                for (int e = 0; e < 8; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * slope;
               }
               uint4 o;
               const __half2 h0 = __floats2half2_rn(f[0], f[1]);
@@ -283,8 +285,8 @@ conv_up_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
           }
         } else if (inside && p.out_zero_sep) {
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch)
-            if (ch < p.out_nchunks) *reinterpret_cast<uint4*>(op + (size_t)ch * p.out_cs) = make_uint4(0u, 0u, 0u, 0u);
+          for (int k = 0; k < 4; ++k)
+            if (hf * 4 + k < nchunks) *reinterpret_cast<uint4*>(op + (size_t)(hf * 4 + k) * p.out_cs) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
     }
