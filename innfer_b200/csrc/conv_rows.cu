@@ -219,7 +219,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     // in shared memory; this thread re-reads that word only when it runs out of known-ready stages,
     // in the middle of a stage, while the first half of the stage's MMAs is still queued.
     const bool leader = elect_one();
+#ifdef INNFER_EXPERIMENTS   // INNFER_ROWS_DX0=3 (wrong results): MMAs of half the N extent -- half the B operand per MMA
+    const uint32_t idesc = PAIR ? make_idesc_f16_m256(p.dbg_dx0 == 3 ? N / 2 : N) : make_idesc_f16(p.dbg_dx0 == 3 ? N / 2 : N);
+#else
     const uint32_t idesc = PAIR ? make_idesc_f16_m256(N) : make_idesc_f16(N);
+#endif
     const uint32_t dxu = p.dbg_dx0 == 1 ? 0u : (DILV ? (uint32_t)p.dil : 1u);    // pixels (16-byte units) between the horizontal taps
     constexpr uint32_t a_lbo = kRowPx;                   // 16-byte units between the two K chunks
     constexpr uint32_t a_hi = 8u | (1u << 14);           // SBO = 128 B (8 consecutive pixels)
@@ -436,8 +440,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           if (r2base && ch < nchunks) s2v[ch] = *reinterpret_cast<const uint4*>(r2base + ro + (size_t)ch * p.res_cs);
         }
       };
-      auto store_row_impl = [&](int y, const float (&o)[CH], const bool use_pre, const uint4 (&pre1)[CH / 8],
+      // use_pre: 0 = load the residuals here, 1 = preloaded by load_res
+      auto store_row_impl = [&](int y, const float (&o)[CH], const int use_pre, const uint4 (&pre1)[CH / 8],
                                 const uint4 (&pre2)[CH / 8]) {
+#ifdef INNFER_EXPERIMENTS   // INNFER_ROWS_DX0=2 (wrong results): the epilogue only drains TMEM, no residual loads / stores
+        if (p.dbg_dx0 == 2) return;
+#endif
         if (!in_range || !(real || p.out_wide)) return;
         const int yr = DILV ? cres + y * dl : y;   // image row of virtual row y
         if (DILV && yr >= p.H) return;
@@ -447,7 +455,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         // one per chunk (measured: 3 200 cycles per row for 4 chunks x 2 residuals when loaded chunk by chunk)
         uint4 s1v[CH / 8], s2v[CH / 8];
         if (RES && real) {
-          if (use_pre) {
+          if (use_pre == 1) {
 #pragma unroll
             for (int ch = 0; ch < CH / 8; ++ch) {
               s1v[ch] = pre1[ch];
@@ -531,19 +539,21 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       };
       auto store_row = [&](int y, const float (&o)[CH]) {
         const uint4 none[CH / 8] = {};
-        store_row_impl(y, o, false, none, none);
+        store_row_impl(y, o, 0, none, none);
       };
       // PPON's dilated convs (12 MMAs per row, their epilogue is the critical path): residuals in registers one row
       // ahead.  Elsewhere the 16 extra registers spill (168 per thread at 352 threads), so the L2 prefetch stays.
       constexpr bool kRegPrefetch = RES && DILV;
       uint4 cur1[CH / 8] = {}, cur2[CH / 8] = {};   // kRegPrefetch: residuals of the row stored in this iteration
       for (int r = pc.r0; r <= pc.r1; ++r) {
+        ROWS_TRACE(if (r > pc.r0 || ecount > 0) ++ecount);
         uint4 nxt1[CH / 8] = {}, nxt2[CH / 8] = {};
         if constexpr (kRegPrefetch) load_res(r, nxt1, nxt2);   // row r is stored one iteration (one row stage) later
         else load_side(r);   // row r is finished one iteration (one whole row stage) later: enough to cover an HBM miss
         mbar_wait(smem_u32(&tfull_bar[slot]), use & 1u);
         tc_fence_after();
-        ROWS_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && ecount < 256) p.trace[2048 + ecount++] = clock64());
+        ROWS_TRACE(const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 64 && ecount < 256;
+                   if (tr) p.trace[2048 + ecount] = clock64());
         const uint32_t tacc = tmem_base + lane_base + (uint32_t)(slot * N + grp * CH);
         auto release_slot = [&]() {
           tc_fence_before();
@@ -565,7 +575,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 16; ++c) accA[c] += __uint_as_float(v[c]);
+          ROWS_TRACE(if (tr) p.trace[2304 + ecount] = clock64());
+          // (measured, round 2e: issuing the residual loads before the accumulator wait does not help -- the epilogue
+          // is itself the critical path here, so there is no wait to hide them behind, and the extra live registers
+          // spill at 96 per thread: 455 -> 462 us per 63-tile launch)
           if (r - 1 >= pc.ya) store_row(r - 1, accA);
+          ROWS_TRACE(if (tr) p.trace[2560 + ecount] = clock64());
           tmem_ld16(tacc + COUT, v);
           tmem_ld_wait();
 #pragma unroll
@@ -575,6 +590,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
 #pragma unroll
           for (int c = 0; c < 16; ++c) accB[c] = __uint_as_float(v[c]);
           release_slot();
+          ROWS_TRACE(if (tr) p.trace[2816 + ecount] = clock64());
         } else if constexpr (CH == 8) {
           // dilated kernels: 8 channels per thread, all three blocks at once, slot released before the row is stored
           float o[CH];
@@ -591,7 +607,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           }
           release_slot();
           if constexpr (kRegPrefetch) {
-            if (r - 1 >= pc.ya) store_row_impl(r - 1, o, true, cur1, cur2);
+            if (r - 1 >= pc.ya) store_row_impl(r - 1, o, 1, cur1, cur2);
 #pragma unroll
             for (int ch = 0; ch < CH / 8; ++ch) {
               cur1[ch] = nxt1[ch];
@@ -617,7 +633,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           }
           release_slot();
           if constexpr (kRegPrefetch) {
-            if (r - 1 >= pc.ya) store_row_impl(r - 1, o, true, cur1, cur2);
+            if (r - 1 >= pc.ya) store_row_impl(r - 1, o, 1, cur1, cur2);
 #pragma unroll
             for (int ch = 0; ch < CH / 8; ++ch) {
               cur1[ch] = nxt1[ch];
@@ -655,7 +671,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         }
       }
       if (pc.yb == Hv) {   // bottom row: the row below is zero padding
-        if constexpr (kRegPrefetch) store_row_impl(Hv - 1, accA, true, cur1, cur2);
+        if constexpr (kRegPrefetch) store_row_impl(Hv - 1, accA, 1, cur1, cur2);
         else store_row(Hv - 1, accA);
       }
     }

@@ -250,6 +250,34 @@ def stage_trace():
     return True
 
 
+def stage_trace_pair():
+    """clock64 trace of the conv5 CTA-pair epilogue (INNFER_TRACE_BUILD=1): warp 2 of CTA 0, per row
+    tfull seen -> first block read -> store_row done -> slot released."""
+    os.environ["INNFER_TRACE_NCH"] = "24"
+    lib = N.load()
+    buf = torch.zeros(3072 + 148 * 8, dtype=torch.int64, device=dev)
+    lib.innfer_debug_set_trace(ctypes.c_void_p(buf.data_ptr()))
+    stage_prof()
+    lib.innfer_debug_set_trace(None)
+    t = buf.cpu().numpy()
+    ep = np.stack([t[2048:2304], t[2304:2560], t[2560:2816], t[2816:3072]], 1)
+    k = int((ep[:, 3] != 0).sum())
+    d = ep[8:k - 2]
+    print("rows traced", k)
+    print("median cycles: row period %.0f | tfull->block2 read %.0f | store_row %.0f | blocks 1,0 + release %.0f | released->next tfull %.0f"
+          % (np.median(np.diff(d[:, 0])), np.median(d[:, 1] - d[:, 0]), np.median(d[:, 2] - d[:, 1]),
+             np.median(d[:, 3] - d[:, 2]), np.median(d[1:, 0] - d[:-1, 3])))
+    for i in range(8, 40):
+        print("%3d: period %6d | ld2 %5d | store %5d | ld1,0+rel %5d | idle %6d" % (
+            i, ep[i + 1, 0] - ep[i, 0], ep[i, 1] - ep[i, 0], ep[i, 2] - ep[i, 1], ep[i, 3] - ep[i, 2], ep[i + 1, 0] - ep[i, 3]))
+    c = t[3072:].reshape(148, 8)
+    lead = c[c[:, 5] > 0]
+    if len(lead):
+        per = (lead[:, 3] - lead[:, 2]) / lead[:, 5]
+        print("issuing CTAs %d: cycles per stage (18 MMAs) median %.0f min %.0f max %.0f" % (len(lead), np.median(per), per.min(), per.max()))
+    return True
+
+
 def stage_steady():
     """Power-limited steady state of single conv kernels: ~3 s of back-to-back launches each, NVML sampled."""
     import threading
@@ -635,6 +663,6 @@ if __name__ == "__main__":
     ap.add_argument("--stage", required=True)
     a = ap.parse_args()
     t0 = time.time()
-    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "trace_up": stage_trace_up, "ppon": stage_ppon, "ppon_prof": stage_ppon_prof, "ppon_time": stage_ppon_time, "pan_time": stage_pan_time, "srres_time": stage_srres_time, "lat": stage_lat, "pan_prof": stage_pan_prof, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3, "i2i_time": stage_i2i_time, "i2i_prof": stage_i2i_prof}[a.stage]()
+    ok = {"conv1": stage_conv1, "convs": stage_convs, "net": stage_net, "time": stage_time, "prof": stage_prof, "trace": stage_trace, "trace_pair": stage_trace_pair, "trace_up": stage_trace_up, "ppon": stage_ppon, "ppon_prof": stage_ppon_prof, "ppon_time": stage_ppon_time, "pan_time": stage_pan_time, "srres_time": stage_srres_time, "lat": stage_lat, "pan_prof": stage_pan_prof, "steady": stage_steady, "pix": stage_pix, "cfg3": stage_cfg3, "i2i_time": stage_i2i_time, "i2i_prof": stage_i2i_prof}[a.stage]()
     print("STAGE %s %s (%.1fs)" % (a.stage, "OK" if ok else "FAILED", time.time() - t0))
     sys.exit(0 if ok else 1)
