@@ -85,7 +85,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&tfull_bar[i]), 1);
-    for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&set_bar[i]), 8);
+    for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&set_bar[i]), 16);
     *ready_cnt = 0u;
     fence_mbar_init();
   }
@@ -285,12 +285,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     }
   } else {
     // ------------------------------------------------------------ epilogue warps
+    // Sixteen epilogue warps = four per TMEM lane quarter: `grp` takes the sub-tiles j = grp, grp + 2, ... of every
+    // tile, `hh` the 8-channel chunks ch = hh, hh + 2, ... of the accumulator (N = 16: both chunks, the hh = 1 warps
+    // idle).  The epilogue of these small-N convs is a chain of latencies (accumulator wait, TMEM read, residual
+    // loads, stores): eight warps -- two per scheduler -- left the SM waiting on it (round 2e).  A self-gated conv
+    // pairs chunk ch with chunk ch + NCH / 2, which has the same parity for N = 32 and 64.
     const int q = warp & 3;
-    const int grp = (warp - 2) >> 2;   // sub-tiles j = grp, grp + 2, ... of every tile
+    const int grp = ((warp - 2) >> 2) & 1;
+    const int hh = (warp - 2) >> 3;
+    constexpr int NCH = N / 8;
+    constexpr int KC = N >= 32 ? NCH / 2 : NCH;   // chunks per thread
+    constexpr int CSTEP = N >= 32 ? 2 : 1;
+    const bool active = N >= 32 || hh == 0;
+    const int ch0 = N >= 32 ? hh : 0;
     const int m = q * 32 + lane;
     const int r = m >> 3, cc = m & 7;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    constexpr int NCH = N / 8;
     int it = 0;
     TileIter ti;
     ti.init(p, blockIdx.x, gridDim.x);
@@ -301,9 +311,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       const int y = c.y0 + r;
       const int oy = y * p.up + p.ph_a[c.phase];
       const uint32_t sb = smem_u32(&set_bar[it & 1]);
-      if (grp >= c.jeff) {   // nothing of this tile for this group: its share of the set is "drained"
+      if (!active || grp >= c.jeff) {   // nothing of this tile for this warp: its share of the set is "drained"
         __syncwarp();
         if (lane == 0) mbar_arrive(sb);
+        continue;
       }
       for (int j = grp; j < c.jeff; j += 2) {
         const uint32_t tacc = tmem_base + lane_base + (uint32_t)(((it & 1) * p.J + j) * N);
@@ -320,25 +331,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         const int ox = xi * p.up + p.ph_b[c.phase];
         // 1. residual loads first: their latency overlaps the TMEM read and nothing below the
         //    slot release depends on the tensor pipe any more
-        uint4 r1[NCH], r2[NCH];
+        uint4 r1[KC], r2[KC];
         if (p.res1 != nullptr) {
           const __half* rp = p.res1 + (size_t)img * p.res1_bs + (size_t)p.res1_chunk0 * p.res1_cs + (size_t)oy * p.res1_ys + (size_t)ox * 8;
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch)
-            if (valid && ch < p.out_nchunks) r1[ch] = *reinterpret_cast<const uint4*>(rp + (size_t)ch * p.res1_cs);
+          for (int k = 0; k < KC; ++k) {
+            const int ch = ch0 + CSTEP * k;
+            if (valid && ch < p.out_nchunks) r1[k] = *reinterpret_cast<const uint4*>(rp + (size_t)ch * p.res1_cs);
+          }
         }
         if (p.res2 != nullptr) {
           const __half* rp = p.res2 + (size_t)img * p.res2_bs + (size_t)p.res2_chunk0 * p.res2_cs + (size_t)oy * p.res2_ys + (size_t)ox * 8;
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch)
-            if (valid && ch < p.out_nchunks) r2[ch] = *reinterpret_cast<const uint4*>(rp + (size_t)ch * p.res2_cs);
+          for (int k = 0; k < KC; ++k) {
+            const int ch = ch0 + CSTEP * k;
+            if (valid && ch < p.out_nchunks) r2[k] = *reinterpret_cast<const uint4*>(rp + (size_t)ch * p.res2_cs);
+          }
         }
-        // 2. drain the accumulator into registers (the set goes back to the MMA warp after the last one)
-        uint32_t v[N];
+        // 2. drain this warp's chunks of the accumulator into registers (the set goes back to the MMA warp after the
+        //    last one)
+        uint32_t v[KC * 8];
 #pragma unroll
-        for (int g = 0; g < N / 16; ++g) tmem_ld16(tacc + g * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[g * 16]));
+        for (int k = 0; k < KC; ++k)
+          tmem_ld8(tacc + (uint32_t)((ch0 + CSTEP * k) * 8), *reinterpret_cast<uint32_t(*)[8]>(&v[k * 8]));
         tmem_ld_wait();
-        if (j + 2 >= c.jeff) {  // this group's last accumulator of the tile is in registers: release its share of the set
+        if (j + 2 >= c.jeff) {  // this warp's last accumulator of the tile is in registers: release its share of the set
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(sb);
@@ -347,27 +364,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         __half* op = p.out + (size_t)img * p.out_bs + (size_t)p.out_chunk0 * p.out_cs + (size_t)oy * p.out_ys + (size_t)ox * p.out_px;
         if (valid) {
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch) {
+          for (int k = 0; k < KC; ++k) {
+            const int ch = ch0 + CSTEP * k;
             if (ch < p.out_nchunks) {
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                float tv = __uint_as_float(v[ch * 8 + e]) + s_bias[c.phase * N + ch * 8 + e];
+                float tv = __uint_as_float(v[k * 8 + e]) + s_bias[c.phase * N + ch * 8 + e];
                 if (p.lrelu && !p.act_after_res) tv = lrelu_f(tv, p.slope);
                 f[e] = tv;
               }
               if (p.gate == 2) {
-                constexpr int PC = (NCH / 2 > 0 ? NCH / 2 : 1);   // chunks per half
-                if (ch < PC) {
+                constexpr int PC = (NCH / 2 > 0 ? NCH / 2 : 1);   // chunks per half of a self-gated conv
+                constexpr int PK = (PC / CSTEP > 0 ? PC / CSTEP : 1);   // ... in this thread's chunk list
+                if (ch < PC && k + PK < KC) {
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
-                    const float gv = __uint_as_float(v[(ch + PC) * 8 + e]) + s_bias[c.phase * N + (ch + PC) * 8 + e];
+                    const float gv = __uint_as_float(v[(k + PK) * 8 + e]) + s_bias[c.phase * N + (ch + PC) * 8 + e];
                     f[e] = __fdividef(f[e], 1.f + __expf(-gv));
                   }
                 }
               }
               if (p.res1 != nullptr) {
-                const __half2* hp = reinterpret_cast<const __half2*>(&r1[ch]);
+                const __half2* hp = reinterpret_cast<const __half2*>(&r1[k]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   float2 rv = __half22float2(hp[e]);
@@ -387,7 +406,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
                 }
               }
               if (p.res2 != nullptr) {
-                const __half2* hp = reinterpret_cast<const __half2*>(&r2[ch]);
+                const __half2* hp = reinterpret_cast<const __half2*>(&r2[k]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 rv = __half22float2(hp[e]);
@@ -431,13 +450,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
         } else if (inside && p.out_zero_sep) {
           // separator column of a wide destination: keep the zero padding between images intact
 #pragma unroll
-          for (int ch = 0; ch < NCH; ++ch)
+          for (int k = 0; k < KC; ++k) {
+            const int ch = ch0 + CSTEP * k;
             if (ch < p.out_nchunks) {
               *reinterpret_cast<uint4*>(op + (size_t)ch * p.out_cs) = make_uint4(0u, 0u, 0u, 0u);
               if (p.raw != nullptr)
                 *reinterpret_cast<uint4*>(p.raw + (size_t)img * p.raw_bs + (size_t)(p.raw_chunk0 + ch) * p.raw_cs +
                                           (size_t)oy * p.raw_ys + (size_t)ox * 8) = make_uint4(0u, 0u, 0u, 0u);
             }
+          }
         }
       }
     }

@@ -33,8 +33,8 @@
 
 namespace innfer {
 
-constexpr int kConvThreads = 352;         // producer, issuer, 8 epilogue warps, scout (does the issuer's barrier waits)
-constexpr int kConvScoutWarp = 10;
+constexpr int kConvThreads = 608;         // producer, issuer, 16 epilogue warps, scout (does the issuer's barrier waits)
+constexpr int kConvScoutWarp = 18;
 constexpr int kPatchRows = 16;            // rows per CTA patch (= rows of one M=128 sub-patch)
 constexpr int kMaxPhases = 9;
 constexpr int kMaxTaps = 9;
