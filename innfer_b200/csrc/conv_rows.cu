@@ -122,7 +122,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   const int S = p.stages;
   const int dl = DILV ? p.dil : 1;   // dilation (compile-time 1 for every kernel of the plain nets)
   const uint32_t stage_bytes = (uint32_t)p.kc * kRowPx * 16;
-  const uint32_t w_total = (uint32_t)(p.nch / 2) * 3u * 2u * NB * 16u;
+  const uint32_t w_main = (uint32_t)(p.nch / 2) * 3u * 2u * NB * 16u;
+  const uint32_t w_total = w_main + (PAIR ? (uint32_t)kRowsIdtBytes : 0u);   // PAIR: + the identity tiles (IDT)
   uint8_t* bar_base = smem + w_total + (size_t)S * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + S;
@@ -232,6 +233,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
     constexpr uint32_t b_sub_step = (uint32_t)KSLABS * 3u * b_blk;
     constexpr int KH = KSLABS > 1 ? KSLABS / 2 : 1;
     const uint32_t b_lo0 = ((w_base & 0x3FFFFu) >> 4) | ((uint32_t)NB << 16);
+    const bool idt = PAIR && p.idt != 0;
+    const uint32_t idt_lo = (((w_base + w_main) & 0x3FFFFu) >> 4) | (32u << 16);   // 32 rows per K chunk
+    const uint32_t idesc_idt = PAIR ? make_idesc_f16_m256(COUT) : 0u;
     const uint32_t a_step = stage_bytes >> 4;
     const uint32_t a_first = ((ring_base & 0x3FFFFu) >> 4) | (a_lbo << 16);
     const uint32_t a_last = a_first + (uint32_t)(S - 1) * a_step;
@@ -314,6 +318,16 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           for (int dx = 0; dx < 3; ++dx)
             mma(acc, make_desc64(a_lo + (uint32_t)(kk * 2 * a_lbo) + (uint32_t)dx * dxu, a_hi),
                 make_desc64(b_lo + (uint32_t)((kk * 3 + dx) * b_blk), b_hi), 1u);
+        }
+        if constexpr (PAIR) {
+          // IDT: the residual x (input channels 0..63, centre tap) enters the centre-row block of the accumulator
+          // through four N = 64 MMAs against identity tiles: D[:, COUT + co] += x[:, co] / alpha1
+          if (idt && sub == 0) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16_ss_pair(acc + (uint32_t)COUT, make_desc64(a_lo + (uint32_t)(kk * 2 * a_lbo) + dxu, a_hi),
+                               make_desc64(idt_lo + (uint32_t)(kk * 64), b_hi), idesc_idt, 1u);
+          }
         }
         commit(ebar);
         if (row_end) commit(tbar);
@@ -481,6 +495,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             if (p.lrelu && !(DILV && p.act_after_res)) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * p.slope;
+            }
+            if (PAIR && p.idt) {   // the residual is already in the accumulator (as x / alpha1)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] *= p.alpha1;
             }
             if (r1base) {
               const __half2* hp = reinterpret_cast<const __half2*>(&s1);
@@ -691,7 +709,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
 
 template <int COUT, int KSLABS, bool RES, bool PAIR, bool DILV = false, bool WE = false>
 int launch_rows_res(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num_sms, cudaStream_t stream) {
-  const size_t smem_bytes = conv_rows_weight_bytes(p.nch, COUT) / (PAIR ? 2 : 1) + (size_t)p.stages * conv_rows_stage_bytes(p.kc) + 1024;
+  const size_t smem_bytes = conv_rows_weight_bytes(p.nch, COUT) / (PAIR ? 2 : 1) + (PAIR ? kRowsIdtBytes : 0) +
+                            (size_t)p.stages * conv_rows_stage_bytes(p.kc) + 1024;
   auto kern = conv_rows_kernel<COUT, KSLABS, RES, PAIR, DILV, WE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int)e;

@@ -42,6 +42,8 @@ struct ConvRowsParams {
   int lrelu;
   float slope;
   int pair;              // 1: clusters of two CTAs, M = 256 MMAs, half of the weight columns per CTA (conv_rows.cu)
+  int idt;               // pair only: t = (acc + bias) * alpha1 where the accumulator already holds x / alpha1 for the
+                         // residual x = input channels 0..63 (identity MMAs, see kRowsIdtBytes); res1 is null then
   // dilated variant (PPON's 64 -> 32 convs, conv_rows.cu DILV): taps at distance `dil` (1..8; the separator between the
   // images must be at least that wide), LeakyReLU AFTER the res1 add, optional second store of the pre-activation value
   int dil;
@@ -54,6 +56,10 @@ struct ConvRowsParams {
   int dbg_dx0;           // timing experiment (INNFER_ROWS_DX0=1, wrong results): all three horizontal taps read the 128-byte
                          // aligned window, to measure what the 16/32-byte shifted A descriptors cost
 };
+
+// CTA-pair weights: every half is followed by four identity B tiles ([kchunk][32 rows][8] fp16, 1 KB each)
+constexpr int kRowsIdtBytes = 4096;
+constexpr float kRowsIdtScale = 5.0f;   // 1 / 0.2, exact in fp16; 0.2f * 5.0f == 1.0f in fp32
 
 int launch_conv_rows(const CUtensorMap* tmap_in, const ConvRowsParams& p, int cout, int num_sms, cudaStream_t stream);
 int conv_rows_stage_bytes(int kc);

@@ -142,15 +142,25 @@ int conv_layer_build(ConvLayer& L, const float* w_in, const float* bias, int Cou
   std::vector<__half> packed_pair;
   if (!packed_rows.empty() && Cout == 64 && Cin > 64) {
     const int NR = 3 * Cout, NH = NR / 2;
-    packed_pair.resize(packed_rows.size());
+    packed_pair.resize(packed_rows.size() + 2 * (size_t)kRowsIdtBytes / sizeof(__half));
     size_t o = 0;
-    for (int half = 0; half < 2; ++half)
+    for (int half = 0; half < 2; ++half) {
       for (int ks = 0; ks < kslabs; ++ks)
         for (int dx = 0; dx < 3; ++dx)
           for (int kc = 0; kc < 2; ++kc)
             for (int n = 0; n < NH; ++n)
               for (int e = 0; e < 8; ++e)
                 packed_pair[o++] = packed_rows[((((size_t)ks * 3 + dx) * 2 + kc) * NR + half * NH + n) * 8 + e];
+      // "identity" B tiles behind this half's weights (conv_rows.cu, IDT): four K slabs (input channels 0..63) x
+      // [kchunk][32 output channels of this half][8], value 1 / 0.2 where ci == co -- the block's `0.2 * conv + x`
+      // residual then comes out of four extra N = 64 MMAs into the centre-row block of the accumulator instead of
+      // being loaded by the epilogue
+      for (int ks = 0; ks < 4; ++ks)
+        for (int kc = 0; kc < 2; ++kc)
+          for (int n = 0; n < 32; ++n)
+            for (int e = 0; e < 8; ++e)
+              packed_pair[o++] = __float2half_rn((ks * 16 + kc * 8 + e == half * 32 + n) ? kRowsIdtScale : 0.f);
+    }
   }
   L.w_bytes = packed.size() * sizeof(__half);
   std::vector<float> hb((size_t)L.nphase * N, 0.f);
@@ -318,7 +328,7 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   // amortised over 12..30 MMAs)
   const bool pair = S < 3 && L.d_wrows_pair != nullptr && (rows_mode & 4) && CR == 64 && kc == 12;
   if (pair) {
-    wbytes /= 2;
+    wbytes = wbytes / 2 + kRowsIdtBytes;
     S = (232448 - 1024 - wbytes) / conv_rows_stage_bytes(kc);
   }
   if (S < 3) return -100;
@@ -375,6 +385,16 @@ static int conv_rows_run(const ConvLayer& L, TmapCache& cache, ChunkView in, int
   p.res2 = ep.res2.base;
   p.res2_chunk0 = ep.res2.chunk0;
   p.alpha2 = ep.alpha2;
+  // conv5 of a dense block on a CTA pair: res1 is the block's input x = the first 64 channels of the conv's own input,
+  // already staged in shared memory for the MMAs -- `alpha1 * conv + x` comes out of four identity MMAs per row
+  // (x * (1 / alpha1) into the accumulator) and the epilogue neither loads nor waits for it.  INNFER_ROWS_IDT=0 keeps
+  // the loaded residual (A/B switch).
+  static const int idt_mode = getenv("INNFER_ROWS_IDT") ? atoi(getenv("INNFER_ROWS_IDT")) : 1;
+  if (idt_mode && pair && !ep.lrelu && ep.res1.base == in.base && ep.res1.chunk0 == in.chunk0 && ep.res1.CT == in.CT &&
+      L.Cout == 64 && std::fabs(ep.alpha1 * kRowsIdtScale - 1.f) < 1e-6f) {
+    p.res1 = nullptr;
+    p.idt = 1;
+  }
   p.dil = L.dil;
   p.act_after_res = ep.act_after_res ? 1 : 0;
   p.res1_unact = ep.res1_unact ? 1 : 0;
