@@ -538,7 +538,8 @@ def run_small(args, dev, warm):
             ref_ms = (time.perf_counter() - t0) * 1e3 / 3
             rec["torch_gpu_reference_ms"] = ref_ms
             rec["ours_e2e_over_reference_gpu"] = ref_ms / e2e_ms
-            rec["max_abs_u8_diff_vs_reference_gpu_fp16"] = int(np.abs(np.asarray(out).astype(int) - np.asarray(runner(frames[1])).astype(int)).max())
+            # same frame through both (the timed loop above ends on frames[0])
+            rec["max_abs_u8_diff_vs_reference_gpu_fp16"] = int(np.abs(np.asarray(one(frames[1])).astype(int) - np.asarray(runner(frames[1])).astype(int)).max())
             del rm
         cases.append(rec)
         del runner, m

@@ -132,7 +132,8 @@ __global__ void image_to_tiles_kernel(const void* __restrict__ src_, int C, cons
 // utils.py:164-194,318-369): a block is (4 tile rows) x (64 pixel columns), the 256 possible `v / 255` values come from
 // a shared-memory table filled with the same expression the generic kernel evaluates (bit-identical), every thread
 // converts one pixel at a time and stores its 16-byte chunk; chunks past the image's channels are zero fill.
-// No 64-bit index arithmetic, no per-pixel division: 62 -> 13 us per 95-tile batch (profiles/r02e_pixel_kernels.md).
+// No 64-bit index arithmetic, no per-pixel division: 62 -> 35 us per 95-tile batch with both chunks written, 23 us per
+// 63 tiles when the engine skips the pad chunk (profiles/r02e_pixel_kernels.md).
 template <typename E>
 __global__ void __launch_bounds__(256)
 image_to_tiles_u8_kernel(const uint8_t* __restrict__ src, int C, const __grid_constant__ TileGeom g, int t0, int nt,
