@@ -30,7 +30,9 @@ for name, blk in zip(names, blocks):
             if key.startswith("SYNCS"):
                 key = "SYNCS"
             cnt[key] += 1
-    short = name.replace("innfer::(anonymous namespace)::", "").replace("innfer::<unnamed>::", "").split("(")[0]
+    short = name.replace("innfer::(anonymous namespace)::", "").replace("innfer::<unnamed>::", "")
+    short = re.sub(r"\((int|bool)\)", "", short)          # cu++filt prints template arguments as (int)64, (bool)1
+    short = short[:short.index(">(") + 1] if ">(" in short else short.split("(")[0]
     if any(k.startswith(("UTCHMMA", "LDTM", "UTMALDG", "UBLKCP", "LDGSTS")) for k in cnt) or cnt.get("FFMA", 0) > 50:
         out.append("%-70s %s" % (short, "  ".join("%s=%d" % kv for kv in sorted(cnt.items()))))
 tot = collections.Counter()
