@@ -268,7 +268,9 @@ int innfer_blend_f32(const float* tiles, int H, int W, int patch_size, double st
  * OIHW.  Builds, runs and frees a temporary layer -- a test/bring-up entry point, not a hot path.
  * x [n][Cin][h][w], res1 (or NULL) and y [n][Cout][up*h][up*w] all of `dtype`.
  * use_fp32_kernel: 0 = fp16 kernels on the tiled layout, 1 = fp32 direct kernel, 2 = fp16 kernels on the wide
- * batch layout the engine uses (row-streaming kernel for Cout = 32). */
+ * batch layout the engine uses (row-streaming kernel for Cout = 32).  In mode 2, res1 == x (the same pointer, Cin >= Cout)
+ * means "the residual is the first Cout channels of the conv's own input", the shape conv5 has inside a dense block
+ * (RRDBNet_arch.py:164-165: x5 * 0.2 + x). */
 int innfer_conv3x3(const void* x, int n, int Cin, int hgt, int wid, const float* w_oihw,
                    const float* bias, int Cout, int up, int lrelu, const void* res1, float alpha1,
                    void* y, int dtype, int use_fp32_kernel, void* stream);

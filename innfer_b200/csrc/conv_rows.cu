@@ -101,7 +101,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   // channels per epilogue thread: two warps per lane quarter share COUT; COUT = 16 (the net's last conv, N = 48) is
   // drained by ONE warp per quarter, the other four epilogue warps idle
   constexpr bool WEPI = PAIR || DILV || WE;    // 16 epilogue warps (608 threads)
-  static_assert(!WE || COUT == 32, "the wide epilogue of single CTAs splits 32 channels over four warp groups");
+  static_assert(!WE || COUT == 32 || COUT == 64, "the wide epilogue splits 32 or 64 channels over four warp groups");
   constexpr int CH = WEPI ? COUT / 4 : (COUT == 16 ? 16 : COUT / 2);
   constexpr int NGRP = COUT / CH;              // active epilogue warps per lane quarter
   constexpr int SCOUT_WARP = WEPI ? 2 + 4 * NGRP : 10;
@@ -585,10 +585,34 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
             ++use;
           }
         };
-        if constexpr (PAIR) {
-          // 16 channels per thread, one 16-register TMEM buffer, the finished row completed in accA and stored before
-          // the other two blocks are read (96 registers per thread with 608 threads: a separate copy would spill)
+        if constexpr (PAIR || (WE && COUT == 64)) {
+          // 16 channels per thread through one 16-register TMEM buffer.
           uint32_t v[16];
+          if constexpr (!RES) {
+            // no residual arrays to hold: the finished row goes to `o`, the running sums move up and the slot returns
+            // to the MMA warp BEFORE the row is converted and stored (with two slots per CTA the store used to sit
+            // between two rows' MMAs)
+            float o[16];
+            tmem_ld16(tacc + 2 * COUT, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) o[c] = accA[c] + __uint_as_float(v[c]);
+            ROWS_TRACE(if (tr) p.trace[2304 + ecount] = clock64());
+            tmem_ld16(tacc + COUT, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) accA[c] = accB[c] + __uint_as_float(v[c]);
+            tmem_ld16(tacc, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) accB[c] = __uint_as_float(v[c]);
+            release_slot();
+            ROWS_TRACE(if (tr) p.trace[2560 + ecount] = clock64());
+            if (r - 1 >= pc.ya) store_row(r - 1, o);
+            ROWS_TRACE(if (tr) p.trace[2816 + ecount] = clock64());
+          } else {
+          // residual epilogues: the finished row is completed in accA and stored before the other two blocks are read
+          // (96 registers per thread with 608 threads: a separate copy next to the residuals would spill)
           tmem_ld16(tacc + 2 * COUT, v);
           tmem_ld_wait();
 #pragma unroll
@@ -609,6 +633,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           for (int c = 0; c < 16; ++c) accB[c] = __uint_as_float(v[c]);
           release_slot();
           ROWS_TRACE(if (tr) p.trace[2816 + ecount] = clock64());
+          }
         } else if constexpr (CH == 8) {
           // dilated kernels: 8 channels per thread, all three blocks at once, slot released before the row is stored
           float o[CH];
@@ -787,12 +812,14 @@ int launch_rows_impl(const CUtensorMap* tmap_in, const ConvRowsParams& p, int nu
                  : launch_rows_res<COUT, KSLABS, false, true>(tmap_in, p, num_sms, stream);
     return (int)cudaErrorInvalidValue;
   }
-  if constexpr (COUT == 32) {
+  if constexpr (COUT == 32 || COUT == 64) {
     // 16 epilogue warps of 8 channels for the Cout = 32 convs (conv1..conv4 of a dense block): INNFER_ROWS_WEPI bit 0
-    // for the residual-free ones, bit 1 for those with residual inputs (ESRGAN+, nf = 32 nets)
-    static const int wepi = getenv("INNFER_ROWS_WEPI") ? atoi(getenv("INNFER_ROWS_WEPI")) : 3;
-    if (!res && (wepi & 1)) return launch_rows_res<COUT, KSLABS, false, false, false, true>(tmap_in, p, num_sms, stream);
-    if (res && (wepi & 2)) return launch_rows_res<COUT, KSLABS, true, false, false, true>(tmap_in, p, num_sms, stream);
+    // for the residual-free ones, bit 1 for those with residual inputs (ESRGAN+, nf = 32 nets); bits 2 / 3: the same
+    // for the single-CTA Cout = 64 convs (16 channels per thread: SRResNet's block convs, PPON's c1, HR_conv0)
+    static const int wepi = getenv("INNFER_ROWS_WEPI") ? atoi(getenv("INNFER_ROWS_WEPI")) : 15;
+    constexpr int sh = COUT == 64 ? 2 : 0;
+    if (!res && (wepi & (1 << sh))) return launch_rows_res<COUT, KSLABS, false, false, false, true>(tmap_in, p, num_sms, stream);
+    if (res && (wepi & (2 << sh))) return launch_rows_res<COUT, KSLABS, true, false, false, true>(tmap_in, p, num_sms, stream);
   }
   return res ? launch_rows_res<COUT, KSLABS, true, false>(tmap_in, p, num_sms, stream)
              : launch_rows_res<COUT, KSLABS, false, false>(tmap_in, p, num_sms, stream);

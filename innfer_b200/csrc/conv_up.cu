@@ -211,8 +211,8 @@ conv_up_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
     // ------------------------------------------------------------ epilogue warps
     pdl_wait();
     const int q = warp & 3;
-    const int ph = (warp - 2) >> 2;          // output phase (a, b) = (ph >> 1, ph & 1) of this warp
-    const int pa = ph >> 1, pb = ph & 1;
+    const int pa = ((warp - 2) >> 2) & 1;    // output row parity of this warp: phases (pa, 0) and (pa, 1)
+    const int hc = (warp - 2) >> 3;          // channel half: channels [32 hc, 32 hc + 32)
     const int m = q * 32 + lane;
     const int r = m >> 3, cc = m & 7;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -236,57 +236,58 @@ conv_up_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
       mbar_wait(smem_u32(&tfull_bar[it & 1u]), (it >> 1) & 1u);
       tc_fence_after();
       UP_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < 64) p.trace[2048 + it * 2] = clock64());
-      // Sixteen epilogue warps: four per TMEM lane quarter, one per output phase (a, b); a thread drains the 64
-      // channels of its source pixel's phase in two halves of 32 and stores them to output pixel (2y + a, 2x + b).
+      // Sixteen epilogue warps: four per TMEM lane quarter = output row parity x channel half.  A thread drains 32
+      // channels of BOTH horizontal phases of its source pixel (two rounds of 16 channels x 2 phases) and stores them
+      // to the output pixels (2y + pa, 2x) and (2y + pa, 2x + 1), which are adjacent: one 32-byte store per chunk, so a
+      // warp writes 256 contiguous bytes per output row and every 32-byte sector is written whole (with one 16-byte
+      // store per phase each sector was filled by two warps at different times).
       // (The epilogue is latency / instruction bound: a tile has 9/4 of the outputs per MMA of a plain 3x3 conv; four
       // warps took 7300 cycles per tile, eight 3600, against ~2100-3000 cycles of MMAs.)
-      const uint32_t tacc = tmem_base + lane_base + (uint32_t)(((it & 1u) * kUpPhases + ph) * kUpN);
-      const int oy = 2 * y + pa, ox = 2 * xi + pb;
+      const uint32_t tacc = tmem_base + lane_base + (uint32_t)(((it & 1u) * kUpPhases + 2 * pa) * kUpN + 32 * hc);
+      const int oy = 2 * y + pa, ox = 2 * xi;
       __half* op = p.out + (size_t)img * p.out_bs + (size_t)p.out_chunk0 * p.out_cs + (size_t)oy * p.out_ys + (size_t)ox * 8;
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t v[32];
-        tmem_ld16(tacc + hf * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        tmem_ld16(tacc + hf * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+      for (int rd = 0; rd < 2; ++rd) {
+        uint32_t v0[16], v1[16];
+        tmem_ld16(tacc + rd * 16, v0);
+        tmem_ld16(tacc + kUpN + rd * 16, v1);
         tmem_ld_wait();
-        if (hf == 1) {   // this warp's part of the set is in registers: hand it back
+        if (rd == 1) {   // this warp's part of the set is in registers: hand it back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&set_bar[it & 1u]));
           UP_TRACE(if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < 64) p.trace[2048 + it * 2 + 1] = clock64());
         }
-        if (valid) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int ch = hf * 4 + k;
-            if (ch < nchunks) {
-              // (the bias table sits 8 bytes past a 16-byte boundary: 8-byte reads, the same address for the warp)
-              const float2* bp = reinterpret_cast<const float2*>(s_bias + ch * 8);
-              const float2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
-              float f[8] = {__uint_as_float(v[k * 8 + 0]) + b0.x, __uint_as_float(v[k * 8 + 1]) + b0.y,
-                            __uint_as_float(v[k * 8 + 2]) + b1.x, __uint_as_float(v[k * 8 + 3]) + b1.y,
-                            __uint_as_float(v[k * 8 + 4]) + b2.x, __uint_as_float(v[k * 8 + 5]) + b2.y,
-                            __uint_as_float(v[k * 8 + 6]) + b3.x, __uint_as_float(v[k * 8 + 7]) + b3.y};
+        for (int k = 0; k < 2; ++k) {
+          const int ch = hc * 4 + rd * 2 + k;
+          if (ch >= nchunks) continue;
+          __half* dst = op + (size_t)ch * p.out_cs;
+          if (valid) {
+            // (the bias table sits 8 bytes past a 16-byte boundary: 8-byte reads, the same address for the warp)
+            const float2* bp = reinterpret_cast<const float2*>(s_bias + ch * 8);
+            const float2 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+            const float bb[8] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, b3.x, b3.y};
+            uint32_t w[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float f0 = __uint_as_float(v0[k * 8 + 2 * e]) + bb[2 * e], f1 = __uint_as_float(v0[k * 8 + 2 * e + 1]) + bb[2 * e + 1];
+              float g0 = __uint_as_float(v1[k * 8 + 2 * e]) + bb[2 * e], g1 = __uint_as_float(v1[k * 8 + 2 * e + 1]) + bb[2 * e + 1];
               if (lrelu) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * slope;
+                f0 = f0 > 0.f ? f0 : f0 * slope;
+                f1 = f1 > 0.f ? f1 : f1 * slope;
+                g0 = g0 > 0.f ? g0 : g0 * slope;
+                g1 = g1 > 0.f ? g1 : g1 * slope;
               }
-              uint4 o;
-              const __half2 h0 = __floats2half2_rn(f[0], f[1]);
-              const __half2 h1 = __floats2half2_rn(f[2], f[3]);
-              const __half2 h2 = __floats2half2_rn(f[4], f[5]);
-              const __half2 h3 = __floats2half2_rn(f[6], f[7]);
-              o.x = *reinterpret_cast<const uint32_t*>(&h0);
-              o.y = *reinterpret_cast<const uint32_t*>(&h1);
-              o.z = *reinterpret_cast<const uint32_t*>(&h2);
-              o.w = *reinterpret_cast<const uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(op + (size_t)ch * p.out_cs) = o;
+              const __half2 hf = __floats2half2_rn(f0, f1), hg = __floats2half2_rn(g0, g1);
+              w[e] = *reinterpret_cast<const uint32_t*>(&hf);
+              w[4 + e] = *reinterpret_cast<const uint32_t*>(&hg);
             }
+            st_global_256(dst, w);
+          } else if (inside && p.out_zero_sep) {
+            const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            st_global_256(dst, z);
           }
-        } else if (inside && p.out_zero_sep) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (hf * 4 + k < nchunks) *reinterpret_cast<uint4*>(op + (size_t)(hf * 4 + k) * p.out_cs) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
     }

@@ -1729,7 +1729,12 @@ int innfer_conv3x3(const void* x, int n, int Cin, int hgt, int wid, const float*
     const int pitch = wide_pitch(wid), cols = wide_cols(n, wid);
     cudaMemsetAsync(bi.p, 0, bi.bytes, st);
     rc = launch_nchw_to_wide(x, to_pix(dtype), n, Cin, hgt, wid, reinterpret_cast<__half*>(bi.p), ict, pitch, cols, st);
-    if (res1) {
+    if (res1 == x && Cin >= Cout) {
+      // the residual is the conv's own input (its first Cout channels), like conv5 inside a dense block: the view the
+      // engine passes there, which lets the CTA-pair kernel take it through identity MMAs (conv_rows.cu, IDT)
+      ep.res1 = wview(bi, ict, 0, n, wid, 1);
+      ep.alpha1 = alpha1;
+    } else if (res1) {
       cudaMemsetAsync(br.p, 0, br.bytes, st);
       rc |= launch_nchw_to_wide(res1, to_pix(dtype), n, Cout, hgt, wid, reinterpret_cast<__half*>(br.p), oct, pitch, cols, st);
       ep.res1 = wview(br, oct, 0, n, wid, 1);

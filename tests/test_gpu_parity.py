@@ -35,7 +35,7 @@ def _engine(sd, dev, fp16=True, scale=None):
     return RRDBEngine.from_state_dict(sd, cfg, dev, fp16=fp16)
 
 
-def _conv(native, dev, cin, cout, h, w, n=1, up=1, lrelu=False, res=False, fp32=False, seed=0, wide=False):
+def _conv(native, dev, cin, cout, h, w, n=1, up=1, lrelu=False, res=False, fp32=False, seed=0, wide=False, res_is_input=False):
     lib = native.load()
     g = torch.Generator().manual_seed(seed)
     x = torch.rand(n, cin, h, w, generator=g) * 2 - 1
@@ -45,6 +45,8 @@ def _conv(native, dev, cin, cout, h, w, n=1, up=1, lrelu=False, res=False, fp32=
     dt = torch.float32 if fp32 else torch.float16
     xd = x.to(dev, dt)
     rd = r.to(dev, dt) if res else None
+    if res_is_input:      # conv5 inside a dense block: the residual is the conv's own input (first cout channels)
+        res, rd = True, xd
     y = torch.empty(n, cout, h * up, w * up, device=dev, dtype=dt)
     wc, bc = wgt.contiguous().numpy(), b.contiguous().numpy()
     native.check(lib.innfer_conv3x3(xd.data_ptr(), n, cin, h, w, wc.ctypes.data, bc.ctypes.data, cout, up, int(lrelu),
@@ -59,7 +61,7 @@ def _conv(native, dev, cin, cout, h, w, n=1, up=1, lrelu=False, res=False, fp32=
     if lrelu:
         ref = F.leaky_relu(ref, 0.2)
     if res:
-        ref = ref * 0.2 + rd.double().cpu()
+        ref = ref * 0.2 + rd.double().cpu()[:, :cout]
     return y.double().cpu(), ref
 
 
@@ -88,6 +90,9 @@ def test_conv_block_tcgen05(native, dev, cin, cout, h, w, kw):
     (64, 32, 7, 200, dict(lrelu=True)), (64, 32, 200, 200, dict(n=2, lrelu=True)), (96, 32, 300, 129, dict(lrelu=True, res=True)),
     # conv5 shape: CTA-pair mode of the row kernel (cta_group::2), one and several strip pairs, odd strip count
     (192, 64, 40, 48, dict(res=True, n=2)), (192, 64, 33, 200, dict(res=True, n=3)), (192, 64, 9, 130, dict(n=2)),
+    # ... with the block residual taken from the conv's own input through identity MMAs (0.2 * conv + x)
+    (192, 64, 40, 48, dict(res_is_input=True, n=2)), (192, 64, 33, 200, dict(res_is_input=True, n=3)),
+    (192, 64, 200, 200, dict(res_is_input=True, n=1)),
     # residual-free 64 -> 64 on the row kernel (N = 192), with residual on the 9-tap kernel
     (64, 64, 21, 150, dict(lrelu=True, n=2)), (64, 64, 21, 150, dict(res=True, n=2)),
     # 9-tap kernel on a wide source: separators, upsampling phases (conv_up for x2), N = 16/32/64 (3, 64, 33, 47, dict(n=2)), (64, 3, 50, 70, dict(n=2)),
@@ -498,6 +503,34 @@ def test_determinism_and_batch_invariance(dev):
     eng.set_max_batch(5)
     c = eng.upscale_u8(img, 32, 0.5).copy()
     assert np.array_equal(a, c)          # tile batching must not change a single byte
+    eng.close()
+
+
+@pytest.mark.parametrize("fp16", [True, False])
+def test_uint8_tile_buffer_pad_chunk_survives_other_writers(dev, fp16):
+    """The uint8 path writes only chunk 0 of every input tile and relies on the other chunk of the first conv's K slab
+    holding zeros (filled once per allocation and tile size).  Other writers of the same buffer -- the tensor interface,
+    another tile size, a larger frame that reallocates it -- must not leave stale data there: every call has to equal the
+    same call on a fresh engine, byte for byte."""
+    sd = O.make_state_dict(scale=2, nb=1, seed=4)
+    img_a, img_b = synth_image(31, 70, 90), synth_image(32, 150, 200)
+    x = (torch.rand(2, 3, 40, 56, generator=torch.Generator().manual_seed(5)) + 1.0).to(dev, torch.float16 if fp16 else torch.float32)
+
+    def fresh(img, p):
+        e = _engine(sd, dev, fp16=fp16)
+        out = e.upscale_u8(img, p, 0.5).copy()
+        e.close()
+        return out
+    want_a32, want_a24, want_b = fresh(img_a, 32), fresh(img_a, 24), fresh(img_b, 64)
+    eng = _engine(sd, dev, fp16=fp16)
+    assert np.array_equal(eng.upscale_u8(img_a, 32, 0.5), want_a32)
+    eng.forward(x)                                   # tensor interface: another geometry, non-zero data everywhere
+    assert np.array_equal(eng.upscale_u8(img_a, 32, 0.5), want_a32)
+    assert np.array_equal(eng.upscale_u8(img_a, 24, 0.5), want_a24)     # another tile size in the same allocation
+    eng.chop_forward(x[:1], 32, 0.5)                 # float frames through the tile path (all chunks written)
+    assert np.array_equal(eng.upscale_u8(img_a, 32, 0.5), want_a32)
+    assert np.array_equal(eng.upscale_u8(img_b, 64, 0.5), want_b)       # larger frame: the buffer is reallocated
+    assert np.array_equal(eng.upscale_u8(img_a, 24, 0.5), want_a24)
     eng.close()
 
 

@@ -8,7 +8,7 @@
 mkdir -p gpurun_out
 timeout 900 ncu --cache-control none --clock-control none \
   --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed \
-  -k regex:conv_ -s 60 -c 40 --csv --log-file gpurun_out/r02_conv_metrics.csv \
+  -k regex:conv_ -s 61 -c 45 --csv --log-file gpurun_out/r02_conv_metrics.csv \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-torch-gpu > gpurun_out/r02_conv_metrics.log 2>&1
 tail -2 gpurun_out/r02_conv_metrics.log
 python tools/conv_metrics.py gpurun_out/r02_conv_metrics.csv gpurun_out/r02_conv_metrics.json
