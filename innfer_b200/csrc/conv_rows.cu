@@ -88,7 +88,7 @@ struct PieceIter {
   }
 };
 
-template <int COUT, int KSLABS, bool RES, bool PAIR, bool DILV = false, bool WE = false>
+template <int COUT, int KSLABS, bool RES, bool PAIR, bool DILV = false, bool WE = false, bool NR1 = false>
 __global__ void __launch_bounds__(rows_threads(COUT, PAIR || DILV || WE), 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ ConvRowsParams p) {
   constexpr int N = 3 * COUT;                 // dy-major: column dy*COUT + co
@@ -421,7 +421,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       // wide: image * pitch + xi == xw, so this is xw * 8 for separator columns too
       __half* const obase = p.out + (size_t)b * p.out_bs + (size_t)(p.out_chunk0 + grp * (CH / 8)) * p.out_cs +
                             (size_t)(xw < 0 ? 0 : xi) * p.out_px;
-      const __half* const r1base = (RES && p.res1) ? p.res1 + (size_t)(p.res1_chunk0 + grp * (CH / 8)) * p.res_cs + col : nullptr;
+      // NR1: the launch has no first residual (conv5 of RDB3 with the block residual in the accumulator, IDT) -- known
+      // at compile time so that its registers go to the one-row-ahead prefetch of the second one
+      const __half* const r1base = (RES && !NR1 && p.res1) ? p.res1 + (size_t)(p.res1_chunk0 + grp * (CH / 8)) * p.res_cs + col : nullptr;
       // (the dilated kernels never get a second residual: layers.cu refuses it)
       const __half* const r2base = (RES && !DILV && p.res2) ? p.res2 + (size_t)(p.res2_chunk0 + grp * (CH / 8)) * p.res_cs + col : nullptr;
       const int nchunks = p.out_nchunks - grp * (CH / 8);   // chunks of this thread that exist in the destination
@@ -561,7 +563,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
       };
       // PPON's dilated convs (12 MMAs per row, their epilogue is the critical path): residuals in registers one row
       // ahead.  Elsewhere the 16 extra registers spill (168 per thread at 352 threads), so the L2 prefetch stays.
-      constexpr bool kRegPrefetch = RES && DILV;
+      constexpr bool kRegPrefetch = RES && (DILV || (PAIR && NR1));
       uint4 cur1[CH / 8] = {}, cur2[CH / 8] = {};   // kRegPrefetch: residuals of the row stored in this iteration
       for (int r = pc.r0; r <= pc.r1; ++r) {
         ROWS_TRACE(if (r > pc.r0 || ecount > 0) ++ecount);
@@ -621,7 +623,16 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
           // (measured, round 2e: issuing the residual loads before the accumulator wait does not help -- the epilogue
           // is itself the critical path here, so there is no wait to hide them behind, and the extra live registers
           // spill at 96 per thread: 455 -> 462 us per 63-tile launch)
-          if (r - 1 >= pc.ya) store_row(r - 1, accA);
+          if constexpr (kRegPrefetch) {   // conv5 of RDB3: the RRDB input row was loaded one row stage ago
+            if (r - 1 >= pc.ya) store_row_impl(r - 1, accA, 1, cur1, cur2);
+#pragma unroll
+            for (int ch = 0; ch < CH / 8; ++ch) {
+              cur1[ch] = nxt1[ch];
+              cur2[ch] = nxt2[ch];
+            }
+          } else {
+            if (r - 1 >= pc.ya) store_row(r - 1, accA);
+          }
           ROWS_TRACE(if (tr) p.trace[2560 + ecount] = clock64());
           tmem_ld16(tacc + COUT, v);
           tmem_ld_wait();
@@ -732,11 +743,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
   ROWS_TRACE(if (p.trace && threadIdx.x == 0) p.trace[3072 + blockIdx.x * 8 + 4] = clock64());
 }
 
-template <int COUT, int KSLABS, bool RES, bool PAIR, bool DILV = false, bool WE = false>
+template <int COUT, int KSLABS, bool RES, bool PAIR, bool DILV = false, bool WE = false, bool NR1 = false>
 int launch_rows_res(const CUtensorMap* tmap_in, const ConvRowsParams& p, int num_sms, cudaStream_t stream) {
   const size_t smem_bytes = conv_rows_weight_bytes(p.nch, COUT) / (PAIR ? 2 : 1) + (PAIR ? kRowsIdtBytes : 0) +
                             (size_t)p.stages * conv_rows_stage_bytes(p.kc) + 1024;
-  auto kern = conv_rows_kernel<COUT, KSLABS, RES, PAIR, DILV, WE>;
+  auto kern = conv_rows_kernel<COUT, KSLABS, RES, PAIR, DILV, WE, NR1>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int)e;
   const int dl = DILV ? p.dil : 1;
@@ -807,9 +818,11 @@ int launch_rows_impl(const CUtensorMap* tmap_in, const ConvRowsParams& p, int nu
     return (int)cudaErrorInvalidValue;
   }
   if (p.pair) {
-    if constexpr (COUT == 64 && KSLABS == 6)   // conv5 of the nf = 64 net is the one conv that needs (and gains from) the pair
+    if constexpr (COUT == 64 && KSLABS == 6) {   // conv5 of the nf = 64 net is the one conv that needs (and gains from) the pair
+      if (res && !p.res1) return launch_rows_res<COUT, KSLABS, true, true, false, false, true>(tmap_in, p, num_sms, stream);
       return res ? launch_rows_res<COUT, KSLABS, true, true>(tmap_in, p, num_sms, stream)
                  : launch_rows_res<COUT, KSLABS, false, true>(tmap_in, p, num_sms, stream);
+    }
     return (int)cudaErrorInvalidValue;
   }
   if constexpr (COUT == 32 || COUT == 64) {
