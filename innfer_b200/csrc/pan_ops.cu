@@ -1,5 +1,6 @@
 #include "pan_ops.cuh"
 
+#include <cmath>
 #include <cstdlib>
 
 #include "ptx.cuh"
@@ -419,6 +420,134 @@ __global__ void pan_bicubic_add_kernel(const float* __restrict__ att, int hp, in
   store8(y + (((size_t)b * y_CT + ch) * H * W + pix) * 8, xv);
 }
 
+// Tiled form of pan_bicubic_add_kernel: a block produces a kBcTY x kBcTX output tile of one (image, chunk).  The
+// attention rows / columns its taps touch are staged in shared memory once and the two passes run separably through
+// shared memory -- the per-pixel kernel fetched its 16 taps (32 bytes each) from L2 for every output pixel, 6.4 GB of
+// L2 -> SM traffic per 63-tile batch for a 0.4 GB result (552 us).  Same expressions in the same order (row = fma chain
+// over kx from 0, acc = fma chain over ky), so the output is bit-identical to the per-pixel kernel.
+constexpr int kBcTX = 64, kBcTY = 16;
+struct BcCoef {
+  float c[4];
+  int s[4];   // tap positions relative to the staged tile (clamped to the attention map like the per-pixel kernel)
+};
+template <typename T>
+__global__ void __launch_bounds__(256)
+pan_bicubic_add_tile_kernel(const float* __restrict__ att, int hp, int wp, const T* __restrict__ x, int x_CT,
+                            T* __restrict__ y, int y_CT, int nchunks, int H, int W, float gamma, int rows_cap,
+                            int cols_cap) {
+  extern __shared__ __align__(16) float bc_smem[];
+  __shared__ __align__(16) BcCoef cxs[kBcTX];
+  __shared__ __align__(16) BcCoef cys[kBcTY];
+  __shared__ int s_org[4];
+  float* sT = bc_smem;                                        // [rows_cap][kBcTX][8] after the horizontal pass
+  float* sS = sT + (size_t)rows_cap * kBcTX * 8;              // [rows_cap][cols_cap][8] staged attention pixels
+  const int tid = threadIdx.x;
+  const int ch = blockIdx.z % nchunks, b = blockIdx.z / nchunks;
+  const int ox0 = blockIdx.x * kBcTX, oy0 = blockIdx.y * kBcTY;
+  const int nx = min(kBcTX, W - ox0), ny = min(kBcTY, H - oy0);
+  // align_corners=False: src = scale * (dst + 0.5) - 0.5 with scale = in / out, not clamped for cubic
+  auto src_of = [](int in, int out, int o, int& i, float& t) {
+    const float sf = ((float)in / (float)out) * ((float)o + 0.5f) - 0.5f;
+    const float fl = floorf(sf);
+    i = (int)fl;
+    t = sf - fl;
+  };
+  if (tid == 0) {
+    int i0, i1;
+    float t;
+    src_of(wp, W, ox0, i0, t);
+    src_of(wp, W, ox0 + nx - 1, i1, t);
+    const int xa = min(max(i0 - 1, 0), wp - 1), xb = min(max(i1 + 2, 0), wp - 1);
+    s_org[0] = xa;
+    s_org[2] = xb - xa + 1;
+    src_of(hp, H, oy0, i0, t);
+    src_of(hp, H, oy0 + ny - 1, i1, t);
+    const int ya = min(max(i0 - 1, 0), hp - 1), yb = min(max(i1 + 2, 0), hp - 1);
+    s_org[1] = ya;
+    s_org[3] = yb - ya + 1;
+  }
+  __syncthreads();
+  const int xa = s_org[0], ya = s_org[1], ncol = s_org[2], nrow = s_org[3];
+  if (tid < kBcTX) {
+    if (tid < nx) {
+      int ix;
+      float t;
+      src_of(wp, W, ox0 + tid, ix, t);
+      cubic_coeffs(t, cxs[tid].c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cxs[tid].s[k] = (min(max(ix - 1 + k, 0), wp - 1) - xa) * 8;
+    }
+  } else if (tid < kBcTX + kBcTY) {
+    const int i = tid - kBcTX;
+    if (i < ny) {
+      int iy;
+      float t;
+      src_of(hp, H, oy0 + i, iy, t);
+      cubic_coeffs(t, cys[i].c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cys[i].s[k] = (min(max(iy - 1 + k, 0), hp - 1) - ya) * (kBcTX * 8);
+    }
+  }
+  const float* ab = att + (size_t)b * hp * wp * kPanRow + ch * 8;
+  for (int i = tid; i < nrow * ncol; i += 256) {
+    const int r = i / ncol, c = i - r * ncol;
+    float v[8];
+    load8(ab + ((size_t)(ya + r) * wp + xa + c) * kPanRow, v);
+    float4* d = reinterpret_cast<float4*>(sS + ((size_t)r * cols_cap + c) * 8);
+    d[0] = make_float4(v[0], v[1], v[2], v[3]);
+    d[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  __syncthreads();
+  for (int i = tid; i < nrow * kBcTX; i += 256) {
+    const int r = i / kBcTX, xx = i - r * kBcTX;
+    if (xx >= nx) continue;
+    const float4 kc = *reinterpret_cast<const float4*>(cxs[xx].c);
+    const int4 ks = *reinterpret_cast<const int4*>(cxs[xx].s);
+    const float cx[4] = {kc.x, kc.y, kc.z, kc.w};
+    const int so[4] = {ks.x, ks.y, ks.z, ks.w};
+    const float* srow = sS + (size_t)r * cols_cap * 8;
+    float row[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) row[e] = 0.f;
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      const float4 a = *reinterpret_cast<const float4*>(srow + so[kx]), c2 = *reinterpret_cast<const float4*>(srow + so[kx] + 4);
+      const float v[8] = {a.x, a.y, a.z, a.w, c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) row[e] = fmaf(cx[kx], v[e], row[e]);
+    }
+    float4* d = reinterpret_cast<float4*>(sT + ((size_t)r * kBcTX + xx) * 8);
+    d[0] = make_float4(row[0], row[1], row[2], row[3]);
+    d[1] = make_float4(row[4], row[5], row[6], row[7]);
+  }
+  __syncthreads();
+  for (int i = tid; i < ny * kBcTX; i += 256) {
+    const int yy = i / kBcTX, xx = i - yy * kBcTX;
+    if (xx >= nx) continue;
+    const float4 kc = *reinterpret_cast<const float4*>(cys[yy].c);
+    const int4 ks = *reinterpret_cast<const int4*>(cys[yy].s);
+    const float cy[4] = {kc.x, kc.y, kc.z, kc.w};
+    const int so[4] = {ks.x, ks.y, ks.z, ks.w};
+    const float* t = sT + (size_t)xx * 8;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const float4 a = *reinterpret_cast<const float4*>(t + so[ky]), c2 = *reinterpret_cast<const float4*>(t + so[ky] + 4);
+      const float v[8] = {a.x, a.y, a.z, a.w, c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(cy[ky], v[e], acc[e]);
+    }
+    const size_t pix = (size_t)(oy0 + yy) * W + ox0 + xx;
+    float xv[8];
+    load8(x + (((size_t)b * x_CT + ch) * H * W + pix) * 8, xv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xv[e] = fmaf(gamma, acc[e], xv[e]);
+    store8(y + (((size_t)b * y_CT + ch) * H * W + pix) * 8, xv);
+  }
+}
+
 // one thread per (image, output pixel): the 8 channels of chunk 0
 template <typename T>
 __global__ void pan_bilinear_kernel(const T* __restrict__ x, int x_CT, int h, int w, int s, T* __restrict__ y,
@@ -500,6 +629,16 @@ template <typename T>
 int launch_pan_bicubic_add(const float* att, int hp, int wp, const T* x, int x_CT, T* y, int y_CT, int nchunks,
                            int B, int H, int W, float gamma, cudaStream_t st) {
   const long long total = (long long)B * nchunks * H * W;
+  // staged attention rows / columns of a tile: the span of the first and last pixel's taps
+  const int rows_cap = (int)std::ceil((kBcTY - 1) * (double)hp / H) + 6, cols_cap = (int)std::ceil((kBcTX - 1) * (double)wp / W) + 6;
+  const size_t smem = ((size_t)rows_cap * kBcTX + (size_t)rows_cap * cols_cap) * 8 * sizeof(float);
+  static const int tiled = getenv("INNFER_PAN_BICUBIC_TILED") ? atoi(getenv("INNFER_PAN_BICUBIC_TILED")) : 1;   // A/B switch
+  if (tiled && hp <= H && wp <= W && smem <= 48 * 1024 && (long long)B * nchunks <= 65535) {
+    dim3 grid((unsigned)((W + kBcTX - 1) / kBcTX), (unsigned)((H + kBcTY - 1) / kBcTY), (unsigned)(B * nchunks));
+    pan_bicubic_add_tile_kernel<T><<<grid, 256, smem, st>>>(att, hp, wp, x, x_CT, y, y_CT, nchunks, H, W, gamma, rows_cap,
+                                                            cols_cap);
+    return (int)cudaGetLastError();
+  }
   pan_bicubic_add_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>(att, hp, wp, x, x_CT, y, y_CT, nchunks, H, W, gamma,
                                                                     total);
   return (int)cudaGetLastError();
