@@ -2,7 +2,7 @@
 # round 2e final single-GPU run: whole GPU suite, smoke, family frame times (A/B of the Cout = 64 wide epilogue), launch
 # list of the RRDB frame, the bench workloads and the reference arm
 mkdir -p gpurun_out
-T=r02f
+T=${TAG:-r02f}
 timeout 900 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -4 > gpurun_out/${T}_pytest.log; tail -3 gpurun_out/${T}_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 for v in 3 15; do echo "== INNFER_ROWS_WEPI=$v"; for st in srres_time ppon_time; do INNFER_ROWS_WEPI=$v timeout 300 python tests/gpu_bringup.py --stage $st 2>&1 | grep "iter=2"; done; done
