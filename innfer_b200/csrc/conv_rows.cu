@@ -44,13 +44,14 @@ namespace innfer {
 namespace {
 
 // warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue (two per TMEM lane quarter, each half of the
-// output channels), 10 = scout.  352 threads leave the epilogue threads 184 registers (COUT = 64 keeps
-// 3 x 32 running sums per thread).
-// The CTA-pair kernel (conv5) runs 16 epilogue warps of 16 channels each (608 threads, 96 registers): its residual
-// epilogue is latency-bound and gains from more warps in flight.
-// PPON's dilated convs (WEPI, "wide epilogue") also run 16 epilogue warps, of 8 channels each: with 12 MMAs per row
-// their residual epilogue is the critical path and two warps per scheduler cannot hide its latencies (ncu: 1.4
-// instructions per cycle and SM, 2 250 cycles per row for 660 cycles of MMAs).
+// output channels), 10 = scout.  352 threads leave the epilogue threads 168 registers (COUT = 64 keeps
+// 3 x 32 running sums per thread).  Since round 2e only the Cout = 16 kernel and the INNFER_ROWS_WEPI=0 fallbacks
+// run this narrow form.
+// The wide epilogue (WEPI: the CTA-pair kernel, the dilated kernels and the WE instantiations of the plain ones) runs 16
+// epilogue warps -- four per TMEM lane quarter, 8 (Cout = 32) or 16 (Cout = 64) channels per thread, 608 threads,
+// 96 registers: with 12..36 MMAs per row the epilogue is a chain of latencies (accumulator wait, TMEM read, residual
+// load, convert, store) and two warps per scheduler could not hide it (ncu on PPON's dilated convs: 1.4 instructions
+// per cycle and SM, 2 250 cycles per row for 660 cycles of MMAs; profiles/r02e_epilogue_warps.md).
 __host__ __device__ constexpr int rows_threads(int /*cout*/, bool wide_epi) { return wide_epi ? 608 : 352; }
 constexpr int kRowPx = 144;        // pixels per staged row segment: 9 groups of 16 (strip of 128 + halo)
 
@@ -561,8 +562,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_const
         const uint4 none[CH / 8] = {};
         store_row_impl(y, o, 0, none, none);
       };
-      // PPON's dilated convs (12 MMAs per row, their epilogue is the critical path): residuals in registers one row
-      // ahead.  Elsewhere the 16 extra registers spill (168 per thread at 352 threads), so the L2 prefetch stays.
+      // PPON's dilated convs (12 MMAs per row, their epilogue is the critical path) and conv5 of RDB3 on the CTA pair
+      // (one residual left, known at compile time): residuals in registers one row ahead.  Elsewhere the extra
+      // registers spill, so the L2 prefetch stays.
       constexpr bool kRegPrefetch = RES && (DILV || (PAIR && NR1));
       uint4 cur1[CH / 8] = {}, cur2[CH / 8] = {};   // kRegPrefetch: residuals of the row stored in this iteration
       for (int r = pc.r0; r <= pc.r1; ++r) {

@@ -73,7 +73,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constan
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tfull_bar = empty_bar + S;
-  uint64_t* set_bar = tfull_bar + 2;       // "accumulator set is drained" (8 epilogue warps arrive)
+  uint64_t* set_bar = tfull_bar + 2;       // "accumulator set is drained" (16 epilogue warps arrive)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(set_bar + 2);
   volatile uint32_t* ready_cnt = tmem_slot + 1;   // stages whose barriers the scout warp has seen complete
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);

@@ -20,9 +20,10 @@
 // one.  The epilogue (bias, LeakyReLU, up to two scaled residual adds, fp16 pack) reads them with
 // tcgen05.ld and stores 16-byte channel chunks straight into the destination chunk slice.
 //
-// Warp roles (352 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4; two groups of four warps that take the 128-pixel
-// sub-tiles of a tile alternately), warp 10 = scout: it waits on the stage and
+// Warp roles (608 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..17 = epilogue (TMEM lane quarter = warp_id % 4; four warps per quarter = sub-tile parity x chunk parity:
+// the 128-pixel sub-tiles of a tile alternate between two groups, each of which splits the accumulator's 8-channel
+// chunks between two warps), warp 18 = scout: it waits on the stage and
 // accumulator-set barriers for the issuer and publishes the number of ready stages in shared memory
 // (an mbarrier wait on the issuing thread costs 170-260 cycles even when already satisfied).
 #pragma once
